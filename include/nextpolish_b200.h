@@ -1,0 +1,218 @@
+/*
+ * nextpolish_b200.h — C ABI of the B200-native polishing engine.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) The reference ABI: exactly the symbols lib/nextpolish1.py binds through ctypes
+ *      (reference source/lib/nextpolish1.py:84-100) and source/lib/main.c calls, with
+ *      byte-identical struct layouts.  The shared object is built as
+ *      nextpolish_b200/lib/nextpolish1.so so that it can be dropped next to an unmodified
+ *      nextpolish1.py.
+ *
+ *  (2) The batch ABI (np_*): plain pointers and sizes over "packed shards" (many contigs and
+ *      their coordinate-sorted read blocks) for callers that already hold decoded reads.
+ *      bench.py, the tests and the native CLI use it; score_chain()/kmer_count() are thin
+ *      per-contig wrappers over the same kernels.
+ *
+ * There is no CPU implementation behind these symbols: every compute entry point launches the
+ * sm_100a kernels and returns an error (or exits like the reference does) when no CUDA
+ * device is usable.
+ */
+#ifndef NEXTPOLISH_B200_H
+#define NEXTPOLISH_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Reference ABI
+ * ---------------------------------------------------------------------------------------- */
+
+/* reference source/lib/config.h:25-67 (mirrored by nextpolish1.py:27-65); sizeof == 152 */
+typedef struct {
+    uint8_t  trim_len_edge;
+    uint8_t  ext_len_edge;
+    uint8_t  min_map_quality;
+    double   indel_balance_factor_sgs;
+    double   min_count_ratio_skip;
+
+    uint8_t  min_len_ldr;
+    uint8_t  min_len_inter_kmer;
+    uint8_t  max_len_kmer;
+    uint8_t  max_count_kmer;
+
+    uint8_t  min_depth_snp;
+    uint8_t  min_count_snp;
+    int8_t   min_count_snp_link;
+    double   ploidy;
+    double   indel_balance_factor_lgs;
+    double   max_indel_factor_lgs;
+    double   max_snp_factor_lgs;
+    double   min_snp_factor_sgs;
+
+    int32_t  region_count;
+    uint32_t count_read_ins_sgs;
+    uint32_t max_ins_len_sgs;
+    int32_t  max_ins_fold_sgs;
+    int32_t  max_variant_count_lgs;
+
+    double   max_clip_ratio_sgs;
+    double   max_clip_ratio_lgs;
+
+    int32_t  trace_polish_open;
+    int32_t  read_tlen;
+    int32_t  read_len;
+
+    char*    fastafn;
+    char*    bamfn;
+    char*    thirdbamfn;
+} Configure;
+
+/* reference source/lib/contig.h:10-22 (nextpolish1.py:67-81) */
+typedef struct {
+    int32_t pos;
+    int16_t index;
+    char    curbase;
+    char    base;
+} PolishPoint;
+
+typedef struct {
+    char*        contig;     /* NUL-terminated polished sequence, malloc()ed */
+    PolishPoint* data;       /* change trace when trace_polish_open, else NULL */
+    int32_t      length;     /* strlen(contig) */
+    int32_t      datalength;
+} PolishResult;
+
+/* replaces config.c:8-56 (config_init), config.c:58-68 (config_destory) */
+Configure* config_init(const char* fastafn, const char* bamfn, const char* thirdbamfn);
+void       config_destory(Configure* config);
+
+/* replaces scorechain.c:3-15 — task 1, whole-contig pileup + k-mer score chain */
+PolishResult* score_chain(const char* tigname, Configure* configure);
+/* replaces kmercount.c:93-126 — task 2, low-depth re-score + spanning-read k-mer vote */
+PolishResult* kmer_count(const char* tigname, Configure* configure);
+/* bound by nextpolish1.py:95-100 but outside this engine's scope:
+ * they print a diagnostic and exit(1), the reference's own fatal-error convention. */
+PolishResult* snp_phase(const char* tigname, Configure* configure);
+PolishResult* snp_valid(const char* tigname, Configure* configure);
+PolishResult* lgspolish(const char* tigname, Configure* configure);
+
+/* replaces contig.c:20-30 */
+PolishResult* polishresult_init(void);
+void          polishresult_destory(PolishResult* polishresult);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Batch ABI over packed shards
+ * ---------------------------------------------------------------------------------------- */
+
+#define NP_OK            0
+#define NP_ERR_CUDA     -1   /* no device / CUDA runtime failure (message via np_last_error) */
+#define NP_ERR_ARG      -2
+#define NP_ERR_IO       -3
+#define NP_ERR_LIMIT    -4   /* shard exceeds a documented limit (columns, depth >= 65535) */
+#define NP_ERR_RATE     -5   /* reserved */
+
+#define NP_TASK_SCORE_CHAIN 1
+#define NP_TASK_KMER_COUNT  2
+
+/*
+ * One packed read block ("record"), 16-byte aligned, little endian:
+ *   int32  pos        0-based leftmost reference position   (bam1_core_t.pos)
+ *   uint16 flag       BAM FLAG
+ *   uint8  mapq       BAM MAPQ
+ *   uint8  reserved   0
+ *   int32  isize      BAM TLEN
+ *   uint16 l_qseq     read length
+ *   uint16 n_cigar    number of CIGAR ops (>= 1)
+ *   uint32 cigar[n_cigar]          BAM encoding, len<<4 | op
+ *   uint8  seq[(l_qseq+1)/2]       BAM 4-bit nt16 codes, high nibble first
+ *   zero padding to a multiple of 16 bytes
+ * Qualities (needed by task 2 only) live in a second stream: l_qseq bytes per read, each
+ * read padded to 16 bytes.
+ * Records are in BAM file order (coordinate sorted) and grouped by contig.
+ */
+typedef struct {
+    int32_t         n_contigs;
+    int64_t         n_reads;
+    const int64_t*  ctg_off;       /* [n_contigs+1] offsets of each contig in ctg_seq           */
+    const uint8_t*  ctg_seq;       /* draft bases as in the FASTA (case preserved), concatenated */
+    const int64_t*  ctg_read_off;  /* [n_contigs+1] read index range of each contig              */
+    const uint32_t* rec_off;       /* [n_reads+1] record offsets in 16-byte units                */
+    const uint8_t*  rec;           /* packed records                                              */
+    const uint32_t* qual_off;      /* [n_reads+1] quality offsets in 16-byte units, or NULL      */
+    const uint8_t*  qual;          /* qualities, or NULL                                          */
+} np_shard_view;
+
+/* ---- host side: FASTA/BAM -> packed shard (own BGZF/BAM/BAI/FASTA reader; zlib only) ---- */
+typedef struct np_shard np_shard;
+/* names == NULL or n_names == 0: every contig of the FASTA, in FASTA order. */
+np_shard* np_shard_load(const char* fasta, const char* bam, const char* const* names,
+                        int32_t n_names, int32_t with_qual, int32_t threads);
+void      np_shard_view_of(const np_shard* shard, np_shard_view* out);
+const char* np_shard_contig_name(const np_shard* shard, int32_t i);
+void      np_shard_free(np_shard* shard);
+
+/* ---- device engine ---------------------------------------------------------------------- */
+typedef struct np_engine np_engine;
+
+np_engine*  np_engine_create(int32_t device);   /* NULL + np_last_error() when CUDA is unusable */
+void        np_engine_destroy(np_engine* e);
+const char* np_last_error(void);
+
+/* Copy a shard (host pointers, pageable or pinned) to HBM; replaces any resident shard. */
+int32_t np_engine_upload(np_engine* e, const np_shard_view* host_shard);
+/* Adopt a shard whose arrays already live in device memory (pointers are device pointers;
+ * they must stay valid until the next upload/adopt). ctg_off / ctg_read_off are host arrays. */
+int32_t np_engine_adopt_device(np_engine* e, const np_shard_view* dev_shard);
+
+/* Run one task step on the resident shard (kernels only; asynchronous on the engine stream
+ * until np_engine_sync / np_engine_download). */
+int32_t np_engine_run(np_engine* e, int32_t task, const Configure* cfg);
+int32_t np_engine_sync(np_engine* e);
+/* Total polished length of the last run (sum over contigs), valid after sync. */
+int64_t np_engine_result_bytes(np_engine* e);
+/* Copy the polished sequences to host: out_seq receives the concatenation (no separators),
+ * out_off[n_contigs+1] the per-contig offsets. */
+int32_t np_engine_download(np_engine* e, uint8_t* out_seq, int64_t out_cap, int64_t* out_off);
+/* Device pointer of the concatenated result (for an on-device gather) and its offsets. */
+const uint8_t* np_engine_result_device(np_engine* e);
+
+/* Per-kernel device time (ms) of the last run, measured with CUDA events on the engine
+ * stream; names[i] points to static strings. Returns the number of entries written. */
+int32_t np_engine_kernel_times(np_engine* e, const char** names, float* ms, int32_t cap);
+/* Number of kernel launches issued by the last np_engine_run. */
+int32_t np_engine_launch_count(np_engine* e);
+/* The stream the engine launches on (cudaStream_t as void*). */
+void*   np_engine_stream(np_engine* e);
+
+/* End-to-end convenience: upload + run + download in one call (host buffers in and out). */
+int32_t np_polish_host(np_engine* e, int32_t task, const np_shard_view* host_shard,
+                       const Configure* cfg, uint8_t* out_seq, int64_t out_cap, int64_t* out_off);
+
+/* Algorithmic bytes of the resident shard for `task`:
+ * sum over reads of (16 + 4*n_cigar + ceil(l_qseq/2)) [+ l_qseq for task 2] + 2 * sum(L). */
+int64_t np_engine_algorithmic_bytes(np_engine* e, int32_t task);
+
+/* ---- seeded synthetic inputs (draft FASTA + coordinate-sorted BAM), for bench and tests -- */
+typedef struct {
+    uint64_t seed;
+    int32_t  n_contigs;
+    int64_t  contig_len;        /* every contig has this length (min_len==0) ...            */
+    int64_t  min_len, max_len;  /* ... or log-uniform lengths in [min_len, max_len]          */
+    double   depth;             /* e.g. 30                                                    */
+    int32_t  read_len;          /* e.g. 150                                                   */
+    double   draft_snv, draft_indel;   /* draft error rates vs truth (0.001 / 0.003)         */
+    double   read_sub, read_indel;     /* sequencing error rates (0.002 / 0.0001)            */
+    double   lowercase_frac;    /* fraction of draft bases written lowercase (task-2 inputs) */
+    int32_t  compress_level;    /* BGZF zlib level (0 = stored blocks)                       */
+} np_synth_params;
+int32_t np_synth_write(const np_synth_params* p, const char* fasta_path, const char* bam_path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEXTPOLISH_B200_H */

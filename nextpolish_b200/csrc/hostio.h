@@ -1,0 +1,94 @@
+// hostio.h — host-side FASTA / BGZF / BAM / BAI readers and the packed-shard builder.
+//
+// This is the engine's own I/O layer (zlib is the only dependency); it stands where the
+// reference links its vendored htslib 1.9 (fai_load/fai_fetch: contig.c:35-36,1119-1128;
+// bam_itr_queryi + sam_itr_next: contig.c:172-174,692-694; bam_read1: config.c:87).
+// Only the iteration ORDER of htslib matters to the algorithm (first-seen tie-breaks):
+// records of one contig are delivered in file order, which is what this reader does.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <functional>
+#include "../../include/nextpolish_b200.h"
+
+namespace np {
+
+struct FastaRecord {
+    std::string name;
+    std::string seq;   // whitespace removed, case preserved
+};
+
+// Reads all (names == empty) or the named sequences. Uses <fasta>.fai when present to seek.
+bool fasta_load(const std::string& path, const std::vector<std::string>& names,
+                std::vector<FastaRecord>& out, std::string& err);
+// Names in file order (from .fai when present, else by scanning).
+bool fasta_names(const std::string& path, std::vector<std::string>& names,
+                 std::vector<int64_t>& lengths, std::string& err);
+
+struct BamHeader {
+    std::vector<std::string> names;
+    std::vector<int64_t>     lengths;
+    uint64_t                 first_record_voffset = 0;
+};
+
+// A decoded BAM alignment record (pointers into a transient buffer).
+struct BamRec {
+    int32_t  tid, pos;
+    uint8_t  mapq;
+    uint16_t flag;
+    uint32_t n_cigar;
+    int32_t  l_qseq, isize;
+    const uint32_t* cigar;   // may be unaligned: use memcpy
+    const uint8_t*  seq;
+    const uint8_t*  qual;
+};
+
+class BamFile {
+public:
+    ~BamFile();
+    bool open(const std::string& path, std::string& err);
+    const BamHeader& header() const { return hdr_; }
+    // Visit records in file order starting at virtual offset `voff` (0 = first record) with
+    // `threads` inflate threads. The visitor returns false to stop.
+    bool scan(uint64_t voff, int threads, const std::function<bool(const BamRec&)>& visit,
+              std::string& err);
+    // Smallest chunk-begin virtual offset of `tid` from <bam>.bai; returns false if the index
+    // is missing/unreadable; *has_reads=false if the contig has no chunks.
+    bool bai_first_offset(int tid, uint64_t* voff, bool* has_reads, std::string& err) const;
+private:
+    bool inflate_batch(size_t first_block, size_t n_blocks, int threads,
+                       std::vector<uint8_t>& out, std::vector<size_t>& block_uoff, std::string& err);
+    bool index_blocks(std::string& err);
+    std::string path_;
+    int fd_ = -1;
+    const uint8_t* data_ = nullptr;
+    size_t size_ = 0;
+    std::vector<uint64_t> block_coff_;   // compressed offset of every BGZF block
+    BamHeader hdr_;
+    bool read_header(std::string& err);
+};
+
+// Host-owned packed shard (see np_shard_view in nextpolish_b200.h for the layout).
+struct Shard {
+    std::vector<std::string> names;
+    std::vector<int64_t>  ctg_off;
+    std::vector<uint8_t>  ctg_seq;
+    std::vector<int64_t>  ctg_read_off;
+    std::vector<uint32_t> rec_off;
+    std::vector<uint8_t>  rec;
+    std::vector<uint32_t> qual_off;
+    std::vector<uint8_t>  qual;
+    bool with_qual = false;
+    void view(np_shard_view* v) const;
+};
+
+bool shard_load(const std::string& fasta, const std::string& bam,
+                const std::vector<std::string>& names, bool with_qual, int threads,
+                Shard& out, std::string& err);
+
+// config.c:80-101 (bam_tlen): mean insert size estimate over the head of the BAM.
+bool bam_insert_estimate(const std::string& bam, uint32_t count_read_ins, uint32_t max_ins_len,
+                         uint32_t* mean, int32_t* read_len, std::string& err);
+
+}  // namespace np
