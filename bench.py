@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — Mbp polished/s of the polishing hot path on N B200s (one process per GPU).
+
+Workload (BASELINE.json configs[1]): synthetic 5 Mb draft (5 contigs x 1 Mb) + 30x 150 bp PE short
+reads per GPU; a "step" = one pass of every implemented task step (score_chain [, kmer_count]) over
+one such shard.  Weak scaling: every rank polishes its own shard of that shape (contigs are
+independent units); after each step the polished FASTA bytes are gathered to rank 0
+with one NCCL collective.
+
+value      device-resident: packed shard already in HBM when the timed region starts
+e2e        through np_polish_host (C ABI) with pinned HOST buffers: H2D of the packed shard, kernels,
+           D2H of the polished sequences, every step
+roofline   the pileup-scan kernel: algorithmic bytes / its CUDA-event time on the engine
+           stream, against the measured HBM peak of MEASURED_PEAKS.json
+cpu_baseline / --impl reference: the reference's own CPU implementation (oracle/_ref/nextpolish1
+           compiled from the reference sources; one process per contig like nextpolish1.py's Pool),
+           else the oracle port, timed on this box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.realpath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(n_contigs=5, contig_len=1000000, depth=30.0, read_len=150)
+SEED0 = 20240917 + 2
+N_ROTATE = 3          # distinct resident shards rotated between steps (defeats L2 reuse across steps)
+
+
+def rank_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clock + throttle reasons of one GPU during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU implementation on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, tasks, tmpdir):
+    """Returns (Mbp/s, ms_per_step, kind, cores, sample). One process per contig, like the
+    multiprocessing.Pool of the reference's nextpolish1.py (nextpolish1.py:223-224)."""
+    from nextpolish_b200 import engine as E
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "nextpolish1")
+    samtools = os.path.join(ROOT, "oracle", "_ref", "samtools")
+    p = E.synth_params(seed=SEED0, lowercase_frac=0.0, **WORKLOAD)
+    ncpu = os.cpu_count() or 1
+    nproc = min(ncpu, WORKLOAD["n_contigs"])
+    total_bp = WORKLOAD["n_contigs"] * WORKLOAD["contig_len"]
+    cmds = {1: "scorechain", 2: "kmercount"}
+    if os.path.exists(ref_bin) and os.path.exists(samtools):
+        kind = "reference"
+        fa, bam = os.path.join(tmpdir, "c2.fa"), os.path.join(tmpdir, "c2.bam")
+        assert E.lib().np_synth_write(p, fa.encode(), bam.encode()) == 0
+        subprocess.check_call([samtools, "index", bam])
+        # one FASTA per contig: `nextpolish1 <cmd> <fa> <bam>` polishes every contig of its FASTA
+        from tests.conftest import read_fasta
+        seqs = read_fasta(fa)
+        parts = []
+        for n, s in seqs.items():
+            f = os.path.join(tmpdir, n + ".fa")
+            open(f, "wb").write(b">" + n.encode() + b"\n" + s + b"\n")
+            parts.append(f)
+
+        def one_step():
+            for t in tasks:
+                procs = [subprocess.Popen([ref_bin, cmds[t], f, bam], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for f in parts]
+                for pr in procs:
+                    assert pr.wait() == 0
+    else:
+        kind = "port"
+        import multiprocessing as mp
+        sh = E.Shard.synthetic(p, 0, WORKLOAD["n_contigs"], with_qual=True)
+        cfg = E.default_config(b"")
+        global _PORT_STATE
+        _PORT_STATE = (sh, cfg)
+        pool = mp.get_context("fork").Pool(nproc)
+
+        def one_step():
+            for t in tasks:
+                pool.map(_port_contig, [(c, t) for c in range(sh.n_contigs)])
+    for _ in range(warmup):
+        one_step()
+    t0 = time.time()
+    for _ in range(steps):
+        one_step()
+    dt = time.time() - t0
+    mbp = total_bp * len(tasks) * steps / 1e6
+    sample = "%d contigs x %d bp, %gx, tasks %s, %d steps" % (WORKLOAD["n_contigs"], WORKLOAD["contig_len"], WORKLOAD["depth"], list(tasks), steps)
+    return mbp / dt, dt / steps * 1e3, kind, nproc, sample
+
+
+_PORT_STATE = None
+
+
+def _port_contig(args):
+    import numpy as np
+    c, task = args
+    sh, cfg = _PORT_STATE
+    O = C.CDLL(os.path.join(ROOT, "oracle", "libnp_oracle.so"))
+    O.np_oracle_run_contig.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    cap = int(sh.view.ctg_off[c + 1] - sh.view.ctg_off[c]) * 2 + 4096
+    out = np.zeros(cap, np.uint8)
+    n = C.c_int64(0)
+    assert O.np_oracle_run_contig(C.addressof(sh.view), c, task, C.cast(cfg, C.c_void_p), out.ctypes.data, cap, C.byref(n)) == 0
+    return int(n.value)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = rank_env()
+    from nextpolish_b200 import engine as E
+    tasks = list(E.TASKS)
+    base = {"metric": "Mbp polished/s", "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+            "config": {"workload": "synthetic 5 Mb draft (5 x 1 Mb) + 30x 150 bp PE short reads per GPU; step = tasks %s" % tasks,
+                       "tasks": tasks, "per_gpu_bp": WORKLOAD["n_contigs"] * WORKLOAD["contig_len"], "parallelism": "contig-sharded x%d" % args.gpus}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        with tempfile.TemporaryDirectory(prefix="npbench") as tmp:
+            v, ms, kind, cores, sample = cpu_reference_run(max(1, args.steps), max(0, min(args.warmup, 1)), tasks, tmp)
+        base.update({"impl": "reference", "value": v, "ms_per_step": ms, "dtype": "int/f64 (CPU)",
+                     "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": sample},
+                     "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0})
+        base["config"]["host_cpus"] = os.cpu_count()
+        print(json.dumps(base))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs: N_ROTATE distinct shards of the workload shape, pinned on host and resident in HBM
+    with_qual = 2 in tasks
+    shards, pinned, resident, views_dev, views_host = [], [], [], [], []
+    for k in range(N_ROTATE):
+        p = E.synth_params(seed=SEED0 + 1000 * rank + k, lowercase_frac=0.02 if with_qual else 0.0, **WORKLOAD)
+        sh = E.Shard.synthetic(p, 0, WORKLOAD["n_contigs"], with_qual=with_qual, threads=max(1, (os.cpu_count() or 8) // max(1, args.gpus)))
+        a = sh.arrays()
+        pin = {k2: torch.from_numpy(v.copy()).pin_memory() for k2, v in a.items() if k2 in ("ctg_seq", "rec_off", "rec", "qual_off", "qual")}
+        res = {k2: t.to(dev) for k2, t in pin.items()}
+
+        def mkview(src, sh=sh):
+            v = E.ShardView()
+            v.n_contigs, v.n_reads = sh.view.n_contigs, sh.view.n_reads
+            v.ctg_off, v.ctg_read_off = sh.view.ctg_off, sh.view.ctg_read_off
+            v.ctg_seq, v.rec_off, v.rec = src["ctg_seq"].data_ptr(), src["rec_off"].data_ptr(), src["rec"].data_ptr()
+            if with_qual:
+                v.qual_off, v.qual = src["qual_off"].data_ptr(), src["qual"].data_ptr()
+            return v
+        shards.append(sh); pinned.append(pin); resident.append(res)
+        views_dev.append(mkview(res)); views_host.append(mkview(pin))
+    cfg = E.default_config(b"")
+    eng = E.Engine(local_rank)
+    bp_step = sum(int(shards[0].total_bases) for _ in tasks)      # bases polished per step on this rank
+    alg_bytes = {t: shards[0].algorithmic_bytes(t) for t in tasks}
+    h2d = sum(t.numel() * t.element_size() for t in pinned[0].values())
+    cap = int(shards[0].total_bases * 1.25) + 4096
+    out_pin = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    off_pin = torch.empty(shards[0].n_contigs + 1, dtype=torch.int64).pin_memory()
+    out_np, off_np = out_pin.numpy(), off_pin.numpy()
+    estream = torch.cuda.ExternalStream(eng.stream(), device=dev)
+    gather_buf = torch.empty(cap, dtype=torch.uint8, device=dev)
+
+    def gather_fasta():
+        """The single collective of the path: corrected FASTA bytes of every rank -> rank 0."""
+        n = eng.result_bytes()
+        E.lib().np_engine_copy_result(eng.h, gather_buf.data_ptr(), cap)
+        eng.sync()
+        if world > 1:
+            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([n], dtype=torch.int64, device=dev))
+            bufs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+            dist.gather(gather_buf, bufs, dst=0)
+
+    def step_resident(i):
+        eng.adopt_device(views_dev[i % N_ROTATE])
+        for t in tasks:
+            eng.run(t, cfg)
+        gather_fasta()
+
+    def step_e2e(i):
+        for t in tasks:
+            eng.polish_host(t, views_host[i % N_ROTATE], cfg, out_np, off_np)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(estream):
+            e0.record()
+        for i in range(steps):
+            fn(i)
+        estream.wait_stream(torch.cuda.current_stream(dev))   # orders the NCCL gather before e1
+        with torch.cuda.stream(estream):
+            e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_res = timed(step_resident, args.steps, args.warmup)
+    launches = eng.launch_count() * len(tasks) * args.steps
+    # per-kernel times of the last resident step (CUDA events on the engine stream)
+    ktimes = {}
+    eng.adopt_device(views_dev[0])
+    kt_by_task = {}
+    for t in tasks:
+        eng.run(t, cfg)
+        eng.sync()
+        kt = eng.kernel_times()
+        kt_by_task[t] = kt
+        for n, v in kt:
+            ktimes[n] = ktimes.get(n, 0.0) + v
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    d2h = int(eng.result_bytes()) + 8 * (shards[0].n_contigs + 1)
+    total_bp = bp_step * world
+    value = total_bp * args.steps / (ms_res / 1e3) / 1e6
+    e2e = total_bp * args.steps / (ms_e2e / 1e3) / 1e6
+    peak, peak_kind = measured_peak_gbs()
+    roof_kernel = "pileup_scan"
+    kms = dict(kt_by_task[1]).get(roof_kernel) if 1 in kt_by_task else None
+    ach = alg_bytes[1] / (kms / 1e3) / 1e9 if kms else None
+    base.update({
+        "value": value, "ms_per_step": ms_res / args.steps, "dtype": "u8/u16/int32 (+f64 score chain)",
+        "e2e": {"value": e2e, "unit": "Mbp/s", "h2d_bytes_per_step": h2d * len(tasks), "d2h_bytes_per_step": d2h * len(tasks),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": (ach / peak) if ach else None, "traffic": None, "peak_kind": peak_kind,
+                     "algorithmic_bytes": alg_bytes[1], "kernel_ms": kms},
+        "kernels_ms": {k: round(v, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1])},
+        "clocks": sampler.summary() if sampler else None,
+    })
+    base["config"].update({"l2": "inputs rotate over %d distinct resident shards (%.0f MB each) and every step rewrites "
+                                 ">300 MB of scratch: working set exceeds the 126 MB L2" % (N_ROTATE, h2d / 1e6),
+                           "reads_per_gpu": int(shards[0].n_reads), "algorithmic_bytes_per_bp": alg_bytes[1] / shards[0].total_bases})
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        with tempfile.TemporaryDirectory(prefix="npbench") as tmp:
+            v, ms, kind, cores, sample = cpu_reference_run(2, 1, tasks, tmp)
+        base["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": sample,
+                                "host_cpus": os.cpu_count()}
+    print(json.dumps(base))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

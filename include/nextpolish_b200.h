@@ -155,6 +155,11 @@ np_shard* np_shard_load(const char* fasta, const char* bam, const char* const* n
 void      np_shard_view_of(const np_shard* shard, np_shard_view* out);
 const char* np_shard_contig_name(const np_shard* shard, int32_t i);
 void      np_shard_free(np_shard* shard);
+/* position of shard contig i in the requested (or FASTA) order; shards are in BAM tid order */
+int32_t   np_shard_contig_rank(const np_shard* shard, int32_t i);
+/* Algorithmic bytes of one task step over this shard:
+ * sum over reads of (16 + 4*n_cigar + ceil(l_qseq/2)) [+ l_qseq for task 2] + 2 * sum(L). */
+int64_t   np_shard_algorithmic_bytes(const np_shard* shard, int32_t task);
 
 /* ---- device engine ---------------------------------------------------------------------- */
 typedef struct np_engine np_engine;
@@ -178,6 +183,9 @@ int64_t np_engine_result_bytes(np_engine* e);
 /* Copy the polished sequences to host: out_seq receives the concatenation (no separators),
  * out_off[n_contigs+1] the per-contig offsets. */
 int32_t np_engine_download(np_engine* e, uint8_t* out_seq, int64_t out_cap, int64_t* out_off);
+/* Copy the concatenated result into another DEVICE buffer (asynchronous on the engine stream);
+ * used for the on-device gather of the corrected FASTA across GPUs. */
+int32_t np_engine_copy_result(np_engine* e, void* dst_device, int64_t dst_cap);
 /* Device pointer of the concatenated result (for an on-device gather) and its offsets. */
 const uint8_t* np_engine_result_device(np_engine* e);
 
@@ -193,9 +201,6 @@ void*   np_engine_stream(np_engine* e);
 int32_t np_polish_host(np_engine* e, int32_t task, const np_shard_view* host_shard,
                        const Configure* cfg, uint8_t* out_seq, int64_t out_cap, int64_t* out_off);
 
-/* Algorithmic bytes of the resident shard for `task`:
- * sum over reads of (16 + 4*n_cigar + ceil(l_qseq/2)) [+ l_qseq for task 2] + 2 * sum(L). */
-int64_t np_engine_algorithmic_bytes(np_engine* e, int32_t task);
 
 /* ---- seeded synthetic inputs (draft FASTA + coordinate-sorted BAM), for bench and tests -- */
 typedef struct {
@@ -211,6 +216,9 @@ typedef struct {
     int32_t  compress_level;    /* BGZF zlib level (0 = stored blocks)                       */
 } np_synth_params;
 int32_t np_synth_write(const np_synth_params* p, const char* fasta_path, const char* bam_path);
+/* The same reads as np_synth_write, packed directly (contigs [contig_lo, contig_hi)). */
+np_shard* np_synth_shard(const np_synth_params* p, int32_t contig_lo, int32_t contig_hi,
+                         int32_t with_qual, int32_t threads);
 
 #ifdef __cplusplus
 }

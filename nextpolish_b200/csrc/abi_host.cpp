@@ -103,5 +103,25 @@ const char* np_shard_contig_name(const np_shard* shard, int32_t i) {
     return shard->s.names[(size_t)i].c_str();
 }
 void np_shard_free(np_shard* shard) { delete shard; }
+int32_t np_shard_contig_rank(const np_shard* shard, int32_t i) {
+    if (i < 0 || (size_t)i >= shard->s.fasta_rank.size()) return -1;
+    return shard->s.fasta_rank[(size_t)i];
+}
+int64_t np_shard_algorithmic_bytes(const np_shard* shard, int32_t task) {
+    int64_t G = shard->s.ctg_off.empty() ? 0 : shard->s.ctg_off.back();
+    return shard->s.alg_bytes + 2 * G + (task == NP_TASK_KMER_COUNT ? shard->s.qual_bytes : 0);
+}
+np_shard* np_synth_shard(const np_synth_params* p, int32_t contig_lo, int32_t contig_hi,
+                         int32_t with_qual, int32_t threads) {
+    if (!p) { np::set_error("np_synth_shard: params is NULL"); return nullptr; }
+    np_shard* sh = new np_shard();
+    std::string err;
+    if (!np::synth_shard(*p, contig_lo, contig_hi, with_qual != 0, threads > 0 ? threads : 1, sh->s, err)) {
+        np::set_error("np_synth_shard: " + err);
+        delete sh;
+        return nullptr;
+    }
+    return sh;
+}
 
 }  // extern "C"

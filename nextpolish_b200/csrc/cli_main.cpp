@@ -1,0 +1,66 @@
+// cli_main.cpp — native CLI with the argument grammar of the reference's main.c:12-75:
+//   nextpolish1 scorechain <fasta> <sgs.bam>   > out.fa
+//   nextpolish1 kmercount  <fasta> <sgs.bam>   > out.fa
+// Output format of contig_write_to_file (contig.c:1050): ">name_<step>\nSEQ\n", contigs in FASTA
+// order; "total time" trace on stderr (contig.c:1116).  Unlike the reference, all contigs are
+// polished in ONE batch on the GPU (np_* batch ABI) instead of one call per contig.
+// Extra command (not in the reference): simulate — seeded synthetic draft + BAM.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <vector>
+#include "../../include/nextpolish_b200.h"
+
+static int usage(const char* a0) {
+    printf("Usage: %s <command> [options]\n\nCommands:\n"
+           "\tscorechain\t\tscore chain run\n\t\t\t\teg. scorechain fastafn sgsbamf > output.fa\n"
+           "\tkmercount\t\tkmer count run\n\t\t\t\teg. kmercount fastafn sgsbamf > output.fa\n"
+           "\tsimulate\t\twrite a seeded synthetic draft + sorted BAM\n"
+           "\t\t\t\teg. simulate out.fa out.bam n_contigs contig_len depth seed [lowercase_frac]\n\n", a0);
+    return 0;
+}
+
+int main(int argc, char* argv[]) {
+    if (argc < 2) return usage(argv[0]);
+    if (strcmp(argv[1], "simulate") == 0) {
+        if (argc < 8) return usage(argv[0]);
+        np_synth_params p; memset(&p, 0, sizeof p);
+        p.n_contigs = atoi(argv[4]); p.contig_len = atoll(argv[5]); p.depth = atof(argv[6]);
+        p.seed = strtoull(argv[7], nullptr, 10);
+        p.read_len = 150; p.draft_snv = 0.001; p.draft_indel = 0.003; p.read_sub = 0.002; p.read_indel = 0.0001;
+        p.lowercase_frac = argc > 8 ? atof(argv[8]) : 0; p.compress_level = 1;
+        if (np_synth_write(&p, argv[2], argv[3]) != NP_OK) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
+        return 0;
+    }
+    int step = 0;
+    if (strcmp(argv[1], "scorechain") == 0) step = 1;
+    else if (strcmp(argv[1], "kmercount") == 0) step = 2;
+    else return usage(argv[0]);
+    if (argc != 4) { printf("%s %s fastafn lgsbam\n", argv[0], argv[1]); return 0; }
+    time_t t0 = time(nullptr);
+    Configure* cfg = config_init(argv[2], argv[3], nullptr);
+    np_shard* sh = np_shard_load(argv[2], argv[3], nullptr, 0, step == 2, 8);
+    if (!sh) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
+    np_shard_view v; np_shard_view_of(sh, &v);
+    np_engine* e = np_engine_create(getenv("NEXTPOLISH_B200_DEVICE") ? atoi(getenv("NEXTPOLISH_B200_DEVICE")) : 0);
+    if (!e) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
+    if (np_engine_upload(e, &v) != NP_OK || np_engine_run(e, step, cfg) != NP_OK) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
+    int64_t n = np_engine_result_bytes(e);
+    std::vector<uint8_t> out((size_t)n + 1);
+    std::vector<int64_t> off((size_t)v.n_contigs + 1);
+    if (np_engine_download(e, out.data(), n + 1, off.data()) != NP_OK) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
+    std::vector<int> slot_of_rank((size_t)v.n_contigs, -1);
+    for (int i = 0; i < v.n_contigs; i++) slot_of_rank[(size_t)np_shard_contig_rank(sh, i)] = i;
+    for (int r = 0; r < v.n_contigs; r++) {
+        int i = slot_of_rank[(size_t)r];
+        printf(">%s_%d\n", np_shard_contig_name(sh, i), step);
+        fwrite(out.data() + off[(size_t)i], 1, (size_t)(off[(size_t)i + 1] - off[(size_t)i]), stdout);
+        fputc('\n', stdout);
+    }
+    np_engine_destroy(e);
+    np_shard_free(sh);
+    config_destory(cfg);
+    fprintf(stderr, "total time:%lds\n", (long)(time(nullptr) - t0));
+    return 0;
+}

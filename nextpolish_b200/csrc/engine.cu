@@ -1,0 +1,413 @@
+// engine.cu — CUDA backend of the polishing engine and the device half of the C ABI.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (see __graft_entry__.build()).
+//
+// Floating point: the score chain is evaluated with separate multiply / subtract / add in
+// double (contig.c:448); the file is compiled with -fmad=false so no FMA contraction can
+// change a rounding relative to the reference's x86-64 SSE2 code.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+
+#include <unistd.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "engine_impl.h"
+#include "errors.h"
+#include "hostio.h"
+#include "../../include/nextpolish_b200.h"
+
+namespace {
+
+struct CudaOps {
+    __host__ __device__ __forceinline__ void atomic_max(int32_t* p, int32_t v) {
+#ifdef __CUDA_ARCH__
+        atomicMax(p, v);
+#else
+        (void)p; (void)v;
+#endif
+    }
+    __host__ __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+        atomicOr(p, v);
+#else
+        (void)p; (void)v;
+#endif
+    }
+};
+
+template <class F>
+__global__ void __launch_bounds__(256) k_items(int64_t n, F f) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { CudaOps ops; f(i, ops); }
+}
+
+struct MaxOp { __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; } };
+
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(#x, e_); } } while (0)
+
+struct CudaBackend {
+    cudaStream_t stream = nullptr;
+    struct Buf { void* p = nullptr; size_t bytes = 0; };
+    std::map<std::string, Buf> pool;
+    void* cub_tmp = nullptr; size_t cub_bytes = 0;
+    int32_t* h_scalar = nullptr;   // pinned
+    bool ok = true; std::string msg;
+    // per-launch timing
+    struct Timed { const char* name; cudaEvent_t a, b; };
+    std::vector<Timed> timed; size_t n_timed = 0; bool timing = true;
+    int32_t launches = 0;
+
+    void fail(const char* what, cudaError_t e) {
+        if (ok) { ok = false; msg = std::string(what) + ": " + cudaGetErrorString(e); }
+    }
+    template <class T> T* buf(const char* name, size_t count) {
+        Buf& b = pool[name];
+        size_t bytes = count * sizeof(T) + 256;
+        if (b.bytes < bytes) {
+            if (b.p) { CUDA_TRY(cudaStreamSynchronize(stream)); CUDA_TRY(cudaFree(b.p)); b.p = nullptr; }
+            size_t want = bytes + bytes / 8;
+            CUDA_TRY(cudaMalloc(&b.p, want));
+            b.bytes = b.p ? want : 0;
+        }
+        return (T*)b.p;
+    }
+    void zero(void* p, size_t bytes) { if (ok && p) CUDA_TRY(cudaMemsetAsync(p, 0, bytes, stream)); }
+    void begin_timed(const char* name) {
+        if (!timing) return;
+        if (n_timed == timed.size()) {
+            Timed t; t.name = name;
+            CUDA_TRY(cudaEventCreate(&t.a)); CUDA_TRY(cudaEventCreate(&t.b));
+            timed.push_back(t);
+        }
+        timed[n_timed].name = name;
+        CUDA_TRY(cudaEventRecord(timed[n_timed].a, stream));
+    }
+    void end_timed() {
+        if (!timing) return;
+        CUDA_TRY(cudaEventRecord(timed[n_timed].b, stream));
+        n_timed++;
+    }
+    template <class F> void launch(const char* name, int64_t n, const F& f) {
+        if (!ok || n <= 0) return;
+        begin_timed(name);
+        int64_t blocks = (n + 255) / 256;
+        k_items<F><<<(unsigned)blocks, 256, 0, stream>>>(n, f);
+        CUDA_TRY(cudaGetLastError());
+        launches++;
+        end_timed();
+    }
+    void cub_reserve(size_t bytes) {
+        if (bytes > cub_bytes) {
+            if (cub_tmp) { CUDA_TRY(cudaStreamSynchronize(stream)); CUDA_TRY(cudaFree(cub_tmp)); }
+            CUDA_TRY(cudaMalloc(&cub_tmp, bytes + 1024));
+            cub_bytes = bytes + 1024;
+        }
+    }
+    void exscan_i32(const int32_t* in, int32_t* out, int64_t n) {
+        if (!ok || n <= 0) return;
+        size_t need = 0;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n, stream));
+        cub_reserve(need);
+        begin_timed("scan_sum");
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, need, in, out, (int)n, stream));
+        launches += 2;
+        end_timed();
+    }
+    void inclmax_i32(const int32_t* in, int32_t* out, int64_t n) {
+        if (!ok || n <= 0) return;
+        size_t need = 0;
+        CUDA_TRY(cub::DeviceScan::InclusiveScan(nullptr, need, in, out, MaxOp(), (int)n, stream));
+        cub_reserve(need);
+        begin_timed("scan_max");
+        CUDA_TRY(cub::DeviceScan::InclusiveScan(cub_tmp, need, in, out, MaxOp(), (int)n, stream));
+        launches += 2;
+        end_timed();
+    }
+    int32_t read_i32(const int32_t* p) {
+        if (!ok) return 0;
+        CUDA_TRY(cudaMemcpyAsync(h_scalar, p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        return ok ? *h_scalar : 0;
+    }
+    void release() {
+        for (auto& kv : pool) if (kv.second.p) cudaFree(kv.second.p);
+        pool.clear();
+        if (cub_tmp) cudaFree(cub_tmp);
+        for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+        if (h_scalar) cudaFreeHost(h_scalar);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static void params_from_cfg(const Configure* cfg, npd::Params* P) {
+    P->trim_len_edge = cfg->trim_len_edge;
+    P->ext_len_edge = cfg->ext_len_edge;
+    P->min_map_quality = cfg->min_map_quality;
+    P->rate = cfg->indel_balance_factor_sgs;
+    P->min_count_ratio_skip = cfg->min_count_ratio_skip;
+    P->min_len_ldr = cfg->min_len_ldr;
+    P->min_len_inter_kmer = cfg->min_len_inter_kmer;
+    P->max_len_kmer = cfg->max_len_kmer;
+    P->max_count_kmer = cfg->max_count_kmer;
+    P->max_clip_ratio_sgs = cfg->max_clip_ratio_sgs;
+    P->read_tlen = cfg->read_tlen;
+}
+
+}  // namespace
+
+struct np_engine {
+    int device = 0;
+    CudaBackend be;
+    npe::Dev d;
+    npe::RunStats st;
+    bool resident = false, owns_shard = false;
+    std::vector<int64_t> h_ctg_off, h_read_off;
+    // device copies of the shard (when uploaded)
+    void *s_seq = nullptr, *s_goff = nullptr, *s_roff = nullptr, *s_recoff = nullptr, *s_rec = nullptr,
+         *s_qoff = nullptr, *s_qual = nullptr;
+    size_t cap_seq = 0, cap_goff = 0, cap_roff = 0, cap_recoff = 0, cap_rec = 0, cap_qoff = 0, cap_qual = 0;
+    std::vector<int64_t> h_out_off;
+    bool ran = false;
+};
+
+static bool dev_reserve(np_engine* e, void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes && *p) return true;
+    if (*p) { cudaStreamSynchronize(e->be.stream); cudaFree(*p); *p = nullptr; *cap = 0; }
+    size_t want = bytes + bytes / 16 + 256;
+    cudaError_t er = cudaMalloc(p, want);
+    if (er != cudaSuccess) { np::set_error(std::string("cudaMalloc: ") + cudaGetErrorString(er)); return false; }
+    *cap = want;
+    return true;
+}
+
+extern "C" {
+
+np_engine* np_engine_create(int32_t device) {
+    int n = 0;
+    cudaError_t er = cudaGetDeviceCount(&n);
+    if (er != cudaSuccess || n == 0) {
+        np::set_error(std::string("np_engine_create: no usable CUDA device (") +
+                      (er != cudaSuccess ? cudaGetErrorString(er) : "device count 0") +
+                      "); this engine has no CPU path");
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { np::set_error("np_engine_create: bad device index"); return nullptr; }
+    if ((er = cudaSetDevice(device)) != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return nullptr; }
+    np_engine* e = new np_engine();
+    e->device = device;
+    memset(&e->d, 0, sizeof(e->d));
+    if ((er = cudaStreamCreateWithFlags(&e->be.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (er = cudaMallocHost((void**)&e->be.h_scalar, 64)) != cudaSuccess) {
+        np::set_error(std::string("np_engine_create: ") + cudaGetErrorString(er));
+        delete e;
+        return nullptr;
+    }
+    return e;
+}
+
+void np_engine_destroy(np_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->be.stream);
+    void* ps[] = {e->s_seq, e->s_goff, e->s_roff, e->s_recoff, e->s_rec, e->s_qoff, e->s_qual};
+    for (void* p : ps) if (p) cudaFree(p);
+    e->be.release();
+    delete e;
+}
+
+static int32_t set_shard_common(np_engine* e, const np_shard_view* v, bool device_resident) {
+    if (!e || !v || v->n_contigs < 0 || v->n_reads < 0) { np::set_error("bad shard"); return NP_ERR_ARG; }
+    int64_t G = v->ctg_off[v->n_contigs];
+    if (G >= 0x7fffff00ll || v->n_reads >= 0x7fffff00ll) {
+        np::set_error("shard exceeds 2^31 positions/reads: split it into several shards");
+        return NP_ERR_LIMIT;
+    }
+    cudaSetDevice(e->device);
+    e->h_ctg_off.assign(v->ctg_off, v->ctg_off + v->n_contigs + 1);
+    e->h_read_off.assign(v->ctg_read_off, v->ctg_read_off + v->n_contigs + 1);
+    std::vector<int32_t> goff((size_t)v->n_contigs + 1);
+    for (int i = 0; i <= v->n_contigs; i++) goff[(size_t)i] = (int32_t)v->ctg_off[i];
+    cudaStream_t s = e->be.stream;
+    if (!dev_reserve(e, &e->s_goff, &e->cap_goff, goff.size() * 4) ||
+        !dev_reserve(e, &e->s_roff, &e->cap_roff, e->h_read_off.size() * 8)) return NP_ERR_CUDA;
+    cudaMemcpyAsync(e->s_goff, goff.data(), goff.size() * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(e->s_roff, e->h_read_off.data(), e->h_read_off.size() * 8, cudaMemcpyHostToDevice, s);
+    size_t rec_bytes = 0, qual_bytes = 0;
+    // rec_off[n_reads] is needed to size the copy; for device-resident shards read it back
+    uint32_t last_rec = 0, last_q = 0;
+    if (device_resident) {
+        cudaMemcpyAsync(&last_rec, v->rec_off + v->n_reads, 4, cudaMemcpyDeviceToHost, s);
+        if (v->qual_off) cudaMemcpyAsync(&last_q, v->qual_off + v->n_reads, 4, cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+    } else {
+        last_rec = v->rec_off[v->n_reads];
+        if (v->qual_off) last_q = v->qual_off[v->n_reads];
+    }
+    rec_bytes = (size_t)last_rec * 16; qual_bytes = (size_t)last_q * 16;
+    npe::Dev& d = e->d;
+    d.n_ctg = v->n_contigs; d.n_reads = v->n_reads; d.G = (int32_t)G;
+    d.ctg_goff = (const int32_t*)e->s_goff; d.ctg_read_off = (const int64_t*)e->s_roff;
+    if (device_resident) {
+        d.ctg_seq = v->ctg_seq; d.rec_off = v->rec_off; d.rec = v->rec; d.qual_off = v->qual_off; d.qual = v->qual;
+    } else {
+        if (!dev_reserve(e, &e->s_seq, &e->cap_seq, (size_t)G + 16) ||
+            !dev_reserve(e, &e->s_recoff, &e->cap_recoff, ((size_t)v->n_reads + 1) * 4) ||
+            !dev_reserve(e, &e->s_rec, &e->cap_rec, rec_bytes + 16)) return NP_ERR_CUDA;
+        cudaMemcpyAsync(e->s_seq, v->ctg_seq, (size_t)G, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(e->s_recoff, v->rec_off, ((size_t)v->n_reads + 1) * 4, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(e->s_rec, v->rec, rec_bytes, cudaMemcpyHostToDevice, s);
+        d.ctg_seq = (const uint8_t*)e->s_seq; d.rec_off = (const uint32_t*)e->s_recoff; d.rec = (const uint8_t*)e->s_rec;
+        d.qual_off = nullptr; d.qual = nullptr;
+        if (v->qual && v->qual_off) {
+            if (!dev_reserve(e, &e->s_qoff, &e->cap_qoff, ((size_t)v->n_reads + 1) * 4) ||
+                !dev_reserve(e, &e->s_qual, &e->cap_qual, qual_bytes + 16)) return NP_ERR_CUDA;
+            cudaMemcpyAsync(e->s_qoff, v->qual_off, ((size_t)v->n_reads + 1) * 4, cudaMemcpyHostToDevice, s);
+            cudaMemcpyAsync(e->s_qual, v->qual, qual_bytes, cudaMemcpyHostToDevice, s);
+            d.qual_off = (const uint32_t*)e->s_qoff; d.qual = (const uint8_t*)e->s_qual;
+        }
+    }
+    cudaError_t er = cudaGetLastError();
+    if (er != cudaSuccess) { np::set_error(std::string("upload: ") + cudaGetErrorString(er)); return NP_ERR_CUDA; }
+    e->resident = true; e->ran = false;
+    return NP_OK;
+}
+
+int32_t np_engine_upload(np_engine* e, const np_shard_view* host_shard) { return set_shard_common(e, host_shard, false); }
+int32_t np_engine_adopt_device(np_engine* e, const np_shard_view* dev_shard) { return set_shard_common(e, dev_shard, true); }
+
+int32_t np_engine_run(np_engine* e, int32_t task, const Configure* cfg) {
+    if (!e || !cfg || !e->resident) { np::set_error("np_engine_run: no resident shard"); return NP_ERR_ARG; }
+    cudaSetDevice(e->device);
+    params_from_cfg(cfg, &e->d.P);
+    e->be.n_timed = 0; e->be.launches = 0;
+    int err;
+    if (task == NP_TASK_SCORE_CHAIN) err = npe::run_score_chain(e->be, e->d, &e->st);
+    else { np::set_error("np_engine_run: task not implemented"); return NP_ERR_ARG; }
+    if (!e->be.ok) { np::set_error("CUDA failure: " + e->be.msg); return NP_ERR_CUDA; }
+    if (err) {
+        char b[160];
+        snprintf(b, sizeof b, "device error word 0x%x (1=insertion overflow 2=depth>=65535 4=missing score 8=column string bound)", err);
+        np::set_error(b);
+        return NP_ERR_LIMIT;
+    }
+    e->ran = true;
+    return NP_OK;
+}
+
+int32_t np_engine_sync(np_engine* e) {
+    cudaSetDevice(e->device);
+    cudaError_t er = cudaStreamSynchronize(e->be.stream);
+    if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
+    return NP_OK;
+}
+int64_t np_engine_result_bytes(np_engine* e) { return e && e->ran ? e->st.out_bytes : -1; }
+const uint8_t* np_engine_result_device(np_engine* e) { return e && e->ran ? e->d.out : nullptr; }
+void* np_engine_stream(np_engine* e) { return e ? (void*)e->be.stream : nullptr; }
+int32_t np_engine_launch_count(np_engine* e) { return e ? e->be.launches : 0; }
+
+int32_t np_engine_download(np_engine* e, uint8_t* out_seq, int64_t out_cap, int64_t* out_off) {
+    if (!e || !e->ran) { np::set_error("np_engine_download: nothing to download"); return NP_ERR_ARG; }
+    if (out_cap < e->st.out_bytes) { np::set_error("np_engine_download: buffer too small"); return NP_ERR_ARG; }
+    cudaSetDevice(e->device);
+    cudaStream_t s = e->be.stream;
+    cudaMemcpyAsync(out_seq, e->d.out, (size_t)e->st.out_bytes, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(out_off, e->d.out_off, ((size_t)e->d.n_ctg + 1) * 8, cudaMemcpyDeviceToHost, s);
+    cudaError_t er = cudaStreamSynchronize(s);
+    if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
+    return NP_OK;
+}
+
+int32_t np_engine_copy_result(np_engine* e, void* dst_device, int64_t dst_cap) {
+    if (!e || !e->ran || dst_cap < e->st.out_bytes) { np::set_error("np_engine_copy_result: bad arguments"); return NP_ERR_ARG; }
+    cudaSetDevice(e->device);
+    cudaError_t er = cudaMemcpyAsync(dst_device, e->d.out, (size_t)e->st.out_bytes, cudaMemcpyDeviceToDevice, e->be.stream);
+    if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
+    return NP_OK;
+}
+
+int32_t np_engine_kernel_times(np_engine* e, const char** names, float* ms, int32_t cap) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->be.stream);
+    int32_t n = 0;
+    for (size_t i = 0; i < e->be.n_timed && n < cap; i++, n++) {
+        names[n] = e->be.timed[i].name;
+        float t = 0;
+        cudaEventElapsedTime(&t, e->be.timed[i].a, e->be.timed[i].b);
+        ms[n] = t;
+    }
+    return n;
+}
+
+int32_t np_polish_host(np_engine* e, int32_t task, const np_shard_view* host_shard,
+                       const Configure* cfg, uint8_t* out_seq, int64_t out_cap, int64_t* out_off) {
+    int32_t rc = np_engine_upload(e, host_shard);
+    if (rc != NP_OK) return rc;
+    rc = np_engine_run(e, task, cfg);
+    if (rc != NP_OK) return rc;
+    return np_engine_download(e, out_seq, out_cap, out_off);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference ABI: one contig per call (nextpolish1.py:181-189, main.c:12-26)
+// ---------------------------------------------------------------------------------------------
+static np_engine* process_engine() {
+    // created lazily in the calling process: nextpolish1.py forks its Pool after config_init
+    // (nextpolish1.py:219-223), and a CUDA context must not cross fork().
+    static np_engine* eng = nullptr;
+    static pid_t owner = 0;
+    if (eng && owner == getpid()) return eng;
+    int dev = 0;
+    if (const char* s = getenv("NEXTPOLISH_B200_DEVICE")) dev = atoi(s);
+    eng = np_engine_create(dev);
+    owner = getpid();
+    if (!eng) {
+        fprintf(stderr, "nextpolish_b200: %s\n", np_last_error());
+        exit(1);   // the reference's fatal-error convention (contig.c:86-89)
+    }
+    return eng;
+}
+
+static PolishResult* run_one_contig(const char* tigname, Configure* cfg, int task) {
+    if (!tigname || !cfg || !cfg->fastafn) { fprintf(stderr, "nextpolish_b200: bad arguments\n"); exit(1); }
+    np::Shard sh; std::string err;
+    std::vector<std::string> names{std::string(tigname)};
+    if (!np::shard_load(cfg->fastafn, cfg->bamfn ? cfg->bamfn : "", names, task == NP_TASK_KMER_COUNT, 4, sh, err)) {
+        fprintf(stderr, "nextpolish_b200: %s\n", err.c_str());
+        exit(1);
+    }
+    np_shard_view v; sh.view(&v);
+    np_engine* e = process_engine();
+    int64_t cap = (int64_t)sh.ctg_seq.size() * 2 + 1024;
+    PolishResult* res = polishresult_init();
+    int32_t rc = np_engine_upload(e, &v);
+    if (rc == NP_OK) rc = np_engine_run(e, task, cfg);
+    if (rc == NP_OK) { cap = np_engine_result_bytes(e) + 1; }
+    if (rc != NP_OK) { fprintf(stderr, "nextpolish_b200: %s\n", np_last_error()); exit(1); }
+    res->contig = (char*)calloc(1, (size_t)cap + 1);
+    int64_t off[2] = {0, 0};
+    rc = np_engine_download(e, (uint8_t*)res->contig, cap, off);
+    if (rc != NP_OK) { fprintf(stderr, "nextpolish_b200: %s\n", np_last_error()); exit(1); }
+    res->length = (int32_t)off[1];
+    res->contig[off[1]] = '\0';
+    return res;
+}
+
+PolishResult* score_chain(const char* tigname, Configure* configure) { return run_one_contig(tigname, configure, NP_TASK_SCORE_CHAIN); }
+PolishResult* kmer_count(const char* tigname, Configure* configure) { return run_one_contig(tigname, configure, NP_TASK_KMER_COUNT); }
+
+static PolishResult* out_of_scope(const char* what) {
+    fprintf(stderr, "nextpolish_b200: %s is outside this engine's scope (SURVEY.md section 8f); "
+                    "use the reference nextpolish1.so for tasks 3-5\n", what);
+    exit(1);
+    return nullptr;
+}
+PolishResult* snp_phase(const char*, Configure*) { return out_of_scope("snp_phase"); }
+PolishResult* snp_valid(const char*, Configure*) { return out_of_scope("snp_valid"); }
+PolishResult* lgspolish(const char*, Configure*) { return out_of_scope("lgspolish"); }
+
+}  // extern "C"

@@ -395,7 +395,7 @@ void Shard::view(np_shard_view* v) const {
     v->qual = with_qual ? qual.data() : nullptr;
 }
 
-static bool pack_record(const BamRec& r, Shard& s, std::string& err) {
+bool shard_pack_record(const BamRec& r, Shard& s, std::string& err) {
     if (r.l_qseq > 65535 || r.n_cigar > 65535) {
         err = "read longer than 65535 bases / CIGAR ops: not a short-read record";
         return false;
@@ -415,6 +415,8 @@ static bool pack_record(const BamRec& r, Shard& s, std::string& err) {
     memcpy(d + 16, r.cigar, 4 * (size_t)r.n_cigar);
     memcpy(d + 16 + 4 * (size_t)r.n_cigar, r.seq, ((size_t)r.l_qseq + 1) / 2);
     s.rec_off.push_back((uint32_t)((o + padded) / 16));
+    s.alg_bytes += (int64_t)body;
+    s.qual_bytes += r.l_qseq;
     if (s.with_qual) {
         size_t qo = s.qual.size(), qp = ((size_t)r.l_qseq + 15) & ~(size_t)15;
         s.qual.resize(qo + qp, 0);
@@ -454,6 +456,7 @@ bool shard_load(const std::string& fasta, const std::string& bam,
     for (size_t k = 0; k < slots.size(); k++) {
         const FastaRecord& r = recs[slots[k].rec_idx];
         out.names.push_back(r.name);
+        out.fasta_rank.push_back((int32_t)slots[k].rec_idx);
         out.ctg_seq.insert(out.ctg_seq.end(), r.seq.begin(), r.seq.end());
         out.ctg_off.push_back((int64_t)out.ctg_seq.size());
         if (slots[k].tid != 0x7fffffff) slot_of_tid.emplace(slots[k].tid, (int)k);
@@ -470,7 +473,7 @@ bool shard_load(const std::string& fasta, const std::string& bam,
             if (it == slot_of_tid.end() || r.n_cigar == 0) return true;
             if (it->second < cur_slot) { err = "BAM is not coordinate sorted"; ok = false; return false; }
             cur_slot = it->second;
-            if (!pack_record(r, out, err)) { ok = false; return false; }
+            if (!shard_pack_record(r, out, err)) { ok = false; return false; }
             counts[(size_t)cur_slot]++;
             return true;
         };
@@ -486,7 +489,7 @@ bool shard_load(const std::string& fasta, const std::string& bam,
                 auto visit_one = [&](const BamRec& r) -> bool {
                     if (r.tid < 0 || r.tid > tid) return false;
                     if (r.tid < tid || r.n_cigar == 0) return true;
-                    if (!pack_record(r, out, err)) { ok = false; return false; }
+                    if (!shard_pack_record(r, out, err)) { ok = false; return false; }
                     counts[k]++;
                     return true;
                 };

