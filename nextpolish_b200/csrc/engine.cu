@@ -15,7 +15,7 @@
 #include <string>
 #include <vector>
 
-#include "engine_impl.h"
+#include "engine_task2.h"
 #include "errors.h"
 #include "hostio.h"
 #include "../../include/nextpolish_b200.h"
@@ -26,6 +26,13 @@ struct CudaOps {
     __host__ __device__ __forceinline__ void atomic_max(int32_t* p, int32_t v) {
 #ifdef __CUDA_ARCH__
         atomicMax(p, v);
+#else
+        (void)p; (void)v;
+#endif
+    }
+    __host__ __device__ __forceinline__ void atomic_add(int32_t* p, int32_t v) {
+#ifdef __CUDA_ARCH__
+        atomicAdd(p, v);
 #else
         (void)p; (void)v;
 #endif
@@ -114,6 +121,16 @@ struct CudaBackend {
         cub_reserve(need);
         begin_timed("scan_sum");
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, need, in, out, (int)n, stream));
+        launches += 2;
+        end_timed();
+    }
+    void inclsum_i32(const int32_t* in, int32_t* out, int64_t n) {
+        if (!ok || n <= 0) return;
+        size_t need = 0;
+        CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, need, in, out, (int)n, stream));
+        cub_reserve(need);
+        begin_timed("scan_sum");
+        CUDA_TRY(cub::DeviceScan::InclusiveSum(cub_tmp, need, in, out, (int)n, stream));
         launches += 2;
         end_timed();
     }
@@ -286,11 +303,14 @@ int32_t np_engine_run(np_engine* e, int32_t task, const Configure* cfg) {
     e->be.n_timed = 0; e->be.launches = 0;
     int err;
     if (task == NP_TASK_SCORE_CHAIN) err = npe::run_score_chain(e->be, e->d, &e->st);
-    else { np::set_error("np_engine_run: task not implemented"); return NP_ERR_ARG; }
+    else if (task == NP_TASK_KMER_COUNT) {
+        if (!e->d.qual || !e->d.qual_off) { np::set_error("np_engine_run: task 2 needs the quality stream (load the shard with_qual)"); return NP_ERR_ARG; }
+        err = npe::run_kmer_count(e->be, e->d, &e->st);
+    } else { np::set_error("np_engine_run: unknown task"); return NP_ERR_ARG; }
     if (!e->be.ok) { np::set_error("CUDA failure: " + e->be.msg); return NP_ERR_CUDA; }
     if (err) {
         char b[160];
-        snprintf(b, sizeof b, "device error word 0x%x (1=insertion overflow 2=depth>=65535 4=missing score 8=column string bound)", err);
+        snprintf(b, sizeof b, "device error word 0x%x (1=insertion overflow 2=depth>=65535 4=missing score 8=column string bound 16=no-depth regions share an endpoint 32=region scratch)", err);
         np::set_error(b);
         return NP_ERR_LIMIT;
     }

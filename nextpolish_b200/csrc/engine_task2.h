@@ -1,0 +1,703 @@
+// engine_task2.h — task 2 (kmer_count, kmercount.c:93-126) as data-parallel passes.
+//
+//   flag runs      per position : lowercase runs of the draft (FLAG_ZERO, contig.c:94-97)
+//   regions        per contig   : contig_get_region x2 over the run list + contig_merge_region
+//                                 (contig.c:498-620) -> no-depth regions, k-mer regions
+//   insert layout  per read     : contig_create_insert_region (contig.c:182-200) -> ins[], colbase
+//   nodepth score  per region   : contig_score_correct(region, 0x12) (contig.c:706-734): level-2
+//                                 votes, chain DP, backtrack, then level-1 votes on the still
+//                                 unsupported sub-regions, re-score, re-correct
+//   split          per region   : ss_spilt_region (kmercount.c:128-173) -> windows
+//   window vote    per window   : ss_kmer_correct (kmercount.c:175-261): spanning level-2 reads,
+//                                 identical-string tally, 50 x MAPQ60 cap, winner
+//   apply + emit                : contig_update_contig (contig.c:811-821), contig_get_contig(FLAG_ZERO)
+//
+// Regions and windows are independent units (one thread each; they are few and small); the
+// order-dependent parts of the reference (first-seen tie-breaks, the MAPQ-60 cap, last-writer-wins
+// on window end columns) are kept by iterating reads in BAM order inside a unit and by applying
+// window winners in window order.
+#pragma once
+#include "engine_impl.h"
+
+namespace npe {
+
+struct Dev2 {
+    Dev d;                       // shared layout / read arrays (task = 2)
+    // lowercase runs
+    int32_t *rs_flag, *rs_idx;   // per position: run-start flag, its exclusive scan
+    int32_t *re_flag, *re_idx;   // per position: run-end flag, its exclusive scan
+    int32_t *run_s, *run_e;      // [n_runs]
+    int32_t n_runs;
+    // region lists per contig (slices [ctg_run_off[k], ctg_run_off[k+1]) * 2 ints)
+    int32_t *nd_reg, *km_reg;    // [2*n_runs+2] (start,end) pairs, global positions
+    int32_t *nd_cnt, *km_cnt;    // per contig: number of regions (pairs)
+    int32_t *nd_off, *km_off;    // exclusive scans of the counts
+    int32_t *ndl, *kml;          // compacted lists [2*NR]
+    int32_t NR_nd, NR_km;
+    int32_t *indiff, *inreg;     // per position (+1): difference array and its scan
+    int32_t* r_hpm;              // prefix max of r_hend
+    // nodepth scoring scratch
+    int32_t *ndmark, *ndidx;     // per column
+    int32_t *vcap, *koff;        // per column vote capacity and its scan
+    int32_t NRC;                 // number of nodepth-region columns
+    uint32_t* ktab2;             // k-mer lists
+    int32_t* nk2;                // [NRC] list lengths
+    uint32_t* cnt2;              // [NRC] votes
+    uint16_t* refk2;             // [NRC] refkmer
+    double* sc2;                 // [NRC*16] scores by base code
+    uint16_t* kc2;               // [NRC*16]
+    uint8_t* ord2;               // [NRC*16] first-seen order of base codes
+    uint8_t* ns2;                // [NRC]
+    int32_t* subbuf;             // [NRC + 2*NR_nd + 2] inner region lists
+    // windows
+    int32_t *wcnt, *woff;        // per k-mer region: window count, scan
+    int32_t *win;                // [2*NW] (start,end)
+    int32_t NW;
+    int32_t *wcand, *wsoff;      // per window: candidate count; scratch offset (bytes, in 4-byte units)
+    int32_t* wscratch;           // strings + tallies
+    int32_t* wbest;              // [NW] offset of the winner string in wscratch (bytes), or -1
+};
+
+enum { ERR_SHARED_ENDPOINT = 16, ERR_REGION_SCRATCH = 32 };
+
+// ---- lowercase runs ---------------------------------------------------------------------------
+NP_HD bool pos_flagged(const Dev& d, int32_t p) { uint32_t ch = d.ctg_seq[p]; return ch >= 97 && ch <= 122; }
+
+struct RunFlags {
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t p, B&) const {
+        const Dev& d = w.d;
+        int32_t s = 0, e = 0;
+        if (p < d.G && pos_flagged(d, (int32_t)p)) {
+            int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, (int32_t)p);
+            int32_t gs = d.ctg_goff[k], ge = d.ctg_goff[k + 1] - 1;
+            s = (p == gs) || !pos_flagged(d, (int32_t)p - 1);
+            e = (p == ge) || !pos_flagged(d, (int32_t)p + 1);
+        }
+        w.rs_flag[p] = s; w.re_flag[p] = e;
+    }
+};
+struct RunFill {
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t p, B&) const {
+        if (w.rs_flag[p]) w.run_s[w.rs_idx[p]] = (int32_t)p;
+        if (w.re_flag[p]) w.run_e[w.re_idx[p]] = (int32_t)p;
+    }
+};
+
+// contig_brim_no_extension / contig_brim_with_extension on positions (contig.c:498-517)
+NP_HD void brim_pos(const Dev& d, bool with_ext, int32_t ext, int32_t bstart, int32_t bend, int32_t* start, int32_t* end) {
+    *start = *start >= bstart + ext ? *start - ext : bstart;
+    *end = *end <= bend - ext ? *end + ext : bend;
+    if (!with_ext) return;
+    while (*start > bstart) {
+        int32_t p = *start + 1;
+        uint32_t a = p <= bend ? d.ctg_seq[p] : 0, b = d.ctg_seq[p - 1];
+        if (a >= 97 && a <= 122) a -= 32;
+        uint32_t bu = (b >= 97 && b <= 122) ? b - 32 : b;
+        bool same = p <= bend && base_code(a) == base_code(bu);
+        if (same || (b >= 97 && b <= 122)) (*start)--; else break;
+    }
+    while (*end < bend) {
+        int32_t p = *end - 1;
+        uint32_t a = p >= bstart ? d.ctg_seq[p] : 0, b = d.ctg_seq[p + 1];
+        if (a >= 97 && a <= 122) a -= 32;
+        uint32_t bu = (b >= 97 && b <= 122) ? b - 32 : b;
+        bool same = p >= bstart && base_code(a) == base_code(bu);
+        if (same || (b >= 97 && b <= 122)) (*end)++; else break;
+    }
+}
+
+// contig_get_region (contig.c:519-563) over the lowercase runs of one contig. Appends (start,end)
+// pairs to out; returns the number of pairs.
+NP_HD int32_t regions_from_runs(const Dev& d, const int32_t* run_s, const int32_t* run_e, int32_t r0, int32_t r1,
+                                int32_t gs, int32_t ge, int32_t gap, int32_t con, bool with_ext, int32_t ext, int32_t* out) {
+    int32_t n = 0, cur = gs, r = r0;
+    while (r < r1) {
+        if (run_e[r] < cur) { r++; continue; }                  // run swallowed by an earlier extension
+        int32_t qstart = run_s[r] > cur ? run_s[r] : cur;
+        int32_t qend = run_e[r];
+        int32_t pcon = qend - qstart + 1;
+        r++;
+        while (r < r1 && run_s[r] - qend - 1 <= gap) { pcon = run_e[r] - run_s[r] + 1; qend = run_e[r]; r++; }
+        int32_t i = qend + gap + 1;                              // position where pgap first exceeds gap
+        if (i > ge) {                                            // open at the contig end: emitted unconditionally
+            brim_pos(d, with_ext, ext, gs, ge, &qstart, &qend);
+            out[2 * n] = qstart; out[2 * n + 1] = qend; n++;
+            break;
+        }
+        if (pcon > con) {
+            brim_pos(d, with_ext, ext, gs, ge, &qstart, &qend);
+            out[2 * n] = qstart; out[2 * n + 1] = qend; n++;
+            cur = (qend > i ? qend : i) + 1;
+        } else cur = i + 1;
+    }
+    return n;
+}
+
+// contig_merge_region (contig.c:595-620), literal, in place; returns the new pair count
+NP_HD int32_t merge_regions(int32_t* l, int32_t npairs) {
+    if (npairs == 0) return 0;
+    int32_t ps = 0, qs = 0, length = 1;
+    for (int32_t i = 0; i < npairs; i++) {
+        if (l[2 * ps] >= l[2 * qs + 1]) {
+            qs += 1;
+            if (qs != ps) { l[2 * qs] = l[2 * ps]; l[2 * qs + 1] = l[2 * ps + 1]; }
+            length += 1;
+        } else {
+            while (l[2 * ps] < l[2 * qs]) qs -= 1;
+            l[2 * qs + 1] = l[2 * ps + 1];
+        }
+        ps += 1;
+    }
+    return length;
+}
+
+struct ContigRegions {   // one thread per contig
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t k, B&) const {
+        const Dev& d = w.d;
+        int32_t gs = d.ctg_goff[k], ge = d.ctg_goff[k + 1] - 1;
+        int32_t r0 = w.rs_idx[gs], r1 = w.rs_idx[ge + 1];
+        int32_t* nd = w.nd_reg + 2 * (size_t)r0 + 2 * (size_t)k;   // slack of one pair per contig
+        int32_t* km = w.km_reg + 2 * (size_t)r0 + 2 * (size_t)k;
+        int32_t a = 0, b = 0;
+        if (ge >= gs) {
+            a = regions_from_runs(d, w.run_s, w.run_e, r0, r1, gs, ge, 0, d.P.min_len_ldr, false, d.P.ext_len_edge, nd);
+            b = regions_from_runs(d, w.run_s, w.run_e, r0, r1, gs, ge, d.P.min_len_inter_kmer, 0, true, d.P.ext_len_edge, km);
+            a = merge_regions(nd, a);
+            b = merge_regions(km, b);
+        }
+        w.nd_cnt[k] = a; w.km_cnt[k] = b;
+        if (k == 0) { w.nd_cnt[d.n_ctg] = 0; w.km_cnt[d.n_ctg] = 0; }
+    }
+};
+struct CompactRegions {  // one thread per contig: copy its slices into the dense lists
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t k, B&) const {
+        const Dev& d = w.d;
+        int32_t gs = d.ctg_goff[k];
+        int32_t r0 = w.rs_idx[gs];
+        const int32_t* nd = w.nd_reg + 2 * (size_t)r0 + 2 * (size_t)k;
+        const int32_t* km = w.km_reg + 2 * (size_t)r0 + 2 * (size_t)k;
+        for (int32_t i = 0; i < 2 * w.nd_cnt[k]; i++) w.ndl[2 * w.nd_off[k] + i] = nd[i];
+        for (int32_t i = 0; i < 2 * w.km_cnt[k]; i++) w.kml[2 * w.km_off[k] + i] = km[i];
+    }
+};
+struct RegionDiff {      // mark (start, end] of every region of both lists in a difference array
+    Dev2 w; int which;
+    template <class B> NP_HD void operator()(int64_t i, B& be) const {
+        const int32_t* l = which == 0 ? w.ndl : w.kml;
+        be.atomic_add(&w.indiff[l[2 * i] + 1], 1);
+        be.atomic_add(&w.indiff[l[2 * i + 1] + 1], -1);
+    }
+};
+struct InsertLen2 {      // contig_create_insert_region (contig.c:182-245)
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t r, B& be) const {
+        const Dev& d = w.d;
+        if (d.r_level[r] < 1) return;
+        Rec rc = load_rec(d.rec, d.rec_off, r);
+        int32_t pos = d.r_gpos[r];
+        for (int i = 0; i < rc.n_cigar; i++) {
+            int op = cig_op(rc.cigar[i]); int32_t len = cig_len(rc.cigar[i]);
+            if (op == OP_M || op == OP_D) pos += len;
+            else if (op == OP_I && pos >= 0 && pos <= d.G && w.inreg[pos] > 0) be.atomic_max(&d.ins[pos - 1], len);
+        }
+    }
+};
+struct ColInit2 {        // live base / flag arrays of task 2 start as the draft's
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t c, B&) const {
+        const Dev& d = w.d;
+        d.obase[c] = d.refsym[c];
+        d.oflag[c] = d.cflag[c];
+        w.ndmark[c] = 0; w.vcap[c] = 0;
+        if (c == 0) { w.ndmark[d.C] = 0; w.vcap[d.C] = 0; }
+    }
+};
+
+// ---- candidate reads of a region / window -----------------------------------------------------
+// reads of the contig in BAM order whose [gpos, hend) may overlap [a, b): index range [lo, hi)
+NP_HD void overlap_range(const Dev2& w, int32_t k, int32_t a, int32_t b, int64_t* lo, int64_t* hi) {
+    const Dev& d = w.d;
+    int64_t r0 = d.ctg_read_off[k], r1 = d.ctg_read_off[k + 1];
+    *hi = lower_bound_i32(d.r_gpos, r0, r1, b);             // first read with gpos >= b
+    int64_t l = upper_bound_i32(w.r_hpm, 0, *hi, a);        // first read whose prefix-max hts end > a
+    *lo = l < r0 ? r0 : l;
+}
+
+// ---- nodepth regions --------------------------------------------------------------------------
+// No-depth regions that share an end column (next.start == this.end survives contig_merge_region)
+// form a chain: the reference processes them in order and the shared column keeps the votes of
+// both passes, so a chain is handled by ONE thread, sequentially.
+NP_HD bool chain_head(const Dev2& w, int64_t i) { return i == 0 || w.ndl[2 * i - 1] < w.ndl[2 * i]; }
+NP_HD bool chain_next(const Dev2& w, int64_t j) { return j + 1 < w.NR_nd && w.ndl[2 * (j + 1)] <= w.ndl[2 * j + 1]; }
+
+struct CountVisitor {
+    int32_t* vcap; int32_t inc;
+    NP_HD void sym(int32_t col, uint32_t, int32_t, bool) { vcap[col] += inc; }
+    NP_HD void overflow() {}
+};
+struct NodepthCount {    // per chain: mark the columns and bound the votes each may receive
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B&) const {
+        const Dev& d = w.d;
+        if (!chain_head(w, i)) return;
+        for (int64_t j = i;; j++) {
+            int32_t s = w.ndl[2 * j], e = w.ndl[2 * j + 1];
+            int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
+            for (int32_t c = d.colbase[s]; c <= d.colbase[e]; c++) { w.ndmark[c] = 1; w.vcap[c] += 1; }
+            int64_t lo, hi; overlap_range(w, k, s, e + 1, &lo, &hi);
+            for (int64_t r = lo; r < hi; r++) {
+                if (d.r_level[r] < 1 || d.r_hend[r] <= s) continue;
+                Rec rc = load_rec(d.rec, d.rec_off, r);
+                // level-1 reads may vote twice on a column shared by two inner sub-regions
+                CountVisitor v{w.vcap, d.r_level[r] == 1 ? 2 : 1};
+                walk_read(rc, d.ctg_goff[k], s, e, d.r_qstart[r], d.r_qend[r], d.colbase, v);
+            }
+            if (!chain_next(w, j)) break;
+        }
+    }
+};
+
+struct NdCtx {           // accessors of the per-region scratch
+    const Dev2* w;
+    NP_HD uint32_t* tab(int32_t c) const { return w->ktab2 + w->koff[c]; }
+    NP_HD int32_t& nk(int32_t c) const { return w->nk2[w->ndidx[c]]; }
+    NP_HD uint32_t& cnt(int32_t c) const { return w->cnt2[w->ndidx[c]]; }
+    NP_HD void add(int32_t c, uint32_t kmer) const {                       // base.c:60-71
+        uint32_t* t = tab(c); int32_t n = nk(c);
+        int32_t j = 0;
+        for (; j < n; j++) if ((t[j] & 0xffffu) == kmer) { t[j] += 1u << 16; break; }
+        if (j == n) {
+            if (n >= w->koff[c + 1] - w->koff[c]) { *w->d.err |= ERR_REGION_SCRATCH; return; }
+            t[n] = kmer | (1u << 16); nk(c) = n + 1;
+        }
+        cnt(c)++;
+    }
+};
+struct VoteVisitor {
+    NdCtx x; uint32_t kmer;
+    NP_HD void sym(int32_t col, uint32_t s, int32_t, bool) { kmer = ((kmer & 0xffu) << 4) | s; x.add(col, kmer); }
+    NP_HD void overflow() { *x.w->d.err |= ERR_INS_OVERFLOW; }
+};
+
+// contig_region_score + contig_region_correct (contig.c:456-496) over columns [c0, c1]
+NP_HD void nd_score_correct(const Dev2& w, int32_t c0, int32_t c1, double rate) {
+    const Dev& d = w.d;
+    NdCtx x{&w};
+    bool zero_prev = true; int32_t pi = -1;
+    for (int32_t c = c0; c <= c1; c++) {
+        int32_t ci = w.ndidx[c];
+        double* sc = w.sc2 + (size_t)ci * 16; uint16_t* kc = w.kc2 + (size_t)ci * 16; uint8_t* ord = w.ord2 + (size_t)ci * 16;
+        bool hc[16]; for (int b = 0; b < 16; b++) hc[b] = false;
+        int no = 0;
+        const uint32_t* t = x.tab(c); int32_t nk = x.nk(c);
+        uint32_t total = x.cnt(c), refk = w.refk2[ci];
+        uint32_t tot = total > 1 ? total - 1 : total;
+        const double* sp = pi >= 0 ? w.sc2 + (size_t)pi * 16 : nullptr;
+        const uint8_t* po = pi >= 0 ? w.ord2 + (size_t)pi * 16 : nullptr;
+        int pn = pi >= 0 ? w.ns2[pi] : 0;
+        for (int32_t j = 0; j < nk; j++) {
+            uint32_t k = t[j] & 0xffffu, cnt = t[j] >> 16, pv = (k >> 4) & 0xfu;
+            double s = 0;
+            if (!zero_prev) {
+                if (pv == 0) { int am = po[0]; double mx = sp[am]; for (int q = 1; q < pn; q++) if (sp[po[q]] > mx) { mx = sp[po[q]]; am = po[q]; } s = mx; }
+                else {
+                    bool found = false;
+                    for (int q = 0; q < pn; q++) if (po[q] == pv) found = true;
+                    if (!found) *d.err |= ERR_MISSING_SCORE;
+                    s = sp[pv];
+                }
+            }
+            if (k == refk && total > 1) cnt--;
+            s = s + ((double)cnt - (double)tot * rate);
+            uint32_t b = k & 0xfu;
+            if (!hc[b]) { hc[b] = true; sc[b] = s; kc[b] = (uint16_t)k; ord[no++] = (uint8_t)b; }
+            else if (sc[b] < s) { sc[b] = s; kc[b] = (uint16_t)k; }
+        }
+        w.ns2[ci] = (uint8_t)no;
+        zero_prev = false; pi = ci;
+    }
+    // backtrack
+    auto argmax = [&](int32_t ci) { const double* sc = w.sc2 + (size_t)ci * 16; const uint8_t* ord = w.ord2 + (size_t)ci * 16;
+        int am = ord[0]; double mx = sc[am]; for (int q = 1; q < w.ns2[ci]; q++) if (sc[ord[q]] > mx) { mx = sc[ord[q]]; am = ord[q]; } return (uint32_t)am; };
+    uint32_t chosen = argmax(w.ndidx[c1]);
+    for (int32_t c = c1;; c--) {
+        int32_t ci = w.ndidx[c];
+        const uint32_t* t = x.tab(c); int32_t nk = x.nk(c);
+        uint32_t total = x.cnt(c), support = 0;
+        for (int32_t j = 0; j < nk; j++) if ((t[j] & 0xfu) == chosen) support += t[j] >> 16;
+        uint8_t fl = d.oflag[c];
+        if (total == 1) fl |= FLAG_ZERO; else fl &= (uint8_t)~FLAG_ZERO;
+        if (support / (double)total < d.P.min_count_ratio_skip) fl |= FLAG_COVERAGE; else fl &= (uint8_t)~FLAG_COVERAGE;
+        d.obase[c] = (uint8_t)chosen; d.oflag[c] = fl;
+        if (c == c0) break;
+        uint32_t k = w.kc2[(size_t)ci * 16 + chosen], pv = (k >> 4) & 0xfu;
+        chosen = (pv == 0) ? argmax(w.ndidx[c - 1]) : pv;
+    }
+}
+
+// contig_get_region over COLUMNS [c0,c1] of region [bs,be] with gap 0, con 0, brim_no_extension
+// (the inner call of contig_score_correct, contig.c:722): returns pair count in out
+NP_HD int32_t inner_regions(const Dev& d, int32_t c0, int32_t c1, int32_t bs, int32_t be, int32_t ext, int32_t* out) {
+    int32_t n = 0, qstart = -1, qend = -1;
+    int32_t c = c0;
+    while (c <= c1) {
+        int32_t i = d.colpos[c];
+        if (d.oflag[c] & FLAG_ZERO) { if (qstart == -1) qstart = i; qend = i; }
+        else if (qstart != -1) {
+            // pgap = 1 > gap = 0; pcon >= 1 > con = 0: always emitted
+            int32_t s = qstart >= bs + ext ? qstart - ext : bs, e = qend <= be - ext ? qend + ext : be;
+            out[2 * n] = s; out[2 * n + 1] = e; n++;
+            if (e > i) c = d.colbase[e];
+            qstart = qend = -1;
+        }
+        c++;
+    }
+    if (qstart != -1) {
+        int32_t s = qstart >= bs + ext ? qstart - ext : bs, e = qend <= be - ext ? qend + ext : be;
+        out[2 * n] = s; out[2 * n + 1] = e; n++;
+    }
+    return n;
+}
+
+struct NodepthScore {    // contig_score_correct(region, 0x12), one thread per chain of no-depth regions
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i0, B&) const {
+        const Dev& d = w.d;
+        if (!chain_head(w, i0)) return;
+        NdCtx x{&w};
+        for (int64_t i = i0;; i++) {
+            int32_t s = w.ndl[2 * i], e = w.ndl[2 * i + 1];
+            int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
+            int32_t c0 = d.colbase[s], c1 = d.colbase[e];
+            uint32_t kmer = 0;
+            for (int32_t c = c0; c <= c1; c++) {                           // contig_as_read
+                int32_t ci = w.ndidx[c];
+                if (!(i > i0 && c == c0)) { w.nk2[ci] = 0; w.cnt2[ci] = 0; }   // shared column keeps its votes
+                kmer = ((kmer & 0xffu) << 4) | d.obase[c];
+                w.refk2[ci] = (uint16_t)kmer;
+                x.add(c, kmer);
+            }
+            int64_t lo, hi; overlap_range(w, k, s, e + 1, &lo, &hi);
+            for (int64_t r = lo; r < hi; r++) {                            // contig_parse_region, level == 2
+                if (d.r_level[r] != 2 || d.r_hend[r] <= s) continue;
+                Rec rc = load_rec(d.rec, d.rec_off, r);
+                VoteVisitor v{x, 0};
+                walk_read(rc, d.ctg_goff[k], s, e, d.r_qstart[r], d.r_qend[r], d.colbase, v);
+            }
+            nd_score_correct(w, c0, c1, d.P.rate);
+            int32_t* sub = w.subbuf + (size_t)w.ndidx[c0] + 2 * (size_t)i;
+            int32_t ns = inner_regions(d, c0, c1, s, e, d.P.ext_len_edge, sub);
+            ns = merge_regions(sub, ns);
+            for (int32_t q = 0; q < ns; q++) {
+                int32_t ss = sub[2 * q], se = sub[2 * q + 1];
+                int64_t l2, h2; overlap_range(w, k, ss, se + 1, &l2, &h2);
+                for (int64_t r = l2; r < h2; r++) {                        // level == 1 reads on top
+                    if (d.r_level[r] != 1 || d.r_hend[r] <= ss) continue;
+                    Rec rc = load_rec(d.rec, d.rec_off, r);
+                    VoteVisitor v{x, 0};
+                    walk_read(rc, d.ctg_goff[k], ss, se, d.r_qstart[r], d.r_qend[r], d.colbase, v);
+                }
+                nd_score_correct(w, d.colbase[ss], d.colbase[se], d.P.rate);
+            }
+            if (!chain_next(w, i)) break;
+        }
+    }
+};
+
+// ---- windows ----------------------------------------------------------------------------------
+// ss_spilt_region (kmercount.c:128-173) for one region; out == nullptr: count only
+NP_HD int32_t split_region(const Dev& d, int32_t s, int32_t e, int32_t maxlen, int32_t* out) {
+    int32_t n = 0, cur = s;
+    if (e - s > maxlen) {
+        int32_t qstart = -1, qend = -1;
+        int32_t c = d.colbase[s], cend = d.colbase[e];
+        while (c <= cend && !(d.oflag[c] & FLAG_ZERO)) c++;
+        for (; c <= cend; c++) {
+            int32_t j = d.colpos[c];
+            if (!(d.oflag[c] & FLAG_ZERO)) { if (qstart == -1) qstart = j; qend = j; }
+            else if (qstart != -1) {
+                int32_t k = (qstart + qend) >> 1;
+                if (out) { out[2 * n] = cur; out[2 * n + 1] = k; }
+                n++; cur = k;
+                qstart = qend = -1;
+            }
+        }
+    }
+    if (out) { out[2 * n] = cur; out[2 * n + 1] = e; }
+    return n + 1;
+}
+struct SplitCount {
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B&) const {
+        if (i >= w.NR_km) { w.wcnt[i] = 0; return; }
+        w.wcnt[i] = split_region(w.d, w.kml[2 * i], w.kml[2 * i + 1], w.d.P.max_len_kmer, nullptr);
+    }
+};
+struct SplitFill {
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B&) const {
+        split_region(w.d, w.kml[2 * i], w.kml[2 * i + 1], w.d.P.max_len_kmer, w.win + 2 * (size_t)w.woff[i]);
+    }
+};
+
+// candidates of window [s,e]: reads of the contig with gpos < s and hend > e+1 (swapped iterator)
+NP_HD void window_range(const Dev2& w, int32_t k, int32_t s, int32_t e, int64_t* lo, int64_t* term) {
+    const Dev& d = w.d;
+    int64_t r0 = d.ctg_read_off[k], r1 = d.ctg_read_off[k + 1];
+    *term = lower_bound_i32(d.r_gpos, r0, r1, s);
+    int64_t l = upper_bound_i32(w.r_hpm, 0, *term, e + 1);
+    *lo = l < r0 ? r0 : l;
+}
+struct WindowCount {     // scratch need of a window: ncand * (len bytes rounded to 4 + 12) / 4 words
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B&) const {
+        const Dev& d = w.d;
+        if (i >= w.NW) { w.wcand[i] = 0; return; }
+        int32_t s = w.win[2 * i], e = w.win[2 * i + 1];
+        int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
+        int64_t lo, term; window_range(w, k, s, e, &lo, &term);
+        int32_t n = 0;
+        for (int64_t r = lo; r < term; r++) if (d.r_hend[r] > e + 1) n++;
+        int32_t len = d.colbase[e] - d.colbase[s] + 1;
+        int32_t words = (len + 3) / 4 + 3;
+        w.wcand[i] = (n + 2) * words;          // + the scratch string of the current read, + stale read
+    }
+};
+
+struct KmerVisitor {     // ss_parse_read_kmer's appends (kmercount.c:389-440)
+    const Dev* d; uint8_t* region; int32_t cap; int32_t length, del, qual; const uint8_t* q;
+    NP_HD void sym(int32_t col, uint32_t s, int32_t qpos, bool subgap) {
+        if (length < cap) region[length] = (uint8_t)s;
+        length++;
+        if (subgap) del++;
+        if (qpos >= 0) qual += q[qpos];
+        d->oflag[col] &= (uint8_t)~FLAG_ZERO;                     // flagzero == 0
+    }
+    NP_HD void overflow() { *d->err |= ERR_INS_OVERFLOW; }
+};
+
+struct WindowVote {      // ss_kmer_correct for one window (kmercount.c:188-253)
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B&) const {
+        const Dev& d = w.d;
+        int32_t s = w.win[2 * i], e = w.win[2 * i + 1];
+        int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
+        int32_t len = d.colbase[e] - d.colbase[s] + 1;
+        int32_t words = (len + 3) / 4 + 3;                         // string (len bytes) + num, mapq, qual
+        int32_t* base = w.wscratch + w.wsoff[i];
+        int32_t nslot = (w.wsoff[i + 1] - w.wsoff[i]) / words;     // >= candidates + 2
+        uint8_t* cur = (uint8_t*)(base + (size_t)(nslot - 1) * words);   // scratch string of the current read
+        int32_t nstr = 0, count = 0;
+        bool broke = false; int64_t ncand = 0;
+        int64_t lo, term; window_range(w, k, s, e, &lo, &term);
+        auto slot_str = [&](int32_t j) { return (uint8_t*)(base + (size_t)j * words); };
+        auto slot_tal = [&](int32_t j) { return base + (size_t)j * words + (len + 3) / 4; };
+        // ss_kmer_get_region (kmercount.c:332-363); returns the read's ks->mapqual after the call
+        auto get_region = [&](int64_t r) -> int32_t {
+            Rec rc = load_rec(d.rec, d.rec_off, r);
+            KmerVisitor v{&d, cur, len, 0, 0, 0, d.qual + (size_t)d.qual_off[r] * 16};
+            walk_read(rc, d.ctg_goff[k], s, e, d.r_qstart[r], d.r_qend[r], d.colbase, v);
+            int32_t q = (v.length > 0 && v.length != v.del) ? v.qual / (v.length - v.del) : 0;
+            if (v.length != len) return 0;
+            int32_t j = 0;
+            for (; j < nstr; j++) {
+                const uint8_t* a = slot_str(j); bool same = true;
+                for (int32_t t = 0; t < len; t++) if (a[t] != cur[t]) { same = false; break; }
+                if (same) break;
+            }
+            if (j == nstr) {
+                if (nstr >= nslot - 1) { *d.err |= ERR_REGION_SCRATCH; return 0; }
+                uint8_t* a = slot_str(j);
+                for (int32_t t = 0; t < len; t++) a[t] = cur[t];
+                int32_t* tl = slot_tal(j); tl[0] = 1; tl[1] = (int32_t)rc.mapq; tl[2] = q;
+                nstr++;
+            } else { int32_t* tl = slot_tal(j); tl[0]++; tl[1] += (int32_t)rc.mapq; tl[2] += q; }
+            return (int32_t)rc.mapq;
+        };
+        for (int64_t r = lo; r < term; r++) {
+            if (!(d.r_hend[r] > e + 1)) continue;
+            ncand++;
+            if (d.r_level[r] == 2) {
+                int32_t mq = get_region(r);
+                if (mq == 60) { count++; if (count >= d.P.max_count_kmer) { broke = true; break; } }
+            }
+        }
+        if (nstr == 0 && !broke && ncand > 0 && term < d.ctg_read_off[k + 1]) {
+            // kmercount.c:209-219: the stale record (the one that ended the first iterator) is
+            // filtered and parsed once per record the second iterator yields
+            if (d.r_level[term] == 1) for (int64_t t = 0; t < ncand; t++) get_region(term);
+        }
+        int32_t best = -1;
+        if (nstr > 0) {
+            if (count == d.P.max_count_kmer) {
+                int32_t want = 60 * count;
+                for (int32_t j = 0; j < nstr; j++) if (slot_tal(j)[1] == want) { best = j; break; }
+            }
+            if (best < 0) {
+                best = 0;
+                for (int32_t j = 0; j < nstr; j++) {
+                    const int32_t *a = slot_tal(best), *b = slot_tal(j);
+                    bool less = a[0] != b[0] ? a[0] < b[0] : a[1] != b[1] ? a[1] < b[1] : a[2] < b[2];   // ks_compare
+                    if (j != best && less) best = j;
+                }
+            }
+        }
+        w.wbest[i] = best < 0 ? -1 : (int32_t)(w.wsoff[i] + best * words);
+    }
+};
+struct WindowApply {     // contig_update_contig in window order: a later window wins shared columns
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B&) const {
+        const Dev& d = w.d;
+        if (w.wbest[i] < 0) return;
+        int32_t s = w.win[2 * i], e = w.win[2 * i + 1];
+        const uint8_t* str = (const uint8_t*)(w.wscratch + w.wbest[i]);
+        int32_t c0 = d.colbase[s], c1 = d.colbase[e];
+        bool next_shares = i + 1 < w.NW && w.win[2 * (i + 1)] == e && w.wbest[i + 1] >= 0;
+        for (int32_t c = c0; c <= c1; c++) {
+            if (c == c1 && next_shares) break;
+            d.obase[c] = str[c - c0];
+        }
+    }
+};
+
+// ---- orchestration ------------------------------------------------------------------------------
+template <class BE>
+int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
+    Dev2 w; memset(&w, 0, sizeof(w));
+    Dev& d = w.d; d = d0;
+    const int64_t R = d.n_reads; const int32_t G = d.G;
+    d.task = 2;
+    d.err = be.template buf<int32_t>("err", 1);
+    be.zero(d.err, sizeof(int32_t));
+    d.r_ctg = be.template buf<int32_t>("r_ctg", R + 1);
+    d.r_gpos = be.template buf<int32_t>("r_gpos", R + 1);
+    d.r_qstart = be.template buf<int32_t>("r_qstart", R + 1);
+    d.r_qend = be.template buf<int32_t>("r_qend", R + 1);
+    d.r_wend = be.template buf<int32_t>("r_wend", R + 1);
+    d.r_hend = be.template buf<int32_t>("r_hend", R + 1);
+    d.r_pm = be.template buf<int32_t>("r_pm", R + 1);
+    w.r_hpm = be.template buf<int32_t>("r_hpm", R + 1);
+    d.r_level = be.template buf<uint8_t>("r_level", R + 1);
+    d.ins = be.template buf<int32_t>("ins", (size_t)G + 1);
+    d.ncol = be.template buf<int32_t>("ncol", (size_t)G + 1);
+    d.colbase = be.template buf<int32_t>("colbase", (size_t)G + 1);
+    d.out_off = be.template buf<int64_t>("out_off", (size_t)d.n_ctg + 1);
+    be.zero(d.ins, sizeof(int32_t) * ((size_t)G + 1));
+    if (R > 0) {
+        be.launch("read_prep", R, ReadPrep{d});
+        be.inclmax_i32(d.r_hend, w.r_hpm, R);
+    }
+    // lowercase runs and region lists
+    w.rs_flag = be.template buf<int32_t>("rs_flag", (size_t)G + 2);
+    w.re_flag = be.template buf<int32_t>("re_flag", (size_t)G + 2);
+    w.rs_idx = be.template buf<int32_t>("rs_idx", (size_t)G + 2);
+    w.re_idx = be.template buf<int32_t>("re_idx", (size_t)G + 2);
+    be.launch("run_flags", (int64_t)G + 1, RunFlags{w});
+    be.exscan_i32(w.rs_flag, w.rs_idx, (int64_t)G + 1);
+    be.exscan_i32(w.re_flag, w.re_idx, (int64_t)G + 1);
+    w.n_runs = be.read_i32(w.rs_idx + G);
+    w.run_s = be.template buf<int32_t>("run_s", (size_t)w.n_runs + 1);
+    w.run_e = be.template buf<int32_t>("run_e", (size_t)w.n_runs + 1);
+    if (G > 0) be.launch("run_fill", G, RunFill{w});
+    size_t regcap = 2 * ((size_t)w.n_runs + (size_t)d.n_ctg + 2);
+    w.nd_reg = be.template buf<int32_t>("nd_reg", regcap);
+    w.km_reg = be.template buf<int32_t>("km_reg", regcap);
+    w.nd_cnt = be.template buf<int32_t>("nd_cnt", (size_t)d.n_ctg + 1);
+    w.km_cnt = be.template buf<int32_t>("km_cnt", (size_t)d.n_ctg + 1);
+    w.nd_off = be.template buf<int32_t>("nd_off", (size_t)d.n_ctg + 1);
+    w.km_off = be.template buf<int32_t>("km_off", (size_t)d.n_ctg + 1);
+    be.launch("contig_regions", d.n_ctg, ContigRegions{w});
+    be.exscan_i32(w.nd_cnt, w.nd_off, (int64_t)d.n_ctg + 1);
+    be.exscan_i32(w.km_cnt, w.km_off, (int64_t)d.n_ctg + 1);
+    w.NR_nd = be.read_i32(w.nd_off + d.n_ctg);
+    w.NR_km = be.read_i32(w.km_off + d.n_ctg);
+    w.ndl = be.template buf<int32_t>("ndl", 2 * (size_t)w.NR_nd + 2);
+    w.kml = be.template buf<int32_t>("kml", 2 * (size_t)w.NR_km + 2);
+    be.launch("compact_regions", d.n_ctg, CompactRegions{w});
+    // insertion columns inside regions only
+    w.indiff = be.template buf<int32_t>("indiff", (size_t)G + 2);
+    w.inreg = be.template buf<int32_t>("inreg", (size_t)G + 2);
+    be.zero(w.indiff, sizeof(int32_t) * ((size_t)G + 2));
+    if (w.NR_nd > 0) be.launch("region_diff_nd", w.NR_nd, RegionDiff{w, 0});
+    if (w.NR_km > 0) be.launch("region_diff_km", w.NR_km, RegionDiff{w, 1});
+    be.inclsum_i32(w.indiff, w.inreg, (int64_t)G + 2);
+    if (R > 0) be.launch("insert_len2", R, InsertLen2{w});
+    be.launch("ncol", (int64_t)G + 1, NcolFromIns{d});
+    be.exscan_i32(d.ncol, d.colbase, (int64_t)G + 1);
+    d.C = be.read_i32(d.colbase + G);
+    const int32_t C = d.C;
+    d.refsym = be.template buf<uint8_t>("refsym", (size_t)C + 1);
+    d.cflag = be.template buf<uint8_t>("cflag", (size_t)C + 1);
+    d.obase = be.template buf<uint8_t>("obase", (size_t)C + 1);
+    d.oflag = be.template buf<uint8_t>("oflag", (size_t)C + 1);
+    d.colpos = be.template buf<int32_t>("colpos", (size_t)C + 1);
+    d.keepi = be.template buf<int32_t>("keepi", (size_t)C + 1);
+    d.keepidx = be.template buf<int32_t>("keepidx", (size_t)C + 1);
+    w.ndmark = be.template buf<int32_t>("ndmark", (size_t)C + 2);
+    w.ndidx = be.template buf<int32_t>("ndidx", (size_t)C + 2);
+    w.vcap = be.template buf<int32_t>("vcap", (size_t)C + 2);
+    w.koff = be.template buf<int32_t>("koff", (size_t)C + 2);
+    if (G > 0) {
+        be.launch("col_init", G, ColInit{d});
+        be.launch("col_ends", d.n_ctg, ColEnds{d});
+    }
+    if (C > 0) be.launch("col_init2", C, ColInit2{w});
+    // no-depth regions
+    if (w.NR_nd > 0) {
+        be.launch("nodepth_count", w.NR_nd, NodepthCount{w});
+        be.exscan_i32(w.ndmark, w.ndidx, (int64_t)C + 1);
+        be.exscan_i32(w.vcap, w.koff, (int64_t)C + 1);
+        w.NRC = be.read_i32(w.ndidx + C);
+        int32_t KE = be.read_i32(w.koff + C);
+        size_t nrc = (size_t)w.NRC + 1;
+        w.ktab2 = be.template buf<uint32_t>("ktab2", (size_t)KE + 1);
+        w.nk2 = be.template buf<int32_t>("nk2", nrc);
+        w.cnt2 = be.template buf<uint32_t>("cnt2", nrc);
+        w.refk2 = be.template buf<uint16_t>("refk2", nrc);
+        w.sc2 = be.template buf<double>("sc2", nrc * 16);
+        w.kc2 = be.template buf<uint16_t>("kc2", nrc * 16);
+        w.ord2 = be.template buf<uint8_t>("ord2", nrc * 16);
+        w.ns2 = be.template buf<uint8_t>("ns2", nrc);
+        w.subbuf = be.template buf<int32_t>("subbuf", nrc + 2 * (size_t)w.NR_nd + 4);
+        int32_t e1 = be.read_i32(d.err);
+        if (e1) return e1;
+        be.launch("nodepth_score", w.NR_nd, NodepthScore{w});
+    }
+    // windows
+    w.NW = 0;
+    if (w.NR_km > 0) {
+        w.wcnt = be.template buf<int32_t>("wcnt", (size_t)w.NR_km + 1);
+        w.woff = be.template buf<int32_t>("woff", (size_t)w.NR_km + 1);
+        be.launch("split_count", (int64_t)w.NR_km + 1, SplitCount{w});
+        be.exscan_i32(w.wcnt, w.woff, (int64_t)w.NR_km + 1);
+        w.NW = be.read_i32(w.woff + w.NR_km);
+        w.win = be.template buf<int32_t>("win", 2 * (size_t)w.NW + 2);
+        be.launch("split_fill", w.NR_km, SplitFill{w});
+        w.wcand = be.template buf<int32_t>("wcand", (size_t)w.NW + 1);
+        w.wsoff = be.template buf<int32_t>("wsoff", (size_t)w.NW + 1);
+        w.wbest = be.template buf<int32_t>("wbest", (size_t)w.NW + 1);
+        be.launch("window_count", (int64_t)w.NW + 1, WindowCount{w});
+        be.exscan_i32(w.wcand, w.wsoff, (int64_t)w.NW + 1);
+        int32_t WS = be.read_i32(w.wsoff + w.NW);
+        w.wscratch = be.template buf<int32_t>("wscratch", (size_t)WS + 4);
+        be.launch("window_vote", w.NW, WindowVote{w});
+        be.launch("window_apply", w.NW, WindowApply{w});
+    }
+    be.launch("keep_flag", (int64_t)C + 1, KeepFlag{d});
+    be.exscan_i32(d.keepi, d.keepidx, (int64_t)C + 1);
+    int32_t total = be.read_i32(d.keepidx + C);
+    d.out = be.template buf<uint8_t>("out", (size_t)total + 1);
+    if (C > 0) be.launch("emit", C, Emit{d, (uint8_t)FLAG_ZERO});
+    be.launch("out_offsets", (int64_t)d.n_ctg + 1, OutOffsets{d});
+    int32_t err = be.read_i32(d.err);
+    if (st) { st->C = C; st->T = w.NW; st->sym_words = w.NR_nd; st->table_entries = w.NR_km; st->out_bytes = total; }
+    d0 = d;
+    return err;
+}
+
+}  // namespace npe

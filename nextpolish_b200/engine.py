@@ -14,7 +14,7 @@ from . import binding  # noqa: F401  (re-exported: engine.binding)
 from .binding import Configure, ShardView, SynthParams
 
 _LIB = None
-TASKS = (1,)   # task steps the device engine implements (1 = score_chain, 2 = kmer_count)
+TASKS = (1, 2)  # task steps the device engine implements (1 = score_chain, 2 = kmer_count)
 
 
 def lib():

@@ -9,13 +9,14 @@
 #include <map>
 #include <string>
 #include <vector>
-#include "../../nextpolish_b200/csrc/engine_impl.h"
+#include "../../nextpolish_b200/csrc/engine_task2.h"
 #include "../../include/nextpolish_b200.h"
 
 namespace {
 struct EmuOps {
     void atomic_max(int32_t* p, int32_t v) { if (*p < v) *p = v; }
     void atomic_or(uint32_t* p, uint32_t v) { *p |= v; }
+    void atomic_add(int32_t* p, int32_t v) { *p += v; }
 };
 struct EmuBackend {
     std::map<std::string, std::vector<uint8_t>> pool;
@@ -33,6 +34,10 @@ struct EmuBackend {
     void exscan_i32(const int32_t* in, int32_t* out, int64_t n) {
         int64_t s = 0;
         for (int64_t i = 0; i < n; i++) { int32_t v = in[i]; out[i] = (int32_t)s; s += v; }
+    }
+    void inclsum_i32(const int32_t* in, int32_t* out, int64_t n) {
+        int64_t s = 0;
+        for (int64_t i = 0; i < n; i++) { s += in[i]; out[i] = (int32_t)s; }
     }
     void inclmax_i32(const int32_t* in, int32_t* out, int64_t n) {
         int32_t m = INT32_MIN;
@@ -59,11 +64,11 @@ extern "C" int np_emu_run(const np_shard_view* v, int task, const Configure* cfg
     d.P.read_tlen = cfg->read_tlen;
     EmuBackend be;
     npe::RunStats st;
-    int err = task == 1 ? npe::run_score_chain(be, d, &st) : -100;
+    int err = task == 1 ? npe::run_score_chain(be, d, &st) : npe::run_kmer_count(be, d, &st);
     if (err) return err > 0 ? -err : err;
     if (st.out_bytes > out_cap) return -1000;
     memcpy(out_seq, d.out, (size_t)st.out_bytes);
     for (int i = 0; i <= v->n_contigs; i++) out_off[i] = d.out_off[i];
-    if (stats) { stats[0] = st.C; stats[1] = st.T; stats[2] = (int32_t)st.table_entries; }
+    if (stats) { stats[0] = st.C; stats[1] = st.T; stats[2] = (int32_t)st.table_entries; stats[3] = (int32_t)st.sym_words; }
     return 0;
 }

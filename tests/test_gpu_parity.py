@@ -38,16 +38,37 @@ def test_gpu_matches_oracle_on_synthetic(E, oracle, eng, case):
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_gpu_matches_reference_md5(E, eng, case):
-    """Against the committed md5s of the reference binary's own output."""
+def test_gpu_matches_reference_md5(E, eng, synth_files, case):
+    """Against the committed md5s of the reference binary's own output (BAM path: read_tlen is
+    estimated from the BAM head exactly like config_init does)."""
     want = json.load(open(os.path.join(GOLDEN, "synth_md5.json")))[case]
-    sh = E.Shard.synthetic(E.synth_params(**CASES[case]), 0, CASES[case]["n_contigs"], with_qual=True)
-    cfg = E.default_config(b"")
+    fa, bam = synth_files(case)
+    sh = E.Shard.load(fa, bam, with_qual=True)
+    cfg = E.default_config(fa, bam)
     for task in tasks(E):
-        # read_tlen comes from the BAM head in the reference run: reproduce it for task 2
-        got = eng.polish(sh, task, cfg) if task == 1 else None
-        if got is not None:
-            assert {"%s_%d" % (n, task): md5(s) for n, s in got.items()} == want[str(task)]
+        got = eng.polish(sh, task, cfg)
+        assert {"%s_%d" % (n, task): md5(s) for n, s in got.items()} == want[str(task)], task
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23, 24])
+def test_gpu_matches_oracle_mutated_thresholds(E, oracle, eng, seed):
+    import random
+    rng = random.Random(seed)
+    kw = dict(seed=rng.randrange(1 << 30), n_contigs=rng.choice([2, 5]), contig_len=rng.choice([8000, 20000]),
+              depth=rng.choice([5, 12, 30, 60]), draft_indel=rng.choice([0.003, 0.02]), read_indel=rng.choice([0.0001, 0.003]),
+              lowercase_frac=rng.choice([0.01, 0.05, 0.15]))
+    sh = E.Shard.synthetic(E.synth_params(**kw), 0, kw["n_contigs"], with_qual=True)
+    cfg = E.default_config(b"")
+    c = cfg.contents
+    c.read_tlen = 2000
+    c.trim_len_edge, c.ext_len_edge = rng.choice([0, 1, 2, 4]), rng.choice([0, 1, 2, 3])
+    c.min_len_ldr, c.min_len_inter_kmer = rng.choice([1, 3, 6]), rng.choice([0, 2, 5, 9])
+    c.max_len_kmer, c.max_count_kmer, c.min_map_quality = rng.choice([10, 50, 120]), rng.choice([3, 50]), rng.choice([0, 30])
+    c.indel_balance_factor_sgs, c.min_count_ratio_skip = rng.choice([0.5, 0.25, 0.75]), rng.choice([0.8, 0.6, 0.95])
+    for task in tasks(E):
+        want = run_checker(oracle.np_oracle_run, sh, task, cfg)
+        got = eng.polish(sh, task, cfg)
+        assert got == want, task
 
 
 def test_gpu_matches_golden_testdata(E, eng):
@@ -62,18 +83,19 @@ def test_gpu_matches_golden_testdata(E, eng):
             assert s == exp["%s_%d" % (n, step)], (step, n)
 
 
-def test_reference_abi_score_chain(E):
-    """The drop-in entry point itself: score_chain(tigname, cfg) -> PolishResult*."""
-    fa = os.path.join(GOLDEN, "td30.step1.fa")
-    bam = os.path.join(GOLDEN, "td30.step1.bam")
-    exp = read_fasta(os.path.join(GOLDEN, "td30.step1.expected.fa"))
+@pytest.mark.parametrize("step,fn", [(1, "score_chain"), (2, "kmer_count")])
+def test_reference_abi_entry_points(E, step, fn):
+    """The drop-in entry points themselves: score_chain / kmer_count(tigname, cfg) -> PolishResult*."""
+    fa = os.path.join(GOLDEN, "td30.step%d.fa" % step)
+    bam = os.path.join(GOLDEN, "td30.step%d.bam" % step)
+    exp = read_fasta(os.path.join(GOLDEN, "td30.step%d.expected.fa" % step))
     L = E.lib()
     cfg = L.config_init(fa.encode(), bam.encode(), None)
     for name in [n[:-2] for n in exp]:
-        res = L.score_chain(name.encode(), cfg)
+        res = getattr(L, fn)(name.encode(), cfg)
         seq = C.string_at(res.contents.contig)
         assert res.contents.length == len(seq)
-        assert seq == exp[name + "_1"]
+        assert seq == exp["%s_%d" % (name, step)]
         L.polishresult_destory(res)
     L.config_destory(cfg)
 
@@ -81,10 +103,11 @@ def test_reference_abi_score_chain(E):
 def test_native_cli_matches_reference_binary(E, tmp_path):
     """nextpolish1 scorechain <fa> <bam> (our CLI) vs the reference binary, byte for byte."""
     cli = os.path.join(os.path.dirname(E.binding.LIB_PATH), "nextpolish1")
-    fa = os.path.join(GOLDEN, "td30.step1.fa")
-    bam = os.path.join(GOLDEN, "td30.step1.bam")
-    ours = subprocess.run([cli, "scorechain", fa, bam], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
-    assert ours == open(os.path.join(GOLDEN, "td30.step1.expected.fa"), "rb").read()
+    for step, cmd in ((1, "scorechain"), (2, "kmercount")):
+        fa = os.path.join(GOLDEN, "td30.step%d.fa" % step)
+        bam = os.path.join(GOLDEN, "td30.step%d.bam" % step)
+        ours = subprocess.run([cli, cmd, fa, bam], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+        assert ours == open(os.path.join(GOLDEN, "td30.step%d.expected.fa" % step), "rb").read(), cmd
 
 
 def test_e2e_host_call_equals_resident_path(E, eng):

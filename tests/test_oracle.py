@@ -55,3 +55,47 @@ def test_oracle_vs_live_reference(E, oracle, tmp_path, step, cmd):
     got = run_checker(oracle.np_oracle_run, sh, step, cfg)
     for n, s in got.items():
         assert s == exp["%s_%d" % (n, step)], n
+
+
+REF_SO = os.path.join(os.path.dirname(REF_BIN), "nextpolish1.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_oracle_vs_reference_so_with_mutated_thresholds(E, oracle, tmp_path, seed):
+    """Calls the reference's own score_chain/kmer_count (oracle/_ref/nextpolish1.so, through the same
+    ctypes declarations nextpolish1.py uses) with non-default Configure fields, like update_cfg does."""
+    import ctypes as C
+    import random
+    from nextpolish_b200.binding import Configure, PolishResult
+    R = C.CDLL(REF_SO)
+    R.config_init.argtypes = [C.c_char_p] * 3
+    R.config_init.restype = C.POINTER(Configure)
+    for f in ("score_chain", "kmer_count"):
+        getattr(R, f).argtypes = [C.c_char_p, C.POINTER(Configure)]
+        getattr(R, f).restype = C.POINTER(PolishResult)
+    R.polishresult_destory.argtypes = [C.POINTER(PolishResult)]
+    rng = random.Random(seed)
+    kw = dict(seed=rng.randrange(1 << 30), n_contigs=rng.choice([1, 3]), contig_len=rng.choice([3000, 8000, 20000]),
+              depth=rng.choice([2, 5, 12, 30, 60]), draft_snv=rng.choice([0.001, 0.01]), draft_indel=rng.choice([0.003, 0.02]),
+              read_sub=rng.choice([0.002, 0.02]), read_indel=rng.choice([0.0001, 0.003]), lowercase_frac=rng.choice([0.01, 0.05, 0.15]))
+    fa, bam = str(tmp_path / "x.fa"), str(tmp_path / "x.bam")
+    assert E.lib().np_synth_write(E.synth_params(**kw), fa.encode(), bam.encode()) == 0
+    subprocess.check_call([REF_SAMTOOLS, "index", bam])
+    sh = E.Shard.load(fa, bam, with_qual=True)
+    cfg, rcfg = E.default_config(fa, bam), R.config_init(fa.encode(), bam.encode(), None)
+    assert (cfg.contents.read_tlen, cfg.contents.read_len) == (rcfg.contents.read_tlen, rcfg.contents.read_len)
+    vals = dict(trim_len_edge=rng.choice([1, 2, 4]), ext_len_edge=rng.choice([1, 2, 3]), min_len_ldr=rng.choice([1, 3, 6]),
+                min_len_inter_kmer=rng.choice([0, 2, 5, 9]), max_len_kmer=rng.choice([10, 50, 120]), max_count_kmer=rng.choice([3, 50]),
+                min_map_quality=rng.choice([0, 30]), indel_balance_factor_sgs=rng.choice([0.5, 0.25, 0.75]),
+                min_count_ratio_skip=rng.choice([0.8, 0.6, 0.95]))
+    for k, v in vals.items():
+        setattr(cfg.contents, k, v)
+        setattr(rcfg.contents, k, v)
+    for task, fn in ((1, R.score_chain), (2, R.kmer_count)):
+        want = run_checker(oracle.np_oracle_run, sh, task, cfg)
+        for n in sh.names:
+            res = fn(n.encode(), rcfg)
+            seq = C.string_at(res.contents.contig)
+            R.polishresult_destory(res)
+            assert seq == want[n], (task, n, vals)
