@@ -194,6 +194,10 @@ const uint8_t* np_engine_result_device(np_engine* e);
 int32_t np_engine_kernel_times(np_engine* e, const char** names, float* ms, int32_t cap);
 /* Number of kernel launches issued by the last np_engine_run. */
 int32_t np_engine_launch_count(np_engine* e);
+/* Fused pileup-scan kernel statistics of the last task-1 run:
+ * {window size W, windows, shared-memory bytes per CTA, windows with unresolved stretches,
+ *  columns handled by the general (global-memory) kernels}. */
+int32_t np_engine_window_stats(np_engine* e, int32_t* out5);
 /* The stream the engine launches on (cudaStream_t as void*). */
 void*   np_engine_stream(np_engine* e);
 

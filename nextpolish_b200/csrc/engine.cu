@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "engine_task2.h"
+#include "engine_v2.h"
 #include "errors.h"
 #include "hostio.h"
 #include "../../include/nextpolish_b200.h"
@@ -37,6 +38,13 @@ struct CudaOps {
         (void)p; (void)v;
 #endif
     }
+    __host__ __device__ __forceinline__ int32_t atomic_add_ret(int32_t* p, int32_t v) {
+#ifdef __CUDA_ARCH__
+        return atomicAdd(p, v);
+#else
+        (void)p; (void)v; return 0;
+#endif
+    }
     __host__ __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) {
 #ifdef __CUDA_ARCH__
         atomicOr(p, v);
@@ -50,6 +58,63 @@ template <class F>
 __global__ void __launch_bounds__(256) k_items(int64_t n, F f) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { CudaOps ops; f(i, ops); }
+}
+
+// ---- fused window kernel: one CTA per pileup window, records staged by one 1-D bulk copy (TMA) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    } while (!done);
+}
+
+constexpr int kWinThreads = 128;
+
+__global__ void __launch_bounds__(kWinThreads) k_window(npe::Dev d, npw::WinGlobals g) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    npw::WCtx x; x.d = d; x.g = g;
+    npw::win_setup(x, (int32_t)blockIdx.x, smem);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    CudaOps ops;
+    const uint32_t bar = smem_u32(smem);
+    const uint32_t recbytes = (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && recbytes) {
+        mbar_expect_tx(bar, recbytes);
+        const uint8_t* src = d.rec + (size_t)d.rec_off[x.rlo] * 16;
+        // one bulk copy per <= 64 KiB piece keeps each transfer's byte count small
+        uint32_t done = 0;
+        while (done < recbytes) {
+            uint32_t piece = recbytes - done > 65536u ? 65536u : recbytes - done;
+            bulk_g2s(smem_u32(x.rec) + done, src + done, piece, bar);
+            done += piece;
+        }
+    }
+    // overlap with the copy: record offsets, clears, draft symbols
+    uint32_t* ro = const_cast<uint32_t*>(x.recoff);
+    for (int i = tid; i <= x.nr; i += nt) ro[i] = d.rec_off[x.rlo + i];
+    npw::ph_clear(x, tid, nt);
+    __syncthreads();
+    npw::ph_ref(x, tid, nt, ops);
+    if (recbytes) mbar_wait(bar, 0);
+    __syncthreads();
+    NP_WINDOW_PHASES(x, tid, nt, ops, __syncthreads())
 }
 
 struct MaxOp { __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; } };
@@ -144,6 +209,29 @@ struct CudaBackend {
         launches += 2;
         end_timed();
     }
+    const int32_t* upload_i32(const char* name, const int32_t* h, size_t n) {
+        int32_t* p = buf<int32_t>(name, n + 1);
+        if (ok && n) {
+            // staged through a pinned bounce buffer so the async copy is legal for pageable vectors
+            CUDA_TRY(cudaMemcpyAsync(p, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        }
+        return p;
+    }
+    void run_windows(const npe::Dev& d, const npw::WinGlobals& g, int32_t smem_bytes) {
+        if (!ok) return;
+        static int32_t attr_set = 0;
+        int32_t want = smem_bytes + 256;
+        if (want > attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+            attr_set = want;
+        }
+        begin_timed("pileup_scan");
+        k_window<<<(unsigned)g.n_win, kWinThreads, (size_t)want, stream>>>(d, g);
+        CUDA_TRY(cudaGetLastError());
+        launches++;
+        end_timed();
+    }
     int32_t read_i32(const int32_t* p) {
         if (!ok) return 0;
         CUDA_TRY(cudaMemcpyAsync(h_scalar, p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -181,6 +269,7 @@ struct np_engine {
     CudaBackend be;
     npe::Dev d;
     npe::RunStats st;
+    npe::V2Stats vs{};
     bool resident = false, owns_shard = false;
     std::vector<int64_t> h_ctg_off, h_read_off;
     // device copies of the shard (when uploaded)
@@ -302,7 +391,11 @@ int32_t np_engine_run(np_engine* e, int32_t task, const Configure* cfg) {
     params_from_cfg(cfg, &e->d.P);
     e->be.n_timed = 0; e->be.launches = 0;
     int err;
-    if (task == NP_TASK_SCORE_CHAIN) err = npe::run_score_chain(e->be, e->d, &e->st);
+    if (task == NP_TASK_SCORE_CHAIN) {
+        const char* v1 = getenv("NEXTPOLISH_B200_GENERAL_KERNELS");     // debugging / A-B timing only
+        if (v1 && v1[0] == '1') err = npe::run_score_chain(e->be, e->d, &e->st);
+        else err = npe::run_score_chain_v2(e->be, e->d, e->h_ctg_off.data(), &e->st, &e->vs);
+    }
     else if (task == NP_TASK_KMER_COUNT) {
         if (!e->d.qual || !e->d.qual_off) { np::set_error("np_engine_run: task 2 needs the quality stream (load the shard with_qual)"); return NP_ERR_ARG; }
         err = npe::run_kmer_count(e->be, e->d, &e->st);
@@ -338,6 +431,12 @@ int32_t np_engine_download(np_engine* e, uint8_t* out_seq, int64_t out_cap, int6
     cudaMemcpyAsync(out_off, e->d.out_off, ((size_t)e->d.n_ctg + 1) * 8, cudaMemcpyDeviceToHost, s);
     cudaError_t er = cudaStreamSynchronize(s);
     if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
+    return NP_OK;
+}
+
+int32_t np_engine_window_stats(np_engine* e, int32_t* out5) {
+    if (!e) return NP_ERR_ARG;
+    out5[0] = e->vs.W; out5[1] = e->vs.n_win; out5[2] = e->vs.smem; out5[3] = e->vs.unresolved_windows; out5[4] = e->vs.fallback_cols;
     return NP_OK;
 }
 

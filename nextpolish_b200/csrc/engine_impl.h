@@ -119,10 +119,10 @@ struct ColEnds {   // mark first / last column of every contig
 };
 
 struct SymBound {  // words needed for the read's column string (+1 pad word)
-    Dev d;
+    Dev d; const uint8_t* need = nullptr;   // optional: only reads with need[r] != 0
     template <class B> NP_HD void operator()(int64_t r, B&) const {
         int32_t words = 0;
-        if (r < d.n_reads && d.r_level[r] >= 1) {
+        if (r < d.n_reads && d.r_level[r] >= 1 && (!need || need[r])) {
             int32_t k = d.r_ctg[r];
             int32_t gs = d.ctg_goff[k], ge = d.ctg_goff[k + 1] - 1;
             int32_t a = d.r_gpos[r], b = d.r_wend[r] - 1;

@@ -175,6 +175,11 @@ class Engine:
         n = lib().np_engine_kernel_times(self.h, names, ms, cap)
         return [(names[i].decode(), ms[i]) for i in range(n)]
 
+    def window_stats(self):
+        a = (C.c_int32 * 5)()
+        lib().np_engine_window_stats(self.h, a)
+        return dict(zip(("W", "n_win", "smem_bytes", "unresolved_windows", "fallback_cols"), list(a)))
+
     def launch_count(self):
         return lib().np_engine_launch_count(self.h)
 

@@ -67,6 +67,8 @@ def emu():
     srcs = [os.path.join(ROOT, "tests", "emu", "emu_engine.cpp"),
             os.path.join(ROOT, "nextpolish_b200", "csrc", "engine_impl.h"),
             os.path.join(ROOT, "nextpolish_b200", "csrc", "engine_task2.h"),
+            os.path.join(ROOT, "nextpolish_b200", "csrc", "engine_v2.h"),
+            os.path.join(ROOT, "nextpolish_b200", "csrc", "window_kernel.h"),
             os.path.join(ROOT, "nextpolish_b200", "csrc", "device_logic.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]])

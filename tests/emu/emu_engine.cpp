@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include "../../nextpolish_b200/csrc/engine_task2.h"
+#include "../../nextpolish_b200/csrc/engine_v2.h"
 #include "../../include/nextpolish_b200.h"
 
 namespace {
@@ -17,6 +18,7 @@ struct EmuOps {
     void atomic_max(int32_t* p, int32_t v) { if (*p < v) *p = v; }
     void atomic_or(uint32_t* p, uint32_t v) { *p |= v; }
     void atomic_add(int32_t* p, int32_t v) { *p += v; }
+    int32_t atomic_add_ret(int32_t* p, int32_t v) { int32_t o = *p; *p += v; return o; }
 };
 struct EmuBackend {
     std::map<std::string, std::vector<uint8_t>> pool;
@@ -44,11 +46,39 @@ struct EmuBackend {
         for (int64_t i = 0; i < n; i++) { m = std::max(m, in[i]); out[i] = m; }
     }
     int32_t read_i32(const int32_t* p) { return *p; }
+    const int32_t* upload_i32(const char* name, const int32_t* h, size_t n) {
+        int32_t* p = buf<int32_t>(name, n + 1);
+        if (n) memcpy(p, h, n * sizeof(int32_t));
+        return p;
+    }
+    void run_windows(const npe::Dev& d, const npw::WinGlobals& g, int32_t smem_bytes) {
+        std::vector<uint8_t> smem((size_t)smem_bytes + 256);
+        EmuOps ops;
+        for (int32_t w = 0; w < g.n_win; w++) {
+            memset(smem.data(), 0xA5, smem.size());          // poison: phases must initialise what they read
+            npw::WCtx x; x.d = d; x.g = g;
+            npw::win_setup(x, w, smem.data());
+            if ((int32_t)npw::win_smem_bytes(x.nr, (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u, x.ncols, x.strw, x.tmax) > smem_bytes) abort();
+            uint32_t recbytes = (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u;
+            memcpy(x.rec, d.rec + (size_t)d.rec_off[x.rlo] * 16, recbytes);                 // stands for the bulk copy
+            memcpy((void*)x.recoff, d.rec_off + x.rlo, 4 * (size_t)(x.nr + 1));
+            npw::ph_clear(x, 0, 1);
+            npw::ph_ref(x, 0, 1, ops);
+            NP_WINDOW_PHASES(x, 0, 1, ops, (void)0)
+        }
+    }
 };
 }  // namespace
 
+extern "C" int np_emu_run_impl(const np_shard_view* v, int task, const Configure* cfg,
+                          uint8_t* out_seq, int64_t out_cap, int64_t* out_off, int32_t* stats, int variant);
 extern "C" int np_emu_run(const np_shard_view* v, int task, const Configure* cfg,
                           uint8_t* out_seq, int64_t out_cap, int64_t* out_off, int32_t* stats) {
+    return np_emu_run_impl(v, task, cfg, out_seq, out_cap, out_off, stats, 1);
+}
+// variant 1: general kernels (engine_impl.h); variant 2: fused window kernel + fallback (engine_v2.h)
+extern "C" int np_emu_run_impl(const np_shard_view* v, int task, const Configure* cfg,
+                          uint8_t* out_seq, int64_t out_cap, int64_t* out_off, int32_t* stats, int variant) {
     npe::Dev d;
     memset(&d, 0, sizeof(d));
     std::vector<int32_t> goff((size_t)v->n_contigs + 1);
@@ -64,11 +94,14 @@ extern "C" int np_emu_run(const np_shard_view* v, int task, const Configure* cfg
     d.P.read_tlen = cfg->read_tlen;
     EmuBackend be;
     npe::RunStats st;
-    int err = task == 1 ? npe::run_score_chain(be, d, &st) : npe::run_kmer_count(be, d, &st);
+    npe::V2Stats vs; memset(&vs, 0, sizeof(vs));
+    int err = task == 1 ? (variant == 2 ? npe::run_score_chain_v2(be, d, v->ctg_off, &st, &vs) : npe::run_score_chain(be, d, &st))
+                        : npe::run_kmer_count(be, d, &st);
     if (err) return err > 0 ? -err : err;
     if (st.out_bytes > out_cap) return -1000;
     memcpy(out_seq, d.out, (size_t)st.out_bytes);
     for (int i = 0; i <= v->n_contigs; i++) out_off[i] = d.out_off[i];
+    if (stats && variant == 2) { stats[4] = vs.W; stats[5] = vs.n_win; stats[6] = vs.smem; stats[7] = vs.unresolved_windows; }
     if (stats) { stats[0] = st.C; stats[1] = st.T; stats[2] = (int32_t)st.table_entries; stats[3] = (int32_t)st.sym_words; }
     return 0;
 }

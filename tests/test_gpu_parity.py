@@ -156,3 +156,27 @@ def test_gpu_vs_live_reference_binary(E, eng, tmp_path):
         got = eng.polish(sh, task, cfg)
         for n, s in got.items():
             assert s == exp["%s_%d" % (n, task)], (task, n)
+
+
+def test_general_kernels_equal_fused_kernel(E, eng):
+    """A/B: the fused window kernel (default) and the general global-memory kernels give identical
+    sequences; the fused path resolves plain 30x data without any fallback column."""
+    sh = E.Shard.synthetic(E.synth_params(seed=31, n_contigs=3, contig_len=200000, depth=30.0), 0, 3)
+    cfg = E.default_config(b"")
+    a = eng.polish(sh, 1, cfg)
+    ws = eng.window_stats()
+    assert ws["n_win"] > 0 and ws["fallback_cols"] == 0, ws
+    os.environ["NEXTPOLISH_B200_GENERAL_KERNELS"] = "1"
+    try:
+        b = eng.polish(sh, 1, cfg)
+    finally:
+        del os.environ["NEXTPOLISH_B200_GENERAL_KERNELS"]
+    assert a == b
+
+
+def test_fused_kernel_deep_and_noisy_use_fallback_correctly(E, oracle, eng):
+    p = E.synth_params(seed=32, n_contigs=2, contig_len=60000, depth=200.0, draft_snv=0.01, draft_indel=0.02, read_sub=0.02, read_indel=0.004)
+    sh = E.Shard.synthetic(p, 0, 2)
+    cfg = E.default_config(b"")
+    want = run_checker(oracle.np_oracle_run, sh, 1, cfg)
+    assert eng.polish(sh, 1, cfg) == want
