@@ -128,18 +128,26 @@ NP_HD void walk_read(const Rec& r, int32_t gshift, int32_t start, int32_t end,
         int32_t len = cig_len(r.cigar[i]);
         int cur = cig_op(r.cigar[i]);
         if (cur == OP_M || cur == OP_D) {
-            for (int32_t j = 0; j < len; j++, pos++) {
-                if (pos >= start && pos <= end && qpos >= qstart && qpos <= qend) {
-                    if (last != OP_I && pos > start && (qpos > qstart || (qpos == qstart && last == OP_D))) {
-                        int32_t cb = colbase[pos - 1], n = colbase[pos] - cb - 1;
-                        for (int32_t k = 0; k < n; k++) v.sym(cb + 1 + k, (uint32_t)SYM_GAP, -1, true);
-                    }
-                    if (cur == OP_D) v.sym(colbase[pos], (uint32_t)SYM_GAP, -1, false);
-                    else v.sym(colbase[pos], seqi(r.seq, qpos), qpos, false);
+            // only bases with start <= pos <= end and qstart <= qpos <= qend cast anything: jump
+            // straight to that sub-run [ja, jb] of the op instead of stepping base by base
+            int32_t ja = pos < start ? start - pos : 0, jb = pos + len - 1 > end ? end - pos : len - 1;
+            if (cur == OP_M) {
+                if (qstart - qpos > ja) ja = qstart - qpos;
+                if (qend - qpos < jb) jb = qend - qpos;
+            } else if (qpos < qstart || qpos > qend) jb = ja - 1;
+            for (int32_t j = ja; j <= jb; j++) {
+                int32_t p = pos + j, q = cur == OP_M ? qpos + j : qpos;
+                int lastj = j == 0 ? last : cur;
+                if (lastj != OP_I && p > start && (q > qstart || (q == qstart && lastj == OP_D))) {
+                    int32_t cb = colbase[p - 1], n = colbase[p] - cb - 1;
+                    for (int32_t k = 0; k < n; k++) v.sym(cb + 1 + k, (uint32_t)SYM_GAP, -1, true);
                 }
-                if (cur != OP_D) qpos++;
-                last = cur;
+                if (cur == OP_D) v.sym(colbase[p], (uint32_t)SYM_GAP, -1, false);
+                else v.sym(colbase[p], seqi(r.seq, q), q, false);
             }
+            pos += len;
+            if (cur == OP_M) qpos += len;
+            if (len > 0) last = cur;
         } else if (cur == OP_I) {
             if (pos != gshift) {
                 bool in_reg = pos > start && pos <= end;

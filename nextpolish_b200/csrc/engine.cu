@@ -31,6 +31,13 @@ struct CudaOps {
         (void)p; (void)v;
 #endif
     }
+    __host__ __device__ __forceinline__ void atomic_min(int32_t* p, int32_t v) {
+#ifdef __CUDA_ARCH__
+        atomicMin(p, v);
+#else
+        (void)p; (void)v;
+#endif
+    }
     __host__ __device__ __forceinline__ void atomic_add(int32_t* p, int32_t v) {
 #ifdef __CUDA_ARCH__
         atomicAdd(p, v);

@@ -56,6 +56,8 @@ struct WCtx {             // per-window context: globals + carved shared memory
     int32_t win, k, gs, ge, p0, p1, e0, e1;   // contig, owned [p0,p1), extended [e0,e1)
     int32_t cb0, ncols, cown0, cown1;         // first ext column, #ext columns, owned local range [cown0,cown1)
     int32_t chr_end;                          // local column bound that a prev-window stretch may reach (HR rule)
+    int32_t lc_first, lc_last;                // local columns of the contig's first / last column
+    int32_t npos, nblk;                       // ext positions, 32-column blocks
     int32_t rlo, nr;                          // staged reads [rlo, rlo+nr)
     int32_t strw, tmax;                       // string pool words, table pool entries
     // shared memory
@@ -64,21 +66,27 @@ struct WCtx {             // per-window context: globals + carved shared memory
     uint32_t *str, *refw, *acc;               // string pool, draft symbol words, compare accumulators
     uint8_t* colinfo;                         // per local column: 1 mism, 2 covered, 4 table, 8 sub-column
     int16_t* tabidx;                          // per local column: table index or -1
-    TabEntry* tab;
+    int16_t* tabcol;                          // dense list: table index -> local column
+    int32_t* lcb;                             // [npos+1] local column of every ext position (staged colbase)
+    int32_t* blk;                             // [2*nblk] first / last+1 staged read overlapping each 32-column block
+    TabEntry* tab;                            // aliases the record area (records are dead after expand)
     int32_t* ctr;                             // [0] string words used, [1] tables used, [2] unresolved flag
 };
 
 NP_HD uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 // shared-memory bytes of a window with nr reads, recbytes of records, ncols ext columns
-NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int32_t strw, int32_t tmax) {
+NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int32_t strw, int32_t npos) {
     uint32_t b = 64;                                   // mbarrier + counters
-    b += align16(recbytes) + align16(4u * (uint32_t)(nr + 1));
+    uint32_t recarea = align16(recbytes);              // later re-used as the table pool
+    uint32_t mintab = (uint32_t)(ncols / 8 + 8) * (uint32_t)sizeof(TabEntry);
+    if (recarea < mintab) recarea = mintab;
+    b += recarea + align16(4u * (uint32_t)(nr + 1));
+    b += align16(4u * (uint32_t)(npos + 2)) + align16(8u * (uint32_t)(ncols / 32 + 2));
     b += 3 * align16(4u * (uint32_t)nr);
     b += align16(4u * (uint32_t)(strw + 4));
     b += 3 * align16(4u * (uint32_t)(ncols / 8 + 3));
     b += align16((uint32_t)ncols + 16);
-    b += align16(2u * (uint32_t)(ncols + 8));
-    b += (uint32_t)tmax * (uint32_t)sizeof(TabEntry);
+    b += 2 * align16(2u * (uint32_t)(ncols + 8));
     return b;
 }
 
@@ -101,12 +109,11 @@ struct WinPlan {
         for (int64_t r = lo; r < hi; r++) {
             int32_t a = d.r_gpos[r] < e0 ? e0 : d.r_gpos[r], b = d.r_wend[r] > e1 ? e1 : d.r_wend[r];
             int32_t span = b > a ? b - a : 0;
-            strw += (span + extra + 7) / 8 + 3;
+            strw += (span + extra + 7) / 8 + 2;
         }
         uint32_t recbytes = (d.rec_off[hi] - d.rec_off[lo]) * 16u;
-        int32_t tmax = ncols / 2 + 8;
         g.win_rlo[w] = (int32_t)lo; g.win_rhi[w] = (int32_t)hi; g.win_strw[w] = strw;
-        uint32_t need = win_smem_bytes((int32_t)(hi - lo), recbytes, ncols, strw, tmax);
+        uint32_t need = win_smem_bytes((int32_t)(hi - lo), recbytes, ncols, strw, e1 - e0);
         g.win_need[w] = (int32_t)need;
         be.atomic_max(g.maxneed, (int32_t)need);
     }
@@ -125,13 +132,20 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
     // a stretch handed over from the previous window must END before that window's extended range:
     int32_t pe = x.p0 + HR > x.ge + 1 ? x.ge + 1 : x.p0 + HR;
     x.chr_end = d.colbase[pe] - x.cb0;
+    x.lc_first = d.colbase[x.gs] - x.cb0; x.lc_last = d.colbase[x.ge] - x.cb0;
+    x.npos = x.e1 - x.e0; x.nblk = x.ncols / 32 + 1;
     x.rlo = x.g.win_rlo[w]; x.nr = x.g.win_rhi[w] - x.rlo;
-    x.strw = x.g.win_strw[w]; x.tmax = x.ncols / 2 + 8;
+    x.strw = x.g.win_strw[w];
     uint32_t recbytes = (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u;
+    uint32_t recarea = align16(recbytes), mintab = (uint32_t)(x.ncols / 8 + 8) * (uint32_t)sizeof(TabEntry);
+    if (recarea < mintab) recarea = mintab;
+    x.tmax = (int32_t)(recarea / sizeof(TabEntry));
     uint8_t* p = smem + 64;
     x.ctr = (int32_t*)(smem + 16);
-    x.rec = p; p += align16(recbytes);
+    x.rec = p; x.tab = (TabEntry*)p; p += recarea;
     x.recoff = (const uint32_t*)p; p += align16(4u * (uint32_t)(x.nr + 1));
+    x.lcb = (int32_t*)p; p += align16(4u * (uint32_t)(x.npos + 2));
+    x.blk = (int32_t*)p; p += align16(8u * (uint32_t)(x.ncols / 32 + 2));
     x.cs = (int32_t*)p; p += align16(4u * (uint32_t)x.nr);
     x.cn = (int32_t*)p; p += align16(4u * (uint32_t)x.nr);
     x.so = (int32_t*)p; p += align16(4u * (uint32_t)x.nr);
@@ -140,7 +154,7 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
     x.acc = (uint32_t*)p; p += 2 * align16(4u * (uint32_t)(x.ncols / 8 + 3));
     x.colinfo = p; p += align16((uint32_t)x.ncols + 16);
     x.tabidx = (int16_t*)p; p += align16(2u * (uint32_t)(x.ncols + 8));
-    x.tab = (TabEntry*)p;
+    x.tabcol = (int16_t*)p;
 }
 
 // ---- big-endian nibble strings -------------------------------------------------------------------
@@ -189,13 +203,15 @@ NP_HD void ph_clear(WCtx& x, int32_t tid, int32_t nt) {
     for (int32_t i = tid; i < x.ncols / 8 + 3; i += nt) { x.refw[i] = 0; x.acc[2 * i] = 0; x.acc[2 * i + 1] = 0; }
     for (int32_t i = tid; i < x.ncols + 16; i += nt) x.colinfo[i] = 0;
     for (int32_t i = tid; i < x.ncols + 8; i += nt) x.tabidx[i] = -1;
+    for (int32_t i = tid; i <= x.npos; i += nt) x.lcb[i] = x.d.colbase[x.e0 + i] - x.cb0;
+    for (int32_t i = tid; i < x.nblk; i += nt) { x.blk[2 * i] = 0x7fffffff; x.blk[2 * i + 1] = 0; }
     if (tid == 0) { x.ctr[0] = 0; x.ctr[1] = 0; x.ctr[2] = 0; }
 }
 template <class B>
 NP_HD void ph_ref(WCtx& x, int32_t tid, int32_t nt, B& be) {   // one thread per ext position
     const Dev& d = x.d;
     for (int32_t p = x.e0 + tid; p < x.e1; p += nt) {
-        int32_t lc = d.colbase[p] - x.cb0, n = d.colbase[p + 1] - d.colbase[p];
+        int32_t lc = x.lcb[p - x.e0], n = x.lcb[p - x.e0 + 1] - lc;
         uint32_t ch = d.ctg_seq[p];
         if (ch >= 97 && ch <= 122) ch -= 32;
         be.atomic_or(&x.refw[lc >> 3], base_code(ch) << (28 - ((lc & 7) << 2)));
@@ -210,18 +226,23 @@ NP_HD void ph_ref(WCtx& x, int32_t tid, int32_t nt, B& be) {   // one thread per
 // ---- phase 1: expand one read into its column string ----------------------------------------------
 // Emits the symbols of contig_parse_read (contig.c:247-331) at CIGAR-op granularity; only columns
 // inside the extended range are stored.
+NP_HD int32_t lcol(const WCtx& x, int32_t p) {     // local column of position p; virtual outside the range
+    int32_t i = p - x.e0;
+    if (i < 0) return i;
+    if (i > x.npos) return x.lcb[x.npos] + (i - x.npos);
+    return x.lcb[i];
+}
 struct StrWriter {
     WCtx* x; uint32_t* w; int32_t cap;        // string words of this read, capacity in nibbles
     int32_t cs, n;                            // local column of the first stored symbol, stored count
-    int32_t next;                             // next expected global column (contiguity)
+    int32_t next;                             // next expected local column (contiguity)
     bool started;
     const uint8_t* seq;
-    // a run of `len` columns starting at global column c: from seq[q..] (q >= 0) or constant gaps
-    NP_HD void run(int32_t c, int32_t len, int32_t q) {
+    // a run of `len` columns starting at local column lc: from seq[q..] (q >= 0) or constant gaps
+    NP_HD void run(int32_t lc, int32_t len, int32_t q) {
         if (len <= 0) return;
-        int32_t lc = c - x->cb0;
-        if (started && c != next) x->ctr[2] = 1;          // cannot happen (votes are contiguous)
-        next = c + len; started = true;
+        if (started && lc != next) x->ctr[2] = 1;         // cannot happen (votes are contiguous)
+        next = lc + len; started = true;
         int32_t skip = lc < 0 ? -lc : 0;                  // clip to the extended range
         if (skip >= len) return;
         lc += skip; len -= skip; if (q >= 0) q += skip;
@@ -254,7 +275,7 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
         int32_t wl, hl; ref_spans(rc, &wl, &hl);
         int32_t a = gpos < x.e0 ? x.e0 : gpos, b = gpos + wl > x.e1 ? x.e1 : gpos + wl;
         int32_t span = b > a ? b - a : 0, extra = x.ncols - (x.e1 - x.e0);
-        int32_t words = (span + extra + 7) / 8 + 3;
+        int32_t words = (span + extra + 7) / 8 + 2;
         int32_t off = be.atomic_add_ret(&x.ctr[0], words);
         if (off + words > x.strw + 4) { x.ctr[2] = 1; continue; }
         StrWriter sw{&x, x.str + off, (words - 1) * 8, 0, 0, 0, false, rc.seq};
@@ -276,19 +297,19 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
                     int lastj = ja == 0 ? last : OP_M;
                     int32_t q0 = qpos + ja, p_a = pos + ja;
                     bool fill0 = lastj != OP_I && p_a > start && (q0 > qstart || (q0 == qstart && lastj == OP_D));
-                    if (fill0) { int32_t cb = d.colbase[p_a - 1]; sw.run(cb + 1, d.colbase[p_a] - cb - 1, -1); }
+                    if (fill0) { int32_t cb = lcol(x, p_a - 1); sw.run(cb + 1, lcol(x, p_a) - cb - 1, -1); }
                     // copy segments between positions that carry sub-columns
                     int32_t j = ja;
                     while (j <= jb) {
-                        int32_t pj = pos + j, cj = d.colbase[pj];
+                        int32_t pj = pos + j, cj = lcol(x, pj);
                         int32_t kmax = jb - j + 1, run = 1;
-                        if (d.colbase[pj + kmax - 1] - cj == kmax - 1) run = kmax;          // no sub-columns inside
-                        else while (run < kmax && d.colbase[pj + run] - cj == run) run++;
+                        if (lcol(x, pj + kmax - 1) - cj == kmax - 1) run = kmax;          // no sub-columns inside
+                        else while (run < kmax && lcol(x, pj + run) - cj == run) run++;
                         sw.run(cj, run, qpos + j);
                         j += run;
                         if (j <= jb) {                                                    // sub-columns behind pos+j-1
-                            int32_t cb = d.colbase[pos + j - 1];
-                            sw.run(cb + 1, d.colbase[pos + j] - cb - 1, -1);
+                            int32_t cb = lcol(x, pos + j - 1);
+                            sw.run(cb + 1, lcol(x, pos + j) - cb - 1, -1);
                         }
                     }
                 }
@@ -300,17 +321,18 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
                         int lastj = ja == 0 ? last : OP_D;
                         int32_t p_a = pos + ja, p_b = pos + jb;
                         bool fill0 = lastj != OP_I && p_a > start && (qpos > qstart || (qpos == qstart && lastj == OP_D));
-                        int32_t c_from = fill0 ? d.colbase[p_a - 1] + 1 : d.colbase[p_a];
+                        int32_t c_from = fill0 ? lcol(x, p_a - 1) + 1 : lcol(x, p_a);
                         if (p_b > x.e1) p_b = x.e1;                    // clip far-right work
-                        if (p_b >= p_a) sw.run(c_from, d.colbase[p_b] - c_from + 1, -1);
+                        if (p_b >= p_a) sw.run(c_from, lcol(x, p_b) - c_from + 1, -1);
                     }
                 }
                 pos += len; last = OP_D;
             } else if (cur == OP_I) {
                 if (pos != x.gs) {
-                    bool in_reg = pos > start && pos <= end && pos <= x.e1;
+                    // sub-columns behind a position left of the range are not stored (virtual columns)
+                    bool in_reg = pos > start && pos <= end && pos - 1 >= x.e0 && pos <= x.e1;
                     if (in_reg) {
-                        int32_t cb = d.colbase[pos - 1], nsub = d.colbase[pos] - cb - 1;
+                        int32_t cb = lcol(x, pos - 1), nsub = lcol(x, pos) - cb - 1;
                         int32_t ja = qstart > qpos ? qstart - qpos : 0;
                         int32_t jb = qend - qpos < len - 1 ? qend - qpos : len - 1;
                         if (ja <= jb) {
@@ -328,24 +350,32 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
             if (pos > end || pos > x.e1 + 1) break;
         }
         x.cs[i] = sw.cs; x.cn[i] = sw.n; x.so[i] = off;
+        if (sw.n > 0)
+            for (int32_t bq = sw.cs >> 5; bq <= (sw.cs + sw.n - 1) >> 5; bq++) {
+                be.atomic_min(&x.blk[2 * bq], i);
+                be.atomic_max(&x.blk[2 * bq + 1], i + 1);
+            }
     }
 }
 
 // ---- phase 2: word-parallel compare ------------------------------------------------------------------
 // item = (8-column word, chunk of CMP_CHUNK reads); partial masks are OR-ed into two accumulators
 // per word (re-using the tabidx area is avoided: accumulators live at the end of the string pool)
-enum { CMP_CHUNK = 16 };
+enum { CMP_SPLIT = 2 };
 template <class B>
 NP_HD void ph_compare(WCtx& x, int32_t tid, int32_t nt, B& be) {
-    int32_t nw = (x.ncols + 7) / 8, nch = (x.nr + CMP_CHUNK - 1) / CMP_CHUNK;
+    int32_t nw = (x.ncols + 7) / 8;
     uint32_t* acc = x.acc;
-    for (int32_t it = tid; it < nw * nch; it += nt) {
-        int32_t cw = it % nw, ch = it / nw;
+    for (int32_t it = tid; it < nw * CMP_SPLIT; it += nt) {
+        int32_t cw = it % nw, half = it / nw;
+        int32_t blo = x.blk[2 * (cw >> 2)], bhi = x.blk[2 * (cw >> 2) + 1];
+        if (blo >= bhi) continue;
+        int32_t mid = blo + (bhi - blo + 1) / 2;
+        int32_t r0 = half == 0 ? blo : mid, r1 = half == 0 ? mid : bhi;
         uint32_t ref = x.refw[cw], mism = 0, cov = 0;
         int32_t c0 = cw * 8;
-        int32_t r1 = (ch + 1) * CMP_CHUNK < x.nr ? (ch + 1) * CMP_CHUNK : x.nr;
-        for (int32_t r = ch * CMP_CHUNK; r < r1; r++) {
-            int32_t n = x.cn[r]; if (n == 0) continue;
+        for (int32_t r = r0; r < r1; r++) {
+            int32_t n = x.cn[r];
             int32_t off = c0 - x.cs[r];                       // read nibble index of column c0
             if (off >= n || off <= -8) continue;
             const uint32_t* s = x.str + x.so[r];
@@ -378,8 +408,8 @@ NP_HD void ph_colinfo(WCtx& x, int32_t tid, int32_t nt) {
 
 // ---- phase 3: table columns ---------------------------------------------------------------------------
 // table status: the column disagrees, or its left neighbour (same contig) does
-NP_HD bool col_first(const WCtx& x, int32_t lc) { return x.cb0 + lc == x.d.colbase[x.gs]; }
-NP_HD bool col_last(const WCtx& x, int32_t lc) { return x.cb0 + lc == x.d.colbase[x.ge]; }
+NP_HD bool col_first(const WCtx& x, int32_t lc) { return lc == x.lc_first; }
+NP_HD bool col_last(const WCtx& x, int32_t lc) { return lc == x.lc_last; }
 NP_HD bool is_table(const WCtx& x, int32_t lc) {
     if (lc < 0 || lc >= x.ncols) return false;
     if (x.colinfo[lc] & 1) return true;
@@ -394,12 +424,13 @@ NP_HD void ph_mark_tables(WCtx& x, int32_t tid, int32_t nt, B& be) {
         x.colinfo[lc] |= 4;
         int32_t t = be.atomic_add_ret(&x.ctr[1], 1);
         x.tabidx[lc] = t < x.tmax ? (int16_t)t : (int16_t)-2;        // -2: pool exhausted
+        if (t < x.tmax) x.tabcol[t] = (int16_t)lc;
     }
 }
 NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
-    for (int32_t lc = x.cown0 + tid; lc < x.ncols; lc += nt) {
-        int32_t ti = x.tabidx[lc];
-        if (ti < 0) continue;
+    int32_t ntab = x.ctr[1] < x.tmax ? x.ctr[1] : x.tmax;
+    for (int32_t ti = tid; ti < ntab; ti += nt) {
+        int32_t lc = x.tabcol[ti];
         TabEntry& T = x.tab[ti];
         T.bad = 0; T.nent = 0; T.amax = 0;
         // reference vote first (contig_as_read, contig.c:373-383)
@@ -410,13 +441,21 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
         }
         int32_t nk = 0; uint32_t votes = 1;
         T.e[nk++] = k | (1u << 16);
-        for (int32_t r = 0; r < x.nr; r++) {
+        int32_t blo = x.blk[2 * (lc >> 5)], bhi = x.blk[2 * (lc >> 5) + 1];
+        for (int32_t r = blo; r < bhi; r++) {
             int32_t i = lc - x.cs[r];
             if (i < 0 || i >= x.cn[r]) continue;
             const uint32_t* s = x.str + x.so[r];
-            uint32_t kk = be_get(s, i);
-            if (i >= 1) kk |= be_get(s, i - 1) << 4;
-            if (i >= 2) kk |= be_get(s, i - 2) << 8;
+            // symbols i-2..i of the read's string as one funnel-shifted extract
+            uint32_t kk;
+            if (i >= 2) {
+                int32_t a = i - 2;
+                uint32_t v = fsl(s[a >> 3], (a & 7) > 5 ? s[(a >> 3) + 1] : 0u, (uint32_t)(a & 7));
+                kk = v >> 20;
+            } else {
+                kk = be_get(s, i);
+                if (i >= 1) kk |= be_get(s, i - 1) << 4;
+            }
             votes++;
             int32_t j = 0;
             for (; j < nk; j++) if ((T.e[j] & 0xffffu) == kk) { T.e[j] += 1u << 16; break; }
@@ -439,8 +478,15 @@ NP_HD void mark_unresolved(WCtx& x, int32_t lc_from, int32_t lc_to) {
 NP_HD void ph_chain(WCtx& x, int32_t tid, int32_t nt) {
     const Dev& d = x.d;
     const double rate = d.P.rate;
-    for (int32_t lc0 = x.cown0 + tid; lc0 < x.cown1; lc0 += nt) {
-        if (!(x.colinfo[lc0] & 4)) continue;
+    int32_t ntab_all = x.ctr[1] < x.tmax ? x.ctr[1] : x.tmax;
+    if (x.ctr[1] > x.tmax) {
+        // table pool exhausted: some table columns are not in the dense list; walk the columns instead
+        ntab_all = -1;
+    }
+    int32_t nitems = ntab_all >= 0 ? ntab_all : x.cown1 - x.cown0;
+    for (int32_t it = tid; it < nitems; it += nt) {
+        int32_t lc0 = ntab_all >= 0 ? (int32_t)x.tabcol[it] : x.cown0 + it;
+        if (lc0 < x.cown0 || lc0 >= x.cown1 || !(x.colinfo[lc0] & 4)) continue;
         bool prev_table = lc0 > 0 && !col_first(x, lc0) && is_table(x, lc0 - 1);
         if (prev_table && lc0 != x.cown0) continue;              // not a stretch start
         // extent of the run of table columns starting here
