@@ -89,7 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
 
 constexpr int kWinThreads = 128;
 
-__global__ void __launch_bounds__(kWinThreads) k_window(npe::Dev d, npw::WinGlobals g) {
+__global__ void __launch_bounds__(256) k_window(npe::Dev d, npw::WinGlobals g) {
     extern __shared__ __align__(128) uint8_t smem[];
     npw::WCtx x; x.d = d; x.g = g;
     npw::win_setup(x, (int32_t)blockIdx.x, smem);
@@ -233,8 +233,10 @@ struct CudaBackend {
             CUDA_TRY(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
             attr_set = want;
         }
+        int threads = kWinThreads;
+        if (const char* ev = getenv("NEXTPOLISH_B200_WIN_THREADS")) { int v = atoi(ev); if (v == 64 || v == 128 || v == 256) threads = v; }   // tuning only
         begin_timed("pileup_scan");
-        k_window<<<(unsigned)g.n_win, kWinThreads, (size_t)want, stream>>>(d, g);
+        k_window<<<(unsigned)g.n_win, threads, (size_t)want, stream>>>(d, g);
         CUDA_TRY(cudaGetLastError());
         launches++;
         end_timed();

@@ -1,6 +1,7 @@
 // engine_v2.h — task 1 with the fused shared-memory window kernel (window_kernel.h) and the general
 // global-memory kernels of engine_impl.h as the fallback for whatever a window leaves unresolved.
 #pragma once
+#include <stdlib.h>
 #include <vector>
 #include "window_kernel.h"
 
@@ -14,8 +15,8 @@ namespace npe {
     npw::ph_colinfo(x, tid, nt);          BARRIER;                  \
     npw::ph_mark_tables(x, tid, nt, ops); BARRIER;                  \
     npw::ph_tally(x, tid, nt);            BARRIER;                  \
-    npw::ph_chain(x, tid, nt);            BARRIER;                  \
-    npw::ph_anchors(x, tid, nt);                                    \
+    npw::ph_chain(x, tid, nt);            /* disjoint columns: */   \
+    npw::ph_anchors(x, tid, nt);          BARRIER;                  \
     npw::ph_finish(x, tid, nt, ops);
 
 struct V2Stats { int32_t W, n_win, smem, unresolved_windows, fallback_cols; };
@@ -60,7 +61,9 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
     int32_t need = 0; bool fits = false;
     std::vector<int32_t> hw_ctg, hw_p0;
     static const int32_t kW[3] = {512, 256, 128};
-    for (int wi = 0; wi < 3 && !fits; wi++) {
+    int wi0 = 0;
+    if (const char* ev = getenv("NEXTPOLISH_B200_WINDOW")) { int v = atoi(ev); wi0 = v == 256 ? 1 : v == 128 ? 2 : 0; }   // tuning only
+    for (int wi = wi0; wi < 3 && !fits; wi++) {
         g.W = kW[wi];
         hw_ctg.clear(); hw_p0.clear();
         for (int32_t k = 0; k < d.n_ctg; k++)

@@ -64,13 +64,13 @@ struct WCtx {             // per-window context: globals + carved shared memory
     uint8_t* rec; const uint32_t* recoff;     // staged records and their offsets (16-byte units, global)
     int32_t *cs, *cn, *so;                    // per read: local column of first stored symbol, count, pool offset
     uint32_t *str, *refw, *acc;               // string pool, draft symbol words, compare accumulators
-    uint8_t* colinfo;                         // per local column: 1 mism, 2 covered, 4 table, 8 sub-column
+    uint8_t* colinfo;                         // per local column: 1 mism, 2 covered, 8 sub-column
     int16_t* tabidx;                          // per local column: table index or -1
     int16_t* tabcol;                          // dense list: table index -> local column
     int32_t* lcb;                             // [npos+1] local column of every ext position (staged colbase)
     int32_t* blk;                             // [2*nblk] first / last+1 staged read overlapping each 32-column block
     TabEntry* tab;                            // aliases the record area (records are dead after expand)
-    int32_t* ctr;                             // [0] string words used, [1] tables used, [2] unresolved flag
+    int32_t* ctr;                             // [0] string words used, [1] tables used, [2] internal error, [3] unresolved
 };
 
 NP_HD uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -160,15 +160,27 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
 // ---- big-endian nibble strings -------------------------------------------------------------------
 // nibble i of a string lives in word i>>3 at bits [28-4*(i&7), +4)
 NP_HD uint32_t be_get(const uint32_t* w, int32_t i) { return (w[i >> 3] >> (28 - ((i & 7) << 2))) & 0xfu; }
-NP_HD uint32_t bswap32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24); }
-NP_HD uint32_t fsl(uint32_t hi, uint32_t lo, uint32_t nib) {   // 8 nibbles starting at nibble `nib` of (hi:lo)
+NP_HD uint32_t bswap32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(v, 0u, 0x0123u);
+#else
+    return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24);
+#endif
+}
+NP_HD uint32_t fsl(uint32_t hi, uint32_t lo, uint32_t nib) {   // 8 nibbles starting at nibble `nib` (0..7) of (hi:lo)
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(lo, hi, nib * 4u);
+#else
     return nib == 0 ? hi : (hi << (nib * 4)) | (lo >> (32 - nib * 4));
+#endif
 }
 // mask with nibbles [a, b) set (0 <= a <= b <= 8), nibble 0 = top
 NP_HD uint32_t nib_mask(int32_t a, int32_t b) {
-    uint32_t hi = a <= 0 ? 0xffffffffu : (a >= 8 ? 0u : 0xffffffffu >> (a * 4));
-    uint32_t lo = b >= 8 ? 0xffffffffu : (b <= 0 ? 0u : ~(0xffffffffu >> (b * 4)));
-    return hi & lo;
+    a = a < 0 ? 0 : (a > 8 ? 8 : a);
+    b = b < 0 ? 0 : (b > 8 ? 8 : b);
+    uint32_t hi = (uint32_t)(0xffffffffull >> (a * 4));         // nibbles a..7
+    uint32_t lo = (uint32_t)(0xffffffffull >> (b * 4));         // nibbles b..7
+    return hi & ~lo;
 }
 // copy `len` nibbles of BAM seq (bytes, high nibble first == big-endian nibble order) starting at
 // query index q into dst string at nibble index di
@@ -205,7 +217,7 @@ NP_HD void ph_clear(WCtx& x, int32_t tid, int32_t nt) {
     for (int32_t i = tid; i < x.ncols + 8; i += nt) x.tabidx[i] = -1;
     for (int32_t i = tid; i <= x.npos; i += nt) x.lcb[i] = x.d.colbase[x.e0 + i] - x.cb0;
     for (int32_t i = tid; i < x.nblk; i += nt) { x.blk[2 * i] = 0x7fffffff; x.blk[2 * i + 1] = 0; }
-    if (tid == 0) { x.ctr[0] = 0; x.ctr[1] = 0; x.ctr[2] = 0; }
+    if (tid == 0) { x.ctr[0] = 0; x.ctr[1] = 0; x.ctr[2] = 0; x.ctr[3] = 0; }
 }
 template <class B>
 NP_HD void ph_ref(WCtx& x, int32_t tid, int32_t nt, B& be) {   // one thread per ext position
@@ -421,7 +433,6 @@ NP_HD void ph_mark_tables(WCtx& x, int32_t tid, int32_t nt, B& be) {
     // k-mer context are available because HL >= 2 positions) to the end of the extended range
     for (int32_t lc = x.cown0 + tid; lc < x.ncols; lc += nt) {
         if (!is_table(x, lc)) continue;
-        x.colinfo[lc] |= 4;
         int32_t t = be.atomic_add_ret(&x.ctr[1], 1);
         x.tabidx[lc] = t < x.tmax ? (int16_t)t : (int16_t)-2;        // -2: pool exhausted
         if (t < x.tmax) x.tabcol[t] = (int16_t)lc;
@@ -472,7 +483,7 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
 NP_HD void mark_unresolved(WCtx& x, int32_t lc_from, int32_t lc_to) {
     const Dev& d = x.d;
     for (int32_t lc = lc_from; lc <= lc_to && lc < x.ncols; lc++) d.needi[x.cb0 + lc] = 1;
-    x.ctr[2] |= 2;
+    x.ctr[3] = 1;
 }
 
 NP_HD void ph_chain(WCtx& x, int32_t tid, int32_t nt) {
@@ -486,7 +497,7 @@ NP_HD void ph_chain(WCtx& x, int32_t tid, int32_t nt) {
     int32_t nitems = ntab_all >= 0 ? ntab_all : x.cown1 - x.cown0;
     for (int32_t it = tid; it < nitems; it += nt) {
         int32_t lc0 = ntab_all >= 0 ? (int32_t)x.tabcol[it] : x.cown0 + it;
-        if (lc0 < x.cown0 || lc0 >= x.cown1 || !(x.colinfo[lc0] & 4)) continue;
+        if (lc0 < x.cown0 || lc0 >= x.cown1 || x.tabidx[lc0] == -1) continue;
         bool prev_table = lc0 > 0 && !col_first(x, lc0) && is_table(x, lc0 - 1);
         if (prev_table && lc0 != x.cown0) continue;              // not a stretch start
         // extent of the run of table columns starting here
@@ -563,7 +574,7 @@ NP_HD void ph_anchors(WCtx& x, int32_t tid, int32_t nt) {
         int32_t c = x.cb0 + lc;
         uint8_t ci = x.colinfo[lc];
         d.mism[c] = ci & 1;
-        if (ci & 4) {
+        if (x.tabidx[lc] != -1) {
             int32_t ti = x.tabidx[lc];
             // votes of table columns are needed by the fallback tables (capacity); recount if no table
             uint32_t v = 1;
@@ -583,8 +594,8 @@ NP_HD void ph_anchors(WCtx& x, int32_t tid, int32_t nt) {
 }
 template <class B>
 NP_HD void ph_finish(WCtx& x, int32_t tid, int32_t nt, B& be) {
-    if (x.ctr[2] & 1) { if (tid == 0) *x.d.err |= npe::ERR_SYM_BOUND; }
-    if (x.ctr[2] & 2) {
+    if (x.ctr[2]) { if (tid == 0) *x.d.err |= npe::ERR_SYM_BOUND; }
+    if (x.ctr[3]) {
         for (int32_t i = tid; i < x.nr; i += nt) x.g.r_need[x.rlo + i] = 1;
         if (tid == 0) be.atomic_add(x.g.n_unresolved, 1);
     }
