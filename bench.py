@@ -238,16 +238,15 @@ def main():
     estream = torch.cuda.ExternalStream(eng.stream(), device=dev)
     gather_buf = torch.empty(cap, dtype=torch.uint8, device=dev)
 
+    from nextpolish_b200.sharding import gather_bytes
+
     def gather_fasta():
         """The single collective of the path: corrected FASTA bytes of every rank -> rank 0."""
         n = eng.result_bytes()
         E.lib().np_engine_copy_result(eng.h, gather_buf.data_ptr(), cap)
         eng.sync()
         if world > 1:
-            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-            dist.all_gather(sizes, torch.tensor([n], dtype=torch.int64, device=dev))
-            bufs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
-            dist.gather(gather_buf, bufs, dst=0)
+            gather_bytes(gather_buf[:n], dst=0)
 
     def step_resident(i):
         for t in tasks:

@@ -72,3 +72,18 @@ def test_compute_fails_loudly_without_gpu(E):
     with pytest.raises(E.NativeError) as ei:
         E.Engine(0)
     assert "no CPU path" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_worker_mirror_bookkeeping(tmp_path):
+    """Block-file selection and resume scan of nextpolish_b200/nextpolish1.py (nextpolish1.py:148-179)."""
+    from nextpolish_b200 import nextpolish1 as n1
+    out = tmp_path / "o.fa"
+    out.write_text(">a_np1 4\nACGT\n>b_np1 4\nAC")          # last record is partial
+    polished = set()
+    assert n1.scan_output(str(out), polished) == 14 and polished == {"a"}
+    blc = tmp_path / "b.blc"
+    blc.write_text("a\t0\nb\t0\nc\t1\n")
+    assert n1.read_block(str(blc), "0", polished) == ["b"]
+    fa = tmp_path / "g.fa"
+    fa.write_text(">a desc\nAC\n>b\nGT\n")
+    assert n1.read_block(str(fa), "all", set()) == ["a", "b"]

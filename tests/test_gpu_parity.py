@@ -180,3 +180,28 @@ def test_fused_kernel_deep_and_noisy_use_fallback_correctly(E, oracle, eng):
     cfg = E.default_config(b"")
     want = run_checker(oracle.np_oracle_run, sh, 1, cfg)
     assert eng.polish(sh, 1, cfg) == want
+
+
+def test_nextpolish1_worker_mirror(E, tmp_path):
+    """python -m nextpolish_b200.nextpolish1 with the reference's flags: block file, resume, header names."""
+    from nextpolish_b200 import nextpolish1
+    fa = os.path.join(GOLDEN, "td30.step1.fa")
+    bam = os.path.join(GOLDEN, "td30.step1.bam")
+    exp = read_fasta(os.path.join(GOLDEN, "td30.step1.expected.fa"))
+    names = [n[:-2] for n in exp]
+    blc = str(tmp_path / "g.blc")
+    open(blc, "w").write("".join("%s\t%d\n" % (n, i % 2) for i, n in enumerate(names)))
+    out = str(tmp_path / "part000.fasta")
+    assert nextpolish1.main(["-g", fa, "-s", bam, "-t", "1", "-b", blc, "-i", "0", "-o", out]) == 0
+    got = read_fasta(out)
+    assert set(got) == {names[0] + "_np1"} and got[names[0] + "_np1"] == exp[names[0] + "_1"]
+    # resume: a truncated last record is re-done, finished contigs are skipped
+    full = open(out).read()
+    open(out, "w").write(full + ">" + names[1] + "_np1 10\nACGT")
+    blc_all = str(tmp_path / "all.blc")
+    open(blc_all, "w").write("".join("%s\t0\n" % n for n in names))
+    assert nextpolish1.main(["-g", fa, "-s", bam, "-t", "1", "-b", blc_all, "-i", "0", "-o", out]) == 0
+    got = read_fasta(out)
+    assert {k: v for k, v in got.items()} == {n + "_np1": exp[n + "_1"] for n in names}
+    header = [l for l in open(out) if l.startswith(">")][0].split()
+    assert int(header[1]) == len(got[header[0][1:]])
