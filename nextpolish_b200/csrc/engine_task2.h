@@ -49,6 +49,12 @@ struct Dev2 {
     uint8_t* ord2;               // [NRC*16] first-seen order of base codes
     uint8_t* ns2;                // [NRC]
     int32_t* subbuf;             // [NRC + 2*NR_nd + 2] inner region lists
+    // (region, read) pairs of the no-depth pass: the CIGAR walks run one thread per pair
+    int32_t *nd_pcnt, *nd_poff;  // per region: candidate reads (level >= 1), scan
+    int32_t *nd_sb, *nd_soff;    // per region: symbol-slot bytes (pairs * columns), scan
+    int32_t *ndp_read, *ndp_first, *ndp_n;   // per pair: read, first column (relative to the region), symbols
+    uint8_t* ndp_sym;            // symbol slots
+    int32_t NP_nd;
     // windows
     int32_t *wcnt, *woff;        // per k-mer region: window count, scan
     int32_t *win;                // [2*NW] (start,end)
@@ -56,6 +62,10 @@ struct Dev2 {
     int32_t *wcand, *wsoff;      // per window: candidate count; scratch offset (bytes, in 4-byte units)
     int32_t* wscratch;           // strings + tallies
     int32_t* wbest;              // [NW] offset of the winner string in wscratch (bytes), or -1
+    // (window, read) pairs of the vote: walks run one thread per pair
+    int32_t *wp_cnt, *wp_off;    // per window: candidates (+1 slot for the stale record), scan
+    int32_t *wp_read;            // per pair: read index (-1: unused stale slot)
+    int32_t NP_w;
 };
 
 enum { ERR_SHARED_ENDPOINT = 16, ERR_REGION_SCRATCH = 32 };
@@ -234,30 +244,65 @@ NP_HD void overlap_range(const Dev2& w, int32_t k, int32_t a, int32_t b, int64_t
 NP_HD bool chain_head(const Dev2& w, int64_t i) { return i == 0 || w.ndl[2 * i - 1] < w.ndl[2 * i]; }
 NP_HD bool chain_next(const Dev2& w, int64_t j) { return j + 1 < w.NR_nd && w.ndl[2 * (j + 1)] <= w.ndl[2 * j + 1]; }
 
-struct CountVisitor {
-    int32_t* vcap; int32_t inc;
-    NP_HD void sym(int32_t col, uint32_t, int32_t, bool) { vcap[col] += inc; }
-    NP_HD void overflow() {}
+// candidate reads of a region: level >= 1 and overlapping [s, e+1) (contig_parse_region, contig.c:692-698)
+struct NdPairCount {     // per region: mark its columns, count its (region, read) pairs
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B& be) const {
+        const Dev& d = w.d;
+        if (i >= w.NR_nd) { w.nd_pcnt[i] = 0; w.nd_sb[i] = 0; return; }
+        int32_t s = w.ndl[2 * i], e = w.ndl[2 * i + 1];
+        int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
+        int32_t c0 = d.colbase[s], c1 = d.colbase[e];
+        for (int32_t c = c0; c <= c1; c++) { w.ndmark[c] = 1; be.atomic_add(&w.vcap[c], 1); }   // the draft's own vote
+        int64_t lo, hi; overlap_range(w, k, s, e + 1, &lo, &hi);
+        int32_t n = 0;
+        for (int64_t r = lo; r < hi; r++) if (d.r_level[r] >= 1 && d.r_hend[r] > s) n++;
+        w.nd_pcnt[i] = n; w.nd_sb[i] = n * (c1 - c0 + 1);
+    }
 };
-struct NodepthCount {    // per chain: mark the columns and bound the votes each may receive
+struct NdPairFill {
     Dev2 w;
     template <class B> NP_HD void operator()(int64_t i, B&) const {
         const Dev& d = w.d;
-        if (!chain_head(w, i)) return;
-        for (int64_t j = i;; j++) {
-            int32_t s = w.ndl[2 * j], e = w.ndl[2 * j + 1];
-            int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
-            for (int32_t c = d.colbase[s]; c <= d.colbase[e]; c++) { w.ndmark[c] = 1; w.vcap[c] += 1; }
-            int64_t lo, hi; overlap_range(w, k, s, e + 1, &lo, &hi);
-            for (int64_t r = lo; r < hi; r++) {
-                if (d.r_level[r] < 1 || d.r_hend[r] <= s) continue;
-                Rec rc = load_rec(d.rec, d.rec_off, r);
-                // level-1 reads may vote twice on a column shared by two inner sub-regions
-                CountVisitor v{w.vcap, d.r_level[r] == 1 ? 2 : 1};
-                walk_read(rc, d.ctg_goff[k], s, e, d.r_qstart[r], d.r_qend[r], d.colbase, v);
-            }
-            if (!chain_next(w, j)) break;
-        }
+        int32_t s = w.ndl[2 * i], e = w.ndl[2 * i + 1];
+        int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
+        int64_t lo, hi; overlap_range(w, k, s, e + 1, &lo, &hi);
+        int32_t n = 0;
+        for (int64_t r = lo; r < hi; r++) if (d.r_level[r] >= 1 && d.r_hend[r] > s) w.ndp_read[w.nd_poff[i] + n++] = (int32_t)r;
+    }
+};
+struct SymSlotVisitor {  // the read's column string over the region, one byte per column
+    uint8_t* slot; int32_t c0, ncols, first, n; int32_t* vcap; int32_t inc; int32_t* err;
+    template <class B> NP_HD void put(int32_t col, uint32_t s, B& be) {
+        int32_t i = col - c0;
+        if (i < 0 || i >= ncols) { *err |= ERR_REGION_SCRATCH; return; }
+        if (n == 0) first = i;
+        if (i != first + n) { *err |= ERR_REGION_SCRATCH; return; }
+        slot[i] = (uint8_t)s; n++;
+        be.atomic_add(&vcap[col], inc);
+    }
+};
+template <class B> struct SymSlotAdapter {
+    SymSlotVisitor* v; B* be;
+    NP_HD void sym(int32_t col, uint32_t s, int32_t, bool) { v->put(col, s, *be); }
+    NP_HD void overflow() { *v->err |= ERR_INS_OVERFLOW; }
+};
+struct NdWalk {          // per (region, read) pair: CIGAR walk over the region
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t p, B& be) const {
+        const Dev& d = w.d;
+        int32_t i = (int32_t)upper_bound_i32(w.nd_poff, 0, w.NR_nd + 1, (int32_t)p) - 1;
+        int32_t s = w.ndl[2 * i], e = w.ndl[2 * i + 1];
+        int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
+        int32_t c0 = d.colbase[s], ncols = d.colbase[e] - c0 + 1;
+        int32_t j = (int32_t)p - w.nd_poff[i];
+        int64_t r = w.ndp_read[p];
+        Rec rc = load_rec(d.rec, d.rec_off, r);
+        // level-1 reads may vote twice on a column shared by two inner sub-regions
+        SymSlotVisitor v{w.ndp_sym + (size_t)w.nd_soff[i] + (size_t)j * ncols, c0, ncols, 0, 0, w.vcap, d.r_level[r] == 1 ? 2 : 1, d.err};
+        SymSlotAdapter<B> a{&v, &be};
+        walk_read(rc, d.ctg_goff[k], s, e, d.r_qstart[r], d.r_qend[r], d.colbase, a);
+        w.ndp_first[p] = v.first; w.ndp_n[p] = v.n;
     }
 };
 
@@ -363,6 +408,16 @@ NP_HD int32_t inner_regions(const Dev& d, int32_t c0, int32_t c1, int32_t bs, in
     return n;
 }
 
+// votes of one pair restricted to region columns [lo, hi] (relative to the region's first column):
+// rolling 3-mer starts at 0 at the first vote inside the range (contig.c:255,360-363)
+NP_HD void nd_apply_pair(const Dev2& w, const NdCtx& x, int32_t c0, int32_t ncols, int32_t i, int32_t j, int32_t p, int32_t lo, int32_t hi) {
+    int32_t first = w.ndp_first[p], n = w.ndp_n[p];
+    const uint8_t* slot = w.ndp_sym + (size_t)w.nd_soff[i] + (size_t)j * ncols;
+    int32_t a = first > lo ? first : lo, b = first + n - 1 < hi ? first + n - 1 : hi;
+    uint32_t kmer = 0;
+    for (int32_t t = a; t <= b; t++) { kmer = ((kmer & 0xffu) << 4) | slot[t]; x.add(c0 + t, kmer); }
+}
+
 struct NodepthScore {    // contig_score_correct(region, 0x12), one thread per chain of no-depth regions
     Dev2 w;
     template <class B> NP_HD void operator()(int64_t i0, B&) const {
@@ -371,8 +426,7 @@ struct NodepthScore {    // contig_score_correct(region, 0x12), one thread per c
         NdCtx x{&w};
         for (int64_t i = i0;; i++) {
             int32_t s = w.ndl[2 * i], e = w.ndl[2 * i + 1];
-            int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
-            int32_t c0 = d.colbase[s], c1 = d.colbase[e];
+            int32_t c0 = d.colbase[s], c1 = d.colbase[e], ncols = c1 - c0 + 1;
             uint32_t kmer = 0;
             for (int32_t c = c0; c <= c1; c++) {                           // contig_as_read
                 int32_t ci = w.ndidx[c];
@@ -381,25 +435,20 @@ struct NodepthScore {    // contig_score_correct(region, 0x12), one thread per c
                 w.refk2[ci] = (uint16_t)kmer;
                 x.add(c, kmer);
             }
-            int64_t lo, hi; overlap_range(w, k, s, e + 1, &lo, &hi);
-            for (int64_t r = lo; r < hi; r++) {                            // contig_parse_region, level == 2
-                if (d.r_level[r] != 2 || d.r_hend[r] <= s) continue;
-                Rec rc = load_rec(d.rec, d.rec_off, r);
-                VoteVisitor v{x, 0};
-                walk_read(rc, d.ctg_goff[k], s, e, d.r_qstart[r], d.r_qend[r], d.colbase, v);
-            }
+            int32_t p0 = w.nd_poff[i], p1 = w.nd_poff[i + 1];
+            for (int32_t p = p0; p < p1; p++)                                // contig_parse_region, level == 2
+                if (d.r_level[w.ndp_read[p]] == 2) nd_apply_pair(w, x, c0, ncols, (int32_t)i, p - p0, p, 0, ncols - 1);
             nd_score_correct(w, c0, c1, d.P.rate);
             int32_t* sub = w.subbuf + (size_t)w.ndidx[c0] + 2 * (size_t)i;
             int32_t ns = inner_regions(d, c0, c1, s, e, d.P.ext_len_edge, sub);
             ns = merge_regions(sub, ns);
             for (int32_t q = 0; q < ns; q++) {
                 int32_t ss = sub[2 * q], se = sub[2 * q + 1];
-                int64_t l2, h2; overlap_range(w, k, ss, se + 1, &l2, &h2);
-                for (int64_t r = l2; r < h2; r++) {                        // level == 1 reads on top
-                    if (d.r_level[r] != 1 || d.r_hend[r] <= ss) continue;
-                    Rec rc = load_rec(d.rec, d.rec_off, r);
-                    VoteVisitor v{x, 0};
-                    walk_read(rc, d.ctg_goff[k], ss, se, d.r_qstart[r], d.r_qend[r], d.colbase, v);
+                int32_t lo = d.colbase[ss] - c0, hi = d.colbase[se] - c0;
+                for (int32_t p = p0; p < p1; p++) {                          // level == 1 reads on top
+                    int64_t r = w.ndp_read[p];
+                    if (d.r_level[r] != 1 || d.r_hend[r] <= ss || d.r_gpos[r] >= se + 1) continue;
+                    nd_apply_pair(w, x, c0, ncols, (int32_t)i, p - p0, p, lo, hi);
                 }
                 nd_score_correct(w, d.colbase[ss], d.colbase[se], d.P.rate);
             }
@@ -452,101 +501,132 @@ NP_HD void window_range(const Dev2& w, int32_t k, int32_t s, int32_t e, int64_t*
     int64_t l = upper_bound_i32(w.r_hpm, 0, *term, e + 1);
     *lo = l < r0 ? r0 : l;
 }
-struct WindowCount {     // scratch need of a window: ncand * (len bytes rounded to 4 + 12) / 4 words
+// Scratch of one window: (ncand + 1) slots [string bytes | length, qual, first column, mapq] — the extra
+// slot is for the stale record of kmercount.c:212-216 — followed by (ncand + 1) tally entries
+// [slot, num, sum mapq, sum qual].
+NP_HD int32_t win_slot_words(int32_t len) { return (len + 3) / 4 + 4; }
+
+struct WindowCount {
     Dev2 w;
     template <class B> NP_HD void operator()(int64_t i, B&) const {
         const Dev& d = w.d;
-        if (i >= w.NW) { w.wcand[i] = 0; return; }
+        if (i >= w.NW) { w.wcand[i] = 0; w.wp_cnt[i] = 0; return; }
         int32_t s = w.win[2 * i], e = w.win[2 * i + 1];
         int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
         int64_t lo, term; window_range(w, k, s, e, &lo, &term);
         int32_t n = 0;
         for (int64_t r = lo; r < term; r++) if (d.r_hend[r] > e + 1) n++;
         int32_t len = d.colbase[e] - d.colbase[s] + 1;
-        int32_t words = (len + 3) / 4 + 3;
-        w.wcand[i] = (n + 2) * words;          // + the scratch string of the current read, + stale read
+        w.wp_cnt[i] = n + 1;
+        w.wcand[i] = (n + 1) * (win_slot_words(len) + 4);
     }
 };
-
-struct KmerVisitor {     // ss_parse_read_kmer's appends (kmercount.c:389-440)
-    const Dev* d; uint8_t* region; int32_t cap; int32_t length, del, qual; const uint8_t* q;
-    NP_HD void sym(int32_t col, uint32_t s, int32_t qpos, bool subgap) {
-        if (length < cap) region[length] = (uint8_t)s;
-        length++;
-        if (subgap) del++;
-        if (qpos >= 0) qual += q[qpos];
-        d->oflag[col] &= (uint8_t)~FLAG_ZERO;                     // flagzero == 0
-    }
-    NP_HD void overflow() { *d->err |= ERR_INS_OVERFLOW; }
-};
-
-struct WindowVote {      // ss_kmer_correct for one window (kmercount.c:188-253)
+struct WinPairFill {
     Dev2 w;
     template <class B> NP_HD void operator()(int64_t i, B&) const {
         const Dev& d = w.d;
         int32_t s = w.win[2 * i], e = w.win[2 * i + 1];
         int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
-        int32_t len = d.colbase[e] - d.colbase[s] + 1;
-        int32_t words = (len + 3) / 4 + 3;                         // string (len bytes) + num, mapq, qual
-        int32_t* base = w.wscratch + w.wsoff[i];
-        int32_t nslot = (w.wsoff[i + 1] - w.wsoff[i]) / words;     // >= candidates + 2
-        uint8_t* cur = (uint8_t*)(base + (size_t)(nslot - 1) * words);   // scratch string of the current read
-        int32_t nstr = 0, count = 0;
-        bool broke = false; int64_t ncand = 0;
         int64_t lo, term; window_range(w, k, s, e, &lo, &term);
-        auto slot_str = [&](int32_t j) { return (uint8_t*)(base + (size_t)j * words); };
-        auto slot_tal = [&](int32_t j) { return base + (size_t)j * words + (len + 3) / 4; };
-        // ss_kmer_get_region (kmercount.c:332-363); returns the read's ks->mapqual after the call
-        auto get_region = [&](int64_t r) -> int32_t {
-            Rec rc = load_rec(d.rec, d.rec_off, r);
-            KmerVisitor v{&d, cur, len, 0, 0, 0, d.qual + (size_t)d.qual_off[r] * 16};
-            walk_read(rc, d.ctg_goff[k], s, e, d.r_qstart[r], d.r_qend[r], d.colbase, v);
-            int32_t q = (v.length > 0 && v.length != v.del) ? v.qual / (v.length - v.del) : 0;
-            if (v.length != len) return 0;
-            int32_t j = 0;
-            for (; j < nstr; j++) {
-                const uint8_t* a = slot_str(j); bool same = true;
-                for (int32_t t = 0; t < len; t++) if (a[t] != cur[t]) { same = false; break; }
+        int32_t n = 0;
+        for (int64_t r = lo; r < term; r++) if (d.r_hend[r] > e + 1) w.wp_read[w.wp_off[i] + n++] = (int32_t)r;
+        // the record that ended the swapped iterator (first read of the contig with pos >= start)
+        w.wp_read[w.wp_off[i] + n] = (term < d.ctg_read_off[k + 1] && d.r_level[term] == 1) ? (int32_t)term : -1;
+    }
+};
+
+struct KmerVisitor {     // ss_parse_read_kmer's appends (kmercount.c:389-440); flag clearing is deferred
+    uint8_t* region; int32_t cap; int32_t length, del, qual, first; const uint8_t* q;
+    NP_HD void sym(int32_t col, uint32_t s, int32_t qpos, bool subgap) {
+        if (length == 0) first = col;
+        if (length < cap) region[length] = (uint8_t)s;
+        length++;
+        if (subgap) del++;
+        if (qpos >= 0) qual += q[qpos];
+    }
+    int32_t* err;
+    NP_HD void overflow() { *err |= ERR_INS_OVERFLOW; }
+};
+struct WinWalk {         // per (window, read) pair: the read's column string over the window
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t p, B&) const {
+        const Dev& d = w.d;
+        int32_t i = (int32_t)upper_bound_i32(w.wp_off, 0, w.NW + 1, (int32_t)p) - 1;
+        int32_t j = (int32_t)p - w.wp_off[i], ncand = w.wp_cnt[i] - 1;
+        int32_t s = w.win[2 * i], e = w.win[2 * i + 1];
+        int32_t len = d.colbase[e] - d.colbase[s] + 1, sw = win_slot_words(len);
+        int32_t* slot = w.wscratch + w.wsoff[i] + (size_t)j * sw;
+        int32_t* meta = slot + (len + 3) / 4;
+        int64_t r = w.wp_read[p];
+        meta[0] = -1;
+        if (r < 0) return;
+        if (j < ncand && d.r_level[r] != 2) return;            // only level-2 candidates are parsed (kmercount.c:197)
+        int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
+        Rec rc = load_rec(d.rec, d.rec_off, r);
+        KmerVisitor v{(uint8_t*)slot, len, 0, 0, 0, 0, d.qual + (size_t)d.qual_off[r] * 16, d.err};
+        walk_read(rc, d.ctg_goff[k], s, e, d.r_qstart[r], d.r_qend[r], d.colbase, v);
+        meta[0] = v.length;
+        meta[1] = (v.length > 0 && v.length != v.del) ? v.qual / (v.length - v.del) : 0;   // kmercount.c:457-462
+        meta[2] = v.first;
+        meta[3] = (int32_t)rc.mapq;
+    }
+};
+
+struct WindowVote {      // ss_kmer_correct for one window (kmercount.c:188-253) over the pre-walked pairs
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B&) const {
+        const Dev& d = w.d;
+        int32_t s = w.win[2 * i], e = w.win[2 * i + 1];
+        int32_t len = d.colbase[e] - d.colbase[s] + 1, sw = win_slot_words(len), lw = (len + 3) / 4;
+        int32_t ncand = w.wp_cnt[i] - 1;
+        int32_t* base = w.wscratch + w.wsoff[i];
+        int32_t* tal = base + (size_t)(ncand + 1) * sw;             // [slot, num, mapq, qual] entries
+        int32_t nstr = 0, count = 0;
+        bool broke = false;
+        // ss_kmer_get_region (kmercount.c:332-363) on pair slot j; returns ks->mapqual after the call
+        auto get_region = [&](int32_t j) -> int32_t {
+            const int32_t* slot = base + (size_t)j * sw;
+            const int32_t* meta = slot + lw;
+            int32_t length = meta[0];
+            for (int32_t c = meta[2]; c < meta[2] + length; c++) d.oflag[c] &= (uint8_t)~FLAG_ZERO;   // flagzero == 0
+            if (length != len) return 0;
+            int32_t q = 0;
+            for (; q < nstr; q++) {
+                const int32_t* a = base + (size_t)tal[4 * q] * sw; bool same = true;
+                const uint8_t *sa = (const uint8_t*)a, *sb = (const uint8_t*)slot;
+                for (int32_t t = 0; t < len; t++) if (sa[t] != sb[t]) { same = false; break; }
                 if (same) break;
             }
-            if (j == nstr) {
-                if (nstr >= nslot - 1) { *d.err |= ERR_REGION_SCRATCH; return 0; }
-                uint8_t* a = slot_str(j);
-                for (int32_t t = 0; t < len; t++) a[t] = cur[t];
-                int32_t* tl = slot_tal(j); tl[0] = 1; tl[1] = (int32_t)rc.mapq; tl[2] = q;
-                nstr++;
-            } else { int32_t* tl = slot_tal(j); tl[0]++; tl[1] += (int32_t)rc.mapq; tl[2] += q; }
-            return (int32_t)rc.mapq;
+            if (q == nstr) { tal[4 * q] = j; tal[4 * q + 1] = 1; tal[4 * q + 2] = meta[3]; tal[4 * q + 3] = meta[1]; nstr++; }
+            else { tal[4 * q + 1]++; tal[4 * q + 2] += meta[3]; tal[4 * q + 3] += meta[1]; }
+            return meta[3];
         };
-        for (int64_t r = lo; r < term; r++) {
-            if (!(d.r_hend[r] > e + 1)) continue;
-            ncand++;
-            if (d.r_level[r] == 2) {
-                int32_t mq = get_region(r);
-                if (mq == 60) { count++; if (count >= d.P.max_count_kmer) { broke = true; break; } }
-            }
+        for (int32_t j = 0; j < ncand; j++) {
+            if (d.r_level[w.wp_read[w.wp_off[i] + j]] != 2) continue;
+            int32_t mq = get_region(j);
+            if (mq == 60) { count++; if (count >= d.P.max_count_kmer) { broke = true; break; } }
         }
-        if (nstr == 0 && !broke && ncand > 0 && term < d.ctg_read_off[k + 1]) {
-            // kmercount.c:209-219: the stale record (the one that ended the first iterator) is
-            // filtered and parsed once per record the second iterator yields
-            if (d.r_level[term] == 1) for (int64_t t = 0; t < ncand; t++) get_region(term);
+        if (nstr == 0 && !broke && ncand > 0 && w.wp_read[w.wp_off[i] + ncand] >= 0) {
+            // kmercount.c:209-219: the stale record is filtered and parsed once per record the second
+            // iterator yields
+            for (int32_t t = 0; t < ncand; t++) get_region(ncand);
         }
         int32_t best = -1;
         if (nstr > 0) {
             if (count == d.P.max_count_kmer) {
                 int32_t want = 60 * count;
-                for (int32_t j = 0; j < nstr; j++) if (slot_tal(j)[1] == want) { best = j; break; }
+                for (int32_t q = 0; q < nstr; q++) if (tal[4 * q + 2] == want) { best = q; break; }
             }
             if (best < 0) {
                 best = 0;
-                for (int32_t j = 0; j < nstr; j++) {
-                    const int32_t *a = slot_tal(best), *b = slot_tal(j);
+                for (int32_t q = 0; q < nstr; q++) {
+                    const int32_t *a = tal + 4 * best + 1, *b = tal + 4 * q + 1;
                     bool less = a[0] != b[0] ? a[0] < b[0] : a[1] != b[1] ? a[1] < b[1] : a[2] < b[2];   // ks_compare
-                    if (j != best && less) best = j;
+                    if (q != best && less) best = q;
                 }
             }
         }
-        w.wbest[i] = best < 0 ? -1 : (int32_t)(w.wsoff[i] + best * words);
+        w.wbest[i] = best < 0 ? -1 : (int32_t)(w.wsoff[i] + tal[4 * best] * sw);
     }
 };
 struct WindowApply {     // contig_update_contig in window order: a later window wins shared columns
@@ -649,7 +729,21 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
     if (C > 0) be.launch("col_init2", C, ColInit2{w});
     // no-depth regions
     if (w.NR_nd > 0) {
-        be.launch("nodepth_count", w.NR_nd, NodepthCount{w});
+        w.nd_pcnt = be.template buf<int32_t>("nd_pcnt", (size_t)w.NR_nd + 1);
+        w.nd_poff = be.template buf<int32_t>("nd_poff", (size_t)w.NR_nd + 1);
+        w.nd_sb = be.template buf<int32_t>("nd_sb", (size_t)w.NR_nd + 1);
+        w.nd_soff = be.template buf<int32_t>("nd_soff", (size_t)w.NR_nd + 1);
+        be.launch("nodepth_pairs", (int64_t)w.NR_nd + 1, NdPairCount{w});
+        be.exscan_i32(w.nd_pcnt, w.nd_poff, (int64_t)w.NR_nd + 1);
+        be.exscan_i32(w.nd_sb, w.nd_soff, (int64_t)w.NR_nd + 1);
+        w.NP_nd = be.read_i32(w.nd_poff + w.NR_nd);
+        int32_t SB = be.read_i32(w.nd_soff + w.NR_nd);
+        w.ndp_read = be.template buf<int32_t>("ndp_read", (size_t)w.NP_nd + 1);
+        w.ndp_first = be.template buf<int32_t>("ndp_first", (size_t)w.NP_nd + 1);
+        w.ndp_n = be.template buf<int32_t>("ndp_n", (size_t)w.NP_nd + 1);
+        w.ndp_sym = be.template buf<uint8_t>("ndp_sym", (size_t)SB + 16);
+        be.launch("nodepth_fill", w.NR_nd, NdPairFill{w});
+        if (w.NP_nd > 0) be.launch("nodepth_walk", w.NP_nd, NdWalk{w});
         be.exscan_i32(w.ndmark, w.ndidx, (int64_t)C + 1);
         be.exscan_i32(w.vcap, w.koff, (int64_t)C + 1);
         w.NRC = be.read_i32(w.ndidx + C);
@@ -681,10 +775,17 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
         w.wcand = be.template buf<int32_t>("wcand", (size_t)w.NW + 1);
         w.wsoff = be.template buf<int32_t>("wsoff", (size_t)w.NW + 1);
         w.wbest = be.template buf<int32_t>("wbest", (size_t)w.NW + 1);
+        w.wp_cnt = be.template buf<int32_t>("wp_cnt", (size_t)w.NW + 1);
+        w.wp_off = be.template buf<int32_t>("wp_off", (size_t)w.NW + 1);
         be.launch("window_count", (int64_t)w.NW + 1, WindowCount{w});
         be.exscan_i32(w.wcand, w.wsoff, (int64_t)w.NW + 1);
+        be.exscan_i32(w.wp_cnt, w.wp_off, (int64_t)w.NW + 1);
         int32_t WS = be.read_i32(w.wsoff + w.NW);
+        w.NP_w = be.read_i32(w.wp_off + w.NW);
         w.wscratch = be.template buf<int32_t>("wscratch", (size_t)WS + 4);
+        w.wp_read = be.template buf<int32_t>("wp_read", (size_t)w.NP_w + 1);
+        be.launch("window_fill", w.NW, WinPairFill{w});
+        be.launch("window_walk", w.NP_w, WinWalk{w});
         be.launch("window_vote", w.NW, WindowVote{w});
         be.launch("window_apply", w.NW, WindowApply{w});
     }
