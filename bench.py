@@ -210,7 +210,7 @@ def main():
       for k in range(N_ROTATE):
         extra = dict(lowercase_frac=0.0) if t == 1 else TASK2_DRAFT
         p = E.synth_params(seed=SEED0 + 1000 * rank + k + 100 * t, **extra, **WORKLOAD)
-        sh = E.Shard.synthetic(p, 0, WORKLOAD["n_contigs"], with_qual=(t == 2), threads=max(1, (os.cpu_count() or 8) // max(1, args.gpus)))
+        sh = E.Shard.synthetic(p, 0, WORKLOAD["n_contigs"], with_qual=(2 if t == 2 else 0), threads=max(1, (os.cpu_count() or 8) // max(1, args.gpus)))
         a = sh.arrays()
         pin = {k2: torch.from_numpy(v.copy()).pin_memory() for k2, v in a.items() if k2 in ("ctg_seq", "rec_off", "rec", "qual_off", "qual")}
         res = {k2: t.to(dev) for k2, t in pin.items()}

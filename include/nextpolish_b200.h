@@ -149,7 +149,11 @@ typedef struct {
 
 /* ---- host side: FASTA/BAM -> packed shard (own BGZF/BAM/BAI/FASTA reader; zlib only) ---- */
 typedef struct np_shard np_shard;
-/* names == NULL or n_names == 0: every contig of the FASTA, in FASTA order. */
+/* names == NULL or n_names == 0: every contig of the FASTA, in FASTA order.
+ * with_qual: 0 = no quality stream (task 1), 1 = qualities of every read, 2 = qualities only of reads
+ * whose reference span contains a lowercase draft base — the only reads task 2 can consult (every
+ * k-mer window contains a lowercase column and its candidate reads span it); the engine reports an
+ * error if a window candidate lacks its qualities. */
 np_shard* np_shard_load(const char* fasta, const char* bam, const char* const* names,
                         int32_t n_names, int32_t with_qual, int32_t threads);
 void      np_shard_view_of(const np_shard* shard, np_shard_view* out);

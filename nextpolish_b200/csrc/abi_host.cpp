@@ -90,7 +90,7 @@ np_shard* np_shard_load(const char* fasta, const char* bam, const char* const* n
     for (int32_t i = 0; names && i < n_names; i++) nm.emplace_back(names[i]);
     np_shard* sh = new np_shard();
     std::string err;
-    if (!np::shard_load(fasta, bam ? bam : "", nm, with_qual != 0, threads > 0 ? threads : 1, sh->s, err)) {
+    if (!np::shard_load(fasta, bam ? bam : "", nm, with_qual, threads > 0 ? threads : 1, sh->s, err)) {
         np::set_error("np_shard_load: " + err);
         delete sh;
         return nullptr;
@@ -116,7 +116,7 @@ np_shard* np_synth_shard(const np_synth_params* p, int32_t contig_lo, int32_t co
     if (!p) { np::set_error("np_synth_shard: params is NULL"); return nullptr; }
     np_shard* sh = new np_shard();
     std::string err;
-    if (!np::synth_shard(*p, contig_lo, contig_hi, with_qual != 0, threads > 0 ? threads : 1, sh->s, err)) {
+    if (!np::synth_shard(*p, contig_lo, contig_hi, with_qual, threads > 0 ? threads : 1, sh->s, err)) {
         np::set_error("np_synth_shard: " + err);
         delete sh;
         return nullptr;

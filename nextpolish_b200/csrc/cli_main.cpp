@@ -40,7 +40,7 @@ int main(int argc, char* argv[]) {
     if (argc != 4) { printf("%s %s fastafn lgsbam\n", argv[0], argv[1]); return 0; }
     time_t t0 = time(nullptr);
     Configure* cfg = config_init(argv[2], argv[3], nullptr);
-    np_shard* sh = np_shard_load(argv[2], argv[3], nullptr, 0, step == 2, 8);
+    np_shard* sh = np_shard_load(argv[2], argv[3], nullptr, 0, step == 2 ? 2 : 0, 8);
     if (!sh) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
     np_shard_view v; np_shard_view_of(sh, &v);
     np_engine* e = np_engine_create(getenv("NEXTPOLISH_B200_DEVICE") ? atoi(getenv("NEXTPOLISH_B200_DEVICE")) : 0);

@@ -377,11 +377,11 @@ static int32_t set_shard_common(np_engine* e, const np_shard_view* v, bool devic
         cudaMemcpyAsync(e->s_rec, v->rec, rec_bytes, cudaMemcpyHostToDevice, s);
         d.ctg_seq = (const uint8_t*)e->s_seq; d.rec_off = (const uint32_t*)e->s_recoff; d.rec = (const uint8_t*)e->s_rec;
         d.qual_off = nullptr; d.qual = nullptr;
-        if (v->qual && v->qual_off) {
+        if (v->qual_off) {
             if (!dev_reserve(e, &e->s_qoff, &e->cap_qoff, ((size_t)v->n_reads + 1) * 4) ||
                 !dev_reserve(e, &e->s_qual, &e->cap_qual, qual_bytes + 16)) return NP_ERR_CUDA;
             cudaMemcpyAsync(e->s_qoff, v->qual_off, ((size_t)v->n_reads + 1) * 4, cudaMemcpyHostToDevice, s);
-            cudaMemcpyAsync(e->s_qual, v->qual, qual_bytes, cudaMemcpyHostToDevice, s);
+            if (qual_bytes) cudaMemcpyAsync(e->s_qual, v->qual, qual_bytes, cudaMemcpyHostToDevice, s);
             d.qual_off = (const uint32_t*)e->s_qoff; d.qual = (const uint8_t*)e->s_qual;
         }
     }
@@ -406,13 +406,13 @@ int32_t np_engine_run(np_engine* e, int32_t task, const Configure* cfg) {
         else err = npe::run_score_chain_v2(e->be, e->d, e->h_ctg_off.data(), &e->st, &e->vs);
     }
     else if (task == NP_TASK_KMER_COUNT) {
-        if (!e->d.qual || !e->d.qual_off) { np::set_error("np_engine_run: task 2 needs the quality stream (load the shard with_qual)"); return NP_ERR_ARG; }
+        if (!e->d.qual_off) { np::set_error("np_engine_run: task 2 needs the quality stream (load the shard with_qual)"); return NP_ERR_ARG; }
         err = npe::run_kmer_count(e->be, e->d, &e->st);
     } else { np::set_error("np_engine_run: unknown task"); return NP_ERR_ARG; }
     if (!e->be.ok) { np::set_error("CUDA failure: " + e->be.msg); return NP_ERR_CUDA; }
     if (err) {
         char b[160];
-        snprintf(b, sizeof b, "device error word 0x%x (1=insertion overflow 2=depth>=65535 4=missing score 8=column string bound 16=no-depth regions share an endpoint 32=region scratch)", err);
+        snprintf(b, sizeof b, "device error word 0x%x (1=insertion overflow 2=depth>=65535 4=missing score 8=column string bound 16=no-depth regions share an endpoint 32=region scratch 64=window candidate without qualities)", err);
         np::set_error(b);
         return NP_ERR_LIMIT;
     }
@@ -504,7 +504,7 @@ static PolishResult* run_one_contig(const char* tigname, Configure* cfg, int tas
     if (!tigname || !cfg || !cfg->fastafn) { fprintf(stderr, "nextpolish_b200: bad arguments\n"); exit(1); }
     np::Shard sh; std::string err;
     std::vector<std::string> names{std::string(tigname)};
-    if (!np::shard_load(cfg->fastafn, cfg->bamfn ? cfg->bamfn : "", names, task == NP_TASK_KMER_COUNT, 4, sh, err)) {
+    if (!np::shard_load(cfg->fastafn, cfg->bamfn ? cfg->bamfn : "", names, task == NP_TASK_KMER_COUNT ? 2 : 0, 4, sh, err)) {
         fprintf(stderr, "nextpolish_b200: %s\n", err.c_str());
         exit(1);
     }

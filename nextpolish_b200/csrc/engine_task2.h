@@ -68,7 +68,7 @@ struct Dev2 {
     int32_t NP_w;
 };
 
-enum { ERR_SHARED_ENDPOINT = 16, ERR_REGION_SCRATCH = 32 };
+enum { ERR_SHARED_ENDPOINT = 16, ERR_REGION_SCRATCH = 32, ERR_QUAL_MISSING = 64 };
 
 // ---- lowercase runs ---------------------------------------------------------------------------
 NP_HD bool pos_flagged(const Dev& d, int32_t p) { uint32_t ch = d.ctg_seq[p]; return ch >= 97 && ch <= 122; }
@@ -542,7 +542,7 @@ struct KmerVisitor {     // ss_parse_read_kmer's appends (kmercount.c:389-440); 
         if (length < cap) region[length] = (uint8_t)s;
         length++;
         if (subgap) del++;
-        if (qpos >= 0) qual += q[qpos];
+        if (qpos >= 0 && q) qual += q[qpos];
     }
     int32_t* err;
     NP_HD void overflow() { *err |= ERR_INS_OVERFLOW; }
@@ -563,7 +563,15 @@ struct WinWalk {         // per (window, read) pair: the read's column string ov
         if (j < ncand && d.r_level[r] != 2) return;            // only level-2 candidates are parsed (kmercount.c:197)
         int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
         Rec rc = load_rec(d.rec, d.rec_off, r);
-        KmerVisitor v{(uint8_t*)slot, len, 0, 0, 0, 0, d.qual + (size_t)d.qual_off[r] * 16, d.err};
+        const uint8_t* qp = d.qual + (size_t)d.qual_off[r] * 16;
+        if (d.qual_off[r + 1] == d.qual_off[r] && rc.l_qseq > 0) {
+            // sparse quality stream: a spanning candidate always overlaps the window's lowercase column and
+            // therefore has qualities; the stale record (slot ncand) may not — it can then never be full
+            // length, so its quality sum is irrelevant
+            if (j < ncand) { *d.err |= ERR_QUAL_MISSING; return; }
+            qp = nullptr;
+        }
+        KmerVisitor v{(uint8_t*)slot, len, 0, 0, 0, 0, qp, d.err};
         walk_read(rc, d.ctg_goff[k], s, e, d.r_qstart[r], d.r_qend[r], d.colbase, v);
         meta[0] = v.length;
         meta[1] = (v.length > 0 && v.length != v.del) ? v.qual / (v.length - v.del) : 0;   // kmercount.c:457-462

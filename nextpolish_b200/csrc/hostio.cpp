@@ -392,7 +392,14 @@ void Shard::view(np_shard_view* v) const {
     v->rec_off = rec_off.data();
     v->rec = rec.data();
     v->qual_off = with_qual ? qual_off.data() : nullptr;
-    v->qual = with_qual ? qual.data() : nullptr;
+    static const uint8_t kNoQual[16] = {0};
+    v->qual = with_qual ? (qual.empty() ? kNoQual : qual.data()) : nullptr;   // non-null even when the sparse stream is empty
+}
+
+void Shard::begin_contig(const uint8_t* seq, size_t len) {
+    if (qual_mode != 2) return;
+    cur_lc.assign(len + 1, 0);
+    for (size_t i = 0; i < len; i++) cur_lc[i + 1] = cur_lc[i] + (seq[i] >= 97 && seq[i] <= 122 ? 1 : 0);
 }
 
 bool shard_pack_record(const BamRec& r, Shard& s, std::string& err) {
@@ -416,8 +423,20 @@ bool shard_pack_record(const BamRec& r, Shard& s, std::string& err) {
     memcpy(d + 16 + 4 * (size_t)r.n_cigar, r.seq, ((size_t)r.l_qseq + 1) / 2);
     s.rec_off.push_back((uint32_t)((o + padded) / 16));
     s.alg_bytes += (int64_t)body;
-    s.qual_bytes += r.l_qseq;
     if (s.with_qual) {
+        bool keep = true;
+        if (s.qual_mode == 2) {
+            int64_t end = r.pos;
+            for (uint32_t i = 0; i < r.n_cigar; i++) {
+                uint32_t c; memcpy(&c, (const uint8_t*)r.cigar + 4 * (size_t)i, 4);
+                uint32_t op = c & 0xf;
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) end += c >> 4;
+            }
+            int64_t L = (int64_t)s.cur_lc.size() - 1, a = r.pos < 0 ? 0 : r.pos, b = end > L ? L : end;
+            keep = a < b && s.cur_lc[(size_t)b] - s.cur_lc[(size_t)a] > 0;
+        }
+        if (!keep) { s.qual_off.push_back(s.qual_off.back()); return true; }
+        s.qual_bytes += r.l_qseq;
         size_t qo = s.qual.size(), qp = ((size_t)r.l_qseq + 15) & ~(size_t)15;
         s.qual.resize(qo + qp, 0);
         memcpy(s.qual.data() + qo, r.qual, (size_t)r.l_qseq);
@@ -427,7 +446,7 @@ bool shard_pack_record(const BamRec& r, Shard& s, std::string& err) {
 }
 
 bool shard_load(const std::string& fasta, const std::string& bam,
-                const std::vector<std::string>& names, bool with_qual, int threads,
+                const std::vector<std::string>& names, int with_qual, int threads,
                 Shard& out, std::string& err) {
     std::vector<FastaRecord> recs;
     if (!fasta_load(fasta, names, recs, err)) return false;
@@ -448,7 +467,8 @@ bool shard_load(const std::string& fasta, const std::string& bam,
     std::stable_sort(slots.begin(), slots.end(), [](const Slot& a, const Slot& b) { return a.tid < b.tid; });
 
     out = Shard();
-    out.with_qual = with_qual;
+    out.with_qual = with_qual != 0;
+    out.qual_mode = with_qual;
     out.ctg_off.push_back(0);
     out.rec_off.push_back(0);
     if (with_qual) out.qual_off.push_back(0);
@@ -472,6 +492,8 @@ bool shard_load(const std::string& fasta, const std::string& bam,
             auto it = slot_of_tid.find(r.tid);
             if (it == slot_of_tid.end() || r.n_cigar == 0) return true;
             if (it->second < cur_slot) { err = "BAM is not coordinate sorted"; ok = false; return false; }
+            if (it->second != cur_slot)
+                out.begin_contig(out.ctg_seq.data() + out.ctg_off[(size_t)it->second], (size_t)(out.ctg_off[(size_t)it->second + 1] - out.ctg_off[(size_t)it->second]));
             cur_slot = it->second;
             if (!shard_pack_record(r, out, err)) { ok = false; return false; }
             counts[(size_t)cur_slot]++;
@@ -486,6 +508,7 @@ bool shard_load(const std::string& fasta, const std::string& bam,
                 uint64_t voff = 0; bool has = true; std::string e2;
                 if (!bf.bai_first_offset(tid, &voff, &has, e2)) { voff = 0; has = true; }  // no index: scan
                 if (!has) continue;
+                out.begin_contig(out.ctg_seq.data() + out.ctg_off[k], (size_t)(out.ctg_off[k + 1] - out.ctg_off[k]));
                 auto visit_one = [&](const BamRec& r) -> bool {
                     if (r.tid < 0 || r.tid > tid) return false;
                     if (r.tid < tid || r.n_cigar == 0) return true;

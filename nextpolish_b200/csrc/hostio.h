@@ -83,14 +83,20 @@ struct Shard {
     int64_t alg_bytes = 0;              // sum over reads of 16 + 4*n_cigar + ceil(l_qseq/2)
     int64_t qual_bytes = 0;             // sum over reads of l_qseq
     bool with_qual = false;
+    // quality mode: 1 = every read, 2 = only reads whose reference span contains a lowercase draft base
+    // (the only reads whose qualities task 2 can consult: every k-mer window contains a lowercase column
+    // and its candidates span the whole window, kmercount.c:128-173,196-199; contig.c:1027)
+    int qual_mode = 0;
+    std::vector<int32_t> cur_lc;        // lowercase prefix counts of the contig being packed (mode 2)
+    void begin_contig(const uint8_t* seq, size_t len);
     void view(np_shard_view* v) const;
 };
 bool shard_pack_record(const BamRec& r, Shard& s, std::string& err);
-bool synth_shard(const np_synth_params& P, int32_t lo, int32_t hi, bool with_qual, int threads,
+bool synth_shard(const np_synth_params& P, int32_t lo, int32_t hi, int with_qual, int threads,
                  Shard& out, std::string& err);
 
 bool shard_load(const std::string& fasta, const std::string& bam,
-                const std::vector<std::string>& names, bool with_qual, int threads,
+                const std::vector<std::string>& names, int with_qual, int threads,
                 Shard& out, std::string& err);
 
 // config.c:80-101 (bam_tlen): mean insert size estimate over the head of the BAM.

@@ -263,7 +263,7 @@ static void run_parallel(int n, int threads, const std::function<void(int)>& fn)
 namespace np {
 
 // Packed shard straight from the generator (contigs [lo,hi) of the synthetic genome).
-bool synth_shard(const np_synth_params& P, int32_t lo, int32_t hi, bool with_qual, int threads, Shard& out, std::string& err) {
+bool synth_shard(const np_synth_params& P, int32_t lo, int32_t hi, int with_qual, int threads, Shard& out, std::string& err) {
     std::vector<int64_t> len = contig_lengths(P);
     if (lo < 0 || hi > P.n_contigs || lo > hi) { err = "synth_shard: bad contig range"; return false; }
     int n = hi - lo;
@@ -273,9 +273,11 @@ bool synth_shard(const np_synth_params& P, int32_t lo, int32_t hi, bool with_qua
         ContigSim cs;
         simulate_contig(P, lo + k, len[(size_t)(lo + k)], cs);
         Shard& s = parts[(size_t)k];
-        s.with_qual = with_qual;
+        s.with_qual = with_qual != 0;
+        s.qual_mode = with_qual;
         s.names.push_back(cs.name);
         s.ctg_seq.assign(cs.draft.begin(), cs.draft.end());
+        s.begin_contig(s.ctg_seq.data(), s.ctg_seq.size());
         s.rec_off.push_back(0); if (with_qual) s.qual_off.push_back(0);
         for (auto& o : cs.order) {
             const uint8_t* p = cs.recs.data() + o.second + 4;
@@ -292,7 +294,8 @@ bool synth_shard(const np_synth_params& P, int32_t lo, int32_t hi, bool with_qua
     });
     for (auto& e : errs) if (!e.empty()) { err = e; return false; }
     out = Shard();
-    out.with_qual = with_qual;
+    out.with_qual = with_qual != 0;
+    out.qual_mode = with_qual;
     out.ctg_off.push_back(0); out.ctg_read_off.push_back(0); out.rec_off.push_back(0);
     if (with_qual) out.qual_off.push_back(0);
     for (auto& s : parts) {

@@ -62,6 +62,7 @@ class Shard:
 
     @classmethod
     def load(cls, fasta, bam, names=None, with_qual=False, threads=8):
+        """with_qual: False/0 none, True/1 every read, 2 only reads overlapping lowercase draft bases."""
         arr, n = None, 0
         if names:
             n = len(names)

@@ -100,7 +100,7 @@ def main(argv=None):
               "max_clip_ratio_sgs", "max_clip_ratio_lgs"):
         setattr(c, f, getattr(args, f))
     if names:
-        shard = E.Shard.load(args.genome, args.bam_sgs, names=names, with_qual=(args.task == 2), threads=max(1, args.process))
+        shard = E.Shard.load(args.genome, args.bam_sgs, names=names, with_qual=(2 if args.task == 2 else 0), threads=max(1, args.process))
         eng = E.Engine(int(os.environ.get("NEXTPOLISH_B200_DEVICE", "0")))
         seqs = eng.polish(shard, args.task, cfg)
         for name in names:                               # the reference's order is completion order; ours is block order

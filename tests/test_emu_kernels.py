@@ -81,3 +81,14 @@ def test_emulated_fused_window_kernel_fuzz(E, oracle, emu, seed):
     want = run_checker(oracle.np_oracle_run, sh, 1, cfg)
     got = run_checker(emu.np_emu_run_impl, sh, 1, cfg, (None, 2))
     assert got == want
+
+
+@pytest.mark.parametrize("case", ["lower", "lower_shallow", "noisy"])
+def test_emulated_task2_with_sparse_quality_stream(E, oracle, emu, case):
+    dense = E.Shard.synthetic(E.synth_params(**CASES[case]), 0, CASES[case]["n_contigs"], with_qual=1)
+    sparse = E.Shard.synthetic(E.synth_params(**CASES[case]), 0, CASES[case]["n_contigs"], with_qual=2)
+    assert len(sparse.arrays()["qual"]) < len(dense.arrays()["qual"])
+    cfg = E.default_config(b"")
+    cfg.contents.read_tlen = 1750
+    want = run_checker(oracle.np_oracle_run, dense, 2, cfg)
+    assert run_checker(emu.np_emu_run, sparse, 2, cfg, (None,)) == want

@@ -43,7 +43,7 @@ def test_gpu_matches_reference_md5(E, eng, synth_files, case):
     estimated from the BAM head exactly like config_init does)."""
     want = json.load(open(os.path.join(GOLDEN, "synth_md5.json")))[case]
     fa, bam = synth_files(case)
-    sh = E.Shard.load(fa, bam, with_qual=True)
+    sh = E.Shard.load(fa, bam, with_qual=2)          # sparse quality stream
     cfg = E.default_config(fa, bam)
     for task in tasks(E):
         got = eng.polish(sh, task, cfg)

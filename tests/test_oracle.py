@@ -27,11 +27,13 @@ def test_oracle_vs_golden_testdata(E, oracle, step):
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
-@pytest.mark.parametrize("step", [1, 2])
-def test_oracle_vs_reference_md5(E, oracle, synth_files, case, step):
+@pytest.mark.parametrize("step,qual_mode", [(1, 1), (2, 1), (2, 2)])
+def test_oracle_vs_reference_md5(E, oracle, synth_files, case, step, qual_mode):
+    """qual_mode 2 = sparse quality stream (only reads overlapping lowercase draft bases): the reference's
+    output must still be reproduced, i.e. no other read's qualities are ever consulted."""
     want = json.load(open(os.path.join(GOLDEN, "synth_md5.json")))[case][str(step)]
     fa, bam = synth_files(case)
-    sh = E.Shard.load(fa, bam, with_qual=True)
+    sh = E.Shard.load(fa, bam, with_qual=qual_mode)
     cfg = E.default_config(fa, bam)
     got = run_checker(oracle.np_oracle_run, sh, step, cfg)
     assert {"%s_%d" % (n, step): md5(s) for n, s in got.items()} == want
