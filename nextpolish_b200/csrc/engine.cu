@@ -234,7 +234,7 @@ struct CudaBackend {
             attr_set = want;
         }
         int threads = kWinThreads;
-        if (const char* ev = getenv("NEXTPOLISH_B200_WIN_THREADS")) { int v = atoi(ev); if (v == 64 || v == 128 || v == 256) threads = v; }   // tuning only
+        if (const char* ev = getenv("NEXTPOLISH_B200_WIN_THREADS")) { int v = atoi(ev); if (v >= 64 && v <= 256 && v % 32 == 0) threads = v; }   // tuning only
         begin_timed("pileup_scan");
         k_window<<<(unsigned)g.n_win, threads, (size_t)want, stream>>>(d, g);
         CUDA_TRY(cudaGetLastError());

@@ -11,7 +11,6 @@ namespace npe {
 // CUDA: tid = threadIdx.x, nt = blockDim.x, barrier = __syncthreads; emu: tid = 0, nt = 1, no-op.
 #define NP_WINDOW_PHASES(x, tid, nt, ops, BARRIER)                 \
     npw::ph_expand(x, tid, nt, ops);      BARRIER;                  \
-    npw::ph_compare(x, tid, nt, ops);     BARRIER;                  \
     npw::ph_colinfo(x, tid, nt);          BARRIER;                  \
     npw::ph_mark_tables(x, tid, nt, ops); BARRIER;                  \
     npw::ph_tally(x, tid, nt);            BARRIER;                  \

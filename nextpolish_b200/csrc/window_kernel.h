@@ -10,8 +10,9 @@
 //   expand   one thread per read: filter level, contig_cut_read, CIGAR walk at op granularity;
 //            the read's column string (4-bit symbols, big-endian nibble order inside 32-bit words)
 //            is written to shared memory with word-parallel nibble copies (contig.c:247-358);
-//   compare  one thread per 8-column word of the draft's symbol string: XOR against the aligned
-//            word of each overlapping read -> per column "covered" and "some read disagrees";
+//   compare  fused into expand: strings are stored aligned to the draft's 8-column symbol words, so each
+//            string word is XORed against one draft word -> per column "covered" / "some read disagrees"
+//            (OR-ed into two shared-memory accumulators per word);
 //   tally    one thread per table column (disagreeing columns + right neighbours): 3-mer tallies in
 //            first-seen (BAM) order from the shared-memory strings (base.c:60-71);
 //   chain    one thread per stretch that starts in the owned range: score chain + backtrack
@@ -109,7 +110,7 @@ struct WinPlan {
         for (int64_t r = lo; r < hi; r++) {
             int32_t a = d.r_gpos[r] < e0 ? e0 : d.r_gpos[r], b = d.r_wend[r] > e1 ? e1 : d.r_wend[r];
             int32_t span = b > a ? b - a : 0;
-            strw += (span + extra + 7) / 8 + 2;
+            strw += (span + extra + 7) / 8 + 3;
         }
         uint32_t recbytes = (d.rec_off[hi] - d.rec_off[lo]) * 16u;
         g.win_rlo[w] = (int32_t)lo; g.win_rhi[w] = (int32_t)hi; g.win_strw[w] = strw;
@@ -186,16 +187,30 @@ NP_HD uint32_t nib_mask(int32_t a, int32_t b) {
 // query index q into dst string at nibble index di
 NP_HD void put_seq(uint32_t* dst, int32_t di, const uint8_t* seq, int32_t q, int32_t len) {
     const uint32_t* sw = (const uint32_t*)seq;   // seq is 4-byte aligned inside a record
-    while (len > 0) {
-        int32_t dw = di >> 3, dn = di & 7;
+    int32_t dn = di & 7;
+    if (dn) {                                    // head: finish the partially filled destination word
         int32_t take = 8 - dn < len ? 8 - dn : len;
         int32_t si = q >> 3, sn = q & 7;
         uint32_t hi = bswap32(sw[si]), lo = (sn + take > 8) ? bswap32(sw[si + 1]) : 0u;
-        uint32_t v = fsl(hi, lo, (uint32_t)sn);          // source nibbles q.. at the top
-        v >>= dn * 4;                                     // move to destination nibble dn
+        uint32_t v = fsl(hi, lo, (uint32_t)sn) >> (dn * 4);
         uint32_t m = nib_mask(dn, dn + take);
-        dst[dw] = (dst[dw] & ~m) | (v & m);
+        dst[di >> 3] = (dst[di >> 3] & ~m) | (v & m);
         di += take; q += take; len -= take;
+    }
+    int32_t dw = di >> 3, si = q >> 3;
+    uint32_t sn = (uint32_t)(q & 7);
+    if (len >= 8) {                              // body: whole destination words, one source load each
+        uint32_t cur = bswap32(sw[si]);
+        if (sn == 0) {
+            for (;;) { dst[dw++] = cur; len -= 8; si++; if (len < 8) break; cur = bswap32(sw[si]); }
+        } else {
+            do { uint32_t nxt = bswap32(sw[si + 1]); dst[dw++] = fsl(cur, nxt, sn); cur = nxt; si++; len -= 8; } while (len >= 8);
+        }
+    }
+    if (len > 0) {                               // tail
+        uint32_t hi = bswap32(sw[si]), lo = (sn + (uint32_t)len > 8u) ? bswap32(sw[si + 1]) : 0u;
+        uint32_t m = nib_mask(0, len);
+        dst[dw] = (dst[dw] & ~m) | (fsl(hi, lo, sn) & m);
     }
 }
 NP_HD void put_const(uint32_t* dst, int32_t di, int32_t len, uint32_t sym) {
@@ -261,8 +276,8 @@ struct StrWriter {
         if (lc + len > x->ncols) len = x->ncols - lc;
         if (len <= 0) return;
         if (n == 0) cs = lc;
-        int32_t di = lc - cs;
-        if (di != n || di + len > cap) { x->ctr[2] = 1; return; }
+        int32_t di = lc - (cs & ~7);                      // strings are aligned to 8-column words of the window
+        if (lc != cs + n || di + len > cap) { x->ctr[2] = 1; return; }
         if (q >= 0) put_seq(w, di, seq, q, len); else put_const(w, di, len, SYM_GAP);
         n += len;
     }
@@ -287,7 +302,7 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
         int32_t wl, hl; ref_spans(rc, &wl, &hl);
         int32_t a = gpos < x.e0 ? x.e0 : gpos, b = gpos + wl > x.e1 ? x.e1 : gpos + wl;
         int32_t span = b > a ? b - a : 0, extra = x.ncols - (x.e1 - x.e0);
-        int32_t words = (span + extra + 7) / 8 + 2;
+        int32_t words = (span + extra + 7) / 8 + 3;
         int32_t off = be.atomic_add_ret(&x.ctr[0], words);
         if (off + words > x.strw + 4) { x.ctr[2] = 1; continue; }
         StrWriter sw{&x, x.str + off, (words - 1) * 8, 0, 0, 0, false, rc.seq};
@@ -362,52 +377,26 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
             if (pos > end || pos > x.e1 + 1) break;
         }
         x.cs[i] = sw.cs; x.cn[i] = sw.n; x.so[i] = off;
-        if (sw.n > 0)
+        if (sw.n > 0) {
             for (int32_t bq = sw.cs >> 5; bq <= (sw.cs + sw.n - 1) >> 5; bq++) {
                 be.atomic_min(&x.blk[2 * bq], i);
                 be.atomic_max(&x.blk[2 * bq + 1], i + 1);
             }
+            // compare against the draft's symbol words (same alignment): per column "covered" / "disagrees"
+            const uint32_t* sp = x.str + off;
+            int32_t base = sw.cs & ~7, cw0 = base >> 3, nwd = (sw.cs + sw.n - base + 7) >> 3;
+            for (int32_t kq = 0; kq < nwd; kq++) {
+                uint32_t m = nib_mask(sw.cs - base - 8 * kq, sw.cs + sw.n - base - 8 * kq);
+                uint32_t df = (sp[kq] ^ x.refw[cw0 + kq]) & m;
+                df |= df >> 1; df |= df >> 2; df &= 0x11111111u;
+                if (df) be.atomic_or(&x.acc[2 * (cw0 + kq)], df);
+                be.atomic_or(&x.acc[2 * (cw0 + kq) + 1], m & 0x11111111u);
+            }
+        }
     }
 }
 
-// ---- phase 2: word-parallel compare ------------------------------------------------------------------
-// item = (8-column word, chunk of CMP_CHUNK reads); partial masks are OR-ed into two accumulators
-// per word (re-using the tabidx area is avoided: accumulators live at the end of the string pool)
-enum { CMP_SPLIT = 2 };
-template <class B>
-NP_HD void ph_compare(WCtx& x, int32_t tid, int32_t nt, B& be) {
-    int32_t nw = (x.ncols + 7) / 8;
-    uint32_t* acc = x.acc;
-    for (int32_t it = tid; it < nw * CMP_SPLIT; it += nt) {
-        int32_t cw = it % nw, half = it / nw;
-        int32_t blo = x.blk[2 * (cw >> 2)], bhi = x.blk[2 * (cw >> 2) + 1];
-        if (blo >= bhi) continue;
-        int32_t mid = blo + (bhi - blo + 1) / 2;
-        int32_t r0 = half == 0 ? blo : mid, r1 = half == 0 ? mid : bhi;
-        uint32_t ref = x.refw[cw], mism = 0, cov = 0;
-        int32_t c0 = cw * 8;
-        for (int32_t r = r0; r < r1; r++) {
-            int32_t n = x.cn[r];
-            int32_t off = c0 - x.cs[r];                       // read nibble index of column c0
-            if (off >= n || off <= -8) continue;
-            const uint32_t* s = x.str + x.so[r];
-            uint32_t v, m;
-            if (off >= 0) {
-                v = fsl(s[off >> 3], s[(off >> 3) + 1], (uint32_t)(off & 7));
-                m = nib_mask(0, n - off);
-            } else {
-                v = s[0] >> ((-off) * 4);
-                m = nib_mask(-off, -off + n);
-            }
-            uint32_t df = (v ^ ref) & m;
-            df |= df >> 1; df |= df >> 2;
-            mism |= df & 0x11111111u;
-            cov |= m & 0x11111111u;
-        }
-        if (mism) be.atomic_or(&acc[2 * cw], mism);
-        if (cov) be.atomic_or(&acc[2 * cw + 1], cov);
-    }
-}
+// ---- phase 2: per-column info from the accumulators the expand phase OR-ed together ---------------------
 NP_HD void ph_colinfo(WCtx& x, int32_t tid, int32_t nt) {
     for (int32_t lc = tid; lc < x.ncols; lc += nt) {
         uint32_t bit = 28 - 4 * (lc & 7);
@@ -457,15 +446,16 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
             int32_t i = lc - x.cs[r];
             if (i < 0 || i >= x.cn[r]) continue;
             const uint32_t* s = x.str + x.so[r];
+            int32_t al = x.cs[r] & 7;                       // the string starts at nibble `al` of its first word
             // symbols i-2..i of the read's string as one funnel-shifted extract
             uint32_t kk;
             if (i >= 2) {
-                int32_t a = i - 2;
+                int32_t a = i - 2 + al;
                 uint32_t v = fsl(s[a >> 3], (a & 7) > 5 ? s[(a >> 3) + 1] : 0u, (uint32_t)(a & 7));
                 kk = v >> 20;
             } else {
-                kk = be_get(s, i);
-                if (i >= 1) kk |= be_get(s, i - 1) << 4;
+                kk = be_get(s, i + al);
+                if (i >= 1) kk |= be_get(s, i - 1 + al) << 4;
             }
             votes++;
             int32_t j = 0;
