@@ -59,9 +59,12 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
     const int32_t budget = 100 * 1024, hard = 200 * 1024;
     int32_t need = 0; bool fits = false;
     std::vector<int32_t> hw_ctg, hw_p0;
-    static const int32_t kW[3] = {512, 256, 128};
+    int32_t kW[3] = {512, 256, 128};
     int wi0 = 0;
-    if (const char* ev = getenv("NEXTPOLISH_B200_WINDOW")) { int v = atoi(ev); wi0 = v == 256 ? 1 : v == 128 ? 2 : 0; }   // tuning only
+    if (const char* ev = getenv("NEXTPOLISH_B200_WINDOW")) {   // tuning only: first window size to try
+        int v = atoi(ev);
+        if (v >= 64 && v <= 2048 && v % 32 == 0) { kW[0] = v; if (v <= 256) kW[1] = v / 2 > 64 ? v / 2 : 64; if (v <= 128) kW[2] = 64; }
+    }
     for (int wi = wi0; wi < 3 && !fits; wi++) {
         g.W = kW[wi];
         hw_ctg.clear(); hw_p0.clear();

@@ -44,8 +44,9 @@ struct WinGlobals {       // extra global arrays of the fused path
     int32_t* n_unresolved;                    // [1]
 };
 
-struct TabEntry {          // one table column in shared memory (64 bytes)
+struct TabEntry {          // one table column in shared memory (128 bytes)
     uint32_t e[WK];        // kmer | count << 16, first-seen order
+    double   sc[WK];       // score per score entry (chain phase)
     uint16_t ekmer[WK];    // winning k-mer per score entry
     uint8_t  ebase[WK];    // base code per score entry, first-seen order
     uint16_t votes;
@@ -68,7 +69,7 @@ struct WCtx {             // per-window context: globals + carved shared memory
     uint8_t* colinfo;                         // per local column: 1 mism, 2 covered, 8 sub-column
     int16_t* tabidx;                          // per local column: table index or -1
     int16_t* tabcol;                          // dense list: table index -> local column
-    int32_t* lcb;                             // [npos+1] local column of every ext position (staged colbase)
+    uint16_t* lcb;                            // [npos+1] local column of every ext position (staged colbase)
     int32_t* blk;                             // [2*nblk] first / last+1 staged read overlapping each 32-column block
     TabEntry* tab;                            // aliases the record area (records are dead after expand)
     int32_t* ctr;                             // [0] string words used, [1] tables used, [2] internal error, [3] unresolved
@@ -82,7 +83,7 @@ NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int3
     uint32_t mintab = (uint32_t)(ncols / 8 + 8) * (uint32_t)sizeof(TabEntry);
     if (recarea < mintab) recarea = mintab;
     b += recarea + align16(4u * (uint32_t)(nr + 1));
-    b += align16(4u * (uint32_t)(npos + 2)) + align16(8u * (uint32_t)(ncols / 32 + 2));
+    b += align16(2u * (uint32_t)(npos + 2)) + align16(8u * (uint32_t)(ncols / 32 + 2));
     b += 3 * align16(4u * (uint32_t)nr);
     b += align16(4u * (uint32_t)(strw + 4));
     b += 3 * align16(4u * (uint32_t)(ncols / 8 + 3));
@@ -110,7 +111,7 @@ struct WinPlan {
         for (int64_t r = lo; r < hi; r++) {
             int32_t a = d.r_gpos[r] < e0 ? e0 : d.r_gpos[r], b = d.r_wend[r] > e1 ? e1 : d.r_wend[r];
             int32_t span = b > a ? b - a : 0;
-            strw += (span + extra + 7) / 8 + 3;
+            strw += (span + extra + 14) / 8 + 2;
         }
         uint32_t recbytes = (d.rec_off[hi] - d.rec_off[lo]) * 16u;
         g.win_rlo[w] = (int32_t)lo; g.win_rhi[w] = (int32_t)hi; g.win_strw[w] = strw;
@@ -145,7 +146,7 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
     x.ctr = (int32_t*)(smem + 16);
     x.rec = p; x.tab = (TabEntry*)p; p += recarea;
     x.recoff = (const uint32_t*)p; p += align16(4u * (uint32_t)(x.nr + 1));
-    x.lcb = (int32_t*)p; p += align16(4u * (uint32_t)(x.npos + 2));
+    x.lcb = (uint16_t*)p; p += align16(2u * (uint32_t)(x.npos + 2));
     x.blk = (int32_t*)p; p += align16(8u * (uint32_t)(x.ncols / 32 + 2));
     x.cs = (int32_t*)p; p += align16(4u * (uint32_t)x.nr);
     x.cn = (int32_t*)p; p += align16(4u * (uint32_t)x.nr);
@@ -230,15 +231,15 @@ NP_HD void ph_clear(WCtx& x, int32_t tid, int32_t nt) {
     for (int32_t i = tid; i < x.ncols / 8 + 3; i += nt) { x.refw[i] = 0; x.acc[2 * i] = 0; x.acc[2 * i + 1] = 0; }
     for (int32_t i = tid; i < x.ncols + 16; i += nt) x.colinfo[i] = 0;
     for (int32_t i = tid; i < x.ncols + 8; i += nt) x.tabidx[i] = -1;
-    for (int32_t i = tid; i <= x.npos; i += nt) x.lcb[i] = x.d.colbase[x.e0 + i] - x.cb0;
+    for (int32_t i = tid; i <= x.npos; i += nt) x.lcb[i] = (uint16_t)(x.d.colbase[x.e0 + i] - x.cb0);
     for (int32_t i = tid; i < x.nblk; i += nt) { x.blk[2 * i] = 0x7fffffff; x.blk[2 * i + 1] = 0; }
-    if (tid == 0) { x.ctr[0] = 0; x.ctr[1] = 0; x.ctr[2] = 0; x.ctr[3] = 0; }
+    if (tid == 0) { x.ctr[0] = 0; x.ctr[1] = 0; x.ctr[2] = 0; x.ctr[3] = 0; x.ctr[4] = 0; }
 }
 template <class B>
 NP_HD void ph_ref(WCtx& x, int32_t tid, int32_t nt, B& be) {   // one thread per ext position
     const Dev& d = x.d;
     for (int32_t p = x.e0 + tid; p < x.e1; p += nt) {
-        int32_t lc = x.lcb[p - x.e0], n = x.lcb[p - x.e0 + 1] - lc;
+        int32_t lc = x.lcb[p - x.e0], n = (int32_t)x.lcb[p - x.e0 + 1] - lc;
         uint32_t ch = d.ctg_seq[p];
         if (ch >= 97 && ch <= 122) ch -= 32;
         be.atomic_or(&x.refw[lc >> 3], base_code(ch) << (28 - ((lc & 7) << 2)));
@@ -256,8 +257,8 @@ NP_HD void ph_ref(WCtx& x, int32_t tid, int32_t nt, B& be) {   // one thread per
 NP_HD int32_t lcol(const WCtx& x, int32_t p) {     // local column of position p; virtual outside the range
     int32_t i = p - x.e0;
     if (i < 0) return i;
-    if (i > x.npos) return x.lcb[x.npos] + (i - x.npos);
-    return x.lcb[i];
+    if (i > x.npos) return (int32_t)x.lcb[x.npos] + (i - x.npos);
+    return (int32_t)x.lcb[i];
 }
 struct StrWriter {
     WCtx* x; uint32_t* w; int32_t cap;        // string words of this read, capacity in nibbles
@@ -286,7 +287,10 @@ struct StrWriter {
 template <class B>
 NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
     const Dev& d = x.d;
-    for (int32_t i = tid; i < x.nr; i += nt) {
+    (void)tid; (void)nt;
+    for (;;) {                                            // reads are handed out dynamically: no straggler round
+        int32_t i = be.atomic_add_ret(&x.ctr[4], 1);
+        if (i >= x.nr) break;
         x.cs[i] = 0; x.cn[i] = 0; x.so[i] = 0;
         const uint8_t* p = x.rec + (size_t)(x.recoff[i] - x.recoff[0]) * 16;
         const uint32_t* hw = (const uint32_t*)p;
@@ -302,7 +306,7 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
         int32_t wl, hl; ref_spans(rc, &wl, &hl);
         int32_t a = gpos < x.e0 ? x.e0 : gpos, b = gpos + wl > x.e1 ? x.e1 : gpos + wl;
         int32_t span = b > a ? b - a : 0, extra = x.ncols - (x.e1 - x.e0);
-        int32_t words = (span + extra + 7) / 8 + 3;
+        int32_t words = (span + extra + 14) / 8 + 2;
         int32_t off = be.atomic_add_ret(&x.ctr[0], words);
         if (off + words > x.strw + 4) { x.ctr[2] = 1; continue; }
         StrWriter sw{&x, x.str + off, (words - 1) * 8, 0, 0, 0, false, rc.seq};
@@ -508,32 +512,31 @@ NP_HD void ph_chain(WCtx& x, int32_t tid, int32_t nt) {
         bool ok = closed;
         for (int32_t lc = lc0; ok && lc <= lend; lc++) { int32_t ti = x.tabidx[lc]; if (ti < 0 || x.tab[ti].bad) ok = false; }
         if (!ok) { mark_unresolved(x, lc0, lend); continue; }
-        // forward score chain (contig.c:424-471)
-        double sp[WK], sc[WK]; uint8_t pb[WK]; int pn = 0; double spmax = 0;
-        bool zero_prev = true;
-        for (int32_t lc = lc0; ok && lc <= lend; lc++) {
+        // forward score chain (contig.c:424-471); scores live in the table entries (shared memory)
+        for (int32_t lc = lc0; lc <= lend; lc++) {
             TabEntry& T = x.tab[x.tabidx[lc]];
+            const TabEntry* P = lc > lc0 ? &x.tab[x.tabidx[lc - 1]] : nullptr;     // nullptr: every lookup resolves to 0
             uint32_t total = T.votes, refk = T.e[0] & 0xffffu, tot = total > 1 ? total - 1 : total;
+            const double dec = (double)tot * rate;
             int no = 0;
             for (int j = 0; j < T.nk; j++) {
                 uint32_t k = T.e[j] & 0xffffu, cnt = T.e[j] >> 16, pv = (k >> 4) & 0xfu;
                 double s = 0;
-                if (!zero_prev) {
-                    if (pv == 0) s = spmax;
-                    else { int q = 0; for (; q < pn; q++) if (pb[q] == pv) break; if (q == pn) { *d.err |= npe::ERR_MISSING_SCORE; q = 0; } s = sp[q]; }
+                if (P) {
+                    int q = P->amax;
+                    if (pv != 0) { for (q = 0; q < P->nent; q++) if (P->ebase[q] == pv) break; if (q == P->nent) { *d.err |= npe::ERR_MISSING_SCORE; q = 0; } }
+                    s = P->sc[q];
                 }
                 if (k == refk && total > 1) cnt--;
-                s = s + ((double)cnt - (double)tot * rate);
+                s = s + ((double)cnt - dec);
                 uint32_t b = k & 0xfu;
                 int q = 0; for (; q < no; q++) if (T.ebase[q] == b) break;
-                if (q == no) { T.ebase[no] = (uint8_t)b; T.ekmer[no] = (uint16_t)k; sc[no] = s; no++; }
-                else if (sc[q] < s) { sc[q] = s; T.ekmer[q] = (uint16_t)k; }
+                if (q == no) { T.ebase[no] = (uint8_t)b; T.ekmer[no] = (uint16_t)k; T.sc[no] = s; no++; }
+                else if (T.sc[q] < s) { T.sc[q] = s; T.ekmer[q] = (uint16_t)k; }
             }
-            int am = 0; double mx = sc[0];
-            for (int q = 1; q < no; q++) if (sc[q] > mx) { mx = sc[q]; am = q; }
+            int am = 0; double mx = T.sc[0];
+            for (int q = 1; q < no; q++) if (T.sc[q] > mx) { mx = T.sc[q]; am = q; }
             T.nent = (uint8_t)no; T.amax = (uint8_t)am;
-            for (int q = 0; q < no; q++) { sp[q] = sc[q]; pb[q] = T.ebase[q]; }
-            pn = no; spmax = mx; zero_prev = false;
         }
         // backtrack (contig.c:473-496)
         int32_t ent = x.tab[x.tabidx[lend]].amax;
