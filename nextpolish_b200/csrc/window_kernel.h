@@ -44,13 +44,29 @@ struct WinGlobals {       // extra global arrays of the fused path
     int32_t* n_unresolved;                    // [1]
 };
 
-struct TabEntry {          // one table column in shared memory (128 bytes)
-    uint32_t e[WK];        // kmer | count << 16, first-seen order
-    double   sc[WK];       // score per score entry (chain phase)
-    uint16_t ekmer[WK];    // winning k-mer per score entry
-    uint8_t  ebase[WK];    // base code per score entry, first-seen order
-    uint16_t votes;
-    uint8_t  nk, nent, amax, bad, pad0, pad1;
+// Table columns live in a structure-of-arrays pool (entry-major) so that the threads of a warp, which
+// work on consecutive tables, touch consecutive shared-memory words (no bank conflicts in the tally).
+enum { TAB_BYTES = 128 };  // pool bytes per table column (8*8 scores + 8*4 k-mers + 8*2 + 8 + 2 + 4, rounded)
+struct TabPool {
+    double*   sc;          // [WK][tmax] score per score entry (chain phase)
+    uint32_t* e;           // [WK][tmax] kmer | count << 16, first-seen order
+    uint16_t* ekmer;       // [WK][tmax] winning k-mer per score entry
+    uint16_t* votes;       // [tmax]
+    uint8_t*  ebase;       // [WK][tmax] base code per score entry, first-seen order
+    uint8_t  *nk, *nent, *amax, *bad;   // [tmax]
+    int32_t   tmax;
+};
+struct TabEntry {          // accessor of one table column
+    const TabPool* p; int32_t t;
+    NP_HD double&   sc(int j) const { return p->sc[j * p->tmax + t]; }
+    NP_HD uint32_t& e(int j) const { return p->e[j * p->tmax + t]; }
+    NP_HD uint16_t& ekmer(int j) const { return p->ekmer[j * p->tmax + t]; }
+    NP_HD uint8_t&  ebase(int j) const { return p->ebase[j * p->tmax + t]; }
+    NP_HD uint16_t& votes() const { return p->votes[t]; }
+    NP_HD uint8_t&  nk() const { return p->nk[t]; }
+    NP_HD uint8_t&  nent() const { return p->nent[t]; }
+    NP_HD uint8_t&  amax() const { return p->amax[t]; }
+    NP_HD uint8_t&  bad() const { return p->bad[t]; }
 };
 
 struct WCtx {             // per-window context: globals + carved shared memory
@@ -71,7 +87,7 @@ struct WCtx {             // per-window context: globals + carved shared memory
     int16_t* tabcol;                          // dense list: table index -> local column
     uint16_t* lcb;                            // [npos+1] local column of every ext position (staged colbase)
     int32_t* blk;                             // [2*nblk] first / last+1 staged read overlapping each 32-column block
-    TabEntry* tab;                            // aliases the record area (records are dead after expand)
+    TabPool tab;                              // aliases the record area (records are dead after expand)
     int32_t* ctr;                             // [0] string words used, [1] tables used, [2] internal error, [3] unresolved
 };
 
@@ -80,7 +96,7 @@ NP_HD uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int32_t strw, int32_t npos) {
     uint32_t b = 64;                                   // mbarrier + counters
     uint32_t recarea = align16(recbytes);              // later re-used as the table pool
-    uint32_t mintab = (uint32_t)(ncols / 8 + 8) * (uint32_t)sizeof(TabEntry);
+    uint32_t mintab = (uint32_t)(ncols / 8 + 8) * (uint32_t)TAB_BYTES;
     if (recarea < mintab) recarea = mintab;
     b += recarea + align16(4u * (uint32_t)(nr + 1));
     b += align16(2u * (uint32_t)(npos + 2)) + align16(8u * (uint32_t)(ncols / 32 + 2));
@@ -139,12 +155,23 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
     x.rlo = x.g.win_rlo[w]; x.nr = x.g.win_rhi[w] - x.rlo;
     x.strw = x.g.win_strw[w];
     uint32_t recbytes = (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u;
-    uint32_t recarea = align16(recbytes), mintab = (uint32_t)(x.ncols / 8 + 8) * (uint32_t)sizeof(TabEntry);
+    uint32_t recarea = align16(recbytes), mintab = (uint32_t)(x.ncols / 8 + 8) * (uint32_t)TAB_BYTES;
     if (recarea < mintab) recarea = mintab;
-    x.tmax = (int32_t)(recarea / sizeof(TabEntry));
+    x.tmax = (int32_t)(recarea / TAB_BYTES) & ~7;      // multiple of 8 keeps every array 8-byte aligned
     uint8_t* p = smem + 64;
     x.ctr = (int32_t*)(smem + 16);
-    x.rec = p; x.tab = (TabEntry*)p; p += recarea;
+    x.rec = p;
+    {   // table pool carved from the same bytes
+        uint8_t* q = p; size_t tm = (size_t)x.tmax;
+        x.tab.tmax = x.tmax;
+        x.tab.sc = (double*)q; q += 8 * WK * tm;
+        x.tab.e = (uint32_t*)q; q += 4 * WK * tm;
+        x.tab.ekmer = (uint16_t*)q; q += 2 * WK * tm;
+        x.tab.votes = (uint16_t*)q; q += 2 * tm;
+        x.tab.ebase = q; q += WK * tm;
+        x.tab.nk = q; q += tm; x.tab.nent = q; q += tm; x.tab.amax = q; q += tm; x.tab.bad = q;
+    }
+    p += recarea;
     x.recoff = (const uint32_t*)p; p += align16(4u * (uint32_t)(x.nr + 1));
     x.lcb = (uint16_t*)p; p += align16(2u * (uint32_t)(x.npos + 2));
     x.blk = (int32_t*)p; p += align16(8u * (uint32_t)(x.ncols / 32 + 2));
@@ -435,8 +462,8 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
     int32_t ntab = x.ctr[1] < x.tmax ? x.ctr[1] : x.tmax;
     for (int32_t ti = tid; ti < ntab; ti += nt) {
         int32_t lc = x.tabcol[ti];
-        TabEntry& T = x.tab[ti];
-        T.bad = 0; T.nent = 0; T.amax = 0;
+        TabEntry T{&x.tab, ti};
+        T.bad() = 0; T.nent() = 0; T.amax() = 0;
         // reference vote first (contig_as_read, contig.c:373-383)
         uint32_t k = be_get(x.refw, lc);
         if (!col_first(x, lc)) {
@@ -444,7 +471,7 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
             if (!col_first(x, lc - 1)) k |= be_get(x.refw, lc - 2) << 8;
         }
         int32_t nk = 0; uint32_t votes = 1;
-        T.e[nk++] = k | (1u << 16);
+        T.e(nk++) = k | (1u << 16);
         int32_t blo = x.blk[2 * (lc >> 5)], bhi = x.blk[2 * (lc >> 5) + 1];
         for (int32_t r = blo; r < bhi; r++) {
             int32_t i = lc - x.cs[r];
@@ -463,10 +490,10 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
             }
             votes++;
             int32_t j = 0;
-            for (; j < nk; j++) if ((T.e[j] & 0xffffu) == kk) { T.e[j] += 1u << 16; break; }
-            if (j == nk) { if (nk < WK) T.e[nk++] = kk | (1u << 16); else T.bad = 1; }
+            for (; j < nk; j++) if ((T.e(j) & 0xffffu) == kk) { T.e(j) += 1u << 16; break; }
+            if (j == nk) { if (nk < WK) T.e(nk++) = kk | (1u << 16); else T.bad() = 1; }
         }
-        T.nk = (uint8_t)nk; T.votes = (uint16_t)votes;
+        T.nk() = (uint8_t)nk; T.votes() = (uint16_t)votes;
     }
 }
 
@@ -510,52 +537,53 @@ NP_HD void ph_chain(WCtx& x, int32_t tid, int32_t nt) {
             continue;
         }
         bool ok = closed;
-        for (int32_t lc = lc0; ok && lc <= lend; lc++) { int32_t ti = x.tabidx[lc]; if (ti < 0 || x.tab[ti].bad) ok = false; }
+        for (int32_t lc = lc0; ok && lc <= lend; lc++) { int32_t ti = x.tabidx[lc]; if (ti < 0 || x.tab.bad[ti]) ok = false; }
         if (!ok) { mark_unresolved(x, lc0, lend); continue; }
         // forward score chain (contig.c:424-471); scores live in the table entries (shared memory)
         for (int32_t lc = lc0; lc <= lend; lc++) {
-            TabEntry& T = x.tab[x.tabidx[lc]];
-            const TabEntry* P = lc > lc0 ? &x.tab[x.tabidx[lc - 1]] : nullptr;     // nullptr: every lookup resolves to 0
-            uint32_t total = T.votes, refk = T.e[0] & 0xffffu, tot = total > 1 ? total - 1 : total;
+            TabEntry T{&x.tab, x.tabidx[lc]};
+            const bool hasP = lc > lc0;                                          // first column: every lookup resolves to 0
+            TabEntry P{&x.tab, hasP ? x.tabidx[lc - 1] : 0};
+            uint32_t total = T.votes(), refk = T.e(0) & 0xffffu, tot = total > 1 ? total - 1 : total;
             const double dec = (double)tot * rate;
             int no = 0;
-            for (int j = 0; j < T.nk; j++) {
-                uint32_t k = T.e[j] & 0xffffu, cnt = T.e[j] >> 16, pv = (k >> 4) & 0xfu;
+            for (int j = 0; j < T.nk(); j++) {
+                uint32_t k = T.e(j) & 0xffffu, cnt = T.e(j) >> 16, pv = (k >> 4) & 0xfu;
                 double s = 0;
-                if (P) {
-                    int q = P->amax;
-                    if (pv != 0) { for (q = 0; q < P->nent; q++) if (P->ebase[q] == pv) break; if (q == P->nent) { *d.err |= npe::ERR_MISSING_SCORE; q = 0; } }
-                    s = P->sc[q];
+                if (hasP) {
+                    int q = P.amax();
+                    if (pv != 0) { for (q = 0; q < P.nent(); q++) if (P.ebase(q) == pv) break; if (q == P.nent()) { *d.err |= npe::ERR_MISSING_SCORE; q = 0; } }
+                    s = P.sc(q);
                 }
                 if (k == refk && total > 1) cnt--;
                 s = s + ((double)cnt - dec);
                 uint32_t b = k & 0xfu;
-                int q = 0; for (; q < no; q++) if (T.ebase[q] == b) break;
-                if (q == no) { T.ebase[no] = (uint8_t)b; T.ekmer[no] = (uint16_t)k; T.sc[no] = s; no++; }
-                else if (T.sc[q] < s) { T.sc[q] = s; T.ekmer[q] = (uint16_t)k; }
+                int q = 0; for (; q < no; q++) if (T.ebase(q) == b) break;
+                if (q == no) { T.ebase(no) = (uint8_t)b; T.ekmer(no) = (uint16_t)k; T.sc(no) = s; no++; }
+                else if (T.sc(q) < s) { T.sc(q) = s; T.ekmer(q) = (uint16_t)k; }
             }
-            int am = 0; double mx = T.sc[0];
-            for (int q = 1; q < no; q++) if (T.sc[q] > mx) { mx = T.sc[q]; am = q; }
-            T.nent = (uint8_t)no; T.amax = (uint8_t)am;
+            int am = 0; double mx = T.sc(0);
+            for (int q = 1; q < no; q++) if (T.sc(q) > mx) { mx = T.sc(q); am = q; }
+            T.nent() = (uint8_t)no; T.amax() = (uint8_t)am;
         }
         // backtrack (contig.c:473-496)
-        int32_t ent = x.tab[x.tabidx[lend]].amax;
+        int32_t ent = x.tab.amax[x.tabidx[lend]];
         for (int32_t lc = lend;; lc--) {
-            TabEntry& T = x.tab[x.tabidx[lc]];
-            uint32_t chosen = T.ebase[ent], support = 0;
-            for (int j = 0; j < T.nk; j++) if ((T.e[j] & 0xfu) == chosen) support += T.e[j] >> 16;
+            TabEntry T{&x.tab, x.tabidx[lc]};
+            uint32_t chosen = T.ebase(ent), support = 0;
+            for (int j = 0; j < T.nk(); j++) if ((T.e(j) & 0xfu) == chosen) support += T.e(j) >> 16;
             int32_t c = x.cb0 + lc;
             uint8_t fl = 0;
             if (col_first(x, lc)) fl |= CF_FIRST;
             if (col_last(x, lc)) fl |= CF_LAST;
-            if (T.votes == 1) fl |= FLAG_ZERO;
-            if (support / (double)T.votes < d.P.min_count_ratio_skip) fl |= FLAG_COVERAGE;
+            if (T.votes() == 1) fl |= FLAG_ZERO;
+            if (support / (double)T.votes() < d.P.min_count_ratio_skip) fl |= FLAG_COVERAGE;
             d.obase[c] = (uint8_t)chosen; d.oflag[c] = fl; d.needi[c] = 0;
             if (lc == lc0) break;
-            uint32_t k = T.ekmer[ent], pv = (k >> 4) & 0xfu;
-            TabEntry& P = x.tab[x.tabidx[lc - 1]];
-            if (pv == 0) ent = P.amax;
-            else { int q = 0; for (; q < P.nent; q++) if (P.ebase[q] == pv) break; if (q == P.nent) { *d.err |= npe::ERR_MISSING_SCORE; q = 0; } ent = q; }
+            uint32_t k = T.ekmer(ent), pv = (k >> 4) & 0xfu;
+            TabEntry P{&x.tab, x.tabidx[lc - 1]};
+            if (pv == 0) ent = P.amax();
+            else { int q = 0; for (; q < P.nent(); q++) if (P.ebase(q) == pv) break; if (q == P.nent()) { *d.err |= npe::ERR_MISSING_SCORE; q = 0; } ent = q; }
         }
     }
 }
@@ -571,7 +599,7 @@ NP_HD void ph_anchors(WCtx& x, int32_t tid, int32_t nt) {
             int32_t ti = x.tabidx[lc];
             // votes of table columns are needed by the fallback tables (capacity); recount if no table
             uint32_t v = 1;
-            if (ti >= 0) v = x.tab[ti].votes;
+            if (ti >= 0) v = x.tab.votes[ti];
             else for (int32_t r = 0; r < x.nr; r++) { int32_t i = lc - x.cs[r]; if (i >= 0 && i < x.cn[r]) v++; }
             d.votes[c] = v;
             continue;
