@@ -285,6 +285,7 @@ def main():
     ktimes = {}
     kt_by_task = {}
     wstats = None
+    eng.set_timing(True)
     for t in tasks:
         eng.adopt_device(views_dev[t][0])
         eng.run(t, cfg)
@@ -295,6 +296,7 @@ def main():
         kt_by_task[t] = kt
         for n, v in kt:
             ktimes[n] = ktimes.get(n, 0.0) + v
+    eng.set_timing(False)
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
     if sampler:
         sampler.stop_flag = True

@@ -196,6 +196,9 @@ const uint8_t* np_engine_result_device(np_engine* e);
 /* Per-kernel device time (ms) of the last run, measured with CUDA events on the engine
  * stream; names[i] points to static strings. Returns the number of entries written. */
 int32_t np_engine_kernel_times(np_engine* e, const char** names, float* ms, int32_t cap);
+/* Per-kernel CUDA-event timing is off by default (two event records per launch cost ~0.2 ms per step);
+ * switch it on before a run whose np_engine_kernel_times() you want to read. */
+void    np_engine_set_timing(np_engine* e, int32_t on);
 /* Number of kernel launches issued by the last np_engine_run. */
 int32_t np_engine_launch_count(np_engine* e);
 /* Fused pileup-scan kernel statistics of the last task-1 run:

@@ -65,7 +65,7 @@ EXPORTS = [  # every symbol include/nextpolish_b200.h declares
     "np_shard_algorithmic_bytes",
     "np_engine_create", "np_engine_destroy", "np_last_error", "np_engine_upload", "np_engine_adopt_device",
     "np_engine_run", "np_engine_sync", "np_engine_result_bytes", "np_engine_download",
-    "np_engine_result_device", "np_engine_copy_result", "np_engine_kernel_times", "np_engine_launch_count", "np_engine_window_stats", "np_engine_stream",
+    "np_engine_result_device", "np_engine_copy_result", "np_engine_kernel_times", "np_engine_set_timing", "np_engine_launch_count", "np_engine_window_stats", "np_engine_stream",
     "np_polish_host", "np_synth_write", "np_synth_shard",
 ]
 
@@ -109,6 +109,8 @@ def load(path=None):
     L.np_engine_result_device.argtypes = [vp]
     L.np_engine_result_device.restype = vp
     L.np_engine_kernel_times.argtypes = [vp, vp, vp, i32]
+    L.np_engine_set_timing.argtypes = [vp, i32]
+    L.np_engine_set_timing.restype = None
     L.np_engine_launch_count.argtypes = [vp]
     L.np_engine_window_stats.argtypes = [vp, vp]
     L.np_engine_stream.argtypes = [vp]

@@ -137,7 +137,7 @@ struct CudaBackend {
     bool ok = true; std::string msg;
     // per-launch timing
     struct Timed { const char* name; cudaEvent_t a, b; };
-    std::vector<Timed> timed; size_t n_timed = 0; bool timing = true;
+    std::vector<Timed> timed; size_t n_timed = 0; bool timing = false;   // off unless np_engine_set_timing(e, 1)
     int32_t launches = 0;
 
     void fail(const char* what, cudaError_t e) {
@@ -240,6 +240,14 @@ struct CudaBackend {
         CUDA_TRY(cudaGetLastError());
         launches++;
         end_timed();
+    }
+    // reads up to 8 scalars with ONE stream synchronisation
+    void read_many(const int32_t* const* ptrs, int n, int32_t* out) {
+        for (int i = 0; i < n; i++) out[i] = 0;
+        if (!ok) return;
+        for (int i = 0; i < n; i++) CUDA_TRY(cudaMemcpyAsync(h_scalar + i, ptrs[i], sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (ok) for (int i = 0; i < n; i++) out[i] = h_scalar[i];
     }
     int32_t read_i32(const int32_t* p) {
         if (!ok) return 0;
@@ -442,6 +450,8 @@ int32_t np_engine_download(np_engine* e, uint8_t* out_seq, int64_t out_cap, int6
     if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
     return NP_OK;
 }
+
+void np_engine_set_timing(np_engine* e, int32_t on) { if (e) { e->be.timing = on != 0; e->be.n_timed = 0; } }
 
 int32_t np_engine_window_stats(np_engine* e, int32_t* out5) {
     if (!e) return NP_ERR_ARG;

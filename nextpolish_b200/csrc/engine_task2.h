@@ -29,6 +29,8 @@ struct Dev2 {
     int32_t *run_s, *run_e;      // [n_runs]
     int32_t n_runs;
     // region lists per contig (slices [ctg_run_off[k], ctg_run_off[k+1]) * 2 ints)
+    int32_t *gnd, *gkm;          // [2*n_runs+2] regions of every run group, written at the group head's slot
+    int32_t *gcnt_nd, *gcnt_km;  // [n_runs] regions emitted by the group headed at this run (0: not a head)
     int32_t *nd_reg, *km_reg;    // [2*n_runs+2] (start,end) pairs, global positions
     int32_t *nd_cnt, *km_cnt;    // per contig: number of regions (pairs)
     int32_t *nd_off, *km_off;    // exclusive scans of the counts
@@ -163,18 +165,55 @@ NP_HD int32_t merge_regions(int32_t* l, int32_t npairs) {
     return length;
 }
 
-struct ContigRegions {   // one thread per contig
+// Right end of the region a cluster whose last run ends at position e would be extended to by
+// contig_brim_* (contig.c:498-517); it depends on e only.
+NP_HD int32_t reach_right(const Dev& d, bool with_ext, int32_t ext, int32_t gs, int32_t ge, int32_t e) {
+    int32_t a = e, b = e;
+    brim_pos(d, with_ext, ext, gs, ge, &a, &b);
+    return b;
+}
+// The region scan (contig.c:519-563) is sequential because an emitted region's extension can swallow
+// the start of the next cluster (`i = qend`).  Between run r and r+1 nothing carries over when the gap
+// closes the cluster AND the extension of a cluster ending at r cannot reach run r+1: such "hard
+// boundaries" cut the run list into groups that are scanned independently, one thread per group.
+NP_HD bool hard_boundary(const Dev& d, const int32_t* run_s, const int32_t* run_e, int32_t r, int32_t gs, int32_t ge,
+                         int32_t gap, bool with_ext, int32_t ext) {
+    if (run_s[r + 1] - run_e[r] - 1 <= gap) return false;
+    return reach_right(d, with_ext, ext, gs, ge, run_e[r]) < run_s[r + 1];
+}
+struct RegionGroups {    // one thread per lowercase run and variant (0: no-depth regions, 1: k-mer regions)
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t it, B&) const {
+        const Dev& d = w.d;
+        int32_t r = (int32_t)(it >> 1), variant = (int32_t)(it & 1);
+        int32_t* cnt = variant ? w.gcnt_km : w.gcnt_nd;
+        int32_t* out = (variant ? w.gkm : w.gnd) + 2 * (size_t)r;
+        int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, w.run_s[r]);
+        int32_t gs = d.ctg_goff[k], ge = d.ctg_goff[k + 1] - 1;
+        int32_t r0 = w.rs_idx[gs], r1 = w.rs_idx[ge + 1];
+        int32_t gap = variant ? d.P.min_len_inter_kmer : 0, con = variant ? 0 : d.P.min_len_ldr;
+        bool with_ext = variant != 0; int32_t ext = d.P.ext_len_edge;
+        cnt[r] = 0;
+        if (r > r0 && !hard_boundary(d, w.run_s, w.run_e, r - 1, gs, ge, gap, with_ext, ext)) return;   // not a group head
+        int32_t rend = r + 1;
+        while (rend < r1 && !hard_boundary(d, w.run_s, w.run_e, rend - 1, gs, ge, gap, with_ext, ext)) rend++;
+        cnt[r] = regions_from_runs(d, w.run_s, w.run_e, r, rend, gs, ge, gap, con, with_ext, ext, out);
+    }
+};
+struct ContigRegions {   // one thread per contig: concatenate its groups' regions, contig_merge_region
     Dev2 w;
     template <class B> NP_HD void operator()(int64_t k, B&) const {
         const Dev& d = w.d;
         int32_t gs = d.ctg_goff[k], ge = d.ctg_goff[k + 1] - 1;
-        int32_t r0 = w.rs_idx[gs], r1 = w.rs_idx[ge + 1];
-        int32_t* nd = w.nd_reg + 2 * (size_t)r0 + 2 * (size_t)k;   // slack of one pair per contig
-        int32_t* km = w.km_reg + 2 * (size_t)r0 + 2 * (size_t)k;
         int32_t a = 0, b = 0;
         if (ge >= gs) {
-            a = regions_from_runs(d, w.run_s, w.run_e, r0, r1, gs, ge, 0, d.P.min_len_ldr, false, d.P.ext_len_edge, nd);
-            b = regions_from_runs(d, w.run_s, w.run_e, r0, r1, gs, ge, d.P.min_len_inter_kmer, 0, true, d.P.ext_len_edge, km);
+            int32_t r0 = w.rs_idx[gs], r1 = w.rs_idx[ge + 1];
+            int32_t* nd = w.nd_reg + 2 * (size_t)r0 + 2 * (size_t)k;   // slack of one pair per contig
+            int32_t* km = w.km_reg + 2 * (size_t)r0 + 2 * (size_t)k;
+            for (int32_t r = r0; r < r1; r++) {
+                for (int32_t q = 0; q < w.gcnt_nd[r]; q++, a++) { nd[2 * a] = w.gnd[2 * (size_t)r + 2 * q]; nd[2 * a + 1] = w.gnd[2 * (size_t)r + 2 * q + 1]; }
+                for (int32_t q = 0; q < w.gcnt_km[r]; q++, b++) { km[2 * b] = w.gkm[2 * (size_t)r + 2 * q]; km[2 * b + 1] = w.gkm[2 * (size_t)r + 2 * q + 1]; }
+            }
             a = merge_regions(nd, a);
             b = merge_regions(km, b);
         }
@@ -699,11 +738,15 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
     w.km_cnt = be.template buf<int32_t>("km_cnt", (size_t)d.n_ctg + 1);
     w.nd_off = be.template buf<int32_t>("nd_off", (size_t)d.n_ctg + 1);
     w.km_off = be.template buf<int32_t>("km_off", (size_t)d.n_ctg + 1);
+    w.gnd = be.template buf<int32_t>("gnd", regcap);
+    w.gkm = be.template buf<int32_t>("gkm", regcap);
+    w.gcnt_nd = be.template buf<int32_t>("gcnt_nd", (size_t)w.n_runs + 1);
+    w.gcnt_km = be.template buf<int32_t>("gcnt_km", (size_t)w.n_runs + 1);
+    if (w.n_runs > 0) be.launch("region_groups", 2 * (int64_t)w.n_runs, RegionGroups{w});
     be.launch("contig_regions", d.n_ctg, ContigRegions{w});
     be.exscan_i32(w.nd_cnt, w.nd_off, (int64_t)d.n_ctg + 1);
     be.exscan_i32(w.km_cnt, w.km_off, (int64_t)d.n_ctg + 1);
-    w.NR_nd = be.read_i32(w.nd_off + d.n_ctg);
-    w.NR_km = be.read_i32(w.km_off + d.n_ctg);
+    { const int32_t* ptrs[2] = {w.nd_off + d.n_ctg, w.km_off + d.n_ctg}; int32_t v[2]; be.read_many(ptrs, 2, v); w.NR_nd = v[0]; w.NR_km = v[1]; }
     w.ndl = be.template buf<int32_t>("ndl", 2 * (size_t)w.NR_nd + 2);
     w.kml = be.template buf<int32_t>("kml", 2 * (size_t)w.NR_km + 2);
     be.launch("compact_regions", d.n_ctg, CompactRegions{w});
@@ -744,8 +787,8 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
         be.launch("nodepth_pairs", (int64_t)w.NR_nd + 1, NdPairCount{w});
         be.exscan_i32(w.nd_pcnt, w.nd_poff, (int64_t)w.NR_nd + 1);
         be.exscan_i32(w.nd_sb, w.nd_soff, (int64_t)w.NR_nd + 1);
-        w.NP_nd = be.read_i32(w.nd_poff + w.NR_nd);
-        int32_t SB = be.read_i32(w.nd_soff + w.NR_nd);
+        int32_t SB = 0;
+        { const int32_t* ptrs[2] = {w.nd_poff + w.NR_nd, w.nd_soff + w.NR_nd}; int32_t v[2]; be.read_many(ptrs, 2, v); w.NP_nd = v[0]; SB = v[1]; }
         w.ndp_read = be.template buf<int32_t>("ndp_read", (size_t)w.NP_nd + 1);
         w.ndp_first = be.template buf<int32_t>("ndp_first", (size_t)w.NP_nd + 1);
         w.ndp_n = be.template buf<int32_t>("ndp_n", (size_t)w.NP_nd + 1);
@@ -754,8 +797,8 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
         if (w.NP_nd > 0) be.launch("nodepth_walk", w.NP_nd, NdWalk{w});
         be.exscan_i32(w.ndmark, w.ndidx, (int64_t)C + 1);
         be.exscan_i32(w.vcap, w.koff, (int64_t)C + 1);
-        w.NRC = be.read_i32(w.ndidx + C);
-        int32_t KE = be.read_i32(w.koff + C);
+        int32_t KE = 0, e1 = 0;
+        { const int32_t* ptrs[3] = {w.ndidx + C, w.koff + C, d.err}; int32_t v[3]; be.read_many(ptrs, 3, v); w.NRC = v[0]; KE = v[1]; e1 = v[2]; }
         size_t nrc = (size_t)w.NRC + 1;
         w.ktab2 = be.template buf<uint32_t>("ktab2", (size_t)KE + 1);
         w.nk2 = be.template buf<int32_t>("nk2", nrc);
@@ -766,7 +809,6 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
         w.ord2 = be.template buf<uint8_t>("ord2", nrc * 16);
         w.ns2 = be.template buf<uint8_t>("ns2", nrc);
         w.subbuf = be.template buf<int32_t>("subbuf", nrc + 2 * (size_t)w.NR_nd + 4);
-        int32_t e1 = be.read_i32(d.err);
         if (e1) return e1;
         be.launch("nodepth_score", w.NR_nd, NodepthScore{w});
     }
@@ -788,8 +830,8 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
         be.launch("window_count", (int64_t)w.NW + 1, WindowCount{w});
         be.exscan_i32(w.wcand, w.wsoff, (int64_t)w.NW + 1);
         be.exscan_i32(w.wp_cnt, w.wp_off, (int64_t)w.NW + 1);
-        int32_t WS = be.read_i32(w.wsoff + w.NW);
-        w.NP_w = be.read_i32(w.wp_off + w.NW);
+        int32_t WS = 0;
+        { const int32_t* ptrs[2] = {w.wsoff + w.NW, w.wp_off + w.NW}; int32_t v[2]; be.read_many(ptrs, 2, v); WS = v[0]; w.NP_w = v[1]; }
         w.wscratch = be.template buf<int32_t>("wscratch", (size_t)WS + 4);
         w.wp_read = be.template buf<int32_t>("wp_read", (size_t)w.NP_w + 1);
         be.launch("window_fill", w.NW, WinPairFill{w});
@@ -799,11 +841,11 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
     }
     be.launch("keep_flag", (int64_t)C + 1, KeepFlag{d});
     be.exscan_i32(d.keepi, d.keepidx, (int64_t)C + 1);
-    int32_t total = be.read_i32(d.keepidx + C);
+    int32_t total = 0, err = 0;
+    { const int32_t* ptrs[2] = {d.keepidx + C, d.err}; int32_t v[2]; be.read_many(ptrs, 2, v); total = v[0]; err = v[1]; }
     d.out = be.template buf<uint8_t>("out", (size_t)total + 1);
     if (C > 0) be.launch("emit", C, Emit{d, (uint8_t)FLAG_ZERO});
     be.launch("out_offsets", (int64_t)d.n_ctg + 1, OutOffsets{d});
-    int32_t err = be.read_i32(d.err);
     if (st) { st->C = C; st->T = w.NW; st->sym_words = w.NR_nd; st->table_entries = w.NR_km; st->out_bytes = total; }
     d0 = d;
     return err;

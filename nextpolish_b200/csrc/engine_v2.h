@@ -79,10 +79,12 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
         g.win_need = be.template buf<int32_t>("w_need", (size_t)g.n_win + 1);
         be.zero(g.maxneed, 2 * sizeof(int32_t));
         if (g.n_win > 0) be.launch("win_plan", g.n_win, npw::WinPlan{d, g});
-        need = be.read_i32(g.maxneed);
+        const int32_t* ptrs[2] = {g.maxneed, d.colbase + G};
+        int32_t vals[2];
+        be.read_many(ptrs, 2, vals);
+        need = vals[0]; d.C = vals[1];
         fits = need <= (wi == 2 ? hard : budget);
     }
-    d.C = be.read_i32(d.colbase + G);
     const int32_t C = d.C;
     if (!fits) return run_score_chain(be, d, st);          // e.g. extreme depth: general kernels only
 
@@ -99,7 +101,13 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
     if (g.n_win > 0) be.run_windows(d, g, need);
 
     be.exscan_i32(d.needi, d.tidx, (int64_t)C + 1);
-    d.T = be.read_i32(d.tidx + C);
+    int32_t n_unres = 0;
+    {
+        const int32_t* ptrs[2] = {d.tidx + C, g.n_unresolved};
+        int32_t vals[2];
+        be.read_many(ptrs, 2, vals);
+        d.T = vals[0]; n_unres = vals[1];
+    }
     int32_t E = 0, Wd = 0;
     if (d.T > 0) {                                           // fallback: general kernels on the marked stretches
         const int32_t T = d.T;
@@ -128,13 +136,18 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
     }
     be.launch("keep_flag", (int64_t)C + 1, KeepFlag{d});
     be.exscan_i32(d.keepi, d.keepidx, (int64_t)C + 1);
-    int32_t total = be.read_i32(d.keepidx + C);
+    int32_t total = 0, err = 0;
+    {
+        const int32_t* ptrs[2] = {d.keepidx + C, d.err};
+        int32_t vals[2];
+        be.read_many(ptrs, 2, vals);
+        total = vals[0]; err = vals[1];
+    }
     d.out = be.template buf<uint8_t>("out", (size_t)total + 1);
     if (C > 0) be.launch("emit", C, Emit{d, (uint8_t)(FLAG_ZERO | FLAG_COVERAGE)});
     be.launch("out_offsets", (int64_t)d.n_ctg + 1, OutOffsets{d});
-    int32_t err = be.read_i32(d.err);
     if (st) { st->C = C; st->T = d.T; st->sym_words = Wd; st->table_entries = E; st->out_bytes = total; }
-    if (vs) { vs->W = g.W; vs->n_win = g.n_win; vs->smem = need; vs->unresolved_windows = be.read_i32(g.n_unresolved); vs->fallback_cols = d.T; }
+    if (vs) { vs->W = g.W; vs->n_win = g.n_win; vs->smem = need; vs->unresolved_windows = n_unres; vs->fallback_cols = d.T; }
     return err;
 }
 

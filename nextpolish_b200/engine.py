@@ -169,6 +169,9 @@ class Engine:
         raw = out.tobytes()
         return {nm: raw[off[i]:off[i + 1]] for i, nm in enumerate(shard.names)}
 
+    def set_timing(self, on):
+        lib().np_engine_set_timing(self.h, int(on))
+
     def kernel_times(self):
         cap = 256
         names = (C.c_char_p * cap)()

@@ -47,6 +47,7 @@ struct EmuBackend {
         for (int64_t i = 0; i < n; i++) { m = std::max(m, in[i]); out[i] = m; }
     }
     int32_t read_i32(const int32_t* p) { return *p; }
+    void read_many(const int32_t* const* ptrs, int n, int32_t* out) { for (int i = 0; i < n; i++) out[i] = *ptrs[i]; }
     const int32_t* upload_i32(const char* name, const int32_t* h, size_t n) {
         int32_t* p = buf<int32_t>(name, n + 1);
         if (n) memcpy(p, h, n * sizeof(int32_t));
