@@ -87,7 +87,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
     } while (!done);
 }
 
-constexpr int kWinThreads = 128;
+constexpr int kWinThreads = 192;   // 4 CTAs x 6 warps per SM at ~55 KB of shared memory per CTA
 
 __global__ void __launch_bounds__(256) k_window(npe::Dev d, npw::WinGlobals g) {
     extern __shared__ __align__(128) uint8_t smem[];

@@ -96,7 +96,7 @@ NP_HD uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int32_t strw, int32_t npos) {
     uint32_t b = 64;                                   // mbarrier + counters
     uint32_t recarea = align16(recbytes);              // later re-used as the table pool
-    uint32_t mintab = (uint32_t)(ncols / 8 + 8) * (uint32_t)TAB_BYTES;
+    uint32_t mintab = (uint32_t)(ncols / 4 + 16) * (uint32_t)TAB_BYTES   /* ~13 % of columns need a table at 30x; 2x headroom */;
     if (recarea < mintab) recarea = mintab;
     b += recarea + align16(4u * (uint32_t)(nr + 1));
     b += align16(2u * (uint32_t)(npos + 2)) + align16(8u * (uint32_t)(ncols / 32 + 2));
@@ -155,7 +155,7 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
     x.rlo = x.g.win_rlo[w]; x.nr = x.g.win_rhi[w] - x.rlo;
     x.strw = x.g.win_strw[w];
     uint32_t recbytes = (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u;
-    uint32_t recarea = align16(recbytes), mintab = (uint32_t)(x.ncols / 8 + 8) * (uint32_t)TAB_BYTES;
+    uint32_t recarea = align16(recbytes), mintab = (uint32_t)(x.ncols / 4 + 16) * (uint32_t)TAB_BYTES;
     if (recarea < mintab) recarea = mintab;
     x.tmax = (int32_t)(recarea / TAB_BYTES) & ~7;      // multiple of 8 keeps every array 8-byte aligned
     uint8_t* p = smem + 64;
