@@ -310,6 +310,12 @@ def main():
     value = total_bp * args.steps / (ms_res / 1e3) / 1e6
     e2e = total_bp * args.steps / (ms_e2e / 1e3) / 1e6
     peak, peak_kind = measured_peak_gbs()
+    traffic = None
+    try:   # DRAM bytes of one launch of the window kernel from the committed ncu --set full capture
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_v2_window_kernel.json")))
+        traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
     roof_kernel = "pileup_scan"
     kms = dict(kt_by_task[1]).get(roof_kernel) if 1 in kt_by_task else None
     ach = alg_bytes[1] / (kms / 1e3) / 1e9 if kms else None
@@ -319,7 +325,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": (ach / peak) if ach else None, "traffic": None, "peak_kind": peak_kind,
+                     "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_kind": peak_kind,
                      "algorithmic_bytes": alg_bytes[1], "kernel_ms": kms},
         "kernels_ms": {k: round(v, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1])},
         "pileup_windows": wstats,
