@@ -238,15 +238,16 @@ def main():
     estream = torch.cuda.ExternalStream(eng.stream(), device=dev)
     gather_buf = torch.empty(cap, dtype=torch.uint8, device=dev)
 
-    from nextpolish_b200.sharding import gather_bytes
+    from nextpolish_b200.sharding import FixedGather
+    fixed_gather = FixedGather(cap, dev) if world > 1 else None
 
     def gather_fasta():
-        """The single collective of the path: corrected FASTA bytes of every rank -> rank 0."""
+        """The single collective of the path: corrected FASTA bytes of every rank -> rank 0 (NCCL)."""
         n = eng.result_bytes()
         E.lib().np_engine_copy_result(eng.h, gather_buf.data_ptr(), cap)
         eng.sync()
         if world > 1:
-            gather_bytes(gather_buf[:n], dst=0)
+            fixed_gather(gather_buf, n)
 
     def step_resident(i):
         for t in tasks:

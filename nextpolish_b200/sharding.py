@@ -37,3 +37,28 @@ def gather_bytes(local, dst=0, group=None):
     if rank != dst:
         return None
     return [o[:s] for o, s in zip(out, sizes)]
+
+
+class FixedGather:
+    """The same collective with buffers allocated once and no host synchronisation in the hot loop:
+    every rank contributes a capacity-sized buffer plus its byte count; rank `dst` slices afterwards."""
+
+    def __init__(self, cap, device, dst=0, group=None):
+        self.cap, self.dst, self.group = cap, dst, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n = torch.zeros(1, dtype=torch.int64, device=device)
+        root = self.rank == dst
+        self.sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(self.world)] if root else None
+        self.bufs = [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(self.world)] if root else None
+
+    def __call__(self, buf, n):
+        """buf: uint8 tensor of exactly `cap` elements holding n valid bytes."""
+        self.n.fill_(n)
+        dist.gather(self.n, self.sizes, dst=self.dst, group=self.group)
+        dist.gather(buf, self.bufs, dst=self.dst, group=self.group)
+
+    def result(self):
+        """On dst: list of per-rank byte tensors of the last call (synchronises)."""
+        if self.rank != self.dst:
+            return None
+        return [b[:int(s.item())] for b, s in zip(self.bufs, self.sizes)]

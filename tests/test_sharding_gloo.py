@@ -48,7 +48,14 @@ def _worker(rank, world, port, q):
         pieces.append(seq)
     local = torch.from_numpy(np.concatenate(pieces) if pieces else np.zeros(0, np.uint8))
     got = gather_bytes(local, dst=0)
+    from nextpolish_b200.sharding import FixedGather
+    fg = FixedGather(200000, torch.device("cpu"))
+    buf = torch.zeros(200000, dtype=torch.uint8)
+    buf[:local.numel()] = local
+    fg(buf, local.numel())
+    got2 = fg.result()
     if rank == 0:
+        assert all(bytes(a.numpy()) == bytes(b.numpy()) for a, b in zip(got, got2))
         whole, off = _polish_with_oracle(E, full, cfg)
         parts = partition_contigs(lengths, world)
         ok = True
