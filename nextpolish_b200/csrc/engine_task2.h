@@ -600,6 +600,7 @@ struct WinWalk {         // per (window, read) pair: the read's column string ov
         meta[0] = -1;
         if (r < 0) return;
         if (j < ncand && d.r_level[r] != 2) return;            // only level-2 candidates are parsed (kmercount.c:197)
+        for (int32_t t = 0; t < (len + 3) / 4; t++) slot[t] = 0;   // strings are compared word-wise
         int32_t k = find_contig_i32(d.ctg_goff, d.n_ctg, s);
         Rec rc = load_rec(d.rec, d.rec_off, r);
         const uint8_t* qp = d.qual + (size_t)d.qual_off[r] * 16;
@@ -630,18 +631,30 @@ struct WindowVote {      // ss_kmer_correct for one window (kmercount.c:188-253)
         int32_t* tal = base + (size_t)(ncand + 1) * sw;             // [slot, num, mapq, qual] entries
         int32_t nstr = 0, count = 0;
         bool broke = false;
+        // every parsed read clears FLAG_ZERO on the columns it covers (kmercount.c:398,411,431,437); the
+        // ranges of successive reads nearly coincide, so only the part outside the interval cleared so
+        // far is touched (a disjoint range is cleared on its own)
+        int32_t clr_lo = 0, clr_hi = 0;
+        auto clear_range = [&](int32_t a, int32_t b) { for (int32_t c = a; c < b; c++) d.oflag[c] &= (uint8_t)~FLAG_ZERO; };
         // ss_kmer_get_region (kmercount.c:332-363) on pair slot j; returns ks->mapqual after the call
         auto get_region = [&](int32_t j) -> int32_t {
             const int32_t* slot = base + (size_t)j * sw;
             const int32_t* meta = slot + lw;
             int32_t length = meta[0];
-            for (int32_t c = meta[2]; c < meta[2] + length; c++) d.oflag[c] &= (uint8_t)~FLAG_ZERO;   // flagzero == 0
+            if (length > 0) {
+                int32_t a = meta[2], b = meta[2] + length;
+                if (clr_hi == clr_lo) { clear_range(a, b); clr_lo = a; clr_hi = b; }
+                else if (b < clr_lo || a > clr_hi) clear_range(a, b);
+                else {
+                    if (a < clr_lo) { clear_range(a, clr_lo); clr_lo = a; }
+                    if (b > clr_hi) { clear_range(clr_hi, b); clr_hi = b; }
+                }
+            }
             if (length != len) return 0;
             int32_t q = 0;
             for (; q < nstr; q++) {
                 const int32_t* a = base + (size_t)tal[4 * q] * sw; bool same = true;
-                const uint8_t *sa = (const uint8_t*)a, *sb = (const uint8_t*)slot;
-                for (int32_t t = 0; t < len; t++) if (sa[t] != sb[t]) { same = false; break; }
+                for (int32_t t = 0; t < lw; t++) if (a[t] != slot[t]) { same = false; break; }   // slots are zero padded
                 if (same) break;
             }
             if (q == nstr) { tal[4 * q] = j; tal[4 * q + 1] = 1; tal[4 * q + 2] = meta[3]; tal[4 * q + 3] = meta[1]; nstr++; }

@@ -92,3 +92,25 @@ def test_emulated_task2_with_sparse_quality_stream(E, oracle, emu, case):
     cfg.contents.read_tlen = 1750
     want = run_checker(oracle.np_oracle_run, dense, 2, cfg)
     assert run_checker(emu.np_emu_run, sparse, 2, cfg, (None,)) == want
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_emulated_kernels_fuzz_both_tasks(E, oracle, emu, seed):
+    """Random data shapes x random thresholds, both tasks (this fuzzer found the window-vote flag-clearing
+    subtlety: candidates span a window by alignment, but their trimmed usable intervals need not overlap)."""
+    import random
+    rng = random.Random(4100 + seed)
+    kw = dict(seed=rng.randrange(1 << 30), n_contigs=rng.choice([1, 2, 5]), contig_len=rng.choice([3000, 8000, 20000]),
+              depth=rng.choice([2, 5, 12, 30, 60]), draft_snv=rng.choice([0.001, 0.01]), draft_indel=rng.choice([0.003, 0.02]),
+              read_sub=rng.choice([0.002, 0.02]), read_indel=rng.choice([0.0001, 0.003]), lowercase_frac=rng.choice([0, 0.01, 0.05, 0.15]))
+    sh = E.Shard.synthetic(E.synth_params(**kw), 0, kw["n_contigs"], with_qual=True)
+    cfg = E.default_config(b"")
+    c = cfg.contents
+    c.read_tlen = rng.choice([0, 2000])
+    c.trim_len_edge, c.ext_len_edge = rng.choice([0, 1, 2, 4]), rng.choice([0, 1, 2, 3])
+    c.min_len_ldr, c.min_len_inter_kmer = rng.choice([1, 3, 6]), rng.choice([0, 2, 5, 9])
+    c.max_len_kmer, c.max_count_kmer, c.min_map_quality = rng.choice([10, 50, 120]), rng.choice([3, 50]), rng.choice([0, 30])
+    c.indel_balance_factor_sgs, c.min_count_ratio_skip = rng.choice([0.5, 0.25, 0.75]), rng.choice([0.8, 0.6, 0.95])
+    for task in (1, 2):
+        want = run_checker(oracle.np_oracle_run, sh, task, cfg)
+        assert run_checker(emu.np_emu_run, sh, task, cfg, (None,)) == want, (task, kw)
