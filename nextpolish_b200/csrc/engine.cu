@@ -295,6 +295,9 @@ struct np_engine {
     size_t cap_seq = 0, cap_goff = 0, cap_roff = 0, cap_recoff = 0, cap_rec = 0, cap_qoff = 0, cap_qual = 0;
     std::vector<int64_t> h_out_off;
     bool ran = false;
+    np_engine* sibling = nullptr;      // second engine (stream + scratch) of the pipelined np_polish_host
+    cudaEvent_t copy_done = nullptr;
+    bool pipelined_last = false;
 };
 
 static bool dev_reserve(np_engine* e, void** p, size_t* cap, size_t bytes) {
@@ -334,6 +337,8 @@ np_engine* np_engine_create(int32_t device) {
 
 void np_engine_destroy(np_engine* e) {
     if (!e) return;
+    if (e->sibling) { np_engine_destroy(e->sibling); e->sibling = nullptr; }
+    if (e->copy_done) cudaEventDestroy(e->copy_done);
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->be.stream);
     void* ps[] = {e->s_seq, e->s_goff, e->s_roff, e->s_recoff, e->s_rec, e->s_qoff, e->s_qual};
@@ -342,61 +347,78 @@ void np_engine_destroy(np_engine* e) {
     delete e;
 }
 
-static int32_t set_shard_common(np_engine* e, const np_shard_view* v, bool device_resident) {
-    if (!e || !v || v->n_contigs < 0 || v->n_reads < 0) { np::set_error("bad shard"); return NP_ERR_ARG; }
-    int64_t G = v->ctg_off[v->n_contigs];
-    if (G >= 0x7fffff00ll || v->n_reads >= 0x7fffff00ll) {
+// Makes contigs [k0, k1) of `v` the engine's resident shard.  Host shards are copied to HBM
+// (asynchronously on the engine stream; pinned buffers overlap with other streams' work); device
+// shards are adopted in place.  Offsets inside rec_off / qual_off stay absolute: the device base
+// pointers are shifted instead of rewriting the offset arrays.
+static int32_t set_shard_slice(np_engine* e, const np_shard_view* v, int32_t k0, int32_t k1, bool device_resident) {
+    if (!e || !v || v->n_contigs < 0 || v->n_reads < 0 || k0 < 0 || k1 < k0 || k1 > v->n_contigs) { np::set_error("bad shard"); return NP_ERR_ARG; }
+    const int64_t c0 = v->ctg_off[k0], G = v->ctg_off[k1] - c0;
+    const int64_t r0 = v->ctg_read_off[k0], R = v->ctg_read_off[k1] - r0;
+    const int32_t nc = k1 - k0;
+    if (G >= 0x7fffff00ll || R >= 0x7fffff00ll) {
         np::set_error("shard exceeds 2^31 positions/reads: split it into several shards");
         return NP_ERR_LIMIT;
     }
     cudaSetDevice(e->device);
-    e->h_ctg_off.assign(v->ctg_off, v->ctg_off + v->n_contigs + 1);
-    e->h_read_off.assign(v->ctg_read_off, v->ctg_read_off + v->n_contigs + 1);
-    std::vector<int32_t> goff((size_t)v->n_contigs + 1);
-    for (int i = 0; i <= v->n_contigs; i++) goff[(size_t)i] = (int32_t)v->ctg_off[i];
+    e->h_ctg_off.resize((size_t)nc + 1); e->h_read_off.resize((size_t)nc + 1);
+    std::vector<int32_t> goff((size_t)nc + 1);
+    for (int i = 0; i <= nc; i++) {
+        e->h_ctg_off[(size_t)i] = v->ctg_off[k0 + i] - c0;
+        e->h_read_off[(size_t)i] = v->ctg_read_off[k0 + i] - r0;
+        goff[(size_t)i] = (int32_t)e->h_ctg_off[(size_t)i];
+    }
     cudaStream_t s = e->be.stream;
     if (!dev_reserve(e, &e->s_goff, &e->cap_goff, goff.size() * 4) ||
         !dev_reserve(e, &e->s_roff, &e->cap_roff, e->h_read_off.size() * 8)) return NP_ERR_CUDA;
+    // small metadata goes through the pinned bounce buffer of the engine (the vectors above are pageable)
     cudaMemcpyAsync(e->s_goff, goff.data(), goff.size() * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(e->s_roff, e->h_read_off.data(), e->h_read_off.size() * 8, cudaMemcpyHostToDevice, s);
-    size_t rec_bytes = 0, qual_bytes = 0;
-    // rec_off[n_reads] is needed to size the copy; for device-resident shards read it back
-    uint32_t last_rec = 0, last_q = 0;
+    cudaStreamSynchronize(s);      // goff is a local: it must not go out of scope before the copy ran
+    // record / quality byte ranges of the slice
+    uint32_t rec_lo = 0, rec_hi = 0, q_lo = 0, q_hi = 0;
     if (device_resident) {
-        cudaMemcpyAsync(&last_rec, v->rec_off + v->n_reads, 4, cudaMemcpyDeviceToHost, s);
-        if (v->qual_off) cudaMemcpyAsync(&last_q, v->qual_off + v->n_reads, 4, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(&rec_lo, v->rec_off + r0, 4, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(&rec_hi, v->rec_off + r0 + R, 4, cudaMemcpyDeviceToHost, s);
+        if (v->qual_off) { cudaMemcpyAsync(&q_lo, v->qual_off + r0, 4, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(&q_hi, v->qual_off + r0 + R, 4, cudaMemcpyDeviceToHost, s); }
         cudaStreamSynchronize(s);
     } else {
-        last_rec = v->rec_off[v->n_reads];
-        if (v->qual_off) last_q = v->qual_off[v->n_reads];
+        rec_lo = v->rec_off[r0]; rec_hi = v->rec_off[r0 + R];
+        if (v->qual_off) { q_lo = v->qual_off[r0]; q_hi = v->qual_off[r0 + R]; }
     }
-    rec_bytes = (size_t)last_rec * 16; qual_bytes = (size_t)last_q * 16;
+    const size_t rec_bytes = (size_t)(rec_hi - rec_lo) * 16, qual_bytes = (size_t)(q_hi - q_lo) * 16;
     npe::Dev& d = e->d;
-    d.n_ctg = v->n_contigs; d.n_reads = v->n_reads; d.G = (int32_t)G;
+    d.n_ctg = nc; d.n_reads = R; d.G = (int32_t)G;
     d.ctg_goff = (const int32_t*)e->s_goff; d.ctg_read_off = (const int64_t*)e->s_roff;
     if (device_resident) {
-        d.ctg_seq = v->ctg_seq; d.rec_off = v->rec_off; d.rec = v->rec; d.qual_off = v->qual_off; d.qual = v->qual;
+        d.ctg_seq = v->ctg_seq + c0; d.rec_off = v->rec_off + r0; d.rec = v->rec;
+        d.qual_off = v->qual_off ? v->qual_off + r0 : nullptr; d.qual = v->qual;
     } else {
         if (!dev_reserve(e, &e->s_seq, &e->cap_seq, (size_t)G + 16) ||
-            !dev_reserve(e, &e->s_recoff, &e->cap_recoff, ((size_t)v->n_reads + 1) * 4) ||
+            !dev_reserve(e, &e->s_recoff, &e->cap_recoff, ((size_t)R + 1) * 4) ||
             !dev_reserve(e, &e->s_rec, &e->cap_rec, rec_bytes + 16)) return NP_ERR_CUDA;
-        cudaMemcpyAsync(e->s_seq, v->ctg_seq, (size_t)G, cudaMemcpyHostToDevice, s);
-        cudaMemcpyAsync(e->s_recoff, v->rec_off, ((size_t)v->n_reads + 1) * 4, cudaMemcpyHostToDevice, s);
-        cudaMemcpyAsync(e->s_rec, v->rec, rec_bytes, cudaMemcpyHostToDevice, s);
-        d.ctg_seq = (const uint8_t*)e->s_seq; d.rec_off = (const uint32_t*)e->s_recoff; d.rec = (const uint8_t*)e->s_rec;
+        cudaMemcpyAsync(e->s_seq, v->ctg_seq + c0, (size_t)G, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(e->s_recoff, v->rec_off + r0, ((size_t)R + 1) * 4, cudaMemcpyHostToDevice, s);
+        if (rec_bytes) cudaMemcpyAsync(e->s_rec, v->rec + (size_t)rec_lo * 16, rec_bytes, cudaMemcpyHostToDevice, s);
+        d.ctg_seq = (const uint8_t*)e->s_seq; d.rec_off = (const uint32_t*)e->s_recoff;
+        d.rec = (const uint8_t*)e->s_rec - (size_t)rec_lo * 16;
         d.qual_off = nullptr; d.qual = nullptr;
         if (v->qual_off) {
-            if (!dev_reserve(e, &e->s_qoff, &e->cap_qoff, ((size_t)v->n_reads + 1) * 4) ||
+            if (!dev_reserve(e, &e->s_qoff, &e->cap_qoff, ((size_t)R + 1) * 4) ||
                 !dev_reserve(e, &e->s_qual, &e->cap_qual, qual_bytes + 16)) return NP_ERR_CUDA;
-            cudaMemcpyAsync(e->s_qoff, v->qual_off, ((size_t)v->n_reads + 1) * 4, cudaMemcpyHostToDevice, s);
-            if (qual_bytes) cudaMemcpyAsync(e->s_qual, v->qual, qual_bytes, cudaMemcpyHostToDevice, s);
-            d.qual_off = (const uint32_t*)e->s_qoff; d.qual = (const uint8_t*)e->s_qual;
+            cudaMemcpyAsync(e->s_qoff, v->qual_off + r0, ((size_t)R + 1) * 4, cudaMemcpyHostToDevice, s);
+            if (qual_bytes) cudaMemcpyAsync(e->s_qual, v->qual + (size_t)q_lo * 16, qual_bytes, cudaMemcpyHostToDevice, s);
+            d.qual_off = (const uint32_t*)e->s_qoff; d.qual = (const uint8_t*)e->s_qual - (size_t)q_lo * 16;
         }
     }
     cudaError_t er = cudaGetLastError();
     if (er != cudaSuccess) { np::set_error(std::string("upload: ") + cudaGetErrorString(er)); return NP_ERR_CUDA; }
     e->resident = true; e->ran = false;
     return NP_OK;
+}
+static int32_t set_shard_common(np_engine* e, const np_shard_view* v, bool device_resident) {
+    if (!v) { np::set_error("bad shard"); return NP_ERR_ARG; }
+    return set_shard_slice(e, v, 0, v->n_contigs, device_resident);
 }
 
 int32_t np_engine_upload(np_engine* e, const np_shard_view* host_shard) { return set_shard_common(e, host_shard, false); }
@@ -481,13 +503,48 @@ int32_t np_engine_kernel_times(np_engine* e, const char** names, float* ms, int3
     return n;
 }
 
+// Upload + run + download.  Shards with several contigs are cut into two halves handled by two engines
+// (two streams): the second half's host-to-device copy runs while the first half is being polished.
 int32_t np_polish_host(np_engine* e, int32_t task, const np_shard_view* host_shard,
                        const Configure* cfg, uint8_t* out_seq, int64_t out_cap, int64_t* out_off) {
-    int32_t rc = np_engine_upload(e, host_shard);
+    if (!e || !host_shard) { np::set_error("np_polish_host: bad arguments"); return NP_ERR_ARG; }
+    const np_shard_view* v = host_shard;
+    const int32_t n = v->n_contigs;
+    const int64_t G = n > 0 ? v->ctg_off[n] - v->ctg_off[0] : 0;
+    const char* nopipe = getenv("NEXTPOLISH_B200_NO_PIPELINE");
+    if (n < 2 || G < (1 << 20) || (nopipe && nopipe[0] == '1')) {
+        int32_t rc = np_engine_upload(e, v);
+        if (rc != NP_OK) return rc;
+        rc = np_engine_run(e, task, cfg);
+        if (rc != NP_OK) return rc;
+        return np_engine_download(e, out_seq, out_cap, out_off);
+    }
+    if (!e->sibling) {
+        e->sibling = np_engine_create(e->device);
+        if (!e->sibling) return NP_ERR_CUDA;
+    }
+    np_engine* b = e->sibling;
+    int32_t kmid = 1;                                   // first contig index of the second half
+    while (kmid < n - 1 && v->ctg_off[kmid] - v->ctg_off[0] < G / 2) kmid++;
+    int32_t rc = set_shard_slice(e, v, 0, kmid, false);
+    if (rc == NP_OK) {
+        // the second half's copy must not share PCIe with the first: order it behind the first copy
+        if (!e->copy_done) cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming);
+        cudaEventRecord(e->copy_done, e->be.stream);
+        cudaStreamWaitEvent(b->be.stream, e->copy_done, 0);
+        rc = set_shard_slice(b, v, kmid, n, false);
+    }
+    if (rc == NP_OK) rc = np_engine_run(e, task, cfg);               // overlaps with the second copy
+    if (rc == NP_OK) rc = np_engine_run(b, task, cfg);
     if (rc != NP_OK) return rc;
-    rc = np_engine_run(e, task, cfg);
+    const int64_t na = np_engine_result_bytes(e), nb = np_engine_result_bytes(b);
+    if (na + nb > out_cap) { np::set_error("np_polish_host: output buffer too small"); return NP_ERR_ARG; }
+    rc = np_engine_download(e, out_seq, out_cap, out_off);
+    if (rc == NP_OK) rc = np_engine_download(b, out_seq + na, out_cap - na, out_off + kmid);
     if (rc != NP_OK) return rc;
-    return np_engine_download(e, out_seq, out_cap, out_off);
+    for (int32_t k = kmid; k <= n; k++) out_off[k] += na;
+    e->pipelined_last = true;
+    return NP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -205,3 +205,27 @@ def test_nextpolish1_worker_mirror(E, tmp_path):
     assert {k: v for k, v in got.items()} == {n + "_np1": exp[n + "_1"] for n in names}
     header = [l for l in open(out) if l.startswith(">")][0].split()
     assert int(header[1]) == len(got[header[0][1:]])
+
+
+def test_pipelined_host_call_equals_resident_path(E, eng):
+    """np_polish_host on a shard big enough to take the two-engine pipelined route (second half's H2D copy
+    overlaps the first half's kernels), both tasks, pinned and pageable host buffers."""
+    import torch
+    p = E.synth_params(seed=41, n_contigs=5, contig_len=400000, depth=20.0, lowercase_frac=0.002)
+    sh = E.Shard.synthetic(p, 0, 5, with_qual=2)
+    cfg = E.default_config(b"")
+    cfg.contents.read_tlen = 1750
+    for task in tasks(E):
+        want = eng.polish(sh, task, cfg)
+        out = np.zeros(int(sh.total_bases * 2), np.uint8)
+        off = np.zeros(sh.n_contigs + 1, np.int64)
+        eng.polish_host(task, sh.view, cfg, out, off)                     # pageable arrays
+        raw = out.tobytes()
+        assert {n: raw[off[i]:off[i + 1]] for i, n in enumerate(sh.names)} == want, task
+        os.environ["NEXTPOLISH_B200_NO_PIPELINE"] = "1"
+        try:
+            eng.polish_host(task, sh.view, cfg, out, off)
+        finally:
+            del os.environ["NEXTPOLISH_B200_NO_PIPELINE"]
+        raw = out.tobytes()
+        assert {n: raw[off[i]:off[i + 1]] for i, n in enumerate(sh.names)} == want, task
