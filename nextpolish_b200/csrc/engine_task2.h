@@ -447,14 +447,38 @@ NP_HD int32_t inner_regions(const Dev& d, int32_t c0, int32_t c1, int32_t bs, in
     return n;
 }
 
-// votes of one pair restricted to region columns [lo, hi] (relative to the region's first column):
-// rolling 3-mer starts at 0 at the first vote inside the range (contig.c:255,360-363)
-NP_HD void nd_apply_pair(const Dev2& w, const NdCtx& x, int32_t c0, int32_t ncols, int32_t i, int32_t j, int32_t p, int32_t lo, int32_t hi) {
-    int32_t first = w.ndp_first[p], n = w.ndp_n[p];
-    const uint8_t* slot = w.ndp_sym + (size_t)w.nd_soff[i] + (size_t)j * ncols;
-    int32_t a = first > lo ? first : lo, b = first + n - 1 < hi ? first + n - 1 : hi;
-    uint32_t kmer = 0;
-    for (int32_t t = a; t <= b; t++) { kmer = ((kmer & 0xffu) << 4) | slot[t]; x.add(c0 + t, kmer); }
+// Votes of the pairs of region i with filter level `level` on region columns [lo, hi] (relative to the
+// region's first column c0), applied COLUMN by column: a column's list length, vote count and its first
+// entries stay in registers while the pairs are visited in BAM order (same first-seen order as the
+// reference's read-by-read walk, base.c:60-71).  The rolling 3-mer context starts at the pair's first vote
+// inside the range (contig.c:255,360-363).
+NP_HD void nd_apply_pairs(const Dev2& w, int32_t c0, int32_t ncols, int32_t i, int32_t level, int32_t lo, int32_t hi,
+                          int32_t ss, int32_t se) {
+    const Dev& d = w.d;
+    const int32_t p0 = w.nd_poff[i], p1 = w.nd_poff[i + 1];
+    for (int32_t t = lo; t <= hi; t++) {
+        const int32_t c = c0 + t, ci = w.ndidx[c];
+        uint32_t* tab = w.ktab2 + w.koff[c];
+        const int32_t cap = w.koff[c + 1] - w.koff[c];
+        int32_t nk = w.nk2[ci]; uint32_t cnt = w.cnt2[ci];
+        for (int32_t p = p0; p < p1; p++) {
+            const int64_t r = w.ndp_read[p];
+            if (d.r_level[r] != level) continue;
+            if (ss >= 0 && (d.r_hend[r] <= ss || d.r_gpos[r] >= se + 1)) continue;    // contig_parse_region's overlap test
+            const int32_t first = w.ndp_first[p], n = w.ndp_n[p];
+            if (t < first || t >= first + n) continue;
+            const uint8_t* slot = w.ndp_sym + (size_t)w.nd_soff[i] + (size_t)(p - p0) * ncols;
+            const int32_t a = first > lo ? first : lo;                                 // first vote inside the range
+            uint32_t kmer = slot[t];
+            if (t - 1 >= a) kmer |= (uint32_t)slot[t - 1] << 4;
+            if (t - 2 >= a) kmer |= (uint32_t)slot[t - 2] << 8;
+            int32_t j = 0;
+            for (; j < nk; j++) if ((tab[j] & 0xffffu) == kmer) { tab[j] += 1u << 16; break; }
+            if (j == nk) { if (nk >= cap) { *d.err |= ERR_REGION_SCRATCH; continue; } tab[nk++] = kmer | (1u << 16); }
+            cnt++;
+        }
+        w.nk2[ci] = nk; w.cnt2[ci] = cnt;
+    }
 }
 
 struct NodepthScore {    // contig_score_correct(region, 0x12), one thread per chain of no-depth regions
@@ -474,21 +498,14 @@ struct NodepthScore {    // contig_score_correct(region, 0x12), one thread per c
                 w.refk2[ci] = (uint16_t)kmer;
                 x.add(c, kmer);
             }
-            int32_t p0 = w.nd_poff[i], p1 = w.nd_poff[i + 1];
-            for (int32_t p = p0; p < p1; p++)                                // contig_parse_region, level == 2
-                if (d.r_level[w.ndp_read[p]] == 2) nd_apply_pair(w, x, c0, ncols, (int32_t)i, p - p0, p, 0, ncols - 1);
+            nd_apply_pairs(w, c0, ncols, (int32_t)i, 2, 0, ncols - 1, -1, -1);   // contig_parse_region, level == 2
             nd_score_correct(w, c0, c1, d.P.rate);
             int32_t* sub = w.subbuf + (size_t)w.ndidx[c0] + 2 * (size_t)i;
             int32_t ns = inner_regions(d, c0, c1, s, e, d.P.ext_len_edge, sub);
             ns = merge_regions(sub, ns);
             for (int32_t q = 0; q < ns; q++) {
                 int32_t ss = sub[2 * q], se = sub[2 * q + 1];
-                int32_t lo = d.colbase[ss] - c0, hi = d.colbase[se] - c0;
-                for (int32_t p = p0; p < p1; p++) {                          // level == 1 reads on top
-                    int64_t r = w.ndp_read[p];
-                    if (d.r_level[r] != 1 || d.r_hend[r] <= ss || d.r_gpos[r] >= se + 1) continue;
-                    nd_apply_pair(w, x, c0, ncols, (int32_t)i, p - p0, p, lo, hi);
-                }
+                nd_apply_pairs(w, c0, ncols, (int32_t)i, 1, d.colbase[ss] - c0, d.colbase[se] - c0, ss, se);   // level == 1 reads on top
                 nd_score_correct(w, d.colbase[ss], d.colbase[se], d.P.rate);
             }
             if (!chain_next(w, i)) break;

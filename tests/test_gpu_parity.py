@@ -219,13 +219,13 @@ def test_pipelined_host_call_equals_resident_path(E, eng):
         want = eng.polish(sh, task, cfg)
         out = np.zeros(int(sh.total_bases * 2), np.uint8)
         off = np.zeros(sh.n_contigs + 1, np.int64)
-        eng.polish_host(task, sh.view, cfg, out, off)                     # pageable arrays
+        eng.polish_host(task, sh.view, cfg, out, off)                     # pageable arrays, single engine
         raw = out.tobytes()
         assert {n: raw[off[i]:off[i + 1]] for i, n in enumerate(sh.names)} == want, task
-        os.environ["NEXTPOLISH_B200_NO_PIPELINE"] = "1"
+        os.environ["NEXTPOLISH_B200_PIPELINE"] = "1"
         try:
-            eng.polish_host(task, sh.view, cfg, out, off)
+            eng.polish_host(task, sh.view, cfg, out, off)                 # two engines, overlapped copy
         finally:
-            del os.environ["NEXTPOLISH_B200_NO_PIPELINE"]
+            del os.environ["NEXTPOLISH_B200_PIPELINE"]
         raw = out.tobytes()
         assert {n: raw[off[i]:off[i + 1]] for i, n in enumerate(sh.names)} == want, task
