@@ -49,7 +49,7 @@ struct Dev2 {
     double* sc2;                 // [NRC*16] scores by base code
     uint16_t* kc2;               // [NRC*16]
     uint8_t* ord2;               // [NRC*16] first-seen order of base codes
-    uint8_t* ns2;                // [NRC]
+    uint8_t* ns2;                // [NRC] argmax base code of the column's score list
     int32_t* subbuf;             // [NRC + 2*NR_nd + 2] inner region lists
     // (region, read) pairs of the no-depth pass: the CIGAR walks run one thread per pair
     int32_t *nd_pcnt, *nd_poff;  // per region: candidate reads (level >= 1), scan
@@ -370,48 +370,48 @@ struct VoteVisitor {
 // contig_region_score + contig_region_correct (contig.c:456-496) over columns [c0, c1]
 NP_HD void nd_score_correct(const Dev2& w, int32_t c0, int32_t c1, double rate) {
     const Dev& d = w.d;
-    NdCtx x{&w};
-    bool zero_prev = true; int32_t pi = -1;
+    // Forward pass with the previous and the current column's score lists in thread-local arrays (the
+    // global copies are only what the backtrack needs: winning k-mer per base code, argmax base code).
+    double sp[16], sc[16]; uint16_t kc[16]; uint8_t ord[16]; bool hp[16], hc[16];
+    int pn = 0; double spmax = 0;
+    bool zero_prev = true;
     for (int32_t c = c0; c <= c1; c++) {
-        int32_t ci = w.ndidx[c];
-        double* sc = w.sc2 + (size_t)ci * 16; uint16_t* kc = w.kc2 + (size_t)ci * 16; uint8_t* ord = w.ord2 + (size_t)ci * 16;
-        bool hc[16]; for (int b = 0; b < 16; b++) hc[b] = false;
+        const int32_t ci = w.ndidx[c];
+        const uint32_t* t = w.ktab2 + w.koff[c];
+        const int32_t nk = w.nk2[ci];
+        const uint32_t total = w.cnt2[ci], refk = w.refk2[ci];
+        const uint32_t tot = total > 1 ? total - 1 : total;
+        const double dec = (double)tot * rate;
+        for (int b = 0; b < 16; b++) hc[b] = false;
         int no = 0;
-        const uint32_t* t = x.tab(c); int32_t nk = x.nk(c);
-        uint32_t total = x.cnt(c), refk = w.refk2[ci];
-        uint32_t tot = total > 1 ? total - 1 : total;
-        const double* sp = pi >= 0 ? w.sc2 + (size_t)pi * 16 : nullptr;
-        const uint8_t* po = pi >= 0 ? w.ord2 + (size_t)pi * 16 : nullptr;
-        int pn = pi >= 0 ? w.ns2[pi] : 0;
         for (int32_t j = 0; j < nk; j++) {
             uint32_t k = t[j] & 0xffffu, cnt = t[j] >> 16, pv = (k >> 4) & 0xfu;
             double s = 0;
             if (!zero_prev) {
-                if (pv == 0) { int am = po[0]; double mx = sp[am]; for (int q = 1; q < pn; q++) if (sp[po[q]] > mx) { mx = sp[po[q]]; am = po[q]; } s = mx; }
-                else {
-                    bool found = false;
-                    for (int q = 0; q < pn; q++) if (po[q] == pv) found = true;
-                    if (!found) *d.err |= ERR_MISSING_SCORE;
-                    s = sp[pv];
-                }
+                if (pv == 0) s = spmax;
+                else { if (!hp[pv]) *d.err |= ERR_MISSING_SCORE; s = sp[pv]; }
             }
             if (k == refk && total > 1) cnt--;
-            s = s + ((double)cnt - (double)tot * rate);
+            s = s + ((double)cnt - dec);
             uint32_t b = k & 0xfu;
             if (!hc[b]) { hc[b] = true; sc[b] = s; kc[b] = (uint16_t)k; ord[no++] = (uint8_t)b; }
             else if (sc[b] < s) { sc[b] = s; kc[b] = (uint16_t)k; }
         }
-        w.ns2[ci] = (uint8_t)no;
-        zero_prev = false; pi = ci;
+        int am = ord[0]; double mx = sc[am];                                   // base_max_score (base.c:185-197)
+        for (int q = 1; q < no; q++) if (sc[ord[q]] > mx) { mx = sc[ord[q]]; am = ord[q]; }
+        uint16_t* gk = w.kc2 + (size_t)ci * 16;
+        for (int q = 0; q < no; q++) gk[ord[q]] = kc[ord[q]];
+        w.ns2[ci] = (uint8_t)am;                                               // argmax base code of this column
+        for (int b = 0; b < 16; b++) { hp[b] = hc[b]; sp[b] = sc[b]; }
+        pn = no; spmax = mx; zero_prev = false;
     }
-    // backtrack
-    auto argmax = [&](int32_t ci) { const double* sc = w.sc2 + (size_t)ci * 16; const uint8_t* ord = w.ord2 + (size_t)ci * 16;
-        int am = ord[0]; double mx = sc[am]; for (int q = 1; q < w.ns2[ci]; q++) if (sc[ord[q]] > mx) { mx = sc[ord[q]]; am = ord[q]; } return (uint32_t)am; };
-    uint32_t chosen = argmax(w.ndidx[c1]);
+    (void)pn;
+    // backtrack (contig.c:473-496)
+    uint32_t chosen = w.ns2[w.ndidx[c1]];
     for (int32_t c = c1;; c--) {
-        int32_t ci = w.ndidx[c];
-        const uint32_t* t = x.tab(c); int32_t nk = x.nk(c);
-        uint32_t total = x.cnt(c), support = 0;
+        const int32_t ci = w.ndidx[c];
+        const uint32_t* t = w.ktab2 + w.koff[c]; const int32_t nk = w.nk2[ci];
+        uint32_t total = w.cnt2[ci], support = 0;
         for (int32_t j = 0; j < nk; j++) if ((t[j] & 0xfu) == chosen) support += t[j] >> 16;
         uint8_t fl = d.oflag[c];
         if (total == 1) fl |= FLAG_ZERO; else fl &= (uint8_t)~FLAG_ZERO;
@@ -419,7 +419,7 @@ NP_HD void nd_score_correct(const Dev2& w, int32_t c0, int32_t c1, double rate) 
         d.obase[c] = (uint8_t)chosen; d.oflag[c] = fl;
         if (c == c0) break;
         uint32_t k = w.kc2[(size_t)ci * 16 + chosen], pv = (k >> 4) & 0xfu;
-        chosen = (pv == 0) ? argmax(w.ndidx[c - 1]) : pv;
+        chosen = (pv == 0) ? w.ns2[w.ndidx[c - 1]] : pv;
     }
 }
 
