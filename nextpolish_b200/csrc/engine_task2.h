@@ -452,22 +452,40 @@ NP_HD int32_t inner_regions(const Dev& d, int32_t c0, int32_t c1, int32_t bs, in
 // entries stay in registers while the pairs are visited in BAM order (same first-seen order as the
 // reference's read-by-read walk, base.c:60-71).  The rolling 3-mer context starts at the pair's first vote
 // inside the range (contig.c:255,360-363).
+enum { ND_CACHE = 96 };   // pairs of a region whose metadata is cached in thread-local arrays
 NP_HD void nd_apply_pairs(const Dev2& w, int32_t c0, int32_t ncols, int32_t i, int32_t level, int32_t lo, int32_t hi,
                           int32_t ss, int32_t se) {
     const Dev& d = w.d;
     const int32_t p0 = w.nd_poff[i], p1 = w.nd_poff[i + 1];
+    // pair metadata once per call (the column loop below would otherwise re-read it from HBM per column)
+    int16_t pf[ND_CACHE], pe[ND_CACHE]; int32_t pidx[ND_CACHE]; int32_t np = 0;
+    bool cached = true;
+    for (int32_t p = p0; p < p1; p++) {
+        const int64_t r = w.ndp_read[p];
+        if (d.r_level[r] != level) continue;
+        if (ss >= 0 && (d.r_hend[r] <= ss || d.r_gpos[r] >= se + 1)) continue;        // contig_parse_region's overlap test
+        const int32_t first = w.ndp_first[p], n = w.ndp_n[p];
+        if (n <= 0 || first > hi || first + n - 1 < lo) continue;
+        if (np == ND_CACHE || first + n > 32767) { cached = false; break; }
+        pf[np] = (int16_t)first; pe[np] = (int16_t)(first + n); pidx[np] = p - p0; np++;
+    }
     for (int32_t t = lo; t <= hi; t++) {
         const int32_t c = c0 + t, ci = w.ndidx[c];
         uint32_t* tab = w.ktab2 + w.koff[c];
         const int32_t cap = w.koff[c + 1] - w.koff[c];
         int32_t nk = w.nk2[ci]; uint32_t cnt = w.cnt2[ci];
-        for (int32_t p = p0; p < p1; p++) {
-            const int64_t r = w.ndp_read[p];
-            if (d.r_level[r] != level) continue;
-            if (ss >= 0 && (d.r_hend[r] <= ss || d.r_gpos[r] >= se + 1)) continue;    // contig_parse_region's overlap test
-            const int32_t first = w.ndp_first[p], n = w.ndp_n[p];
-            if (t < first || t >= first + n) continue;
-            const uint8_t* slot = w.ndp_sym + (size_t)w.nd_soff[i] + (size_t)(p - p0) * ncols;
+        const int32_t nloop = cached ? np : p1 - p0;
+        for (int32_t q = 0; q < nloop; q++) {
+            int32_t first, end, pj;
+            if (cached) { first = pf[q]; end = pe[q]; pj = pidx[q]; }
+            else {
+                const int32_t p = p0 + q; const int64_t r = w.ndp_read[p];
+                if (d.r_level[r] != level) continue;
+                if (ss >= 0 && (d.r_hend[r] <= ss || d.r_gpos[r] >= se + 1)) continue;
+                first = w.ndp_first[p]; end = first + w.ndp_n[p]; pj = q;
+            }
+            if (t < first || t >= end) continue;
+            const uint8_t* slot = w.ndp_sym + (size_t)w.nd_soff[i] + (size_t)pj * ncols;
             const int32_t a = first > lo ? first : lo;                                 // first vote inside the range
             uint32_t kmer = slot[t];
             if (t - 1 >= a) kmer |= (uint32_t)slot[t - 1] << 4;
