@@ -57,6 +57,7 @@ struct Dev2 {
     int32_t *ndp_read, *ndp_first, *ndp_n;   // per pair: read, first column (relative to the region), symbols
     uint8_t* ndp_sym;            // symbol slots
     int32_t NP_nd;
+    int32_t *nd_reg_of, *nd_col_of;   // per no-depth column (compact index): its region, its global column
     // windows
     int32_t *wcnt, *woff;        // per k-mer region: window count, scan
     int32_t *win;                // [2*NW] (start,end)
@@ -454,7 +455,8 @@ NP_HD int32_t inner_regions(const Dev& d, int32_t c0, int32_t c1, int32_t bs, in
 // inside the range (contig.c:255,360-363).
 enum { ND_CACHE = 96 };   // pairs of a region whose metadata is cached in thread-local arrays
 NP_HD void nd_apply_pairs(const Dev2& w, int32_t c0, int32_t ncols, int32_t i, int32_t level, int32_t lo, int32_t hi,
-                          int32_t ss, int32_t se) {
+                          int32_t ss, int32_t se, int32_t ctx_lo = -1) {
+    if (ctx_lo < 0) ctx_lo = lo;                   // column (relative) where the rolling 3-mer context starts
     const Dev& d = w.d;
     const int32_t p0 = w.nd_poff[i], p1 = w.nd_poff[i + 1];
     // pair metadata once per call (the column loop below would otherwise re-read it from HBM per column)
@@ -486,7 +488,7 @@ NP_HD void nd_apply_pairs(const Dev2& w, int32_t c0, int32_t ncols, int32_t i, i
             }
             if (t < first || t >= end) continue;
             const uint8_t* slot = w.ndp_sym + (size_t)w.nd_soff[i] + (size_t)pj * ncols;
-            const int32_t a = first > lo ? first : lo;                                 // first vote inside the range
+            const int32_t a = first > ctx_lo ? first : ctx_lo;                         // first vote inside the range
             uint32_t kmer = slot[t];
             if (t - 1 >= a) kmer |= (uint32_t)slot[t - 1] << 4;
             if (t - 2 >= a) kmer |= (uint32_t)slot[t - 2] << 8;
@@ -499,6 +501,36 @@ NP_HD void nd_apply_pairs(const Dev2& w, int32_t c0, int32_t ncols, int32_t i, i
     }
 }
 
+NP_HD bool nd_isolated(const Dev2& w, int64_t i) { return chain_head(w, i) && !chain_next(w, i); }
+
+struct NdColFill {       // per region: reverse map of its columns (compact index -> region, column)
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B&) const {
+        const Dev& d = w.d;
+        int32_t c0 = d.colbase[w.ndl[2 * i]], c1 = d.colbase[w.ndl[2 * i + 1]];
+        for (int32_t c = c0; c <= c1; c++) { w.nd_reg_of[w.ndidx[c]] = (int32_t)i; w.nd_col_of[w.ndidx[c]] = c; }
+    }
+};
+// First pass of an ISOLATED region (no shared end column), one thread per column: the draft's own vote
+// (contig_as_read) and the level-2 votes.  Chained regions keep the sequential path in NodepthScore.
+struct NdTallyCols {
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t ci, B&) const {
+        const Dev& d = w.d;
+        int32_t i = w.nd_reg_of[ci];
+        if (!nd_isolated(w, i)) return;
+        int32_t c = w.nd_col_of[ci];
+        int32_t c0 = d.colbase[w.ndl[2 * i]], c1 = d.colbase[w.ndl[2 * i + 1]], ncols = c1 - c0 + 1, t = c - c0;
+        uint32_t kmer = d.obase[c];
+        if (t >= 1) kmer |= (uint32_t)d.obase[c - 1] << 4;
+        if (t >= 2) kmer |= (uint32_t)d.obase[c - 2] << 8;
+        w.refk2[ci] = (uint16_t)kmer;
+        w.ktab2[w.koff[c]] = kmer | (1u << 16);
+        w.nk2[ci] = 1; w.cnt2[ci] = 1;
+        nd_apply_pairs(w, c0, ncols, i, 2, t, t, -1, -1, 0);
+    }
+};
+
 struct NodepthScore {    // contig_score_correct(region, 0x12), one thread per chain of no-depth regions
     Dev2 w;
     template <class B> NP_HD void operator()(int64_t i0, B&) const {
@@ -508,15 +540,17 @@ struct NodepthScore {    // contig_score_correct(region, 0x12), one thread per c
         for (int64_t i = i0;; i++) {
             int32_t s = w.ndl[2 * i], e = w.ndl[2 * i + 1];
             int32_t c0 = d.colbase[s], c1 = d.colbase[e], ncols = c1 - c0 + 1;
-            uint32_t kmer = 0;
-            for (int32_t c = c0; c <= c1; c++) {                           // contig_as_read
-                int32_t ci = w.ndidx[c];
-                if (!(i > i0 && c == c0)) { w.nk2[ci] = 0; w.cnt2[ci] = 0; }   // shared column keeps its votes
-                kmer = ((kmer & 0xffu) << 4) | d.obase[c];
-                w.refk2[ci] = (uint16_t)kmer;
-                x.add(c, kmer);
+            if (!nd_isolated(w, i)) {                                          // isolated regions: done by NdTallyCols
+                uint32_t kmer = 0;
+                for (int32_t c = c0; c <= c1; c++) {                           // contig_as_read
+                    int32_t ci = w.ndidx[c];
+                    if (!(i > i0 && c == c0)) { w.nk2[ci] = 0; w.cnt2[ci] = 0; }   // shared column keeps its votes
+                    kmer = ((kmer & 0xffu) << 4) | d.obase[c];
+                    w.refk2[ci] = (uint16_t)kmer;
+                    x.add(c, kmer);
+                }
+                nd_apply_pairs(w, c0, ncols, (int32_t)i, 2, 0, ncols - 1, -1, -1);   // contig_parse_region, level == 2
             }
-            nd_apply_pairs(w, c0, ncols, (int32_t)i, 2, 0, ncols - 1, -1, -1);   // contig_parse_region, level == 2
             nd_score_correct(w, c0, c1, d.P.rate);
             int32_t* sub = w.subbuf + (size_t)w.ndidx[c0] + 2 * (size_t)i;
             int32_t ns = inner_regions(d, c0, c1, s, e, d.P.ext_len_edge, sub);
@@ -858,6 +892,10 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
         w.ns2 = be.template buf<uint8_t>("ns2", nrc);
         w.subbuf = be.template buf<int32_t>("subbuf", nrc + 2 * (size_t)w.NR_nd + 4);
         if (e1) return e1;
+        w.nd_reg_of = be.template buf<int32_t>("nd_reg_of", nrc);
+        w.nd_col_of = be.template buf<int32_t>("nd_col_of", nrc);
+        be.launch("nodepth_colfill", w.NR_nd, NdColFill{w});
+        if (w.NRC > 0) be.launch("nodepth_tally", w.NRC, NdTallyCols{w});
         be.launch("nodepth_score", w.NR_nd, NodepthScore{w});
     }
     // windows
