@@ -6,6 +6,7 @@
 // change a rounding relative to the reference's x86-64 SSE2 code.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <unistd.h>
 #include <cstdio>
@@ -124,6 +125,13 @@ __global__ void __launch_bounds__(256) k_window(npe::Dev d, npw::WinGlobals g) {
     NP_WINDOW_PHASES(x, tid, nt, ops, __syncthreads())
 }
 
+struct NcolOp {   // 1 + insertion length (0 past the end): column count of a position
+    int32_t G;
+    __host__ __device__ __forceinline__ int32_t operator()(int32_t v) const { return 1 + v; }
+};
+struct KeepOp {   // a column is emitted unless its chosen base is the gap symbol (contig.c:751)
+    __host__ __device__ __forceinline__ int32_t operator()(uint8_t b) const { return b != npd::SYM_GAP ? 1 : 0; }
+};
 struct MaxOp { __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; } };
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(#x, e_); } } while (0)
@@ -193,6 +201,30 @@ struct CudaBackend {
         cub_reserve(need);
         begin_timed("scan_sum");
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, need, in, out, (int)n, stream));
+        launches += 2;
+        end_timed();
+    }
+    // colbase[p] = sum_{q<p} (1 + ins[q]) for p in [0, G]: the +1 is applied on the fly (no ncol array)
+    void exscan_ncol(const int32_t* ins, int32_t* out, int64_t G) {
+        if (!ok) return;
+        cub::TransformInputIterator<int32_t, NcolOp, const int32_t*> it(ins, NcolOp{(int32_t)G});
+        size_t need = 0;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, it, out, (int)(G + 1), stream));
+        cub_reserve(need);
+        begin_timed("scan_sum");
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, need, it, out, (int)(G + 1), stream));
+        launches += 2;
+        end_timed();
+    }
+    // keepidx[c] = number of emitted columns before c, c in [0, C]
+    void exscan_keep(const uint8_t* obase, int32_t* out, int64_t C) {
+        if (!ok) return;
+        cub::TransformInputIterator<int32_t, KeepOp, const uint8_t*> it(obase, KeepOp());
+        size_t need = 0;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, it, out, (int)(C + 1), stream));
+        cub_reserve(need);
+        begin_timed("scan_sum");
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, need, it, out, (int)(C + 1), stream));
         launches += 2;
         end_timed();
     }

@@ -321,7 +321,7 @@ struct KeepFlag {
 struct Emit {   // contig_get_contig, contig.c:748-786
     Dev d; uint8_t lowmask;
     template <class B> NP_HD void operator()(int64_t c, B&) const {
-        if (!d.keepi[c]) return;
+        if (d.obase[c] == SYM_GAP) return;
         bool low = (d.oflag[c] & lowmask) != 0;
         // `sign` carry: flagged deleted columns since the previous emitted column of this contig
         for (int64_t q = c - 1; !low && q >= 0 && !(d.oflag[q + 1] & CF_FIRST) && d.obase[q] == SYM_GAP; q--)
@@ -368,7 +368,6 @@ int run_score_chain(BE& be, Dev& d, RunStats* st) {
     d.r_symoff = be.template buf<int32_t>("r_symoff", R + 1);
     d.r_level = be.template buf<uint8_t>("r_level", R + 1);
     d.ins = be.template buf<int32_t>("ins", (size_t)G + 1);
-    d.ncol = be.template buf<int32_t>("ncol", (size_t)G + 1);
     d.colbase = be.template buf<int32_t>("colbase", (size_t)G + 1);
     d.out_off = be.template buf<int64_t>("out_off", (size_t)d.n_ctg + 1);
     be.zero(d.ins, sizeof(int32_t) * ((size_t)G + 1));
@@ -377,8 +376,7 @@ int run_score_chain(BE& be, Dev& d, RunStats* st) {
         be.launch("read_prep", R, ReadPrep{d});
         be.inclmax_i32(d.r_wend, d.r_pm, R);
     }
-    be.launch("ncol", (int64_t)G + 1, NcolFromIns{d});
-    be.exscan_i32(d.ncol, d.colbase, (int64_t)G + 1);
+    be.exscan_ncol(d.ins, d.colbase, (int64_t)G);
     d.C = be.read_i32(d.colbase + G);
     const int32_t C = d.C;
     d.refsym = be.template buf<uint8_t>("refsym", (size_t)C + 1);
@@ -390,7 +388,6 @@ int run_score_chain(BE& be, Dev& d, RunStats* st) {
     d.votes = be.template buf<uint32_t>("votes", (size_t)C + 1);
     d.needi = be.template buf<int32_t>("needi", (size_t)C + 1);
     d.tidx = be.template buf<int32_t>("tidx", (size_t)C + 1);
-    d.keepi = be.template buf<int32_t>("keepi", (size_t)C + 1);
     d.keepidx = be.template buf<int32_t>("keepidx", (size_t)C + 1);
     if (G > 0) {
         be.launch("col_init", G, ColInit{d});
@@ -422,8 +419,7 @@ int run_score_chain(BE& be, Dev& d, RunStats* st) {
         be.launch("chain_dp", T, ChainDP{d});
     }
     if (C > 0) be.launch("anchor_cols", C, AnchorCols{d});
-    be.launch("keep_flag", (int64_t)C + 1, KeepFlag{d});
-    be.exscan_i32(d.keepi, d.keepidx, (int64_t)C + 1);
+    be.exscan_keep(d.obase, d.keepidx, (int64_t)C);
     int32_t total = be.read_i32(d.keepidx + C);
     d.out = be.template buf<uint8_t>("out", (size_t)total + 1);
     if (C > 0) be.launch("emit", C, Emit{d, (uint8_t)(FLAG_ZERO | FLAG_COVERAGE)});

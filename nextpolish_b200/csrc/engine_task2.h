@@ -36,7 +36,7 @@ struct Dev2 {
     int32_t *nd_off, *km_off;    // exclusive scans of the counts
     int32_t *ndl, *kml;          // compacted lists [2*NR]
     int32_t NR_nd, NR_km;
-    int32_t *indiff, *inreg;     // per position (+1): difference array and its scan
+    uint8_t* inreg;              // per position (+1): inside (start, end] of some region
     int32_t* r_hpm;              // prefix max of r_hend
     // nodepth scoring scratch
     int32_t *ndmark, *ndidx;     // per column
@@ -94,7 +94,8 @@ struct RunFill {
     Dev2 w;
     template <class B> NP_HD void operator()(int64_t p, B&) const {
         if (w.rs_flag[p]) w.run_s[w.rs_idx[p]] = (int32_t)p;
-        if (w.re_flag[p]) w.run_e[w.re_idx[p]] = (int32_t)p;
+        // the run ending at p is the last one started at or before p: no second scan needed
+        if (w.re_flag[p]) w.run_e[w.rs_idx[p] + w.rs_flag[p] - 1] = (int32_t)p;
     }
 };
 
@@ -234,12 +235,11 @@ struct CompactRegions {  // one thread per contig: copy its slices into the dens
         for (int32_t i = 0; i < 2 * w.km_cnt[k]; i++) w.kml[2 * w.km_off[k] + i] = km[i];
     }
 };
-struct RegionDiff {      // mark (start, end] of every region of both lists in a difference array
+struct RegionDiff {      // mark the positions (start, end] of every region of both lists
     Dev2 w; int which;
-    template <class B> NP_HD void operator()(int64_t i, B& be) const {
+    template <class B> NP_HD void operator()(int64_t i, B&) const {
         const int32_t* l = which == 0 ? w.ndl : w.kml;
-        be.atomic_add(&w.indiff[l[2 * i] + 1], 1);
-        be.atomic_add(&w.indiff[l[2 * i + 1] + 1], -1);
+        for (int32_t p = l[2 * i] + 1; p <= l[2 * i + 1]; p++) w.inreg[p] = 1;
     }
 };
 struct InsertLen2 {      // contig_create_insert_region (contig.c:182-245)
@@ -793,7 +793,6 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
     w.r_hpm = be.template buf<int32_t>("r_hpm", R + 1);
     d.r_level = be.template buf<uint8_t>("r_level", R + 1);
     d.ins = be.template buf<int32_t>("ins", (size_t)G + 1);
-    d.ncol = be.template buf<int32_t>("ncol", (size_t)G + 1);
     d.colbase = be.template buf<int32_t>("colbase", (size_t)G + 1);
     d.out_off = be.template buf<int64_t>("out_off", (size_t)d.n_ctg + 1);
     be.zero(d.ins, sizeof(int32_t) * ((size_t)G + 1));
@@ -805,10 +804,8 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
     w.rs_flag = be.template buf<int32_t>("rs_flag", (size_t)G + 2);
     w.re_flag = be.template buf<int32_t>("re_flag", (size_t)G + 2);
     w.rs_idx = be.template buf<int32_t>("rs_idx", (size_t)G + 2);
-    w.re_idx = be.template buf<int32_t>("re_idx", (size_t)G + 2);
     be.launch("run_flags", (int64_t)G + 1, RunFlags{w});
     be.exscan_i32(w.rs_flag, w.rs_idx, (int64_t)G + 1);
-    be.exscan_i32(w.re_flag, w.re_idx, (int64_t)G + 1);
     w.n_runs = be.read_i32(w.rs_idx + G);
     w.run_s = be.template buf<int32_t>("run_s", (size_t)w.n_runs + 1);
     w.run_e = be.template buf<int32_t>("run_e", (size_t)w.n_runs + 1);
@@ -833,15 +830,12 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
     w.kml = be.template buf<int32_t>("kml", 2 * (size_t)w.NR_km + 2);
     be.launch("compact_regions", d.n_ctg, CompactRegions{w});
     // insertion columns inside regions only
-    w.indiff = be.template buf<int32_t>("indiff", (size_t)G + 2);
-    w.inreg = be.template buf<int32_t>("inreg", (size_t)G + 2);
-    be.zero(w.indiff, sizeof(int32_t) * ((size_t)G + 2));
+    w.inreg = be.template buf<uint8_t>("inreg", (size_t)G + 2);
+    be.zero(w.inreg, (size_t)G + 2);
     if (w.NR_nd > 0) be.launch("region_diff_nd", w.NR_nd, RegionDiff{w, 0});
     if (w.NR_km > 0) be.launch("region_diff_km", w.NR_km, RegionDiff{w, 1});
-    be.inclsum_i32(w.indiff, w.inreg, (int64_t)G + 2);
     if (R > 0) be.launch("insert_len2", R, InsertLen2{w});
-    be.launch("ncol", (int64_t)G + 1, NcolFromIns{d});
-    be.exscan_i32(d.ncol, d.colbase, (int64_t)G + 1);
+    be.exscan_ncol(d.ins, d.colbase, (int64_t)G);
     d.C = be.read_i32(d.colbase + G);
     const int32_t C = d.C;
     d.refsym = be.template buf<uint8_t>("refsym", (size_t)C + 1);
@@ -849,7 +843,6 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
     d.obase = be.template buf<uint8_t>("obase", (size_t)C + 1);
     d.oflag = be.template buf<uint8_t>("oflag", (size_t)C + 1);
     d.colpos = be.template buf<int32_t>("colpos", (size_t)C + 1);
-    d.keepi = be.template buf<int32_t>("keepi", (size_t)C + 1);
     d.keepidx = be.template buf<int32_t>("keepidx", (size_t)C + 1);
     w.ndmark = be.template buf<int32_t>("ndmark", (size_t)C + 2);
     w.ndidx = be.template buf<int32_t>("ndidx", (size_t)C + 2);
@@ -925,8 +918,7 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
         be.launch("window_vote", w.NW, WindowVote{w});
         be.launch("window_apply", w.NW, WindowApply{w});
     }
-    be.launch("keep_flag", (int64_t)C + 1, KeepFlag{d});
-    be.exscan_i32(d.keepi, d.keepidx, (int64_t)C + 1);
+    be.exscan_keep(d.obase, d.keepidx, (int64_t)C);
     int32_t total = 0, err = 0;
     { const int32_t* ptrs[2] = {d.keepidx + C, d.err}; int32_t v[2]; be.read_many(ptrs, 2, v); total = v[0]; err = v[1]; }
     d.out = be.template buf<uint8_t>("out", (size_t)total + 1);

@@ -40,7 +40,6 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
     d.r_symoff = be.template buf<int32_t>("r_symoff", R + 1);
     d.r_level = be.template buf<uint8_t>("r_level", R + 1);
     d.ins = be.template buf<int32_t>("ins", (size_t)G + 1);
-    d.ncol = be.template buf<int32_t>("ncol", (size_t)G + 1);
     d.colbase = be.template buf<int32_t>("colbase", (size_t)G + 1);
     d.out_off = be.template buf<int64_t>("out_off", (size_t)d.n_ctg + 1);
     be.zero(d.ins, sizeof(int32_t) * ((size_t)G + 1));
@@ -48,8 +47,7 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
         be.launch("read_prep", R, ReadPrep{d});
         be.inclmax_i32(d.r_wend, d.r_pm, R);
     }
-    be.launch("ncol", (int64_t)G + 1, NcolFromIns{d});
-    be.exscan_i32(d.ncol, d.colbase, (int64_t)G + 1);
+    be.exscan_ncol(d.ins, d.colbase, (int64_t)G);
 
     // ---- window plan: largest W whose biggest window fits the shared-memory budget
     npw::WinGlobals g; memset(&g, 0, sizeof(g));
@@ -94,19 +92,18 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
     d.votes = be.template buf<uint32_t>("votes", (size_t)C + 1);
     d.needi = be.template buf<int32_t>("needi", (size_t)C + 1);
     d.tidx = be.template buf<int32_t>("tidx", (size_t)C + 1);
-    d.keepi = be.template buf<int32_t>("keepi", (size_t)C + 1);
     d.keepidx = be.template buf<int32_t>("keepidx", (size_t)C + 1);
     be.zero(d.needi, sizeof(int32_t) * ((size_t)C + 1));
     be.zero(g.r_need, (size_t)R + 1);
     if (g.n_win > 0) be.run_windows(d, g, need);
 
-    be.exscan_i32(d.needi, d.tidx, (int64_t)C + 1);
-    int32_t n_unres = 0;
-    {
-        const int32_t* ptrs[2] = {d.tidx + C, g.n_unresolved};
-        int32_t vals[2];
-        be.read_many(ptrs, 2, vals);
-        d.T = vals[0]; n_unres = vals[1];
+    // windows that left something unresolved bump a counter: the compaction scan over all columns and the
+    // general kernels run only then
+    int32_t n_unres = be.read_i32(g.n_unresolved);
+    d.T = 0;
+    if (n_unres > 0) {
+        be.exscan_i32(d.needi, d.tidx, (int64_t)C + 1);
+        d.T = be.read_i32(d.tidx + C);
     }
     int32_t E = 0, Wd = 0;
     if (d.T > 0) {                                           // fallback: general kernels on the marked stretches
@@ -134,8 +131,7 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
         be.launch("build_table", T, BuildTable{d});
         be.launch("chain_dp", T, ChainDP{d});
     }
-    be.launch("keep_flag", (int64_t)C + 1, KeepFlag{d});
-    be.exscan_i32(d.keepi, d.keepidx, (int64_t)C + 1);
+    be.exscan_keep(d.obase, d.keepidx, (int64_t)C);
     int32_t total = 0, err = 0;
     {
         const int32_t* ptrs[2] = {d.keepidx + C, d.err};

@@ -38,6 +38,14 @@ struct EmuBackend {
         int64_t s = 0;
         for (int64_t i = 0; i < n; i++) { int32_t v = in[i]; out[i] = (int32_t)s; s += v; }
     }
+    void exscan_ncol(const int32_t* ins, int32_t* out, int64_t G) {
+        int64_t s = 0;
+        for (int64_t i = 0; i <= G; i++) { out[i] = (int32_t)s; s += 1 + ins[i]; }
+    }
+    void exscan_keep(const uint8_t* obase, int32_t* out, int64_t C) {
+        int64_t s = 0;
+        for (int64_t i = 0; i <= C; i++) { out[i] = (int32_t)s; s += obase[i] != 3 ? 1 : 0; }
+    }
     void inclsum_i32(const int32_t* in, int32_t* out, int64_t n) {
         int64_t s = 0;
         for (int64_t i = 0; i < n; i++) { s += in[i]; out[i] = (int32_t)s; }
