@@ -40,35 +40,58 @@ def rank_env():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clock + throttle reasons of one GPU during the timed region."""
+    """Samples SM clock + throttle reasons of one GPU during the timed region (NVML every 5 ms; falls back
+    to polling nvidia-smi when pynvml is unavailable)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.mx, self.reasons, self.stop_flag, self.n = index, [], [], set(), False, 0
 
-    def run(self):
+    def _nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        self.mx.append(float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)))
+        bits = {"hw_slowdown": N.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": N.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+            r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, b in bits.items():
+                if r & b:
+                    self.reasons.add(name)
+            self.n += 1
+            time.sleep(0.005)
+
+    def _smi(self):
         while not self.stop_flag:
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                r = [x.strip() for x in o.split(",")]
+                if len(r) >= 6 and r[0].replace(".", "").isdigit():
+                    self.sm.append(float(r[0])); self.mx.append(float(r[1])); self.n += 1
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
             except Exception:
                 pass
             time.sleep(0.1)
 
+    def run(self):
+        try:
+            self._nvml()
+        except Exception:
+            self._smi()
+
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": self.n}
 
 
 def measured_peak_gbs():
@@ -136,7 +159,9 @@ def cpu_reference_run(steps, warmup, tasks, tmpdir):
         one_step()
     dt = time.time() - t0
     mbp = total_bp * len(tasks) * steps / 1e6
-    sample = "%d contigs x %d bp, %gx, tasks %s, %d steps" % (WORKLOAD["n_contigs"], WORKLOAD["contig_len"], WORKLOAD["depth"], list(tasks), steps)
+    sample = ("%d contigs x %d bp, %gx, tasks %s, %d steps; one process per contig (the reference's parallel grain, "
+              "nextpolish1.py:223-224): %d of %d host threads usable" % (WORKLOAD["n_contigs"], WORKLOAD["contig_len"], WORKLOAD["depth"],
+                                                                      list(tasks), steps, nproc, ncpu))
     return mbp / dt, dt / steps * 1e3, kind, nproc, sample
 
 

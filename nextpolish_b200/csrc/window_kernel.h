@@ -578,7 +578,7 @@ NP_HD void ph_chain(WCtx& x, int32_t tid, int32_t nt) {
             if (col_last(x, lc)) fl |= CF_LAST;
             if (T.votes() == 1) fl |= FLAG_ZERO;
             if (support / (double)T.votes() < d.P.min_count_ratio_skip) fl |= FLAG_COVERAGE;
-            d.obase[c] = (uint8_t)chosen; d.oflag[c] = fl; d.needi[c] = 0;
+            d.obase[c] = (uint8_t)chosen; d.oflag[c] = fl;
             if (lc == lc0) break;
             uint32_t k = T.ekmer(ent), pv = (k >> 4) & 0xfu;
             TabEntry P{&x.tab, x.tabidx[lc - 1]};
@@ -594,7 +594,6 @@ NP_HD void ph_anchors(WCtx& x, int32_t tid, int32_t nt) {
     for (int32_t lc = x.cown0 + tid; lc < x.cown1; lc += nt) {
         int32_t c = x.cb0 + lc;
         uint8_t ci = x.colinfo[lc];
-        d.mism[c] = ci & 1;
         if (x.tabidx[lc] != -1) {
             int32_t ti = x.tabidx[lc];
             // votes of table columns are needed by the fallback tables (capacity); recount if no table
@@ -609,8 +608,7 @@ NP_HD void ph_anchors(WCtx& x, int32_t tid, int32_t nt) {
         if (col_last(x, lc)) fl |= CF_LAST;
         if (!(ci & 2)) fl |= FLAG_ZERO;                      // only the draft's own vote
         if (1.0 < d.P.min_count_ratio_skip) fl |= FLAG_COVERAGE;
-        d.obase[c] = (uint8_t)be_get(x.refw, lc); d.oflag[c] = fl; d.needi[c] = 0;
-        d.votes[c] = (ci & 2) ? 2 : 1;
+        d.obase[c] = (uint8_t)be_get(x.refw, lc); d.oflag[c] = fl;      // needi stays 0 (cleared before the launch)
     }
 }
 template <class B>
