@@ -81,6 +81,7 @@ struct WCtx {             // per-window context: globals + carved shared memory
     // shared memory
     uint8_t* rec; const uint32_t* recoff;     // staged records and their offsets (16-byte units, global)
     int32_t *cs, *cn, *so;                    // per read: local column of first stored symbol, count, pool offset
+    uint32_t* mm;                             // per read: bit k set = its k-th string word disagrees with the draft somewhere
     uint32_t *str, *refw, *acc;               // string pool, draft symbol words, compare accumulators
     uint8_t* colinfo;                         // per local column: 1 mism, 2 covered, 8 sub-column
     int16_t* tabidx;                          // per local column: table index or -1
@@ -100,7 +101,7 @@ NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int3
     if (recarea < mintab) recarea = mintab;
     b += recarea + align16(4u * (uint32_t)(nr + 1));
     b += align16(2u * (uint32_t)(npos + 2)) + align16(8u * (uint32_t)(ncols / 32 + 2));
-    b += 3 * align16(4u * (uint32_t)nr);
+    b += 4 * align16(4u * (uint32_t)nr);
     b += align16(4u * (uint32_t)(strw + 4));
     b += 3 * align16(4u * (uint32_t)(ncols / 8 + 3));
     b += align16((uint32_t)ncols + 16);
@@ -178,6 +179,7 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
     x.cs = (int32_t*)p; p += align16(4u * (uint32_t)x.nr);
     x.cn = (int32_t*)p; p += align16(4u * (uint32_t)x.nr);
     x.so = (int32_t*)p; p += align16(4u * (uint32_t)x.nr);
+    x.mm = (uint32_t*)p; p += align16(4u * (uint32_t)x.nr);
     x.str = (uint32_t*)p; p += align16(4u * (uint32_t)(x.strw + 4));
     x.refw = (uint32_t*)p; p += align16(4u * (uint32_t)(x.ncols / 8 + 3));
     x.acc = (uint32_t*)p; p += 2 * align16(4u * (uint32_t)(x.ncols / 8 + 3));
@@ -318,7 +320,7 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
     for (;;) {                                            // reads are handed out dynamically: no straggler round
         int32_t i = be.atomic_add_ret(&x.ctr[4], 1);
         if (i >= x.nr) break;
-        x.cs[i] = 0; x.cn[i] = 0; x.so[i] = 0;
+        x.cs[i] = 0; x.cn[i] = 0; x.so[i] = 0; x.mm[i] = 0;
         const uint8_t* p = x.rec + (size_t)(x.recoff[i] - x.recoff[0]) * 16;
         const uint32_t* hw = (const uint32_t*)p;
         Rec rc;
@@ -416,13 +418,15 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
             // compare against the draft's symbol words (same alignment): per column "covered" / "disagrees"
             const uint32_t* sp = x.str + off;
             int32_t base = sw.cs & ~7, cw0 = base >> 3, nwd = (sw.cs + sw.n - base + 7) >> 3;
+            uint32_t mmask = nwd > 32 ? 0xffffffffu : 0u;       // very long strings: no fast path in the tally
             for (int32_t kq = 0; kq < nwd; kq++) {
                 uint32_t m = nib_mask(sw.cs - base - 8 * kq, sw.cs + sw.n - base - 8 * kq);
                 uint32_t df = (sp[kq] ^ x.refw[cw0 + kq]) & m;
                 df |= df >> 1; df |= df >> 2; df &= 0x11111111u;
-                if (df) be.atomic_or(&x.acc[2 * (cw0 + kq)], df);
+                if (df) { be.atomic_or(&x.acc[2 * (cw0 + kq)], df); if (kq < 32) mmask |= 1u << kq; }
                 be.atomic_or(&x.acc[2 * (cw0 + kq) + 1], m & 0x11111111u);
             }
+            x.mm[i] = mmask;
         }
     }
 }
@@ -476,8 +480,16 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
         for (int32_t r = blo; r < bhi; r++) {
             int32_t i = lc - x.cs[r];
             if (i < 0 || i >= x.cn[r]) continue;
-            const uint32_t* s = x.str + x.so[r];
             int32_t al = x.cs[r] & 7;                       // the string starts at nibble `al` of its first word
+            votes++;
+            // fast path: the read agrees with the draft in the words holding columns lc-2..lc and has cast at
+            // least two symbols before lc -> it votes the draft's own 3-mer (entry 0)
+            if (i >= 2) {
+                uint32_t mmr = x.mm[r];
+                int32_t k0 = (i - 2 + al) >> 3, k1 = (i + al) >> 3;
+                if (k1 < 32 && !(((mmr >> k0) | (mmr >> k1)) & 1u)) { T.e(0) += 1u << 16; continue; }
+            }
+            const uint32_t* s = x.str + x.so[r];
             // symbols i-2..i of the read's string as one funnel-shifted extract
             uint32_t kk;
             if (i >= 2) {
@@ -488,7 +500,6 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
                 kk = be_get(s, i + al);
                 if (i >= 1) kk |= be_get(s, i - 1 + al) << 4;
             }
-            votes++;
             int32_t j = 0;
             for (; j < nk; j++) if ((T.e(j) & 0xffffu) == kk) { T.e(j) += 1u << 16; break; }
             if (j == nk) { if (nk < WK) T.e(nk++) = kk | (1u << 16); else T.bad() = 1; }
