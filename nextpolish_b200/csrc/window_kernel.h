@@ -105,7 +105,7 @@ NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int3
     b += align16(4u * (uint32_t)(strw + 4));
     b += 3 * align16(4u * (uint32_t)(ncols / 8 + 3));
     b += align16((uint32_t)ncols + 16);
-    b += 2 * align16(2u * (uint32_t)(ncols + 8));
+    b += align16(2u * (uint32_t)(ncols + 8)) + align16(2u * (uint32_t)(ncols / 2 + 16));   // tabidx, tabcol
     return b;
 }
 
@@ -159,6 +159,7 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
     uint32_t recarea = align16(recbytes), mintab = (uint32_t)(x.ncols / 4 + 16) * (uint32_t)TAB_BYTES;
     if (recarea < mintab) recarea = mintab;
     x.tmax = (int32_t)(recarea / TAB_BYTES) & ~7;      // multiple of 8 keeps every array 8-byte aligned
+    if (x.tmax > ((x.ncols / 2 + 8) & ~7)) x.tmax = (x.ncols / 2 + 8) & ~7;   // the dense list (tabcol) holds ncols/2+16 entries
     uint8_t* p = smem + 64;
     x.ctr = (int32_t*)(smem + 16);
     x.rec = p;
@@ -474,8 +475,7 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
             k |= be_get(x.refw, lc - 1) << 4;
             if (!col_first(x, lc - 1)) k |= be_get(x.refw, lc - 2) << 8;
         }
-        int32_t nk = 0; uint32_t votes = 1;
-        T.e(nk++) = k | (1u << 16);
+        int32_t nk = 1; uint32_t votes = 1, e0 = 1;            // entry 0 = the draft's 3-mer, its count kept in a register
         int32_t blo = x.blk[2 * (lc >> 5)], bhi = x.blk[2 * (lc >> 5) + 1];
         for (int32_t r = blo; r < bhi; r++) {
             int32_t i = lc - x.cs[r];
@@ -487,7 +487,7 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
             if (i >= 2) {
                 uint32_t mmr = x.mm[r];
                 int32_t k0 = (i - 2 + al) >> 3, k1 = (i + al) >> 3;
-                if (k1 < 32 && !(((mmr >> k0) | (mmr >> k1)) & 1u)) { T.e(0) += 1u << 16; continue; }
+                if (k1 < 32 && !(((mmr >> k0) | (mmr >> k1)) & 1u)) { e0++; continue; }
             }
             const uint32_t* s = x.str + x.so[r];
             // symbols i-2..i of the read's string as one funnel-shifted extract
@@ -500,10 +500,12 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
                 kk = be_get(s, i + al);
                 if (i >= 1) kk |= be_get(s, i - 1 + al) << 4;
             }
-            int32_t j = 0;
+            if (kk == k) { e0++; continue; }
+            int32_t j = 1;
             for (; j < nk; j++) if ((T.e(j) & 0xffffu) == kk) { T.e(j) += 1u << 16; break; }
             if (j == nk) { if (nk < WK) T.e(nk++) = kk | (1u << 16); else T.bad() = 1; }
         }
+        T.e(0) = k | (e0 << 16);
         T.nk() = (uint8_t)nk; T.votes() = (uint16_t)votes;
     }
 }
