@@ -96,6 +96,10 @@ __global__ void __launch_bounds__(256) k_window(npe::Dev d, npw::WinGlobals g) {
     npw::win_setup(x, (int32_t)blockIdx.x, smem);
     const int tid = threadIdx.x, nt = blockDim.x;
     CudaOps ops;
+    long long t_prev = 0;
+    const bool stamp = g.phase_cycles != nullptr && tid == 0;
+    if (stamp) t_prev = clock64();
+#define NP_STAMP(k) do { if (stamp) { long long t_ = clock64(); atomicAdd(&g.phase_cycles[k], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
     const uint32_t bar = smem_u32(smem);
     const uint32_t recbytes = (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u;
     if (tid == 0) {
@@ -120,9 +124,12 @@ __global__ void __launch_bounds__(256) k_window(npe::Dev d, npw::WinGlobals g) {
     npw::ph_clear(x, tid, nt);
     __syncthreads();
     npw::ph_ref(x, tid, nt, ops);
+    NP_STAMP(0);
     if (recbytes) mbar_wait(bar, 0);
     __syncthreads();
-    NP_WINDOW_PHASES(x, tid, nt, ops, __syncthreads())
+    NP_STAMP(1);
+    NP_WINDOW_PHASES(x, tid, nt, ops, __syncthreads(), NP_STAMP)
+    NP_STAMP(6);
 }
 
 struct NcolOp {   // 1 + insertion length (0 past the end): column count of a position
@@ -265,10 +272,23 @@ struct CudaBackend {
             CUDA_TRY(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
             attr_set = want;
         }
+        npw::WinGlobals gg = g;
+        gg.phase_cycles = nullptr;
+        if (getenv("NEXTPOLISH_B200_PHASE_CYCLES")) {            // tuning only
+            gg.phase_cycles = (unsigned long long*)buf<unsigned long long>("phase_cycles", 16);
+            CUDA_TRY(cudaMemsetAsync(gg.phase_cycles, 0, 16 * sizeof(unsigned long long), stream));
+        }
         int threads = kWinThreads;
         if (const char* ev = getenv("NEXTPOLISH_B200_WIN_THREADS")) { int v = atoi(ev); if (v >= 64 && v <= 256 && v % 32 == 0) threads = v; }   // tuning only
         begin_timed("pileup_scan");
-        k_window<<<(unsigned)g.n_win, threads, (size_t)want, stream>>>(d, g);
+        k_window<<<(unsigned)g.n_win, threads, (size_t)want, stream>>>(d, gg);
+        if (gg.phase_cycles) {
+            unsigned long long h[16];
+            CUDA_TRY(cudaMemcpyAsync(h, gg.phase_cycles, sizeof(h), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            fprintf(stderr, "k_window phase cycles per CTA (thread 0): clear+ref %llu, wait-stage %llu, expand %llu, colinfo+mark %llu, tally %llu, chain+anchors %llu, finish %llu\n",
+                    h[0] / g.n_win, h[1] / g.n_win, h[2] / g.n_win, h[3] / g.n_win, h[4] / g.n_win, h[5] / g.n_win, h[6] / g.n_win);
+        }
         CUDA_TRY(cudaGetLastError());
         launches++;
         end_timed();

@@ -9,13 +9,13 @@ namespace npe {
 
 // One window, all phases, for a backend-provided "thread range" (tid, nt) and barrier.
 // CUDA: tid = threadIdx.x, nt = blockDim.x, barrier = __syncthreads; emu: tid = 0, nt = 1, no-op.
-#define NP_WINDOW_PHASES(x, tid, nt, ops, BARRIER)                 \
-    npw::ph_expand(x, tid, nt, ops);      BARRIER;                  \
+#define NP_WINDOW_PHASES(x, tid, nt, ops, BARRIER, STAMP)          \
+    npw::ph_expand(x, tid, nt, ops);      BARRIER; STAMP(2);        \
     npw::ph_colinfo(x, tid, nt);          BARRIER;                  \
-    npw::ph_mark_tables(x, tid, nt, ops); BARRIER;                  \
-    npw::ph_tally(x, tid, nt);            BARRIER;                  \
+    npw::ph_mark_tables(x, tid, nt, ops); BARRIER; STAMP(3);        \
+    npw::ph_tally(x, tid, nt);            BARRIER; STAMP(4);        \
     npw::ph_chain(x, tid, nt);            /* disjoint columns: */   \
-    npw::ph_anchors(x, tid, nt);          BARRIER;                  \
+    npw::ph_anchors(x, tid, nt);          BARRIER; STAMP(5);        \
     npw::ph_finish(x, tid, nt, ops);
 
 struct V2Stats { int32_t W, n_win, smem, unresolved_windows, fallback_cols; };

@@ -42,6 +42,7 @@ struct WinGlobals {       // extra global arrays of the fused path
     int32_t* maxneed;                         // [1]
     uint8_t* r_need;                          // [n_reads] reads the fallback path must expand
     int32_t* n_unresolved;                    // [1]
+    unsigned long long* phase_cycles;         // [16] optional per-phase cycle sums over all CTAs (tuning), or null
 };
 
 // Table columns live in a structure-of-arrays pool (entry-major) so that the threads of a warp, which
@@ -69,6 +70,14 @@ struct TabEntry {          // accessor of one table column
     NP_HD uint8_t&  bad() const { return p->bad[t]; }
 };
 
+struct alignas(16) Quad { uint32_t a, b, c, d; };
+struct alignas(16) ReadMeta {
+    int32_t cs;            // local column of the first stored symbol
+    int32_t cn;            // stored symbols
+    int32_t so;            // word offset of the string in the pool
+    uint32_t mm;           // bit k set = the k-th string word disagrees with the draft somewhere
+};
+
 struct WCtx {             // per-window context: globals + carved shared memory
     Dev d; WinGlobals g;
     int32_t win, k, gs, ge, p0, p1, e0, e1;   // contig, owned [p0,p1), extended [e0,e1)
@@ -80,8 +89,7 @@ struct WCtx {             // per-window context: globals + carved shared memory
     int32_t strw, tmax;                       // string pool words, table pool entries
     // shared memory
     uint8_t* rec; const uint32_t* recoff;     // staged records and their offsets (16-byte units, global)
-    int32_t *cs, *cn, *so;                    // per read: local column of first stored symbol, count, pool offset
-    uint32_t* mm;                             // per read: bit k set = its k-th string word disagrees with the draft somewhere
+    ReadMeta* rd;                             // per read: one 16-byte record (a single 128-bit shared-memory load)
     uint32_t *str, *refw, *acc;               // string pool, draft symbol words, compare accumulators
     uint8_t* colinfo;                         // per local column: 1 mism, 2 covered, 8 sub-column
     int16_t* tabidx;                          // per local column: table index or -1
@@ -101,7 +109,7 @@ NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int3
     if (recarea < mintab) recarea = mintab;
     b += recarea + align16(4u * (uint32_t)(nr + 1));
     b += align16(2u * (uint32_t)(npos + 2)) + align16(8u * (uint32_t)(ncols / 32 + 2));
-    b += 4 * align16(4u * (uint32_t)nr);
+    b += 16u * (uint32_t)nr;
     b += align16(4u * (uint32_t)(strw + 4));
     b += 3 * align16(4u * (uint32_t)(ncols / 8 + 3));
     b += align16((uint32_t)ncols + 16);
@@ -177,10 +185,7 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
     x.recoff = (const uint32_t*)p; p += align16(4u * (uint32_t)(x.nr + 1));
     x.lcb = (uint16_t*)p; p += align16(2u * (uint32_t)(x.npos + 2));
     x.blk = (int32_t*)p; p += align16(8u * (uint32_t)(x.ncols / 32 + 2));
-    x.cs = (int32_t*)p; p += align16(4u * (uint32_t)x.nr);
-    x.cn = (int32_t*)p; p += align16(4u * (uint32_t)x.nr);
-    x.so = (int32_t*)p; p += align16(4u * (uint32_t)x.nr);
-    x.mm = (uint32_t*)p; p += align16(4u * (uint32_t)x.nr);
+    x.rd = (ReadMeta*)p; p += 16u * (uint32_t)x.nr;
     x.str = (uint32_t*)p; p += align16(4u * (uint32_t)(x.strw + 4));
     x.refw = (uint32_t*)p; p += align16(4u * (uint32_t)(x.ncols / 8 + 3));
     x.acc = (uint32_t*)p; p += 2 * align16(4u * (uint32_t)(x.ncols / 8 + 3));
@@ -257,7 +262,10 @@ NP_HD void put_const(uint32_t* dst, int32_t di, int32_t len, uint32_t sym) {
 
 // ---- phase 0: clear + draft symbols --------------------------------------------------------------
 NP_HD void ph_clear(WCtx& x, int32_t tid, int32_t nt) {
-    for (int32_t i = tid; i < x.strw + 4; i += nt) x.str[i] = 0;
+    {   // the string pool is 16-byte aligned: clear it with 128-bit stores
+        Quad* q4 = (Quad*)x.str; const Quad z{0u, 0u, 0u, 0u};
+        for (int32_t i = tid; i < (x.strw + 4 + 3) / 4; i += nt) q4[i] = z;
+    }
     for (int32_t i = tid; i < x.ncols / 8 + 3; i += nt) { x.refw[i] = 0; x.acc[2 * i] = 0; x.acc[2 * i + 1] = 0; }
     for (int32_t i = tid; i < x.ncols + 16; i += nt) x.colinfo[i] = 0;
     for (int32_t i = tid; i < x.ncols + 8; i += nt) x.tabidx[i] = -1;
@@ -321,7 +329,7 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
     for (;;) {                                            // reads are handed out dynamically: no straggler round
         int32_t i = be.atomic_add_ret(&x.ctr[4], 1);
         if (i >= x.nr) break;
-        x.cs[i] = 0; x.cn[i] = 0; x.so[i] = 0; x.mm[i] = 0;
+        x.rd[i] = ReadMeta{0, 0, 0, 0u};
         const uint8_t* p = x.rec + (size_t)(x.recoff[i] - x.recoff[0]) * 16;
         const uint32_t* hw = (const uint32_t*)p;
         Rec rc;
@@ -410,7 +418,7 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
             }
             if (pos > end || pos > x.e1 + 1) break;
         }
-        x.cs[i] = sw.cs; x.cn[i] = sw.n; x.so[i] = off;
+        uint32_t mmask = 0;
         if (sw.n > 0) {
             for (int32_t bq = sw.cs >> 5; bq <= (sw.cs + sw.n - 1) >> 5; bq++) {
                 be.atomic_min(&x.blk[2 * bq], i);
@@ -419,7 +427,7 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
             // compare against the draft's symbol words (same alignment): per column "covered" / "disagrees"
             const uint32_t* sp = x.str + off;
             int32_t base = sw.cs & ~7, cw0 = base >> 3, nwd = (sw.cs + sw.n - base + 7) >> 3;
-            uint32_t mmask = nwd > 32 ? 0xffffffffu : 0u;       // very long strings: no fast path in the tally
+            mmask = nwd > 32 ? 0xffffffffu : 0u;                // very long strings: no fast path in the tally
             for (int32_t kq = 0; kq < nwd; kq++) {
                 uint32_t m = nib_mask(sw.cs - base - 8 * kq, sw.cs + sw.n - base - 8 * kq);
                 uint32_t df = (sp[kq] ^ x.refw[cw0 + kq]) & m;
@@ -427,8 +435,8 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
                 if (df) { be.atomic_or(&x.acc[2 * (cw0 + kq)], df); if (kq < 32) mmask |= 1u << kq; }
                 be.atomic_or(&x.acc[2 * (cw0 + kq) + 1], m & 0x11111111u);
             }
-            x.mm[i] = mmask;
         }
+        x.rd[i] = ReadMeta{sw.cs, sw.n, off, mmask};
     }
 }
 
@@ -478,18 +486,19 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
         int32_t nk = 1; uint32_t votes = 1, e0 = 1;            // entry 0 = the draft's 3-mer, its count kept in a register
         int32_t blo = x.blk[2 * (lc >> 5)], bhi = x.blk[2 * (lc >> 5) + 1];
         for (int32_t r = blo; r < bhi; r++) {
-            int32_t i = lc - x.cs[r];
-            if (i < 0 || i >= x.cn[r]) continue;
-            int32_t al = x.cs[r] & 7;                       // the string starts at nibble `al` of its first word
+            const ReadMeta m = x.rd[r];                     // one 128-bit load
+            int32_t i = lc - m.cs;
+            if (i < 0 || i >= m.cn) continue;
+            int32_t al = m.cs & 7;                          // the string starts at nibble `al` of its first word
             votes++;
             // fast path: the read agrees with the draft in the words holding columns lc-2..lc and has cast at
             // least two symbols before lc -> it votes the draft's own 3-mer (entry 0)
             if (i >= 2) {
-                uint32_t mmr = x.mm[r];
+                uint32_t mmr = m.mm;
                 int32_t k0 = (i - 2 + al) >> 3, k1 = (i + al) >> 3;
                 if (k1 < 32 && !(((mmr >> k0) | (mmr >> k1)) & 1u)) { e0++; continue; }
             }
-            const uint32_t* s = x.str + x.so[r];
+            const uint32_t* s = x.str + m.so;
             // symbols i-2..i of the read's string as one funnel-shifted extract
             uint32_t kk;
             if (i >= 2) {
@@ -612,7 +621,7 @@ NP_HD void ph_anchors(WCtx& x, int32_t tid, int32_t nt) {
             // votes of table columns are needed by the fallback tables (capacity); recount if no table
             uint32_t v = 1;
             if (ti >= 0) v = x.tab.votes[ti];
-            else for (int32_t r = 0; r < x.nr; r++) { int32_t i = lc - x.cs[r]; if (i >= 0 && i < x.cn[r]) v++; }
+            else for (int32_t r = 0; r < x.nr; r++) { int32_t i = lc - x.rd[r].cs; if (i >= 0 && i < x.rd[r].cn) v++; }
             d.votes[c] = v;
             continue;
         }

@@ -74,7 +74,8 @@ struct EmuBackend {
             memcpy((void*)x.recoff, d.rec_off + x.rlo, 4 * (size_t)(x.nr + 1));
             npw::ph_clear(x, 0, 1);
             npw::ph_ref(x, 0, 1, ops);
-            NP_WINDOW_PHASES(x, 0, 1, ops, (void)0)
+#define NP_NOSTAMP(k) (void)0
+            NP_WINDOW_PHASES(x, 0, 1, ops, (void)0, NP_NOSTAMP)
         }
     }
 };
