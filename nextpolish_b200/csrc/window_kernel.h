@@ -325,7 +325,10 @@ struct StrWriter {
 template <class B>
 NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
     const Dev& d = x.d;
-    for (int32_t i = tid; i < x.nr; i += nt) {
+    (void)tid; (void)nt;
+    for (;;) {                                            // reads are handed out dynamically: no straggler round
+        int32_t i = be.atomic_add_ret(&x.ctr[4], 1);
+        if (i >= x.nr) break;
         x.rd[i] = ReadMeta{0, 0, 0, 0u};
         const uint8_t* p = x.rec + (size_t)(x.recoff[i] - x.recoff[0]) * 16;
         const uint32_t* hw = (const uint32_t*)p;
@@ -482,43 +485,34 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
         }
         int32_t nk = 1; uint32_t votes = 1, e0 = 1;            // entry 0 = the draft's 3-mer, its count kept in a register
         int32_t blo = x.blk[2 * (lc >> 5)], bhi = x.blk[2 * (lc >> 5) + 1];
-        // Pass 1 (branch-free per read): count the covering reads and those that certainly vote the draft's
-        // 3-mer (no disagreement in the words holding columns lc-2..lc, >= 2 symbols cast before lc); the others
-        // are remembered in a 64-bit mask.  Pass 2 visits only those (in BAM order: first-seen order kept).
-        for (int32_t rb = blo; rb < bhi; rb += 64) {
-            const int32_t re = rb + 64 < bhi ? rb + 64 : bhi;
-            unsigned long long slow = 0;
-            for (int32_t r = rb; r < re; r++) {
-                const ReadMeta m = x.rd[r];                 // one 128-bit load
-                const int32_t i = lc - m.cs, al = m.cs & 7;
-                const bool cov = i >= 0 && i < m.cn;
-                const int32_t k0 = (i - 2 + al) >> 3, k1 = (i + al) >> 3;
-                const bool fast = i >= 2 && k1 < 32 && !(((m.mm >> (k0 & 31)) | (m.mm >> (k1 & 31))) & 1u);
-                votes += cov ? 1u : 0u;
-                e0 += (cov && fast) ? 1u : 0u;
-                slow |= (unsigned long long)((cov && !fast) ? 1u : 0u) << (r - rb);
+        for (int32_t r = blo; r < bhi; r++) {
+            const ReadMeta m = x.rd[r];                     // one 128-bit load
+            int32_t i = lc - m.cs;
+            if (i < 0 || i >= m.cn) continue;
+            int32_t al = m.cs & 7;                          // the string starts at nibble `al` of its first word
+            votes++;
+            // fast path: the read agrees with the draft in the words holding columns lc-2..lc and has cast at
+            // least two symbols before lc -> it votes the draft's own 3-mer (entry 0)
+            if (i >= 2) {
+                uint32_t mmr = m.mm;
+                int32_t k0 = (i - 2 + al) >> 3, k1 = (i + al) >> 3;
+                if (k1 < 32 && !(((mmr >> k0) | (mmr >> k1)) & 1u)) { e0++; continue; }
             }
-            while (slow) {
-                int32_t bit = 0;
-                { unsigned long long t = slow; while (!(t & 1ull)) { t >>= 1; bit++; } }
-                slow &= slow - 1;
-                const ReadMeta m = x.rd[rb + bit];
-                const int32_t i = lc - m.cs, al = m.cs & 7;
-                const uint32_t* s = x.str + m.so;
-                uint32_t kk;                                // symbols i-2..i of the read's string
-                if (i >= 2) {
-                    int32_t a = i - 2 + al;
-                    uint32_t v = fsl(s[a >> 3], (a & 7) > 5 ? s[(a >> 3) + 1] : 0u, (uint32_t)(a & 7));
-                    kk = v >> 20;
-                } else {
-                    kk = be_get(s, i + al);
-                    if (i >= 1) kk |= be_get(s, i - 1 + al) << 4;
-                }
-                if (kk == k) { e0++; continue; }
-                int32_t j = 1;
-                for (; j < nk; j++) if ((T.e(j) & 0xffffu) == kk) { T.e(j) += 1u << 16; break; }
-                if (j == nk) { if (nk < WK) T.e(nk++) = kk | (1u << 16); else T.bad() = 1; }
+            const uint32_t* s = x.str + m.so;
+            // symbols i-2..i of the read's string as one funnel-shifted extract
+            uint32_t kk;
+            if (i >= 2) {
+                int32_t a = i - 2 + al;
+                uint32_t v = fsl(s[a >> 3], (a & 7) > 5 ? s[(a >> 3) + 1] : 0u, (uint32_t)(a & 7));
+                kk = v >> 20;
+            } else {
+                kk = be_get(s, i + al);
+                if (i >= 1) kk |= be_get(s, i - 1 + al) << 4;
             }
+            if (kk == k) { e0++; continue; }
+            int32_t j = 1;
+            for (; j < nk; j++) if ((T.e(j) & 0xffffu) == kk) { T.e(j) += 1u << 16; break; }
+            if (j == nk) { if (nk < WK) T.e(nk++) = kk | (1u << 16); else T.bad() = 1; }
         }
         T.e(0) = k | (e0 << 16);
         T.nk() = (uint8_t)nk; T.votes() = (uint16_t)votes;
