@@ -121,9 +121,11 @@ __global__ void __launch_bounds__(256) k_window(npe::Dev d, npw::WinGlobals g) {
     // overlap with the copy: record offsets, clears, draft symbols
     uint32_t* ro = const_cast<uint32_t*>(x.recoff);
     for (int i = tid; i <= x.nr; i += nt) ro[i] = d.rec_off[x.rlo + i];
-    npw::ph_clear(x, tid, nt);
+    npw::Prefetch pf;
+    npw::ph_prefetch(x, tid, nt, pf);
+    npw::ph_clear(x, tid, nt, pf);
     __syncthreads();
-    npw::ph_ref(x, tid, nt, ops);
+    npw::ph_ref(x, tid, nt, ops, pf);
     NP_STAMP(0);
     if (recbytes) mbar_wait(bar, 0);
     __syncthreads();

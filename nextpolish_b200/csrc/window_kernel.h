@@ -261,7 +261,18 @@ NP_HD void put_const(uint32_t* dst, int32_t di, int32_t len, uint32_t sym) {
 }
 
 // ---- phase 0: clear + draft symbols --------------------------------------------------------------
-NP_HD void ph_clear(WCtx& x, int32_t tid, int32_t nt) {
+// Global loads of the window's colbase slice and draft bases are ISSUED first (up to PF per thread, held
+// in registers) so that their latency overlaps the shared-memory clears and the bulk copy.
+enum { PF = 4 };
+struct Prefetch { int32_t cb[PF]; uint32_t ch[PF]; };
+NP_HD void ph_prefetch(const WCtx& x, int32_t tid, int32_t nt, Prefetch& pf) {
+    for (int k = 0; k < PF; k++) {
+        int32_t i = tid + k * nt;
+        pf.cb[k] = i <= x.npos ? x.d.colbase[x.e0 + i] : 0;
+        pf.ch[k] = i < x.npos ? x.d.ctg_seq[x.e0 + i] : 0;
+    }
+}
+NP_HD void ph_clear(WCtx& x, int32_t tid, int32_t nt, const Prefetch& pf) {
     {   // the string pool is 16-byte aligned: clear it with 128-bit stores
         Quad* q4 = (Quad*)x.str; const Quad z{0u, 0u, 0u, 0u};
         for (int32_t i = tid; i < (x.strw + 4 + 3) / 4; i += nt) q4[i] = z;
@@ -269,16 +280,18 @@ NP_HD void ph_clear(WCtx& x, int32_t tid, int32_t nt) {
     for (int32_t i = tid; i < x.ncols / 8 + 3; i += nt) { x.refw[i] = 0; x.acc[2 * i] = 0; x.acc[2 * i + 1] = 0; }
     for (int32_t i = tid; i < x.ncols + 16; i += nt) x.colinfo[i] = 0;
     for (int32_t i = tid; i < x.ncols + 8; i += nt) x.tabidx[i] = -1;
-    for (int32_t i = tid; i <= x.npos; i += nt) x.lcb[i] = (uint16_t)(x.d.colbase[x.e0 + i] - x.cb0);
     for (int32_t i = tid; i < x.nblk; i += nt) { x.blk[2 * i] = 0x7fffffff; x.blk[2 * i + 1] = 0; }
     if (tid == 0) { x.ctr[0] = 0; x.ctr[1] = 0; x.ctr[2] = 0; x.ctr[3] = 0; x.ctr[4] = 0; }
+    for (int k = 0; k < PF; k++) { int32_t i = tid + k * nt; if (i <= x.npos) x.lcb[i] = (uint16_t)(pf.cb[k] - x.cb0); }
+    for (int32_t i = tid + PF * nt; i <= x.npos; i += nt) x.lcb[i] = (uint16_t)(x.d.colbase[x.e0 + i] - x.cb0);
 }
 template <class B>
-NP_HD void ph_ref(WCtx& x, int32_t tid, int32_t nt, B& be) {   // one thread per ext position
+NP_HD void ph_ref(WCtx& x, int32_t tid, int32_t nt, B& be, const Prefetch& pf) {   // one thread per ext position
     const Dev& d = x.d;
-    for (int32_t p = x.e0 + tid; p < x.e1; p += nt) {
+    int k = 0;
+    for (int32_t p = x.e0 + tid; p < x.e1; p += nt, k++) {
         int32_t lc = x.lcb[p - x.e0], n = (int32_t)x.lcb[p - x.e0 + 1] - lc;
-        uint32_t ch = d.ctg_seq[p];
+        uint32_t ch = k < PF ? pf.ch[k] : d.ctg_seq[p];
         if (ch >= 97 && ch <= 122) ch -= 32;
         be.atomic_or(&x.refw[lc >> 3], base_code(ch) << (28 - ((lc & 7) << 2)));
         for (int32_t j = 1; j < n; j++) {
@@ -330,18 +343,19 @@ NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
         int32_t i = be.atomic_add_ret(&x.ctr[4], 1);
         if (i >= x.nr) break;
         x.rd[i] = ReadMeta{0, 0, 0, 0u};
+        // filter level, usable query interval and reference span were computed per read by ReadPrep
+        // (coalesced global arrays); only the record header, CIGAR and bases come from shared memory
+        const int64_t r = (int64_t)x.rlo + i;
+        if (d.r_level[r] != 1) continue;
+        int32_t qstart = d.r_qstart[r], qend = d.r_qend[r];
+        const int32_t gpos = d.r_gpos[r], wl = d.r_wend[r] - gpos;
         const uint8_t* p = x.rec + (size_t)(x.recoff[i] - x.recoff[0]) * 16;
-        const uint32_t* hw = (const uint32_t*)p;
+        const Quad h = *(const Quad*)p;                       // one 128-bit load of the header
         Rec rc;
-        rc.pos = (int32_t)hw[0]; rc.flag = hw[1] & 0xffffu; rc.mapq = (hw[1] >> 16) & 0xffu; rc.isize = (int32_t)hw[2];
-        rc.l_qseq = (int32_t)(hw[3] & 0xffffu); rc.n_cigar = (int32_t)(hw[3] >> 16);
-        rc.cigar = hw + 4; rc.seq = p + 16 + 4 * (size_t)rc.n_cigar;
-        if (filter_level(rc, 1, d.P) != 1) continue;
-        int32_t qstart, qend;
-        cut_read(rc, d.P.trim_len_edge, &qstart, &qend);
-        int32_t gpos = x.gs + rc.pos;
+        rc.pos = (int32_t)h.a; rc.flag = h.b & 0xffffu; rc.mapq = (h.b >> 16) & 0xffu; rc.isize = (int32_t)h.c;
+        rc.l_qseq = (int32_t)(h.d & 0xffffu); rc.n_cigar = (int32_t)(h.d >> 16);
+        rc.cigar = (const uint32_t*)p + 4; rc.seq = p + 16 + 4 * (size_t)rc.n_cigar;
         // string capacity: same bound as the plan kernel
-        int32_t wl, hl; ref_spans(rc, &wl, &hl);
         int32_t a = gpos < x.e0 ? x.e0 : gpos, b = gpos + wl > x.e1 ? x.e1 : gpos + wl;
         int32_t span = b > a ? b - a : 0, extra = x.ncols - (x.e1 - x.e0);
         int32_t words = (span + extra + 14) / 8 + 2;

@@ -72,8 +72,10 @@ struct EmuBackend {
             uint32_t recbytes = (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u;
             memcpy(x.rec, d.rec + (size_t)d.rec_off[x.rlo] * 16, recbytes);                 // stands for the bulk copy
             memcpy((void*)x.recoff, d.rec_off + x.rlo, 4 * (size_t)(x.nr + 1));
-            npw::ph_clear(x, 0, 1);
-            npw::ph_ref(x, 0, 1, ops);
+            npw::Prefetch pf;
+            npw::ph_prefetch(x, 0, 1, pf);
+            npw::ph_clear(x, 0, 1, pf);
+            npw::ph_ref(x, 0, 1, ops, pf);
 #define NP_NOSTAMP(k) (void)0
             NP_WINDOW_PHASES(x, 0, 1, ops, (void)0, NP_NOSTAMP)
         }
