@@ -486,7 +486,7 @@ int32_t np_engine_run(np_engine* e, int32_t task, const Configure* cfg) {
     int err;
     if (task == NP_TASK_SCORE_CHAIN) {
         const char* v1 = getenv("NEXTPOLISH_B200_GENERAL_KERNELS");     // debugging / A-B timing only
-        if (v1 && v1[0] == '1') err = npe::run_score_chain(e->be, e->d, &e->st);
+        if (v1 && v1[0] == '1') err = npe::run_score_chain(e->be, e->d, &e->st, !npe::rate_is_dyadic(e->d.P.rate));
         else err = npe::run_score_chain_v2(e->be, e->d, e->h_ctg_off.data(), &e->st, &e->vs);
     }
     else if (task == NP_TASK_KMER_COUNT) {

@@ -193,11 +193,11 @@ struct PileupScan {   // per column: votes and draft-disagreement
 };
 
 struct NeedTable {   // table columns: disagreeing columns and their right neighbours
-    Dev d;
+    Dev d; int all = 0;   // all != 0: every column (strictly sequential chain over whole contigs)
     template <class B> NP_HD void operator()(int64_t c, B&) const {
         int32_t nd = 0;
         if (c < d.C) {
-            nd = d.mism[c];
+            nd = all ? 1 : d.mism[c];
             if (!nd && !(d.cflag[c] & CF_FIRST) && c > 0) nd = d.mism[c - 1];
         }
         d.needi[c] = nd;
@@ -349,8 +349,17 @@ namespace npe {
 
 struct RunStats { int32_t C, T; int64_t sym_words, table_entries, out_bytes; };
 
+// The anchor decomposition needs exact (order-independent) score sums: true when the indel balance
+// factor is a dyadic rational k/1024 of moderate size.  For any other user-supplied rate the chain is run
+// strictly left to right over whole contigs (every column gets a table, one thread per contig), which
+// reproduces the reference's rounding sequence exactly.
+inline bool rate_is_dyadic(double r) {
+    double s = r * 1024.0;
+    return r > -64.0 && r < 64.0 && s == (double)(long long)s;
+}
+
 template <class BE>
-int run_score_chain(BE& be, Dev& d, RunStats* st) {
+int run_score_chain(BE& be, Dev& d, RunStats* st, bool exact_sequential = false) {
     const int64_t R = d.n_reads; const int32_t G = d.G;
     d.task = 1;
     d.err = be.template buf<int32_t>("err", 1);
@@ -399,7 +408,7 @@ int run_score_chain(BE& be, Dev& d, RunStats* st) {
     d.sym = be.template buf<uint32_t>("sym", (size_t)W + 1);
     if (R > 0) be.launch("expand", R, Expand{d, 1});
     if (C > 0) be.launch("pileup_scan", C, PileupScan{d});
-    be.launch("need_table", (int64_t)C + 1, NeedTable{d});
+    be.launch("need_table", (int64_t)C + 1, NeedTable{d, exact_sequential ? 1 : 0});
     be.exscan_i32(d.needi, d.tidx, (int64_t)C + 1);
     d.T = be.read_i32(d.tidx + C);
     int32_t E = 0;

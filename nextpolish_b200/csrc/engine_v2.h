@@ -23,6 +23,7 @@ struct V2Stats { int32_t W, n_win, smem, unresolved_windows, fallback_cols; };
 // host_ctg_off: contig offsets on the host (n_ctg + 1 entries)
 template <class BE>
 int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st, V2Stats* vs) {
+    if (!rate_is_dyadic(d.P.rate)) return run_score_chain(be, d, st, true);   // see rate_is_dyadic
     const int64_t R = d.n_reads; const int32_t G = d.G;
     d.task = 1;
     d.err = be.template buf<int32_t>("err", 1);

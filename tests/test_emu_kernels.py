@@ -114,3 +114,18 @@ def test_emulated_kernels_fuzz_both_tasks(E, oracle, emu, seed):
     for task in (1, 2):
         want = run_checker(oracle.np_oracle_run, sh, task, cfg)
         assert run_checker(emu.np_emu_run, sh, task, cfg, (None,)) == want, (task, kw)
+
+
+@pytest.mark.parametrize("rate", [0.33, 0.7, 0.1])
+def test_emulated_non_dyadic_rate_uses_sequential_chain(E, oracle, emu, rate):
+    """-indel_balance_factor_sgs values that are not k/1024: score sums are not exact, so the engine runs the
+    chain strictly left to right over whole contigs and must still match the oracle bit for bit."""
+    emu.np_emu_run_impl.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    emu.np_emu_run_impl.restype = C.c_int
+    sh = E.Shard.synthetic(E.synth_params(seed=91, n_contigs=3, contig_len=30000, depth=40.0, draft_indel=0.01, read_sub=0.01), 0, 3)
+    cfg = E.default_config(b"")
+    cfg.contents.indel_balance_factor_sgs = rate
+    want = run_checker(oracle.np_oracle_run, sh, 1, cfg)
+    stats = (C.c_int32 * 8)()
+    assert run_checker(emu.np_emu_run_impl, sh, 1, cfg, (C.cast(stats, C.c_void_p), 2)) == want
+    assert stats[1] == stats[0]          # every column went through the tables

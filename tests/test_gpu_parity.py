@@ -229,3 +229,14 @@ def test_pipelined_host_call_equals_resident_path(E, eng):
             del os.environ["NEXTPOLISH_B200_PIPELINE"]
         raw = out.tobytes()
         assert {n: raw[off[i]:off[i + 1]] for i, n in enumerate(sh.names)} == want, task
+
+
+@pytest.mark.parametrize("rate", [0.33, 0.7])
+def test_gpu_non_dyadic_rate(E, oracle, eng, rate):
+    sh = E.Shard.synthetic(E.synth_params(seed=92, n_contigs=3, contig_len=60000, depth=40.0, draft_indel=0.01, read_sub=0.01,
+                                          lowercase_frac=0.01), 0, 3, with_qual=2)
+    cfg = E.default_config(b"")
+    cfg.contents.read_tlen = 1750
+    cfg.contents.indel_balance_factor_sgs = rate
+    for task in tasks(E):
+        assert eng.polish(sh, task, cfg) == run_checker(oracle.np_oracle_run, sh, task, cfg), task

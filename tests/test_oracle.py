@@ -89,7 +89,7 @@ def test_oracle_vs_reference_so_with_mutated_thresholds(E, oracle, tmp_path, see
     assert (cfg.contents.read_tlen, cfg.contents.read_len) == (rcfg.contents.read_tlen, rcfg.contents.read_len)
     vals = dict(trim_len_edge=rng.choice([1, 2, 4]), ext_len_edge=rng.choice([1, 2, 3]), min_len_ldr=rng.choice([1, 3, 6]),
                 min_len_inter_kmer=rng.choice([0, 2, 5, 9]), max_len_kmer=rng.choice([10, 50, 120]), max_count_kmer=rng.choice([3, 50]),
-                min_map_quality=rng.choice([0, 30]), indel_balance_factor_sgs=rng.choice([0.5, 0.25, 0.75]),
+                min_map_quality=rng.choice([0, 30]), indel_balance_factor_sgs=rng.choice([0.5, 0.25, 0.75, 0.33, 0.7]),
                 min_count_ratio_skip=rng.choice([0.8, 0.6, 0.95]))
     for k, v in vals.items():
         setattr(cfg.contents, k, v)
