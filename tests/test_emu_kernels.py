@@ -129,3 +129,20 @@ def test_emulated_non_dyadic_rate_uses_sequential_chain(E, oracle, emu, rate):
     stats = (C.c_int32 * 8)()
     assert run_checker(emu.np_emu_run_impl, sh, 1, cfg, (C.cast(stats, C.c_void_p), 2)) == want
     assert stats[1] == stats[0]          # every column went through the tables
+
+
+@pytest.mark.parametrize("kw", [
+    dict(seed=5, n_contigs=3, contig_len=2000, depth=0.0),                       # no reads at all
+    dict(seed=6, n_contigs=4, contig_len=0, min_len=40, max_len=160, depth=30.0),  # contigs shorter than a read
+    dict(seed=7, n_contigs=1, contig_len=1, depth=0.0),                           # single-base contig
+    dict(seed=8, n_contigs=2, contig_len=700, depth=400.0),                       # very deep, tiny
+], ids=["noreads", "tiny_contigs", "one_base", "deep_tiny"])
+def test_emulated_edge_shapes(E, oracle, emu, kw):
+    emu.np_emu_run_impl.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    emu.np_emu_run_impl.restype = C.c_int
+    sh = E.Shard.synthetic(E.synth_params(lowercase_frac=0.05, **kw), 0, kw["n_contigs"], with_qual=True)
+    cfg = E.default_config(b"")
+    for task in (1, 2):
+        want = run_checker(oracle.np_oracle_run, sh, task, cfg)
+        assert run_checker(emu.np_emu_run, sh, task, cfg, (None,)) == want, task
+    assert run_checker(emu.np_emu_run_impl, sh, 1, cfg, (None, 2)) == run_checker(oracle.np_oracle_run, sh, 1, cfg)

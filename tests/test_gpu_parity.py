@@ -240,3 +240,17 @@ def test_gpu_non_dyadic_rate(E, oracle, eng, rate):
     cfg.contents.indel_balance_factor_sgs = rate
     for task in tasks(E):
         assert eng.polish(sh, task, cfg) == run_checker(oracle.np_oracle_run, sh, task, cfg), task
+
+
+@pytest.mark.parametrize("kw", [
+    dict(seed=5, n_contigs=3, contig_len=2000, depth=0.0),
+    dict(seed=6, n_contigs=4, contig_len=0, min_len=40, max_len=160, depth=30.0),
+    dict(seed=7, n_contigs=1, contig_len=1, depth=0.0),
+    dict(seed=8, n_contigs=2, contig_len=700, depth=400.0),
+    dict(seed=9, n_contigs=300, contig_len=0, min_len=200, max_len=6000, depth=20.0),
+], ids=["noreads", "tiny_contigs", "one_base", "deep_tiny", "many_contigs"])
+def test_gpu_edge_shapes(E, oracle, eng, kw):
+    sh = E.Shard.synthetic(E.synth_params(lowercase_frac=0.05, **kw), 0, kw["n_contigs"], with_qual=True)
+    cfg = E.default_config(b"")
+    for task in tasks(E):
+        assert eng.polish(sh, task, cfg) == run_checker(oracle.np_oracle_run, sh, task, cfg), task
