@@ -53,6 +53,48 @@ struct CudaOps {
         (void)p; (void)v; return 0;
 #endif
     }
+    __host__ __device__ __forceinline__ uint32_t atomic_cas_u32(uint32_t* p, uint32_t cmp, uint32_t v) {
+#ifdef __CUDA_ARCH__
+        return atomicCAS(p, cmp, v);
+#else
+        (void)p; (void)cmp; (void)v; return 0;
+#endif
+    }
+    __host__ __device__ __forceinline__ void atomic_add_u32(uint32_t* p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+        atomicAdd(p, v);
+#else
+        (void)p; (void)v;
+#endif
+    }
+    __host__ __device__ __forceinline__ void atomic_min_u32(uint32_t* p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+        atomicMin(p, v);
+#else
+        (void)p; (void)v;
+#endif
+    }
+    // exclusive prefix sum of one value per thread over the CTA (every thread calls it; contains barriers)
+    __host__ __device__ __forceinline__ int32_t block_exscan(int32_t v, int32_t* scratch) {
+#ifdef __CUDA_ARCH__
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        int32_t inc = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) scratch[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int32_t w = lane < nw ? scratch[lane] : 0, wi = w;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            if (lane < nw) scratch[lane] = wi - w;
+        }
+        __syncthreads();
+        return inc - v + scratch[wid];
+#else
+        (void)scratch; (void)v; return 0;
+#endif
+    }
     __host__ __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) {
 #ifdef __CUDA_ARCH__
         atomicOr(p, v);
@@ -288,7 +330,7 @@ struct CudaBackend {
             unsigned long long h[16];
             CUDA_TRY(cudaMemcpyAsync(h, gg.phase_cycles, sizeof(h), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
-            fprintf(stderr, "k_window phase cycles per CTA (thread 0): clear+ref %llu, wait-stage %llu, expand %llu, colinfo+mark %llu, tally %llu, chain+anchors %llu, finish %llu\n",
+            fprintf(stderr, "k_window phase cycles per CTA (thread 0): clear+ref %llu, wait-stage %llu, compare %llu, scan+mark %llu, votes+tally %llu, chain+anchors %llu, finish %llu\n",
                     h[0] / g.n_win, h[1] / g.n_win, h[2] / g.n_win, h[3] / g.n_win, h[4] / g.n_win, h[5] / g.n_win, h[6] / g.n_win);
         }
         CUDA_TRY(cudaGetLastError());

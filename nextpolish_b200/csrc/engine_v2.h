@@ -10,9 +10,10 @@ namespace npe {
 // One window, all phases, for a backend-provided "thread range" (tid, nt) and barrier.
 // CUDA: tid = threadIdx.x, nt = blockDim.x, barrier = __syncthreads; emu: tid = 0, nt = 1, no-op.
 #define NP_WINDOW_PHASES(x, tid, nt, ops, BARRIER, STAMP)          \
-    npw::ph_expand(x, tid, nt, ops);      BARRIER; STAMP(2);        \
-    npw::ph_colinfo(x, tid, nt);          BARRIER;                  \
+    npw::ph_compare(x, tid, nt, ops);     BARRIER; STAMP(2);        \
+    npw::ph_scan(x, tid, nt, ops);        BARRIER;                  \
     npw::ph_mark_tables(x, tid, nt, ops); BARRIER; STAMP(3);        \
+    npw::ph_votes(x, tid, nt, ops);       BARRIER;                  \
     npw::ph_tally(x, tid, nt);            BARRIER; STAMP(4);        \
     npw::ph_chain(x, tid, nt);            /* disjoint columns: */   \
     npw::ph_anchors(x, tid, nt);          BARRIER; STAMP(5);        \
@@ -74,7 +75,6 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
         g.win_p0 = be.upload_i32("w_p0", hw_p0.data(), hw_p0.size());
         g.win_rlo = be.template buf<int32_t>("w_rlo", (size_t)g.n_win + 1);
         g.win_rhi = be.template buf<int32_t>("w_rhi", (size_t)g.n_win + 1);
-        g.win_strw = be.template buf<int32_t>("w_strw", (size_t)g.n_win + 1);
         g.win_need = be.template buf<int32_t>("w_need", (size_t)g.n_win + 1);
         be.zero(g.maxneed, 2 * sizeof(int32_t));
         if (g.n_win > 0) be.launch("win_plan", g.n_win, npw::WinPlan{d, g});

@@ -7,14 +7,18 @@
 //   stage    the contiguous byte range of the packed records of every read overlapping [e0,e1)
 //            is copied into shared memory with ONE bulk copy (cp.async.bulk / TMA, mbarrier
 //            completion), together with their rec_off entries;
-//   expand   one thread per read: filter level, contig_cut_read, CIGAR walk at op granularity;
-//            the read's column string (4-bit symbols, big-endian nibble order inside 32-bit words)
-//            is written to shared memory with word-parallel nibble copies (contig.c:247-358);
-//   compare  fused into expand: strings are stored aligned to the draft's 8-column symbol words, so each
-//            string word is XORed against one draft word -> per column "covered" / "some read disagrees"
-//            (OR-ed into two shared-memory accumulators per word);
-//   tally    one thread per table column (disagreeing columns + right neighbours): 3-mer tallies in
-//            first-seen (BAM) order from the shared-memory strings (base.c:60-71);
+//   compare  one thread per read: CIGAR walk at op granularity (contig.c:247-358); the read's column
+//            string (4-bit symbols) is never materialised: it is produced 8 symbols at a time, aligned
+//            to the draft's 8-column symbol words, and XORed against them.  A read leaves behind only
+//            (a) +1/-1 at the ends of its (contiguous) voted column range, (b) a flag on every column
+//            where it disagrees with the draft and (c) one EVENT (column, read index, 3-mer) for every
+//            column within two columns after a disagreement — the only columns where its 3-mer can
+//            differ from the draft's — plus its first two symbols (partial 3-mers of a read start);
+//   scan     block-wide prefix sum of (a): reads voting on every column (votes = 1 + that);
+//   tally    one thread per event: find-or-insert of the 3-mer in the table of its column (columns that
+//            disagree + right neighbours) with shared-memory atomics, carrying the smallest read index
+//            per entry; one thread per table then orders the entries by that index = first-seen (BAM)
+//            order (base.c:60-71); the draft's own 3-mer gets all remaining votes;
 //   chain    one thread per stretch that starts in the owned range: score chain + backtrack
 //            (contig.c:424-496), result bases/flags written for every column of the stretch;
 //   anchors  owned columns outside stretches keep the draft symbol.
@@ -38,7 +42,7 @@ enum { WK = 8,            // table capacity per column (distinct 3-mers) handled
 struct WinGlobals {       // extra global arrays of the fused path
     int32_t W, n_win;
     const int32_t *win_ctg, *win_p0;          // [n_win]
-    int32_t *win_rlo, *win_rhi, *win_strw, *win_need;   // [n_win] plan: staged reads, string words, smem bytes
+    int32_t *win_rlo, *win_rhi, *win_need;    // [n_win] plan: staged reads, smem bytes
     int32_t* maxneed;                         // [1]
     uint8_t* r_need;                          // [n_reads] reads the fallback path must expand
     int32_t* n_unresolved;                    // [1]
@@ -46,11 +50,12 @@ struct WinGlobals {       // extra global arrays of the fused path
 };
 
 // Table columns live in a structure-of-arrays pool (entry-major) so that the threads of a warp, which
-// work on consecutive tables, touch consecutive shared-memory words (no bank conflicts in the tally).
+// work on consecutive tables, touch consecutive shared-memory words.
 enum { TAB_BYTES = 128 };  // pool bytes per table column (8*8 scores + 8*4 k-mers + 8*2 + 8 + 2 + 4, rounded)
 struct TabPool {
-    double*   sc;          // [WK][tmax] score per score entry (chain phase)
-    uint32_t* e;           // [WK][tmax] kmer | count << 16, first-seen order
+    double*   sc;          // [WK][tmax] score per score entry (chain phase); the tally phase keeps the
+                           //            smallest read index per k-mer entry in the same bytes (uint32 [WK][tmax])
+    uint32_t* e;           // [WK][tmax] kmer | count << 16; entry 0 = the draft's 3-mer, then first-seen order
     uint16_t* ekmer;       // [WK][tmax] winning k-mer per score entry
     uint16_t* votes;       // [tmax]
     uint8_t*  ebase;       // [WK][tmax] base code per score entry, first-seen order
@@ -60,6 +65,7 @@ struct TabPool {
 struct TabEntry {          // accessor of one table column
     const TabPool* p; int32_t t;
     NP_HD double&   sc(int j) const { return p->sc[j * p->tmax + t]; }
+    NP_HD uint32_t& fs(int j) const { return ((uint32_t*)p->sc)[j * p->tmax + t]; }
     NP_HD uint32_t& e(int j) const { return p->e[j * p->tmax + t]; }
     NP_HD uint16_t& ekmer(int j) const { return p->ekmer[j * p->tmax + t]; }
     NP_HD uint8_t&  ebase(int j) const { return p->ebase[j * p->tmax + t]; }
@@ -71,12 +77,17 @@ struct TabEntry {          // accessor of one table column
 };
 
 struct alignas(16) Quad { uint32_t a, b, c, d; };
-struct alignas(16) ReadMeta {
-    int32_t cs;            // local column of the first stored symbol
-    int32_t cn;            // stored symbols
-    int32_t so;            // word offset of the string in the pool
-    uint32_t mm;           // bit k set = the k-th string word disagrees with the draft somewhere
+struct alignas(8) ReadStart {
+    int32_t cs;            // local column of the read's first stored symbol, -1: the read casts nothing here
+    uint32_t info;         // sym0 << 4 | sym1 | min(stored symbols, 2) << 8
 };
+
+enum { RUNCAP = 8 };      // runs per read kept in shared memory (longer lists continue with the generator)
+#ifndef __CUDACC__
+struct uint2 { unsigned int x, y; };
+#endif
+enum { CTR_EVENTS = 0, CTR_TABLES = 1, CTR_ERROR = 2, CTR_UNRESOLVED = 3, CTR_TICKET = 4, N_CTR = 6,
+       SCAN_SCRATCH_BYTES = 160 };
 
 struct WCtx {             // per-window context: globals + carved shared memory
     Dev d; WinGlobals g;
@@ -84,34 +95,41 @@ struct WCtx {             // per-window context: globals + carved shared memory
     int32_t cb0, ncols, cown0, cown1;         // first ext column, #ext columns, owned local range [cown0,cown1)
     int32_t chr_end;                          // local column bound that a prev-window stretch may reach (HR rule)
     int32_t lc_first, lc_last;                // local columns of the contig's first / last column
-    int32_t npos, nblk;                       // ext positions, 32-column blocks
+    int32_t npos;                             // ext positions
     int32_t rlo, nr;                          // staged reads [rlo, rlo+nr)
-    int32_t strw, tmax;                       // string pool words, table pool entries
+    int32_t evcap, tmax;                      // event list capacity, table pool entries
     // shared memory
     uint8_t* rec; const uint32_t* recoff;     // staged records and their offsets (16-byte units, global)
-    ReadMeta* rd;                             // per read: one 16-byte record (a single 128-bit shared-memory load)
-    uint32_t *str, *refw, *acc;               // string pool, draft symbol words, compare accumulators
-    uint8_t* colinfo;                         // per local column: 1 mism, 2 covered, 8 sub-column
+    ReadStart* rs;                            // per read
+    Quad* ev;                                 // parked chunks (see ph_compare)
+    uint2* runs;                              // [nr][RUNCAP] pre-walked runs: .x = lc | len << 16, .y = first query index or -1
+    uint32_t* refw;                           // draft symbol words (8 columns per word, big-endian nibbles)
+    uint32_t* acc;                            // same layout: bit 0 of a nibble set = some read disagrees at that column
+    int32_t* cov;                             // [ncols+1] +1/-1 at string ends, then (scan) reads voting on each column
+    uint8_t* colinfo;                         // per local column: 1 mism, 2 covered
     int16_t* tabidx;                          // per local column: table index or -1
     int16_t* tabcol;                          // dense list: table index -> local column
     uint16_t* lcb;                            // [npos+1] local column of every ext position (staged colbase)
-    int32_t* blk;                             // [2*nblk] first / last+1 staged read overlapping each 32-column block
-    TabPool tab;                              // aliases the record area (records are dead after expand)
-    int32_t* ctr;                             // [0] string words used, [1] tables used, [2] internal error, [3] unresolved
+    TabPool tab;                              // aliases the record area (records are dead after the compare phase)
+    int32_t* ctr;                             // counters (CTR_*)
+    int32_t* scan_scratch;                    // block scan scratch
 };
 
 NP_HD uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+NP_HD int32_t win_evcap(int32_t nr) { int32_t c = 4 * nr; return c < 512 ? 512 : c; }   // parked chunks per window
 // shared-memory bytes of a window with nr reads, recbytes of records, ncols ext columns
-NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int32_t strw, int32_t npos) {
-    uint32_t b = 64;                                   // mbarrier + counters
+NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int32_t npos) {
+    uint32_t b = 64 + SCAN_SCRATCH_BYTES;              // mbarrier + counters, scan scratch
     uint32_t recarea = align16(recbytes);              // later re-used as the table pool
     uint32_t mintab = (uint32_t)(ncols / 4 + 16) * (uint32_t)TAB_BYTES   /* ~13 % of columns need a table at 30x; 2x headroom */;
     if (recarea < mintab) recarea = mintab;
     b += recarea + align16(4u * (uint32_t)(nr + 1));
-    b += align16(2u * (uint32_t)(npos + 2)) + align16(8u * (uint32_t)(ncols / 32 + 2));
-    b += 16u * (uint32_t)nr;
-    b += align16(4u * (uint32_t)(strw + 4));
-    b += 3 * align16(4u * (uint32_t)(ncols / 8 + 3));
+    b += align16(2u * (uint32_t)(npos + 2));
+    b += align16(8u * (uint32_t)(nr + 1));
+    b += 16u * (uint32_t)win_evcap(nr);
+    b += 8u * (uint32_t)RUNCAP * (uint32_t)(nr + 1);
+    b += 2 * align16(4u * (uint32_t)(ncols / 8 + 3));
+    b += align16(4u * (uint32_t)(ncols + 2));
     b += align16((uint32_t)ncols + 16);
     b += align16(2u * (uint32_t)(ncols + 8)) + align16(2u * (uint32_t)(ncols / 2 + 16));   // tabidx, tabcol
     return b;
@@ -131,16 +149,9 @@ struct WinPlan {
         if (lo < r0) lo = r0;
         if (lo > hi) lo = hi;
         int32_t ncols = d.colbase[e1] - d.colbase[e0];
-        int32_t extra = ncols - (e1 - e0);                           // insertion sub-columns in range
-        int32_t strw = 0;
-        for (int64_t r = lo; r < hi; r++) {
-            int32_t a = d.r_gpos[r] < e0 ? e0 : d.r_gpos[r], b = d.r_wend[r] > e1 ? e1 : d.r_wend[r];
-            int32_t span = b > a ? b - a : 0;
-            strw += (span + extra + 14) / 8 + 2;
-        }
         uint32_t recbytes = (d.rec_off[hi] - d.rec_off[lo]) * 16u;
-        g.win_rlo[w] = (int32_t)lo; g.win_rhi[w] = (int32_t)hi; g.win_strw[w] = strw;
-        uint32_t need = win_smem_bytes((int32_t)(hi - lo), recbytes, ncols, strw, e1 - e0);
+        g.win_rlo[w] = (int32_t)lo; g.win_rhi[w] = (int32_t)hi;
+        uint32_t need = win_smem_bytes((int32_t)(hi - lo), recbytes, ncols, e1 - e0);
         g.win_need[w] = (int32_t)need;
         be.atomic_max(g.maxneed, (int32_t)need);
     }
@@ -160,16 +171,17 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
     int32_t pe = x.p0 + HR > x.ge + 1 ? x.ge + 1 : x.p0 + HR;
     x.chr_end = d.colbase[pe] - x.cb0;
     x.lc_first = d.colbase[x.gs] - x.cb0; x.lc_last = d.colbase[x.ge] - x.cb0;
-    x.npos = x.e1 - x.e0; x.nblk = x.ncols / 32 + 1;
+    x.npos = x.e1 - x.e0;
     x.rlo = x.g.win_rlo[w]; x.nr = x.g.win_rhi[w] - x.rlo;
-    x.strw = x.g.win_strw[w];
+    x.evcap = win_evcap(x.nr);
     uint32_t recbytes = (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u;
     uint32_t recarea = align16(recbytes), mintab = (uint32_t)(x.ncols / 4 + 16) * (uint32_t)TAB_BYTES;
     if (recarea < mintab) recarea = mintab;
     x.tmax = (int32_t)(recarea / TAB_BYTES) & ~7;      // multiple of 8 keeps every array 8-byte aligned
     if (x.tmax > ((x.ncols / 2 + 8) & ~7)) x.tmax = (x.ncols / 2 + 8) & ~7;   // the dense list (tabcol) holds ncols/2+16 entries
-    uint8_t* p = smem + 64;
     x.ctr = (int32_t*)(smem + 16);
+    x.scan_scratch = (int32_t*)(smem + 64);
+    uint8_t* p = smem + 64 + SCAN_SCRATCH_BYTES;
     x.rec = p;
     {   // table pool carved from the same bytes
         uint8_t* q = p; size_t tm = (size_t)x.tmax;
@@ -184,18 +196,19 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
     p += recarea;
     x.recoff = (const uint32_t*)p; p += align16(4u * (uint32_t)(x.nr + 1));
     x.lcb = (uint16_t*)p; p += align16(2u * (uint32_t)(x.npos + 2));
-    x.blk = (int32_t*)p; p += align16(8u * (uint32_t)(x.ncols / 32 + 2));
-    x.rd = (ReadMeta*)p; p += 16u * (uint32_t)x.nr;
-    x.str = (uint32_t*)p; p += align16(4u * (uint32_t)(x.strw + 4));
+    x.rs = (ReadStart*)p; p += align16(8u * (uint32_t)(x.nr + 1));
+    x.ev = (Quad*)p; p += 16u * (uint32_t)x.evcap;
+    x.runs = (uint2*)p; p += 8u * (uint32_t)RUNCAP * (uint32_t)(x.nr + 1);
     x.refw = (uint32_t*)p; p += align16(4u * (uint32_t)(x.ncols / 8 + 3));
-    x.acc = (uint32_t*)p; p += 2 * align16(4u * (uint32_t)(x.ncols / 8 + 3));
+    x.acc = (uint32_t*)p; p += align16(4u * (uint32_t)(x.ncols / 8 + 3));
+    x.cov = (int32_t*)p; p += align16(4u * (uint32_t)(x.ncols + 2));
     x.colinfo = p; p += align16((uint32_t)x.ncols + 16);
     x.tabidx = (int16_t*)p; p += align16(2u * (uint32_t)(x.ncols + 8));
     x.tabcol = (int16_t*)p;
 }
 
-// ---- big-endian nibble strings -------------------------------------------------------------------
-// nibble i of a string lives in word i>>3 at bits [28-4*(i&7), +4)
+// ---- big-endian nibble words ---------------------------------------------------------------------
+// nibble i of a symbol array lives in word i>>3 at bits [28-4*(i&7), +4)
 NP_HD uint32_t be_get(const uint32_t* w, int32_t i) { return (w[i >> 3] >> (28 - ((i & 7) << 2))) & 0xfu; }
 NP_HD uint32_t bswap32(uint32_t v) {
 #ifdef __CUDA_ARCH__
@@ -211,54 +224,6 @@ NP_HD uint32_t fsl(uint32_t hi, uint32_t lo, uint32_t nib) {   // 8 nibbles star
     return nib == 0 ? hi : (hi << (nib * 4)) | (lo >> (32 - nib * 4));
 #endif
 }
-// mask with nibbles [a, b) set (0 <= a <= b <= 8), nibble 0 = top
-NP_HD uint32_t nib_mask(int32_t a, int32_t b) {
-    a = a < 0 ? 0 : (a > 8 ? 8 : a);
-    b = b < 0 ? 0 : (b > 8 ? 8 : b);
-    uint32_t hi = (uint32_t)(0xffffffffull >> (a * 4));         // nibbles a..7
-    uint32_t lo = (uint32_t)(0xffffffffull >> (b * 4));         // nibbles b..7
-    return hi & ~lo;
-}
-// copy `len` nibbles of BAM seq (bytes, high nibble first == big-endian nibble order) starting at
-// query index q into dst string at nibble index di
-NP_HD void put_seq(uint32_t* dst, int32_t di, const uint8_t* seq, int32_t q, int32_t len) {
-    const uint32_t* sw = (const uint32_t*)seq;   // seq is 4-byte aligned inside a record
-    int32_t dn = di & 7;
-    if (dn) {                                    // head: finish the partially filled destination word
-        int32_t take = 8 - dn < len ? 8 - dn : len;
-        int32_t si = q >> 3, sn = q & 7;
-        uint32_t hi = bswap32(sw[si]), lo = (sn + take > 8) ? bswap32(sw[si + 1]) : 0u;
-        uint32_t v = fsl(hi, lo, (uint32_t)sn) >> (dn * 4);
-        uint32_t m = nib_mask(dn, dn + take);
-        dst[di >> 3] = (dst[di >> 3] & ~m) | (v & m);
-        di += take; q += take; len -= take;
-    }
-    int32_t dw = di >> 3, si = q >> 3;
-    uint32_t sn = (uint32_t)(q & 7);
-    if (len >= 8) {                              // body: whole destination words, one source load each
-        uint32_t cur = bswap32(sw[si]);
-        if (sn == 0) {
-            for (;;) { dst[dw++] = cur; len -= 8; si++; if (len < 8) break; cur = bswap32(sw[si]); }
-        } else {
-            do { uint32_t nxt = bswap32(sw[si + 1]); dst[dw++] = fsl(cur, nxt, sn); cur = nxt; si++; len -= 8; } while (len >= 8);
-        }
-    }
-    if (len > 0) {                               // tail
-        uint32_t hi = bswap32(sw[si]), lo = (sn + (uint32_t)len > 8u) ? bswap32(sw[si + 1]) : 0u;
-        uint32_t m = nib_mask(0, len);
-        dst[dw] = (dst[dw] & ~m) | (fsl(hi, lo, sn) & m);
-    }
-}
-NP_HD void put_const(uint32_t* dst, int32_t di, int32_t len, uint32_t sym) {
-    uint32_t pat = sym * 0x11111111u;
-    while (len > 0) {
-        int32_t dw = di >> 3, dn = di & 7;
-        int32_t take = 8 - dn < len ? 8 - dn : len;
-        uint32_t m = nib_mask(dn, dn + take);
-        dst[dw] = (dst[dw] & ~m) | (pat & m);
-        di += take; len -= take;
-    }
-}
 
 // ---- phase 0: clear + draft symbols --------------------------------------------------------------
 // Global loads of the window's colbase slice and draft bases are ISSUED first (up to PF per thread, held
@@ -273,15 +238,10 @@ NP_HD void ph_prefetch(const WCtx& x, int32_t tid, int32_t nt, Prefetch& pf) {
     }
 }
 NP_HD void ph_clear(WCtx& x, int32_t tid, int32_t nt, const Prefetch& pf) {
-    {   // the string pool is 16-byte aligned: clear it with 128-bit stores
-        Quad* q4 = (Quad*)x.str; const Quad z{0u, 0u, 0u, 0u};
-        for (int32_t i = tid; i < (x.strw + 4 + 3) / 4; i += nt) q4[i] = z;
-    }
-    for (int32_t i = tid; i < x.ncols / 8 + 3; i += nt) { x.refw[i] = 0; x.acc[2 * i] = 0; x.acc[2 * i + 1] = 0; }
-    for (int32_t i = tid; i < x.ncols + 16; i += nt) x.colinfo[i] = 0;
+    for (int32_t i = tid; i < x.ncols / 8 + 3; i += nt) { x.refw[i] = 0; x.acc[i] = 0; }
+    for (int32_t i = tid; i < x.ncols + 2; i += nt) x.cov[i] = 0;
     for (int32_t i = tid; i < x.ncols + 8; i += nt) x.tabidx[i] = -1;
-    for (int32_t i = tid; i < x.nblk; i += nt) { x.blk[2 * i] = 0x7fffffff; x.blk[2 * i + 1] = 0; }
-    if (tid == 0) { x.ctr[0] = 0; x.ctr[1] = 0; x.ctr[2] = 0; x.ctr[3] = 0; x.ctr[4] = 0; }
+    if (tid == 0) for (int k = 0; k < N_CTR; k++) x.ctr[k] = 0;
     for (int k = 0; k < PF; k++) { int32_t i = tid + k * nt; if (i <= x.npos) x.lcb[i] = (uint16_t)(pf.cb[k] - x.cb0); }
     for (int32_t i = tid + PF * nt; i <= x.npos; i += nt) x.lcb[i] = (uint16_t)(x.d.colbase[x.e0 + i] - x.cb0);
 }
@@ -297,171 +257,240 @@ NP_HD void ph_ref(WCtx& x, int32_t tid, int32_t nt, B& be, const Prefetch& pf) {
         for (int32_t j = 1; j < n; j++) {
             int32_t c = lc + j;
             be.atomic_or(&x.refw[c >> 3], (uint32_t)SYM_GAP << (28 - ((c & 7) << 2)));
-            x.colinfo[c] = 8;
         }
     }
 }
 
-// ---- phase 1: expand one read into its column string ----------------------------------------------
+// ---- phase 1: compare one read's column string against the draft ------------------------------------
 // Emits the symbols of contig_parse_read (contig.c:247-331) at CIGAR-op granularity; only columns
-// inside the extended range are stored.
+// inside the extended range are looked at.
 NP_HD int32_t lcol(const WCtx& x, int32_t p) {     // local column of position p; virtual outside the range
     int32_t i = p - x.e0;
     if (i < 0) return i;
     if (i > x.npos) return (int32_t)x.lcb[x.npos] + (i - x.npos);
     return (int32_t)x.lcb[i];
 }
-struct StrWriter {
-    WCtx* x; uint32_t* w; int32_t cap;        // string words of this read, capacity in nibbles
-    int32_t cs, n;                            // local column of the first stored symbol, stored count
-    int32_t next;                             // next expected local column (contiguity)
-    bool started;
-    const uint8_t* seq;
-    // a run of `len` columns starting at local column lc: from seq[q..] (q >= 0) or constant gaps
-    NP_HD void run(int32_t lc, int32_t len, int32_t q) {
-        if (len <= 0) return;
-        if (started && lc != next) x->ctr[2] = 1;         // cannot happen (votes are contiguous)
-        next = lc + len; started = true;
-        int32_t skip = lc < 0 ? -lc : 0;                  // clip to the extended range
-        if (skip >= len) return;
-        lc += skip; len -= skip; if (q >= 0) q += skip;
-        if (lc + len > x->ncols) len = x->ncols - lc;
-        if (len <= 0) return;
-        if (n == 0) cs = lc;
-        int32_t di = lc - (cs & ~7);                      // strings are aligned to 8-column words of the window
-        if (lc != cs + n || di + len > cap) { x->ctr[2] = 1; return; }
-        if (q >= 0) put_seq(w, di, seq, q, len); else put_const(w, di, len, SYM_GAP);
-        n += len;
-    }
+// The CIGAR walk is a resumable generator of RUNS (a run = consecutive local columns that take their symbols
+// either from consecutive read bases or from the gap symbol), so that the compare loop below is ONE loop over
+// 8-column chunks shared by all lanes of a warp, whatever CIGAR op each lane is in.
+struct Walk {
+    const uint32_t* cigar; int32_t n_cigar, ci;
+    int32_t pos, qpos, qstart, qend; int last;
+    int32_t mj, mjb, mlen; bool in_m;         // M op in progress: next base index, last in-range index, op length
+    int32_t plc, plen, pq;                    // pending second run of the current op (plen > 0)
+    int32_t next; bool started, done;         // contiguity check, walk finished
 };
-
+NP_HD void walk_op_done(const WCtx& x, Walk& w) {
+    w.ci++;
+    if (w.pos > x.ge || w.pos > x.e1 + 1) w.done = true;
+}
 template <class B>
-NP_HD void ph_expand(WCtx& x, int32_t tid, int32_t nt, B& be) {
-    const Dev& d = x.d;
-    (void)tid; (void)nt;
-    for (;;) {                                            // reads are handed out dynamically: no straggler round
-        int32_t i = be.atomic_add_ret(&x.ctr[4], 1);
-        if (i >= x.nr) break;
-        x.rd[i] = ReadMeta{0, 0, 0, 0u};
-        // filter level, usable query interval and reference span were computed per read by ReadPrep
-        // (coalesced global arrays); only the record header, CIGAR and bases come from shared memory
-        const int64_t r = (int64_t)x.rlo + i;
-        if (d.r_level[r] != 1) continue;
-        int32_t qstart = d.r_qstart[r], qend = d.r_qend[r];
-        const int32_t gpos = d.r_gpos[r], wl = d.r_wend[r] - gpos;
-        const uint8_t* p = x.rec + (size_t)(x.recoff[i] - x.recoff[0]) * 16;
-        const Quad h = *(const Quad*)p;                       // one 128-bit load of the header
-        Rec rc;
-        rc.pos = (int32_t)h.a; rc.flag = h.b & 0xffffu; rc.mapq = (h.b >> 16) & 0xffu; rc.isize = (int32_t)h.c;
-        rc.l_qseq = (int32_t)(h.d & 0xffffu); rc.n_cigar = (int32_t)(h.d >> 16);
-        rc.cigar = (const uint32_t*)p + 4; rc.seq = p + 16 + 4 * (size_t)rc.n_cigar;
-        // string capacity: same bound as the plan kernel
-        int32_t a = gpos < x.e0 ? x.e0 : gpos, b = gpos + wl > x.e1 ? x.e1 : gpos + wl;
-        int32_t span = b > a ? b - a : 0, extra = x.ncols - (x.e1 - x.e0);
-        int32_t words = (span + extra + 14) / 8 + 2;
-        int32_t off = be.atomic_add_ret(&x.ctr[0], words);
-        if (off + words > x.strw + 4) { x.ctr[2] = 1; continue; }
-        StrWriter sw{&x, x.str + off, (words - 1) * 8, 0, 0, 0, false, rc.seq};
-        const int32_t start = x.gs, end = x.ge;
-        int32_t pos = gpos, qpos = 0;
-        int last = OP_I;
-        for (int ci = 0; ci < rc.n_cigar; ci++) {
-            int32_t len = cig_len(rc.cigar[ci]); int cur = cig_op(rc.cigar[ci]);
+NP_HD bool next_run(WCtx& x, Walk& w, int32_t& lc, int32_t& len, int32_t& q, B& be) {
+    (void)be;
+    const int32_t start = x.gs, end = x.ge;
+    for (;;) {
+        int32_t rl = 0, rn = 0, rq = -1;      // raw run: first local column, length, first query index or -1 (gaps)
+        if (w.plen > 0) { rl = w.plc; rn = w.plen; rq = w.pq; w.plen = 0; }
+        else if (w.in_m) {
+            // compare segments between positions that carry sub-columns
+            int32_t pj = w.pos + w.mj, cj = lcol(x, pj);
+            int32_t kmax = w.mjb - w.mj + 1, run = 1;
+            if (lcol(x, pj + kmax - 1) - cj == kmax - 1) run = kmax;          // no sub-columns inside
+            else {
+                // largest run with lcol(pj + run - 1) - cj == run - 1 (the excess is monotone): binary search
+                int32_t lo = 1, hi = kmax - 1;                                // answer in [lo, hi]
+                while (lo < hi) { int32_t mid = (lo + hi + 1) >> 1; if (lcol(x, pj + mid - 1) - cj == mid - 1) lo = mid; else hi = mid - 1; }
+                run = lo;
+            }
+            rl = cj; rn = run; rq = w.qpos + w.mj;
+            w.mj += run;
+            if (w.mj <= w.mjb) {                                              // sub-columns behind pos+mj-1
+                int32_t cb = lcol(x, w.pos + w.mj - 1);
+                w.plc = cb + 1; w.plen = lcol(x, w.pos + w.mj) - cb - 1; w.pq = -1;
+            } else {
+                w.in_m = false; w.pos += w.mlen; w.qpos += w.mlen; w.last = OP_M;
+                walk_op_done(x, w);
+            }
+        } else {
+            if (w.done || w.ci >= w.n_cigar) return false;
+            const uint32_t cg = w.cigar[w.ci];
+            const int32_t oplen = cig_len(cg); const int cur = cig_op(cg);
+            const int32_t pos = w.pos, qpos = w.qpos, qstart = w.qstart, qend = w.qend;
             if (cur == OP_M) {
                 // in-range bases: query [max(qpos,qstart), min(qpos+len-1,qend)], pos in [start,end]
                 int32_t ja = qstart > qpos ? qstart - qpos : 0;
                 if (pos + ja < start) ja = start - pos;
-                int32_t jb = qend - qpos < len - 1 ? qend - qpos : len - 1;
+                int32_t jb = qend - qpos < oplen - 1 ? qend - qpos : oplen - 1;
                 if (pos + jb > end) jb = end - pos;
-                if (pos + jb > x.e1) jb = x.e1 - pos;               // nothing beyond the extended range is stored
+                if (pos + jb > x.e1) jb = x.e1 - pos;               // nothing beyond the extended range is looked at
                 if (ja <= jb) {
                     // first in-range base: sub-columns behind pos-1 are filled only under the rule of
                     // contig.c:273; every later base of the op fills unconditionally
-                    int lastj = ja == 0 ? last : OP_M;
+                    int lastj = ja == 0 ? w.last : OP_M;
                     int32_t q0 = qpos + ja, p_a = pos + ja;
                     bool fill0 = lastj != OP_I && p_a > start && (q0 > qstart || (q0 == qstart && lastj == OP_D));
-                    if (fill0) { int32_t cb = lcol(x, p_a - 1); sw.run(cb + 1, lcol(x, p_a) - cb - 1, -1); }
-                    // copy segments between positions that carry sub-columns
-                    int32_t j = ja;
-                    while (j <= jb) {
-                        int32_t pj = pos + j, cj = lcol(x, pj);
-                        int32_t kmax = jb - j + 1, run = 1;
-                        if (lcol(x, pj + kmax - 1) - cj == kmax - 1) run = kmax;          // no sub-columns inside
-                        else while (run < kmax && lcol(x, pj + run) - cj == run) run++;
-                        sw.run(cj, run, qpos + j);
-                        j += run;
-                        if (j <= jb) {                                                    // sub-columns behind pos+j-1
-                            int32_t cb = lcol(x, pos + j - 1);
-                            sw.run(cb + 1, lcol(x, pos + j) - cb - 1, -1);
-                        }
-                    }
+                    w.in_m = true; w.mj = ja; w.mjb = jb; w.mlen = oplen;
+                    if (fill0) { int32_t cb = lcol(x, p_a - 1); rl = cb + 1; rn = lcol(x, p_a) - cb - 1; rq = -1; }
+                } else {
+                    w.pos += oplen; w.qpos += oplen; w.last = OP_M;
+                    walk_op_done(x, w);
                 }
-                pos += len; qpos += len; last = OP_M;
             } else if (cur == OP_D) {
                 if (qpos >= qstart && qpos <= qend) {
-                    int32_t ja = pos < start ? start - pos : 0, jb = pos + len - 1 > end ? end - pos : len - 1;
+                    int32_t ja = pos < start ? start - pos : 0, jb = pos + oplen - 1 > end ? end - pos : oplen - 1;
                     if (ja <= jb) {
-                        int lastj = ja == 0 ? last : OP_D;
+                        int lastj = ja == 0 ? w.last : OP_D;
                         int32_t p_a = pos + ja, p_b = pos + jb;
                         bool fill0 = lastj != OP_I && p_a > start && (qpos > qstart || (qpos == qstart && lastj == OP_D));
                         int32_t c_from = fill0 ? lcol(x, p_a - 1) + 1 : lcol(x, p_a);
                         if (p_b > x.e1) p_b = x.e1;                    // clip far-right work
-                        if (p_b >= p_a) sw.run(c_from, lcol(x, p_b) - c_from + 1, -1);
+                        if (p_b >= p_a) { rl = c_from; rn = lcol(x, p_b) - c_from + 1; rq = -1; }
                     }
                 }
-                pos += len; last = OP_D;
+                w.pos += oplen; w.last = OP_D;
+                walk_op_done(x, w);
             } else if (cur == OP_I) {
                 if (pos != x.gs) {
-                    // sub-columns behind a position left of the range are not stored (virtual columns)
+                    // sub-columns behind a position left of the range are not looked at (virtual columns)
                     bool in_reg = pos > start && pos <= end && pos - 1 >= x.e0 && pos <= x.e1;
                     if (in_reg) {
                         int32_t cb = lcol(x, pos - 1), nsub = lcol(x, pos) - cb - 1;
                         int32_t ja = qstart > qpos ? qstart - qpos : 0;
-                        int32_t jb = qend - qpos < len - 1 ? qend - qpos : len - 1;
+                        int32_t jb = qend - qpos < oplen - 1 ? qend - qpos : oplen - 1;
                         if (ja <= jb) {
-                            if (jb >= nsub) { *d.err |= npe::ERR_INS_OVERFLOW; jb = nsub - 1; }
-                            if (ja <= jb) sw.run(cb + 1 + ja, jb - ja + 1, qpos + ja);
+                            if (jb >= nsub) { *x.d.err |= npe::ERR_INS_OVERFLOW; jb = nsub - 1; }
+                            if (ja <= jb) { rl = cb + 1 + ja; rn = jb - ja + 1; rq = qpos + ja; }
                         }
-                        int32_t qa = qpos + len;
-                        if (qa > qstart && qa <= qend + 1 && nsub > len) sw.run(cb + 1 + len, nsub - len, -1);
+                        int32_t qa = qpos + oplen;
+                        if (qa > qstart && qa <= qend + 1 && nsub > oplen) {
+                            if (rn > 0) { w.plc = cb + 1 + oplen; w.plen = nsub - oplen; w.pq = -1; }
+                            else { rl = cb + 1 + oplen; rn = nsub - oplen; rq = -1; }
+                        }
                     }
-                    qpos += len; last = OP_I;
-                } else { qpos += len; qstart += len; last = OP_I; }
-            } else if (cur == OP_S || cur == OP_H) {
-                qpos += len;
-            }
-            if (pos > end || pos > x.e1 + 1) break;
-        }
-        uint32_t mmask = 0;
-        if (sw.n > 0) {
-            for (int32_t bq = sw.cs >> 5; bq <= (sw.cs + sw.n - 1) >> 5; bq++) {
-                be.atomic_min(&x.blk[2 * bq], i);
-                be.atomic_max(&x.blk[2 * bq + 1], i + 1);
-            }
-            // compare against the draft's symbol words (same alignment): per column "covered" / "disagrees"
-            const uint32_t* sp = x.str + off;
-            int32_t base = sw.cs & ~7, cw0 = base >> 3, nwd = (sw.cs + sw.n - base + 7) >> 3;
-            mmask = nwd > 32 ? 0xffffffffu : 0u;                // very long strings: no fast path in the tally
-            for (int32_t kq = 0; kq < nwd; kq++) {
-                uint32_t m = nib_mask(sw.cs - base - 8 * kq, sw.cs + sw.n - base - 8 * kq);
-                uint32_t df = (sp[kq] ^ x.refw[cw0 + kq]) & m;
-                df |= df >> 1; df |= df >> 2; df &= 0x11111111u;
-                if (df) { be.atomic_or(&x.acc[2 * (cw0 + kq)], df); if (kq < 32) mmask |= 1u << kq; }
-                be.atomic_or(&x.acc[2 * (cw0 + kq) + 1], m & 0x11111111u);
+                    w.qpos += oplen; w.last = OP_I;
+                } else { w.qpos += oplen; w.qstart += oplen; w.last = OP_I; }
+                walk_op_done(x, w);
+            } else {
+                if (cur == OP_S || cur == OP_H) w.qpos += oplen;
+                walk_op_done(x, w);
             }
         }
-        x.rd[i] = ReadMeta{sw.cs, sw.n, off, mmask};
+        if (rn <= 0) continue;
+        if (w.started && rl != w.next) x.ctr[CTR_ERROR] = 1;   // cannot happen (votes are contiguous)
+        w.next = rl + rn; w.started = true;
+        int32_t skip = rl < 0 ? -rl : 0;                  // clip to the extended range
+        if (skip >= rn) continue;
+        rl += skip; rn -= skip; if (rq >= 0) rq += skip;
+        if (rl + rn > x.ncols) rn = x.ncols - rl;
+        if (rn <= 0) continue;
+        lc = rl; len = rn; q = rq;
+        return true;
     }
 }
 
-// ---- phase 2: per-column info from the accumulators the expand phase OR-ed together ---------------------
-NP_HD void ph_colinfo(WCtx& x, int32_t tid, int32_t nt) {
-    for (int32_t lc = tid; lc < x.ncols; lc += nt) {
-        uint32_t bit = 28 - 4 * (lc & 7);
-        uint8_t f = x.colinfo[lc] & 8;
-        if ((x.acc[2 * (lc >> 3)] >> bit) & 1u) f |= 1;
-        if ((x.acc[2 * (lc >> 3) + 1] >> bit) & 1u) f |= 2;
-        x.colinfo[lc] = f;
+// A chunk that disagrees with the draft (or still owes events for a disagreement just before it) is parked as a
+// 16-byte descriptor; its votes are cast by ph_votes once the table columns are known.
+//   a = symbols (left-justified, zero below), b = lc | take << 16 | pend_in << 20 | min(idx0, 2) << 22 | hist << 24,
+//   c = read index
+template <class B>
+NP_HD void ph_compare(WCtx& x, int32_t tid, int32_t nt, B& be) {
+    const Dev& d = x.d;
+    // Static assignment and a loop whose only exit is its condition: the lanes of a warp enter and leave the
+    // chunk loop together and reconverge at its latch after every divergent `if`.
+    for (int32_t i = tid; i < x.nr; i += nt) {
+        // filter level, usable query interval and reference span were computed per read by ReadPrep
+        // (coalesced global arrays); only the record header, CIGAR and bases come from shared memory
+        const int64_t r = (int64_t)x.rlo + i;
+        const uint8_t* p = x.rec + (size_t)(x.recoff[i] - x.recoff[0]) * 16;
+        const uint32_t hd = ((const uint32_t*)p)[3];
+        const int32_t n_cigar = (int32_t)(hd >> 16);
+        const uint32_t* sw = (const uint32_t*)(p + 16 + 4 * (size_t)n_cigar);   // bases, 4-byte aligned
+        Walk w;
+        w.cigar = (const uint32_t*)p + 4; w.n_cigar = n_cigar; w.ci = 0;
+        w.pos = d.r_gpos[r]; w.qpos = 0; w.qstart = d.r_qstart[r]; w.qend = d.r_qend[r]; w.last = OP_I;
+        w.mj = w.mjb = w.mlen = 0; w.in_m = false; w.plc = w.plen = 0; w.pq = -1;
+        w.next = 0; w.started = false; w.done = false;
+        int32_t lc = 0, len = 0, q = -1;
+        int32_t cs = 0, n = 0;                            // first stored local column, stored symbols
+        uint32_t hist = 0, pend = 0, s01 = 0;             // last two symbols; columns still owing an event; first two symbols
+        uint32_t cur = 0; int32_t cur_si = -1;            // rolling big-endian word of the bases
+        // pass A: the first RUNCAP runs of every read are generated with all lanes in step (the generator is
+        // long, divergent code: called from inside the chunk loop it would run for one lane at a time)
+        uint2* rl = x.runs + (size_t)i * RUNCAP;
+        int32_t nrun = 0, krun = 1;
+        bool more = d.r_level[r] == 1;
+        while (more && nrun < RUNCAP) {
+            more = next_run(x, w, lc, len, q, be);
+            if (more) { rl[nrun] = uint2{(uint32_t)lc | (uint32_t)len << 16, (uint32_t)q}; nrun++; }
+        }
+        bool alive = nrun > 0;
+        if (alive) { const uint2 u = rl[0]; lc = (int32_t)(u.x & 0xffffu); len = (int32_t)(u.x >> 16); q = (int32_t)u.y; cs = lc; }
+        while (alive) {
+            // one chunk, aligned to the draft's symbol words
+            const int32_t dn = lc & 7;
+            const int32_t take = 8 - dn < len ? 8 - dn : len;
+            const uint32_t m = 0xffffffffu << (32 - 4 * take);
+            uint32_t S = 0x33333333u;                     // SYM_GAP x 8
+            if (q >= 0) {
+                const int32_t si = q >> 3, sn = q & 7;
+                if (si != cur_si) { cur = bswap32(sw[si]); cur_si = si; }
+                uint32_t lo = 0u;
+                if (sn + take > 8) lo = bswap32(sw[si + 1]);
+                S = fsl(cur, lo, (uint32_t)sn);
+                if (sn + take > 8) { cur = lo; cur_si = si + 1; }
+                q += take;
+            }
+            S &= m;
+            const uint32_t R = (x.refw[lc >> 3] << (4 * dn)) & m;
+            const uint32_t D = S ^ R;
+            if (n < 2 && n + take >= 2) s01 = n == 0 ? S >> 24 : ((hist << 4) | (S >> 28)) & 0xffu;
+            if (D | pend) {
+                uint32_t Dn = D | (D >> 1); Dn |= Dn >> 2; Dn &= 0x11111111u;
+                if (Dn) be.atomic_or(&x.acc[lc >> 3], Dn >> (4 * dn));
+                int32_t slot = be.atomic_add_ret(&x.ctr[CTR_EVENTS], 1);
+                if (slot < x.evcap)
+                    x.ev[slot] = Quad{S, (uint32_t)lc | (uint32_t)take << 16 | pend << 20 | (uint32_t)(n < 2 ? n : 2) << 22 | hist << 24,
+                                      (uint32_t)i, 0u};
+                // events spill two columns past a disagreement: what the next chunk still owes
+                const unsigned long long M = (unsigned long long)Dn << 32;
+                const unsigned long long E = M | (M >> 4) | (M >> 8) |
+                                             ((unsigned long long)((pend >= 1u ? 0x10000000u : 0u) | (pend >= 2u ? 0x01000000u : 0u)) << 32);
+                pend = ((E >> (56 - 4 * take)) & 1u) ? 2u : ((E >> (60 - 4 * take)) & 1u) ? 1u : 0u;
+            }
+            hist = (uint32_t)(((((unsigned long long)hist) << 32) | S) >> (32 - 4 * take)) & 0xffu;
+            n += take; lc += take; len -= take;
+            if (len == 0) {
+                if (krun < nrun) { const uint2 u = rl[krun++]; lc = (int32_t)(u.x & 0xffffu); len = (int32_t)(u.x >> 16); q = (int32_t)u.y; }
+                else alive = more && next_run(x, w, lc, len, q, be);
+                if (alive && lc != cs + n) { x.ctr[CTR_ERROR] = 1; alive = false; }
+            }
+        }
+        ReadStart rs{-1, 0u};
+        if (n > 0) {
+            if (n == 1) s01 = (hist & 0xfu) << 4;
+            be.atomic_add(&x.cov[cs], 1);
+            be.atomic_add(&x.cov[cs + n], -1);
+            rs = ReadStart{cs, s01 | (uint32_t)(n < 2 ? n : 2) << 8};
+        }
+        x.rs[i] = rs;
+    }
+}
+
+// ---- phase 2: votes per column (block-wide prefix sum of the +1/-1 marks) + per-column info ------------
+template <class B>
+NP_HD void ph_scan(WCtx& x, int32_t tid, int32_t nt, B& be) {
+    const int32_t n = x.ncols + 1, per = (n + nt - 1) / nt;
+    int32_t a = tid * per, b = a + per;
+    if (a > n) a = n;
+    if (b > n) b = n;
+    int32_t s = 0;
+    for (int32_t i = a; i < b; i++) s += x.cov[i];
+    int32_t run = be.block_exscan(s, x.scan_scratch);          // barrier inside: every thread calls it
+    for (int32_t i = a; i < b; i++) {
+        run += x.cov[i];
+        x.cov[i] = run;                                        // reads voting on column i
+        x.colinfo[i] = (uint8_t)(((x.acc[i >> 3] >> (28 - 4 * (i & 7))) & 1u) | (run > 0 ? 2u : 0u));
+        if (run >= 65534) *x.d.err |= npe::ERR_DEPTH;          // uint16 counters of the reference would wrap (base.h:28-31,45)
     }
 }
 
@@ -480,55 +509,90 @@ NP_HD void ph_mark_tables(WCtx& x, int32_t tid, int32_t nt, B& be) {
     // k-mer context are available because HL >= 2 positions) to the end of the extended range
     for (int32_t lc = x.cown0 + tid; lc < x.ncols; lc += nt) {
         if (!is_table(x, lc)) continue;
-        int32_t t = be.atomic_add_ret(&x.ctr[1], 1);
+        int32_t t = be.atomic_add_ret(&x.ctr[CTR_TABLES], 1);
         x.tabidx[lc] = t < x.tmax ? (int16_t)t : (int16_t)-2;        // -2: pool exhausted
-        if (t < x.tmax) x.tabcol[t] = (int16_t)lc;
-    }
-}
-NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
-    int32_t ntab = x.ctr[1] < x.tmax ? x.ctr[1] : x.tmax;
-    for (int32_t ti = tid; ti < ntab; ti += nt) {
-        int32_t lc = x.tabcol[ti];
-        TabEntry T{&x.tab, ti};
-        T.bad() = 0; T.nent() = 0; T.amax() = 0;
-        // reference vote first (contig_as_read, contig.c:373-383)
+        if (t >= x.tmax) continue;
+        x.tabcol[t] = (int16_t)lc;
+        TabEntry T{&x.tab, t};
+        // entry 0 = the draft's own 3-mer (contig_as_read, contig.c:373-383); the others start empty
         uint32_t k = be_get(x.refw, lc);
         if (!col_first(x, lc)) {
             k |= be_get(x.refw, lc - 1) << 4;
             if (!col_first(x, lc - 1)) k |= be_get(x.refw, lc - 2) << 8;
         }
-        int32_t nk = 1; uint32_t votes = 1, e0 = 1;            // entry 0 = the draft's 3-mer, its count kept in a register
-        int32_t blo = x.blk[2 * (lc >> 5)], bhi = x.blk[2 * (lc >> 5) + 1];
-        for (int32_t r = blo; r < bhi; r++) {
-            const ReadMeta m = x.rd[r];                     // one 128-bit load
-            int32_t i = lc - m.cs;
-            if (i < 0 || i >= m.cn) continue;
-            int32_t al = m.cs & 7;                          // the string starts at nibble `al` of its first word
-            votes++;
-            // fast path: the read agrees with the draft in the words holding columns lc-2..lc and has cast at
-            // least two symbols before lc -> it votes the draft's own 3-mer (entry 0)
-            if (i >= 2) {
-                uint32_t mmr = m.mm;
-                int32_t k0 = (i - 2 + al) >> 3, k1 = (i + al) >> 3;
-                if (k1 < 32 && !(((mmr >> k0) | (mmr >> k1)) & 1u)) { e0++; continue; }
-            }
-            const uint32_t* s = x.str + m.so;
-            // symbols i-2..i of the read's string as one funnel-shifted extract
-            uint32_t kk;
-            if (i >= 2) {
-                int32_t a = i - 2 + al;
-                uint32_t v = fsl(s[a >> 3], (a & 7) > 5 ? s[(a >> 3) + 1] : 0u, (uint32_t)(a & 7));
-                kk = v >> 20;
-            } else {
-                kk = be_get(s, i + al);
-                if (i >= 1) kk |= be_get(s, i - 1 + al) << 4;
-            }
-            if (kk == k) { e0++; continue; }
-            int32_t j = 1;
-            for (; j < nk; j++) if ((T.e(j) & 0xffffu) == kk) { T.e(j) += 1u << 16; break; }
-            if (j == nk) { if (nk < WK) T.e(nk++) = kk | (1u << 16); else T.bad() = 1; }
+        T.e(0) = k;
+        for (int j = 1; j < WK; j++) { T.e(j) = 0; T.fs(j) = 0xffffffffu; }
+        T.bad() = 0; T.nent() = 0; T.amax() = 0;
+    }
+}
+
+// one vote of read `ridx` for 3-mer `kmer` at local column lc (no-op unless lc has a table and the 3-mer is
+// not the draft's): find-or-insert with atomics; entries fill slots 1.. in claim order, the smallest read
+// index per entry restores the first-seen order afterwards
+template <class B>
+NP_HD void tab_vote(WCtx& x, int32_t lc, uint32_t kmer, uint32_t ridx, B& be) {
+    if (lc < 0 || lc >= x.ncols) return;
+    int32_t t = x.tabidx[lc];
+    if (t < 0) return;
+    TabEntry T{&x.tab, t};
+    if (kmer == (T.e(0) & 0xffffu)) return;
+    for (int j = 1; j < WK; j++) {
+        uint32_t old = be.atomic_cas_u32(&T.e(j), 0u, kmer | (1u << 16));
+        if (old == 0u) { be.atomic_min_u32(&T.fs(j), ridx); return; }
+        if ((old & 0xffffu) == kmer) { be.atomic_add_u32(&T.e(j), 1u << 16); be.atomic_min_u32(&T.fs(j), ridx); return; }
+    }
+    T.bad() = 1;
+}
+NP_HD int32_t clz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __clz((int)v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+template <class B>
+NP_HD void ph_votes(WCtx& x, int32_t tid, int32_t nt, B& be) {
+    // parked chunks: every column that disagrees, and the two after it, casts the read's 3-mer there
+    int32_t nev = x.ctr[CTR_EVENTS] < x.evcap ? x.ctr[CTR_EVENTS] : x.evcap;
+    for (int32_t i = tid; i < nev; i += nt) {
+        const Quad e = x.ev[i];
+        const uint32_t S = e.a, hist = e.b >> 24, pin = (e.b >> 20) & 3u, ridx = e.c;
+        const int32_t lc = (int32_t)(e.b & 0xffffu), take = (int32_t)((e.b >> 16) & 0xfu), idx0 = (int32_t)((e.b >> 22) & 3u);
+        const uint32_t m = 0xffffffffu << (32 - 4 * take);
+        const uint32_t R = (x.refw[lc >> 3] << (4 * (lc & 7))) & m;
+        uint32_t Dn = S ^ R; Dn |= Dn >> 1; Dn |= Dn >> 2; Dn &= 0x11111111u;
+        uint32_t Ev = (Dn | (Dn >> 4) | (Dn >> 8) | (pin >= 1u ? 0x10000000u : 0u) | (pin >= 2u ? 0x01000000u : 0u)) & m & 0x11111111u;
+        const unsigned long long W = ((unsigned long long)hist << 32) | S;
+        while (Ev) {
+            const int32_t k = clz32(Ev) >> 2;
+            Ev &= ~(0x10000000u >> (4 * k));
+            if (idx0 + k >= 2 && lc + k >= x.cown0) tab_vote(x, lc + k, (uint32_t)(W >> (28 - 4 * k)) & 0xfffu, ridx, be);
         }
-        T.e(0) = k | (e0 << 16);
+    }
+    // read starts: the first two symbols of a string cast partial 3-mers (zeros for the missing symbols)
+    for (int32_t i = tid; i < x.nr; i += nt) {
+        const ReadStart rs = x.rs[i];
+        if (rs.cs < 0) continue;
+        tab_vote(x, rs.cs, (rs.info >> 4) & 0xfu, (uint32_t)i, be);
+        if ((rs.info >> 8) >= 2u) tab_vote(x, rs.cs + 1, rs.info & 0xffu, (uint32_t)i, be);
+    }
+}
+NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
+    int32_t ntab = x.ctr[CTR_TABLES] < x.tmax ? x.ctr[CTR_TABLES] : x.tmax;
+    const bool overflow = x.ctr[CTR_EVENTS] > x.evcap;       // lost events: nothing of this window is trusted
+    for (int32_t ti = tid; ti < ntab; ti += nt) {
+        int32_t lc = x.tabcol[ti];
+        TabEntry T{&x.tab, ti};
+        if (overflow) T.bad() = 1;
+        int32_t nk = 1; uint32_t nd = 0;
+        while (nk < WK && T.e(nk) != 0u) { nd += T.e(nk) >> 16; nk++; }
+        for (int a = 1; a < nk; a++) {                        // order by first voter = first-seen order
+            int m = a;
+            for (int b = a + 1; b < nk; b++) if (T.fs(b) < T.fs(m)) m = b;
+            if (m != a) { uint32_t te = T.e(a), tf = T.fs(a); T.e(a) = T.e(m); T.fs(a) = T.fs(m); T.e(m) = te; T.fs(m) = tf; }
+        }
+        uint32_t votes = 1u + (uint32_t)x.cov[lc];
+        T.e(0) = (T.e(0) & 0xffffu) | ((votes - nd) << 16);
         T.nk() = (uint8_t)nk; T.votes() = (uint16_t)votes;
     }
 }
@@ -540,14 +604,14 @@ NP_HD void ph_tally(WCtx& x, int32_t tid, int32_t nt) {
 NP_HD void mark_unresolved(WCtx& x, int32_t lc_from, int32_t lc_to) {
     const Dev& d = x.d;
     for (int32_t lc = lc_from; lc <= lc_to && lc < x.ncols; lc++) d.needi[x.cb0 + lc] = 1;
-    x.ctr[3] = 1;
+    x.ctr[CTR_UNRESOLVED] = 1;
 }
 
 NP_HD void ph_chain(WCtx& x, int32_t tid, int32_t nt) {
     const Dev& d = x.d;
     const double rate = d.P.rate;
-    int32_t ntab_all = x.ctr[1] < x.tmax ? x.ctr[1] : x.tmax;
-    if (x.ctr[1] > x.tmax) {
+    int32_t ntab_all = x.ctr[CTR_TABLES] < x.tmax ? x.ctr[CTR_TABLES] : x.tmax;
+    if (x.ctr[CTR_TABLES] > x.tmax) {
         // table pool exhausted: some table columns are not in the dense list; walk the columns instead
         ntab_all = -1;
     }
@@ -631,12 +695,8 @@ NP_HD void ph_anchors(WCtx& x, int32_t tid, int32_t nt) {
         int32_t c = x.cb0 + lc;
         uint8_t ci = x.colinfo[lc];
         if (x.tabidx[lc] != -1) {
-            int32_t ti = x.tabidx[lc];
-            // votes of table columns are needed by the fallback tables (capacity); recount if no table
-            uint32_t v = 1;
-            if (ti >= 0) v = x.tab.votes[ti];
-            else for (int32_t r = 0; r < x.nr; r++) { int32_t i = lc - x.rd[r].cs; if (i >= 0 && i < x.rd[r].cn) v++; }
-            d.votes[c] = v;
+            // votes of table columns are needed by the fallback tables (capacity)
+            d.votes[c] = 1u + (uint32_t)x.cov[lc];
             continue;
         }
         uint8_t fl = 0;
@@ -649,8 +709,8 @@ NP_HD void ph_anchors(WCtx& x, int32_t tid, int32_t nt) {
 }
 template <class B>
 NP_HD void ph_finish(WCtx& x, int32_t tid, int32_t nt, B& be) {
-    if (x.ctr[2]) { if (tid == 0) *x.d.err |= npe::ERR_SYM_BOUND; }
-    if (x.ctr[3]) {
+    if (x.ctr[CTR_ERROR]) { if (tid == 0) *x.d.err |= npe::ERR_SYM_BOUND; }
+    if (x.ctr[CTR_UNRESOLVED]) {
         for (int32_t i = tid; i < x.nr; i += nt) x.g.r_need[x.rlo + i] = 1;
         if (tid == 0) be.atomic_add(x.g.n_unresolved, 1);
     }

@@ -20,6 +20,10 @@ struct EmuOps {
     void atomic_or(uint32_t* p, uint32_t v) { *p |= v; }
     void atomic_add(int32_t* p, int32_t v) { *p += v; }
     int32_t atomic_add_ret(int32_t* p, int32_t v) { int32_t o = *p; *p += v; return o; }
+    uint32_t atomic_cas_u32(uint32_t* p, uint32_t cmp, uint32_t v) { uint32_t o = *p; if (o == cmp) *p = v; return o; }
+    void atomic_add_u32(uint32_t* p, uint32_t v) { *p += v; }
+    void atomic_min_u32(uint32_t* p, uint32_t v) { if (*p > v) *p = v; }
+    int32_t block_exscan(int32_t, int32_t*) { return 0; }      // one "thread" per phase: nothing before it
 };
 struct EmuBackend {
     std::map<std::string, std::vector<uint8_t>> pool;
@@ -68,7 +72,7 @@ struct EmuBackend {
             memset(smem.data(), 0xA5, smem.size());          // poison: phases must initialise what they read
             npw::WCtx x; x.d = d; x.g = g;
             npw::win_setup(x, w, smem.data());
-            if ((int32_t)npw::win_smem_bytes(x.nr, (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u, x.ncols, x.strw, x.npos) > smem_bytes) abort();
+            if ((int32_t)npw::win_smem_bytes(x.nr, (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u, x.ncols, x.npos) > smem_bytes) abort();
             uint32_t recbytes = (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u;
             memcpy(x.rec, d.rec + (size_t)d.rec_off[x.rlo] * 16, recbytes);                 // stands for the bulk copy
             memcpy((void*)x.recoff, d.rec_off + x.rlo, 4 * (size_t)(x.nr + 1));

@@ -53,6 +53,26 @@ def main():
     for f in os.listdir(os.path.join(ROOT, "nextpolish_b200", "csrc")):
         if f.endswith((".h", ".cu")):
             src[f] = open(os.path.join(ROOT, "nextpolish_b200", "csrc", f)).read().split("\n")
+    # by function: line ranges of top-level definitions in each source file
+    import bisect
+    starts = {}
+    for f, lines in src.items():
+        st = [(i + 1, l.strip()[:70]) for i, l in enumerate(lines) if re.match(r"(NP_HD|template|struct|__global__|static|inline)\b", l)]
+        starts[f] = st
+    fagg, fsamp = collections.Counter(), collections.Counter()
+    for fl, v in agg.items():
+        key = fl
+        if fl and fl[0] in starts and starts[fl[0]]:
+            st = starts[fl[0]]
+            j = bisect.bisect_right([a for a, _ in st], fl[1]) - 1
+            # a "template <...>" line is followed by the definition it belongs to
+            name = st[j][1] if j >= 0 else "?"
+            if name.startswith("template") and j + 1 < len(st) and st[j + 1][0] == st[j][0] + 1: name = st[j + 1][1]
+            key = (fl[0], name)
+        fagg[key] += v; fsamp[key] += samp[fl]
+    print("\nby function (warp instructions / samples):")
+    for k, v in fagg.most_common(25):
+        print("%5.1f%% inst %5.1f%% samp  %s" % (100 * v / tot, 100 * fsamp[k] / ts, k))
     print("\nwarp instructions: %.0f, samples: %.0f" % (tot, ts))
     for fl, v in agg.most_common(top):
         t = src.get(fl[0], [""] * 100000)[fl[1] - 1].strip()[:90] if fl and fl[0] in src else ""
