@@ -213,6 +213,21 @@ int32_t np_polish_host(np_engine* e, int32_t task, const np_shard_view* host_sha
                        const Configure* cfg, uint8_t* out_seq, int64_t out_cap, int64_t* out_off);
 
 
+/* Streaming front end (double-buffered): jobs are submitted in order; a job's host-to-device copy is
+ * enqueued at submission on its own slot (engine, stream, buffers) and overlaps the kernels of the jobs
+ * submitted before it.  `depth` = slots (2 = one job computing while the next one uploads).
+ * host_shard / out_seq / out_off must stay valid until np_stream_wait(ticket) returned; cfg is copied.
+ * np_stream_submit returns a ticket >= 0 or a negative NP_ERR_*; when every slot is busy it first
+ * finishes the oldest job.  np_stream_wait finishes every job up to `ticket` and returns its status. */
+typedef struct np_stream np_stream;
+np_stream* np_stream_create(int32_t device, int32_t depth);
+void       np_stream_destroy(np_stream* s);
+int64_t    np_stream_submit(np_stream* s, int32_t task, const np_shard_view* host_shard, const Configure* cfg,
+                            uint8_t* out_seq, int64_t out_cap, int64_t* out_off);
+int32_t    np_stream_wait(np_stream* s, int64_t ticket);
+int64_t    np_stream_launch_count(np_stream* s);   /* kernel launches of every finished job */
+
+
 /* ---- seeded synthetic inputs (draft FASTA + coordinate-sorted BAM), for bench and tests -- */
 typedef struct {
     uint64_t seed;

@@ -394,6 +394,7 @@ struct np_engine {
     np_engine* sibling = nullptr;      // second engine (stream + scratch) of the pipelined np_polish_host
     cudaEvent_t copy_done = nullptr;
     bool pipelined_last = false;
+    int64_t launches_total = 0;        // kernel launches of every run so far
 };
 
 static bool dev_reserve(np_engine* e, void** p, size_t* cap, size_t bytes) {
@@ -447,7 +448,8 @@ void np_engine_destroy(np_engine* e) {
 // (asynchronously on the engine stream; pinned buffers overlap with other streams' work); device
 // shards are adopted in place.  Offsets inside rec_off / qual_off stay absolute: the device base
 // pointers are shifted instead of rewriting the offset arrays.
-static int32_t set_shard_slice(np_engine* e, const np_shard_view* v, int32_t k0, int32_t k1, bool device_resident) {
+static int32_t set_shard_slice(np_engine* e, const np_shard_view* v, int32_t k0, int32_t k1, bool device_resident,
+                               cudaEvent_t bulk_after = nullptr) {
     if (!e || !v || v->n_contigs < 0 || v->n_reads < 0 || k0 < 0 || k1 < k0 || k1 > v->n_contigs) { np::set_error("bad shard"); return NP_ERR_ARG; }
     const int64_t c0 = v->ctg_off[k0], G = v->ctg_off[k1] - c0;
     const int64_t r0 = v->ctg_read_off[k0], R = v->ctg_read_off[k1] - r0;
@@ -483,6 +485,9 @@ static int32_t set_shard_slice(np_engine* e, const np_shard_view* v, int32_t k0,
         if (v->qual_off) { q_lo = v->qual_off[r0]; q_hi = v->qual_off[r0 + R]; }
     }
     const size_t rec_bytes = (size_t)(rec_hi - rec_lo) * 16, qual_bytes = (size_t)(q_hi - q_lo) * 16;
+    // the bulk copies below are ordered behind `bulk_after` (an earlier upload on another stream): uploads
+    // share one PCIe link, so they are kept in submission order instead of splitting its bandwidth
+    if (bulk_after) cudaStreamWaitEvent(s, bulk_after, 0);
     npe::Dev& d = e->d;
     d.n_ctg = nc; d.n_reads = R; d.G = (int32_t)G;
     d.ctg_goff = (const int32_t*)e->s_goff; d.ctg_read_off = (const int64_t*)e->s_roff;
@@ -543,6 +548,7 @@ int32_t np_engine_run(np_engine* e, int32_t task, const Configure* cfg) {
         return NP_ERR_LIMIT;
     }
     e->ran = true;
+    e->launches_total += e->be.launches;
     return NP_OK;
 }
 
@@ -643,6 +649,85 @@ int32_t np_polish_host(np_engine* e, int32_t task, const np_shard_view* host_sha
     for (int32_t k = kmid; k <= n; k++) out_off[k] += na;
     e->pipelined_last = true;
     return NP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming front end: jobs (task, host shard) are submitted in order; the upload of a job is enqueued at
+// submission on its own slot (engine + stream + buffers) and overlaps the kernels of the jobs before it.
+// This is the double-buffered pinned-ring of SURVEY.md 7.3 H7: contig blocks stream through HBM.
+// ---------------------------------------------------------------------------------------------
+struct np_stream {
+    int device = 0;
+    std::vector<np_engine*> slot;
+    struct Job { int64_t ticket; int32_t task; const np_shard_view* v; Configure cfg; uint8_t* out; int64_t cap; int64_t* off; int s; int32_t rc; };
+    std::vector<Job> q;                 // submitted, unfinished, oldest first
+    std::map<int64_t, int32_t> finished;
+    cudaEvent_t last_upload = nullptr; bool have_upload = false;
+    int64_t next_ticket = 0;
+};
+
+static void stream_process_oldest(np_stream* st) {
+    np_stream::Job j = st->q.front();
+    st->q.erase(st->q.begin());
+    np_engine* e = st->slot[(size_t)j.s];
+    if (j.rc == NP_OK) j.rc = np_engine_run(e, j.task, &j.cfg);
+    if (j.rc == NP_OK) j.rc = np_engine_download(e, j.out, j.cap, j.off);
+    st->finished[j.ticket] = j.rc;
+}
+
+np_stream* np_stream_create(int32_t device, int32_t depth) {
+    if (depth < 1) depth = 1;
+    if (depth > 8) depth = 8;
+    np_stream* st = new np_stream();
+    st->device = device;
+    for (int i = 0; i < depth; i++) {
+        np_engine* e = np_engine_create(device);
+        if (!e) { for (np_engine* x : st->slot) np_engine_destroy(x); delete st; return nullptr; }
+        st->slot.push_back(e);
+    }
+    cudaEventCreateWithFlags(&st->last_upload, cudaEventDisableTiming);
+    return st;
+}
+void np_stream_destroy(np_stream* st) {
+    if (!st) return;
+    while (!st->q.empty()) stream_process_oldest(st);
+    for (np_engine* e : st->slot) np_engine_destroy(e);
+    if (st->last_upload) cudaEventDestroy(st->last_upload);
+    delete st;
+}
+// Returns a ticket >= 0 (or a negative NP_ERR_*).  host_shard, out_seq and out_off must stay valid until
+// np_stream_wait(ticket) returned; cfg is copied.  When every slot is busy the oldest job is finished first.
+int64_t np_stream_submit(np_stream* st, int32_t task, const np_shard_view* host_shard, const Configure* cfg,
+                         uint8_t* out_seq, int64_t out_cap, int64_t* out_off) {
+    if (!st || !host_shard || !cfg) { np::set_error("np_stream_submit: bad arguments"); return NP_ERR_ARG; }
+    if (st->q.size() == st->slot.size()) stream_process_oldest(st);
+    std::vector<char> used(st->slot.size(), 0);
+    for (const auto& j : st->q) used[(size_t)j.s] = 1;
+    int s = 0;
+    while (used[(size_t)s]) s++;
+    np_stream::Job j{st->next_ticket++, task, host_shard, *cfg, out_seq, out_cap, out_off, s, NP_OK};
+    np_engine* e = st->slot[(size_t)s];
+    j.rc = set_shard_slice(e, host_shard, 0, host_shard->n_contigs, false, st->have_upload ? st->last_upload : nullptr);
+    cudaEventRecord(st->last_upload, e->be.stream);
+    st->have_upload = true;
+    st->q.push_back(j);
+    return j.ticket;
+}
+// Finishes every job up to and including `ticket` (kernels + download); returns that job's status.
+int32_t np_stream_wait(np_stream* st, int64_t ticket) {
+    if (!st) return NP_ERR_ARG;
+    while (!st->finished.count(ticket)) {
+        if (st->q.empty()) { np::set_error("np_stream_wait: unknown ticket"); return NP_ERR_ARG; }
+        stream_process_oldest(st);
+    }
+    int32_t rc = st->finished[ticket];
+    st->finished.erase(ticket);
+    return rc;
+}
+int64_t np_stream_launch_count(np_stream* st) {      // kernel launches of every job finished so far
+    int64_t n = 0;
+    if (st) for (np_engine* e : st->slot) n += e->launches_total;
+    return n;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -101,7 +101,7 @@ struct WCtx {             // per-window context: globals + carved shared memory
     // shared memory
     uint8_t* rec; const uint32_t* recoff;     // staged records and their offsets (16-byte units, global)
     ReadStart* rs;                            // per read
-    Quad* ev;                                 // parked chunks (see ph_compare)
+    uint32_t *ev_s, *ev_m; uint16_t* ev_r;    // parked chunks (see ph_compare): symbols, meta word, read index
     uint2* runs;                              // [nr][RUNCAP] pre-walked runs: .x = lc | len << 16, .y = first query index or -1
     uint32_t* refw;                           // draft symbol words (8 columns per word, big-endian nibbles)
     uint32_t* acc;                            // same layout: bit 0 of a nibble set = some read disagrees at that column
@@ -116,7 +116,7 @@ struct WCtx {             // per-window context: globals + carved shared memory
 };
 
 NP_HD uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
-NP_HD int32_t win_evcap(int32_t nr) { int32_t c = 4 * nr; return c < 512 ? 512 : c; }   // parked chunks per window
+NP_HD int32_t win_evcap(int32_t nr) { int32_t c = (6 * nr + 7) & ~7; return c < 1024 ? 1024 : c; }   // parked chunks per window (~170 on 30x data, outliers 3-4x)
 // shared-memory bytes of a window with nr reads, recbytes of records, ncols ext columns
 NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int32_t npos) {
     uint32_t b = 64 + SCAN_SCRATCH_BYTES;              // mbarrier + counters, scan scratch
@@ -126,7 +126,7 @@ NP_HD uint32_t win_smem_bytes(int32_t nr, uint32_t recbytes, int32_t ncols, int3
     b += recarea + align16(4u * (uint32_t)(nr + 1));
     b += align16(2u * (uint32_t)(npos + 2));
     b += align16(8u * (uint32_t)(nr + 1));
-    b += 16u * (uint32_t)win_evcap(nr);
+    b += 10u * (uint32_t)win_evcap(nr);
     b += 8u * (uint32_t)RUNCAP * (uint32_t)(nr + 1);
     b += 2 * align16(4u * (uint32_t)(ncols / 8 + 3));
     b += align16(4u * (uint32_t)(ncols + 2));
@@ -197,7 +197,9 @@ NP_HD void win_setup(WCtx& x, int32_t w, uint8_t* smem) {
     x.recoff = (const uint32_t*)p; p += align16(4u * (uint32_t)(x.nr + 1));
     x.lcb = (uint16_t*)p; p += align16(2u * (uint32_t)(x.npos + 2));
     x.rs = (ReadStart*)p; p += align16(8u * (uint32_t)(x.nr + 1));
-    x.ev = (Quad*)p; p += 16u * (uint32_t)x.evcap;
+    x.ev_s = (uint32_t*)p; p += 4u * (uint32_t)x.evcap;
+    x.ev_m = (uint32_t*)p; p += 4u * (uint32_t)x.evcap;
+    x.ev_r = (uint16_t*)p; p += 2u * (uint32_t)x.evcap;
     x.runs = (uint2*)p; p += 8u * (uint32_t)RUNCAP * (uint32_t)(x.nr + 1);
     x.refw = (uint32_t*)p; p += align16(4u * (uint32_t)(x.ncols / 8 + 3));
     x.acc = (uint32_t*)p; p += align16(4u * (uint32_t)(x.ncols / 8 + 3));
@@ -390,8 +392,8 @@ NP_HD bool next_run(WCtx& x, Walk& w, int32_t& lc, int32_t& len, int32_t& q, B& 
 
 // A chunk that disagrees with the draft (or still owes events for a disagreement just before it) is parked as a
 // 16-byte descriptor; its votes are cast by ph_votes once the table columns are known.
-//   a = symbols (left-justified, zero below), b = lc | take << 16 | pend_in << 20 | min(idx0, 2) << 22 | hist << 24,
-//   c = read index
+//   symbols (left-justified, zero below); meta = lc | take << 16 | pend_in << 20 | min(idx0, 2) << 22 | hist << 24;
+//   read index (uint16: a window with 65 536 reads does not fit shared memory)
 template <class B>
 NP_HD void ph_compare(WCtx& x, int32_t tid, int32_t nt, B& be) {
     const Dev& d = x.d;
@@ -448,9 +450,11 @@ NP_HD void ph_compare(WCtx& x, int32_t tid, int32_t nt, B& be) {
                 uint32_t Dn = D | (D >> 1); Dn |= Dn >> 2; Dn &= 0x11111111u;
                 if (Dn) be.atomic_or(&x.acc[lc >> 3], Dn >> (4 * dn));
                 int32_t slot = be.atomic_add_ret(&x.ctr[CTR_EVENTS], 1);
-                if (slot < x.evcap)
-                    x.ev[slot] = Quad{S, (uint32_t)lc | (uint32_t)take << 16 | pend << 20 | (uint32_t)(n < 2 ? n : 2) << 22 | hist << 24,
-                                      (uint32_t)i, 0u};
+                if (slot < x.evcap) {
+                    x.ev_s[slot] = S;
+                    x.ev_m[slot] = (uint32_t)lc | (uint32_t)take << 16 | pend << 20 | (uint32_t)(n < 2 ? n : 2) << 22 | hist << 24;
+                    x.ev_r[slot] = (uint16_t)i;
+                }
                 // events spill two columns past a disagreement: what the next chunk still owes
                 const unsigned long long M = (unsigned long long)Dn << 32;
                 const unsigned long long E = M | (M >> 4) | (M >> 8) |
@@ -555,9 +559,8 @@ NP_HD void ph_votes(WCtx& x, int32_t tid, int32_t nt, B& be) {
     // parked chunks: every column that disagrees, and the two after it, casts the read's 3-mer there
     int32_t nev = x.ctr[CTR_EVENTS] < x.evcap ? x.ctr[CTR_EVENTS] : x.evcap;
     for (int32_t i = tid; i < nev; i += nt) {
-        const Quad e = x.ev[i];
-        const uint32_t S = e.a, hist = e.b >> 24, pin = (e.b >> 20) & 3u, ridx = e.c;
-        const int32_t lc = (int32_t)(e.b & 0xffffu), take = (int32_t)((e.b >> 16) & 0xfu), idx0 = (int32_t)((e.b >> 22) & 3u);
+        const uint32_t S = x.ev_s[i], eb = x.ev_m[i], hist = eb >> 24, pin = (eb >> 20) & 3u, ridx = x.ev_r[i];
+        const int32_t lc = (int32_t)(eb & 0xffffu), take = (int32_t)((eb >> 16) & 0xfu), idx0 = (int32_t)((eb >> 22) & 3u);
         const uint32_t m = 0xffffffffu << (32 - 4 * take);
         const uint32_t R = (x.refw[lc >> 3] << (4 * (lc & 7))) & m;
         uint32_t Dn = S ^ R; Dn |= Dn >> 1; Dn |= Dn >> 2; Dn &= 0x11111111u;
@@ -710,6 +713,11 @@ NP_HD void ph_anchors(WCtx& x, int32_t tid, int32_t nt) {
 template <class B>
 NP_HD void ph_finish(WCtx& x, int32_t tid, int32_t nt, B& be) {
     if (x.ctr[CTR_ERROR]) { if (tid == 0) *x.d.err |= npe::ERR_SYM_BOUND; }
+#if !defined(__CUDA_ARCH__) && defined(NP_DEBUG_UNRESOLVED)
+    { static long long se = 0, sw = 0, st = 0, sr = 0; se += x.ctr[CTR_EVENTS]; st += x.ctr[CTR_TABLES]; sr += x.nr; sw++;
+      if (sw % 500 == 0) printf("avg events %.1f tables %.1f reads %.1f\n", (double)se / sw, (double)st / sw, (double)sr / sw); }
+    if (x.ctr[CTR_UNRESOLVED]) printf("unresolved window %d: nr %d events %d/%d tables %d/%d\n", x.win, x.nr, x.ctr[CTR_EVENTS], x.evcap, x.ctr[CTR_TABLES], x.tmax);
+#endif
     if (x.ctr[CTR_UNRESOLVED]) {
         for (int32_t i = tid; i < x.nr; i += nt) x.g.r_need[x.rlo + i] = 1;
         if (tid == 0) be.atomic_add(x.g.n_unresolved, 1);

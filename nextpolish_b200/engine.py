@@ -124,6 +124,41 @@ class Shard:
             pass
 
 
+class Stream:
+    """np_stream: jobs (task, host shard) submitted in order; a job's upload overlaps the kernels of the jobs
+    before it (double buffering).  Buffers handed to submit() must stay alive until wait(ticket) returned."""
+
+    def __init__(self, device=0, depth=2):
+        self.h = lib().np_stream_create(device, depth)
+        if not self.h:
+            raise NativeError(last_error())
+
+    def submit(self, task, view, cfg, out, off):
+        t = lib().np_stream_submit(self.h, task, C.byref(view), cfg, out.ctypes.data, out.size, off.ctypes.data)
+        if t < 0:
+            raise NativeError("rc=%d: %s" % (t, last_error()))
+        return t
+
+    def wait(self, ticket):
+        rc = lib().np_stream_wait(self.h, ticket)
+        if rc != 0:
+            raise NativeError("rc=%d: %s" % (rc, last_error()))
+
+    def launch_count(self):
+        return lib().np_stream_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().np_stream_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     """One GPU's polishing engine (np_engine). Creating it fails loudly without a CUDA device."""
 

@@ -231,6 +231,31 @@ def test_pipelined_host_call_equals_resident_path(E, eng):
         assert {n: raw[off[i]:off[i + 1]] for i, n in enumerate(sh.names)} == want, task
 
 
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_streaming_front_end_equals_resident_path(E, eng, depth):
+    """np_stream_submit / np_stream_wait: jobs of both tasks on different shards, uploads overlapping the
+    kernels of the jobs before them; every job's bytes equal the resident-path result."""
+    cfg = E.default_config(b"")
+    cfg.contents.read_tlen = 1750
+    shards = [E.Shard.synthetic(E.synth_params(seed=300 + k, n_contigs=2 + k, contig_len=150000, depth=25.0,
+                                               lowercase_frac=0.002 * k), 0, 2 + k, with_qual=2) for k in range(3)]
+    jobs = [(t, sh) for sh in shards for t in tasks(E)] * 2
+    want = {(t, id(sh)): eng.polish(sh, t, cfg) for t, sh in set(jobs)}
+    st = E.Stream(0, depth)
+    bufs, tickets = [], []
+    for t, sh in jobs:
+        out = np.zeros(int(sh.total_bases * 2), np.uint8)
+        off = np.zeros(sh.n_contigs + 1, np.int64)
+        bufs.append((out, off))
+        tickets.append(st.submit(t, sh.view, cfg, out, off))
+    for (t, sh), (out, off), tk in reversed(list(zip(jobs, bufs, tickets))):      # waiting out of order is allowed
+        st.wait(tk)
+        raw = out.tobytes()
+        assert {n: raw[off[i]:off[i + 1]] for i, n in enumerate(sh.names)} == want[(t, id(sh))], (t, depth)
+    assert st.launch_count() > 0
+    st.close()
+
+
 @pytest.mark.parametrize("rate", [0.33, 0.7])
 def test_gpu_non_dyadic_rate(E, oracle, eng, rate):
     sh = E.Shard.synthetic(E.synth_params(seed=92, n_contigs=3, contig_len=60000, depth=40.0, draft_indel=0.01, read_sub=0.01,
