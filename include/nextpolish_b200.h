@@ -124,12 +124,15 @@ void          polishresult_destory(PolishResult* polishresult);
  *   int32  pos        0-based leftmost reference position   (bam1_core_t.pos)
  *   uint16 flag       BAM FLAG
  *   uint8  mapq       BAM MAPQ
- *   uint8  reserved   0
+ *   uint8  enc        encoding of seq[]: 0 = BAM 4-bit nt16 codes, 1 = 2 bits per base (see below)
  *   int32  isize      BAM TLEN
  *   uint16 l_qseq     read length
  *   uint16 n_cigar    number of CIGAR ops (>= 1)
  *   uint32 cigar[n_cigar]          BAM encoding, len<<4 | op
- *   uint8  seq[(l_qseq+1)/2]       BAM 4-bit nt16 codes, high nibble first
+ *   uint8  seq[]                   enc 0: (l_qseq+1)/2 bytes, BAM 4-bit nt16 codes, high nibble first;
+ *                                  enc 1: (l_qseq+3)/4 bytes, A=0 C=1 G=2 T=3 (nt16 code = 1 << v), first base in
+ *                                  the two highest bits — chosen by the packer for reads made of A/C/G/T only
+ *                                  (halves the bytes that cross PCIe; set NEXTPOLISH_B200_4BIT=1 to disable)
  *   zero padding to a multiple of 16 bytes
  * Qualities (needed by task 2 only) live in a second stream: l_qseq bytes per read, each
  * read padded to 16 bytes.

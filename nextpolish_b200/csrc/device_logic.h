@@ -37,6 +37,7 @@ struct Params {
 struct Rec {
     int32_t pos; uint32_t flag, mapq; int32_t isize; int32_t l_qseq, n_cigar;
     const uint32_t* cigar; const uint8_t* seq;
+    uint32_t enc;                  // 0: 4-bit nt16 codes, 1: 2 bits per base (include/nextpolish_b200.h)
 };
 NP_HD Rec load_rec(const uint8_t* rec, const uint32_t* rec_off, int64_t r) {
     const uint8_t* p = rec + (size_t)rec_off[r] * 16;
@@ -46,6 +47,7 @@ NP_HD Rec load_rec(const uint8_t* rec, const uint32_t* rec_off, int64_t r) {
     o.pos = (int32_t)w0;
     o.flag = w1 & 0xffffu;
     o.mapq = (w1 >> 16) & 0xffu;
+    o.enc = w1 >> 24;
     o.isize = (int32_t)w2;
     o.l_qseq = (int32_t)(w3 & 0xffffu);
     o.n_cigar = (int32_t)(w3 >> 16);
@@ -54,6 +56,9 @@ NP_HD Rec load_rec(const uint8_t* rec, const uint32_t* rec_off, int64_t r) {
     return o;
 }
 NP_HD uint32_t seqi(const uint8_t* s, int32_t i) { return (s[i >> 1] >> ((~i & 1) << 2)) & 0xfu; }   // bam_seqi
+NP_HD uint32_t rseq(const Rec& r, int32_t i) {                                                        // nt16 code of base i
+    return r.enc ? 1u << ((r.seq[i >> 2] >> (6 - 2 * (i & 3))) & 3u) : seqi(r.seq, i);
+}
 NP_HD int cig_op(uint32_t c) { return (int)(c & 0xf); }
 NP_HD int32_t cig_len(uint32_t c) { return (int32_t)(c >> 4); }
 
@@ -97,8 +102,8 @@ NP_HD void cut_read(const Rec& r, int32_t trim, int32_t* qstart, int32_t* qend) 
     if (cig_op(r.cigar[r.n_cigar - 1]) == OP_S) add = cig_len(r.cigar[r.n_cigar - 1]);
     int32_t qe = r.l_qseq - trim - add - 1;
     if (trim > 0) {
-        while (qs < r.l_qseq && qs >= 1 && seqi(r.seq, qs) == seqi(r.seq, qs - 1)) qs++;
-        while (qe >= 0 && qe + 1 < r.l_qseq && seqi(r.seq, qe) == seqi(r.seq, qe + 1)) qe--;
+        while (qs < r.l_qseq && qs >= 1 && rseq(r, qs) == rseq(r, qs - 1)) qs++;
+        while (qe >= 0 && qe + 1 < r.l_qseq && rseq(r, qe) == rseq(r, qe + 1)) qe--;
     }
     *qstart = qs; *qend = qe;
 }
@@ -143,7 +148,7 @@ NP_HD void walk_read(const Rec& r, int32_t gshift, int32_t start, int32_t end,
                     for (int32_t k = 0; k < n; k++) v.sym(cb + 1 + k, (uint32_t)SYM_GAP, -1, true);
                 }
                 if (cur == OP_D) v.sym(colbase[p], (uint32_t)SYM_GAP, -1, false);
-                else v.sym(colbase[p], seqi(r.seq, q), q, false);
+                else v.sym(colbase[p], rseq(r, q), q, false);
             }
             pos += len;
             if (cur == OP_M) qpos += len;
@@ -156,7 +161,7 @@ NP_HD void walk_read(const Rec& r, int32_t gshift, int32_t start, int32_t end,
                 int32_t j = 0;
                 for (; j < len; j++, qpos++) {
                     if (in_reg && qpos >= qstart && qpos <= qend) {
-                        if (j < n) v.sym(cb + 1 + j, seqi(r.seq, qpos), qpos, false);
+                        if (j < n) v.sym(cb + 1 + j, rseq(r, qpos), qpos, false);
                         else v.overflow();
                     }
                 }

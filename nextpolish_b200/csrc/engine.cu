@@ -132,7 +132,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
 
 constexpr int kWinThreads = 192;   // 4 CTAs x 6 warps per SM at ~55 KB of shared memory per CTA
 
-__global__ void __launch_bounds__(256) k_window(npe::Dev d, npw::WinGlobals g) {
+__global__ void __launch_bounds__(kWinThreads, 4) k_window(npe::Dev d, npw::WinGlobals g) {
     extern __shared__ __align__(128) uint8_t smem[];
     npw::WCtx x; x.d = d; x.g = g;
     npw::win_setup(x, (int32_t)blockIdx.x, smem);
@@ -323,7 +323,7 @@ struct CudaBackend {
             CUDA_TRY(cudaMemsetAsync(gg.phase_cycles, 0, 16 * sizeof(unsigned long long), stream));
         }
         int threads = kWinThreads;
-        if (const char* ev = getenv("NEXTPOLISH_B200_WIN_THREADS")) { int v = atoi(ev); if (v >= 64 && v <= 256 && v % 32 == 0) threads = v; }   // tuning only
+        if (const char* ev = getenv("NEXTPOLISH_B200_WIN_THREADS")) { int v = atoi(ev); if (v >= 64 && v <= kWinThreads && v % 32 == 0) threads = v; }   // tuning only
         begin_timed("pileup_scan");
         k_window<<<(unsigned)g.n_win, threads, (size_t)want, stream>>>(d, gg);
         if (gg.phase_cycles) {

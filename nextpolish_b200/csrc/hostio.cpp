@@ -1,6 +1,7 @@
 // hostio.cpp — FASTA / BGZF / BAM / BAI readers and the packed-shard builder (host side).
 // See hostio.h for the role of this file relative to the reference's htslib calls.
 #include "hostio.h"
+#include <cstdlib>
 
 #include <zlib.h>
 #include <fcntl.h>
@@ -407,7 +408,14 @@ bool shard_pack_record(const BamRec& r, Shard& s, std::string& err) {
         err = "read longer than 65535 bases / CIGAR ops: not a short-read record";
         return false;
     }
-    size_t body = 16 + 4 * (size_t)r.n_cigar + ((size_t)r.l_qseq + 1) / 2;
+    // 2 bits per base when the read is made of A/C/G/T only (nt16 codes 1,2,4,8)
+    bool two = s.two_bit && r.l_qseq > 0;
+    for (int32_t i = 0; two && i < (int32_t)r.l_qseq; i++) {
+        uint32_t c = (r.seq[i >> 1] >> ((~i & 1) << 2)) & 0xfu;
+        two = c == 1 || c == 2 || c == 4 || c == 8;
+    }
+    const size_t seq_bytes = two ? ((size_t)r.l_qseq + 3) / 4 : ((size_t)r.l_qseq + 1) / 2;
+    size_t body = 16 + 4 * (size_t)r.n_cigar + seq_bytes;
     size_t padded = (body + 15) & ~(size_t)15;
     size_t o = s.rec.size();
     if ((o + padded) / 16 > 0xffffffffull) { err = "shard record stream exceeds 64 GiB"; return false; }
@@ -415,14 +423,21 @@ bool shard_pack_record(const BamRec& r, Shard& s, std::string& err) {
     uint8_t* d = s.rec.data() + o;
     int32_t pos = r.pos; memcpy(d, &pos, 4);
     uint16_t flag = r.flag; memcpy(d + 4, &flag, 2);
-    d[6] = r.mapq; d[7] = 0;
+    d[6] = r.mapq; d[7] = two ? 1 : 0;
     int32_t isz = r.isize; memcpy(d + 8, &isz, 4);
     uint16_t lq = (uint16_t)r.l_qseq, nc = (uint16_t)r.n_cigar;
     memcpy(d + 12, &lq, 2); memcpy(d + 14, &nc, 2);
     memcpy(d + 16, r.cigar, 4 * (size_t)r.n_cigar);
-    memcpy(d + 16 + 4 * (size_t)r.n_cigar, r.seq, ((size_t)r.l_qseq + 1) / 2);
+    uint8_t* ds = d + 16 + 4 * (size_t)r.n_cigar;
+    if (!two) memcpy(ds, r.seq, seq_bytes);
+    else for (int32_t i = 0; i < (int32_t)r.l_qseq; i++) {
+        uint32_t c = (r.seq[i >> 1] >> ((~i & 1) << 2)) & 0xfu;
+        uint32_t v = c == 1 ? 0u : c == 2 ? 1u : c == 4 ? 2u : 3u;
+        ds[i >> 2] |= (uint8_t)(v << (6 - 2 * (i & 3)));
+    }
     s.rec_off.push_back((uint32_t)((o + padded) / 16));
-    s.alg_bytes += (int64_t)body;
+    // algorithmic bytes are defined on the 4-bit form, whatever encoding is shipped
+    s.alg_bytes += (int64_t)(16 + 4 * (size_t)r.n_cigar + ((size_t)r.l_qseq + 1) / 2);
     if (s.with_qual) {
         bool keep = true;
         if (s.qual_mode == 2) {

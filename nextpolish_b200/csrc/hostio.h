@@ -6,6 +6,7 @@
 // Only the iteration ORDER of htslib matters to the algorithm (first-seen tie-breaks):
 // records of one contig are delivered in file order, which is what this reader does.
 #pragma once
+#include <stdlib.h>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -87,6 +88,8 @@ struct Shard {
     // (the only reads whose qualities task 2 can consult: every k-mer window contains a lowercase column
     // and its candidates span the whole window, kmercount.c:128-173,196-199; contig.c:1027)
     int qual_mode = 0;
+    // bases of A/C/G/T-only reads are packed with 2 bits each unless NEXTPOLISH_B200_4BIT=1 (A/B tests)
+    bool two_bit = !(getenv("NEXTPOLISH_B200_4BIT") && getenv("NEXTPOLISH_B200_4BIT")[0] == '1');
     std::vector<int32_t> cur_lc;        // lowercase prefix counts of the contig being packed (mode 2)
     void begin_contig(const uint8_t* seq, size_t len);
     void view(np_shard_view* v) const;

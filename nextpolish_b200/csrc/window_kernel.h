@@ -104,7 +104,7 @@ struct WCtx {             // per-window context: globals + carved shared memory
     uint32_t *ev_s, *ev_m; uint16_t* ev_r;    // parked chunks (see ph_compare): symbols, meta word, read index
     uint2* runs;                              // [nr][RUNCAP] pre-walked runs: .x = lc | len << 16, .y = first query index or -1
     uint32_t* refw;                           // draft symbol words (8 columns per word, big-endian nibbles)
-    uint32_t* acc;                            // same layout: bit 0 of a nibble set = some read disagrees at that column
+    uint32_t* acc;                            // same layout as refw: bit 0 of a nibble set = some read disagrees at that column
     int32_t* cov;                             // [ncols+1] +1/-1 at string ends, then (scan) reads voting on each column
     uint8_t* colinfo;                         // per local column: 1 mism, 2 covered
     int16_t* tabidx;                          // per local column: table index or -1
@@ -225,6 +225,18 @@ NP_HD uint32_t fsl(uint32_t hi, uint32_t lo, uint32_t nib) {   // 8 nibbles star
 #else
     return nib == 0 ? hi : (hi << (nib * 4)) | (lo >> (32 - nib * 4));
 #endif
+}
+
+// 8 bases of a 2-bit read (16 bits, first base in the two highest bits) -> 8 nt16 nibbles (1 << v), first base
+// in the highest nibble
+NP_HD uint32_t expand2(uint32_t v16) {
+    uint32_t t = v16 & 0xffffu;
+    t = (t | (t << 8)) & 0x00ff00ffu;
+    t = (t | (t << 4)) & 0x0f0f0f0fu;
+    t = (t | (t << 2)) & 0x33333333u;                       // one 2-bit value per nibble
+    const uint32_t hi = (t >> 1) & 0x11111111u, mh = hi * 0xfu;
+    const uint32_t r = 0x11111111u + (t & 0x11111111u);     // 1 or 2
+    return (r & ~mh) | ((r << 2) & mh);                     // x4 where the high bit was set
 }
 
 // ---- phase 0: clear + draft symbols --------------------------------------------------------------
@@ -406,6 +418,7 @@ NP_HD void ph_compare(WCtx& x, int32_t tid, int32_t nt, B& be) {
         const uint8_t* p = x.rec + (size_t)(x.recoff[i] - x.recoff[0]) * 16;
         const uint32_t hd = ((const uint32_t*)p)[3];
         const int32_t n_cigar = (int32_t)(hd >> 16);
+        const bool two = (((const uint32_t*)p)[1] >> 24) != 0u;           // 2 bits per base
         const uint32_t* sw = (const uint32_t*)(p + 16 + 4 * (size_t)n_cigar);   // bases, 4-byte aligned
         Walk w;
         w.cigar = (const uint32_t*)p + 4; w.n_cigar = n_cigar; w.ci = 0;
@@ -434,12 +447,20 @@ NP_HD void ph_compare(WCtx& x, int32_t tid, int32_t nt, B& be) {
             const uint32_t m = 0xffffffffu << (32 - 4 * take);
             uint32_t S = 0x33333333u;                     // SYM_GAP x 8
             if (q >= 0) {
-                const int32_t si = q >> 3, sn = q & 7;
+                // `cur` = big-endian word holding base q (8 bases per word, or 16 for 2-bit reads)
+                const int32_t sh = two ? 4 : 3, per = 1 << sh;
+                const int32_t si = q >> sh, sn = q & (per - 1);
                 if (si != cur_si) { cur = bswap32(sw[si]); cur_si = si; }
                 uint32_t lo = 0u;
-                if (sn + take > 8) lo = bswap32(sw[si + 1]);
-                S = fsl(cur, lo, (uint32_t)sn);
-                if (sn + take > 8) { cur = lo; cur_si = si + 1; }
+                if (sn + take > per) lo = bswap32(sw[si + 1]);
+                if (two) {
+#ifdef __CUDA_ARCH__
+                    S = expand2(__funnelshift_l(lo, cur, 2u * (uint32_t)sn) >> 16);
+#else
+                    S = expand2((uint32_t)(((((unsigned long long)cur) << 32 | lo) << (2 * sn)) >> 48));
+#endif
+                } else S = fsl(cur, lo, (uint32_t)sn);
+                if (sn + take > per) { cur = lo; cur_si = si + 1; }
                 q += take;
             }
             S &= m;

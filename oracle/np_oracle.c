@@ -65,7 +65,7 @@ typedef struct {                                             /* base.h:40-48 */
 } Col;
 
 typedef struct {
-    int32_t pos; uint16_t flag; uint8_t mapq; int32_t isize; int32_t l_qseq; int32_t n_cigar;
+    int32_t pos; uint16_t flag; uint8_t mapq, enc; int32_t isize; int32_t l_qseq; int32_t n_cigar;
     const uint32_t* cigar; const uint8_t* seq; const uint8_t* qual;
 } Rd;
 
@@ -87,6 +87,8 @@ static void il_push(IList* l, int32_t x)
 }
 
 static inline uint8_t seqi(const uint8_t* s, int32_t i) { return (s[i >> 1] >> ((~i & 1) << 2)) & 0xf; }
+/* packed-shard base i as an nt16 code: enc 0 = BAM 4-bit, enc 1 = 2 bits per base (include/nextpolish_b200.h) */
+#define rdseq(rd, i) ((rd)->enc ? (uint8_t)(1u << (((rd)->seq[(i) >> 2] >> (6 - 2 * ((i) & 3))) & 3u)) : seqi((rd)->seq, (i)))
 static inline int cig_op(uint32_t c) { return (int)(c & 0xf); }
 static inline int32_t cig_len(uint32_t c) { return (int32_t)(c >> 4); }
 
@@ -97,6 +99,7 @@ static void get_read(const np_shard_view* v, int64_t r, Rd* rd)
     memcpy(&rd->pos, p, 4);
     memcpy(&rd->flag, p + 4, 2);
     rd->mapq = p[6];
+    rd->enc = p[7];
     memcpy(&rd->isize, p + 8, 4);
     memcpy(&u16, p + 12, 2); rd->l_qseq = u16;
     memcpy(&u16, p + 14, 2); rd->n_cigar = u16;
@@ -152,8 +155,8 @@ static void cut_read(const Ctg* g, const Rd* rd, int32_t* qstart, int32_t* qend)
     if (cig_op(rd->cigar[rd->n_cigar - 1]) == BAM_CSOFT_CLIP) addlen = cig_len(rd->cigar[rd->n_cigar - 1]);
     *qend = rd->l_qseq - trim - addlen - 1;
     if (trim > 0) {
-        while (*qstart < rd->l_qseq && *qstart >= 1 && seqi(rd->seq, *qstart) == seqi(rd->seq, *qstart - 1)) (*qstart)++;
-        while (*qend >= 0 && *qend + 1 < rd->l_qseq && seqi(rd->seq, *qend) == seqi(rd->seq, *qend + 1)) (*qend)--;
+        while (*qstart < rd->l_qseq && *qstart >= 1 && rdseq(rd, *qstart) == rdseq(rd, *qstart - 1)) (*qstart)++;
+        while (*qend >= 0 && *qend + 1 < rd->l_qseq && rdseq(rd, *qend) == rdseq(rd, *qend + 1)) (*qend)--;
     }
 }
 
@@ -312,7 +315,7 @@ static void parse_read(Ctg* g, const Rd* rd, int32_t start, int32_t end)
                         for (k = 0; k < n; k++) { kmer = left_kmer(kmer, BASE_DEL); col_add(&g->col[g->colbase[pos - 1] + 1 + k], kmer); }
                     }
                     if (cur == BAM_CDEL) kmer = left_kmer(kmer, BASE_DEL);
-                    else kmer = left_kmer(kmer, seqi(rd->seq, qpos));
+                    else kmer = left_kmer(kmer, rdseq(rd, qpos));
                     col_add(&g->col[g->colbase[pos]], kmer);
                 }
                 if (cur != BAM_CDEL) qpos++;
@@ -325,7 +328,7 @@ static void parse_read(Ctg* g, const Rd* rd, int32_t start, int32_t end)
                 for (j = 0; j < len; j++, qpos++) {
                     if (pos > start && pos <= end && qpos >= qstart && qpos <= qend) {
                         if (j >= n) { fprintf(stderr, "oracle: insertion longer than its sub-columns\n"); exit(2); }
-                        kmer = left_kmer(kmer, seqi(rd->seq, qpos));
+                        kmer = left_kmer(kmer, rdseq(rd, qpos));
                         col_add(&g->col[g->colbase[pos - 1] + 1 + j], kmer);
                     }
                 }
@@ -583,7 +586,7 @@ static void parse_read_kmer(Ctg* g, const Rd* rd, int32_t start, int32_t end, KS
                         }
                     }
                     if (cur == BAM_CDEL) KS_APPEND(BASE_DEL);
-                    else { KS_APPEND(seqi(rd->seq, qpos)); ks->qual += rd->qual[qpos]; }
+                    else { KS_APPEND(rdseq(rd, qpos)); ks->qual += rd->qual[qpos]; }
                     if (flagzero == 0) g->col[g->colbase[pos]].flag &= (uint8_t)~FLAG_ZERO;
                 }
                 if (cur != BAM_CDEL) qpos++;
@@ -596,7 +599,7 @@ static void parse_read_kmer(Ctg* g, const Rd* rd, int32_t start, int32_t end, KS
                 for (j = 0; j < len; j++, qpos++) {
                     if (pos > start && pos <= end && qpos >= qstart && qpos <= qend) {
                         if (j >= n) { fprintf(stderr, "oracle: insertion longer than its sub-columns (kmer)\n"); exit(2); }
-                        KS_APPEND(seqi(rd->seq, qpos)); ks->qual += rd->qual[qpos];
+                        KS_APPEND(rdseq(rd, qpos)); ks->qual += rd->qual[qpos];
                         if (flagzero == 0) g->col[g->colbase[pos - 1] + 1 + j].flag &= (uint8_t)~FLAG_ZERO;
                     }
                 }

@@ -146,3 +146,27 @@ def test_emulated_edge_shapes(E, oracle, emu, kw):
         want = run_checker(oracle.np_oracle_run, sh, task, cfg)
         assert run_checker(emu.np_emu_run, sh, task, cfg, (None,)) == want, task
     assert run_checker(emu.np_emu_run_impl, sh, 1, cfg, (None, 2)) == run_checker(oracle.np_oracle_run, sh, 1, cfg)
+
+
+def test_two_bit_and_four_bit_records_polish_identically(E, oracle, emu, monkeypatch):
+    """The packer ships A/C/G/T-only reads with 2 bits per base (include/nextpolish_b200.h); forcing the 4-bit
+    form must change the record stream but not a single polished base (oracle, general kernels, window kernel)."""
+    emu.np_emu_run_impl.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    emu.np_emu_run_impl.restype = C.c_int
+    kw = dict(seed=123, n_contigs=2, contig_len=30000, depth=30.0, draft_indel=0.01, lowercase_frac=0.02)
+    two = E.Shard.synthetic(E.synth_params(**kw), 0, 2, with_qual=True)
+    monkeypatch.setenv("NEXTPOLISH_B200_4BIT", "1")
+    four = E.Shard.synthetic(E.synth_params(**kw), 0, 2, with_qual=True)
+    monkeypatch.delenv("NEXTPOLISH_B200_4BIT")
+    assert len(two.arrays()["rec"]) < 0.75 * len(four.arrays()["rec"])
+    assert two.algorithmic_bytes(1) == four.algorithmic_bytes(1)          # defined on the 4-bit form
+    cfg = E.default_config(b"")
+    cfg.contents.read_tlen = 1750
+    for task in (1, 2):
+        want = run_checker(oracle.np_oracle_run, four, task, cfg)
+        assert run_checker(oracle.np_oracle_run, two, task, cfg) == want
+        assert run_checker(emu.np_emu_run, two, task, cfg, (None,)) == want
+        assert run_checker(emu.np_emu_run, four, task, cfg, (None,)) == want
+    want = run_checker(oracle.np_oracle_run, four, 1, cfg)
+    assert run_checker(emu.np_emu_run_impl, two, 1, cfg, (None, 2)) == want
+    assert run_checker(emu.np_emu_run_impl, four, 1, cfg, (None, 2)) == want

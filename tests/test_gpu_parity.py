@@ -256,6 +256,22 @@ def test_streaming_front_end_equals_resident_path(E, eng, depth):
     st.close()
 
 
+def test_gpu_two_bit_and_four_bit_records(E, oracle, eng, monkeypatch):
+    """2-bit (default) and 4-bit record streams polish identically on the device, both tasks."""
+    kw = dict(seed=124, n_contigs=3, contig_len=120000, depth=30.0, draft_indel=0.01, lowercase_frac=0.01)
+    two = E.Shard.synthetic(E.synth_params(**kw), 0, 3, with_qual=2)
+    monkeypatch.setenv("NEXTPOLISH_B200_4BIT", "1")
+    four = E.Shard.synthetic(E.synth_params(**kw), 0, 3, with_qual=2)
+    monkeypatch.delenv("NEXTPOLISH_B200_4BIT")
+    assert len(two.arrays()["rec"]) < 0.75 * len(four.arrays()["rec"])
+    cfg = E.default_config(b"")
+    cfg.contents.read_tlen = 1750
+    for task in tasks(E):
+        want = run_checker(oracle.np_oracle_run, four, task, cfg)
+        assert eng.polish(two, task, cfg) == want, task
+        assert eng.polish(four, task, cfg) == want, task
+
+
 @pytest.mark.parametrize("rate", [0.33, 0.7])
 def test_gpu_non_dyadic_rate(E, oracle, eng, rate):
     sh = E.Shard.synthetic(E.synth_params(seed=92, n_contigs=3, contig_len=60000, depth=40.0, draft_indel=0.01, read_sub=0.01,
