@@ -260,18 +260,37 @@ def main():
     h2d = sum(sum(x.numel() * x.element_size() for x in pinned[t][0].values()) for t in tasks)
     cap = int(max(shards[t][0].total_bases for t in tasks) * 1.25) + 4096
     estream = torch.cuda.ExternalStream(eng.stream(), device=dev)
-    gather_buf = torch.empty(cap, dtype=torch.uint8, device=dev)
-
     from nextpolish_b200.sharding import FixedGather
-    fixed_gather = FixedGather(cap, dev) if world > 1 else None
+    GSLOTS = 2
+    HDR = FixedGather.HEADER
+    fixed_gather = FixedGather(cap, dev, slots=GSLOTS) if world > 1 else None
+    gbufs = [torch.zeros(cap + HDR, dtype=torch.uint8, device=dev) for _ in range(GSLOTS)]
+    ghdr = [torch.zeros(HDR, dtype=torch.uint8).pin_memory() for _ in range(GSLOTS)]
+    gready = [torch.cuda.Event() for _ in range(GSLOTS)]
+    gdone = [None] * GSLOTS
+    gstate = {"job": 0}
 
     def gather_fasta():
-        """The single collective of the path: corrected FASTA bytes of every rank -> rank 0 (NCCL)."""
-        n = eng.result_bytes()
-        E.lib().np_engine_copy_result(eng.h, gather_buf.data_ptr(), cap)
-        eng.sync()
+        """The single collective of the path: corrected FASTA bytes of every rank -> rank 0 (one NCCL gather per
+        task step; byte count in the buffer header).  Stream-ordered and double-buffered: the gather of one step
+        runs on torch's NCCL stream while the engine stream already computes the next step; no host sync."""
+        j = gstate["job"] % GSLOTS
+        gstate["job"] += 1
+        b = gbufs[j]
+        with torch.cuda.stream(estream):
+            if gdone[j] is not None:
+                estream.wait_event(gdone[j])                 # the gather that last read this buffer is over
+            ghdr[j].view(torch.int64)[0] = int(eng.result_bytes())
+            b[:HDR].copy_(ghdr[j], non_blocking=True)
+            E.lib().np_engine_copy_result(eng.h, b.data_ptr() + HDR, cap)
+            gready[j].record(estream)
         if world > 1:
-            fixed_gather(gather_buf, n)
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(gready[j])
+            fixed_gather(b, slot=j)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            gdone[j] = ev
 
     def step_resident(i):
         for t in tasks:
@@ -318,7 +337,7 @@ def main():
             fn(i)
         if flush:
             flush()                                            # every job finished and read back (host-synchronised)
-        estream.wait_stream(torch.cuda.current_stream(dev))   # orders the NCCL gather before e1
+        estream.wait_stream(torch.cuda.current_stream(dev))   # orders the (asynchronous) NCCL gathers before e1
         with torch.cuda.stream(estream):
             e1.record()
         barrier()
@@ -352,10 +371,21 @@ def main():
     if sampler:
         sampler.stop_flag = True
         sampler.join()
-    if rank != 0:
+    def teardown():
+        """Ordered shutdown: engines (their CUDA streams) go before the interpreter tears torch's context down;
+        the process then leaves through os._exit so that no destructor runs against a half-dead CUDA runtime."""
+        torch.cuda.synchronize()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
-        return
+        pipe.close()
+        eng.close()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+    if rank != 0:
+        teardown()
     d2h = state["d2h"]
     total_bp = bp_step * world
     value = total_bp * args.steps / (ms_res / 1e3) / 1e6
@@ -393,8 +423,7 @@ def main():
         base["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": sample,
                                 "host_cpus": os.cpu_count()}
     print(json.dumps(base))
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 if __name__ == "__main__":

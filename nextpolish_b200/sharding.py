@@ -40,25 +40,40 @@ def gather_bytes(local, dst=0, group=None):
 
 
 class FixedGather:
-    """The same collective with buffers allocated once and no host synchronisation in the hot loop:
-    every rank contributes a capacity-sized buffer plus its byte count; rank `dst` slices afterwards."""
+    """The same collective with buffers allocated once, ONE gather per call and no host synchronisation in the
+    hot loop: every rank contributes a capacity-sized buffer whose first HEADER bytes hold its byte count
+    (little-endian int64) and whose payload follows; rank `dst` slices afterwards.  `slots` rotating receive
+    sets let a gather stay in flight while the next step is being computed."""
+    HEADER = 16
 
-    def __init__(self, cap, device, dst=0, group=None):
+    def __init__(self, cap, device, dst=0, group=None, slots=1):
         self.cap, self.dst, self.group = cap, dst, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.n = torch.zeros(1, dtype=torch.int64, device=device)
         root = self.rank == dst
-        self.sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(self.world)] if root else None
-        self.bufs = [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(self.world)] if root else None
+        self.bufs = [[torch.empty(cap + self.HEADER, dtype=torch.uint8, device=device) for _ in range(self.world)]
+                     for _ in range(slots)] if root else None
+        self.last = 0
 
-    def __call__(self, buf, n):
-        """buf: uint8 tensor of exactly `cap` elements holding n valid bytes."""
-        self.n.fill_(n)
-        dist.gather(self.n, self.sizes, dst=self.dst, group=self.group)
-        dist.gather(buf, self.bufs, dst=self.dst, group=self.group)
+    def send_buffer(self, device):
+        """A buffer of the right size for __call__ (header + cap payload bytes)."""
+        return torch.zeros(self.cap + self.HEADER, dtype=torch.uint8, device=device)
 
-    def result(self):
+    @staticmethod
+    def set_count(buf, n):
+        """Writes the byte count into the header (host-side helper for CPU tensors / small jobs)."""
+        buf[:8] = torch.tensor([n], dtype=torch.int64).view(torch.uint8).to(buf.device)
+
+    def __call__(self, buf, slot=0, async_op=False):
+        """buf: uint8 tensor of cap + HEADER elements (header already filled)."""
+        self.last = slot
+        return dist.gather(buf, self.bufs[slot] if self.bufs else None, dst=self.dst, group=self.group, async_op=async_op)
+
+    def result(self, slot=None):
         """On dst: list of per-rank byte tensors of the last call (synchronises)."""
         if self.rank != self.dst:
             return None
-        return [b[:int(s.item())] for b, s in zip(self.bufs, self.sizes)]
+        out = []
+        for b in self.bufs[self.last if slot is None else slot]:
+            n = int(b[:8].cpu().view(torch.int64).item())
+            out.append(b[self.HEADER:self.HEADER + n])
+        return out

@@ -49,10 +49,11 @@ def _worker(rank, world, port, q):
     local = torch.from_numpy(np.concatenate(pieces) if pieces else np.zeros(0, np.uint8))
     got = gather_bytes(local, dst=0)
     from nextpolish_b200.sharding import FixedGather
-    fg = FixedGather(200000, torch.device("cpu"))
-    buf = torch.zeros(200000, dtype=torch.uint8)
-    buf[:local.numel()] = local
-    fg(buf, local.numel())
+    fg = FixedGather(200000, torch.device("cpu"), slots=2)
+    buf = fg.send_buffer(torch.device("cpu"))
+    buf[fg.HEADER:fg.HEADER + local.numel()] = local
+    fg.set_count(buf, local.numel())
+    fg(buf, slot=1)
     got2 = fg.result()
     if rank == 0:
         assert all(bytes(a.numpy()) == bytes(b.numpy()) for a, b in zip(got, got2))
