@@ -231,6 +231,16 @@ int32_t    np_stream_wait(np_stream* s, int64_t ticket);
 int64_t    np_stream_launch_count(np_stream* s);   /* kernel launches of every finished job */
 
 
+/* ---- GPU inflate of BGZF (replaces htslib bgzf.c -> zlib inflate on the host, the step
+ * immediately before the polishing path: contig.c:170-180,688-704 decode the BAM region twice per contig) ----
+ * Inflates a BGZF byte range (concatenated blocks: a whole BAM file or one contig's chunk) with one warp per
+ * block: headers are parsed on the host, compressed bytes go to HBM, the inflated bytes come back.
+ * out == NULL: size query (out_bytes, n_blocks only).  kernel_ms (optional): device time of the kernel alone.
+ * CRC32 of the blocks is not verified on the device (ISIZE is). */
+int32_t np_bgzf_inflate(int32_t device, const uint8_t* comp, int64_t comp_bytes, uint8_t* out, int64_t out_cap,
+                        int64_t* out_bytes, int32_t* n_blocks, float* kernel_ms);
+
+
 /* ---- seeded synthetic inputs (draft FASTA + coordinate-sorted BAM), for bench and tests -- */
 typedef struct {
     uint64_t seed;

@@ -67,6 +67,7 @@ EXPORTS = [  # every symbol include/nextpolish_b200.h declares
     "np_engine_run", "np_engine_sync", "np_engine_result_bytes", "np_engine_download",
     "np_engine_result_device", "np_engine_copy_result", "np_engine_kernel_times", "np_engine_set_timing", "np_engine_launch_count", "np_engine_window_stats", "np_engine_stream",
     "np_polish_host", "np_synth_write", "np_synth_shard",
+    "np_bgzf_inflate",
     "np_stream_create", "np_stream_destroy", "np_stream_submit", "np_stream_wait", "np_stream_launch_count",
 ]
 
@@ -117,6 +118,7 @@ def load(path=None):
     L.np_engine_stream.argtypes = [vp]
     L.np_engine_stream.restype = vp
     L.np_polish_host.argtypes = [vp, i32, C.POINTER(ShardView), C.POINTER(Configure), vp, i64, vp]
+    L.np_bgzf_inflate.argtypes = [i32, vp, i64, vp, i64, vp, vp, vp]
     L.np_stream_create.argtypes = [i32, i32]
     L.np_stream_create.restype = vp
     L.np_stream_destroy.argtypes = [vp]

@@ -8,6 +8,7 @@
 // (gpos = ctg_goff[k] + pos) and one global column space (a column is a reference position or
 // an insertion sub-column behind it, in contig_data_next order, contig.c:385-399).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)

@@ -265,6 +265,29 @@ static inline uint16_t rd_u16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); 
 
 }  // namespace
 
+bool bgzf_scan(const uint8_t* data, size_t size, std::vector<npz::Block>& blocks, int64_t& total, std::string& err) {
+    blocks.clear();
+    total = 0;
+    size_t coff = 0;
+    while (coff < size) {
+        BlockDesc b;
+        if (!bgzf_block_at(data, size, coff, b)) { err = "corrupt BGZF block header at offset " + std::to_string(coff); return false; }
+        const uint8_t* p = data + coff;
+        uint32_t xlen = p[10] | (p[11] << 8);
+        size_t hdr = 12 + xlen;
+        if (b.csize < hdr + 8) { err = "BGZF block shorter than its header"; return false; }
+        npz::Block o;
+        o.in_off = coff + hdr;
+        o.in_len = (uint32_t)(b.csize - hdr - 8);
+        o.out_len = (uint32_t)b.isize;
+        o.out_off = (uint64_t)total;
+        blocks.push_back(o);
+        total += (int64_t)b.isize;
+        coff += b.csize;
+    }
+    return true;
+}
+
 BamFile::~BamFile() {
     if (data_) munmap(const_cast<uint8_t*>(data_), size_);
     if (fd_ >= 0) close(fd_);

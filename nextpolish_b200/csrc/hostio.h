@@ -6,6 +6,7 @@
 // Only the iteration ORDER of htslib matters to the algorithm (first-seen tie-breaks):
 // records of one contig are delivered in file order, which is what this reader does.
 #pragma once
+#include "bgzf_inflate.h"
 #include <stdlib.h>
 #include <cstdint>
 #include <string>
@@ -101,6 +102,10 @@ bool synth_shard(const np_synth_params& P, int32_t lo, int32_t hi, int with_qual
 bool shard_load(const std::string& fasta, const std::string& bam,
                 const std::vector<std::string>& names, int with_qual, int threads,
                 Shard& out, std::string& err);
+
+// Walks the BGZF blocks of a byte range: deflate payload location and output placement of every block
+// (for np_bgzf_inflate, bgzf_inflate.cu); total = sum of the blocks' ISIZE.
+bool bgzf_scan(const uint8_t* data, size_t size, std::vector<npz::Block>& blocks, int64_t& total, std::string& err);
 
 // config.c:80-101 (bam_tlen): mean insert size estimate over the head of the BAM.
 bool bam_insert_estimate(const std::string& bam, uint32_t count_read_ins, uint32_t max_ins_len,

@@ -70,11 +70,15 @@ def emu():
             os.path.join(ROOT, "nextpolish_b200", "csrc", "engine_v2.h"),
             os.path.join(ROOT, "nextpolish_b200", "csrc", "window_kernel.h"),
             os.path.join(ROOT, "nextpolish_b200", "csrc", "device_logic.h")]
+    extra = [os.path.join(ROOT, "tests", "emu", "emu_bgzf.cpp"), os.path.join(ROOT, "nextpolish_b200", "csrc", "hostio.cpp")]
+    srcs += extra + [os.path.join(ROOT, "nextpolish_b200", "csrc", "bgzf_inflate.h"), os.path.join(ROOT, "nextpolish_b200", "csrc", "hostio.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]] + extra + ["-lz", "-lpthread"])
     L = C.CDLL(so)
     L.np_emu_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.np_emu_run.restype = C.c_int
+    L.np_emu_bgzf_inflate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.np_emu_bgzf_inflate.restype = C.c_int
     return L
 
 

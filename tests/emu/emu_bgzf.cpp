@@ -1,0 +1,38 @@
+// emu_bgzf.cpp — TEST BUILD ONLY.  Runs the warp inflate of bgzf_inflate.h with a one-lane backend on the CPU so
+// that the decoder (the same source nvcc compiles into k_bgzf_inflate) can be compared with zlib without a GPU.
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../nextpolish_b200/csrc/bgzf_inflate.h"
+#include "../../nextpolish_b200/csrc/hostio.h"
+
+namespace {
+struct OneLane {
+    int32_t lane() const { return 0; }
+    int32_t width() const { return 1; }
+    int32_t bcast(int32_t v) const { return v; }
+    void sync() const {}
+};
+}  // namespace
+
+extern "C" int np_emu_bgzf_inflate(const uint8_t* comp, int64_t comp_bytes, uint8_t* out, int64_t out_cap, int64_t* out_bytes,
+                                   int32_t* n_blocks) {
+    std::vector<npz::Block> blocks;
+    std::string err;
+    int64_t total = 0;
+    if (!np::bgzf_scan(comp, (size_t)comp_bytes, blocks, total, err)) return -100;
+    *out_bytes = total;
+    if (n_blocks) *n_blocks = (int32_t)blocks.size();
+    if (!out) return 0;
+    if (out_cap < total) return -101;
+    npz::Tables t;
+    OneLane w;
+    for (size_t i = 0; i < blocks.size(); i++) {
+        const npz::Block& b = blocks[i];
+        if (!b.out_len) continue;
+        memset(&t, 0xA5, sizeof t);                       // poison: the decoder must initialise what it reads
+        int rc = npz::inflate_block(comp + b.in_off, b.in_len, out + b.out_off, b.out_len, t, w);
+        if (rc != npz::OK) return rc;
+    }
+    return 0;
+}
