@@ -18,6 +18,7 @@
 
 #include "engine_task2.h"
 #include "engine_v2.h"
+#include "engine_v3.h"
 #include "errors.h"
 #include "hostio.h"
 #include "../../include/nextpolish_b200.h"
@@ -214,6 +215,7 @@ struct CudaBackend {
         return (T*)b.p;
     }
     void zero(void* p, size_t bytes) { if (ok && p) CUDA_TRY(cudaMemsetAsync(p, 0, bytes, stream)); }
+    void fill_ff(void* p, size_t bytes) { if (ok && p) CUDA_TRY(cudaMemsetAsync(p, 0xff, bytes, stream)); }
     void begin_timed(const char* name) {
         if (!timing) return;
         if (n_timed == timed.size()) {
@@ -533,7 +535,9 @@ int32_t np_engine_run(np_engine* e, int32_t task, const Configure* cfg) {
     int err;
     if (task == NP_TASK_SCORE_CHAIN) {
         const char* v1 = getenv("NEXTPOLISH_B200_GENERAL_KERNELS");     // debugging / A-B timing only
+        const char* v3 = getenv("NEXTPOLISH_B200_V3");                     // A/B: window-less kernel chain (engine_v3.h)
         if (v1 && v1[0] == '1') err = npe::run_score_chain(e->be, e->d, &e->st, !npe::rate_is_dyadic(e->d.P.rate));
+        else if (v3 && v3[0] == '1') err = npe::run_score_chain_v3(e->be, e->d, &e->st);
         else err = npe::run_score_chain_v2(e->be, e->d, e->h_ctg_off.data(), &e->st, &e->vs);
     }
     else if (task == NP_TASK_KMER_COUNT) {

@@ -294,12 +294,15 @@ struct Walk {
     int32_t plc, plen, pq;                    // pending second run of the current op (plen > 0)
     int32_t next; bool started, done;         // contiguity check, walk finished
 };
-NP_HD void walk_op_done(const WCtx& x, Walk& w) {
+template <class X>
+NP_HD void walk_op_done(const X& x, Walk& w) {
     w.ci++;
     if (w.pos > x.ge || w.pos > x.e1 + 1) w.done = true;
 }
-template <class B>
-NP_HD bool next_run(WCtx& x, Walk& w, int32_t& lc, int32_t& len, int32_t& q, B& be) {
+// X: a context with gs, ge, e0, e1, ncols, ctr[], d.err and an lcol(x, p) overload (the window's WCtx, or the
+// whole-contig context of engine_v3.h)
+template <class X, class B>
+NP_HD bool next_run(X& x, Walk& w, int32_t& lc, int32_t& len, int32_t& q, B& be) {
     (void)be;
     const int32_t start = x.gs, end = x.ge;
     for (;;) {

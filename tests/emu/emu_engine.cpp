@@ -11,6 +11,7 @@
 #include <vector>
 #include "../../nextpolish_b200/csrc/engine_task2.h"
 #include "../../nextpolish_b200/csrc/engine_v2.h"
+#include "../../nextpolish_b200/csrc/engine_v3.h"
 #include "../../include/nextpolish_b200.h"
 
 namespace {
@@ -34,6 +35,7 @@ struct EmuBackend {
         return (T*)v.data();
     }
     void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+    void fill_ff(void* p, size_t bytes) { memset(p, 0xff, bytes); }
     template <class F> void launch(const char*, int64_t n, const F& f) {
         EmuOps ops;
         for (int64_t i = 0; i < n; i++) f(i, ops);
@@ -93,7 +95,8 @@ extern "C" int np_emu_run(const np_shard_view* v, int task, const Configure* cfg
                           uint8_t* out_seq, int64_t out_cap, int64_t* out_off, int32_t* stats) {
     return np_emu_run_impl(v, task, cfg, out_seq, out_cap, out_off, stats, 1);
 }
-// variant 1: general kernels (engine_impl.h); variant 2: fused window kernel + fallback (engine_v2.h)
+// variant 1: general kernels (engine_impl.h); variant 2: fused window kernel + fallback (engine_v2.h);
+// variant 3: window-less chain of full-GPU kernels (engine_v3.h)
 extern "C" int np_emu_run_impl(const np_shard_view* v, int task, const Configure* cfg,
                           uint8_t* out_seq, int64_t out_cap, int64_t* out_off, int32_t* stats, int variant) {
     npe::Dev d;
@@ -112,7 +115,8 @@ extern "C" int np_emu_run_impl(const np_shard_view* v, int task, const Configure
     EmuBackend be;
     npe::RunStats st;
     npe::V2Stats vs; memset(&vs, 0, sizeof(vs));
-    int err = task == 1 ? (variant == 2 ? npe::run_score_chain_v2(be, d, v->ctg_off, &st, &vs) : npe::run_score_chain(be, d, &st))
+    int err = task == 1 ? (variant == 3 ? npe::run_score_chain_v3(be, d, &st)
+                           : variant == 2 ? npe::run_score_chain_v2(be, d, v->ctg_off, &st, &vs) : npe::run_score_chain(be, d, &st))
                         : npe::run_kmer_count(be, d, &st);
     if (err) return err > 0 ? -err : err;
     if (st.out_bytes > out_cap) return -1000;
