@@ -241,6 +241,28 @@ int32_t np_bgzf_inflate(int32_t device, const uint8_t* comp, int64_t comp_bytes,
                         int64_t* out_bytes, int32_t* n_blocks, float* kernel_ms);
 
 
+/* ---- device-side shard construction: FASTA + BAM (+ .bai) -> packed shard built in HBM ----
+ * Replaces np_shard_load's host inflate + packing (the reference's contig_init + bam_itr_queryi / sam_itr_next /
+ * bam_read1 loop, contig.c:32-79,170-180,688-704): the compressed byte range of the wanted contigs is copied to
+ * the GPU as it is on disk; BGZF inflate, record-boundary discovery (chains between the record starts the .bai
+ * index knows, each verified to land on the next one), field extraction and packing run as kernels.  The shard
+ * is byte-identical to np_shard_load's.  Needs <bam>.bai; returns NULL + np_last_error() otherwise (callers fall
+ * back to np_shard_load).  The view holds DEVICE pointers (ctg_off / ctg_read_off are host arrays): pass it to
+ * np_engine_adopt_device; it stays valid until np_dev_shard_free. */
+typedef struct np_dev_shard np_dev_shard;
+np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* bam, const char* const* names,
+                                int32_t n_names, int32_t with_qual);
+void        np_dev_shard_view(const np_dev_shard* shard, np_shard_view* out);
+const char* np_dev_shard_contig_name(const np_dev_shard* shard, int32_t i);
+int32_t     np_dev_shard_contig_rank(const np_dev_shard* shard, int32_t i);
+/* sizes5: {record bytes, quality bytes, draft bytes, compressed bytes shipped, inflated bytes}; ms2: {inflate kernel,
+ * whole load on the device} */
+void        np_dev_shard_stats(const np_dev_shard* shard, int64_t* sizes5, float* ms2);
+int32_t     np_dev_shard_download(const np_dev_shard* shard, uint8_t* ctg_seq, uint32_t* rec_off, uint8_t* rec,
+                                  uint32_t* qual_off, uint8_t* qual);
+void        np_dev_shard_free(np_dev_shard* shard);
+
+
 /* ---- seeded synthetic inputs (draft FASTA + coordinate-sorted BAM), for bench and tests -- */
 typedef struct {
     uint64_t seed;

@@ -62,6 +62,47 @@ static bool reserve(void** p, size_t* cap, size_t bytes) {
 
 }  // namespace
 
+namespace npz_dev {
+// Inflates `blocks` (payload offsets relative to comp_host) into d_out (device) on `stream`; synchronises the
+// stream and checks every block's status.  Used by np_bgzf_inflate's callers that keep the bytes in HBM
+// (devload.cu).
+int32_t inflate_to_device(const uint8_t* comp_host, size_t comp_bytes, const std::vector<npz::Block>& blocks, int64_t total,
+                          uint8_t* d_out, cudaStream_t stream, float* kernel_ms, std::string& err) {
+    (void)total;
+    const size_t nb = blocks.size();
+    if (nb == 0) return NP_OK;
+    void *d_comp = nullptr, *d_blocks = nullptr, *d_status = nullptr;
+    auto cleanup = [&]() { if (d_comp) cudaFreeAsync(d_comp, stream); if (d_blocks) cudaFreeAsync(d_blocks, stream); if (d_status) cudaFreeAsync(d_status, stream); };
+    if (cudaMallocAsync(&d_comp, comp_bytes + 16, stream) != cudaSuccess || cudaMallocAsync(&d_blocks, nb * sizeof(npz::Block), stream) != cudaSuccess ||
+        cudaMallocAsync(&d_status, (nb + 1) * 4, stream) != cudaSuccess) { cleanup(); err = "cudaMalloc failed"; return NP_ERR_CUDA; }
+    cudaMemcpyAsync(d_comp, comp_host, comp_bytes, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_blocks, blocks.data(), nb * sizeof(npz::Block), cudaMemcpyHostToDevice, stream);
+    cudaMemsetAsync(d_status, 0xff, nb * 4, stream);
+    cudaMemsetAsync((int32_t*)d_status + nb, 0, 4, stream);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int ctas = (int)((nb + kWarpsPerCta - 1) / kWarpsPerCta);
+    if (ctas > sms * 8) ctas = sms * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, stream);
+    k_bgzf_inflate<<<ctas, kWarpsPerCta * 32, 0, stream>>>((const uint8_t*)d_comp, (const npz::Block*)d_blocks, (int32_t)nb, d_out,
+                                                          (int32_t*)d_status, (int32_t*)d_status + nb);
+    cudaEventRecord(e1, stream);
+    std::vector<int32_t> st(nb);
+    cudaMemcpyAsync(st.data(), d_status, nb * 4, cudaMemcpyDeviceToHost, stream);
+    cudaError_t er = cudaStreamSynchronize(stream);
+    if (kernel_ms && er == cudaSuccess) cudaEventElapsedTime(kernel_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cleanup();
+    if (er != cudaSuccess) { err = cudaGetErrorString(er); return NP_ERR_CUDA; }
+    for (size_t i = 0; i < nb; i++)
+        if (st[i] != npz::OK) { err = "BGZF block " + std::to_string(i) + " failed with inflate error " + std::to_string(st[i]); return NP_ERR_IO; }
+    return NP_OK;
+}
+}  // namespace npz_dev
+
 extern "C" {
 
 // Inflates a whole BGZF byte range (concatenated blocks, e.g. a BAM file or the chunk of one contig) on the GPU:

@@ -40,26 +40,41 @@ int main(int argc, char* argv[]) {
     if (argc != 4) { printf("%s %s fastafn lgsbam\n", argv[0], argv[1]); return 0; }
     time_t t0 = time(nullptr);
     Configure* cfg = config_init(argv[2], argv[3], nullptr);
-    np_shard* sh = np_shard_load(argv[2], argv[3], nullptr, 0, step == 2 ? 2 : 0, 8);
-    if (!sh) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
-    np_shard_view v; np_shard_view_of(sh, &v);
-    np_engine* e = np_engine_create(getenv("NEXTPOLISH_B200_DEVICE") ? atoi(getenv("NEXTPOLISH_B200_DEVICE")) : 0);
+    const int dev = getenv("NEXTPOLISH_B200_DEVICE") ? atoi(getenv("NEXTPOLISH_B200_DEVICE")) : 0;
+    // the shard is built on the GPU (inflate + record unpack + packing, devload.cu) when the BAM has a .bai index;
+    // otherwise (or with NEXTPOLISH_B200_HOST_LOAD=1) the host packer builds it and it is uploaded
+    np_dev_shard* ds = nullptr;
+    np_shard* sh = nullptr;
+    const char* hl = getenv("NEXTPOLISH_B200_HOST_LOAD");
+    if (!(hl && hl[0] == '1')) ds = np_shard_load_gpu(dev, argv[2], argv[3], nullptr, 0, step == 2 ? 2 : 0);
+    np_shard_view v;
+    if (ds) np_dev_shard_view(ds, &v);
+    else {
+        sh = np_shard_load(argv[2], argv[3], nullptr, 0, step == 2 ? 2 : 0, 8);
+        if (!sh) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
+        np_shard_view_of(sh, &v);
+    }
+    np_engine* e = np_engine_create(dev);
     if (!e) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
-    if (np_engine_upload(e, &v) != NP_OK || np_engine_run(e, step, cfg) != NP_OK) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
+    if ((ds ? np_engine_adopt_device(e, &v) : np_engine_upload(e, &v)) != NP_OK || np_engine_run(e, step, cfg) != NP_OK) {
+        fprintf(stderr, "%s\n", np_last_error());
+        return 1;
+    }
     int64_t n = np_engine_result_bytes(e);
     std::vector<uint8_t> out((size_t)n + 1);
     std::vector<int64_t> off((size_t)v.n_contigs + 1);
     if (np_engine_download(e, out.data(), n + 1, off.data()) != NP_OK) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
     std::vector<int> slot_of_rank((size_t)v.n_contigs, -1);
-    for (int i = 0; i < v.n_contigs; i++) slot_of_rank[(size_t)np_shard_contig_rank(sh, i)] = i;
+    for (int i = 0; i < v.n_contigs; i++) slot_of_rank[(size_t)(ds ? np_dev_shard_contig_rank(ds, i) : np_shard_contig_rank(sh, i))] = i;
     for (int r = 0; r < v.n_contigs; r++) {
         int i = slot_of_rank[(size_t)r];
-        printf(">%s_%d\n", np_shard_contig_name(sh, i), step);
+        printf(">%s_%d\n", ds ? np_dev_shard_contig_name(ds, i) : np_shard_contig_name(sh, i), step);
         fwrite(out.data() + off[(size_t)i], 1, (size_t)(off[(size_t)i + 1] - off[(size_t)i]), stdout);
         fputc('\n', stdout);
     }
     np_engine_destroy(e);
-    np_shard_free(sh);
+    if (ds) np_dev_shard_free(ds);
+    if (sh) np_shard_free(sh);
     config_destory(cfg);
     fprintf(stderr, "total time:%lds\n", (long)(time(nullptr) - t0));
     return 0;

@@ -1,0 +1,449 @@
+// devload.cu — BAM bytes -> packed shard, built in HBM (second piece).
+//
+// The reference decodes the BAM on the host through htslib (bgzf.c inflate + bam_read1, contig.c:170-180 and
+// :688-704, twice per contig); our host packer (hostio.cpp) does the same work once and is the real-world
+// bottleneck (~2-3 Mbp/s against ~3000 Mbp/s for the polishing kernels).  Here the compressed byte range of the
+// wanted contigs goes to the GPU as it is on disk and everything else happens there:
+//
+//   k_bgzf_inflate   one warp per BGZF block                                            (bgzf_inflate.h)
+//   k_rec_count/index one thread per ANCHOR interval: record boundaries.  A BAM record only says how long it is,
+//                    so boundaries are a sequential chain; the .bai index knows a true record start for every
+//                    chunk and every 16 kb window (bai_record_starts), and every chain must land exactly on the
+//                    next anchor — a chain that starts on a true record start and is followed faithfully IS the
+//                    file's record sequence, so this is a proof, not a heuristic
+//   k_rec_meta       one thread per record: fields, contig slot, 2-bit / 4-bit decision, packed size, whether the
+//                    qualities are shipped (sparse mode: the span contains a lowercase draft base)
+//   scans            record / quality offsets (CUB)
+//   k_rec_pack       one thread per kept record: header, CIGAR, bases, qualities
+//
+// The result is byte-identical to the host packer's shard (tests/test_devload.py) and is adopted by the engine in
+// place (np_engine_adopt_device).
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "bgzf_inflate.h"
+#include "errors.h"
+#include "hostio.h"
+#include "../../include/nextpolish_b200.h"
+
+namespace npz_dev {   // bgzf_inflate.cu
+int32_t inflate_to_device(const uint8_t* comp_host, size_t comp_bytes, const std::vector<npz::Block>& blocks, int64_t total,
+                          uint8_t* d_out, cudaStream_t stream, float* kernel_ms, std::string& err);
+}
+
+namespace {
+
+__device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+__device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8; }
+
+enum { DL_ERR_CHAIN = 1, DL_ERR_RECORD = 2, DL_ERR_LONG = 4, DL_ERR_ORDER = 8 };
+
+// pass 0: count the records of every anchor interval; pass 1: write their offsets
+__global__ void k_rec_walk(const uint8_t* U, int64_t total, const int64_t* anchors, int32_t n_int, int32_t* cnt,
+                           const int32_t* base, int64_t* rec_start, int32_t* err) {
+    int32_t i = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n_int) return;
+    int64_t off = anchors[i];
+    const int64_t end = anchors[i + 1];
+    int32_t n = 0;
+    int64_t* out = rec_start ? rec_start + base[i] : nullptr;
+    while (off < end) {
+        if (off + 4 > total) { atomicOr(err, DL_ERR_CHAIN); break; }
+        uint32_t bs = ld32(U + off);
+        if (bs < 32u || off + 4 + (int64_t)bs > total) { atomicOr(err, DL_ERR_CHAIN); break; }
+        if (out) out[n] = off;
+        n++;
+        off += 4 + (int64_t)bs;
+    }
+    if (off != end) atomicOr(err, DL_ERR_CHAIN);
+    if (!rec_start) cnt[i] = n;
+}
+
+struct MetaArgs {
+    const uint8_t* U; const int64_t* rec_start; int32_t n_rec;
+    const int32_t* slot_of_tid; int32_t n_ref;
+    const int64_t* slot_goff;      // [n_slots + 1] offset of every slot's contig in the concatenated draft
+    const int32_t* lcpre;          // [G + 1] lowercase prefix counts of the draft (qual mode 2) or null
+    int32_t qual_mode, two_bit;
+    int32_t *keep, *units, *qunits, *slot; uint8_t* enc;
+    int32_t* err;
+};
+__global__ void k_rec_meta(MetaArgs a) {
+    int32_t r = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (r >= a.n_rec) return;
+    const uint8_t* p = a.U + a.rec_start[r];
+    const uint32_t bs = ld32(p);
+    p += 4;
+    const int32_t tid = (int32_t)ld32(p), pos = (int32_t)ld32(p + 4);
+    const uint32_t l_name = p[8], n_cigar = ld16(p + 12);
+    const int32_t l_seq = (int32_t)ld32(p + 16);
+    int32_t keep = 0, units = 0, qunits = 0, slot = -1; uint32_t enc = 0;
+    if (l_seq < 0 || 32ull + l_name + 4ull * n_cigar + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq > (uint64_t)bs) atomicOr(a.err, DL_ERR_RECORD);
+    else if (tid >= 0 && tid < a.n_ref && (slot = a.slot_of_tid[tid]) >= 0 && n_cigar > 0) {
+        keep = 1;
+        if (l_seq > 65535) atomicOr(a.err, DL_ERR_LONG);
+        const uint8_t* cig = p + 32 + l_name;
+        const uint8_t* seq = cig + 4 * n_cigar;
+        bool two = a.two_bit && l_seq > 0;
+        for (int32_t i = 0; two && i < l_seq; i++) {
+            uint32_t c = (seq[i >> 1] >> ((~i & 1) << 2)) & 0xfu;
+            two = c == 1 || c == 2 || c == 4 || c == 8;
+        }
+        enc = two ? 1u : 0u;
+        const uint32_t seq_bytes = two ? ((uint32_t)l_seq + 3) / 4 : ((uint32_t)l_seq + 1) / 2;
+        units = (int32_t)((16u + 4u * n_cigar + seq_bytes + 15u) / 16u);
+        bool kq = a.qual_mode == 1;
+        if (a.qual_mode == 2) {
+            int64_t end = pos;
+            for (uint32_t i = 0; i < n_cigar; i++) {
+                uint32_t c = ld32(cig + 4 * i), op = c & 0xfu;
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) end += c >> 4;
+            }
+            const int64_t g0 = a.slot_goff[slot], L = a.slot_goff[slot + 1] - g0;
+            const int64_t x = pos < 0 ? 0 : pos, y = end > L ? L : end;
+            kq = x < y && a.lcpre[g0 + y] - a.lcpre[g0 + x] > 0;
+        }
+        if (kq) qunits = (l_seq + 15) / 16;
+    }
+    if (r > 0 && keep) {     // coordinate-sorted input: contig slots never go backwards
+        const uint8_t* q = a.U + a.rec_start[r - 1] + 4;
+        const int32_t ptid = (int32_t)ld32(q);
+        if (ptid >= 0 && ptid < a.n_ref && a.slot_of_tid[ptid] > slot && ld16(q + 12) > 0) atomicOr(a.err, DL_ERR_ORDER);
+    }
+    a.keep[r] = keep; a.units[r] = units; a.qunits[r] = qunits; a.slot[r] = slot; a.enc[r] = (uint8_t)enc;
+}
+
+struct PackArgs {
+    const uint8_t* U; const int64_t* rec_start; int32_t n_rec;
+    const int32_t *keep, *kidx, *uoff, *quoff, *qunits, *slot; const uint8_t* enc;
+    uint32_t* rec_off; uint8_t* rec; uint32_t* qual_off; uint8_t* qual;
+    int32_t* slot_count; int32_t n_keep, total_units, total_qunits;
+};
+__global__ void k_rec_pack(PackArgs a) {
+    int32_t r = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (r == 0) {     // closing entries of the offset arrays
+        a.rec_off[a.n_keep] = (uint32_t)a.total_units;
+        if (a.qual_off) a.qual_off[a.n_keep] = (uint32_t)a.total_qunits;
+    }
+    if (r >= a.n_rec || !a.keep[r]) return;
+    const int32_t k = a.kidx[r];
+    const uint8_t* p = a.U + a.rec_start[r] + 4;
+    const uint32_t l_name = p[8], n_cigar = ld16(p + 12);
+    const int32_t l_seq = (int32_t)ld32(p + 16);
+    uint8_t* d = a.rec + (size_t)a.uoff[r] * 16;
+    a.rec_off[k] = (uint32_t)a.uoff[r];
+    // header: pos, flag, mapq, enc, isize, l_qseq, n_cigar (include/nextpolish_b200.h)
+    for (int i = 0; i < 4; i++) d[i] = p[4 + i];
+    d[4] = p[14]; d[5] = p[15]; d[6] = p[9]; d[7] = a.enc[r];
+    for (int i = 0; i < 4; i++) d[8 + i] = p[28 + i];
+    d[12] = (uint8_t)(l_seq & 0xff); d[13] = (uint8_t)(l_seq >> 8); d[14] = p[12]; d[15] = p[13];
+    const uint8_t* cig = p + 32 + l_name;
+    for (uint32_t i = 0; i < 4 * n_cigar; i++) d[16 + i] = cig[i];
+    const uint8_t* seq = cig + 4 * n_cigar;
+    uint8_t* ds = d + 16 + 4 * n_cigar;
+    if (!a.enc[r]) { for (int32_t i = 0; i < (l_seq + 1) / 2; i++) ds[i] = seq[i]; }
+    else {
+        for (int32_t b = 0; b < (l_seq + 3) / 4; b++) {
+            uint32_t o = 0;
+            for (int32_t j = 0; j < 4; j++) {
+                const int32_t i = 4 * b + j;
+                if (i >= l_seq) break;
+                const uint32_t c = (seq[i >> 1] >> ((~i & 1) << 2)) & 0xfu;
+                o |= (c == 1 ? 0u : c == 2 ? 1u : c == 4 ? 2u : 3u) << (6 - 2 * j);
+            }
+            ds[b] = (uint8_t)o;
+        }
+    }
+    if (a.qual_off) {
+        a.qual_off[k] = (uint32_t)a.quoff[r];
+        if (a.qunits[r]) {
+            const uint8_t* q = seq + (l_seq + 1) / 2;
+            uint8_t* dq = a.qual + (size_t)a.quoff[r] * 16;
+            for (int32_t i = 0; i < l_seq; i++) dq[i] = q[i];
+        }
+    }
+    atomicAdd(&a.slot_count[a.slot[r]], 1);
+}
+__global__ void k_lower_flags(const uint8_t* seq, int64_t n, int32_t* f) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f[i] = seq[i] >= 97 && seq[i] <= 122 ? 1 : 0; else if (i == n) f[i] = 0;
+}
+
+// Stream-ordered allocations from the device's default memory pool, whose release threshold is raised once so
+// that freed blocks stay cached: a load allocates ~20 buffers (276 MB of inflated bytes among them) and
+// cudaMalloc / cudaFree would cost more than the kernels.
+static cudaStream_t g_alloc_stream = nullptr;
+static void pool_setup(int device) {
+    static int done_for = -1;
+    if (done_for == device) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_for = device;
+}
+struct Dbuf {
+    void* p = nullptr;
+    ~Dbuf() { if (p) cudaFreeAsync(p, g_alloc_stream); }
+    bool alloc(size_t bytes) { return cudaMallocAsync(&p, bytes + 256, g_alloc_stream) == cudaSuccess; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+static bool exscan(const int32_t* in, int32_t* out, int n, cudaStream_t s) {
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, n, s);
+    Dbuf tmp;
+    if (!tmp.alloc(need)) return false;
+    cub::DeviceScan::ExclusiveSum(tmp.p, need, in, out, n, s);
+    return true;                   // tmp is freed in stream order
+}
+
+}  // namespace
+
+struct np_dev_shard {
+    int device = 0;
+    std::vector<std::string> names;
+    std::vector<int64_t> ctg_off, ctg_read_off;
+    std::vector<int32_t> fasta_rank;
+    Dbuf seq, rec_off, rec, qual_off, qual;
+    int64_t n_reads = 0, rec_bytes = 0, qual_bytes = 0, seq_bytes = 0;
+    bool with_qual = false;
+    float ms_inflate = 0, ms_total = 0;
+    int64_t comp_bytes = 0, inflated_bytes = 0;
+};
+
+extern "C" {
+
+void np_dev_shard_free(np_dev_shard* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (g_alloc_stream) cudaStreamSynchronize(g_alloc_stream);
+    delete s;
+}
+
+np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* bam, const char* const* names_in,
+                                int32_t n_names, int32_t with_qual) {
+    using namespace np;
+    if (!fasta || !bam) { set_error("np_shard_load_gpu: fasta / bam is NULL"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        set_error("np_shard_load_gpu: no usable CUDA device; this loader has no CPU path (use np_shard_load)");
+        return nullptr;
+    }
+    cudaSetDevice(device);
+    std::string err;
+    std::vector<std::string> names;
+    for (int32_t i = 0; i < n_names; i++) names.emplace_back(names_in[i]);
+    std::vector<FastaRecord> recs;
+    if (!fasta_load(fasta, names, recs, err)) { set_error("np_shard_load_gpu: " + err); return nullptr; }
+    BamFile bf;
+    if (!bf.open(bam, err)) { set_error("np_shard_load_gpu: " + err); return nullptr; }
+    std::vector<std::vector<uint64_t>> starts;
+    if (!bf.bai_record_starts(starts, err)) { set_error("np_shard_load_gpu: needs " + std::string(bam) + ".bai (" + err + ")"); return nullptr; }
+    const int32_t n_ref = (int32_t)bf.header().names.size();
+    starts.resize((size_t)n_ref);
+
+    // contigs in BAM tid order (those absent from the BAM header go last, with no reads) — as shard_load
+    std::unordered_map<std::string, int> tid_of;
+    for (int32_t i = 0; i < n_ref; i++) tid_of.emplace(bf.header().names[(size_t)i], i);
+    struct Slot { int tid; size_t rec_idx; };
+    std::vector<Slot> slots;
+    for (size_t i = 0; i < recs.size(); i++) {
+        auto it = tid_of.find(recs[i].name);
+        slots.push_back({it == tid_of.end() ? 0x7fffffff : it->second, i});
+    }
+    std::stable_sort(slots.begin(), slots.end(), [](const Slot& a, const Slot& b) { return a.tid < b.tid; });
+    np_dev_shard* S = new np_dev_shard();
+    S->device = device;
+    S->with_qual = with_qual != 0;
+    std::vector<uint8_t> ctg_seq;
+    std::vector<int32_t> slot_of_tid((size_t)std::max(1, n_ref), -1);
+    S->ctg_off.push_back(0);
+    int tid_min = 0x7fffffff, tid_max = -1;
+    for (size_t k = 0; k < slots.size(); k++) {
+        const FastaRecord& r = recs[slots[k].rec_idx];
+        S->names.push_back(r.name);
+        S->fasta_rank.push_back((int32_t)slots[k].rec_idx);
+        ctg_seq.insert(ctg_seq.end(), r.seq.begin(), r.seq.end());
+        S->ctg_off.push_back((int64_t)ctg_seq.size());
+        if (slots[k].tid != 0x7fffffff) {
+            if (slot_of_tid[(size_t)slots[k].tid] < 0) slot_of_tid[(size_t)slots[k].tid] = (int32_t)k;
+            tid_min = std::min(tid_min, slots[k].tid); tid_max = std::max(tid_max, slots[k].tid);
+        }
+    }
+    const int32_t n_slots = (int32_t)slots.size();
+    S->ctg_read_off.assign((size_t)n_slots + 1, 0);
+    S->seq_bytes = (int64_t)ctg_seq.size();
+    auto fail = [&](const std::string& m) { set_error("np_shard_load_gpu: " + m); np_dev_shard_free(S); return (np_dev_shard*)nullptr; };
+    pool_setup(device);
+    if (!g_alloc_stream) cudaStreamCreateWithFlags(&g_alloc_stream, cudaStreamNonBlocking);
+    cudaStream_t st = g_alloc_stream;      // one stream for allocations and work: stream-ordered reuse is safe
+    if (!S->seq.alloc(ctg_seq.size() + 16)) return fail("cudaMalloc failed");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    if (!ctg_seq.empty()) cudaMemcpyAsync(S->seq.p, ctg_seq.data(), ctg_seq.size(), cudaMemcpyHostToDevice, st);
+
+    // ---- byte range of the wanted contigs: [begin, end) as virtual offsets
+    const bool all = names.empty();
+    uint64_t vbeg = 0, vend = (uint64_t)bf.size() << 16;
+    bool any_reads = false;
+    if (all) { vbeg = bf.header().first_record_voffset; any_reads = true; }
+    else if (tid_max >= 0) {
+        for (int t = tid_min; t <= tid_max && !any_reads; t++) if (!starts[(size_t)t].empty()) { vbeg = starts[(size_t)t][0]; any_reads = true; }
+        for (int t = tid_max + 1; t < n_ref; t++) if (!starts[(size_t)t].empty()) { vend = starts[(size_t)t][0]; break; }
+    }
+    auto finish_empty = [&]() {
+        if (!S->rec_off.alloc(16) || !S->rec.alloc(16) || (with_qual && (!S->qual_off.alloc(16) || !S->qual.alloc(16)))) return false;
+        cudaMemsetAsync(S->rec_off.p, 0, 16, st);
+        if (with_qual) cudaMemsetAsync(S->qual_off.p, 0, 16, st);
+        return cudaStreamSynchronize(st) == cudaSuccess;
+    };
+    if (!any_reads || (vbeg >> 16) >= bf.size()) { if (!finish_empty()) return fail("cudaMalloc failed"); return S; }
+
+    std::vector<npz::Block> blocks; std::vector<uint64_t> coffs; int64_t total = 0;
+    const size_t cbeg = (size_t)(vbeg >> 16);
+    const size_t cend = (vend >> 16) >= bf.size() ? bf.size() : (size_t)(vend >> 16) + 1;
+    if (!bgzf_scan(bf.data(), bf.size(), blocks, total, err, &coffs, cbeg, cend)) return fail(err);
+    // the scan includes the block that starts before `cend`: ship it whole (payload + 8 trailer bytes)
+    const size_t ship = blocks.empty() ? 0 : (size_t)blocks.back().in_off + blocks.back().in_len + 8;
+    auto u_of = [&](uint64_t v, int64_t* out) -> bool {
+        if ((v >> 16) >= bf.size()) { *out = total; return true; }
+        auto it = std::lower_bound(coffs.begin(), coffs.end(), v >> 16);
+        if (it == coffs.end() || *it != (v >> 16)) return false;
+        const npz::Block& b = blocks[(size_t)(it - coffs.begin())];
+        if ((v & 0xffff) > b.out_len) return false;
+        *out = (int64_t)b.out_off + (int64_t)(v & 0xffff);
+        return true;
+    };
+    std::vector<int64_t> anchors;
+    int64_t ub = 0, ue = 0;
+    if (!u_of(vbeg, &ub) || !u_of(vend, &ue)) return fail("index offsets do not match the BGZF blocks");
+    anchors.push_back(ub);
+    for (int t = all ? 0 : tid_min; t <= (all ? n_ref - 1 : tid_max); t++)
+        for (uint64_t v : starts[(size_t)t]) {
+            if (v <= vbeg || v >= vend) continue;
+            int64_t u;
+            if (!u_of(v, &u)) return fail("index offsets do not match the BGZF blocks");
+            anchors.push_back(u);
+        }
+    anchors.push_back(ue);
+    std::sort(anchors.begin(), anchors.end());
+    anchors.erase(std::unique(anchors.begin(), anchors.end()), anchors.end());
+    const int32_t n_int = (int32_t)anchors.size() - 1;
+    S->comp_bytes = (int64_t)ship; S->inflated_bytes = total;
+
+    // ---- inflate on the device
+    Dbuf U, d_anch, d_cnt, d_base, d_err;
+    if (!U.alloc((size_t)total + 16) || !d_anch.alloc(anchors.size() * 8) || !d_cnt.alloc(((size_t)n_int + 2) * 4) ||
+        !d_base.alloc(((size_t)n_int + 2) * 4) || !d_err.alloc(16)) return fail("cudaMalloc failed");
+    if (npz_dev::inflate_to_device(bf.data() + cbeg, ship, blocks, total, U.as<uint8_t>(), st, &S->ms_inflate, err) != NP_OK) return fail(err);
+    cudaMemcpyAsync(d_anch.p, anchors.data(), anchors.size() * 8, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(d_err.p, 0, 16, st);
+    cudaMemsetAsync(d_cnt.p, 0, ((size_t)n_int + 2) * 4, st);
+    int32_t n_rec = 0, h_err = 0;
+    if (n_int > 0) {
+        k_rec_walk<<<(n_int + 127) / 128, 128, 0, st>>>(U.as<uint8_t>(), total, d_anch.as<int64_t>(), n_int, d_cnt.as<int32_t>(), nullptr, nullptr, d_err.as<int32_t>());
+        if (!exscan(d_cnt.as<int32_t>(), d_base.as<int32_t>(), n_int + 1, st)) return fail("cudaMalloc failed");
+        cudaMemcpyAsync(&n_rec, d_base.as<int32_t>() + n_int, 4, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(&h_err, d_err.p, 4, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+    }
+    if (h_err) return fail("record chain does not meet the index anchors (corrupt BAM or stale .bai)");
+    if (n_rec == 0) { if (!finish_empty()) return fail("cudaMalloc failed"); return S; }
+    Dbuf d_start, d_keep, d_units, d_qunits, d_slot, d_enc, d_kidx, d_uoff, d_quoff, d_sot, d_goff, d_lc, d_lcf, d_scount;
+    const size_t nr1 = (size_t)n_rec + 1;
+    if (!d_start.alloc(nr1 * 8) || !d_keep.alloc(nr1 * 4) || !d_units.alloc(nr1 * 4) || !d_qunits.alloc(nr1 * 4) || !d_slot.alloc(nr1 * 4) ||
+        !d_enc.alloc(nr1) || !d_kidx.alloc(nr1 * 4) || !d_uoff.alloc(nr1 * 4) || !d_quoff.alloc(nr1 * 4) || !d_sot.alloc(slot_of_tid.size() * 4) ||
+        !d_goff.alloc(((size_t)n_slots + 1) * 8) || !d_scount.alloc(((size_t)n_slots + 1) * 4)) return fail("cudaMalloc failed");
+    k_rec_walk<<<(n_int + 127) / 128, 128, 0, st>>>(U.as<uint8_t>(), total, d_anch.as<int64_t>(), n_int, nullptr, d_base.as<int32_t>(), d_start.as<int64_t>(), d_err.as<int32_t>());
+    cudaMemcpyAsync(d_sot.p, slot_of_tid.data(), slot_of_tid.size() * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_goff.p, S->ctg_off.data(), ((size_t)n_slots + 1) * 8, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(d_scount.p, 0, ((size_t)n_slots + 1) * 4, st);
+    const int64_t G = (int64_t)ctg_seq.size();
+    if (with_qual == 2) {
+        if (!d_lc.alloc(((size_t)G + 2) * 4) || !d_lcf.alloc(((size_t)G + 2) * 4)) return fail("cudaMalloc failed");
+        k_lower_flags<<<(unsigned)((G + 1 + 255) / 256), 256, 0, st>>>(S->seq.as<uint8_t>(), G, d_lcf.as<int32_t>());
+        if (!exscan(d_lcf.as<int32_t>(), d_lc.as<int32_t>(), (int)(G + 1), st)) return fail("cudaMalloc failed");
+    }
+    const char* e4 = getenv("NEXTPOLISH_B200_4BIT");
+    MetaArgs ma{U.as<uint8_t>(), d_start.as<int64_t>(), n_rec, d_sot.as<int32_t>(), n_ref, d_goff.as<int64_t>(),
+                with_qual == 2 ? d_lc.as<int32_t>() : nullptr, with_qual, (e4 && e4[0] == '1') ? 0 : 1,
+                d_keep.as<int32_t>(), d_units.as<int32_t>(), d_qunits.as<int32_t>(), d_slot.as<int32_t>(), d_enc.as<uint8_t>(), d_err.as<int32_t>()};
+    cudaMemsetAsync(d_keep.as<int32_t>() + n_rec, 0, 4, st); cudaMemsetAsync(d_units.as<int32_t>() + n_rec, 0, 4, st);
+    cudaMemsetAsync(d_qunits.as<int32_t>() + n_rec, 0, 4, st);
+    k_rec_meta<<<(n_rec + 127) / 128, 128, 0, st>>>(ma);
+    if (!exscan(d_keep.as<int32_t>(), d_kidx.as<int32_t>(), n_rec + 1, st) || !exscan(d_units.as<int32_t>(), d_uoff.as<int32_t>(), n_rec + 1, st) ||
+        !exscan(d_qunits.as<int32_t>(), d_quoff.as<int32_t>(), n_rec + 1, st)) return fail("cudaMalloc failed");
+    int32_t tot[3] = {0, 0, 0};
+    cudaMemcpyAsync(&tot[0], d_kidx.as<int32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&tot[1], d_uoff.as<int32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&tot[2], d_quoff.as<int32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&h_err, d_err.p, 4, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    if (h_err) {
+        return fail(h_err & DL_ERR_LONG ? "read longer than 65535 bases / CIGAR ops: not a short-read record"
+                    : h_err & DL_ERR_ORDER ? "BAM is not coordinate sorted" : "corrupt BAM record layout");
+    }
+    const int32_t n_keep = tot[0];
+    S->n_reads = n_keep; S->rec_bytes = (int64_t)tot[1] * 16; S->qual_bytes = (int64_t)tot[2] * 16;
+    if (!S->rec_off.alloc(((size_t)n_keep + 1) * 4) || !S->rec.alloc((size_t)S->rec_bytes + 16) ||
+        (with_qual && (!S->qual_off.alloc(((size_t)n_keep + 1) * 4) || !S->qual.alloc((size_t)S->qual_bytes + 16)))) return fail("cudaMalloc failed");
+    cudaMemsetAsync(S->rec.p, 0, (size_t)S->rec_bytes + 16, st);
+    if (with_qual) cudaMemsetAsync(S->qual.p, 0, (size_t)S->qual_bytes + 16, st);
+    PackArgs pa{U.as<uint8_t>(), d_start.as<int64_t>(), n_rec, d_keep.as<int32_t>(), d_kidx.as<int32_t>(), d_uoff.as<int32_t>(), d_quoff.as<int32_t>(),
+                d_qunits.as<int32_t>(), d_slot.as<int32_t>(), d_enc.as<uint8_t>(), S->rec_off.as<uint32_t>(), S->rec.as<uint8_t>(),
+                with_qual ? S->qual_off.as<uint32_t>() : nullptr, with_qual ? S->qual.as<uint8_t>() : nullptr, d_scount.as<int32_t>(), n_keep, tot[1], tot[2]};
+    k_rec_pack<<<(n_rec + 127) / 128, 128, 0, st>>>(pa);
+    std::vector<int32_t> counts((size_t)n_slots + 1, 0);
+    cudaMemcpyAsync(counts.data(), d_scount.p, ((size_t)n_slots + 1) * 4, cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(e1, st);
+    cudaError_t er = cudaStreamSynchronize(st);
+    if (er != cudaSuccess) return fail(cudaGetErrorString(er));
+    cudaEventElapsedTime(&S->ms_total, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (int32_t k = 0; k < n_slots; k++) S->ctg_read_off[(size_t)k + 1] = S->ctg_read_off[(size_t)k] + counts[(size_t)k];
+    return S;
+}
+
+void np_dev_shard_view(const np_dev_shard* s, np_shard_view* v) {
+    memset(v, 0, sizeof(*v));
+    v->n_contigs = (int32_t)s->names.size();
+    v->n_reads = s->n_reads;
+    v->ctg_off = s->ctg_off.data();
+    v->ctg_read_off = s->ctg_read_off.data();
+    v->ctg_seq = s->seq.as<uint8_t>();
+    v->rec_off = s->rec_off.as<uint32_t>();
+    v->rec = s->rec.as<uint8_t>();
+    v->qual_off = s->with_qual ? s->qual_off.as<uint32_t>() : nullptr;
+    v->qual = s->with_qual ? s->qual.as<uint8_t>() : nullptr;
+}
+const char* np_dev_shard_contig_name(const np_dev_shard* s, int32_t i) { return s && i >= 0 && i < (int32_t)s->names.size() ? s->names[(size_t)i].c_str() : nullptr; }
+int32_t np_dev_shard_contig_rank(const np_dev_shard* s, int32_t i) { return s && i >= 0 && i < (int32_t)s->fasta_rank.size() ? s->fasta_rank[(size_t)i] : -1; }
+// sizes: {rec bytes, qual bytes, draft bytes, compressed bytes shipped, inflated bytes}; times: {inflate kernel ms, whole load ms (device)}
+void np_dev_shard_stats(const np_dev_shard* s, int64_t* sizes5, float* ms2) {
+    if (sizes5) { sizes5[0] = s->rec_bytes; sizes5[1] = s->qual_bytes; sizes5[2] = s->seq_bytes; sizes5[3] = s->comp_bytes; sizes5[4] = s->inflated_bytes; }
+    if (ms2) { ms2[0] = s->ms_inflate; ms2[1] = s->ms_total; }
+}
+// Copies the device arrays to host buffers of the sizes np_dev_shard_stats / the view report (tests, debugging).
+int32_t np_dev_shard_download(const np_dev_shard* s, uint8_t* ctg_seq, uint32_t* rec_off, uint8_t* rec, uint32_t* qual_off, uint8_t* qual) {
+    cudaSetDevice(s->device);
+    if (ctg_seq && s->seq_bytes) cudaMemcpy(ctg_seq, s->seq.p, (size_t)s->seq_bytes, cudaMemcpyDeviceToHost);
+    if (rec_off) cudaMemcpy(rec_off, s->rec_off.p, ((size_t)s->n_reads + 1) * 4, cudaMemcpyDeviceToHost);
+    if (rec && s->rec_bytes) cudaMemcpy(rec, s->rec.p, (size_t)s->rec_bytes, cudaMemcpyDeviceToHost);
+    if (s->with_qual && qual_off) cudaMemcpy(qual_off, s->qual_off.p, ((size_t)s->n_reads + 1) * 4, cudaMemcpyDeviceToHost);
+    if (s->with_qual && qual && s->qual_bytes) cudaMemcpy(qual, s->qual.p, (size_t)s->qual_bytes, cudaMemcpyDeviceToHost);
+    cudaError_t er = cudaDeviceSynchronize();
+    if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
+    return NP_OK;
+}
+
+}  // extern "C"

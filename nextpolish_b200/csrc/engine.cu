@@ -756,26 +756,40 @@ static np_engine* process_engine() {
 
 static PolishResult* run_one_contig(const char* tigname, Configure* cfg, int task) {
     if (!tigname || !cfg || !cfg->fastafn) { fprintf(stderr, "nextpolish_b200: bad arguments\n"); exit(1); }
-    np::Shard sh; std::string err;
-    std::vector<std::string> names{std::string(tigname)};
-    if (!np::shard_load(cfg->fastafn, cfg->bamfn ? cfg->bamfn : "", names, task == NP_TASK_KMER_COUNT ? 2 : 0, 4, sh, err)) {
-        fprintf(stderr, "nextpolish_b200: %s\n", err.c_str());
-        exit(1);
-    }
-    np_shard_view v; sh.view(&v);
     np_engine* e = process_engine();
-    int64_t cap = (int64_t)sh.ctg_seq.size() * 2 + 1024;
+    const char* names[1] = {tigname};
+    const int wq = task == NP_TASK_KMER_COUNT ? 2 : 0;
+    // the contig's shard is built on the GPU from the BAM's compressed bytes when <bam>.bai exists (devload.cu);
+    // otherwise (or with NEXTPOLISH_B200_HOST_LOAD=1) by the host packer
+    np_dev_shard* ds = nullptr;
+    const char* hl = getenv("NEXTPOLISH_B200_HOST_LOAD");
+    if (cfg->bamfn && !(hl && hl[0] == '1')) ds = np_shard_load_gpu(e->device, cfg->fastafn, cfg->bamfn, names, 1, wq);
+    np::Shard sh; std::string err;
+    np_shard_view v;
+    int32_t rc;
+    if (ds) {
+        np_dev_shard_view(ds, &v);
+        rc = np_engine_adopt_device(e, &v);
+    } else {
+        std::vector<std::string> nm{std::string(tigname)};
+        if (!np::shard_load(cfg->fastafn, cfg->bamfn ? cfg->bamfn : "", nm, wq, 4, sh, err)) {
+            fprintf(stderr, "nextpolish_b200: %s\n", err.c_str());
+            exit(1);
+        }
+        sh.view(&v);
+        rc = np_engine_upload(e, &v);
+    }
     PolishResult* res = polishresult_init();
-    int32_t rc = np_engine_upload(e, &v);
     if (rc == NP_OK) rc = np_engine_run(e, task, cfg);
-    if (rc == NP_OK) { cap = np_engine_result_bytes(e) + 1; }
     if (rc != NP_OK) { fprintf(stderr, "nextpolish_b200: %s\n", np_last_error()); exit(1); }
+    int64_t cap = np_engine_result_bytes(e) + 1;
     res->contig = (char*)calloc(1, (size_t)cap + 1);
     int64_t off[2] = {0, 0};
     rc = np_engine_download(e, (uint8_t*)res->contig, cap, off);
     if (rc != NP_OK) { fprintf(stderr, "nextpolish_b200: %s\n", np_last_error()); exit(1); }
     res->length = (int32_t)off[1];
     res->contig[off[1]] = '\0';
+    if (ds) np_dev_shard_free(ds);
     return res;
 }
 

@@ -265,11 +265,14 @@ static inline uint16_t rd_u16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); 
 
 }  // namespace
 
-bool bgzf_scan(const uint8_t* data, size_t size, std::vector<npz::Block>& blocks, int64_t& total, std::string& err) {
+bool bgzf_scan(const uint8_t* data, size_t size, std::vector<npz::Block>& blocks, int64_t& total, std::string& err,
+               std::vector<uint64_t>* coffs, size_t begin, size_t end) {
     blocks.clear();
+    if (coffs) coffs->clear();
     total = 0;
-    size_t coff = 0;
-    while (coff < size) {
+    size_t coff = begin;
+    if (end > size) end = size;
+    while (coff < end) {
         BlockDesc b;
         if (!bgzf_block_at(data, size, coff, b)) { err = "corrupt BGZF block header at offset " + std::to_string(coff); return false; }
         const uint8_t* p = data + coff;
@@ -277,13 +280,46 @@ bool bgzf_scan(const uint8_t* data, size_t size, std::vector<npz::Block>& blocks
         size_t hdr = 12 + xlen;
         if (b.csize < hdr + 8) { err = "BGZF block shorter than its header"; return false; }
         npz::Block o;
-        o.in_off = coff + hdr;
+        o.in_off = coff + hdr - begin;           // relative to `begin`: the caller ships data + begin
         o.in_len = (uint32_t)(b.csize - hdr - 8);
         o.out_len = (uint32_t)b.isize;
         o.out_off = (uint64_t)total;
         blocks.push_back(o);
+        if (coffs) coffs->push_back((uint64_t)coff);
         total += (int64_t)b.isize;
         coff += b.csize;
+    }
+    return true;
+}
+
+bool BamFile::bai_record_starts(std::vector<std::vector<uint64_t>>& starts, std::string& err) const {
+    std::string raw;
+    if (!read_file(path_ + ".bai", raw, err)) return false;
+    const uint8_t* p = (const uint8_t*)raw.data();
+    size_t n = raw.size(), x = 8;
+    if (n < 8 || memcmp(p, "BAI\1", 4) != 0) { err = "bad BAI magic"; return false; }
+    int32_t n_ref = rd_i32(p + 4);
+    starts.assign((size_t)std::max(0, n_ref), {});
+    for (int32_t r = 0; r < n_ref; r++) {
+        std::vector<uint64_t>& v = starts[(size_t)r];
+        if (x + 4 > n) { err = "truncated BAI"; return false; }
+        int32_t n_bin = rd_i32(p + x); x += 4;
+        for (int32_t b = 0; b < n_bin; b++) {
+            if (x + 8 > n) { err = "truncated BAI"; return false; }
+            uint32_t bin; memcpy(&bin, p + x, 4);
+            int32_t n_chunk = rd_i32(p + x + 4); x += 8;
+            if (x + 16 * (size_t)n_chunk > n) { err = "truncated BAI"; return false; }
+            if (bin != 37450)
+                for (int32_t c = 0; c < n_chunk; c++) { uint64_t beg; memcpy(&beg, p + x + 16 * (size_t)c, 8); v.push_back(beg); }
+            x += 16 * (size_t)n_chunk;
+        }
+        if (x + 4 > n) { err = "truncated BAI"; return false; }
+        int32_t n_intv = rd_i32(p + x); x += 4;
+        if (x + 8 * (size_t)n_intv > n) { err = "truncated BAI"; return false; }
+        for (int32_t i = 0; i < n_intv; i++) { uint64_t o; memcpy(&o, p + x + 8 * (size_t)i, 8); if (o) v.push_back(o); }
+        x += 8 * (size_t)n_intv;
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
     }
     return true;
 }

@@ -58,6 +58,11 @@ public:
     // Smallest chunk-begin virtual offset of `tid` from <bam>.bai; returns false if the index
     // is missing/unreadable; *has_reads=false if the contig has no chunks.
     bool bai_first_offset(int tid, uint64_t* voff, bool* has_reads, std::string& err) const;
+    // Every record-start virtual offset the index knows per reference: chunk begins of all bins and the linear
+    // index entries (16 kb windows) — anchors for the device-side record walk (devload.cu).  sorted, unique.
+    bool bai_record_starts(std::vector<std::vector<uint64_t>>& starts, std::string& err) const;
+    const uint8_t* data() const { return data_; }
+    size_t size() const { return size_; }
 private:
     bool inflate_batch(size_t first_block, size_t n_blocks, int threads,
                        std::vector<uint8_t>& out, std::vector<size_t>& block_uoff, std::string& err);
@@ -105,7 +110,8 @@ bool shard_load(const std::string& fasta, const std::string& bam,
 
 // Walks the BGZF blocks of a byte range: deflate payload location and output placement of every block
 // (for np_bgzf_inflate, bgzf_inflate.cu); total = sum of the blocks' ISIZE.
-bool bgzf_scan(const uint8_t* data, size_t size, std::vector<npz::Block>& blocks, int64_t& total, std::string& err);
+bool bgzf_scan(const uint8_t* data, size_t size, std::vector<npz::Block>& blocks, int64_t& total, std::string& err,
+               std::vector<uint64_t>* coffs = nullptr, size_t begin = 0, size_t end = (size_t)-1);
 
 // config.c:80-101 (bam_tlen): mean insert size estimate over the head of the BAM.
 bool bam_insert_estimate(const std::string& bam, uint32_t count_read_ins, uint32_t max_ins_len,

@@ -124,6 +124,71 @@ class Shard:
             pass
 
 
+class DeviceShard:
+    """Packed shard built in HBM from FASTA + BAM (+ .bai) by np_shard_load_gpu (inflate, record unpack and packing
+    on the GPU).  `view` holds device pointers: pass it to Engine.adopt_device."""
+
+    def __init__(self, fasta, bam, names=None, with_qual=False, device=0):
+        arr, n = None, 0
+        if names:
+            n = len(names)
+            arr = (C.c_char_p * n)(*[s.encode() for s in names])
+        self.h = lib().np_shard_load_gpu(device, fasta.encode(), bam.encode(), arr, n, int(with_qual))
+        if not self.h:
+            raise NativeError(last_error())
+        self.view = ShardView()
+        lib().np_dev_shard_view(self.h, C.byref(self.view))
+        self.names = [lib().np_dev_shard_contig_name(self.h, i).decode() for i in range(self.view.n_contigs)]
+
+    @property
+    def n_contigs(self):
+        return self.view.n_contigs
+
+    @property
+    def n_reads(self):
+        return self.view.n_reads
+
+    @property
+    def total_bases(self):
+        return self.view.ctg_off[self.view.n_contigs]
+
+    def stats(self):
+        sizes = (C.c_int64 * 5)()
+        ms = (C.c_float * 2)()
+        lib().np_dev_shard_stats(self.h, sizes, ms)
+        return dict(rec_bytes=sizes[0], qual_bytes=sizes[1], draft_bytes=sizes[2], compressed_bytes=sizes[3],
+                    inflated_bytes=sizes[4], inflate_kernel_ms=ms[0], device_ms=ms[1])
+
+    def arrays(self):
+        """Host copies of the device arrays (tests): same keys as Shard.arrays()."""
+        st = self.stats()
+        n, r = self.view.n_contigs, self.view.n_reads
+        out = {"ctg_off": np.array([self.view.ctg_off[i] for i in range(n + 1)], np.int64),
+               "ctg_read_off": np.array([self.view.ctg_read_off[i] for i in range(n + 1)], np.int64),
+               "rec_off": np.zeros(r + 1, np.uint32), "ctg_seq": np.zeros(st["draft_bytes"], np.uint8),
+               "rec": np.zeros(st["rec_bytes"], np.uint8)}
+        has_q = bool(self.view.qual_off)
+        if has_q:
+            out["qual_off"] = np.zeros(r + 1, np.uint32)
+            out["qual"] = np.zeros(st["qual_bytes"], np.uint8)
+        rc = lib().np_dev_shard_download(self.h, out["ctg_seq"].ctypes.data, out["rec_off"].ctypes.data, out["rec"].ctypes.data,
+                                         out["qual_off"].ctypes.data if has_q else None, out["qual"].ctypes.data if has_q else None)
+        if rc != 0:
+            raise NativeError(last_error())
+        return out
+
+    def close(self):
+        if self.h:
+            lib().np_dev_shard_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Stream:
     """np_stream: jobs (task, host shard) submitted in order; a job's upload overlaps the kernels of the jobs
     before it (double buffering).  Buffers handed to submit() must stay alive until wait(ticket) returned."""
