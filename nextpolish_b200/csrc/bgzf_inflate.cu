@@ -63,41 +63,49 @@ static bool reserve(void** p, size_t* cap, size_t bytes) {
 }  // namespace
 
 namespace npz_dev {
-// Inflates `blocks` (payload offsets relative to comp_host) into d_out (device) on `stream`; synchronises the
-// stream and checks every block's status.  Used by np_bgzf_inflate's callers that keep the bytes in HBM
-// (devload.cu).
-int32_t inflate_to_device(const uint8_t* comp_host, size_t comp_bytes, const std::vector<npz::Block>& blocks, int64_t total,
-                          uint8_t* d_out, cudaStream_t stream, float* kernel_ms, std::string& err) {
-    (void)total;
-    const size_t nb = blocks.size();
-    if (nb == 0) return NP_OK;
+// Asynchronous inflate of `blocks` (payload offsets relative to comp_host) into d_out (device) on `stream`:
+// inflate_launch enqueues the copies and the kernel and returns; inflate_finish synchronises the stream and
+// checks every block's status.  Used by callers that keep the bytes in HBM (devload.cu) and overlap host work.
+struct InflateJob {
     void *d_comp = nullptr, *d_blocks = nullptr, *d_status = nullptr;
-    auto cleanup = [&]() { if (d_comp) cudaFreeAsync(d_comp, stream); if (d_blocks) cudaFreeAsync(d_blocks, stream); if (d_status) cudaFreeAsync(d_status, stream); };
-    if (cudaMallocAsync(&d_comp, comp_bytes + 16, stream) != cudaSuccess || cudaMallocAsync(&d_blocks, nb * sizeof(npz::Block), stream) != cudaSuccess ||
-        cudaMallocAsync(&d_status, (nb + 1) * 4, stream) != cudaSuccess) { cleanup(); err = "cudaMalloc failed"; return NP_ERR_CUDA; }
-    cudaMemcpyAsync(d_comp, comp_host, comp_bytes, cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(d_blocks, blocks.data(), nb * sizeof(npz::Block), cudaMemcpyHostToDevice, stream);
-    cudaMemsetAsync(d_status, 0xff, nb * 4, stream);
-    cudaMemsetAsync((int32_t*)d_status + nb, 0, 4, stream);
+    size_t nb = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t stream = nullptr;
+};
+int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_bytes, const std::vector<npz::Block>& blocks,
+                       uint8_t* d_out, cudaStream_t stream, std::string& err) {
+    j.nb = blocks.size(); j.stream = stream;
+    if (j.nb == 0) return NP_OK;
+    const size_t nb = j.nb;
+    if (cudaMallocAsync(&j.d_comp, comp_bytes + 16, stream) != cudaSuccess || cudaMallocAsync(&j.d_blocks, nb * sizeof(npz::Block), stream) != cudaSuccess ||
+        cudaMallocAsync(&j.d_status, (nb + 1) * 4, stream) != cudaSuccess) { err = "cudaMalloc failed"; return NP_ERR_CUDA; }
+    cudaMemcpyAsync(j.d_comp, comp_host, comp_bytes, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(j.d_blocks, blocks.data(), nb * sizeof(npz::Block), cudaMemcpyHostToDevice, stream);
+    cudaMemsetAsync(j.d_status, 0xff, nb * 4, stream);
+    cudaMemsetAsync((int32_t*)j.d_status + nb, 0, 4, stream);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int ctas = (int)((nb + kWarpsPerCta - 1) / kWarpsPerCta);
     if (ctas > sms * 8) ctas = sms * 8;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, stream);
-    k_bgzf_inflate<<<ctas, kWarpsPerCta * 32, 0, stream>>>((const uint8_t*)d_comp, (const npz::Block*)d_blocks, (int32_t)nb, d_out,
-                                                          (int32_t*)d_status, (int32_t*)d_status + nb);
-    cudaEventRecord(e1, stream);
-    std::vector<int32_t> st(nb);
-    cudaMemcpyAsync(st.data(), d_status, nb * 4, cudaMemcpyDeviceToHost, stream);
-    cudaError_t er = cudaStreamSynchronize(stream);
-    if (kernel_ms && er == cudaSuccess) cudaEventElapsedTime(kernel_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cleanup();
+    cudaEventCreate(&j.e0); cudaEventCreate(&j.e1);
+    cudaEventRecord(j.e0, stream);
+    k_bgzf_inflate<<<ctas, kWarpsPerCta * 32, 0, stream>>>((const uint8_t*)j.d_comp, (const npz::Block*)j.d_blocks, (int32_t)nb, d_out,
+                                                          (int32_t*)j.d_status, (int32_t*)j.d_status + nb);
+    cudaEventRecord(j.e1, stream);
+    return NP_OK;
+}
+int32_t inflate_finish(InflateJob& j, float* kernel_ms, std::string& err) {
+    if (j.nb == 0) return NP_OK;
+    std::vector<int32_t> st(j.nb);
+    cudaMemcpyAsync(st.data(), j.d_status, j.nb * 4, cudaMemcpyDeviceToHost, j.stream);
+    cudaError_t er = cudaStreamSynchronize(j.stream);
+    if (kernel_ms && er == cudaSuccess) cudaEventElapsedTime(kernel_ms, j.e0, j.e1);
+    cudaEventDestroy(j.e0); cudaEventDestroy(j.e1);
+    cudaFreeAsync(j.d_comp, j.stream); cudaFreeAsync(j.d_blocks, j.stream); cudaFreeAsync(j.d_status, j.stream);
+    j.nb = 0;
     if (er != cudaSuccess) { err = cudaGetErrorString(er); return NP_ERR_CUDA; }
-    for (size_t i = 0; i < nb; i++)
+    for (size_t i = 0; i < st.size(); i++)
         if (st[i] != npz::OK) { err = "BGZF block " + std::to_string(i) + " failed with inflate error " + std::to_string(st[i]); return NP_ERR_IO; }
     return NP_OK;
 }

@@ -22,6 +22,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -34,8 +35,15 @@
 #include "../../include/nextpolish_b200.h"
 
 namespace npz_dev {   // bgzf_inflate.cu
-int32_t inflate_to_device(const uint8_t* comp_host, size_t comp_bytes, const std::vector<npz::Block>& blocks, int64_t total,
-                          uint8_t* d_out, cudaStream_t stream, float* kernel_ms, std::string& err);
+struct InflateJob {
+    void *d_comp = nullptr, *d_blocks = nullptr, *d_status = nullptr;
+    size_t nb = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t stream = nullptr;
+};
+int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_bytes, const std::vector<npz::Block>& blocks,
+                       uint8_t* d_out, cudaStream_t stream, std::string& err);
+int32_t inflate_finish(InflateJob& j, float* kernel_ms, std::string& err);
 }
 
 namespace {
@@ -239,61 +247,46 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
         return nullptr;
     }
     cudaSetDevice(device);
+    // NEXTPOLISH_B200_TRACE=1: host-side phase times on stderr
+    const bool trace = getenv("NEXTPOLISH_B200_TRACE") && getenv("NEXTPOLISH_B200_TRACE")[0] == '1';
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tprev = now();
+    auto lap = [&](const char* what) { if (trace) { double t = now(); fprintf(stderr, "np_shard_load_gpu: %-32s %8.2f ms\n", what, t - tprev); tprev = t; } };
     std::string err;
     std::vector<std::string> names;
     for (int32_t i = 0; i < n_names; i++) names.emplace_back(names_in[i]);
-    std::vector<FastaRecord> recs;
-    if (!fasta_load(fasta, names, recs, err)) { set_error("np_shard_load_gpu: " + err); return nullptr; }
+    const bool all = names.empty();
+
+    // ---- BAM side first: everything up to the launch of the inflate needs only the BAM and its index, so the
+    //      FASTA is read and parsed on the host while the GPU copies and inflates
     BamFile bf;
     if (!bf.open(bam, err)) { set_error("np_shard_load_gpu: " + err); return nullptr; }
     std::vector<std::vector<uint64_t>> starts;
     if (!bf.bai_record_starts(starts, err)) { set_error("np_shard_load_gpu: needs " + std::string(bam) + ".bai (" + err + ")"); return nullptr; }
     const int32_t n_ref = (int32_t)bf.header().names.size();
     starts.resize((size_t)n_ref);
-
-    // contigs in BAM tid order (those absent from the BAM header go last, with no reads) — as shard_load
     std::unordered_map<std::string, int> tid_of;
     for (int32_t i = 0; i < n_ref; i++) tid_of.emplace(bf.header().names[(size_t)i], i);
-    struct Slot { int tid; size_t rec_idx; };
-    std::vector<Slot> slots;
-    for (size_t i = 0; i < recs.size(); i++) {
-        auto it = tid_of.find(recs[i].name);
-        slots.push_back({it == tid_of.end() ? 0x7fffffff : it->second, i});
-    }
-    std::stable_sort(slots.begin(), slots.end(), [](const Slot& a, const Slot& b) { return a.tid < b.tid; });
-    np_dev_shard* S = new np_dev_shard();
-    S->device = device;
-    S->with_qual = with_qual != 0;
-    std::vector<uint8_t> ctg_seq;
-    std::vector<int32_t> slot_of_tid((size_t)std::max(1, n_ref), -1);
-    S->ctg_off.push_back(0);
     int tid_min = 0x7fffffff, tid_max = -1;
-    for (size_t k = 0; k < slots.size(); k++) {
-        const FastaRecord& r = recs[slots[k].rec_idx];
-        S->names.push_back(r.name);
-        S->fasta_rank.push_back((int32_t)slots[k].rec_idx);
-        ctg_seq.insert(ctg_seq.end(), r.seq.begin(), r.seq.end());
-        S->ctg_off.push_back((int64_t)ctg_seq.size());
-        if (slots[k].tid != 0x7fffffff) {
-            if (slot_of_tid[(size_t)slots[k].tid] < 0) slot_of_tid[(size_t)slots[k].tid] = (int32_t)k;
-            tid_min = std::min(tid_min, slots[k].tid); tid_max = std::max(tid_max, slots[k].tid);
-        }
+    if (all) { if (n_ref > 0) { tid_min = 0; tid_max = n_ref - 1; } }
+    else for (const auto& nm : names) {
+        auto it = tid_of.find(nm);
+        if (it != tid_of.end()) { tid_min = std::min(tid_min, it->second); tid_max = std::max(tid_max, it->second); }
     }
-    const int32_t n_slots = (int32_t)slots.size();
-    S->ctg_read_off.assign((size_t)n_slots + 1, 0);
-    S->seq_bytes = (int64_t)ctg_seq.size();
-    auto fail = [&](const std::string& m) { set_error("np_shard_load_gpu: " + m); np_dev_shard_free(S); return (np_dev_shard*)nullptr; };
+    lap("bam open + header + index");
+
     pool_setup(device);
     if (!g_alloc_stream) cudaStreamCreateWithFlags(&g_alloc_stream, cudaStreamNonBlocking);
     cudaStream_t st = g_alloc_stream;      // one stream for allocations and work: stream-ordered reuse is safe
-    if (!S->seq.alloc(ctg_seq.size() + 16)) return fail("cudaMalloc failed");
+    np_dev_shard* S = new np_dev_shard();
+    S->device = device;
+    S->with_qual = with_qual != 0;
+    auto fail = [&](const std::string& m) { set_error("np_shard_load_gpu: " + m); cudaStreamSynchronize(st); np_dev_shard_free(S); return (np_dev_shard*)nullptr; };
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
-    if (!ctg_seq.empty()) cudaMemcpyAsync(S->seq.p, ctg_seq.data(), ctg_seq.size(), cudaMemcpyHostToDevice, st);
 
-    // ---- byte range of the wanted contigs: [begin, end) as virtual offsets
-    const bool all = names.empty();
+    // byte range of the wanted contigs: [vbeg, vend) as virtual offsets
     uint64_t vbeg = 0, vend = (uint64_t)bf.size() << 16;
     bool any_reads = false;
     if (all) { vbeg = bf.header().first_record_voffset; any_reads = true; }
@@ -301,51 +294,87 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
         for (int t = tid_min; t <= tid_max && !any_reads; t++) if (!starts[(size_t)t].empty()) { vbeg = starts[(size_t)t][0]; any_reads = true; }
         for (int t = tid_max + 1; t < n_ref; t++) if (!starts[(size_t)t].empty()) { vend = starts[(size_t)t][0]; break; }
     }
+    if ((vbeg >> 16) >= bf.size()) any_reads = false;
+    std::vector<npz::Block> blocks; std::vector<uint64_t> coffs; int64_t total = 0;
+    std::vector<int64_t> anchors;
+    Dbuf U;
+    npz_dev::InflateJob job;
+    if (any_reads) {
+        const size_t cbeg = (size_t)(vbeg >> 16);
+        const size_t cend = (vend >> 16) >= bf.size() ? bf.size() : (size_t)(vend >> 16) + 1;
+        if (!bgzf_scan(bf.data(), bf.size(), blocks, total, err, &coffs, cbeg, cend)) return fail(err);
+        // the scan includes the block that starts before `cend`: ship it whole (payload + 8 trailer bytes)
+        const size_t ship = blocks.empty() ? 0 : (size_t)blocks.back().in_off + blocks.back().in_len + 8;
+        auto u_of = [&](uint64_t v, int64_t* out) -> bool {
+            if ((v >> 16) >= bf.size()) { *out = total; return true; }
+            auto it = std::lower_bound(coffs.begin(), coffs.end(), v >> 16);
+            if (it == coffs.end() || *it != (v >> 16)) return false;
+            const npz::Block& b = blocks[(size_t)(it - coffs.begin())];
+            if ((v & 0xffff) > b.out_len) return false;
+            *out = (int64_t)b.out_off + (int64_t)(v & 0xffff);
+            return true;
+        };
+        int64_t ub = 0, ue = 0;
+        if (!u_of(vbeg, &ub) || !u_of(vend, &ue)) return fail("index offsets do not match the BGZF blocks");
+        anchors.push_back(ub);
+        for (int t = tid_min; t <= tid_max; t++)
+            for (uint64_t v : starts[(size_t)t]) {
+                if (v <= vbeg || v >= vend) continue;
+                int64_t u;
+                if (!u_of(v, &u)) return fail("index offsets do not match the BGZF blocks");
+                anchors.push_back(u);
+            }
+        anchors.push_back(ue);
+        std::sort(anchors.begin(), anchors.end());
+        anchors.erase(std::unique(anchors.begin(), anchors.end()), anchors.end());
+        S->comp_bytes = (int64_t)ship; S->inflated_bytes = total;
+        lap("bgzf_scan + anchors");
+        if (!U.alloc((size_t)total + 16)) return fail("cudaMalloc failed");
+        if (npz_dev::inflate_launch(job, bf.data() + cbeg, ship, blocks, U.as<uint8_t>(), st, err) != NP_OK) return fail(err);
+        lap("H2D (pageable) + inflate launch");
+    }
+
+    // ---- FASTA side (the GPU is busy with the copy and the inflate meanwhile)
+    std::vector<FastaRecord> recs;
+    if (!fasta_load(fasta, names, recs, err)) return fail(err);
+    // contigs in BAM tid order (those absent from the BAM header go last, with no reads) — as shard_load
+    struct Slot { int tid; size_t rec_idx; };
+    std::vector<Slot> slots;
+    for (size_t i = 0; i < recs.size(); i++) {
+        auto it = tid_of.find(recs[i].name);
+        slots.push_back({it == tid_of.end() ? 0x7fffffff : it->second, i});
+    }
+    std::stable_sort(slots.begin(), slots.end(), [](const Slot& a, const Slot& b) { return a.tid < b.tid; });
+    std::vector<uint8_t> ctg_seq;
+    std::vector<int32_t> slot_of_tid((size_t)std::max(1, n_ref), -1);
+    S->ctg_off.push_back(0);
+    for (size_t k = 0; k < slots.size(); k++) {
+        const FastaRecord& r = recs[slots[k].rec_idx];
+        S->names.push_back(r.name);
+        S->fasta_rank.push_back((int32_t)slots[k].rec_idx);
+        ctg_seq.insert(ctg_seq.end(), r.seq.begin(), r.seq.end());
+        S->ctg_off.push_back((int64_t)ctg_seq.size());
+        if (slots[k].tid != 0x7fffffff && slot_of_tid[(size_t)slots[k].tid] < 0) slot_of_tid[(size_t)slots[k].tid] = (int32_t)k;
+    }
+    const int32_t n_slots = (int32_t)slots.size();
+    S->ctg_read_off.assign((size_t)n_slots + 1, 0);
+    S->seq_bytes = (int64_t)ctg_seq.size();
+    lap("fasta_load + contig table");
+    if (!S->seq.alloc(ctg_seq.size() + 16)) return fail("cudaMalloc failed");
+    if (!ctg_seq.empty()) cudaMemcpyAsync(S->seq.p, ctg_seq.data(), ctg_seq.size(), cudaMemcpyHostToDevice, st);
     auto finish_empty = [&]() {
         if (!S->rec_off.alloc(16) || !S->rec.alloc(16) || (with_qual && (!S->qual_off.alloc(16) || !S->qual.alloc(16)))) return false;
         cudaMemsetAsync(S->rec_off.p, 0, 16, st);
         if (with_qual) cudaMemsetAsync(S->qual_off.p, 0, 16, st);
         return cudaStreamSynchronize(st) == cudaSuccess;
     };
-    if (!any_reads || (vbeg >> 16) >= bf.size()) { if (!finish_empty()) return fail("cudaMalloc failed"); return S; }
-
-    std::vector<npz::Block> blocks; std::vector<uint64_t> coffs; int64_t total = 0;
-    const size_t cbeg = (size_t)(vbeg >> 16);
-    const size_t cend = (vend >> 16) >= bf.size() ? bf.size() : (size_t)(vend >> 16) + 1;
-    if (!bgzf_scan(bf.data(), bf.size(), blocks, total, err, &coffs, cbeg, cend)) return fail(err);
-    // the scan includes the block that starts before `cend`: ship it whole (payload + 8 trailer bytes)
-    const size_t ship = blocks.empty() ? 0 : (size_t)blocks.back().in_off + blocks.back().in_len + 8;
-    auto u_of = [&](uint64_t v, int64_t* out) -> bool {
-        if ((v >> 16) >= bf.size()) { *out = total; return true; }
-        auto it = std::lower_bound(coffs.begin(), coffs.end(), v >> 16);
-        if (it == coffs.end() || *it != (v >> 16)) return false;
-        const npz::Block& b = blocks[(size_t)(it - coffs.begin())];
-        if ((v & 0xffff) > b.out_len) return false;
-        *out = (int64_t)b.out_off + (int64_t)(v & 0xffff);
-        return true;
-    };
-    std::vector<int64_t> anchors;
-    int64_t ub = 0, ue = 0;
-    if (!u_of(vbeg, &ub) || !u_of(vend, &ue)) return fail("index offsets do not match the BGZF blocks");
-    anchors.push_back(ub);
-    for (int t = all ? 0 : tid_min; t <= (all ? n_ref - 1 : tid_max); t++)
-        for (uint64_t v : starts[(size_t)t]) {
-            if (v <= vbeg || v >= vend) continue;
-            int64_t u;
-            if (!u_of(v, &u)) return fail("index offsets do not match the BGZF blocks");
-            anchors.push_back(u);
-        }
-    anchors.push_back(ue);
-    std::sort(anchors.begin(), anchors.end());
-    anchors.erase(std::unique(anchors.begin(), anchors.end()), anchors.end());
+    if (!any_reads) { if (!finish_empty()) return fail("cudaMalloc failed"); return S; }
     const int32_t n_int = (int32_t)anchors.size() - 1;
-    S->comp_bytes = (int64_t)ship; S->inflated_bytes = total;
 
-    // ---- inflate on the device
-    Dbuf U, d_anch, d_cnt, d_base, d_err;
-    if (!U.alloc((size_t)total + 16) || !d_anch.alloc(anchors.size() * 8) || !d_cnt.alloc(((size_t)n_int + 2) * 4) ||
-        !d_base.alloc(((size_t)n_int + 2) * 4) || !d_err.alloc(16)) return fail("cudaMalloc failed");
-    if (npz_dev::inflate_to_device(bf.data() + cbeg, ship, blocks, total, U.as<uint8_t>(), st, &S->ms_inflate, err) != NP_OK) return fail(err);
+    // ---- record boundaries
+    Dbuf d_anch, d_cnt, d_base, d_err;
+    if (!d_anch.alloc(anchors.size() * 8) || !d_cnt.alloc(((size_t)n_int + 2) * 4) || !d_base.alloc(((size_t)n_int + 2) * 4) || !d_err.alloc(16))
+        return fail("cudaMalloc failed");
     cudaMemcpyAsync(d_anch.p, anchors.data(), anchors.size() * 8, cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(d_err.p, 0, 16, st);
     cudaMemsetAsync(d_cnt.p, 0, ((size_t)n_int + 2) * 4, st);
@@ -355,8 +384,9 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
         if (!exscan(d_cnt.as<int32_t>(), d_base.as<int32_t>(), n_int + 1, st)) return fail("cudaMalloc failed");
         cudaMemcpyAsync(&n_rec, d_base.as<int32_t>() + n_int, 4, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(&h_err, d_err.p, 4, cudaMemcpyDeviceToHost, st);
-        cudaStreamSynchronize(st);
     }
+    if (npz_dev::inflate_finish(job, &S->ms_inflate, err) != NP_OK) return fail(err);      // synchronises the stream
+    lap("inflate + record count walk (sync)");
     if (h_err) return fail("record chain does not meet the index anchors (corrupt BAM or stale .bai)");
     if (n_rec == 0) { if (!finish_empty()) return fail("cudaMalloc failed"); return S; }
     Dbuf d_start, d_keep, d_units, d_qunits, d_slot, d_enc, d_kidx, d_uoff, d_quoff, d_sot, d_goff, d_lc, d_lcf, d_scount;
@@ -389,6 +419,7 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     cudaMemcpyAsync(&tot[2], d_quoff.as<int32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&h_err, d_err.p, 4, cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
+    lap("index walk + meta + scans (sync)");
     if (h_err) {
         return fail(h_err & DL_ERR_LONG ? "read longer than 65535 bases / CIGAR ops: not a short-read record"
                     : h_err & DL_ERR_ORDER ? "BAM is not coordinate sorted" : "corrupt BAM record layout");
@@ -408,6 +439,15 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     cudaEventRecord(e1, st);
     cudaError_t er = cudaStreamSynchronize(st);
     if (er != cudaSuccess) return fail(cudaGetErrorString(er));
+    lap("pack (sync)");
+    if (trace) {
+        cudaMemPool_t pool; unsigned long long used = 0, resv = 0; size_t fr = 0, tt = 0;
+        cudaDeviceGetDefaultMemPool(&pool, device);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &resv);
+        cudaMemGetInfo(&fr, &tt);
+        fprintf(stderr, "np_shard_load_gpu: pool used %.1f MB reserved %.1f MB, device free %.1f MB\n", used / 1e6, resv / 1e6, fr / 1e6);
+    }
     cudaEventElapsedTime(&S->ms_total, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     for (int32_t k = 0; k < n_slots; k++) S->ctg_read_off[(size_t)k + 1] = S->ctg_read_off[(size_t)k] + counts[(size_t)k];

@@ -70,11 +70,19 @@ static void parse_fasta_text(const std::string& text, std::vector<FastaRecord>& 
         r.name = text.substr(ns, ne - ns);
         i = e + 1;
         size_t j = i;
+        {   // the record's text ends at the next '>' that starts a line: reserve once
+            const void* nx = memchr(text.data() + i, '>', n - i);
+            r.seq.reserve(nx ? (size_t)((const char*)nx - (text.data() + i)) : n - i);
+        }
         while (j < n && text[j] != '>') {
-            size_t le = text.find('\n', j);
-            if (le == std::string::npos) le = n;
-            for (size_t k = j; k < le; k++)
-                if (isgraph((unsigned char)text[k])) r.seq.push_back(text[k]);
+            const void* nl = memchr(text.data() + j, '\n', n - j);
+            size_t le = nl ? (size_t)((const char*)nl - text.data()) : n;
+            const char* p = text.data() + j;
+            const size_t len = le - j;
+            unsigned bad = 0;                                    // any byte outside isgraph (33..126)?
+            for (size_t k = 0; k < len; k++) bad |= (unsigned)((unsigned char)(p[k] - 33) >= 94u);
+            if (!bad) r.seq.append(p, len);                      // whole line at once (the common case)
+            else for (size_t k = 0; k < len; k++) if (isgraph((unsigned char)p[k])) r.seq.push_back(p[k]);
             j = le + 1;
         }
         i = j;
