@@ -6,7 +6,7 @@
 // wanted contigs goes to the GPU as it is on disk and everything else happens there:
 //
 //   k_bgzf_inflate   one warp per BGZF block                                            (bgzf_inflate.h)
-//   k_rec_count/index one thread per ANCHOR interval: record boundaries.  A BAM record only says how long it is,
+//   k_rec_walk       one thread per ANCHOR interval: record boundaries.  A BAM record only says how long it is,
 //                    so boundaries are a sequential chain; the .bai index knows a true record start for every
 //                    chunk and every 16 kb window (bai_record_starts), and every chain must land exactly on the
 //                    next anchor — a chain that starts on a true record start and is followed faithfully IS the
@@ -53,25 +53,35 @@ __device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return (uint32_t)p[
 
 enum { DL_ERR_CHAIN = 1, DL_ERR_RECORD = 2, DL_ERR_LONG = 4, DL_ERR_ORDER = 8 };
 
-// pass 0: count the records of every anchor interval; pass 1: write their offsets
-__global__ void k_rec_walk(const uint8_t* U, int64_t total, const int64_t* anchors, int32_t n_int, int32_t* cnt,
-                           const int32_t* base, int64_t* rec_start, int32_t* err) {
+// One walk per anchor interval: counts the records and writes their offsets into the interval's scratch range
+// (capacity = interval bytes / 36, a record being at least 4 + 32 bytes; range starts computed on the host).
+__global__ void k_rec_walk(const uint8_t* U, int64_t total, const int64_t* anchors, const int64_t* cap_base, int32_t n_int,
+                           int32_t* cnt, int64_t* scratch, int32_t* err) {
     int32_t i = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n_int) return;
     int64_t off = anchors[i];
     const int64_t end = anchors[i + 1];
     int32_t n = 0;
-    int64_t* out = rec_start ? rec_start + base[i] : nullptr;
+    int64_t* out = scratch + cap_base[i];
+    const int64_t cap = cap_base[i + 1] - cap_base[i];
     while (off < end) {
         if (off + 4 > total) { atomicOr(err, DL_ERR_CHAIN); break; }
         uint32_t bs = ld32(U + off);
-        if (bs < 32u || off + 4 + (int64_t)bs > total) { atomicOr(err, DL_ERR_CHAIN); break; }
-        if (out) out[n] = off;
-        n++;
+        if (bs < 32u || off + 4 + (int64_t)bs > total || n >= cap) { atomicOr(err, DL_ERR_CHAIN); break; }
+        out[n++] = off;
         off += 4 + (int64_t)bs;
     }
     if (off != end) atomicOr(err, DL_ERR_CHAIN);
-    if (!rec_start) cnt[i] = n;
+    cnt[i] = n;
+}
+// scratch ranges -> one dense array of record offsets (one warp per interval)
+__global__ void k_rec_compact(const int64_t* scratch, const int64_t* cap_base, const int32_t* cnt, const int32_t* base, int32_t n_int,
+                              int64_t* rec_start) {
+    int32_t i = (int32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int32_t)(threadIdx.x & 31u);
+    if (i >= n_int) return;
+    const int64_t* in = scratch + cap_base[i];
+    int64_t* out = rec_start + base[i];
+    for (int32_t j = lane; j < cnt[i]; j += 32) out[j] = in[j];
 }
 
 struct MetaArgs {
@@ -372,15 +382,19 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     const int32_t n_int = (int32_t)anchors.size() - 1;
 
     // ---- record boundaries
-    Dbuf d_anch, d_cnt, d_base, d_err;
-    if (!d_anch.alloc(anchors.size() * 8) || !d_cnt.alloc(((size_t)n_int + 2) * 4) || !d_base.alloc(((size_t)n_int + 2) * 4) || !d_err.alloc(16))
-        return fail("cudaMalloc failed");
+    Dbuf d_anch, d_cnt, d_base, d_err, d_capb, d_scratch;
+    std::vector<int64_t> cap_base((size_t)n_int + 1, 0);
+    for (int32_t i = 0; i < n_int; i++) cap_base[(size_t)i + 1] = cap_base[(size_t)i] + (anchors[(size_t)i + 1] - anchors[(size_t)i]) / 36 + 1;
+    if (!d_anch.alloc(anchors.size() * 8) || !d_cnt.alloc(((size_t)n_int + 2) * 4) || !d_base.alloc(((size_t)n_int + 2) * 4) || !d_err.alloc(16) ||
+        !d_capb.alloc(cap_base.size() * 8) || !d_scratch.alloc(((size_t)cap_base.back() + 1) * 8)) return fail("cudaMalloc failed");
     cudaMemcpyAsync(d_anch.p, anchors.data(), anchors.size() * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_capb.p, cap_base.data(), cap_base.size() * 8, cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(d_err.p, 0, 16, st);
     cudaMemsetAsync(d_cnt.p, 0, ((size_t)n_int + 2) * 4, st);
     int32_t n_rec = 0, h_err = 0;
     if (n_int > 0) {
-        k_rec_walk<<<(n_int + 127) / 128, 128, 0, st>>>(U.as<uint8_t>(), total, d_anch.as<int64_t>(), n_int, d_cnt.as<int32_t>(), nullptr, nullptr, d_err.as<int32_t>());
+        k_rec_walk<<<(n_int + 63) / 64, 64, 0, st>>>(U.as<uint8_t>(), total, d_anch.as<int64_t>(), d_capb.as<int64_t>(), n_int, d_cnt.as<int32_t>(),
+                                                   d_scratch.as<int64_t>(), d_err.as<int32_t>());
         if (!exscan(d_cnt.as<int32_t>(), d_base.as<int32_t>(), n_int + 1, st)) return fail("cudaMalloc failed");
         cudaMemcpyAsync(&n_rec, d_base.as<int32_t>() + n_int, 4, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(&h_err, d_err.p, 4, cudaMemcpyDeviceToHost, st);
@@ -394,7 +408,7 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     if (!d_start.alloc(nr1 * 8) || !d_keep.alloc(nr1 * 4) || !d_units.alloc(nr1 * 4) || !d_qunits.alloc(nr1 * 4) || !d_slot.alloc(nr1 * 4) ||
         !d_enc.alloc(nr1) || !d_kidx.alloc(nr1 * 4) || !d_uoff.alloc(nr1 * 4) || !d_quoff.alloc(nr1 * 4) || !d_sot.alloc(slot_of_tid.size() * 4) ||
         !d_goff.alloc(((size_t)n_slots + 1) * 8) || !d_scount.alloc(((size_t)n_slots + 1) * 4)) return fail("cudaMalloc failed");
-    k_rec_walk<<<(n_int + 127) / 128, 128, 0, st>>>(U.as<uint8_t>(), total, d_anch.as<int64_t>(), n_int, nullptr, d_base.as<int32_t>(), d_start.as<int64_t>(), d_err.as<int32_t>());
+    k_rec_compact<<<(n_int * 32 + 127) / 128, 128, 0, st>>>(d_scratch.as<int64_t>(), d_capb.as<int64_t>(), d_cnt.as<int32_t>(), d_base.as<int32_t>(), n_int, d_start.as<int64_t>());
     cudaMemcpyAsync(d_sot.p, slot_of_tid.data(), slot_of_tid.size() * 4, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_goff.p, S->ctg_off.data(), ((size_t)n_slots + 1) * 8, cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(d_scount.p, 0, ((size_t)n_slots + 1) * 4, st);
