@@ -25,7 +25,7 @@ constexpr int kWarpsPerCta = 8;
 
 // One warp per BGZF block; blocks are handed out through an atomic ticket so that the long blocks of a batch
 // do not wait behind a static assignment.
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_bgzf_inflate(const uint8_t* comp, const npz::Block* blocks, int32_t n_blocks,
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_bgzf_inflate(const uint8_t* comp, const npz::Block* blocks, int32_t n_blocks,
                                                                     uint8_t* out, int32_t* status, int32_t* ticket) {
     __shared__ npz::Tables tabs[kWarpsPerCta];
     const int wid = (int)(threadIdx.x >> 5);

@@ -44,7 +44,16 @@ struct Tables {            // per-warp shared memory (2.9 KB)
 struct Bits {              // LSB-first bit reader over the compressed bytes (lane 0 only)
     const uint8_t* p; const uint8_t* end;
     uint64_t buf; int32_t cnt; int32_t overrun;
+    NP_HD static uint32_t load32(const uint8_t* q) {     // 4 bytes at any alignment, little endian
+#ifdef __CUDA_ARCH__
+        const uint32_t* a = (const uint32_t*)((uintptr_t)q & ~(uintptr_t)3);   // two aligned words + funnel shift; the
+        return __funnelshift_r(a[0], a[1], 8u * (uint32_t)((uintptr_t)q & 3u)); // second word may lie past q+4 (buffer slack)
+#else
+        return (uint32_t)q[0] | (uint32_t)q[1] << 8 | (uint32_t)q[2] << 16 | (uint32_t)q[3] << 24;
+#endif
+    }
     NP_HD void refill() {
+        if (cnt <= 32 && p + 4 <= end) { buf |= (uint64_t)load32(p) << cnt; p += 4; cnt += 32; return; }
         while (cnt <= 56) {
             if (p < end) buf |= (uint64_t)(*p++) << cnt;
             else overrun += 8;                   // zeros past the end: an error only if they get consumed
@@ -122,16 +131,15 @@ NP_HD int decode_lit(Bits& b, const Tables& t) {
     return decode_slow(b, t.lcount, t.lsym);
 }
 
+// RFC 1951 3.2.5 tables in closed form (a local array would be rebuilt on the stack at every call):
+// lengths 3,4,..,10, 11,13,15,17, 19,23,27,31, ... 227, 258; distances 1,2,3,4, 5,7, 9,13, 17,25, ... 24577
 NP_HD int32_t len_base(int s) {     // s = symbol - 257
-    const int32_t k[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-    return k[s];
+    if (s < 8) return 3 + s;
+    if (s == 28) return 258;
+    return ((4 + (s & 3)) << ((s >> 2) - 1)) + 3;
 }
 NP_HD int32_t len_extra(int s) { return s < 8 || s == 28 ? 0 : (s - 4) >> 2; }
-NP_HD int32_t dist_base(int s) {
-    const int32_t k[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073,
-                           4097, 6145, 8193, 12289, 16385, 24577};
-    return k[s];
-}
+NP_HD int32_t dist_base(int s) { return s < 4 ? s + 1 : ((2 + (s & 1)) << ((s >> 1) - 1)) + 1; }
 NP_HD int32_t dist_extra(int s) { return s < 4 ? 0 : (s >> 1) - 1; }
 
 // reads a dynamic block header into t (lane 0)
@@ -179,6 +187,8 @@ NP_HD void set_fixed(Tables& t) {
 }
 
 // Inflates one BGZF block.  W: warp backend with lane(), width(), bcast(int32_t v) (value of lane 0) and sync().
+// (A shared-memory mirror of the recent output was tried for near matches and measured slower: the kernel is bound by
+// instruction issue — 65 warp instructions per symbol with ~5 active lanes — not by the L2 round trip of the copies.)
 // Returns OK or an ERR_* (same value on every lane).
 template <class W>
 NP_HD int inflate_block(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, Tables& t, W& w) {
@@ -222,7 +232,11 @@ NP_HD int inflate_block(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32
                 for (;;) {
                     int s = decode_lit(b, t);
                     if (s < 0) { state = 1 + ERR_CODE; break; }
-                    if (s < 256) { if (p >= (int32_t)out_len) { state = 1 + ERR_OUTPUT; break; } out[p++] = (uint8_t)s; continue; }
+                    if (s < 256) {
+                        if (p >= (int32_t)out_len) { state = 1 + ERR_OUTPUT; break; }
+                        out[p++] = (uint8_t)s;
+                        continue;
+                    }
                     if (s == 256) { state = 1; break; }
                     s -= 257;
                     if (s >= 29) { state = 1 + ERR_CODE; break; }
@@ -243,6 +257,8 @@ NP_HD int inflate_block(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32
             if (state == 1) break;
             len = w.bcast(len); dist = w.bcast(dist);
             w.sync();                                                // lane 0's literals are visible to the copiers
+            // source index of byte i: i for disjoint ranges, i mod dist when the match overlaps its own output (only
+            // the `dist` bytes before pos are read then) — no byte is both read and written within one match
             if (dist >= len) { for (int32_t i = w.lane(); i < len; i += w.width()) out[pos + i] = out[pos - dist + i]; }
             else { for (int32_t i = w.lane(); i < len; i += w.width()) out[pos + i] = out[pos - dist + i % dist]; }
             pos += len;
