@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 
+#include <sys/stat.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -269,14 +271,31 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
 
     // ---- BAM side first: everything up to the launch of the inflate needs only the BAM and its index, so the
     //      FASTA is read and parsed on the host while the GPU copies and inflates
-    BamFile bf;
-    if (!bf.open(bam, err)) { set_error("np_shard_load_gpu: " + err); return nullptr; }
-    std::vector<std::vector<uint64_t>> starts;
-    if (!bf.bai_record_starts(starts, err)) { set_error("np_shard_load_gpu: needs " + std::string(bam) + ".bai (" + err + ")"); return nullptr; }
+    // The reference ABI polishes one contig per call (nextpolish1.py:181-189): the open BAM (mmap + header), its
+    // parsed index and the name table are kept for the last path used instead of being rebuilt for every contig.
+    struct BamCache {
+        std::string path; struct stat st;
+        BamFile* bf = nullptr;
+        std::vector<std::vector<uint64_t>> starts;
+        std::unordered_map<std::string, int> tid_of;
+    };
+    static BamCache cache;
+    struct stat stnow;
+    memset(&stnow, 0, sizeof stnow);
+    if (stat(bam, &stnow) != 0) { set_error(std::string("np_shard_load_gpu: cannot stat ") + bam); return nullptr; }
+    if (!cache.bf || cache.path != bam || cache.st.st_size != stnow.st_size || cache.st.st_mtime != stnow.st_mtime || cache.st.st_ino != stnow.st_ino) {
+        delete cache.bf; cache.bf = nullptr; cache.starts.clear(); cache.tid_of.clear();
+        BamFile* nb = new BamFile();
+        if (!nb->open(bam, err)) { delete nb; set_error("np_shard_load_gpu: " + err); return nullptr; }
+        if (!nb->bai_record_starts(cache.starts, err)) { delete nb; set_error("np_shard_load_gpu: needs " + std::string(bam) + ".bai (" + err + ")"); return nullptr; }
+        cache.starts.resize(nb->header().names.size());
+        for (size_t i = 0; i < nb->header().names.size(); i++) cache.tid_of.emplace(nb->header().names[i], (int)i);
+        cache.bf = nb; cache.path = bam; cache.st = stnow;
+    }
+    BamFile& bf = *cache.bf;
+    const std::vector<std::vector<uint64_t>>& starts = cache.starts;
+    const std::unordered_map<std::string, int>& tid_of = cache.tid_of;
     const int32_t n_ref = (int32_t)bf.header().names.size();
-    starts.resize((size_t)n_ref);
-    std::unordered_map<std::string, int> tid_of;
-    for (int32_t i = 0; i < n_ref; i++) tid_of.emplace(bf.header().names[(size_t)i], i);
     int tid_min = 0x7fffffff, tid_max = -1;
     if (all) { if (n_ref > 0) { tid_min = 0; tid_max = n_ref - 1; } }
     else for (const auto& nm : names) {
