@@ -196,6 +196,11 @@ int32_t np_engine_copy_result(np_engine* e, void* dst_device, int64_t dst_cap);
 /* Device pointer of the concatenated result (for an on-device gather) and its offsets. */
 const uint8_t* np_engine_result_device(np_engine* e);
 
+/* PolishPoint trace of the last run (contig_get_contig's change list, contig.c:743-799; what nextpolish1.py -debug
+ * prints): produced only when cfg->trace_polish_open is set.  Positions are contig-relative; off[n_contigs+1]. */
+int64_t np_engine_point_count(np_engine* e);
+int32_t np_engine_points(np_engine* e, PolishPoint* out, int64_t cap, int64_t* off);
+
 /* Per-kernel device time (ms) of the last run, measured with CUDA events on the engine
  * stream; names[i] points to static strings. Returns the number of entries written. */
 int32_t np_engine_kernel_times(np_engine* e, const char** names, float* ms, int32_t cap);

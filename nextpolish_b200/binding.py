@@ -67,6 +67,7 @@ EXPORTS = [  # every symbol include/nextpolish_b200.h declares
     "np_engine_run", "np_engine_sync", "np_engine_result_bytes", "np_engine_download",
     "np_engine_result_device", "np_engine_copy_result", "np_engine_kernel_times", "np_engine_set_timing", "np_engine_launch_count", "np_engine_window_stats", "np_engine_stream",
     "np_polish_host", "np_synth_write", "np_synth_shard",
+    "np_engine_point_count", "np_engine_points",
     "np_bgzf_inflate", "np_shard_load_gpu", "np_dev_shard_view", "np_dev_shard_contig_name", "np_dev_shard_contig_rank",
     "np_dev_shard_stats", "np_dev_shard_download", "np_dev_shard_free",
     "np_stream_create", "np_stream_destroy", "np_stream_submit", "np_stream_wait", "np_stream_launch_count",
@@ -120,6 +121,9 @@ def load(path=None):
     L.np_engine_stream.restype = vp
     L.np_polish_host.argtypes = [vp, i32, C.POINTER(ShardView), C.POINTER(Configure), vp, i64, vp]
     L.np_bgzf_inflate.argtypes = [i32, vp, i64, vp, i64, vp, vp, vp]
+    L.np_engine_point_count.argtypes = [vp]
+    L.np_engine_point_count.restype = i64
+    L.np_engine_points.argtypes = [vp, vp, i64, vp]
     L.np_shard_load_gpu.argtypes = [i32, C.c_char_p, C.c_char_p, vp, i32, i32]
     L.np_shard_load_gpu.restype = vp
     L.np_dev_shard_view.argtypes = [vp, C.POINTER(ShardView)]

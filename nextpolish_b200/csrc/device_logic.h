@@ -32,6 +32,7 @@ struct Params {
     int32_t min_len_ldr, min_len_inter_kmer, max_len_kmer, max_count_kmer;
     double  max_clip_ratio_sgs;
     int32_t read_tlen;
+    int32_t trace;                 // Configure.trace_polish_open: also produce the PolishPoint trace
 };
 
 // packed record header (include/nextpolish_b200.h)

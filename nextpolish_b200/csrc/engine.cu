@@ -375,6 +375,7 @@ static void params_from_cfg(const Configure* cfg, npd::Params* P) {
     P->max_count_kmer = cfg->max_count_kmer;
     P->max_clip_ratio_sgs = cfg->max_clip_ratio_sgs;
     P->read_tlen = cfg->read_tlen;
+    P->trace = cfg->trace_polish_open ? 1 : 0;
 }
 
 }  // namespace
@@ -574,6 +575,22 @@ int32_t np_engine_download(np_engine* e, uint8_t* out_seq, int64_t out_cap, int6
     cudaStream_t s = e->be.stream;
     cudaMemcpyAsync(out_seq, e->d.out, (size_t)e->st.out_bytes, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(out_off, e->d.out_off, ((size_t)e->d.n_ctg + 1) * 8, cudaMemcpyDeviceToHost, s);
+    cudaError_t er = cudaStreamSynchronize(s);
+    if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
+    return NP_OK;
+}
+
+// PolishPoint trace of the last run (only when cfg->trace_polish_open was set): count, and a download of the points
+// (contig-relative positions, contig order) with their per-contig offsets.
+int64_t np_engine_point_count(np_engine* e) { return e && e->ran ? e->d.n_pts : -1; }
+int32_t np_engine_points(np_engine* e, PolishPoint* out, int64_t cap, int64_t* off) {
+    if (!e || !e->ran || !e->d.P.trace) { np::set_error("np_engine_points: the last run did not trace (Configure.trace_polish_open)"); return NP_ERR_ARG; }
+    if (cap < e->d.n_pts) { np::set_error("np_engine_points: buffer too small"); return NP_ERR_ARG; }
+    static_assert(sizeof(PolishPoint) == sizeof(npe::TracePoint), "PolishPoint layout");
+    cudaSetDevice(e->device);
+    cudaStream_t s = e->be.stream;
+    if (e->d.n_pts > 0) cudaMemcpyAsync(out, e->d.pts, (size_t)e->d.n_pts * sizeof(PolishPoint), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(off, e->d.pts_off, ((size_t)e->d.n_ctg + 1) * 8, cudaMemcpyDeviceToHost, s);
     cudaError_t er = cudaStreamSynchronize(s);
     if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
     return NP_OK;
@@ -789,6 +806,13 @@ static PolishResult* run_one_contig(const char* tigname, Configure* cfg, int tas
     if (rc != NP_OK) { fprintf(stderr, "nextpolish_b200: %s\n", np_last_error()); exit(1); }
     res->length = (int32_t)off[1];
     res->contig[off[1]] = '\0';
+    if (cfg->trace_polish_open) {                       // contig.c:792-797: the change trace travels with the result
+        const int64_t np_ = np_engine_point_count(e);
+        res->data = (PolishPoint*)calloc((size_t)(np_ > 0 ? np_ : 1), sizeof(PolishPoint));
+        int64_t poff[2] = {0, 0};
+        if (np_engine_points(e, res->data, np_ > 0 ? np_ : 0, poff) != NP_OK) { fprintf(stderr, "nextpolish_b200: %s\n", np_last_error()); exit(1); }
+        res->datalength = (int32_t)np_;
+    }
     if (ds) np_dev_shard_free(ds);
     return res;
 }

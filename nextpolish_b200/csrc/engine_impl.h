@@ -57,8 +57,12 @@ struct Dev {
     uint8_t*  amax;          // [T] argmax base of the column's score list
     // output
     uint8_t* out; int64_t* out_off;
+    // optional change trace (contig_get_contig's PolishPoint list, contig.c:743-799)
+    int32_t *pcnt, *poff; struct TracePoint* pts; int64_t* pts_off; int32_t n_pts;
     int32_t* err;            // device error word (0 = ok)
 };
+
+struct TracePoint { int32_t pos; int16_t index; char curbase, base; };   // PolishPoint, contig.h:10-15
 
 enum { ERR_INS_OVERFLOW = 1, ERR_DEPTH = 2, ERR_MISSING_SCORE = 4, ERR_SYM_BOUND = 8 };
 
@@ -340,6 +344,57 @@ struct OutOffsets {
     }
 };
 
+// ---- PolishPoint trace (contig.c:743-799), per draft position: a deleted main column, an emitted base that differs
+//      from the (upper-cased) draft character, and every emitted insertion sub-column are change points
+struct TraceCount {
+    Dev d; int fill;
+    template <class B> NP_HD void operator()(int64_t p, B&) const {
+        if (p >= d.G) { if (!fill) d.pcnt[p] = 0; return; }
+        const int32_t c0 = d.colbase[p], n = d.colbase[p + 1] - c0;
+        uint32_t raw = d.ctg_seq[p];
+        if (raw >= 97 && raw <= 122) raw -= 32;
+        int32_t k = 0;
+        TracePoint* out = nullptr; int32_t rel = 0;
+        if (fill) {
+            out = d.pts + d.poff[p];
+            rel = (int32_t)p - d.ctg_goff[find_contig_i32(d.ctg_goff, d.n_ctg, (int32_t)p)];
+        }
+        for (int32_t j = 0; j < n; j++) {
+            const uint32_t b = d.obase[c0 + j];
+            const char ch = (char)code_char(b);
+            bool pt; char cur, base;
+            if (b == SYM_GAP) { pt = j == 0; cur = '.'; base = (char)raw; }
+            else if (j != 0) { pt = true; cur = ch; base = '.'; }
+            else { pt = (uint32_t)(uint8_t)ch != raw; cur = ch; base = (char)raw; }
+            if (!pt) continue;
+            if (fill) out[k] = TracePoint{rel, (int16_t)j, cur, base};
+            k++;
+        }
+        if (!fill) d.pcnt[p] = k;
+    }
+};
+struct TraceOffsets {
+    Dev d;
+    template <class B> NP_HD void operator()(int64_t k, B&) const { d.pts_off[k] = k == d.n_ctg ? d.poff[d.G] : d.poff[d.ctg_goff[k]]; }
+};
+
+// after obase is final: builds the trace when Params.trace is set (every task path ends with this)
+template <class BE>
+void run_trace(BE& be, Dev& d) {
+    d.n_pts = 0;
+    if (!d.P.trace) return;
+    const int32_t G = d.G;
+    d.pcnt = be.template buf<int32_t>("pcnt", (size_t)G + 2);
+    d.poff = be.template buf<int32_t>("poff", (size_t)G + 2);
+    d.pts_off = be.template buf<int64_t>("pts_off", (size_t)d.n_ctg + 1);
+    be.launch("trace_count", (int64_t)G + 1, TraceCount{d, 0});
+    be.exscan_i32(d.pcnt, d.poff, (int64_t)G + 1);
+    d.n_pts = be.read_i32(d.poff + G);
+    d.pts = be.template buf<TracePoint>("pts", (size_t)d.n_pts + 1);
+    if (d.n_pts > 0) be.launch("trace_fill", G, TraceCount{d, 1});
+    be.launch("trace_offsets", (int64_t)d.n_ctg + 1, TraceOffsets{d});
+}
+
 }  // namespace npe
 
 // =============================================================================================
@@ -433,6 +488,7 @@ int run_score_chain(BE& be, Dev& d, RunStats* st, bool exact_sequential = false)
     d.out = be.template buf<uint8_t>("out", (size_t)total + 1);
     if (C > 0) be.launch("emit", C, Emit{d, (uint8_t)(FLAG_ZERO | FLAG_COVERAGE)});
     be.launch("out_offsets", (int64_t)d.n_ctg + 1, OutOffsets{d});
+    run_trace(be, d);
     int32_t err = be.read_i32(d.err);
     if (st) { st->C = C; st->T = d.T; st->sym_words = W; st->table_entries = E; st->out_bytes = total; }
     return err;

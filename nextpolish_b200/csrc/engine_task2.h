@@ -924,6 +924,7 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
     d.out = be.template buf<uint8_t>("out", (size_t)total + 1);
     if (C > 0) be.launch("emit", C, Emit{d, (uint8_t)FLAG_ZERO});
     be.launch("out_offsets", (int64_t)d.n_ctg + 1, OutOffsets{d});
+    run_trace(be, d);
     if (st) { st->C = C; st->T = w.NW; st->sym_words = w.NR_nd; st->table_entries = w.NR_km; st->out_bytes = total; }
     d0 = d;
     return err;

@@ -143,6 +143,7 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
     d.out = be.template buf<uint8_t>("out", (size_t)total + 1);
     if (C > 0) be.launch("emit", C, Emit{d, (uint8_t)(FLAG_ZERO | FLAG_COVERAGE)});
     be.launch("out_offsets", (int64_t)d.n_ctg + 1, OutOffsets{d});
+    run_trace(be, d);
     if (st) { st->C = C; st->T = d.T; st->sym_words = Wd; st->table_entries = E; st->out_bytes = total; }
     if (vs) { vs->W = g.W; vs->n_win = g.n_win; vs->smem = need; vs->unresolved_windows = n_unres; vs->fallback_cols = d.T; }
     return err;

@@ -391,6 +391,7 @@ int run_score_chain_v3(BE& be, Dev& d, RunStats* st) {
     d.out = be.template buf<uint8_t>("out", (size_t)total + 1);
     if (C > 0) be.launch("emit", C, Emit{d, (uint8_t)(FLAG_ZERO | FLAG_COVERAGE)});
     be.launch("out_offsets", (int64_t)d.n_ctg + 1, OutOffsets{d});
+    run_trace(be, d);
     if (st) { st->C = C; st->T = d.T; st->sym_words = n_runs; st->table_entries = E; st->out_bytes = total; }
     return err;
 }

@@ -269,6 +269,16 @@ class Engine:
         raw = out.tobytes()
         return {nm: raw[off[i]:off[i + 1]] for i, nm in enumerate(shard.names)}
 
+    def points(self, n_contigs):
+        """PolishPoint trace of the last run (cfg.contents.trace_polish_open = 1): list per contig of
+        (pos, index, curbase, base) tuples."""
+        from .binding import PolishPoint
+        n = lib().np_engine_point_count(self.h)
+        buf = (PolishPoint * max(int(n), 1))()
+        off = np.zeros(n_contigs + 1, dtype=np.int64)
+        self._check(lib().np_engine_points(self.h, buf, max(int(n), 0), off.ctypes.data))
+        return [[(buf[i].pos, buf[i].index, buf[i].curbase, buf[i].base) for i in range(off[k], off[k + 1])] for k in range(n_contigs)]
+
     def set_timing(self, on):
         lib().np_engine_set_timing(self.h, int(on))
 

@@ -15,7 +15,10 @@ Behavioural contract kept from the reference (nextpolish1.py:148-235):
     digit appended); -u uppercases;
   * Configure fields are set after config_init exactly like update_cfg() does (so read_tlen keeps the
     estimate made with the default count_read_ins_sgs / max_ins_len_sgs / max_ins_fold_sgs).
-Not supported: -debug PolishPoint traces, tasks 3-5 (exit code 1, like the reference does for task 5)."""
+  * -debug sets Configure.trace_polish_open and prints "name pos index curbase base" change points to stderr
+    (nextpolish1.py:133,230-231).
+The shard is built on the GPU from the BAM's compressed bytes when <bam>.bai exists (np_shard_load_gpu), by the host
+packer otherwise.  Not supported: tasks 3-5 (exit code 1, like the reference does for task 5)."""
 import argparse
 import os
 import sys
@@ -99,16 +102,36 @@ def main(argv=None):
               "min_len_inter_kmer", "max_len_kmer", "max_count_kmer", "count_read_ins_sgs", "max_ins_len_sgs", "max_ins_fold_sgs",
               "max_clip_ratio_sgs", "max_clip_ratio_lgs"):
         setattr(c, f, getattr(args, f))
+    c.trace_polish_open = 1 if args.debug else 0        # nextpolish1.py:133
     if names:
-        shard = E.Shard.load(args.genome, args.bam_sgs, names=names, with_qual=(2 if args.task == 2 else 0), threads=max(1, args.process))
-        eng = E.Engine(int(os.environ.get("NEXTPOLISH_B200_DEVICE", "0")))
-        seqs = eng.polish(shard, args.task, cfg)
+        dev = int(os.environ.get("NEXTPOLISH_B200_DEVICE", "0"))
+        wq = 2 if args.task == 2 else 0
+        eng = E.Engine(dev)
+        shard = None
+        if args.bam_sgs and os.path.exists(args.bam_sgs + ".bai") and os.environ.get("NEXTPOLISH_B200_HOST_LOAD") != "1":
+            try:
+                shard = E.DeviceShard(args.genome, args.bam_sgs, names=names, with_qual=wq, device=dev)
+            except E.NativeError:
+                shard = None                             # e.g. a stale index: the host packer takes over
+        if shard is not None:
+            eng.adopt_device(shard.view)
+            eng.run(args.task, cfg)
+            raw, off = eng.download(shard.n_contigs)
+            raw = raw.tobytes()
+            seqs = {nm: raw[off[i]:off[i + 1]] for i, nm in enumerate(shard.names)}
+        else:
+            shard = E.Shard.load(args.genome, args.bam_sgs, names=names, with_qual=wq, threads=max(1, args.process))
+            seqs = eng.polish(shard, args.task, cfg)
+        points = dict(zip(shard.names, eng.points(shard.n_contigs))) if args.debug else {}
         for name in names:                               # the reference's order is completion order; ours is block order
             seq = seqs[name].decode()
             if args.uppercase:
                 seq = seq.upper()
             tag = name + (str(args.task) if name.split("_")[-1].startswith("np") else "_np" + str(args.task))
             out.write(">%s %d\n%s\n" % (tag, len(seq), seq))
+            for pos, idx, cur, base in points.get(name, ()):
+                sys.stderr.write("%s %d %d %s %s\n" % (name, pos, idx, cur.decode(), base.decode()))
+        shard.close()
         eng.close()
     if out is not sys.stdout:
         out.close()

@@ -77,6 +77,7 @@ typedef struct {
     int32_t C; Col* col;
     int filter_kind;              /* 1: contig_read_fliter1, 0: contig_read_fliter */
     int32_t max_rlen;
+    PolishPoint* pts; int64_t pts_cap, npts;   /* optional change trace (contig.c:743-799) */
 } Ctg;
 
 typedef struct { int32_t* d; int n, cap; } IList;
@@ -514,16 +515,31 @@ static void score_correct(Ctg* g, int32_t start, int32_t end, int32_t flag, doub
     }
 }
 
-/* contig.c:736-799 (sequence only; the PolishPoint trace is not restated) */
+/* contig.c:736-799: the sequence and, when g->pts is set (trace_polish_open), the PolishPoint trace */
 static int64_t get_contig(Ctg* g, uint8_t flag, uint8_t* out, int64_t cap)
 {
     int64_t n = 0; uint8_t sign = 0;
+    g->npts = 0;
     for (int32_t c = 0; c <= g->colbase[g->L - 1]; c++) {
         Col* p = &g->col[c];
-        if (p->base == 3) { if ((p->flag & flag) != 0) sign = 1; }
-        else {
+        const int32_t i = g->colpos[c], j = c - g->colbase[i];
+        uint8_t raw = g->seq[i];
+        if (raw >= 'a' && raw <= 'z') raw = (uint8_t)(raw - 32);                  /* toupper(seqbase[i]) */
+        if (p->base == 3) {
+            if ((p->flag & flag) != 0) sign = 1;
+            if (g->pts && j == 0) {
+                if (g->npts >= g->pts_cap) return -1;
+                PolishPoint t = {i, (int16_t)j, '.', (char)raw};
+                g->pts[g->npts++] = t;
+            }
+        } else {
             if (n >= cap) return -1;
             uint8_t ch = (uint8_t)basetostr_[p->base];
+            if (g->pts && (j != 0 || ch != raw)) {
+                if (g->npts >= g->pts_cap) return -1;
+                PolishPoint t = {i, (int16_t)j, (char)ch, j != 0 ? '.' : (char)raw};
+                g->pts[g->npts++] = t;
+            }
             if (sign || (p->flag & flag) != 0) { ch += 32; sign = 0; }
             out[n++] = ch;
         }
@@ -759,6 +775,24 @@ int np_oracle_run_contig(const np_shard_view* v, int contig, int task, const Con
     Ctg g;
     ctg_init(&g, v, contig, cfg);
     int64_t n = task == 1 ? run_score_chain(&g, out_seq, out_cap) : run_kmer_count(&g, out_seq, out_cap);
+    ctg_free(&g);
+    if (n < 0) return -1;
+    *out_len = n;
+    return 0;
+}
+
+/* The same run with the PolishPoint trace of contig.c:743-799 (what trace_polish_open / nextpolish1.py -debug returns) */
+int np_oracle_run_contig_points(const np_shard_view* v, int contig, int task, const Configure* cfg,
+                                uint8_t* out_seq, int64_t out_cap, int64_t* out_len,
+                                PolishPoint* pts, int64_t pts_cap, int64_t* n_pts)
+{
+    if (!v || contig < 0 || contig >= v->n_contigs || (task != 1 && task != 2) || !pts) return -1;
+    if (task == 2 && !v->qual) return -1;
+    Ctg g;
+    ctg_init(&g, v, contig, cfg);
+    g.pts = pts; g.pts_cap = pts_cap;
+    int64_t n = task == 1 ? run_score_chain(&g, out_seq, out_cap) : run_kmer_count(&g, out_seq, out_cap);
+    *n_pts = g.npts;
     ctg_free(&g);
     if (n < 0) return -1;
     *out_len = n;

@@ -28,6 +28,11 @@ int np_oracle_run(const np_shard_view* shard, int task, const Configure* cfg,
 int np_oracle_run_contig(const np_shard_view* shard, int contig, int task, const Configure* cfg,
                          uint8_t* out_seq, int64_t out_cap, int64_t* out_len);
 
+/* One contig with the PolishPoint trace of contig.c:743-799 (what Configure.trace_polish_open makes the reference return). */
+int np_oracle_run_contig_points(const np_shard_view* shard, int contig, int task, const Configure* cfg,
+                                uint8_t* out_seq, int64_t out_cap, int64_t* out_len,
+                                PolishPoint* pts, int64_t pts_cap, int64_t* n_pts);
+
 /* Default thresholds exactly as config.c:11-40 (file names left NULL, read_tlen 0). */
 void np_oracle_default_config(Configure* cfg);
 

@@ -97,8 +97,19 @@ extern "C" int np_emu_run(const np_shard_view* v, int task, const Configure* cfg
 }
 // variant 1: general kernels (engine_impl.h); variant 2: fused window kernel + fallback (engine_v2.h);
 // variant 3: window-less chain of full-GPU kernels (engine_v3.h)
+static int emu_run(const np_shard_view* v, int task, const Configure* cfg, uint8_t* out_seq, int64_t out_cap, int64_t* out_off,
+                   int32_t* stats, int variant, PolishPoint* pts, int64_t pts_cap, int64_t* pts_off);
 extern "C" int np_emu_run_impl(const np_shard_view* v, int task, const Configure* cfg,
                           uint8_t* out_seq, int64_t out_cap, int64_t* out_off, int32_t* stats, int variant) {
+    return emu_run(v, task, cfg, out_seq, out_cap, out_off, stats, variant, nullptr, 0, nullptr);
+}
+// the same run with the PolishPoint trace (Configure.trace_polish_open is forced on)
+extern "C" int np_emu_run_points(const np_shard_view* v, int task, const Configure* cfg, uint8_t* out_seq, int64_t out_cap,
+                                 int64_t* out_off, int variant, PolishPoint* pts, int64_t pts_cap, int64_t* pts_off) {
+    return emu_run(v, task, cfg, out_seq, out_cap, out_off, nullptr, variant, pts, pts_cap, pts_off);
+}
+static int emu_run(const np_shard_view* v, int task, const Configure* cfg, uint8_t* out_seq, int64_t out_cap, int64_t* out_off,
+                   int32_t* stats, int variant, PolishPoint* pts, int64_t pts_cap, int64_t* pts_off) {
     npe::Dev d;
     memset(&d, 0, sizeof(d));
     std::vector<int32_t> goff((size_t)v->n_contigs + 1);
@@ -112,6 +123,7 @@ extern "C" int np_emu_run_impl(const np_shard_view* v, int task, const Configure
     d.P.min_len_inter_kmer = cfg->min_len_inter_kmer; d.P.max_len_kmer = cfg->max_len_kmer;
     d.P.max_count_kmer = cfg->max_count_kmer; d.P.max_clip_ratio_sgs = cfg->max_clip_ratio_sgs;
     d.P.read_tlen = cfg->read_tlen;
+    d.P.trace = pts ? 1 : 0;
     EmuBackend be;
     npe::RunStats st;
     npe::V2Stats vs; memset(&vs, 0, sizeof(vs));
@@ -122,6 +134,12 @@ extern "C" int np_emu_run_impl(const np_shard_view* v, int task, const Configure
     if (st.out_bytes > out_cap) return -1000;
     memcpy(out_seq, d.out, (size_t)st.out_bytes);
     for (int i = 0; i <= v->n_contigs; i++) out_off[i] = d.out_off[i];
+    if (pts) {
+        if (d.n_pts > pts_cap) return -1001;
+        static_assert(sizeof(PolishPoint) == sizeof(npe::TracePoint), "PolishPoint layout");
+        if (d.n_pts > 0) memcpy(pts, d.pts, (size_t)d.n_pts * sizeof(PolishPoint));
+        for (int i = 0; i <= v->n_contigs; i++) pts_off[i] = d.pts_off[i];
+    }
     if (stats && variant == 2) { stats[4] = vs.W; stats[5] = vs.n_win; stats[6] = vs.smem; stats[7] = vs.unresolved_windows; }
     if (stats) { stats[0] = st.C; stats[1] = st.T; stats[2] = (int32_t)st.table_entries; stats[3] = (int32_t)st.sym_words; }
     return 0;

@@ -199,7 +199,7 @@ def test_fused_kernel_deep_and_noisy_use_fallback_correctly(E, oracle, eng):
     assert eng.polish(sh, 1, cfg) == want
 
 
-def test_nextpolish1_worker_mirror(E, tmp_path):
+def test_nextpolish1_worker_mirror(E, tmp_path, capsys):
     """python -m nextpolish_b200.nextpolish1 with the reference's flags: block file, resume, header names."""
     from nextpolish_b200 import nextpolish1
     fa = os.path.join(GOLDEN, "td30.step1.fa")
@@ -222,6 +222,13 @@ def test_nextpolish1_worker_mirror(E, tmp_path):
     assert {k: v for k, v in got.items()} == {n + "_np1": exp[n + "_1"] for n in names}
     header = [l for l in open(out) if l.startswith(">")][0].split()
     assert int(header[1]) == len(got[header[0][1:]])
+    # -debug: change points on stderr, "name pos index curbase base" (nextpolish1.py:230-231), sequences unchanged
+    out2 = str(tmp_path / "dbg.fa")
+    capsys.readouterr()
+    assert nextpolish1.main(["-g", fa, "-s", bam, "-t", "1", "-b", blc_all, "-i", "0", "-o", out2, "-debug"]) == 0
+    err = capsys.readouterr().err.strip().split("\n")
+    assert read_fasta(out2) == got
+    assert len(err) > 10 and all(len(l.split()) == 5 and l.split()[0] in names for l in err)
 
 
 def test_pipelined_host_call_equals_resident_path(E, eng):
