@@ -202,37 +202,38 @@ struct RegionGroups {    // one thread per lowercase run and variant (0: no-dept
         cnt[r] = regions_from_runs(d, w.run_s, w.run_e, r, rend, gs, ge, gap, con, with_ext, ext, out);
     }
 };
-struct ContigRegions {   // one thread per contig: concatenate its groups' regions, contig_merge_region
+struct ContigRegions {   // one thread per contig and list (0: no-depth, 1: k-mer): concatenate its groups' regions, contig_merge_region
     Dev2 w;
-    template <class B> NP_HD void operator()(int64_t k, B&) const {
+    template <class B> NP_HD void operator()(int64_t it, B&) const {
         const Dev& d = w.d;
+        const int64_t k = it >> 1; const bool km_list = (it & 1) != 0;
         int32_t gs = d.ctg_goff[k], ge = d.ctg_goff[k + 1] - 1;
-        int32_t a = 0, b = 0;
+        int32_t a = 0;
         if (ge >= gs) {
             int32_t r0 = w.rs_idx[gs], r1 = w.rs_idx[ge + 1];
-            int32_t* nd = w.nd_reg + 2 * (size_t)r0 + 2 * (size_t)k;   // slack of one pair per contig
-            int32_t* km = w.km_reg + 2 * (size_t)r0 + 2 * (size_t)k;
-            for (int32_t r = r0; r < r1; r++) {
-                for (int32_t q = 0; q < w.gcnt_nd[r]; q++, a++) { nd[2 * a] = w.gnd[2 * (size_t)r + 2 * q]; nd[2 * a + 1] = w.gnd[2 * (size_t)r + 2 * q + 1]; }
-                for (int32_t q = 0; q < w.gcnt_km[r]; q++, b++) { km[2 * b] = w.gkm[2 * (size_t)r + 2 * q]; km[2 * b + 1] = w.gkm[2 * (size_t)r + 2 * q + 1]; }
-            }
-            a = merge_regions(nd, a);
-            b = merge_regions(km, b);
+            int32_t* dst = (km_list ? w.km_reg : w.nd_reg) + 2 * (size_t)r0 + 2 * (size_t)k;   // slack of one pair per contig
+            const int32_t* cnt = km_list ? w.gcnt_km : w.gcnt_nd;
+            const int32_t* src = km_list ? w.gkm : w.gnd;
+            for (int32_t r = r0; r < r1; r++)
+                for (int32_t q = 0; q < cnt[r]; q++, a++) { dst[2 * a] = src[2 * (size_t)r + 2 * q]; dst[2 * a + 1] = src[2 * (size_t)r + 2 * q + 1]; }
+            a = merge_regions(dst, a);
         }
-        w.nd_cnt[k] = a; w.km_cnt[k] = b;
-        if (k == 0) { w.nd_cnt[d.n_ctg] = 0; w.km_cnt[d.n_ctg] = 0; }
+        (km_list ? w.km_cnt : w.nd_cnt)[k] = a;
+        if (k == 0) (km_list ? w.km_cnt : w.nd_cnt)[d.n_ctg] = 0;
     }
 };
-struct CompactRegions {  // one thread per contig: copy its slices into the dense lists
+struct CompactRegions {  // COMPACT_LANES threads per contig: copy its slices into the dense lists
+    enum { COMPACT_LANES = 256 };
     Dev2 w;
-    template <class B> NP_HD void operator()(int64_t k, B&) const {
+    template <class B> NP_HD void operator()(int64_t it, B&) const {
         const Dev& d = w.d;
+        const int64_t k = it / COMPACT_LANES; const int32_t t = (int32_t)(it % COMPACT_LANES);
         int32_t gs = d.ctg_goff[k];
         int32_t r0 = w.rs_idx[gs];
         const int32_t* nd = w.nd_reg + 2 * (size_t)r0 + 2 * (size_t)k;
         const int32_t* km = w.km_reg + 2 * (size_t)r0 + 2 * (size_t)k;
-        for (int32_t i = 0; i < 2 * w.nd_cnt[k]; i++) w.ndl[2 * w.nd_off[k] + i] = nd[i];
-        for (int32_t i = 0; i < 2 * w.km_cnt[k]; i++) w.kml[2 * w.km_off[k] + i] = km[i];
+        for (int32_t i = t; i < 2 * w.nd_cnt[k]; i += COMPACT_LANES) w.ndl[2 * w.nd_off[k] + i] = nd[i];
+        for (int32_t i = t; i < 2 * w.km_cnt[k]; i += COMPACT_LANES) w.kml[2 * w.km_off[k] + i] = km[i];
     }
 };
 struct RegionDiff {      // mark the positions (start, end] of every region of both lists
@@ -822,13 +823,13 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
     w.gcnt_nd = be.template buf<int32_t>("gcnt_nd", (size_t)w.n_runs + 1);
     w.gcnt_km = be.template buf<int32_t>("gcnt_km", (size_t)w.n_runs + 1);
     if (w.n_runs > 0) be.launch("region_groups", 2 * (int64_t)w.n_runs, RegionGroups{w});
-    be.launch("contig_regions", d.n_ctg, ContigRegions{w});
+    be.launch("contig_regions", 2 * (int64_t)d.n_ctg, ContigRegions{w});
     be.exscan_i32(w.nd_cnt, w.nd_off, (int64_t)d.n_ctg + 1);
     be.exscan_i32(w.km_cnt, w.km_off, (int64_t)d.n_ctg + 1);
     { const int32_t* ptrs[2] = {w.nd_off + d.n_ctg, w.km_off + d.n_ctg}; int32_t v[2]; be.read_many(ptrs, 2, v); w.NR_nd = v[0]; w.NR_km = v[1]; }
     w.ndl = be.template buf<int32_t>("ndl", 2 * (size_t)w.NR_nd + 2);
     w.kml = be.template buf<int32_t>("kml", 2 * (size_t)w.NR_km + 2);
-    be.launch("compact_regions", d.n_ctg, CompactRegions{w});
+    be.launch("compact_regions", (int64_t)d.n_ctg * CompactRegions::COMPACT_LANES, CompactRegions{w});
     // insertion columns inside regions only
     w.inreg = be.template buf<uint8_t>("inreg", (size_t)G + 2);
     be.zero(w.inreg, (size_t)G + 2);
