@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "bgzf_inflate.h"
+#include "bgzf_inflate_dev.h"
 #include "errors.h"
 #include "hostio.h"
 #include "../../include/nextpolish_b200.h"
@@ -66,12 +67,6 @@ namespace npz_dev {
 // Asynchronous inflate of `blocks` (payload offsets relative to comp_host) into d_out (device) on `stream`:
 // inflate_launch enqueues the copies and the kernel and returns; inflate_finish synchronises the stream and
 // checks every block's status.  Used by callers that keep the bytes in HBM (devload.cu) and overlap host work.
-struct InflateJob {
-    void *d_comp = nullptr, *d_blocks = nullptr, *d_status = nullptr;
-    size_t nb = 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    cudaStream_t stream = nullptr;
-};
 int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_bytes, const std::vector<npz::Block>& blocks,
                        uint8_t* d_out, cudaStream_t stream, std::string& err) {
     j.nb = blocks.size(); j.stream = stream;

@@ -32,21 +32,10 @@
 #include <vector>
 
 #include "bgzf_inflate.h"
+#include "bgzf_inflate_dev.h"
 #include "errors.h"
 #include "hostio.h"
 #include "../../include/nextpolish_b200.h"
-
-namespace npz_dev {   // bgzf_inflate.cu
-struct InflateJob {
-    void *d_comp = nullptr, *d_blocks = nullptr, *d_status = nullptr;
-    size_t nb = 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    cudaStream_t stream = nullptr;
-};
-int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_bytes, const std::vector<npz::Block>& blocks,
-                       uint8_t* d_out, cudaStream_t stream, std::string& err);
-int32_t inflate_finish(InflateJob& j, float* kernel_ms, std::string& err);
-}
 
 namespace {
 
@@ -310,9 +299,21 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     np_dev_shard* S = new np_dev_shard();
     S->device = device;
     S->with_qual = with_qual != 0;
-    auto fail = [&](const std::string& m) { set_error("np_shard_load_gpu: " + m); cudaStreamSynchronize(st); np_dev_shard_free(S); return (np_dev_shard*)nullptr; };
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    npz_dev::InflateJob job;
+    auto fail = [&](const std::string& m) {
+        std::string ignored;
+        if (job.nb) npz_dev::inflate_finish(job, nullptr, ignored);        // an inflate in flight: wait and release its buffers
+        set_error("np_shard_load_gpu: " + m);
+        cudaStreamSynchronize(st);
+        np_dev_shard_free(S);
+        return (np_dev_shard*)nullptr;
+    };
+    struct EventPair {
+        cudaEvent_t a = nullptr, b = nullptr;
+        EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+        ~EventPair() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    } ev;
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     cudaEventRecord(e0, st);
 
     // byte range of the wanted contigs: [vbeg, vend) as virtual offsets
@@ -327,7 +328,6 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     std::vector<npz::Block> blocks; std::vector<uint64_t> coffs; int64_t total = 0;
     std::vector<int64_t> anchors;
     Dbuf U;
-    npz_dev::InflateJob job;
     if (any_reads) {
         const size_t cbeg = (size_t)(vbeg >> 16);
         const size_t cend = (vend >> 16) >= bf.size() ? bf.size() : (size_t)(vend >> 16) + 1;
@@ -482,7 +482,6 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
         fprintf(stderr, "np_shard_load_gpu: pool used %.1f MB reserved %.1f MB, device free %.1f MB\n", used / 1e6, resv / 1e6, fr / 1e6);
     }
     cudaEventElapsedTime(&S->ms_total, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     for (int32_t k = 0; k < n_slots; k++) S->ctg_read_off[(size_t)k + 1] = S->ctg_read_off[(size_t)k] + counts[(size_t)k];
     return S;
 }
