@@ -72,3 +72,23 @@ def test_missing_index_is_reported(E, tmp_path):
     shutil.copy(os.path.join(GOLDEN, "td30.step1.bam"), bam)
     with pytest.raises(E.NativeError):
         E.DeviceShard(os.path.join(GOLDEN, "td30.step1.fa"), bam)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SAMTOOLS), reason="needs oracle/_ref/samtools to index the synthetic BAM")
+def test_device_shard_edge_inputs(E, tmp_path):
+    """Contigs without reads, a FASTA contig the BAM header does not know, and a shard with no reads at all."""
+    kw = dict(seed=61, n_contigs=5, contig_len=0, min_len=300, max_len=20000, depth=8.0, lowercase_frac=0.02)
+    fa, bam = str(tmp_path / "e.fa"), str(tmp_path / "e.bam")
+    assert E.lib().np_synth_write(E.synth_params(**kw), fa.encode(), bam.encode()) == 0
+    subprocess.check_call([REF_SAMTOOLS, "index", bam])
+    with open(fa, "a") as f:                       # a contig that is not in the BAM header: goes last, no reads
+        f.write(">extra_contig\nACGTACGTTTGACCAacgtNNACGT\n")
+    host, dev = _same(E, fa, bam, None, 2)
+    assert host.names[-1] == "extra_contig"
+    _same(E, fa, bam, ["extra_contig"], 2)         # nothing to read from the BAM
+    _same(E, fa, bam, ["extra_contig", host.names[0]], 1)
+    # a BAM without any record for the requested contigs (depth 0)
+    fa0, bam0 = str(tmp_path / "z.fa"), str(tmp_path / "z.bam")
+    assert E.lib().np_synth_write(E.synth_params(seed=62, n_contigs=2, contig_len=1000, depth=0.0), fa0.encode(), bam0.encode()) == 0
+    subprocess.check_call([REF_SAMTOOLS, "index", bam0])
+    _same(E, fa0, bam0, None, 0)
