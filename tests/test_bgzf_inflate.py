@@ -73,6 +73,35 @@ def test_emulated_decoder_matches_zlib_on_golden_bam(emu, f):
     assert got == zlib_inflate(comp)
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_emulated_decoder_fuzz(emu, seed):
+    """Random payload kinds x sizes (0 .. 65280) x zlib levels / strategies, several blocks per stream."""
+    import random
+    rng = random.Random(500 + seed)
+    nrng = np.random.default_rng(rng.randrange(1 << 30))
+
+    def payload():
+        kind = rng.choice(["rand", "text", "runs", "mixed", "alphabet", "zeros"])
+        n = rng.choice([0, 1, 2, 3, 7, 63, 64, 65, 255, 256, 257, 258, 259, 1000, 4095, 4096, 5000, 20000, 65000, 65280])
+        if kind == "rand":
+            return bytes(nrng.integers(0, 256, n, dtype=np.uint8))
+        if kind == "text":
+            return (b"ACGTTTGACCAGGT" * 6000)[:n]
+        if kind == "runs":
+            return b"".join(bytes([rng.randrange(256)]) * rng.choice([1, 2, 3, 4, 5, 30, 258, 259, 600]) for _ in range(300))[:n]
+        if kind == "mixed":
+            return bytes(nrng.choice([65, 67, 71, 84, 10, 33], n).astype(np.uint8))
+        if kind == "alphabet":
+            return bytes(nrng.integers(0, rng.choice([2, 3, 5, 17, 100]), n, dtype=np.uint8))
+        return b"\0" * n
+
+    for _ in range(25):
+        comp = b"".join(bgzf_block(payload(), rng.choice(range(10)), strategy=rng.choice(
+            [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED])) for _ in range(rng.choice([1, 2, 5])))
+        rc, got, nb = inflate_with(emu.np_emu_bgzf_inflate, comp)
+        assert rc == 0 and got == zlib_inflate(comp)
+
+
 def test_emulated_decoder_rejects_corrupt_payload(emu):
     comp = bytearray(bgzf_block(b"hello hello hello hello" * 100, 6))
     comp[30] ^= 0x55
