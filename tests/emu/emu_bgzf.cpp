@@ -36,3 +36,17 @@ extern "C" int np_emu_bgzf_inflate(const uint8_t* comp, int64_t comp_bytes, uint
     }
     return 0;
 }
+
+// Record-start virtual offsets the .bai index knows for reference `tid` (BamFile::bai_record_starts) — the anchors of
+// the device-side record walk (devload.cu); exported for the CPU test that checks them against an independent parse.
+extern "C" int64_t np_emu_bai_record_starts(const char* bam, int32_t tid, uint64_t* out, int64_t cap) {
+    np::BamFile bf;
+    std::string err;
+    if (!bf.open(bam, err)) return -1;
+    std::vector<std::vector<uint64_t>> starts;
+    if (!bf.bai_record_starts(starts, err)) return -2;
+    if (tid < 0 || tid >= (int32_t)starts.size()) return 0;
+    const auto& v = starts[(size_t)tid];
+    for (size_t i = 0; i < v.size() && (int64_t)i < cap; i++) out[i] = v[i];
+    return (int64_t)v.size();
+}

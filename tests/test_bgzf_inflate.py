@@ -134,3 +134,60 @@ def test_gpu_inflate_matches_zlib_on_bams(E, synth_files):
         rc, got, nb = inflate_with(_gpu_fn(E), comp, 0)
         assert rc == 0, E.last_error()
         assert nb > 1 and got == zlib_inflate(comp), f
+
+
+def _bam_record_voffsets(comp):
+    """Independent walk (zlib + struct): virtual offset and reference id of every alignment record of a BAM."""
+    blocks, off, uoff = [], 0, 0
+    while off < len(comp):
+        xlen = struct.unpack_from("<H", comp, off + 10)[0]
+        bsize = struct.unpack_from("<H", comp, off + 16)[0] + 1
+        data = zlib.decompress(comp[off + 12 + xlen:off + bsize - 8], -15)
+        blocks.append((off, uoff, len(data)))
+        uoff += len(data)
+        off += bsize
+    u = zlib_inflate(comp)
+    l_text = struct.unpack_from("<i", u, 4)[0]
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", u, p)[0]
+    p += 4
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", u, p)[0]
+        p += 4 + l_name + 4
+    import bisect
+    ustarts = [b[1] for b in blocks]
+    recs = []
+    while p + 4 <= len(u):
+        bs = struct.unpack_from("<i", u, p)[0]
+        tid = struct.unpack_from("<i", u, p + 4)[0]
+        k = bisect.bisect_right(ustarts, p) - 1
+        while blocks[k][2] == 0 or p - blocks[k][1] >= blocks[k][2]:      # skip empty blocks / move to the owning block
+            k += 1
+        recs.append(((blocks[k][0] << 16) | (p - blocks[k][1]), tid))
+        p += 4 + bs
+    return recs
+
+
+@pytest.mark.parametrize("f", ["td30.step1.bam", "td30.step2.bam"])
+def test_index_anchors_are_record_starts(emu, f):
+    """The premise of the device-side record walk (devload.cu): every virtual offset BamFile::bai_record_starts takes
+    from the .bai (chunk begins + linear index) is the start of a record of that reference, and the first record of
+    every reference is among them."""
+    path = os.path.join(GOLDEN, f)
+    recs = _bam_record_voffsets(open(path, "rb").read())
+    emu.np_emu_bai_record_starts.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.c_int64]
+    emu.np_emu_bai_record_starts.restype = C.c_int64
+    by_tid = {}
+    for v, tid in recs:
+        by_tid.setdefault(tid, []).append(v)
+    assert by_tid
+    for tid, vs in by_tid.items():
+        if tid < 0:
+            continue
+        out = (C.c_uint64 * 100000)()
+        n = emu.np_emu_bai_record_starts(path.encode(), tid, out, 100000)
+        assert n > 0
+        anchors = [out[i] for i in range(n)]
+        assert anchors == sorted(set(anchors))
+        assert set(anchors) <= set(vs), "an index offset is not a record start of reference %d" % tid
+        assert anchors[0] == vs[0]
