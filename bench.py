@@ -379,15 +379,16 @@ def main():
     if sampler:
         sampler.start()
     ms_res = timed(step_resident, args.steps, args.warmup)
-    launches = eng.launch_count() * len(tasks) * args.steps
     # per-kernel times of the last resident step (CUDA events on the engine stream)
     ktimes = {}
     kt_by_task = {}
+    launches_per_step = 0          # kernels launched by one resident step: counted per task run below
     wstats = None
     eng.set_timing(True)
     for t in tasks:
         eng.adopt_device(views_dev[t][0])
         eng.run(t, cfg)
+        launches_per_step += eng.launch_count()
         if t == 1:
             wstats = eng.window_stats()
         eng.sync()
@@ -434,7 +435,7 @@ def main():
         "e2e": {"value": e2e, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h * len(tasks),
                 "ms_per_step": ms_e2e / args.steps,
                 "api": "np_stream_submit/np_stream_wait, depth %d" % DEPTH},
-        "gpu_launches": launches,
+        "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_kind": peak_kind,
                      "algorithmic_bytes": alg_bytes[1], "kernel_ms": kms},
