@@ -268,6 +268,30 @@ int32_t     np_dev_shard_download(const np_dev_shard* shard, uint8_t* ctg_seq, u
 void        np_dev_shard_free(np_dev_shard* shard);
 
 
+/* ---- from-files front end (pipelined): the batch form of the reference ABI's per-contig calls (score_chain / kmer_count,
+ * scorechain.c:3-15, kmercount.c:93-126) and of main.c:12-26 — draft FASTA + coordinate-sorted BGZF BAM (+ .bai) in,
+ * polished sequences in FASTA order out.  A pipeline owns `depth` slots (engine + host worker thread); a submitted job's
+ * file reads, upload, inflate and unpack overlap the kernels of the job before it.  np_files_submit returns a ticket >= 0
+ * or a negative NP_ERR_*; at most `depth` tickets may be outstanding (submitted and not yet waited for).  The arrays of a
+ * result stay valid until the next np_files_submit that reuses the slot (ticket + depth) or np_files_destroy. */
+typedef struct np_files np_files;
+typedef struct {
+    int32_t            task;
+    int32_t            n_contigs;
+    const char* const* names;      /* [n_contigs], FASTA order                                   */
+    const uint8_t*     seq;        /* polished bytes of all contigs (pinned host memory)         */
+    const int64_t*     start;      /* [n_contigs] offset of contig i in seq                      */
+    const int64_t*     len;        /* [n_contigs] polished length of contig i                    */
+    int64_t            h2d_bytes;  /* compressed BAM range + draft bases copied host -> device   */
+    int64_t            d2h_bytes;  /* polished bytes + offsets copied device -> host             */
+    float              load_ms, polish_ms;   /* host wall clock: shard construction / adopt + kernels + download */
+} np_files_result;
+np_files* np_files_create(int32_t device, int32_t depth);
+void      np_files_destroy(np_files* p);
+int64_t   np_files_submit(np_files* p, int32_t task, const char* fasta, const char* bam, const Configure* cfg);
+int32_t   np_files_wait(np_files* p, int64_t ticket, np_files_result* out);
+
+
 /* ---- seeded synthetic inputs (draft FASTA + coordinate-sorted BAM), for bench and tests -- */
 typedef struct {
     uint64_t seed;

@@ -58,6 +58,12 @@ class SynthParams(C.Structure):  # np_synth_params
     ]
 
 
+class FilesResult(C.Structure):  # np_files_result
+    _fields_ = [("task", C.c_int32), ("n_contigs", C.c_int32), ("names", C.POINTER(C.c_char_p)), ("seq", C.c_void_p),
+                ("start", C.POINTER(C.c_int64)), ("len", C.POINTER(C.c_int64)),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("load_ms", C.c_float), ("polish_ms", C.c_float)]
+
+
 EXPORTS = [  # every symbol include/nextpolish_b200.h declares
     "config_init", "config_destory", "score_chain", "kmer_count", "snp_phase", "snp_valid", "lgspolish",
     "polishresult_init", "polishresult_destory",
@@ -71,6 +77,7 @@ EXPORTS = [  # every symbol include/nextpolish_b200.h declares
     "np_bgzf_inflate", "np_shard_load_gpu", "np_dev_shard_view", "np_dev_shard_contig_name", "np_dev_shard_contig_rank",
     "np_dev_shard_stats", "np_dev_shard_download", "np_dev_shard_free",
     "np_stream_create", "np_stream_destroy", "np_stream_submit", "np_stream_wait", "np_stream_launch_count",
+    "np_files_create", "np_files_destroy", "np_files_submit", "np_files_wait",
 ]
 
 
@@ -145,6 +152,13 @@ def load(path=None):
     L.np_stream_wait.argtypes = [vp, i64]
     L.np_stream_launch_count.argtypes = [vp]
     L.np_stream_launch_count.restype = i64
+    L.np_files_create.argtypes = [i32, i32]
+    L.np_files_create.restype = vp
+    L.np_files_destroy.argtypes = [vp]
+    L.np_files_destroy.restype = None
+    L.np_files_submit.argtypes = [vp, i32, C.c_char_p, C.c_char_p, C.POINTER(Configure)]
+    L.np_files_submit.restype = i64
+    L.np_files_wait.argtypes = [vp, i64, C.POINTER(FilesResult)]
     L.np_synth_write.argtypes = [C.POINTER(SynthParams), C.c_char_p, C.c_char_p]
     L.np_synth_shard.argtypes = [C.POINTER(SynthParams), i32, i32, i32, i32]
     L.np_synth_shard.restype = vp

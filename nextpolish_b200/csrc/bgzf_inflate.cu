@@ -79,7 +79,7 @@ int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_byte
     // The compressed bytes usually sit in pageable memory (an mmap of the BAM), which the driver would stage with one
     // thread (~11 GB/s measured).  Larger ranges are copied into a grow-only pinned buffer by a few host threads
     // and go up as one asynchronous DMA; the buffer is reused by the next job only after inflate_finish synchronised.
-    static void* pinned = nullptr; static size_t pinned_bytes = 0;
+    static thread_local void* pinned = nullptr; static thread_local size_t pinned_bytes = 0;   // per host thread: loads may run concurrently
     const uint8_t* src = comp_host;
     if (comp_bytes >= (4u << 20)) {
         if (pinned_bytes < comp_bytes) {

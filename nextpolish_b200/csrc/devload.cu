@@ -24,6 +24,10 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -188,21 +192,33 @@ __global__ void k_lower_flags(const uint8_t* seq, int64_t n, int32_t* f) {
 // Stream-ordered allocations from the device's default memory pool, whose release threshold is raised once so
 // that freed blocks stay cached: a load allocates ~20 buffers (276 MB of inflated bytes among them) and
 // cudaMalloc / cudaFree would cost more than the kernels.
-static cudaStream_t g_alloc_stream = nullptr;
+// One allocation/work stream per (host thread, device): loads issued from different threads (the files pipeline runs
+// one worker thread per slot) or for different devices never share a stream, an allocation or a cached BAM handle.
+static std::mutex g_pool_mu;
 static void pool_setup(int device) {
-    static int done_for = -1;
-    if (done_for == device) return;
+    static std::set<int> done;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (done.count(device)) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         unsigned long long keep = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    done_for = device;
+    done.insert(device);
+}
+static cudaStream_t thread_stream(int device) {
+    static thread_local std::map<int, cudaStream_t> streams;
+    auto it = streams.find(device);
+    if (it != streams.end()) return it->second;
+    cudaStream_t s = nullptr;
+    cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    streams[device] = s;
+    return s;
 }
 struct Dbuf {
-    void* p = nullptr;
-    ~Dbuf() { if (p) cudaFreeAsync(p, g_alloc_stream); }
-    bool alloc(size_t bytes) { return cudaMallocAsync(&p, bytes + 256, g_alloc_stream) == cudaSuccess; }
+    void* p = nullptr; cudaStream_t st = nullptr;
+    ~Dbuf() { if (p) cudaFreeAsync(p, st); }
+    bool alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes + 256, s) == cudaSuccess; }
     template <class T> T* as() const { return (T*)p; }
 };
 
@@ -210,7 +226,7 @@ static bool exscan(const int32_t* in, int32_t* out, int n, cudaStream_t s) {
     size_t need = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, n, s);
     Dbuf tmp;
-    if (!tmp.alloc(need)) return false;
+    if (!tmp.alloc(need, s)) return false;
     cub::DeviceScan::ExclusiveSum(tmp.p, need, in, out, n, s);
     return true;                   // tmp is freed in stream order
 }
@@ -219,6 +235,7 @@ static bool exscan(const int32_t* in, int32_t* out, int n, cudaStream_t s) {
 
 struct np_dev_shard {
     int device = 0;
+    cudaStream_t stream = nullptr;     // the loading thread's stream: every buffer below was allocated on it
     std::vector<std::string> names;
     std::vector<int64_t> ctg_off, ctg_read_off;
     std::vector<int32_t> fasta_rank;
@@ -234,7 +251,7 @@ extern "C" {
 void np_dev_shard_free(np_dev_shard* s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    if (g_alloc_stream) cudaStreamSynchronize(g_alloc_stream);
+    if (s->stream) cudaStreamSynchronize(s->stream);
     delete s;
 }
 
@@ -262,28 +279,46 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     //      FASTA is read and parsed on the host while the GPU copies and inflates
     // The reference ABI polishes one contig per call (nextpolish1.py:181-189): the open BAM (mmap + header), its
     // parsed index and the name table are kept for the last path used instead of being rebuilt for every contig.
-    struct BamCache {
+    // Entries are immutable once built and handed out as shared_ptr: a thread keeps its BAM alive while another thread
+    // replaces the cache slot; the table itself is guarded by a mutex.
+    struct BamEntry {
         std::string path; struct stat st;
-        BamFile* bf = nullptr;
+        BamFile bf;
         std::vector<std::vector<uint64_t>> starts;
         std::unordered_map<std::string, int> tid_of;
     };
-    static BamCache cache;
+    static std::mutex cache_mu;
+    static std::vector<std::shared_ptr<BamEntry>> cache;          // most recently used first, at most 4 entries
     struct stat stnow;
     memset(&stnow, 0, sizeof stnow);
     if (stat(bam, &stnow) != 0) { set_error(std::string("np_shard_load_gpu: cannot stat ") + bam); return nullptr; }
-    if (!cache.bf || cache.path != bam || cache.st.st_size != stnow.st_size || cache.st.st_mtime != stnow.st_mtime || cache.st.st_ino != stnow.st_ino) {
-        delete cache.bf; cache.bf = nullptr; cache.starts.clear(); cache.tid_of.clear();
-        BamFile* nb = new BamFile();
-        if (!nb->open(bam, err)) { delete nb; set_error("np_shard_load_gpu: " + err); return nullptr; }
-        if (!nb->bai_record_starts(cache.starts, err)) { delete nb; set_error("np_shard_load_gpu: needs " + std::string(bam) + ".bai (" + err + ")"); return nullptr; }
-        cache.starts.resize(nb->header().names.size());
-        for (size_t i = 0; i < nb->header().names.size(); i++) cache.tid_of.emplace(nb->header().names[i], (int)i);
-        cache.bf = nb; cache.path = bam; cache.st = stnow;
+    std::shared_ptr<BamEntry> ent;
+    {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        for (size_t i = 0; i < cache.size(); i++) {
+            BamEntry& c = *cache[i];
+            if (c.path == bam && c.st.st_size == stnow.st_size && c.st.st_mtime == stnow.st_mtime && c.st.st_ino == stnow.st_ino) {
+                ent = cache[i];
+                cache.erase(cache.begin() + (long)i);
+                cache.insert(cache.begin(), ent);
+                break;
+            }
+        }
     }
-    BamFile& bf = *cache.bf;
-    const std::vector<std::vector<uint64_t>>& starts = cache.starts;
-    const std::unordered_map<std::string, int>& tid_of = cache.tid_of;
+    if (!ent) {
+        ent = std::make_shared<BamEntry>();
+        if (!ent->bf.open(bam, err)) { set_error("np_shard_load_gpu: " + err); return nullptr; }
+        if (!ent->bf.bai_record_starts(ent->starts, err)) { set_error("np_shard_load_gpu: needs " + std::string(bam) + ".bai (" + err + ")"); return nullptr; }
+        ent->starts.resize(ent->bf.header().names.size());
+        for (size_t i = 0; i < ent->bf.header().names.size(); i++) ent->tid_of.emplace(ent->bf.header().names[i], (int)i);
+        ent->path = bam; ent->st = stnow;
+        std::lock_guard<std::mutex> lk(cache_mu);
+        cache.insert(cache.begin(), ent);
+        if (cache.size() > 4) cache.pop_back();
+    }
+    BamFile& bf = ent->bf;
+    const std::vector<std::vector<uint64_t>>& starts = ent->starts;
+    const std::unordered_map<std::string, int>& tid_of = ent->tid_of;
     const int32_t n_ref = (int32_t)bf.header().names.size();
     int tid_min = 0x7fffffff, tid_max = -1;
     if (all) { if (n_ref > 0) { tid_min = 0; tid_max = n_ref - 1; } }
@@ -294,10 +329,9 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     lap("bam open + header + index");
 
     pool_setup(device);
-    if (!g_alloc_stream) cudaStreamCreateWithFlags(&g_alloc_stream, cudaStreamNonBlocking);
-    cudaStream_t st = g_alloc_stream;      // one stream for allocations and work: stream-ordered reuse is safe
+    cudaStream_t st = thread_stream(device);      // one stream for allocations and work: stream-ordered reuse is safe
     np_dev_shard* S = new np_dev_shard();
-    S->device = device;
+    S->device = device; S->stream = st;
     S->with_qual = with_qual != 0;
     npz_dev::InflateJob job;
     auto fail = [&](const std::string& m) {
@@ -358,7 +392,7 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
         anchors.erase(std::unique(anchors.begin(), anchors.end()), anchors.end());
         S->comp_bytes = (int64_t)ship; S->inflated_bytes = total;
         lap("bgzf_scan + anchors");
-        if (!U.alloc((size_t)total + 16)) return fail("cudaMalloc failed");
+        if (!U.alloc((size_t)total + 16, st)) return fail("cudaMalloc failed");
         if (npz_dev::inflate_launch(job, bf.data() + cbeg, ship, blocks, U.as<uint8_t>(), st, err) != NP_OK) return fail(err);
         lap("H2D (pageable) + inflate launch");
     }
@@ -386,13 +420,14 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
         if (slots[k].tid != 0x7fffffff && slot_of_tid[(size_t)slots[k].tid] < 0) slot_of_tid[(size_t)slots[k].tid] = (int32_t)k;
     }
     const int32_t n_slots = (int32_t)slots.size();
+    if (ctg_seq.size() >= 0x7fffff00ull) return fail("shard exceeds 2^31 positions: load it in several contig groups");
     S->ctg_read_off.assign((size_t)n_slots + 1, 0);
     S->seq_bytes = (int64_t)ctg_seq.size();
     lap("fasta_load + contig table");
-    if (!S->seq.alloc(ctg_seq.size() + 16)) return fail("cudaMalloc failed");
+    if (!S->seq.alloc(ctg_seq.size() + 16, st)) return fail("cudaMalloc failed");
     if (!ctg_seq.empty()) cudaMemcpyAsync(S->seq.p, ctg_seq.data(), ctg_seq.size(), cudaMemcpyHostToDevice, st);
     auto finish_empty = [&]() {
-        if (!S->rec_off.alloc(16) || !S->rec.alloc(16) || (with_qual && (!S->qual_off.alloc(16) || !S->qual.alloc(16)))) return false;
+        if (!S->rec_off.alloc(16, st) || !S->rec.alloc(16, st) || (with_qual && (!S->qual_off.alloc(16, st) || !S->qual.alloc(16, st)))) return false;
         cudaMemsetAsync(S->rec_off.p, 0, 16, st);
         if (with_qual) cudaMemsetAsync(S->qual_off.p, 0, 16, st);
         return cudaStreamSynchronize(st) == cudaSuccess;
@@ -404,8 +439,8 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     Dbuf d_anch, d_cnt, d_base, d_err, d_capb, d_scratch;
     std::vector<int64_t> cap_base((size_t)n_int + 1, 0);
     for (int32_t i = 0; i < n_int; i++) cap_base[(size_t)i + 1] = cap_base[(size_t)i] + (anchors[(size_t)i + 1] - anchors[(size_t)i]) / 36 + 1;
-    if (!d_anch.alloc(anchors.size() * 8) || !d_cnt.alloc(((size_t)n_int + 2) * 4) || !d_base.alloc(((size_t)n_int + 2) * 4) || !d_err.alloc(16) ||
-        !d_capb.alloc(cap_base.size() * 8) || !d_scratch.alloc(((size_t)cap_base.back() + 1) * 8)) return fail("cudaMalloc failed");
+    if (!d_anch.alloc(anchors.size() * 8, st) || !d_cnt.alloc(((size_t)n_int + 2) * 4, st) || !d_base.alloc(((size_t)n_int + 2) * 4, st) || !d_err.alloc(16, st) ||
+        !d_capb.alloc(cap_base.size() * 8, st) || !d_scratch.alloc(((size_t)cap_base.back() + 1) * 8, st)) return fail("cudaMalloc failed");
     cudaMemcpyAsync(d_anch.p, anchors.data(), anchors.size() * 8, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_capb.p, cap_base.data(), cap_base.size() * 8, cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(d_err.p, 0, 16, st);
@@ -424,16 +459,16 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     if (n_rec == 0) { if (!finish_empty()) return fail("cudaMalloc failed"); return S; }
     Dbuf d_start, d_keep, d_units, d_qunits, d_slot, d_enc, d_kidx, d_uoff, d_quoff, d_sot, d_goff, d_lc, d_lcf, d_scount;
     const size_t nr1 = (size_t)n_rec + 1;
-    if (!d_start.alloc(nr1 * 8) || !d_keep.alloc(nr1 * 4) || !d_units.alloc(nr1 * 4) || !d_qunits.alloc(nr1 * 4) || !d_slot.alloc(nr1 * 4) ||
-        !d_enc.alloc(nr1) || !d_kidx.alloc(nr1 * 4) || !d_uoff.alloc(nr1 * 4) || !d_quoff.alloc(nr1 * 4) || !d_sot.alloc(slot_of_tid.size() * 4) ||
-        !d_goff.alloc(((size_t)n_slots + 1) * 8) || !d_scount.alloc(((size_t)n_slots + 1) * 4)) return fail("cudaMalloc failed");
+    if (!d_start.alloc(nr1 * 8, st) || !d_keep.alloc(nr1 * 4, st) || !d_units.alloc(nr1 * 4, st) || !d_qunits.alloc(nr1 * 4, st) || !d_slot.alloc(nr1 * 4, st) ||
+        !d_enc.alloc(nr1, st) || !d_kidx.alloc(nr1 * 4, st) || !d_uoff.alloc(nr1 * 4, st) || !d_quoff.alloc(nr1 * 4, st) || !d_sot.alloc(slot_of_tid.size() * 4, st) ||
+        !d_goff.alloc(((size_t)n_slots + 1) * 8, st) || !d_scount.alloc(((size_t)n_slots + 1) * 4, st)) return fail("cudaMalloc failed");
     k_rec_compact<<<(n_int * 32 + 127) / 128, 128, 0, st>>>(d_scratch.as<int64_t>(), d_capb.as<int64_t>(), d_cnt.as<int32_t>(), d_base.as<int32_t>(), n_int, d_start.as<int64_t>());
     cudaMemcpyAsync(d_sot.p, slot_of_tid.data(), slot_of_tid.size() * 4, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_goff.p, S->ctg_off.data(), ((size_t)n_slots + 1) * 8, cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(d_scount.p, 0, ((size_t)n_slots + 1) * 4, st);
     const int64_t G = (int64_t)ctg_seq.size();
     if (with_qual == 2) {
-        if (!d_lc.alloc(((size_t)G + 2) * 4) || !d_lcf.alloc(((size_t)G + 2) * 4)) return fail("cudaMalloc failed");
+        if (!d_lc.alloc(((size_t)G + 2) * 4, st) || !d_lcf.alloc(((size_t)G + 2) * 4, st)) return fail("cudaMalloc failed");
         k_lower_flags<<<(unsigned)((G + 1 + 255) / 256), 256, 0, st>>>(S->seq.as<uint8_t>(), G, d_lcf.as<int32_t>());
         if (!exscan(d_lcf.as<int32_t>(), d_lc.as<int32_t>(), (int)(G + 1), st)) return fail("cudaMalloc failed");
     }
@@ -459,8 +494,8 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     }
     const int32_t n_keep = tot[0];
     S->n_reads = n_keep; S->rec_bytes = (int64_t)tot[1] * 16; S->qual_bytes = (int64_t)tot[2] * 16;
-    if (!S->rec_off.alloc(((size_t)n_keep + 1) * 4) || !S->rec.alloc((size_t)S->rec_bytes + 16) ||
-        (with_qual && (!S->qual_off.alloc(((size_t)n_keep + 1) * 4) || !S->qual.alloc((size_t)S->qual_bytes + 16)))) return fail("cudaMalloc failed");
+    if (!S->rec_off.alloc(((size_t)n_keep + 1) * 4, st) || !S->rec.alloc((size_t)S->rec_bytes + 16, st) ||
+        (with_qual && (!S->qual_off.alloc(((size_t)n_keep + 1) * 4, st) || !S->qual.alloc((size_t)S->qual_bytes + 16, st)))) return fail("cudaMalloc failed");
     cudaMemsetAsync(S->rec.p, 0, (size_t)S->rec_bytes + 16, st);
     if (with_qual) cudaMemsetAsync(S->qual.p, 0, (size_t)S->qual_bytes + 16, st);
     PackArgs pa{U.as<uint8_t>(), d_start.as<int64_t>(), n_rec, d_keep.as<int32_t>(), d_kidx.as<int32_t>(), d_uoff.as<int32_t>(), d_quoff.as<int32_t>(),

@@ -199,6 +199,7 @@ struct CudaBackend {
     struct Timed { const char* name; cudaEvent_t a, b; };
     std::vector<Timed> timed; size_t n_timed = 0; bool timing = false;   // off unless np_engine_set_timing(e, 1)
     int32_t launches = 0;
+    int32_t attr_set = 0;          // dynamic shared memory opted in for k_window on THIS engine's device (per context)
 
     void fail(const char* what, cudaError_t e) {
         if (ok) { ok = false; msg = std::string(what) + ": " + cudaGetErrorString(e); }
@@ -312,11 +313,12 @@ struct CudaBackend {
     }
     void run_windows(const npe::Dev& d, const npw::WinGlobals& g, int32_t smem_bytes) {
         if (!ok) return;
-        static int32_t attr_set = 0;
         int32_t want = smem_bytes + 256;
-        if (want > attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
-            attr_set = want;
+        if (!attr_set) {
+            // the device-wide maximum, once per engine (= per device context): the attribute is a ceiling, not a reservation,
+            // so engines with different needs on one device cannot lower each other's limit
+            CUDA_TRY(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set = 1;
         }
         npw::WinGlobals gg = g;
         gg.phase_cycles = nullptr;

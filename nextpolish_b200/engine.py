@@ -224,6 +224,60 @@ class Stream:
             pass
 
 
+class FilePipeline:
+    """np_files: FASTA + BAM (+ .bai) files -> polished sequences on the host, `depth` jobs in flight (each slot = engine +
+    host worker thread; load, upload, inflate and unpack of one job overlap the kernels of the other)."""
+
+    def __init__(self, device=0, depth=2):
+        self.h = lib().np_files_create(device, depth)
+        if not self.h:
+            raise NativeError(last_error())
+        self.tickets = []
+
+    def submit(self, task, fasta, bam, cfg):
+        t = lib().np_files_submit(self.h, task, fasta.encode(), bam.encode(), cfg)
+        if t < 0:
+            raise NativeError("rc=%d: %s" % (t, last_error()))
+        self.tickets.append(t)
+        return t
+
+    def in_flight(self):
+        return len(self.tickets)
+
+    def wait_oldest(self, want_seqs=False):
+        """Finishes the oldest outstanding job -> dict(task, names, md5 {name: hex}, h2d_bytes, d2h_bytes[, seqs])."""
+        import hashlib
+        from .binding import FilesResult
+        t = self.tickets.pop(0)
+        r = FilesResult()
+        rc = lib().np_files_wait(self.h, t, C.byref(r))
+        if rc != 0:
+            raise NativeError("rc=%d: %s" % (rc, last_error()))
+        names = [r.names[i].decode() for i in range(r.n_contigs)]
+        out = {"task": r.task, "names": names, "h2d_bytes": r.h2d_bytes, "d2h_bytes": r.d2h_bytes,
+               "load_ms": r.load_ms, "polish_ms": r.polish_ms, "md5": {}}
+        seqs = {}
+        for i, nm in enumerate(names):
+            b = C.string_at(r.seq + r.start[i], r.len[i])
+            out["md5"][nm] = hashlib.md5(b).hexdigest()
+            if want_seqs:
+                seqs[nm] = b
+        if want_seqs:
+            out["seqs"] = seqs
+        return out
+
+    def close(self):
+        if self.h:
+            lib().np_files_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     """One GPU's polishing engine (np_engine). Creating it fails loudly without a CUDA device."""
 
