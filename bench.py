@@ -354,7 +354,6 @@ def main_ours(args, tasks):
     HDR = FixedGather.HEADER
     fixed_gather = FixedGather(cap, dev, slots=GSLOTS) if world > 1 else None
     gbufs = [torch.zeros(cap + HDR, dtype=torch.uint8, device=dev) for _ in range(GSLOTS)]
-    ghdr = [torch.zeros(HDR, dtype=torch.uint8).pin_memory() for _ in range(GSLOTS)]
     gready = [torch.cuda.Event() for _ in range(GSLOTS)]
     gdone = [None] * GSLOTS
     gstate = {"job": 0}
@@ -366,13 +365,13 @@ def main_ours(args, tasks):
         j = gstate["job"] % GSLOTS
         gstate["job"] += 1
         b = gbufs[j]
-        with torch.cuda.stream(estream):
-            if gdone[j] is not None:
-                estream.wait_event(gdone[j])                 # the gather that last read this buffer is over
-            ghdr[j].view(torch.int64)[0] = int(eng.result_bytes())
-            b[:HDR].copy_(ghdr[j], non_blocking=True)
-            E.lib().np_engine_copy_result(eng.h, b.data_ptr() + HDR, cap)
-            gready[j].record(estream)
+        if gdone[j] is not None:
+            estream.wait_event(gdone[j])                     # the gather that last read this buffer is over
+        # header (byte count) + polished bytes, written by the engine on its own stream from device memory: no torch
+        # tensor op ever runs on the engine's stream, so torch's allocators hold no reference to it at shutdown
+        rc = E.lib().np_engine_pack_result(eng.h, b.data_ptr(), cap + HDR)
+        assert rc == 0, E.last_error()
+        gready[j].record(estream)
         if world > 1:
             cur = torch.cuda.current_stream(dev)
             cur.wait_event(gready[j])
@@ -553,6 +552,9 @@ def main_ours(args, tasks):
                 base["task2_sensitivity"] = {"error": repr(ex)}
         line = json.dumps(base)
 
+    if line:
+        print(line)
+        sys.stdout.flush()
     # ordered shutdown: engines / pipelines (their CUDA streams) first, then the process group; the interpreter then
     # exits normally (no os._exit) so that exit hooks run
     torch.cuda.synchronize()
@@ -566,9 +568,6 @@ def main_ours(args, tasks):
         dist.barrier()
         dist.destroy_process_group()
     shutil.rmtree(tmp, ignore_errors=True)
-    if line:
-        print(line)
-        sys.stdout.flush()
 
 
 def task2_dense_run(E, eng, cfg, dev, args):

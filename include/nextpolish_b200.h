@@ -193,6 +193,9 @@ int32_t np_engine_download(np_engine* e, uint8_t* out_seq, int64_t out_cap, int6
 /* Copy the concatenated result into another DEVICE buffer (asynchronous on the engine stream);
  * used for the on-device gather of the corrected FASTA across GPUs. */
 int32_t np_engine_copy_result(np_engine* e, void* dst_device, int64_t dst_cap);
+/* The same with a 16-byte header in front (int64 byte count + padding), all written from device memory on the engine
+ * stream: the per-rank buffer of the multi-GPU gather.  dst_cap >= result bytes + 16. */
+int32_t np_engine_pack_result(np_engine* e, void* dst_device, int64_t dst_cap);
 /* Device pointer of the concatenated result (for an on-device gather) and its offsets. */
 const uint8_t* np_engine_result_device(np_engine* e);
 

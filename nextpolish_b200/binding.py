@@ -71,7 +71,7 @@ EXPORTS = [  # every symbol include/nextpolish_b200.h declares
     "np_shard_algorithmic_bytes",
     "np_engine_create", "np_engine_destroy", "np_last_error", "np_engine_upload", "np_engine_adopt_device",
     "np_engine_run", "np_engine_sync", "np_engine_result_bytes", "np_engine_download",
-    "np_engine_result_device", "np_engine_copy_result", "np_engine_kernel_times", "np_engine_set_timing", "np_engine_launch_count", "np_engine_window_stats", "np_engine_stream",
+    "np_engine_result_device", "np_engine_copy_result", "np_engine_pack_result", "np_engine_kernel_times", "np_engine_set_timing", "np_engine_launch_count", "np_engine_window_stats", "np_engine_stream",
     "np_polish_host", "np_synth_write", "np_synth_shard",
     "np_engine_point_count", "np_engine_points",
     "np_bgzf_inflate", "np_shard_load_gpu", "np_dev_shard_view", "np_dev_shard_contig_name", "np_dev_shard_contig_rank",
@@ -117,6 +117,7 @@ def load(path=None):
     L.np_engine_result_bytes.restype = i64
     L.np_engine_download.argtypes = [vp, vp, i64, vp]
     L.np_engine_copy_result.argtypes = [vp, vp, i64]
+    L.np_engine_pack_result.argtypes = [vp, vp, i64]
     L.np_engine_result_device.argtypes = [vp]
     L.np_engine_result_device.restype = vp
     L.np_engine_kernel_times.argtypes = [vp, vp, vp, i32]

@@ -17,6 +17,24 @@ const std::string& get_error() { return g_err; }
 
 struct np_shard { np::Shard s; };
 
+// NEXTPOLISH_B200_BACKTRACE=1: print a native backtrace on SIGSEGV / SIGABRT (debugging aid; addresses resolve with
+// addr2line -e nextpolish1.so since the library is built with -lineinfo / symbols)
+#include <execinfo.h>
+#include <signal.h>
+static void np_crash_handler(int sig) {
+    void* frames[64];
+    int n = backtrace(frames, 64);
+    const char msg[] = "nextpolish_b200: fatal signal, native backtrace:\n";
+    if (write(2, msg, sizeof msg - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+__attribute__((constructor)) static void np_install_crash_handler() {
+    const char* e = getenv("NEXTPOLISH_B200_BACKTRACE");
+    if (e && e[0] == '1') { signal(SIGSEGV, np_crash_handler); signal(SIGABRT, np_crash_handler); signal(SIGBUS, np_crash_handler); }
+}
+
 extern "C" {
 
 const char* np_last_error(void) { return np::get_error().c_str(); }

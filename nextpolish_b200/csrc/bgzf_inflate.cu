@@ -92,9 +92,10 @@ int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_byte
             const size_t nt = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
             std::vector<std::thread> th;
             const size_t step = (comp_bytes + nt - 1) / nt;
+            uint8_t* const pin = (uint8_t*)pinned;      // a thread_local is not captured: the helper threads need the value
             for (size_t t = 1; t < nt; t++) {
                 const size_t a = t * step, b = std::min(comp_bytes, a + step);
-                if (a < b) th.emplace_back([=] { memcpy((uint8_t*)pinned + a, comp_host + a, b - a); });
+                if (a < b) th.emplace_back([=] { memcpy(pin + a, comp_host + a, b - a); });
             }
             memcpy(pinned, comp_host, std::min(step, comp_bytes));
             for (auto& x : th) x.join();

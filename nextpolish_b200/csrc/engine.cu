@@ -614,6 +614,20 @@ int32_t np_engine_copy_result(np_engine* e, void* dst_device, int64_t dst_cap) {
     return NP_OK;
 }
 
+// The gather form: a 16-byte header (int64 byte count, 8 bytes of padding) followed by the polished bytes, written on the
+// engine stream entirely from device memory (the count comes from out_off[n_contigs]): one buffer per rank is what the
+// single collective of the path moves.
+int32_t np_engine_pack_result(np_engine* e, void* dst_device, int64_t dst_cap) {
+    if (!e || !e->ran || dst_cap < e->st.out_bytes + 16) { np::set_error("np_engine_pack_result: bad arguments"); return NP_ERR_ARG; }
+    cudaSetDevice(e->device);
+    cudaStream_t s = e->be.stream;
+    cudaMemsetAsync(dst_device, 0, 16, s);
+    cudaMemcpyAsync(dst_device, e->d.out_off + e->d.n_ctg, 8, cudaMemcpyDeviceToDevice, s);
+    cudaError_t er = cudaMemcpyAsync((uint8_t*)dst_device + 16, e->d.out, (size_t)e->st.out_bytes, cudaMemcpyDeviceToDevice, s);
+    if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
+    return NP_OK;
+}
+
 int32_t np_engine_kernel_times(np_engine* e, const char** names, float* ms, int32_t cap) {
     if (!e) return 0;
     cudaSetDevice(e->device);
