@@ -18,7 +18,6 @@
 
 #include "engine_task2.h"
 #include "engine_v2.h"
-#include "engine_v3.h"
 #include "errors.h"
 #include "hostio.h"
 #include "../../include/nextpolish_b200.h"
@@ -96,6 +95,22 @@ struct CudaOps {
         (void)scratch; (void)v; return 0;
 #endif
     }
+    // warp-aggregated reservation of n items from a global counter: EVERY lane of the warp must call it
+    __host__ __device__ __forceinline__ int32_t reserve(int32_t* ctr, int32_t n) {
+#ifdef __CUDA_ARCH__
+        const int lane = threadIdx.x & 31;
+        int32_t inc = n;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        int32_t base = 0;
+        const int32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == 31 && total > 0) base = atomicAdd(ctr, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        return base + inc - n;
+#else
+        (void)ctr; (void)n; return 0;
+#endif
+    }
     __host__ __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) {
 #ifdef __CUDA_ARCH__
         atomicOr(p, v);
@@ -111,7 +126,15 @@ __global__ void __launch_bounds__(256) k_items(int64_t n, F f) {
     if (i < n) { CudaOps ops; f(i, ops); }
 }
 
-// ---- fused window kernel: one CTA per pileup window, records staged by one 1-D bulk copy (TMA) ----
+// every thread of the grid calls f (i may be >= n): for functors with warp-collective operations
+template <class F>
+__global__ void __launch_bounds__(256) k_items_full(int64_t n, F f) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    (void)n;
+    CudaOps ops; f(i, ops);
+}
+
+// ---- tile kernels of the column pass (column_pass.h): one CTA per tile of TW draft positions ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -131,50 +154,117 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
     } while (!done);
 }
 
-constexpr int kWinThreads = 192;   // 4 CTAs x 6 warps per SM at ~55 KB of shared memory per CTA
-
-__global__ void __launch_bounds__(kWinThreads, 4) k_window(npe::Dev d, npw::WinGlobals g) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    npw::WCtx x; x.d = d; x.g = g;
-    npw::win_setup(x, (int32_t)blockIdx.x, smem);
-    const int tid = threadIdx.x, nt = blockDim.x;
-    CudaOps ops;
-    long long t_prev = 0;
-    const bool stamp = g.phase_cycles != nullptr && tid == 0;
-    if (stamp) t_prev = clock64();
-#define NP_STAMP(k) do { if (stamp) { long long t_ = clock64(); atomicAdd(&g.phase_cycles[k], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
-    const uint32_t bar = smem_u32(smem);
-    const uint32_t recbytes = (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u;
-    if (tid == 0) {
+// The tile's cov slice (and nothing else: colbase and the draft are read through L1) is staged into shared memory by
+// one bulk copy while the threads compute their slices.  Slices longer than the staged area read global memory.
+struct CovStage {
+    const int32_t* base;     // cov of column c at base[c - c0]
+    int32_t c0, c1;          // staged columns [c0, c1)
+    __device__ __forceinline__ const int32_t* at(const int32_t* gcov, int32_t ca, int32_t cb) const {
+        return (ca >= c0 && cb <= c1) ? base + (ca - c0) : gcov + ca;
+    }
+};
+__device__ __forceinline__ CovStage stage_cov(const npc::ColGlobals& g, const npc::Tile& t, int32_t* s_cov, uint32_t bar) {
+    CovStage cs;
+    const int32_t c0 = t.cbeg & ~3;                                   // 16-byte aligned source
+    int32_t n = ((t.cend - c0) + 3) & ~3;
+    if (n > npc::COV_CAP) n = npc::COV_CAP & ~3;
+    cs.base = s_cov; cs.c0 = c0; cs.c1 = c0 + n;
+    if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)n * 4u);
+        bulk_g2s(smem_u32(s_cov), g.cov + c0, (uint32_t)n * 4u, bar);
     }
+    return cs;
+}
+
+__global__ void __launch_bounds__(npc::TT) k_tile_agg(npe::Dev d, npc::ColGlobals g) {
+    __shared__ __align__(128) int32_t s_cov[npc::COV_CAP];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int32_t s_red[2 * (npc::TT / 32)];
+    const int32_t w = (int32_t)blockIdx.x, tid = (int32_t)threadIdx.x;
+    const npc::Tile t = npc::tile_of(d, g, w);
+    const uint32_t bar = smem_u32(&s_bar);
+    const CovStage cs = stage_cov(g, t, s_cov, bar);
+    const npc::Slice sl = npc::slice_of(d, t, tid);
+    __syncthreads();                                   // the barrier is initialised
+    mbar_wait(bar, 0);
+    int32_t a, b;
+    npc::slice_sums(d, g, t, sl, cs.at(g.cov, sl.ca, sl.cb), a, b);
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if ((tid & 31) == 0) { s_red[tid >> 5] = a; s_red[npc::TT / 32 + (tid >> 5)] = b; }
     __syncthreads();
-    if (tid == 0 && recbytes) {
-        mbar_expect_tx(bar, recbytes);
-        const uint8_t* src = d.rec + (size_t)d.rec_off[x.rlo] * 16;
-        // one bulk copy per <= 64 KiB piece keeps each transfer's byte count small
-        uint32_t done = 0;
-        while (done < recbytes) {
-            uint32_t piece = recbytes - done > 65536u ? 65536u : recbytes - done;
-            bulk_g2s(smem_u32(x.rec) + done, src + done, piece, bar);
-            done += piece;
+    if (tid == 0) {
+        int32_t sa = 0, sb = 0;
+        for (int i = 0; i < npc::TT / 32; i++) { sa += s_red[i]; sb += s_red[npc::TT / 32 + i]; }
+        g.tile_cov[w] = sa; g.tile_tbl[w] = sb;
+    }
+}
+// exclusive prefix of the tile aggregates, in place; [n_tiles] = totals (one CTA)
+__global__ void __launch_bounds__(1024) k_tile_scan(npc::ColGlobals g) {
+    __shared__ int32_t s_a[32], s_b[32];
+    __shared__ int32_t carry[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { carry[0] = 0; carry[1] = 0; }
+    __syncthreads();
+    for (int32_t base = 0; base <= g.n_tiles; base += 1024) {
+        const int32_t i = base + tid;
+        const int32_t va = i < g.n_tiles ? g.tile_cov[i] : 0, vb = i < g.n_tiles ? g.tile_tbl[i] : 0;
+        int32_t ia = va, ib = vb;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia += ta; ib += tb; }
         }
+        if (lane == 31) { s_a[wid] = ia; s_b[wid] = ib; }
+        __syncthreads();
+        if (wid == 0) {
+            int32_t wa = s_a[lane], wb = s_b[lane], xa = wa, xb = wb;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
+                if (lane >= o) { xa += ta; xb += tb; }
+            }
+            s_a[lane] = xa - wa; s_b[lane] = xb - wb;
+        }
+        __syncthreads();
+        const int32_t ea = carry[0] + s_a[wid] + ia - va, eb = carry[1] + s_b[wid] + ib - vb;
+        if (i <= g.n_tiles) { g.tile_cov[i] = ea; g.tile_tbl[i] = eb; }
+        __syncthreads();
+        if (tid == 1023) { carry[0] = ea + va; carry[1] = eb + vb; }
+        __syncthreads();
     }
-    // overlap with the copy: record offsets, clears, draft symbols
-    uint32_t* ro = const_cast<uint32_t*>(x.recoff);
-    for (int i = tid; i <= x.nr; i += nt) ro[i] = d.rec_off[x.rlo + i];
-    npw::Prefetch pf;
-    npw::ph_prefetch(x, tid, nt, pf);
-    npw::ph_clear(x, tid, nt, pf);
+}
+__global__ void __launch_bounds__(npc::TT) k_col_pass(npe::Dev d, npc::ColGlobals g) {
+    __shared__ __align__(128) int32_t s_cov[npc::COV_CAP];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int32_t s_a[npc::TT / 32], s_b[npc::TT / 32];
+    const int32_t w = (int32_t)blockIdx.x, tid = (int32_t)threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const npc::Tile t = npc::tile_of(d, g, w);
+    const uint32_t bar = smem_u32(&s_bar);
+    const CovStage cs = stage_cov(g, t, s_cov, bar);
+    const npc::Slice sl = npc::slice_of(d, t, tid);
+    const int32_t carry_cov = g.tile_cov[w], carry_tbl = g.tile_tbl[w];
     __syncthreads();
-    npw::ph_ref(x, tid, nt, ops, pf);
-    NP_STAMP(0);
-    if (recbytes) mbar_wait(bar, 0);
+    mbar_wait(bar, 0);
+    const int32_t* cov = cs.at(g.cov, sl.ca, sl.cb);
+    int32_t a, b;
+    npc::slice_sums(d, g, t, sl, cov, a, b);
+    // block-wide exclusive scan of both sums (warp shuffles + one shared-memory hop)
+    int32_t ia = a, ib = b;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) { s_a[wid] = ia; s_b[wid] = ib; }
     __syncthreads();
-    NP_STAMP(1);
-    NP_WINDOW_PHASES(x, tid, nt, ops, __syncthreads(), NP_STAMP)
-    NP_STAMP(6);
+    int32_t wa = 0, wb = 0;
+    #pragma unroll
+    for (int i = 0; i < npc::TT / 32; i++) if (i < wid) { wa += s_a[i]; wb += s_b[i]; }
+    CudaOps ops;
+    npc::slice_walk(d, g, t, sl, cov, carry_cov + wa + ia - a, carry_tbl + wb + ib - b, ops);
 }
 
 struct NcolOp {   // 1 + insertion length (0 past the end): column count of a position
@@ -199,7 +289,6 @@ struct CudaBackend {
     struct Timed { const char* name; cudaEvent_t a, b; };
     std::vector<Timed> timed; size_t n_timed = 0; bool timing = false;   // off unless np_engine_set_timing(e, 1)
     int32_t launches = 0;
-    int32_t attr_set = 0;          // dynamic shared memory opted in for k_window on THIS engine's device (per context)
 
     void fail(const char* what, cudaError_t e) {
         if (ok) { ok = false; msg = std::string(what) + ": " + cudaGetErrorString(e); }
@@ -237,6 +326,15 @@ struct CudaBackend {
         begin_timed(name);
         int64_t blocks = (n + 255) / 256;
         k_items<F><<<(unsigned)blocks, 256, 0, stream>>>(n, f);
+        CUDA_TRY(cudaGetLastError());
+        launches++;
+        end_timed();
+    }
+    template <class F> void launch_full(const char* name, int64_t n, const F& f) {
+        if (!ok || n <= 0) return;
+        begin_timed(name);
+        int64_t blocks = (n + 255) / 256;
+        k_items_full<F><<<(unsigned)blocks, 256, 0, stream>>>(n, f);
         CUDA_TRY(cudaGetLastError());
         launches++;
         end_timed();
@@ -311,32 +409,19 @@ struct CudaBackend {
         }
         return p;
     }
-    void run_windows(const npe::Dev& d, const npw::WinGlobals& g, int32_t smem_bytes) {
-        if (!ok) return;
-        int32_t want = smem_bytes + 256;
-        if (!attr_set) {
-            // the device-wide maximum, once per engine (= per device context): the attribute is a ceiling, not a reservation,
-            // so engines with different needs on one device cannot lower each other's limit
-            CUDA_TRY(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_set = 1;
-        }
-        npw::WinGlobals gg = g;
-        gg.phase_cycles = nullptr;
-        if (getenv("NEXTPOLISH_B200_PHASE_CYCLES")) {            // tuning only
-            gg.phase_cycles = (unsigned long long*)buf<unsigned long long>("phase_cycles", 16);
-            CUDA_TRY(cudaMemsetAsync(gg.phase_cycles, 0, 16 * sizeof(unsigned long long), stream));
-        }
-        int threads = kWinThreads;
-        if (const char* ev = getenv("NEXTPOLISH_B200_WIN_THREADS")) { int v = atoi(ev); if (v >= 64 && v <= kWinThreads && v % 32 == 0) threads = v; }   // tuning only
+    void tile_aggregates(const npe::Dev& d, const npc::ColGlobals& g) {
+        if (!ok || g.n_tiles <= 0) return;
+        begin_timed("tile_agg");
+        k_tile_agg<<<(unsigned)g.n_tiles, npc::TT, 0, stream>>>(d, g);
+        k_tile_scan<<<1, 1024, 0, stream>>>(g);
+        CUDA_TRY(cudaGetLastError());
+        launches += 2;
+        end_timed();
+    }
+    void column_pass(const npe::Dev& d, const npc::ColGlobals& g) {
+        if (!ok || g.n_tiles <= 0) return;
         begin_timed("pileup_scan");
-        k_window<<<(unsigned)g.n_win, threads, (size_t)want, stream>>>(d, gg);
-        if (gg.phase_cycles) {
-            unsigned long long h[16];
-            CUDA_TRY(cudaMemcpyAsync(h, gg.phase_cycles, sizeof(h), cudaMemcpyDeviceToHost, stream));
-            CUDA_TRY(cudaStreamSynchronize(stream));
-            fprintf(stderr, "k_window phase cycles per CTA (thread 0): clear+ref %llu, wait-stage %llu, compare %llu, scan+mark %llu, votes+tally %llu, chain+anchors %llu, finish %llu\n",
-                    h[0] / g.n_win, h[1] / g.n_win, h[2] / g.n_win, h[3] / g.n_win, h[4] / g.n_win, h[5] / g.n_win, h[6] / g.n_win);
-        }
+        k_col_pass<<<(unsigned)g.n_tiles, npc::TT, 0, stream>>>(d, g);
         CUDA_TRY(cudaGetLastError());
         launches++;
         end_timed();
@@ -538,9 +623,7 @@ int32_t np_engine_run(np_engine* e, int32_t task, const Configure* cfg) {
     int err;
     if (task == NP_TASK_SCORE_CHAIN) {
         const char* v1 = getenv("NEXTPOLISH_B200_GENERAL_KERNELS");     // debugging / A-B timing only
-        const char* v3 = getenv("NEXTPOLISH_B200_V3");                     // A/B: window-less kernel chain (engine_v3.h)
         if (v1 && v1[0] == '1') err = npe::run_score_chain(e->be, e->d, &e->st, !npe::rate_is_dyadic(e->d.P.rate));
-        else if (v3 && v3[0] == '1') err = npe::run_score_chain_v3(e->be, e->d, &e->st);
         else err = npe::run_score_chain_v2(e->be, e->d, e->h_ctg_off.data(), &e->st, &e->vs);
     }
     else if (task == NP_TASK_KMER_COUNT) {

@@ -68,8 +68,8 @@ def emu():
             os.path.join(ROOT, "nextpolish_b200", "csrc", "engine_impl.h"),
             os.path.join(ROOT, "nextpolish_b200", "csrc", "engine_task2.h"),
             os.path.join(ROOT, "nextpolish_b200", "csrc", "engine_v2.h"),
-            os.path.join(ROOT, "nextpolish_b200", "csrc", "engine_v3.h"),
-            os.path.join(ROOT, "nextpolish_b200", "csrc", "window_kernel.h"),
+            os.path.join(ROOT, "nextpolish_b200", "csrc", "diff_pass.h"),
+            os.path.join(ROOT, "nextpolish_b200", "csrc", "column_pass.h"),
             os.path.join(ROOT, "nextpolish_b200", "csrc", "device_logic.h")]
     extra = [os.path.join(ROOT, "tests", "emu", "emu_bgzf.cpp"), os.path.join(ROOT, "nextpolish_b200", "csrc", "hostio.cpp")]
     srcs += extra + [os.path.join(ROOT, "nextpolish_b200", "csrc", "bgzf_inflate.h"), os.path.join(ROOT, "nextpolish_b200", "csrc", "hostio.h")]

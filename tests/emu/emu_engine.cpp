@@ -11,7 +11,6 @@
 #include <vector>
 #include "../../nextpolish_b200/csrc/engine_task2.h"
 #include "../../nextpolish_b200/csrc/engine_v2.h"
-#include "../../nextpolish_b200/csrc/engine_v3.h"
 #include "../../include/nextpolish_b200.h"
 
 namespace {
@@ -25,6 +24,7 @@ struct EmuOps {
     void atomic_add_u32(uint32_t* p, uint32_t v) { *p += v; }
     void atomic_min_u32(uint32_t* p, uint32_t v) { if (*p > v) *p = v; }
     int32_t block_exscan(int32_t, int32_t*) { return 0; }      // one "thread" per phase: nothing before it
+    int32_t reserve(int32_t* ctr, int32_t n) { int32_t o = *ctr; *ctr += n; return o; }
 };
 struct EmuBackend {
     std::map<std::string, std::vector<uint8_t>> pool;
@@ -40,6 +40,7 @@ struct EmuBackend {
         EmuOps ops;
         for (int64_t i = 0; i < n; i++) f(i, ops);
     }
+    template <class F> void launch_full(const char* nm, int64_t n, const F& f) { launch(nm, n, f); }
     void exscan_i32(const int32_t* in, int32_t* out, int64_t n) {
         int64_t s = 0;
         for (int64_t i = 0; i < n; i++) { int32_t v = in[i]; out[i] = (int32_t)s; s += v; }
@@ -67,23 +68,35 @@ struct EmuBackend {
         if (n) memcpy(p, h, n * sizeof(int32_t));
         return p;
     }
-    void run_windows(const npe::Dev& d, const npw::WinGlobals& g, int32_t smem_bytes) {
-        std::vector<uint8_t> smem((size_t)smem_bytes + 256);
+    // the tile kernels with one "thread" per tile (column_pass.h): aggregates + scan, then the column walk
+    void tile_aggregates(const npe::Dev& d, const npc::ColGlobals& g) {
+        int32_t rc = 0, rt = 0;
+        for (int32_t w = 0; w < g.n_tiles; w++) {
+            const npc::Tile t = npc::tile_of(d, g, w);
+            int32_t a = 0, b = 0;
+            for (int32_t s = 0; s < npc::TT; s++) {
+                const npc::Slice sl = npc::slice_of(d, t, s);
+                int32_t sc, stb;
+                npc::slice_sums(d, g, t, sl, g.cov + sl.ca, sc, stb);
+                a += sc; b += stb;
+            }
+            g.tile_cov[w] = rc; g.tile_tbl[w] = rt;
+            rc += a; rt += b;
+        }
+        g.tile_cov[g.n_tiles] = rc; g.tile_tbl[g.n_tiles] = rt;
+    }
+    void column_pass(const npe::Dev& d, const npc::ColGlobals& g) {
         EmuOps ops;
-        for (int32_t w = 0; w < g.n_win; w++) {
-            memset(smem.data(), 0xA5, smem.size());          // poison: phases must initialise what they read
-            npw::WCtx x; x.d = d; x.g = g;
-            npw::win_setup(x, w, smem.data());
-            if ((int32_t)npw::win_smem_bytes(x.nr, (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u, x.ncols, x.npos) > smem_bytes) abort();
-            uint32_t recbytes = (d.rec_off[x.rlo + x.nr] - d.rec_off[x.rlo]) * 16u;
-            memcpy(x.rec, d.rec + (size_t)d.rec_off[x.rlo] * 16, recbytes);                 // stands for the bulk copy
-            memcpy((void*)x.recoff, d.rec_off + x.rlo, 4 * (size_t)(x.nr + 1));
-            npw::Prefetch pf;
-            npw::ph_prefetch(x, 0, 1, pf);
-            npw::ph_clear(x, 0, 1, pf);
-            npw::ph_ref(x, 0, 1, ops, pf);
-#define NP_NOSTAMP(k) (void)0
-            NP_WINDOW_PHASES(x, 0, 1, ops, (void)0, NP_NOSTAMP)
+        for (int32_t w = 0; w < g.n_tiles; w++) {
+            const npc::Tile t = npc::tile_of(d, g, w);
+            int32_t run = g.tile_cov[w], trank = g.tile_tbl[w];
+            for (int32_t s = 0; s < npc::TT; s++) {
+                const npc::Slice sl = npc::slice_of(d, t, s);
+                int32_t sc, stb;
+                npc::slice_sums(d, g, t, sl, g.cov + sl.ca, sc, stb);
+                npc::slice_walk(d, g, t, sl, g.cov + sl.ca, run, trank, ops);
+                run += sc; trank += stb;
+            }
         }
     }
 };
@@ -95,8 +108,7 @@ extern "C" int np_emu_run(const np_shard_view* v, int task, const Configure* cfg
                           uint8_t* out_seq, int64_t out_cap, int64_t* out_off, int32_t* stats) {
     return np_emu_run_impl(v, task, cfg, out_seq, out_cap, out_off, stats, 1);
 }
-// variant 1: general kernels (engine_impl.h); variant 2: fused window kernel + fallback (engine_v2.h);
-// variant 3: window-less chain of full-GPU kernels (engine_v3.h)
+// variant 1: general kernels (engine_impl.h); variant 2: diff pass + window kernel + fallback (engine_v2.h)
 static int emu_run(const np_shard_view* v, int task, const Configure* cfg, uint8_t* out_seq, int64_t out_cap, int64_t* out_off,
                    int32_t* stats, int variant, PolishPoint* pts, int64_t pts_cap, int64_t* pts_off);
 extern "C" int np_emu_run_impl(const np_shard_view* v, int task, const Configure* cfg,
@@ -127,8 +139,7 @@ static int emu_run(const np_shard_view* v, int task, const Configure* cfg, uint8
     EmuBackend be;
     npe::RunStats st;
     npe::V2Stats vs; memset(&vs, 0, sizeof(vs));
-    int err = task == 1 ? (variant == 3 ? npe::run_score_chain_v3(be, d, &st)
-                           : variant == 2 ? npe::run_score_chain_v2(be, d, v->ctg_off, &st, &vs) : npe::run_score_chain(be, d, &st))
+    int err = task == 1 ? (variant == 2 ? npe::run_score_chain_v2(be, d, v->ctg_off, &st, &vs) : npe::run_score_chain(be, d, &st))
                         : npe::run_kmer_count(be, d, &st);
     if (err) return err > 0 ? -err : err;
     if (st.out_bytes > out_cap) return -1000;

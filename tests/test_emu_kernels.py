@@ -170,32 +170,3 @@ def test_two_bit_and_four_bit_records_polish_identically(E, oracle, emu, monkeyp
     want = run_checker(oracle.np_oracle_run, four, 1, cfg)
     assert run_checker(emu.np_emu_run_impl, two, 1, cfg, (None, 2)) == want
     assert run_checker(emu.np_emu_run_impl, four, 1, cfg, (None, 2)) == want
-
-
-@pytest.mark.parametrize("case", sorted(CASES))
-def test_emulated_windowless_v3_matches_oracle(E, oracle, emu, case):
-    """Task 1 through the experimental window-less kernel chain (engine_v3.h), emulated."""
-    emu.np_emu_run_impl.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
-    emu.np_emu_run_impl.restype = C.c_int
-    sh = E.Shard.synthetic(E.synth_params(**CASES[case]), 0, CASES[case]["n_contigs"])
-    cfg = E.default_config(b"")
-    want = run_checker(oracle.np_oracle_run, sh, 1, cfg)
-    assert run_checker(emu.np_emu_run_impl, sh, 1, cfg, (None, 3)) == want
-
-
-@pytest.mark.parametrize("seed", range(6))
-def test_emulated_windowless_v3_fuzz(E, oracle, emu, seed):
-    import random
-    emu.np_emu_run_impl.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
-    emu.np_emu_run_impl.restype = C.c_int
-    rng = random.Random(9000 + seed)
-    kw = dict(seed=rng.randrange(1 << 30), n_contigs=rng.choice([1, 2, 5]), contig_len=rng.choice([700, 3000, 8000, 20000]),
-              depth=rng.choice([2, 5, 12, 30, 60, 120]), draft_snv=rng.choice([0.001, 0.01]), draft_indel=rng.choice([0.003, 0.02]),
-              read_sub=rng.choice([0.002, 0.02]), read_indel=rng.choice([0.0001, 0.003]))
-    sh = E.Shard.synthetic(E.synth_params(**kw), 0, kw["n_contigs"])
-    cfg = E.default_config(b"")
-    cfg.contents.trim_len_edge = rng.choice([0, 1, 2, 4])
-    cfg.contents.indel_balance_factor_sgs = rng.choice([0.5, 0.25])
-    cfg.contents.min_count_ratio_skip = rng.choice([0.8, 0.95])
-    want = run_checker(oracle.np_oracle_run, sh, 1, cfg)
-    assert run_checker(emu.np_emu_run_impl, sh, 1, cfg, (None, 3)) == want

@@ -174,23 +174,6 @@ def test_general_kernels_equal_fused_kernel(E, eng):
     assert a == b
 
 
-def test_windowless_v3_equals_fused_kernel(E, oracle, eng):
-    """A/B: the experimental window-less kernel chain (engine_v3.h, NEXTPOLISH_B200_V3=1) gives the oracle's bytes,
-    including deep / noisy data that the window kernel hands to the general fallback."""
-    cfg = E.default_config(b"")
-    for kw in (dict(seed=31, n_contigs=3, contig_len=200000, depth=30.0),
-               dict(seed=32, n_contigs=2, contig_len=60000, depth=200.0, draft_snv=0.01, draft_indel=0.02, read_sub=0.02, read_indel=0.004),
-               dict(seed=6, n_contigs=4, contig_len=0, min_len=40, max_len=160, depth=30.0)):
-        sh = E.Shard.synthetic(E.synth_params(**kw), 0, kw["n_contigs"])
-        want = run_checker(oracle.np_oracle_run, sh, 1, cfg)
-        os.environ["NEXTPOLISH_B200_V3"] = "1"
-        try:
-            got = eng.polish(sh, 1, cfg)
-        finally:
-            del os.environ["NEXTPOLISH_B200_V3"]
-        assert got == want, kw
-
-
 def test_fused_kernel_deep_and_noisy_use_fallback_correctly(E, oracle, eng):
     p = E.synth_params(seed=32, n_contigs=2, contig_len=60000, depth=200.0, draft_snv=0.01, draft_indel=0.02, read_sub=0.02, read_indel=0.004)
     sh = E.Shard.synthetic(p, 0, 2)

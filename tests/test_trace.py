@@ -82,7 +82,7 @@ def test_emulated_trace_matches_oracle(E, oracle, emu, case):
     sh = E.Shard.synthetic(E.synth_params(**CASES[case]), 0, CASES[case]["n_contigs"], with_qual=True)
     cfg = E.default_config(b"")
     cfg.contents.read_tlen = 1750
-    for task, variants in ((1, (1, 2, 3)), (2, (1,))):
+    for task, variants in ((1, (1, 2)), (2, (1,))):
         want = [oracle_points(oracle, sh, ci, task, cfg)[1] for ci in range(sh.n_contigs)]
         assert task == 2 or sum(len(w) for w in want) > 0
         for variant in variants:

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Correlate an ncu report (--import-source on, built with -lineinfo) with source lines.
-usage: ncu_hot_lines.py report.ncu-rep kernel_substring [topN]
+usage: ncu_hot_lines.py report.ncu-rep kernel_substring [topN] [ncu_kernel_regex]
 Prints headline metrics and the hottest source lines (by executed warp instructions)."""
 import collections, csv, os, re, subprocess, sys, tempfile
 
@@ -14,7 +14,8 @@ def run(cmd):
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
-    raw = list(csv.reader(run("ncu -i %s --page raw --csv" % rep).splitlines()))
+    kf = (" -k regex:%s" % sys.argv[4]) if len(sys.argv) > 4 else ""      # ncu-side kernel filter (reports with several kernels)
+    raw = list(csv.reader(run("ncu -i %s --page raw --csv%s" % (rep, kf)).splitlines()))
     hdr, units, vals = raw[0], raw[1], raw[2]
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
@@ -38,10 +39,15 @@ def main():
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(\S.*?);", l)
         if m:
             seq[int(m.group(1), 16)] = cur
-    rows = list(csv.reader(run("ncu -i %s --page source --csv" % rep).splitlines()))
+    rows = list(csv.reader(run("ncu -i %s --page source --csv%s" % (rep, kf)).splitlines()))
     h = rows[1]
     ia, ie, isamp = h.index("Address"), h.index("Instructions Executed"), h.index("# Samples")
-    data = [r for r in rows[2:] if len(r) > ie]
+    data = []
+    for r in rows[2:]:                       # the page repeats itself per view / kernel: keep the first block
+        if r and r[0] in ("Kernel Name", "Address"):
+            break
+        if len(r) > ie:
+            data.append(r)
     base = int(data[0][ia], 16)
     agg, samp = collections.Counter(), collections.Counter()
     for r in data:
