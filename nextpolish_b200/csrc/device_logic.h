@@ -41,11 +41,13 @@ struct Rec {
     const uint32_t* cigar; const uint8_t* seq;
     uint32_t enc;                  // 0: 4-bit nt16 codes, 1: 2 bits per base (include/nextpolish_b200.h)
 };
+struct alignas(16) RecHead { uint32_t w0, w1, w2, w3; };   // records are 16-byte aligned: one 128-bit load
 NP_HD Rec load_rec(const uint8_t* rec, const uint32_t* rec_off, int64_t r) {
     const uint8_t* p = rec + (size_t)rec_off[r] * 16;
     const uint32_t* w = (const uint32_t*)p;
     Rec o;
-    uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    const RecHead hd = *(const RecHead*)p;
+    const uint32_t w0 = hd.w0, w1 = hd.w1, w2 = hd.w2, w3 = hd.w3;
     o.pos = (int32_t)w0;
     o.flag = w1 & 0xffffu;
     o.mapq = (w1 >> 16) & 0xffu;
@@ -66,12 +68,12 @@ NP_HD int32_t cig_len(uint32_t c) { return (int32_t)(c >> 4); }
 
 // base.c:6-15 (strtobase): ASCII -> nt16 code, everything unknown -> 15
 NP_HD uint32_t base_code(uint32_t c) {
-    switch (c) {
-    case '=': return 0;  case 'A': return 1;  case 'C': return 2;  case 'M': return 3;
-    case 'G': return 4;  case 'R': return 5;  case 'S': return 6;  case 'V': return 7;
-    case 'T': return 8;  case 'W': return 9;  case 'Y': return 10; case 'H': return 11;
-    case 'K': return 12; case 'D': return 13; case 'B': return 14; default: return 15;
-    }
+    // nibble LUT over 'A'..'P' and 'Q'..'Z': A1 B14 C2 D13 G4 H11 K12 M3 | R5 S6 T8 V7 W9 Y10, every other letter 15
+    const unsigned long long lo = 0xfff3fcffb4ffd2e1ull, hi = 0xfffffffaf97f865full;
+    const uint32_t i = c - 65u;
+    if (i < 16u) return (uint32_t)(lo >> (4u * i)) & 0xfu;
+    if (i < 26u) return (uint32_t)(hi >> (4u * (i - 16u))) & 0xfu;
+    return c == 61u ? 0u : 15u;        // '='
 }
 NP_HD uint8_t code_char(uint32_t b) { return (uint8_t)("=ACMGRSVTWYHKDBN"[b & 15]); }   // base.c:5
 

@@ -26,7 +26,7 @@ using npe::Dev;
 
 struct alignas(16) ReadDesc { int32_t cs, n; uint32_t doff, dcnt; };   // cs < 0: the read casts nothing
 struct alignas(8) DiffEnt { int32_t col; uint32_t sr; };               // sr = sym | read index << 4
-enum { DIFF_MAX_READS = 1 << 28 };
+enum { DIFF_MAX_READS = 1 << 28, DIFF_GROUP = 32, DIFF_GROUP_SLOTS = 128 };
 
 NP_HD uint32_t bswap32(uint32_t v) {
 #ifdef __CUDA_ARCH__
@@ -54,10 +54,14 @@ NP_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, uint32_t sh) {
 // ---- 2-bit draft ------------------------------------------------------------------------------------------------
 // d2[k] = positions 16k .. 16k+15, two bits per position (A 0, C 1, G 2, T 3 = log2 of the nt16 code), position 16k
 // in the two highest bits; dn[k] = 0b11 at every position whose (upper-cased) draft character is not A/C/G/T.
+struct alignas(8) Draft2 { uint32_t x, y; };
 struct DiffGlobals {
-    uint32_t *d2, *dn;                 // [G/16 + 2]
+    Draft2* dd;                         // [-4 .. G/16 + 2] .x = d2 word, .y = dn word (4 words of front padding: reads near position 0)
     ReadDesc* rdesc;                   // [R]
-    DiffEnt* pool; int32_t* pool_n; int32_t pool_cap;
+    // entry pool: group w of 32 consecutive reads owns slots [w * DIFF_GROUP_SLOTS, +gcnt[w]) (no atomics); reads that do
+    // not fit their group's region take space from the overflow area [n_groups * DIFF_GROUP_SLOTS, pool_cap) instead
+    DiffEnt* pool; int32_t* pool_n; int32_t pool_cap;    // pool_n: entries in the overflow area
+    int32_t* gcnt; int32_t n_groups;
     int32_t* cov;                      // [C+2] +1 at a read's first column, -1 one past its last (prefix sum = reads voting on a column)
     uint32_t* disb;                    // [C/32+2] bit c: some read disagrees with the draft at column c
 };
@@ -77,7 +81,7 @@ struct PackDraft2 {                    // per 16 positions
             }
             w |= v << (30 - 2 * j); nmask |= bad << (30 - 2 * j);
         }
-        g.d2[k] = w; g.dn[k] = nmask;
+        g.dd[k] = Draft2{w, nmask};
     }
 };
 
@@ -88,48 +92,59 @@ NP_HD uint32_t draft_sym(const Dev& d, int32_t p) {
 }
 
 // Entries of one read, buffered in local memory; a read with more than LB entries is walked a second time
-// in write mode.
+// in write mode.  Every entry also sets its column's bit in the disagreement bitmap.
 enum { DIFF_LB = 12 };
 struct DiffSink {
     DiffEnt* out;                      // write mode: destination (null: buffer + count)
     DiffEnt buf[DIFF_LB];
     int32_t n; uint32_t rtag;          // entries so far; read index << 4
-    NP_HD void put(int32_t col, uint32_t sym) {
+    uint32_t* disb;
+    template <class B> NP_HD void put(int32_t col, uint32_t sym, B& be) {
         if (out) out[n] = DiffEnt{col, sym | rtag};
-        else if (n < DIFF_LB) buf[n] = DiffEnt{col, sym | rtag};
+        else {
+            if (n < DIFF_LB) buf[n] = DiffEnt{col, sym | rtag};
+            be.atomic_or(&disb[col >> 5], 1u << (col & 31));
+        }
         n++;
     }
 };
 
 // M run: read bases [q0, q0+len) against draft positions [p0, p0+len).  col0 >= 0: the columns are consecutive from
 // col0; col0 < 0: column = colbase[p] (sub-columns lie inside the run).
-NP_HD void diff_m_run(const Dev& d, const DiffGlobals& g, const Rec& rc, int32_t q0, int32_t p0, int32_t len, int32_t col0, DiffSink& s) {
+// 2-bit reads: one iteration per 16-base word of the read.  Read base q sits at draft position q + delta, so the draft
+// side is a sliding 64-bit window over dd[] shifted by a loop-invariant amount: one 8-byte load per iteration.
+template <class B>
+NP_HD void diff_m_run(const Dev& d, const Draft2* dd, const Rec& rc, int32_t q0, int32_t p0, int32_t len, int32_t col0, DiffSink& s, B& be) {
     if (!rc.enc) {                     // 4-bit reads (a base other than A/C/G/T somewhere): base by base
         for (int32_t j = 0; j < len; j++) {
             const uint32_t sy = seqi(rc.seq, q0 + j);
-            if (sy != draft_sym(d, p0 + j)) s.put(col0 >= 0 ? col0 + j : d.colbase[p0 + j], sy);
+            if (sy != draft_sym(d, p0 + j)) s.put(col0 >= 0 ? col0 + j : d.colbase[p0 + j], sy, be);
         }
         return;
     }
     const uint32_t* sw = (const uint32_t*)rc.seq;
-    int32_t q = q0, p = p0, rem = len;
-    while (rem > 0) {
-        const int32_t sn = q & 15;
-        const int32_t take = 16 - sn < rem ? 16 - sn : rem;
-        const uint32_t rw = bswap32(sw[q >> 4]) << (2 * sn);                 // bases q.. in the highest bits
-        const int32_t pi = p >> 4; const uint32_t ps = 2u * (uint32_t)(p & 15);
-        const uint32_t dw = funnel_l(g.d2[pi], g.d2[pi + 1], ps);
-        const uint32_t nw = funnel_l(g.dn[pi], g.dn[pi + 1], ps);
-        const uint32_t m = take == 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * take));
-        uint32_t X = rw ^ dw;
-        uint32_t D = ((X | (X >> 1)) | nw) & 0x55555555u & m;
+    const int32_t delta = p0 - q0, q1 = q0 + len - 1;
+    const int32_t wi0 = q0 >> 4, wi1 = q1 >> 4;
+    const int32_t P = 16 * wi0 + delta;                                      // draft position of the first word's base 0 (may be < 0)
+    int32_t pi = P >> 4; const uint32_t ps = 2u * (uint32_t)(P & 15);
+    const uint32_t mfirst = 0xffffffffu >> (2 * (q0 & 15));
+    const uint32_t mlast = (q1 & 15) == 15 ? 0xffffffffu : ~(0xffffffffu >> (2 * ((q1 & 15) + 1)));
+    Draft2 lo = dd[pi];
+    for (int32_t wi = wi0; wi <= wi1; wi++, pi++) {
+        const Draft2 hi = dd[pi + 1];
+        const uint32_t rw = bswap32(sw[wi]);
+        const uint32_t X = rw ^ funnel_l(lo.x, hi.x, ps);
+        uint32_t D = ((X | (X >> 1)) | funnel_l(lo.y, hi.y, ps)) & 0x55555555u;
+        if (wi == wi0) D &= mfirst;
+        if (wi == wi1) D &= mlast;
         while (D) {
             const int32_t b = clz32(D) >> 1;
             D &= ~(0x40000000u >> (2 * b));
             const uint32_t sy = 1u << ((rw >> (30 - 2 * b)) & 3u);
-            s.put(col0 >= 0 ? col0 + (p - p0) + b : d.colbase[p + b], sy);
+            const int32_t q = 16 * wi + b;
+            s.put(col0 >= 0 ? col0 + (q - q0) : d.colbase[q + delta], sy, be);
         }
-        q += take; p += take; rem -= take;
+        lo = hi;
     }
 }
 
@@ -138,7 +153,8 @@ NP_HD void diff_m_run(const Dev& d, const DiffGlobals& g, const Rec& rc, int32_t
 // conditions as the run generator above, straight-line: the threads of a warp step through their ops together and
 // meet at the single M-run compare below.
 enum { DK_NONE = 0, DK_M = 1, DK_D = 2, DK_I = 3 };
-NP_HD void diff_read(const Dev& d, const DiffGlobals& g, int64_t r, const Rec& rc, int32_t& cs_out, int32_t& n_out, DiffSink& s) {
+template <class B>
+NP_HD void diff_read(const Dev& d, const Draft2* dd, int64_t r, const Rec& rc, int32_t& cs_out, int32_t& n_out, DiffSink& s, B& be) {
     const int32_t k = d.r_ctg[r];
     const int32_t gs = d.ctg_goff[k], ge = d.ctg_goff[k + 1] - 1;
     int32_t pos = d.r_gpos[r], qpos = 0, qstart = d.r_qstart[r];
@@ -203,11 +219,11 @@ NP_HD void diff_read(const Dev& d, const DiffGlobals& g, int64_t r, const Rec& r
             if (cs < 0) cs = first; else if (first != next) bad = true;   // cannot happen (votes are contiguous)
             next = lastc + 1;
         }
-        if (kind == DK_M) diff_m_run(d, g, rc, a0, a1, a2, a3, s);
+        if (kind == DK_M) diff_m_run(d, dd, rc, a0, a1, a2, a3, s, be);
         else if (kind == DK_D) {
-            for (int32_t p = a1; p <= a2; p++) if (draft_sym(d, p) != (uint32_t)SYM_GAP) s.put(d.colbase[p], (uint32_t)SYM_GAP);
+            for (int32_t p = a1; p <= a2; p++) if (draft_sym(d, p) != (uint32_t)SYM_GAP) s.put(d.colbase[p], (uint32_t)SYM_GAP, be);
         } else if (kind == DK_I) {
-            for (int32_t j = 0; j < a2; j++) { const uint32_t sy = rseq(rc, a0 + j); if (sy != (uint32_t)SYM_GAP) s.put(a1 + j, sy); }
+            for (int32_t j = 0; j < a2; j++) { const uint32_t sy = rseq(rc, a0 + j); if (sy != (uint32_t)SYM_GAP) s.put(a1 + j, sy, be); }
         }
         if (pos > ge) break;
     }
@@ -215,36 +231,35 @@ NP_HD void diff_read(const Dev& d, const DiffGlobals& g, int64_t r, const Rec& r
     cs_out = cs; n_out = cs >= 0 ? next - cs : 0;
 }
 
-struct DiffPass {                      // per read; EVERY thread of the launch calls it (r may be >= n_reads): warp-wide pool reservation
+struct DiffPass {
     Dev d; DiffGlobals g;
-    template <class B> NP_HD void operator()(int64_t r, B& be) const {
-        const bool live = r < d.n_reads && d.r_level[r] == 1;
-        DiffSink s; s.out = nullptr; s.n = 0; s.rtag = (uint32_t)r << 4;
-        int32_t cs = -1, n = 0;
-        Rec rc;
-        if (live) { rc = load_rec(d.rec, d.rec_off, r); diff_read(d, g, r, rc, cs, n, s); }
+    // part 1 (per read): walk, entries buffered in the sink; returns the number of entries
+    // rec / dd: where the records / the 2-bit draft are read from (global memory, or a staged copy)
+    template <class B> NP_HD int32_t walk(int64_t r, const uint8_t* rec, const Draft2* dd, DiffSink& s, Rec& rc, int32_t& cs, int32_t& n, B& be) const {
+        s.out = nullptr; s.n = 0; s.rtag = (uint32_t)r << 4; s.disb = g.disb;
+        cs = -1; n = 0;
+        if (r < d.n_reads && d.r_level[r] == 1) { rc = load_rec(rec, d.rec_off, r); diff_read(d, dd, r, rc, cs, n, s, be); }
+        return s.n;
+    }
+    // part 2 (per read, r < n_reads): entries to the pool at `base`, coverage marks, descriptor
+    template <class B> NP_HD void commit(int64_t r, int32_t base, DiffSink& s, const Rec& rc, int32_t cs, int32_t n, B& be) const {
         const int32_t cnt = s.n;
-        const int32_t base = be.reserve(g.pool_n, cnt);            // exclusive offset inside the pool (all lanes call)
-        if (r >= d.n_reads) return;
         ReadDesc rd{cs, n, (uint32_t)base, (uint32_t)cnt};
         if (cs >= 0) { be.atomic_add(&g.cov[cs], 1); be.atomic_add(&g.cov[cs + n], -1); }
         if (cnt > 0) {
-            if ((int64_t)base + cnt > (int64_t)g.pool_cap) { *d.err |= ERR_DIFF_POOL; rd.dcnt = 0; }
+            if (base < 0 || (int64_t)base + cnt > (int64_t)g.pool_cap) { *d.err |= ERR_DIFF_POOL; rd.dcnt = 0; rd.doff = 0; }
+            else if (cnt <= DIFF_LB) { for (int32_t i = 0; i < cnt; i++) g.pool[base + i] = s.buf[i]; }
             else {
-                if (cnt <= DIFF_LB) { for (int32_t i = 0; i < cnt; i++) g.pool[base + i] = s.buf[i]; }
-                else {
-                    DiffSink s2; s2.out = g.pool + base; s2.n = 0; s2.rtag = s.rtag;
-                    int32_t cs2, n2;
-                    diff_read(d, g, r, rc, cs2, n2, s2);
-                }
-                for (int32_t i = 0; i < cnt; i++) {
-                    const int32_t c = cnt <= DIFF_LB ? s.buf[i].col : g.pool[base + i].col;
-                    be.atomic_or(&g.disb[c >> 5], 1u << (c & 31));
-                }
+                DiffSink s2; s2.out = g.pool + base; s2.n = 0; s2.rtag = s.rtag; s2.disb = g.disb;
+                int32_t cs2, n2;
+                diff_read(d, g.dd, r, rc, cs2, n2, s2, be);
             }
         }
         g.rdesc[r] = rd;
     }
 };
-
+// slot of a read inside its group's region given the inclusive prefix of the group's counts, or -1: overflow area
+NP_HD int32_t diff_group_slot(int32_t group, int32_t inc, int32_t cnt) {
+    return inc <= DIFF_GROUP_SLOTS ? group * DIFF_GROUP_SLOTS + inc - cnt : -1;
+}
 }  // namespace npw

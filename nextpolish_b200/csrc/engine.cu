@@ -74,6 +74,13 @@ struct CudaOps {
         (void)p; (void)v;
 #endif
     }
+    __host__ __device__ __forceinline__ void atomic_max_u32(uint32_t* p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+        atomicMax(p, v);
+#else
+        (void)p; (void)v;
+#endif
+    }
     // exclusive prefix sum of one value per thread over the CTA (every thread calls it; contains barriers)
     __host__ __device__ __forceinline__ int32_t block_exscan(int32_t v, int32_t* scratch) {
 #ifdef __CUDA_ARCH__
@@ -178,10 +185,44 @@ __device__ __forceinline__ CovStage stage_cov(const npc::ColGlobals& g, const np
     return cs;
 }
 
+// ---- the streaming diff pass: one WARP per group of 32 consecutive reads, no block-wide barrier.  The group's entries
+// go to the group's own pool region (exclusive prefix of the per-read counts by warp shuffles, no atomics); only a group
+// with more than 128 entries takes space for its last reads from the overflow area (one atomic per such warp).
+// Measured and dropped (round 2, B200, 1 M reads): staging the group's records and / or its 2-bit draft slice into shared
+// memory by per-warp bulk copies made the kernel slower (0.113 ms direct, 0.128-0.156 ms staged): every warp visits
+// its bytes exactly once, so the copy only adds its own latency in front of the walk and takes L1 capacity away.
+constexpr int kDiffThreads = 256, kDiffWarps = kDiffThreads / 32;
+__global__ void __launch_bounds__(kDiffThreads) k_diff(npw::DiffPass f) {
+    const npe::Dev& d = f.d;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t group = (int64_t)blockIdx.x * kDiffWarps + wid;
+    const int64_t r = group * 32 + lane;
+    if (group * 32 >= d.n_reads) return;
+    CudaOps ops;
+    npw::DiffSink s; npd::Rec rc; int32_t cs, n;
+    const int32_t cnt = f.walk(r, d.rec, f.g.dd, s, rc, cs, n, ops);
+    int32_t inc = cnt;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    int32_t base = npw::diff_group_slot((int32_t)group, inc, cnt);
+    const unsigned fit = __ballot_sync(0xffffffffu, base >= 0);
+    const int nfit = __popc(fit);                                          // the fitting reads are the first nfit lanes
+    const int32_t used = __shfl_sync(0xffffffffu, inc, nfit > 0 ? nfit - 1 : 0);
+    if (lane == 0) f.g.gcnt[group] = nfit > 0 ? used : 0;
+    if (nfit < 32) {                                                       // rare: the tail of the group goes to the overflow area
+        const int32_t total = __shfl_sync(0xffffffffu, inc, 31), before = nfit > 0 ? used : 0;
+        int32_t obase = 0;
+        if (lane == 0) obase = atomicAdd(f.g.pool_n, total - before);
+        obase = __shfl_sync(0xffffffffu, obase, 0);
+        if (base < 0) base = f.g.n_groups * npw::DIFF_GROUP_SLOTS + obase + (inc - cnt - before);
+    }
+    if (r < d.n_reads) f.commit(r, base, s, rc, cs, n, ops);
+}
+
 __global__ void __launch_bounds__(npc::TT) k_tile_agg(npe::Dev d, npc::ColGlobals g) {
     __shared__ __align__(128) int32_t s_cov[npc::COV_CAP];
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ int32_t s_red[2 * (npc::TT / 32)];
+    __shared__ int32_t s_red[3 * (npc::TT / 32)];
     const int32_t w = (int32_t)blockIdx.x, tid = (int32_t)threadIdx.x;
     const npc::Tile t = npc::tile_of(d, g, w);
     const uint32_t bar = smem_u32(&s_bar);
@@ -189,82 +230,64 @@ __global__ void __launch_bounds__(npc::TT) k_tile_agg(npe::Dev d, npc::ColGlobal
     const npc::Slice sl = npc::slice_of(d, t, tid);
     __syncthreads();                                   // the barrier is initialised
     mbar_wait(bar, 0);
-    int32_t a, b;
-    npc::slice_sums(d, g, t, sl, cs.at(g.cov, sl.ca, sl.cb), a, b);
+    npc::Sums x = npc::slice_sums(d, g, t, sl, cs.at(g.cov, sl.ca, sl.cb));
     #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-    if ((tid & 31) == 0) { s_red[tid >> 5] = a; s_red[npc::TT / 32 + (tid >> 5)] = b; }
+    for (int o = 16; o > 0; o >>= 1) {
+        x.cov += __shfl_xor_sync(0xffffffffu, x.cov, o); x.tbl += __shfl_xor_sync(0xffffffffu, x.tbl, o); x.str += __shfl_xor_sync(0xffffffffu, x.str, o);
+    }
+    constexpr int NW = npc::TT / 32;
+    if ((tid & 31) == 0) { s_red[tid >> 5] = x.cov; s_red[NW + (tid >> 5)] = x.tbl; s_red[2 * NW + (tid >> 5)] = x.str; }
     __syncthreads();
     if (tid == 0) {
-        int32_t sa = 0, sb = 0;
-        for (int i = 0; i < npc::TT / 32; i++) { sa += s_red[i]; sb += s_red[npc::TT / 32 + i]; }
-        g.tile_cov[w] = sa; g.tile_tbl[w] = sb;
+        int32_t sa = 0, sb = 0, sc = 0;
+        for (int i = 0; i < NW; i++) { sa += s_red[i]; sb += s_red[NW + i]; sc += s_red[2 * NW + i]; }
+        g.tile_cov[w] = sa; g.tile_tbl[w] = sb; g.tile_str[w] = sc;
     }
 }
-// exclusive prefix of the tile aggregates, in place; [n_tiles] = totals (one CTA)
-__global__ void __launch_bounds__(1024) k_tile_scan(npc::ColGlobals g) {
-    __shared__ int32_t s_a[32], s_b[32];
-    __shared__ int32_t carry[2];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { carry[0] = 0; carry[1] = 0; }
-    __syncthreads();
-    for (int32_t base = 0; base <= g.n_tiles; base += 1024) {
-        const int32_t i = base + tid;
-        const int32_t va = i < g.n_tiles ? g.tile_cov[i] : 0, vb = i < g.n_tiles ? g.tile_tbl[i] : 0;
-        int32_t ia = va, ib = vb;
+// exclusive prefix of the tile aggregates, in place; [n_tiles] = totals (one CTA; warp w scans array w)
+__global__ void __launch_bounds__(96) k_tile_scan(npc::ColGlobals g) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t* a = wid == 0 ? g.tile_cov : wid == 1 ? g.tile_tbl : g.tile_str;
+    int32_t carry = 0;
+    for (int32_t base = 0; base <= g.n_tiles; base += 32) {
+        const int32_t i = base + lane;
+        const int32_t v = i < g.n_tiles ? a[i] : 0;
+        int32_t inc = v;
         #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
-            if (lane >= o) { ia += ta; ib += tb; }
-        }
-        if (lane == 31) { s_a[wid] = ia; s_b[wid] = ib; }
-        __syncthreads();
-        if (wid == 0) {
-            int32_t wa = s_a[lane], wb = s_b[lane], xa = wa, xb = wb;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int32_t ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
-                if (lane >= o) { xa += ta; xb += tb; }
-            }
-            s_a[lane] = xa - wa; s_b[lane] = xb - wb;
-        }
-        __syncthreads();
-        const int32_t ea = carry[0] + s_a[wid] + ia - va, eb = carry[1] + s_b[wid] + ib - vb;
-        if (i <= g.n_tiles) { g.tile_cov[i] = ea; g.tile_tbl[i] = eb; }
-        __syncthreads();
-        if (tid == 1023) { carry[0] = ea + va; carry[1] = eb + vb; }
-        __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (i <= g.n_tiles) a[i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
     }
 }
 __global__ void __launch_bounds__(npc::TT) k_col_pass(npe::Dev d, npc::ColGlobals g) {
     __shared__ __align__(128) int32_t s_cov[npc::COV_CAP];
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ int32_t s_a[npc::TT / 32], s_b[npc::TT / 32];
+    constexpr int NW = npc::TT / 32;
+    __shared__ int32_t s_w[3 * NW];
     const int32_t w = (int32_t)blockIdx.x, tid = (int32_t)threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const npc::Tile t = npc::tile_of(d, g, w);
     const uint32_t bar = smem_u32(&s_bar);
     const CovStage cs = stage_cov(g, t, s_cov, bar);
     const npc::Slice sl = npc::slice_of(d, t, tid);
-    const int32_t carry_cov = g.tile_cov[w], carry_tbl = g.tile_tbl[w];
+    const int32_t carry_cov = g.tile_cov[w], carry_tbl = g.tile_tbl[w], carry_str = g.tile_str[w];
     __syncthreads();
     mbar_wait(bar, 0);
     const int32_t* cov = cs.at(g.cov, sl.ca, sl.cb);
-    int32_t a, b;
-    npc::slice_sums(d, g, t, sl, cov, a, b);
-    // block-wide exclusive scan of both sums (warp shuffles + one shared-memory hop)
-    int32_t ia = a, ib = b;
+    const npc::Sums x = npc::slice_sums(d, g, t, sl, cov);
+    // block-wide exclusive scan of the three sums (warp shuffles + one shared-memory hop)
+    int32_t ia = x.cov, ib = x.tbl, ic = x.str;
     #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
-        if (lane >= o) { ia += ta; ib += tb; }
+        const int32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
+        if (lane >= o) { ia += ta; ib += tb; ic += tc; }
     }
-    if (lane == 31) { s_a[wid] = ia; s_b[wid] = ib; }
+    if (lane == 31) { s_w[wid] = ia; s_w[NW + wid] = ib; s_w[2 * NW + wid] = ic; }
     __syncthreads();
-    int32_t wa = 0, wb = 0;
+    int32_t wa = 0, wb = 0, wc = 0;
     #pragma unroll
-    for (int i = 0; i < npc::TT / 32; i++) if (i < wid) { wa += s_a[i]; wb += s_b[i]; }
+    for (int i = 0; i < NW; i++) if (i < wid) { wa += s_w[i]; wb += s_w[NW + i]; wc += s_w[2 * NW + i]; }
     CudaOps ops;
-    npc::slice_walk(d, g, t, sl, cov, carry_cov + wa + ia - a, carry_tbl + wb + ib - b, ops);
+    npc::slice_walk(d, g, t, sl, cov, carry_cov + wa + ia - x.cov, carry_tbl + wb + ib - x.tbl, carry_str + wc + ic - x.str, ops);
 }
 
 struct NcolOp {   // 1 + insertion length (0 past the end): column count of a position
@@ -409,11 +432,19 @@ struct CudaBackend {
         }
         return p;
     }
+    void diff_pass(const npw::DiffPass& f) {
+        if (!ok || f.d.n_reads <= 0) return;
+        begin_timed("pileup_diff");
+        k_diff<<<(unsigned)((f.d.n_reads + kDiffThreads - 1) / kDiffThreads), kDiffThreads, 0, stream>>>(f);
+        CUDA_TRY(cudaGetLastError());
+        launches++;
+        end_timed();
+    }
     void tile_aggregates(const npe::Dev& d, const npc::ColGlobals& g) {
         if (!ok || g.n_tiles <= 0) return;
         begin_timed("tile_agg");
         k_tile_agg<<<(unsigned)g.n_tiles, npc::TT, 0, stream>>>(d, g);
-        k_tile_scan<<<1, 1024, 0, stream>>>(g);
+        k_tile_scan<<<1, 96, 0, stream>>>(g);
         CUDA_TRY(cudaGetLastError());
         launches += 2;
         end_timed();

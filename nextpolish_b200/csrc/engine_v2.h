@@ -48,35 +48,39 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
 
     // ---- streaming half of the pileup scan: every read against the 2-bit draft, once (diff_pass.h)
     npw::DiffGlobals dg; memset(&dg, 0, sizeof(dg));
-    dg.d2 = be.template buf<uint32_t>("d2", (size_t)G / 16 + 4);
-    dg.dn = be.template buf<uint32_t>("dn", (size_t)G / 16 + 4);
+    dg.dd = be.template buf<npw::Draft2>("dd", (size_t)G / 16 + 12) + 4;
     dg.rdesc = be.template buf<npw::ReadDesc>("rdesc", (size_t)R + 1);
-    dg.pool_cap = (int32_t)((R * 4 + 4096 < 0x3ffffff0ll) ? R * 4 + 4096 : 0x3ffffff0ll);
+    dg.n_groups = (int32_t)((R + npw::DIFF_GROUP - 1) / npw::DIFF_GROUP);
+    const int64_t n_region = (int64_t)dg.n_groups * npw::DIFF_GROUP_SLOTS;            // 4 slots per read on average
+    if (n_region + R / 2 + 4096 >= 0x7ffffff0ll) return run_score_chain(be, d, st);
+    dg.pool_cap = (int32_t)(n_region + R / 2 + 4096);
     dg.pool = be.template buf<npw::DiffEnt>("dpool", (size_t)dg.pool_cap);
     dg.pool_n = be.template buf<int32_t>("dpool_n", 2);
+    dg.gcnt = be.template buf<int32_t>("dpool_gcnt", (size_t)dg.n_groups + 1);
     dg.cov = be.template buf<int32_t>("cov", (size_t)C + 4);
     dg.disb = be.template buf<uint32_t>("disb", (size_t)C / 32 + 8);
     g.tile_cov = be.template buf<int32_t>("tile_cov", (size_t)g.n_tiles + 2);
     g.tile_tbl = be.template buf<int32_t>("tile_tbl", (size_t)g.n_tiles + 2);
+    g.tile_str = be.template buf<int32_t>("tile_str", (size_t)g.n_tiles + 2);
     d.obase = be.template buf<uint8_t>("obase", (size_t)C + 1);
     d.oflag = be.template buf<uint8_t>("oflag", (size_t)C + 1);
     d.keepidx = be.template buf<int32_t>("keepidx", (size_t)C + 1);
     be.launch("pack_draft", (int64_t)G / 16 + 2, npw::PackDraft2{d, dg});
-    int32_t n_ent = 0, T = 0;
+    int32_t n_ent = 0, n_ovf = 0, T = 0;
     for (int attempt = 0;; attempt++) {
         g.cov = dg.cov; g.disb = dg.disb;
         be.zero(dg.pool_n, 2 * sizeof(int32_t));
         be.zero(dg.cov, sizeof(int32_t) * ((size_t)C + 4));
         be.zero(dg.disb, sizeof(uint32_t) * ((size_t)C / 32 + 8));
-        if (R > 0) be.launch_full("pileup_diff", R, npw::DiffPass{d, dg});
+        be.diff_pass(npw::DiffPass{d, dg});
         be.tile_aggregates(d, g);                                   // tile_agg + tile_scan
         const int32_t* ptrs[3] = {d.err, dg.pool_n, g.tile_tbl + g.n_tiles};
         int32_t vals[3];
         be.read_many(ptrs, 3, vals);
-        n_ent = vals[1]; T = vals[2];
+        n_ovf = vals[1]; n_ent = (int32_t)n_region + vals[1]; T = vals[2];
         if (!(vals[0] & npw::ERR_DIFF_POOL)) break;
-        // noisy shard: the diff pool was too small.  The pass counted what it needs: grow the pool and repeat it once.
-        if (attempt > 0 || n_ent <= dg.pool_cap || n_ent >= 0x3ffffff0) return run_score_chain(be, d, st);
+        // noisy shard: the overflow area was too small.  The pass counted what it needs: grow the pool and repeat it once.
+        if (attempt > 0 || n_ent <= dg.pool_cap || n_ent >= 0x7ffffff0 - 16) return run_score_chain(be, d, st);
         dg.pool_cap = n_ent + 16;
         dg.pool = be.template buf<npw::DiffEnt>("dpool", (size_t)dg.pool_cap);
         be.zero(d.err, sizeof(int32_t));
@@ -96,15 +100,21 @@ int run_score_chain_v2(BE& be, Dev& d, const int64_t* host_ctg_off, RunStats* st
     g.tfs = be.template buf<uint32_t>("t_fs", (size_t)T * npc::WK + 1);
     g.bt_base = be.template buf<uint32_t>("bt_base", (size_t)T + 1);
     g.bt_pv = be.template buf<uint32_t>("bt_pv", (size_t)T + 1);
-    g.bt_am = be.template buf<uint8_t>("bt_am", (size_t)T + 1);
+    g.bt_am = be.template buf<uint16_t>("bt_am", (size_t)T + 1);
+    g.sstart = be.template buf<int32_t>("s_start", (size_t)T + 1);
     g.n_unresolved = be.template buf<int32_t>("n_unres", 2);
+    g.n_start = g.tile_str + g.n_tiles;
     be.zero(g.n_unresolved, 2 * sizeof(int32_t));
+    be.zero(g.tbad, (size_t)T + 1);
+    be.zero(g.tunres, (size_t)T + 1);
+    be.zero(g.te, sizeof(uint32_t) * ((size_t)T * npc::WK + 1));
+    be.zero(g.tfs, sizeof(uint32_t) * ((size_t)T * npc::WK + 1));
     be.zero(g.refw, sizeof(uint32_t) * ((size_t)C / 8 + 4));
     be.zero(g.tblb, sizeof(uint32_t) * ((size_t)C / 32 + 8));
     if (g.n_tiles > 0) be.column_pass(d, g);
     if (T > 0) {
-        if (n_ent > 0) be.launch("entry_votes", n_ent, npc::EntryVotes{d, dg, g});
-        be.launch("start_votes", R, npc::StartVotes{d, dg, g});
+        const npc::Votes votes{npc::EntryVotes{d, dg, g}, npc::StartVotes{d, dg, g}, (int64_t)n_ovf};
+        be.launch("votes", votes.items(), votes);
         be.launch("chain", T, npc::Chain{d, g});
     }
     be.exscan_keep(d.obase, d.keepidx, (int64_t)C);

@@ -58,12 +58,10 @@ def oracle():
     return O
 
 
-@pytest.fixture(scope="session")
-def emu():
-    """Kernel bodies compiled for the host (tests/emu/emu_engine.cpp) — test build only."""
+def _emu_build(name, defines=()):
     d = os.path.join(ROOT, "tests", "_emu")
     os.makedirs(d, exist_ok=True)
-    so = os.path.join(d, "libnp_emu.so")
+    so = os.path.join(d, name)
     srcs = [os.path.join(ROOT, "tests", "emu", "emu_engine.cpp"),
             os.path.join(ROOT, "nextpolish_b200", "csrc", "engine_impl.h"),
             os.path.join(ROOT, "nextpolish_b200", "csrc", "engine_task2.h"),
@@ -74,13 +72,26 @@ def emu():
     extra = [os.path.join(ROOT, "tests", "emu", "emu_bgzf.cpp"), os.path.join(ROOT, "nextpolish_b200", "csrc", "hostio.cpp")]
     srcs += extra + [os.path.join(ROOT, "nextpolish_b200", "csrc", "bgzf_inflate.h"), os.path.join(ROOT, "nextpolish_b200", "csrc", "hostio.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]] + extra + ["-lz", "-lpthread"])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + list(defines) + ["-o", so, srcs[0]] + extra + ["-lz", "-lpthread"])
     L = C.CDLL(so)
     L.np_emu_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.np_emu_run.restype = C.c_int
     L.np_emu_bgzf_inflate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.np_emu_bgzf_inflate.restype = C.c_int
     return L
+
+
+@pytest.fixture(scope="session")
+def emu():
+    """Kernel bodies compiled for the host (tests/emu/emu_engine.cpp) — test build only."""
+    return _emu_build("libnp_emu.so")
+
+
+@pytest.fixture(scope="session")
+def emu_general_slices():
+    """The same test build with the column pass's 64-bit fast path limited to 9 columns per thread slice, so that
+    ordinary inputs reach the general (many insertion sub-columns) loops of column_pass.h."""
+    return _emu_build("libnp_emu_slow.so", ("-DNP_SLICE_FAST_MAX=9",))
 
 
 def run_checker(fn, shard, task, cfg, extra=()):

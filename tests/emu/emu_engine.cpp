@@ -23,6 +23,7 @@ struct EmuOps {
     uint32_t atomic_cas_u32(uint32_t* p, uint32_t cmp, uint32_t v) { uint32_t o = *p; if (o == cmp) *p = v; return o; }
     void atomic_add_u32(uint32_t* p, uint32_t v) { *p += v; }
     void atomic_min_u32(uint32_t* p, uint32_t v) { if (*p > v) *p = v; }
+    void atomic_max_u32(uint32_t* p, uint32_t v) { if (*p < v) *p = v; }
     int32_t block_exscan(int32_t, int32_t*) { return 0; }      // one "thread" per phase: nothing before it
     int32_t reserve(int32_t* ctr, int32_t n) { int32_t o = *ctr; *ctr += n; return o; }
 };
@@ -68,34 +69,53 @@ struct EmuBackend {
         if (n) memcpy(p, h, n * sizeof(int32_t));
         return p;
     }
+    // the diff kernel's glue, one "warp" (group of 32 reads) at a time
+    void diff_pass(const npw::DiffPass& f) {
+        EmuOps ops;
+        for (int32_t grp = 0; grp < f.g.n_groups; grp++) {
+            npw::DiffSink s[32]; npd::Rec rc[32]; int32_t cs[32], n[32], cnt[32];
+            int32_t inc = 0, used = 0, nfit = 0;
+            for (int l = 0; l < 32; l++) cnt[l] = f.walk((int64_t)grp * 32 + l, f.d.rec, f.g.dd, s[l], rc[l], cs[l], n[l], ops);
+            for (int l = 0; l < 32; l++) { inc += cnt[l]; if (inc <= npw::DIFF_GROUP_SLOTS) { used = inc; nfit = l + 1; } }
+            f.g.gcnt[grp] = used;
+            int32_t obase = 0;
+            if (nfit < 32) obase = ops.atomic_add_ret(f.g.pool_n, inc - used);
+            inc = 0;
+            for (int l = 0; l < 32; l++) {
+                inc += cnt[l];
+                int32_t base = npw::diff_group_slot(grp, inc, cnt[l]);
+                if (base < 0) base = f.g.n_groups * npw::DIFF_GROUP_SLOTS + obase + (inc - cnt[l] - used);
+                const int64_t r = (int64_t)grp * 32 + l;
+                if (r < f.d.n_reads) f.commit(r, base, s[l], rc[l], cs[l], n[l], ops);
+            }
+        }
+    }
     // the tile kernels with one "thread" per tile (column_pass.h): aggregates + scan, then the column walk
     void tile_aggregates(const npe::Dev& d, const npc::ColGlobals& g) {
-        int32_t rc = 0, rt = 0;
+        npc::Sums run{0, 0, 0};
         for (int32_t w = 0; w < g.n_tiles; w++) {
             const npc::Tile t = npc::tile_of(d, g, w);
-            int32_t a = 0, b = 0;
+            npc::Sums a{0, 0, 0};
             for (int32_t s = 0; s < npc::TT; s++) {
                 const npc::Slice sl = npc::slice_of(d, t, s);
-                int32_t sc, stb;
-                npc::slice_sums(d, g, t, sl, g.cov + sl.ca, sc, stb);
-                a += sc; b += stb;
+                const npc::Sums x = npc::slice_sums(d, g, t, sl, g.cov + sl.ca);
+                a.cov += x.cov; a.tbl += x.tbl; a.str += x.str;
             }
-            g.tile_cov[w] = rc; g.tile_tbl[w] = rt;
-            rc += a; rt += b;
+            g.tile_cov[w] = run.cov; g.tile_tbl[w] = run.tbl; g.tile_str[w] = run.str;
+            run.cov += a.cov; run.tbl += a.tbl; run.str += a.str;
         }
-        g.tile_cov[g.n_tiles] = rc; g.tile_tbl[g.n_tiles] = rt;
+        g.tile_cov[g.n_tiles] = run.cov; g.tile_tbl[g.n_tiles] = run.tbl; g.tile_str[g.n_tiles] = run.str;
     }
     void column_pass(const npe::Dev& d, const npc::ColGlobals& g) {
         EmuOps ops;
         for (int32_t w = 0; w < g.n_tiles; w++) {
             const npc::Tile t = npc::tile_of(d, g, w);
-            int32_t run = g.tile_cov[w], trank = g.tile_tbl[w];
+            npc::Sums run{g.tile_cov[w], g.tile_tbl[w], g.tile_str[w]};
             for (int32_t s = 0; s < npc::TT; s++) {
                 const npc::Slice sl = npc::slice_of(d, t, s);
-                int32_t sc, stb;
-                npc::slice_sums(d, g, t, sl, g.cov + sl.ca, sc, stb);
-                npc::slice_walk(d, g, t, sl, g.cov + sl.ca, run, trank, ops);
-                run += sc; trank += stb;
+                const npc::Sums x = npc::slice_sums(d, g, t, sl, g.cov + sl.ca);
+                npc::slice_walk(d, g, t, sl, g.cov + sl.ca, run.cov, run.tbl, run.str, ops);
+                run.cov += x.cov; run.tbl += x.tbl; run.str += x.str;
             }
         }
     }

@@ -170,3 +170,16 @@ def test_two_bit_and_four_bit_records_polish_identically(E, oracle, emu, monkeyp
     want = run_checker(oracle.np_oracle_run, four, 1, cfg)
     assert run_checker(emu.np_emu_run_impl, two, 1, cfg, (None, 2)) == want
     assert run_checker(emu.np_emu_run_impl, four, 1, cfg, (None, 2)) == want
+
+
+@pytest.mark.parametrize("case", ["c30", "noisy", "ragged", "shallow"])
+def test_emulated_column_pass_general_slices(E, oracle, emu_general_slices, case):
+    """column_pass.h handles a thread slice of up to 62 columns with 64-bit bit tricks and longer ones (dense
+    insertion sub-columns) with per-column loops: a build with the limit lowered to 9 runs those loops on ordinary data."""
+    L = emu_general_slices
+    L.np_emu_run_impl.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    L.np_emu_run_impl.restype = C.c_int
+    sh = E.Shard.synthetic(E.synth_params(**CASES[case]), 0, CASES[case]["n_contigs"])
+    cfg = E.default_config(b"")
+    want = run_checker(oracle.np_oracle_run, sh, 1, cfg)
+    assert run_checker(L.np_emu_run_impl, sh, 1, cfg, (None, 2)) == want

@@ -14,7 +14,10 @@ def run(cmd):
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
-    kf = (" -k regex:%s" % sys.argv[4]) if len(sys.argv) > 4 else ""      # ncu-side kernel filter (reports with several kernels)
+    # ncu-side kernel filter (reports with several kernels): a kernel-name regex, or "#N" = the N-th launch of the report
+    kf = ""
+    if len(sys.argv) > 4:
+        kf = (" --launch-skip %s --launch-count 1" % sys.argv[4][1:]) if sys.argv[4].startswith("#") else (" -k regex:%s" % sys.argv[4])
     raw = list(csv.reader(run("ncu -i %s --page raw --csv%s" % (rep, kf)).splitlines()))
     hdr, units, vals = raw[0], raw[1], raw[2]
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
