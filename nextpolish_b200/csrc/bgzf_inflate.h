@@ -5,11 +5,17 @@
 // contig (contig.c:170-180 and :688-704); BGZF blocks are independent <= 64 KiB deflate members, so a
 // whole BAM region inflates as thousands of independent streams.
 //
-// Division of labour inside a warp: lane 0 owns the bit reader and decodes Huffman symbols (a strictly
-// sequential dependency chain); literals are stored by lane 0, LZ77 matches are copied by all lanes
-// (the copy is the byte-heavy part).  Code tables live in shared memory, one small region per warp:
+// Division of labour inside a warp: DECODE and RESOLVE are decoupled.  Lane 0 owns the bit reader and decodes a
+// batch of up to 32 symbols (a strictly sequential dependency chain) into shared memory without touching the output;
+// then the warp resolves the batch: lane i takes symbol i, an exclusive prefix sum of the lengths gives every symbol
+// its output position, literals are stored at once and LZ77 matches are copied by their own lanes as soon as all the
+// bytes they read are final (round by round; a match that reads output of the same batch waits for the lanes before
+// it).  BAM payloads are match-dominated (read bases repeat in the overlapping reads of the 32 KiB window, names and
+// qualities likewise: ~9 bytes per symbol), and the old scheme — every match copied by the whole warp before the next
+// symbol is decoded — put one L2 round trip per symbol on the critical path.
+// Code tables live in shared memory, one small region per warp:
 //   literal/length and distance symbols ordered by code (canonical Huffman, RFC 1951 3.2.2), code-length
-//   histograms, and a 9-bit lookup table for literal/length codes (one shared-memory load decodes the
+//   histograms, and a 10-bit lookup table for literal/length codes (one shared-memory load decodes the
 //   common symbols; longer codes fall back to the canonical walk).
 //
 // The decoder is NP_HD code over a warp backend (lane id, broadcast, barrier) so that tests/emu can run
@@ -31,9 +37,12 @@ struct Block {             // one BGZF block: where its raw deflate payload live
     uint64_t out_off;      // offset of the block's bytes in the output buffer
 };
 
-enum { MAXBITS = 15, MAXL = 288, MAXD = 30, FASTBITS = 9, DFASTBITS = 8 };
+enum { MAXBITS = 15, MAXL = 288, MAXD = 30, FASTBITS = 10, DFASTBITS = 8, BATCH = 32 };
 
-struct Tables {            // per-warp shared memory (2.9 KB)
+struct Tables {            // per-warp shared memory (4.3 KB)
+    uint32_t batch[BATCH];                 // decoded symbols: literal = 0x8000 | byte; match = length | distance << 16
+    uint32_t lenx[32], distx[32];          // RFC 1951 3.2.5: base | extra bits << 16 of length symbol 257+i / distance symbol i
+    int32_t lfirst, lindex, dfirst, dindex; // state of the canonical walk after FASTBITS / DFASTBITS steps (decode_slow resumes there)
     uint16_t lcount[MAXBITS + 1], lsym[MAXL];
     uint16_t dcount[MAXBITS + 1], dsym[MAXD + 2];
     uint16_t fast[1 << FASTBITS];          // literal/length: symbol << 4 | code length (0: not in the table)
@@ -101,16 +110,25 @@ NP_HD void build_fast(uint16_t* fast, int bits, const uint16_t* count, const uin
         code <<= 1;
     }
 }
+NP_HD void walk_state(const uint16_t* count, int steps, int32_t& first, int32_t& index) {
+    first = 0; index = 0;
+    for (int l = 1; l <= steps; l++) { const int c = count[l]; index += c; first += c; first <<= 1; }
+}
 NP_HD void build_fast(Tables& t) {
     build_fast(t.fast, FASTBITS, t.lcount, t.lsym);
     build_fast(t.dfast, DFASTBITS, t.dcount, t.dsym);
+    walk_state(t.lcount, FASTBITS, t.lfirst, t.lindex);
+    walk_state(t.dcount, DFASTBITS, t.dfirst, t.dindex);
 }
-// canonical walk, one bit at a time (puff-style): returns the symbol or -1
-NP_HD int decode_slow(Bits& b, const uint16_t* count, const uint16_t* sym) {
+// canonical walk, one bit at a time (puff-style): returns the symbol or -1.
+// The walk's `first` / `index` after l steps depend only on the code-length histogram, and its `code` is the bit-reversed
+// l-bit prefix of the stream: a code known to be longer than `from` bits (it missed the lookup table) resumes there.
+NP_HD int decode_slow(Bits& b, const uint16_t* count, const uint16_t* sym, int from = 0, int first0 = 0, int index0 = 0) {
     if (b.cnt < MAXBITS) b.refill();
-    int code = 0, first = 0, index = 0;
+    int code = 0, first = first0, index = index0;
     uint32_t bits = b.peek(MAXBITS);
-    for (int l = 1; l <= MAXBITS; l++) {
+    if (from > 0) { code = (int)(rev_bits(bits, from) << 1); bits >>= from; }
+    for (int l = from + 1; l <= MAXBITS; l++) {
         code |= (int)(bits & 1u); bits >>= 1;
         int c = count[l];
         if (code - c < first) { b.drop(l); return sym[index + (code - first)]; }
@@ -133,6 +151,13 @@ NP_HD int decode_lit(Bits& b, const Tables& t) {
 
 // RFC 1951 3.2.5 tables in closed form (a local array would be rebuilt on the stack at every call):
 // lengths 3,4,..,10, 11,13,15,17, 19,23,27,31, ... 227, 258; distances 1,2,3,4, 5,7, 9,13, 17,25, ... 24577
+NP_HD int32_t first_bit(uint32_t v) {     // index of the lowest set bit (v != 0)
+#ifdef __CUDA_ARCH__
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
 NP_HD int32_t len_base(int s) {     // s = symbol - 257
     if (s < 8) return 3 + s;
     if (s == 28) return 258;
@@ -141,6 +166,15 @@ NP_HD int32_t len_base(int s) {     // s = symbol - 257
 NP_HD int32_t len_extra(int s) { return s < 8 || s == 28 ? 0 : (s - 4) >> 2; }
 NP_HD int32_t dist_base(int s) { return s < 4 ? s + 1 : ((2 + (s & 1)) << ((s >> 1) - 1)) + 1; }
 NP_HD int32_t dist_extra(int s) { return s < 4 ? 0 : (s >> 1) - 1; }
+// the same as per-warp lookup tables (filled once per warp by init_tables: one load instead of ~8 dependent ALU steps)
+template <class W>
+NP_HD void init_tables(Tables& t, W& w) {
+    for (int i = w.lane(); i < 32; i += w.width()) {
+        t.lenx[i] = i < 29 ? (uint32_t)len_base(i) | (uint32_t)len_extra(i) << 16 : 0xffffffffu;
+        t.distx[i] = i < MAXD ? (uint32_t)dist_base(i) | (uint32_t)dist_extra(i) << 16 : 0xffffffffu;
+    }
+    w.sync();
+}
 
 // reads a dynamic block header into t (lane 0)
 NP_HD int read_dynamic(Bits& b, Tables& t) {
@@ -186,86 +220,175 @@ NP_HD void set_fixed(Tables& t) {
     build_fast(t);
 }
 
-// Inflates one BGZF block.  W: warp backend with lane(), width(), bcast(int32_t v) (value of lane 0) and sync().
-// (A shared-memory mirror of the recent output was tried for near matches and measured slower: the kernel is bound by
-// instruction issue — 65 warp instructions per symbol with ~5 active lanes — not by the L2 round trip of the copies.)
-// Returns OK or an ERR_* (same value on every lane).
+// Resolves a batch of decoded symbols (t.batch[0..nsym)) at output position pos.  Returns the new position, or a
+// negative error code.  W: warp backend (see inflate_block).
+template <class W>
+NP_HD int32_t resolve_batch(uint8_t* out, uint32_t out_len, int32_t pos, int32_t nsym, const Tables& t, W& w) {
+    for (int32_t base = 0; base < nsym; base += w.width()) {
+        const int32_t i = base + w.lane();
+        const bool valid = i < nsym;
+        const uint32_t e = valid ? t.batch[i] : 0u;
+        const bool lit = valid && (e & 0x8000u) != 0u;
+        const int32_t len = !valid ? 0 : lit ? 1 : (int32_t)(e & 0x1ffu);
+        const int32_t dist = (int32_t)(e >> 16);
+        int32_t total = 0;
+        const int32_t dst = pos + w.exscan(len, &total);
+        int32_t err = 0;
+        if (valid && !lit && dist > dst) err = ERR_DIST;
+        if (pos + total > (int32_t)out_len) err = ERR_OUTPUT;
+        if (w.any(err != 0)) return -(w.any(err == ERR_OUTPUT) ? (int32_t)ERR_OUTPUT : (int32_t)ERR_DIST);
+        bool done = !valid;
+        if (lit) { out[dst] = (uint8_t)(e & 0xffu); done = true; }
+        w.sync();
+        for (;;) {
+            const uint32_t open = w.ballot(!done);
+            if (!open) break;
+            const int32_t upto = w.shfl(dst, first_bit(open));       // everything before the first open symbol is final
+            if (!done) {
+                const int32_t src = dst - dist;
+                if (dist >= len) {
+                    if (src + len <= upto) {
+                        int32_t j = 0;
+                        for (; j + 8 <= len; j += 8) {               // loads first, then stores: eight bytes in flight
+                            uint8_t v[8];
+                            for (int u = 0; u < 8; u++) v[u] = out[src + j + u];
+                            for (int u = 0; u < 8; u++) out[dst + j + u] = v[u];
+                        }
+                        for (; j < len; j++) out[dst + j] = out[src + j];
+                        done = true;
+                    }
+                } else if (dst <= upto) {
+                    // the match overlaps its own output: only the `dist` bytes before dst are read
+                    for (int32_t j = 0; j < len; j++) out[dst + j] = out[src + j % dist];
+                    done = true;
+                }
+            }
+            w.sync();
+        }
+        pos += total;
+    }
+    return pos;
+}
+
+// ---- one decoder = one lane walking one BGZF block -------------------------------------------------------------------
+// Several lanes of a warp decode DIFFERENT blocks in lockstep (the decode chain is serial per block and issue-bound:
+// with one decoder per warp 31 lanes idle through ~65 warp instructions per symbol); the batches they produce are then
+// resolved one block after the other by the whole warp (resolve_batch).  A decoder's state lives in its lane's
+// registers, its code tables in its own Tables slot.
+struct Decoder {
+    Bits b; const uint8_t* in; uint8_t* out;
+    uint32_t in_len, out_len;
+    int32_t pos;               // output bytes resolved so far
+    int32_t last;              // the current deflate block is the stream's last one
+    int32_t phase;             // PH_*
+    int32_t err;               // first error (OK)
+};
+enum { PH_IDLE = 0, PH_HEADER = 1, PH_SYMBOLS = 2, PH_DONE = 3 };
+NP_HD void dec_start(Decoder& d, const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) {
+    d.b = Bits{in, in + in_len, 0ull, 0, 0};
+    d.in = in; d.out = out; d.in_len = in_len; d.out_len = out_len;
+    d.pos = 0; d.last = 0; d.err = OK; d.phase = PH_HEADER;
+}
+// deflate block header (RFC 1951 3.2.3); a stored block is copied by the decoder's own lane (incompressible data: rare)
+NP_HD void dec_header(Decoder& d, Tables& t) {
+    Bits& b = d.b;
+    d.last = (int32_t)b.get(1);
+    const int32_t type = (int32_t)b.get(2);
+    if (type == 0) {
+        b.drop(b.cnt & 7);                                   // to the next byte boundary
+        const uint32_t l = b.get(16), nl = b.get(16);
+        if ((l ^ 0xffffu) != nl) { d.err = ERR_STORED; d.phase = PH_DONE; return; }
+        // bytes still sitting in the bit buffer belong to the stored data: give them back
+        int32_t back = (b.cnt - b.overrun) / 8; if (back < 0) back = 0;
+        const int32_t src = (int32_t)(b.p - d.in) - back, len = (int32_t)l;
+        if (src + len > (int32_t)d.in_len) { d.err = ERR_INPUT; d.phase = PH_DONE; return; }
+        if (d.pos + len > (int32_t)d.out_len) { d.err = ERR_OUTPUT; d.phase = PH_DONE; return; }
+        for (int32_t i = 0; i < len; i++) d.out[d.pos + i] = d.in[src + i];
+        d.pos += len;
+        b.p = d.in + src + len; b.buf = 0; b.cnt = 0; b.overrun = 0;
+        d.phase = d.last ? PH_DONE : PH_HEADER;
+        return;
+    }
+    if (type == 3) { d.err = ERR_BTYPE; d.phase = PH_DONE; return; }
+    int e = OK;
+    if (type == 1) set_fixed(t); else e = read_dynamic(b, t);
+    if (e) { d.err = e; d.phase = PH_DONE; return; }
+    d.phase = PH_SYMBOLS;
+}
+// Decodes up to BATCH symbols into t.batch; returns their number.  Nothing is written to the output.
+// Tight loop: at most two refill checks, two table loads and two base/extra loads per match.  The bit buffer holds
+// >= 32 valid bits at each check: a literal/length code + extra needs <= 20, a distance code + extra <= 28.
+NP_HD int32_t dec_batch(Decoder& d, Tables& t) {
+    Bits& b = d.b;
+    int32_t nsym = 0;
+    bool run = true, end = false;
+    // A fixed trip count and structured ifs (no continue / break): the decoder lanes of a warp reconverge after every
+    // symbol and execute the loop body together, whatever kind of symbol each of them meets.
+    for (int it = 0; it < BATCH; it++) {
+        if (run) {
+            if (b.cnt < 32) b.refill();
+            uint32_t e = t.fast[(uint32_t)b.buf & ((1u << FASTBITS) - 1u)];
+            int s;
+            if (e & 15u) { b.drop((int)(e & 15u)); s = (int)(e >> 4); }
+            else s = decode_slow(b, t.lcount, t.lsym, FASTBITS, t.lfirst, t.lindex);
+            if (s < 256) {
+                if (s < 0) { d.err = ERR_CODE; run = false; }
+                else t.batch[nsym++] = 0x8000u | (uint32_t)s;
+            } else if (s == 256) { end = true; run = false; }
+            else if (s >= 286) { d.err = ERR_CODE; run = false; }
+            else {
+                const uint32_t lx = t.lenx[s - 257];
+                const uint32_t lxb = lx >> 16;
+                const uint32_t len = (lx & 0xffffu) + ((uint32_t)b.buf & ((1u << lxb) - 1u));
+                b.drop((int)lxb);
+                if (b.cnt < 32) b.refill();
+                e = t.dfast[(uint32_t)b.buf & ((1u << DFASTBITS) - 1u)];
+                int ds;
+                if (e & 15u) { b.drop((int)(e & 15u)); ds = (int)(e >> 4); }
+                else ds = decode_slow(b, t.dcount, t.dsym, DFASTBITS, t.dfirst, t.dindex);
+                if (ds < 0 || ds >= MAXD) { d.err = ERR_CODE; run = false; }
+                else {
+                    const uint32_t dx = t.distx[ds];
+                    const uint32_t dxb = dx >> 16;
+                    const uint32_t dist = (dx & 0xffffu) + ((uint32_t)b.buf & ((1u << dxb) - 1u));
+                    b.drop((int)dxb);
+                    t.batch[nsym++] = len | dist << 16;
+                }
+            }
+        }
+    }
+    if (!d.err && b.past_end()) d.err = ERR_INPUT;
+    if (d.err) { d.phase = PH_DONE; return 0; }              // an inconsistent batch is not resolved
+    if (end) d.phase = d.last ? PH_DONE : PH_HEADER;
+    return nsym;
+}
+NP_HD int dec_status(const Decoder& d) { return d.err ? d.err : d.pos == (int32_t)d.out_len ? OK : ERR_SIZE; }
+
+// Inflates one BGZF block with ONE decoder (lane 0) — the test build's driver (tests/emu) and the reference for the
+// kernel's multi-decoder loop (bgzf_inflate.cu), which runs the same dec_* / resolve_batch steps.
+// W: warp backend with lane(), width(), bcast(int32_t v) (value of lane 0), sync(), exscan(v, &total) (exclusive prefix
+// sum over the lanes), any(pred), ballot(pred), shfl(v, lane).  Returns OK or an ERR_* (same value on every lane).
 template <class W>
 NP_HD int inflate_block(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, Tables& t, W& w) {
     const bool lead = w.lane() == 0;
-    Bits b{in, in + in_len, 0ull, 0, 0};
-    int32_t pos = 0;                  // output bytes written so far (kept identical on all lanes)
-    int32_t last = 0;
-    while (!last) {
-        int32_t type = 0, err = OK;
-        if (lead) { last = (int32_t)b.get(1); type = (int32_t)b.get(2); }
-        last = w.bcast(last); type = w.bcast(type);
-        if (type == 0) {
-            // stored block: LEN, ~LEN, bytes — copied by all lanes
-            int32_t len = 0, src = 0;
-            if (lead) {
-                b.drop(b.cnt & 7);                                   // to the next byte boundary
-                uint32_t l = b.get(16), nl = b.get(16);
-                if ((l ^ 0xffffu) != nl) err = ERR_STORED;
-                // bytes still sitting in the bit buffer belong to the stored data: give them back
-                int32_t back = (b.cnt - b.overrun) / 8; if (back < 0) back = 0;
-                src = (int32_t)(b.p - in) - back;
-                len = (int32_t)l;
-                if (src + len > (int32_t)in_len) err = ERR_INPUT;
-                if (pos + len > (int32_t)out_len) err = ERR_OUTPUT;
-                b.p = in + src + (err ? 0 : len); b.buf = 0; b.cnt = 0; b.overrun = 0;
-            }
-            err = w.bcast(err); if (err) return err;
-            len = w.bcast(len); src = w.bcast(src);
-            for (int32_t i = w.lane(); i < len; i += w.width()) out[pos + i] = in[src + i];
-            pos += len;
-            w.sync();
-            continue;
+    Decoder d;
+    dec_start(d, in, in_len, out, out_len);
+    for (;;) {
+        int32_t nsym = 0;
+        if (lead) {
+            while (d.phase == PH_HEADER) dec_header(d, t);
+            if (d.phase == PH_SYMBOLS) nsym = dec_batch(d, t);
         }
-        if (type == 3) return ERR_BTYPE;
-        if (lead) { if (type == 1) set_fixed(t); else err = read_dynamic(b, t); }
-        err = w.bcast(err); if (err) return err;
-        for (;;) {
-            // lane 0 runs through literals until it meets a match or the end of the block
-            int32_t len = 0, dist = 0, p = pos, state = 0;          // state: 0 match, 1 end of block, >1 error
-            if (lead) {
-                for (;;) {
-                    int s = decode_lit(b, t);
-                    if (s < 0) { state = 1 + ERR_CODE; break; }
-                    if (s < 256) {
-                        if (p >= (int32_t)out_len) { state = 1 + ERR_OUTPUT; break; }
-                        out[p++] = (uint8_t)s;
-                        continue;
-                    }
-                    if (s == 256) { state = 1; break; }
-                    s -= 257;
-                    if (s >= 29) { state = 1 + ERR_CODE; break; }
-                    len = len_base(s) + (int32_t)b.get(len_extra(s));
-                    int ds = decode_dist(b, t);
-                    if (ds < 0 || ds >= MAXD) { state = 1 + ERR_CODE; break; }
-                    dist = dist_base(ds) + (int32_t)b.get(dist_extra(ds));
-                    if (dist > p) state = 1 + ERR_DIST;
-                    else if (p + len > (int32_t)out_len) state = 1 + ERR_OUTPUT;
-                    break;
-                }
-                if (b.past_end()) state = 1 + ERR_INPUT;
-            }
-            state = w.bcast(state);
-            p = w.bcast(p);
-            if (state > 1) return state - 1;
-            pos = p;
-            if (state == 1) break;
-            len = w.bcast(len); dist = w.bcast(dist);
-            w.sync();                                                // lane 0's literals are visible to the copiers
-            // source index of byte i: i for disjoint ranges, i mod dist when the match overlaps its own output (only
-            // the `dist` bytes before pos are read then) — no byte is both read and written within one match
-            if (dist >= len) { for (int32_t i = w.lane(); i < len; i += w.width()) out[pos + i] = out[pos - dist + i]; }
-            else { for (int32_t i = w.lane(); i < len; i += w.width()) out[pos + i] = out[pos - dist + i % dist]; }
-            pos += len;
-            w.sync();
+        nsym = w.bcast(nsym);
+        const int32_t pos = w.bcast(d.pos);
+        w.sync();                                                // the batch (and a stored block's bytes) are visible to every lane
+        if (nsym > 0) {
+            const int32_t np = resolve_batch(out, out_len, pos, nsym, t, w);
+            if (lead) { if (np < 0) { d.err = -np; d.phase = PH_DONE; } else d.pos = np; }
         }
+        if (w.bcast(lead ? d.phase : 0) == PH_DONE) break;
     }
-    return pos == (int32_t)out_len ? OK : ERR_SIZE;
+    return w.bcast(lead ? dec_status(d) : 0);
 }
 
 }  // namespace npz

@@ -10,6 +10,11 @@
 
 namespace npz_dev {
 
+// Stream-ordered allocations come from a memory pool PRIVATE to the calling host thread (and device): loads issued from
+// different threads (the files pipeline runs one worker per slot) never reuse each other's freed blocks, so the
+// allocator never orders one worker's stream behind the other's.  Release threshold = keep everything cached.
+cudaMemPool_t thread_pool(int device);
+
 struct InflateJob {
     void *d_comp = nullptr, *d_blocks = nullptr, *d_status = nullptr;
     size_t nb = 0;

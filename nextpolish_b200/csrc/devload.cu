@@ -50,24 +50,50 @@ enum { DL_ERR_CHAIN = 1, DL_ERR_RECORD = 2, DL_ERR_LONG = 4, DL_ERR_ORDER = 8 };
 
 // One walk per anchor interval: counts the records and writes their offsets into the interval's scratch range
 // (capacity = interval bytes / 36, a record being at least 4 + 32 bytes; range starts computed on the host).
-__global__ void k_rec_walk(const uint8_t* U, int64_t total, const int64_t* anchors, const int64_t* cap_base, int32_t n_int,
-                           int32_t* cnt, int64_t* scratch, int32_t* err) {
-    int32_t i = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+// A record only says how long it is, so the walk is a chain of dependent loads; one WARP per interval streams the
+// interval through shared memory in 4 KiB windows (coalesced 16-byte loads) and lane 0 follows the chain there: one
+// global round trip per ~12 records instead of one per record.
+constexpr int kWalkWin = 4096, kWalkWarps = 4;
+__global__ void __launch_bounds__(kWalkWarps * 32) k_rec_walk(const uint8_t* U, int64_t total, const int64_t* anchors, const int64_t* cap_base, int32_t n_int,
+                                                             int32_t* cnt, int64_t* scratch, int32_t* err) {
+    __shared__ __align__(16) uint8_t win[kWalkWarps][kWalkWin + 16];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int32_t i = (int32_t)(blockIdx.x * kWalkWarps + wid);
     if (i >= n_int) return;
     int64_t off = anchors[i];
     const int64_t end = anchors[i + 1];
     int32_t n = 0;
     int64_t* out = scratch + cap_base[i];
     const int64_t cap = cap_base[i + 1] - cap_base[i];
-    while (off < end) {
-        if (off + 4 > total) { atomicOr(err, DL_ERR_CHAIN); break; }
-        uint32_t bs = ld32(U + off);
-        if (bs < 32u || off + 4 + (int64_t)bs > total || n >= cap) { atomicOr(err, DL_ERR_CHAIN); break; }
-        out[n++] = off;
-        off += 4 + (int64_t)bs;
+    uint8_t* w = win[wid];
+    bool bad = false;
+    while (off < end && !bad) {
+        const int64_t base = off & ~(int64_t)15;                        // U comes from cudaMalloc: 16-byte aligned windows
+        for (int k = lane; k < kWalkWin / 16; k += 32) {
+            const int64_t a = base + 16 * k;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (a + 16 <= total + 16) v = *(const uint4*)(U + a);       // the inflate buffer has 16 bytes of slack
+            *(uint4*)(w + 16 * k) = v;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            while (off < end && off + 4 <= base + kWalkWin) {
+                if (off + 4 > total) { bad = true; break; }
+                const uint8_t* p = w + (off - base);
+                const uint32_t bs = (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
+                if (bs < 32u || off + 4 + (int64_t)bs > total || n >= cap) { bad = true; break; }
+                out[n++] = off;
+                off += 4 + (int64_t)bs;
+            }
+        }
+        off = __shfl_sync(0xffffffffu, off, 0);
+        bad = __shfl_sync(0xffffffffu, (int)bad, 0) != 0;
+        __syncwarp();
     }
-    if (off != end) atomicOr(err, DL_ERR_CHAIN);
-    cnt[i] = n;
+    if (lane == 0) {
+        if (bad || off != end) atomicOr(err, DL_ERR_CHAIN);
+        cnt[i] = n;
+    }
 }
 // scratch ranges -> one dense array of record offsets (one warp per interval)
 __global__ void k_rec_compact(const int64_t* scratch, const int64_t* cap_base, const int32_t* cnt, const int32_t* base, int32_t n_int,
@@ -218,7 +244,12 @@ static cudaStream_t thread_stream(int device) {
 struct Dbuf {
     void* p = nullptr; cudaStream_t st = nullptr;
     ~Dbuf() { if (p) cudaFreeAsync(p, st); }
-    bool alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes + 256, s) == cudaSuccess; }
+    bool alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return cudaMallocFromPoolAsync(&p, bytes + 256, npz_dev::thread_pool(dev), s) == cudaSuccess;
+    }
     template <class T> T* as() const { return (T*)p; }
 };
 
@@ -398,34 +429,66 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     }
 
     // ---- FASTA side (the GPU is busy with the copy and the inflate meanwhile)
+    // Whole-file loads parse straight into a grow-only pinned buffer of the calling thread (one copy, asynchronous upload);
+    // named subsets go through fasta_load (seeks with the .fai).
+    struct PinBuf { uint8_t* p = nullptr; size_t cap = 0; };
+    static thread_local PinBuf fa_pin;
+    std::vector<std::string> fa_names; std::vector<int64_t> fa_off;
     std::vector<FastaRecord> recs;
-    if (!fasta_load(fasta, names, recs, err)) return fail(err);
+    const uint8_t* flat = nullptr;
+    if (all) {
+        auto grow = [](void* ctx, size_t bytes) -> uint8_t* {
+            PinBuf& b = *(PinBuf*)ctx;
+            if (b.cap >= bytes) return b.p;
+            if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+            const size_t want = bytes + bytes / 4 + 4096;
+            if (cudaMallocHost((void**)&b.p, want) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return nullptr; }
+            b.cap = want;
+            return b.p;
+        };
+        // the previous upload out of this buffer has completed: every load ends with a stream synchronisation
+        if (!fasta_load_flat(fasta, fa_names, fa_off, grow, &fa_pin, err)) return fail(err);
+        flat = fa_pin.p;
+    } else {
+        if (!fasta_load(fasta, names, recs, err)) return fail(err);
+        fa_off.push_back(0);
+        for (auto& r : recs) { fa_names.push_back(r.name); fa_off.push_back(fa_off.back() + (int64_t)r.seq.size()); }
+    }
+    const size_t n_fa = fa_names.size();
     // contigs in BAM tid order (those absent from the BAM header go last, with no reads) — as shard_load
     struct Slot { int tid; size_t rec_idx; };
     std::vector<Slot> slots;
-    for (size_t i = 0; i < recs.size(); i++) {
-        auto it = tid_of.find(recs[i].name);
+    for (size_t i = 0; i < n_fa; i++) {
+        auto it = tid_of.find(fa_names[i]);
         slots.push_back({it == tid_of.end() ? 0x7fffffff : it->second, i});
     }
     std::stable_sort(slots.begin(), slots.end(), [](const Slot& a, const Slot& b) { return a.tid < b.tid; });
-    std::vector<uint8_t> ctg_seq;
+    bool identity = flat != nullptr;
+    for (size_t k = 0; k < slots.size() && identity; k++) identity = slots[k].rec_idx == k;
+    std::vector<uint8_t> ctg_perm;                        // only when the order changes or the records came from fasta_load
     std::vector<int32_t> slot_of_tid((size_t)std::max(1, n_ref), -1);
     S->ctg_off.push_back(0);
     for (size_t k = 0; k < slots.size(); k++) {
-        const FastaRecord& r = recs[slots[k].rec_idx];
-        S->names.push_back(r.name);
-        S->fasta_rank.push_back((int32_t)slots[k].rec_idx);
-        ctg_seq.insert(ctg_seq.end(), r.seq.begin(), r.seq.end());
-        S->ctg_off.push_back((int64_t)ctg_seq.size());
+        const size_t ri = slots[k].rec_idx;
+        const size_t len = (size_t)(fa_off[ri + 1] - fa_off[ri]);
+        S->names.push_back(fa_names[ri]);
+        S->fasta_rank.push_back((int32_t)ri);
+        if (!identity) {
+            const uint8_t* src = flat ? flat + fa_off[ri] : (const uint8_t*)recs[ri].seq.data();
+            ctg_perm.insert(ctg_perm.end(), src, src + len);
+        }
+        S->ctg_off.push_back(S->ctg_off.back() + (int64_t)len);
         if (slots[k].tid != 0x7fffffff && slot_of_tid[(size_t)slots[k].tid] < 0) slot_of_tid[(size_t)slots[k].tid] = (int32_t)k;
     }
+    const uint8_t* ctg_ptr = identity ? flat : ctg_perm.data();
+    const size_t ctg_bytes = (size_t)S->ctg_off.back();
     const int32_t n_slots = (int32_t)slots.size();
-    if (ctg_seq.size() >= 0x7fffff00ull) return fail("shard exceeds 2^31 positions: load it in several contig groups");
+    if (ctg_bytes >= 0x7fffff00ull) return fail("shard exceeds 2^31 positions: load it in several contig groups");
     S->ctg_read_off.assign((size_t)n_slots + 1, 0);
-    S->seq_bytes = (int64_t)ctg_seq.size();
+    S->seq_bytes = (int64_t)ctg_bytes;
     lap("fasta_load + contig table");
-    if (!S->seq.alloc(ctg_seq.size() + 16, st)) return fail("cudaMalloc failed");
-    if (!ctg_seq.empty()) cudaMemcpyAsync(S->seq.p, ctg_seq.data(), ctg_seq.size(), cudaMemcpyHostToDevice, st);
+    if (!S->seq.alloc(ctg_bytes + 16, st)) return fail("cudaMalloc failed");
+    if (ctg_bytes) cudaMemcpyAsync(S->seq.p, ctg_ptr, ctg_bytes, cudaMemcpyHostToDevice, st);
     auto finish_empty = [&]() {
         if (!S->rec_off.alloc(16, st) || !S->rec.alloc(16, st) || (with_qual && (!S->qual_off.alloc(16, st) || !S->qual.alloc(16, st)))) return false;
         cudaMemsetAsync(S->rec_off.p, 0, 16, st);
@@ -447,7 +510,7 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     cudaMemsetAsync(d_cnt.p, 0, ((size_t)n_int + 2) * 4, st);
     int32_t n_rec = 0, h_err = 0;
     if (n_int > 0) {
-        k_rec_walk<<<(n_int + 63) / 64, 64, 0, st>>>(U.as<uint8_t>(), total, d_anch.as<int64_t>(), d_capb.as<int64_t>(), n_int, d_cnt.as<int32_t>(),
+        k_rec_walk<<<(n_int + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, 0, st>>>(U.as<uint8_t>(), total, d_anch.as<int64_t>(), d_capb.as<int64_t>(), n_int, d_cnt.as<int32_t>(),
                                                    d_scratch.as<int64_t>(), d_err.as<int32_t>());
         if (!exscan(d_cnt.as<int32_t>(), d_base.as<int32_t>(), n_int + 1, st)) return fail("cudaMalloc failed");
         cudaMemcpyAsync(&n_rec, d_base.as<int32_t>() + n_int, 4, cudaMemcpyDeviceToHost, st);
@@ -466,7 +529,7 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     cudaMemcpyAsync(d_sot.p, slot_of_tid.data(), slot_of_tid.size() * 4, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_goff.p, S->ctg_off.data(), ((size_t)n_slots + 1) * 8, cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(d_scount.p, 0, ((size_t)n_slots + 1) * 4, st);
-    const int64_t G = (int64_t)ctg_seq.size();
+    const int64_t G = (int64_t)ctg_bytes;
     if (with_qual == 2) {
         if (!d_lc.alloc(((size_t)G + 2) * 4, st) || !d_lcf.alloc(((size_t)G + 2) * 4, st)) return fail("cudaMalloc failed");
         k_lower_flags<<<(unsigned)((G + 1 + 255) / 256), 256, 0, st>>>(S->seq.as<uint8_t>(), G, d_lcf.as<int32_t>());
@@ -509,8 +572,7 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     if (er != cudaSuccess) return fail(cudaGetErrorString(er));
     lap("pack (sync)");
     if (trace) {
-        cudaMemPool_t pool; unsigned long long used = 0, resv = 0; size_t fr = 0, tt = 0;
-        cudaDeviceGetDefaultMemPool(&pool, device);
+        cudaMemPool_t pool = npz_dev::thread_pool(device); unsigned long long used = 0, resv = 0; size_t fr = 0, tt = 0;
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &resv);
         cudaMemGetInfo(&fr, &tt);

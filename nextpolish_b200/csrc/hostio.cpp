@@ -105,6 +105,47 @@ bool fasta_names(const std::string& path, std::vector<std::string>& names,
     return true;
 }
 
+bool fasta_load_flat(const std::string& path, std::vector<std::string>& names, std::vector<int64_t>& off,
+                     uint8_t* (*grow)(void* ctx, size_t bytes), void* ctx, std::string& err) {
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) { err = "cannot open " + path; return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); err = "cannot stat " + path; return false; }
+    const size_t n = (size_t)st.st_size;
+    names.clear(); off.assign(1, 0);
+    if (n == 0) { close(fd); return true; }
+    void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) { err = "cannot map " + path; return false; }
+    const char* text = (const char*)m;
+    uint8_t* dst = grow(ctx, n + 16);                 // the sequences are never longer than the file
+    if (!dst) { munmap(m, n); err = "out of memory"; return false; }
+    size_t i = 0, w = 0;
+    bool in_rec = false;
+    while (i < n) {
+        const void* nl = memchr(text + i, '\n', n - i);
+        const size_t le = nl ? (size_t)((const char*)nl - text) : n;
+        if (text[i] == '>') {
+            if (in_rec) off.push_back((int64_t)w);
+            size_t ns = i + 1, ne = ns;
+            while (ne < le && !isspace((unsigned char)text[ne])) ne++;
+            names.emplace_back(text + ns, ne - ns);
+            in_rec = true;
+        } else if (in_rec) {
+            const char* p = text + i;
+            const size_t len = le - i;
+            unsigned bad = 0;                                    // any byte outside isgraph (33..126)?
+            for (size_t k = 0; k < len; k++) bad |= (unsigned)((unsigned char)(p[k] - 33) >= 94u);
+            if (!bad) { memcpy(dst + w, p, len); w += len; }
+            else for (size_t k = 0; k < len; k++) if (isgraph((unsigned char)p[k])) dst[w++] = (uint8_t)p[k];
+        }
+        i = le + 1;
+    }
+    if (in_rec) off.push_back((int64_t)w);
+    munmap(m, n);
+    return true;
+}
+
 bool fasta_load(const std::string& path, const std::vector<std::string>& names,
                 std::vector<FastaRecord>& out, std::string& err) {
     std::vector<FaiEntry> fai;

@@ -21,6 +21,13 @@ struct FastaRecord {
     std::string seq;   // whitespace removed, case preserved
 };
 
+// Every sequence of a FASTA file, concatenated without line breaks into `dst` (grown through `grow(bytes)`, which returns
+// the — possibly moved — buffer of at least that many bytes; contents up to the previous size are preserved by the caller's
+// allocator or re-parsed): names[i] owns dst[off[i], off[i+1]).  One pass over an mmap of the file, one copy.
+// Same character rules as fasta_load (isgraph bytes of non-header lines; junk before the first header is skipped).
+bool fasta_load_flat(const std::string& path, std::vector<std::string>& names, std::vector<int64_t>& off,
+                     uint8_t* (*grow)(void* ctx, size_t bytes), void* ctx, std::string& err);
+
 // Reads all (names == empty) or the named sequences. Uses <fasta>.fai when present to seek.
 bool fasta_load(const std::string& path, const std::vector<std::string>& names,
                 std::vector<FastaRecord>& out, std::string& err);

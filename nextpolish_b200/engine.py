@@ -244,8 +244,9 @@ class FilePipeline:
     def in_flight(self):
         return len(self.tickets)
 
-    def wait_oldest(self, want_seqs=False):
-        """Finishes the oldest outstanding job -> dict(task, names, md5 {name: hex}, h2d_bytes, d2h_bytes[, seqs])."""
+    def wait_oldest(self, want_seqs=False, want_md5=True):
+        """Finishes the oldest outstanding job -> dict(task, names, md5 {name: hex}, h2d_bytes, d2h_bytes[, seqs]).
+        want_md5=False skips the hashing (the result bytes stay valid in the slot until its next submit)."""
         import hashlib
         from .binding import FilesResult
         t = self.tickets.pop(0)
@@ -258,8 +259,11 @@ class FilePipeline:
                "load_ms": r.load_ms, "polish_ms": r.polish_ms, "md5": {}}
         seqs = {}
         for i, nm in enumerate(names):
+            if not (want_md5 or want_seqs):
+                break
             b = C.string_at(r.seq + r.start[i], r.len[i])
-            out["md5"][nm] = hashlib.md5(b).hexdigest()
+            if want_md5:
+                out["md5"][nm] = hashlib.md5(b).hexdigest()
             if want_seqs:
                 seqs[nm] = b
         if want_seqs:

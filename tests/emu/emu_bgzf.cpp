@@ -12,6 +12,10 @@ struct OneLane {
     int32_t width() const { return 1; }
     int32_t bcast(int32_t v) const { return v; }
     void sync() const {}
+    int32_t exscan(int32_t v, int32_t* total) const { *total = v; return 0; }
+    bool any(bool p) const { return p; }
+    uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+    int32_t shfl(int32_t v, int32_t) const { return v; }
 };
 }  // namespace
 
@@ -31,6 +35,7 @@ extern "C" int np_emu_bgzf_inflate(const uint8_t* comp, int64_t comp_bytes, uint
         const npz::Block& b = blocks[i];
         if (!b.out_len) continue;
         memset(&t, 0xA5, sizeof t);                       // poison: the decoder must initialise what it reads
+        npz::init_tables(t, w);
         int rc = npz::inflate_block(comp + b.in_off, b.in_len, out + b.out_off, b.out_len, t, w);
         if (rc != npz::OK) return rc;
     }

@@ -29,7 +29,7 @@ def main():
             print("%-90s %-10s %s" % (h, units[i], vals[i]))
     tmp = tempfile.mkdtemp()
     run("cd %s && cuobjdump -xelf all %s/nextpolish_b200/lib/nextpolish1.so" % (tmp, ROOT))
-    dis = run("nvdisasm -g -c %s/engine.sm_100a.cubin" % tmp).split("\n")
+    dis = run("nvdisasm -g -c %s/%s.sm_100a.cubin" % (tmp, os.environ.get("NCU_CUBIN", "engine"))).split("\n")
     start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l)
     cur, seq = None, {}
     for l in dis[start + 1:]:
