@@ -118,6 +118,7 @@ void          polishresult_destory(PolishResult* polishresult);
 
 #define NP_TASK_SCORE_CHAIN 1
 #define NP_TASK_KMER_COUNT  2
+#define NP_TASK_SNP_VALID   4   /* snp_valid, snpvalid.c:3-35 (task 4 of nextpolish1.py) */
 
 /*
  * One packed read block ("record"), 16-byte aligned, little endian:

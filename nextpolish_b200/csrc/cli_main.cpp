@@ -1,6 +1,7 @@
 // cli_main.cpp — native CLI with the argument grammar of the reference's main.c:12-75:
 //   nextpolish1 scorechain <fasta> <sgs.bam>   > out.fa
 //   nextpolish1 kmercount  <fasta> <sgs.bam>   > out.fa
+//   nextpolish1 snpvalid   <fasta> <sgs.bam>   > out.fa
 // Output format of contig_write_to_file (contig.c:1050): ">name_<step>\nSEQ\n", contigs in FASTA
 // order; "total time" trace on stderr (contig.c:1116).  Unlike the reference, all contigs are
 // polished in ONE batch on the GPU (np_* batch ABI) instead of one call per contig.
@@ -16,6 +17,7 @@ static int usage(const char* a0) {
     printf("Usage: %s <command> [options]\n\nCommands:\n"
            "\tscorechain\t\tscore chain run\n\t\t\t\teg. scorechain fastafn sgsbamf > output.fa\n"
            "\tkmercount\t\tkmer count run\n\t\t\t\teg. kmercount fastafn sgsbamf > output.fa\n"
+           "\tsnpvalid\t\tsnp valid run\n\t\t\t\teg. snpvalid fastafn sgsbamf > output.fa\n"
            "\tsimulate\t\twrite a seeded synthetic draft + sorted BAM\n"
            "\t\t\t\teg. simulate out.fa out.bam n_contigs contig_len depth seed [lowercase_frac]\n\n", a0);
     return 0;
@@ -36,6 +38,7 @@ int main(int argc, char* argv[]) {
     int step = 0;
     if (strcmp(argv[1], "scorechain") == 0) step = 1;
     else if (strcmp(argv[1], "kmercount") == 0) step = 2;
+    else if (strcmp(argv[1], "snpvalid") == 0) step = 4;
     else return usage(argv[0]);
     if (argc != 4) { printf("%s %s fastafn lgsbam\n", argv[0], argv[1]); return 0; }
     time_t t0 = time(nullptr);
@@ -46,11 +49,11 @@ int main(int argc, char* argv[]) {
     np_dev_shard* ds = nullptr;
     np_shard* sh = nullptr;
     const char* hl = getenv("NEXTPOLISH_B200_HOST_LOAD");
-    if (!(hl && hl[0] == '1')) ds = np_shard_load_gpu(dev, argv[2], argv[3], nullptr, 0, step == 2 ? 2 : 0);
+    if (!(hl && hl[0] == '1')) ds = np_shard_load_gpu(dev, argv[2], argv[3], nullptr, 0, step == 2 ? 2 : step == 4 ? 1 : 0);
     np_shard_view v;
     if (ds) np_dev_shard_view(ds, &v);
     else {
-        sh = np_shard_load(argv[2], argv[3], nullptr, 0, step == 2 ? 2 : 0, 8);
+        sh = np_shard_load(argv[2], argv[3], nullptr, 0, step == 2 ? 2 : step == 4 ? 1 : 0, 8);
         if (!sh) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
         np_shard_view_of(sh, &v);
     }

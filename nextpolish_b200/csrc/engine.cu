@@ -657,9 +657,9 @@ int32_t np_engine_run(np_engine* e, int32_t task, const Configure* cfg) {
         if (v1 && v1[0] == '1') err = npe::run_score_chain(e->be, e->d, &e->st, !npe::rate_is_dyadic(e->d.P.rate));
         else err = npe::run_score_chain_v2(e->be, e->d, e->h_ctg_off.data(), &e->st, &e->vs);
     }
-    else if (task == NP_TASK_KMER_COUNT) {
-        if (!e->d.qual_off) { np::set_error("np_engine_run: task 2 needs the quality stream (load the shard with_qual)"); return NP_ERR_ARG; }
-        err = npe::run_kmer_count(e->be, e->d, &e->st);
+    else if (task == NP_TASK_KMER_COUNT || task == NP_TASK_SNP_VALID) {
+        if (!e->d.qual_off) { np::set_error("np_engine_run: tasks 2 and 4 need the quality stream (load the shard with_qual)"); return NP_ERR_ARG; }
+        err = npe::run_kmer_count(e->be, e->d, &e->st, task);
     } else { np::set_error("np_engine_run: unknown task"); return NP_ERR_ARG; }
     if (!e->be.ok) { np::set_error("CUDA failure: " + e->be.msg); return NP_ERR_CUDA; }
     if (err) {
@@ -905,7 +905,7 @@ static PolishResult* run_one_contig(const char* tigname, Configure* cfg, int tas
     if (!tigname || !cfg || !cfg->fastafn) { fprintf(stderr, "nextpolish_b200: bad arguments\n"); exit(1); }
     np_engine* e = process_engine();
     const char* names[1] = {tigname};
-    const int wq = task == NP_TASK_KMER_COUNT ? 2 : 0;
+    const int wq = task == NP_TASK_KMER_COUNT ? 2 : task == NP_TASK_SNP_VALID ? 1 : 0;
     // the contig's shard is built on the GPU from the BAM's compressed bytes when <bam>.bai exists (devload.cu);
     // otherwise (or with NEXTPOLISH_B200_HOST_LOAD=1) by the host packer
     np_dev_shard* ds = nullptr;
@@ -957,7 +957,7 @@ static PolishResult* out_of_scope(const char* what) {
     return nullptr;
 }
 PolishResult* snp_phase(const char*, Configure*) { return out_of_scope("snp_phase"); }
-PolishResult* snp_valid(const char*, Configure*) { return out_of_scope("snp_valid"); }
+PolishResult* snp_valid(const char* tigname, Configure* configure) { return run_one_contig(tigname, configure, NP_TASK_SNP_VALID); }
 PolishResult* lgspolish(const char*, Configure*) { return out_of_scope("lgspolish"); }
 
 }  // extern "C"

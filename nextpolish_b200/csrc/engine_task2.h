@@ -65,6 +65,12 @@ struct Dev2 {
     int32_t *wcand, *wsoff;      // per window: candidate count; scratch offset (bytes, in 4-byte units)
     int32_t* wscratch;           // strings + tallies
     int32_t* wbest;              // [NW] offset of the winner string in wscratch (bytes), or -1
+    int32_t flagzero;            // ss_kmer_correct's flagzero (kmercount.c:175): 1 = parsed reads leave FLAG_ZERO alone and a window
+                                 // that found a string is cleared as a whole (snp_valid's first pass, snpvalid.c:18)
+    int32_t *wfail, *wfidx;      // snp_valid: window found no string; exclusive scan
+    int32_t *fcnt, *foff;        // snp_valid: sub-windows of every failed window (snpvalid.c:37-66), scan
+    const int32_t* win1;         // snp_valid: the first pass's windows while the second list is built
+    int32_t NW1; int32_t* warn;  // [1] device flag: a cut-point list was odd / inverted (reference behaviour undefined)
     // (window, read) pairs of the vote: walks run one thread per pair
     int32_t *wp_cnt, *wp_off;    // per window: candidates (+1 slot for the stale record), scan
     int32_t *wp_read;            // per pair: read index (-1: unused stale slot)
@@ -711,7 +717,7 @@ struct WindowVote {      // ss_kmer_correct for one window (kmercount.c:188-253)
             const int32_t* slot = base + (size_t)j * sw;
             const int32_t* meta = slot + lw;
             int32_t length = meta[0];
-            if (length > 0) {
+            if (length > 0 && !w.flagzero) {
                 int32_t a = meta[2], b = meta[2] + length;
                 if (clr_hi == clr_lo) { clear_range(a, b); clr_lo = a; clr_hi = b; }
                 else if (b < clr_lo || a > clr_hi) clear_range(a, b);
@@ -743,6 +749,7 @@ struct WindowVote {      // ss_kmer_correct for one window (kmercount.c:188-253)
         }
         int32_t best = -1;
         if (nstr > 0) {
+            if (w.flagzero) clear_range(d.colbase[s], d.colbase[e] + 1);      // contig_clean_flag(start, end, FLAG_ZERO_N), kmercount.c:222-224
             if (count == d.P.max_count_kmer) {
                 int32_t want = 60 * count;
                 for (int32_t q = 0; q < nstr; q++) if (tal[4 * q + 2] == want) { best = q; break; }
@@ -775,9 +782,83 @@ struct WindowApply {     // contig_update_contig in window order: a later window
     }
 };
 
-// ---- orchestration ------------------------------------------------------------------------------
+// ---- snp_valid's second pass: a window that found no string is cut again (fts_spilt_region, snpvalid.c:37-66) -------
+// cut points: the middle of every unflagged stretch that a flagged column follows (twice, or once for the stretch the
+// window starts with), then the window's end; ss_kmer_correct reads them as (start, end) pairs.  out == nullptr: count.
+// A list that is odd, or has start > end (a window that starts on a flagged column / has no flagged column), makes the
+// reference read past its list: undefined there; here the dangling point and inverted pairs are dropped and *warn is set.
+NP_HD int32_t fts_split(const Dev& d, int32_t start, int32_t end, int32_t* out, int32_t* warn) {
+    int32_t np = 0, npair = 0, pend = 0;
+    int32_t qstart = -1, qend = -1;
+    auto point = [&](int32_t v) {
+        if (np & 1) {
+            if (pend <= v) { if (out) { out[2 * npair] = pend; out[2 * npair + 1] = v; } npair++; }
+            else *warn = 1;
+        } else pend = v;
+        np++;
+    };
+    for (int32_t c = d.colbase[start]; c <= d.colbase[end]; c++) {
+        const int32_t i = d.colpos[c];
+        if (!(d.oflag[c] & FLAG_ZERO)) { if (qstart == -1) qstart = i; qend = i; }
+        else if (qstart != -1) {
+            int count = 2;
+            if (qstart == start) { qend = start; count--; }
+            int32_t mid = (qstart + qend) / 2;
+            for (int k = 0; k < count; k++) { point(mid); if (qstart != qend) mid++; }
+            qstart = qend = -1;
+        }
+    }
+    point(end);
+    if (np & 1) *warn = 1;
+    return npair;
+}
+struct WinFailFlag {     // per first-pass window
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B&) const { w.wfail[i] = (i < w.NW && w.wbest[i] < 0) ? 1 : 0; }
+};
+struct FtsCount {        // per first-pass window (failed ones count their sub-windows)
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B&) const {
+        int32_t n = 0;
+        if (i < w.NW1 && w.wfail[i]) n = fts_split(w.d, w.win1[2 * i], w.win1[2 * i + 1], nullptr, w.warn);
+        w.fcnt[i] = n;
+    }
+};
+struct FtsFill {
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t i, B&) const {
+        int32_t dummy = 0;
+        if (w.wfail[i] && w.fcnt[i] > 0) fts_split(w.d, w.win1[2 * i], w.win1[2 * i + 1], w.win + 2 * (size_t)w.foff[i], &dummy);
+    }
+};
+
+// the vote over the windows w.win[0 .. NW) (kmercount.c:175-261): candidates, column strings, tally, winner, apply
 template <class BE>
-int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
+void run_window_votes(BE& be, Dev2& w) {
+    if (w.NW <= 0) return;
+    w.wcand = be.template buf<int32_t>("wcand", (size_t)w.NW + 1);
+    w.wsoff = be.template buf<int32_t>("wsoff", (size_t)w.NW + 1);
+    w.wbest = be.template buf<int32_t>("wbest", (size_t)w.NW + 1);
+    w.wp_cnt = be.template buf<int32_t>("wp_cnt", (size_t)w.NW + 1);
+    w.wp_off = be.template buf<int32_t>("wp_off", (size_t)w.NW + 1);
+    be.launch("window_count", (int64_t)w.NW + 1, WindowCount{w});
+    be.exscan_i32(w.wcand, w.wsoff, (int64_t)w.NW + 1);
+    be.exscan_i32(w.wp_cnt, w.wp_off, (int64_t)w.NW + 1);
+    int32_t WS = 0;
+    { const int32_t* ptrs[2] = {w.wsoff + w.NW, w.wp_off + w.NW}; int32_t v[2]; be.read_many(ptrs, 2, v); WS = v[0]; w.NP_w = v[1]; }
+    w.wscratch = be.template buf<int32_t>("wscratch", (size_t)WS + 4);
+    w.wp_read = be.template buf<int32_t>("wp_read", (size_t)w.NP_w + 1);
+    be.launch("window_fill", w.NW, WinPairFill{w});
+    be.launch("window_walk", w.NP_w, WinWalk{w});
+    be.launch("window_vote", w.NW, WindowVote{w});
+    be.launch("window_apply", w.NW, WindowApply{w});
+}
+
+// ---- orchestration ------------------------------------------------------------------------------
+// mode 2: kmer_count (kmercount.c:93-126); mode 4: snp_valid (snpvalid.c:3-35: the k-mer regions only, a first vote that
+// leaves FLAG_ZERO to whole windows, a second vote over the re-cut windows that found no string, no lowercase on output)
+template <class BE>
+int run_kmer_count(BE& be, Dev& d0, RunStats* st, int mode = 2) {
     Dev2 w; memset(&w, 0, sizeof(w));
     Dev& d = w.d; d = d0;
     const int64_t R = d.n_reads; const int32_t G = d.G;
@@ -833,6 +914,7 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
     // insertion columns inside regions only
     w.inreg = be.template buf<uint8_t>("inreg", (size_t)G + 2);
     be.zero(w.inreg, (size_t)G + 2);
+    if (mode == 4) w.NR_nd = 0;                                  // snp_valid has no low-depth re-scoring
     if (w.NR_nd > 0) be.launch("region_diff_nd", w.NR_nd, RegionDiff{w, 0});
     if (w.NR_km > 0) be.launch("region_diff_km", w.NR_km, RegionDiff{w, 1});
     if (R > 0) be.launch("insert_len2", R, InsertLen2{w});
@@ -902,28 +984,34 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st) {
         w.NW = be.read_i32(w.woff + w.NR_km);
         w.win = be.template buf<int32_t>("win", 2 * (size_t)w.NW + 2);
         be.launch("split_fill", w.NR_km, SplitFill{w});
-        w.wcand = be.template buf<int32_t>("wcand", (size_t)w.NW + 1);
-        w.wsoff = be.template buf<int32_t>("wsoff", (size_t)w.NW + 1);
-        w.wbest = be.template buf<int32_t>("wbest", (size_t)w.NW + 1);
-        w.wp_cnt = be.template buf<int32_t>("wp_cnt", (size_t)w.NW + 1);
-        w.wp_off = be.template buf<int32_t>("wp_off", (size_t)w.NW + 1);
-        be.launch("window_count", (int64_t)w.NW + 1, WindowCount{w});
-        be.exscan_i32(w.wcand, w.wsoff, (int64_t)w.NW + 1);
-        be.exscan_i32(w.wp_cnt, w.wp_off, (int64_t)w.NW + 1);
-        int32_t WS = 0;
-        { const int32_t* ptrs[2] = {w.wsoff + w.NW, w.wp_off + w.NW}; int32_t v[2]; be.read_many(ptrs, 2, v); WS = v[0]; w.NP_w = v[1]; }
-        w.wscratch = be.template buf<int32_t>("wscratch", (size_t)WS + 4);
-        w.wp_read = be.template buf<int32_t>("wp_read", (size_t)w.NP_w + 1);
-        be.launch("window_fill", w.NW, WinPairFill{w});
-        be.launch("window_walk", w.NP_w, WinWalk{w});
-        be.launch("window_vote", w.NW, WindowVote{w});
-        be.launch("window_apply", w.NW, WindowApply{w});
+        w.flagzero = mode == 4 ? 1 : 0;
+        run_window_votes(be, w);
+        if (mode == 4 && w.NW > 0) {
+            // second pass over the windows that found no string
+            const int32_t NW1 = w.NW;
+            w.NW1 = NW1; w.win1 = w.win;
+            w.wfail = be.template buf<int32_t>("wfail", (size_t)NW1 + 1);
+            w.fcnt = be.template buf<int32_t>("fcnt", (size_t)NW1 + 1);
+            w.foff = be.template buf<int32_t>("foff", (size_t)NW1 + 1);
+            w.warn = be.template buf<int32_t>("snp_warn", 1);
+            be.zero(w.warn, sizeof(int32_t));
+            be.launch("win_fail", (int64_t)NW1 + 1, WinFailFlag{w});
+            be.launch("fts_count", (int64_t)NW1 + 1, FtsCount{w});
+            be.exscan_i32(w.fcnt, w.foff, (int64_t)NW1 + 1);
+            const int32_t NW2 = be.read_i32(w.foff + NW1);
+            if (NW2 > 0) {
+                w.win = be.template buf<int32_t>("win2", 2 * (size_t)NW2 + 2);
+                be.launch("fts_fill", NW1, FtsFill{w});
+                w.NW = NW2; w.flagzero = 0;
+                run_window_votes(be, w);
+            }
+        }
     }
     be.exscan_keep(d.obase, d.keepidx, (int64_t)C);
     int32_t total = 0, err = 0;
     { const int32_t* ptrs[2] = {d.keepidx + C, d.err}; int32_t v[2]; be.read_many(ptrs, 2, v); total = v[0]; err = v[1]; }
     d.out = be.template buf<uint8_t>("out", (size_t)total + 1);
-    if (C > 0) be.launch("emit", C, Emit{d, (uint8_t)FLAG_ZERO});
+    if (C > 0) be.launch("emit", C, Emit{d, (uint8_t)(mode == 4 ? 0 : FLAG_ZERO)});
     be.launch("out_offsets", (int64_t)d.n_ctg + 1, OutOffsets{d});
     run_trace(be, d);
     if (st) { st->C = C; st->T = w.NW; st->sym_words = w.NR_nd; st->table_entries = w.NR_km; st->out_bytes = total; }

@@ -50,7 +50,7 @@ static void run_job(np_files* P, Slot& s) {
     cudaSetDevice(P->device);
     s.rc = NP_OK; s.err.clear();
     const double t0 = now_ms();
-    const int wq = s.task == NP_TASK_KMER_COUNT ? 2 : 0;
+    const int wq = s.task == NP_TASK_KMER_COUNT ? 2 : s.task == NP_TASK_SNP_VALID ? 1 : 0;
     np_dev_shard* ds = np_shard_load_gpu(P->device, s.fasta.c_str(), s.bam.c_str(), nullptr, 0, wq);
     if (!ds) { s.rc = NP_ERR_IO; s.err = np_last_error(); return; }
     np_shard_view v;
@@ -146,7 +146,7 @@ void np_files_destroy(np_files* P) {
 }
 
 int64_t np_files_submit(np_files* P, int32_t task, const char* fasta, const char* bam, const Configure* cfg) {
-    if (!P || !fasta || !bam || !cfg || (task != NP_TASK_SCORE_CHAIN && task != NP_TASK_KMER_COUNT)) { np::set_error("np_files_submit: bad arguments"); return NP_ERR_ARG; }
+    if (!P || !fasta || !bam || !cfg || (task != NP_TASK_SCORE_CHAIN && task != NP_TASK_KMER_COUNT && task != NP_TASK_SNP_VALID)) { np::set_error("np_files_submit: bad arguments"); return NP_ERR_ARG; }
     const int64_t ticket = P->next_ticket;
     Slot& s = *P->slots[(size_t)(ticket % (int64_t)P->slots.size())];
     {

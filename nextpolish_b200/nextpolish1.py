@@ -18,7 +18,8 @@ Behavioural contract kept from the reference (nextpolish1.py:148-235):
   * -debug sets Configure.trace_polish_open and prints "name pos index curbase base" change points to stderr
     (nextpolish1.py:133,230-231).
 The shard is built on the GPU from the BAM's compressed bytes when <bam>.bai exists (np_shard_load_gpu), by the host
-packer otherwise.  Not supported: tasks 3-5 (exit code 1, like the reference does for task 5)."""
+packer otherwise.  Tasks 1 (score_chain), 2 (kmer_count) and 4 (snp_valid) run on the GPU; not supported: tasks 3 and 5
+(exit code 1, like the reference does for task 5)."""
 import argparse
 import os
 import sys
@@ -78,8 +79,8 @@ def main(argv=None):
                             ("min_len_inter_kmer", int, 5), ("max_count_kmer", int, 50)):
         ap.add_argument("-" + flag, type=typ, default=dflt)
     args, _unknown = ap.parse_known_args(argv)
-    if args.task not in (1, 2):
-        sys.stderr.write("tasks 3-5 are outside this engine's scope: use the reference nextpolish1.py / nextpolish2.py\n")
+    if args.task not in (1, 2, 4):
+        sys.stderr.write("tasks 3 and 5 are outside this engine's scope: use the reference nextpolish1.py / nextpolish2.py\n")
         return 1
     from nextpolish_b200 import engine as E
 
@@ -105,7 +106,7 @@ def main(argv=None):
     c.trace_polish_open = 1 if args.debug else 0        # nextpolish1.py:133
     if names:
         dev = int(os.environ.get("NEXTPOLISH_B200_DEVICE", "0"))
-        wq = 2 if args.task == 2 else 0
+        wq = 2 if args.task == 2 else 1 if args.task == 4 else 0
         eng = E.Engine(dev)
         shard = None
         if args.bam_sgs and os.path.exists(args.bam_sgs + ".bai") and os.environ.get("NEXTPOLISH_B200_HOST_LOAD") != "1":

@@ -670,8 +670,8 @@ static int ks_compare(const KS* a, const KS* b)              /* kmercount.c:63-8
     return 0;
 }
 
-/* kmercount.c:175-261 (nodepth = NULL, flagzero = 0) */
-static void kmer_correct(Ctg* g, const IList* region)
+/* kmercount.c:175-261: windows without an accepted string go to `nodepth` (may be NULL); flagzero as in the reference */
+static void kmer_correct(Ctg* g, const IList* region, IList* nodepth, int flagzero)
 {
     KSList rl = {0, 0, 0};
     for (int i = 0; i < region->n; i += 2) {
@@ -689,7 +689,7 @@ static void kmer_correct(Ctg* g, const IList* region)
             ncand++;
             if (read_filter(g, &rd) == 2) {
                 ks.length = 0; ks.qual = 0; ks.mapqual = 0; ks.num = 0;   /* ks_clean */
-                kmer_get_region(g, &rd, start, end, length, &rl, &ks, 0);
+                kmer_get_region(g, &rd, start, end, length, &rl, &ks, flagzero);
                 if (ks.mapqual == MAX_MAPQ) {
                     count++;
                     if (count >= g->cfg->max_count_kmer) { broke = 1; break; }
@@ -703,11 +703,13 @@ static void kmer_correct(Ctg* g, const IList* region)
             for (int64_t t = 0; t < ncand; t++) {
                 if (read_filter(g, &st) == 1) {
                     ks.length = 0; ks.qual = 0; ks.mapqual = 0; ks.num = 0;
-                    kmer_get_region(g, &st, start, end, length, &rl, &ks, 0);
+                    kmer_get_region(g, &st, start, end, length, &rl, &ks, flagzero);
                 }
             }
         }
         if (rl.n > 0) {
+            if (flagzero)                                               /* contig_clean_flag(start, end, FLAG_ZERO_N), contig.c:823-831 */
+                for (int32_t c = g->colbase[start]; c <= g->colbase[end]; c++) g->col[c].flag &= (uint8_t)~FLAG_ZERO;
             KS* best = NULL;
             if (count == g->cfg->max_count_kmer) {
                 int32_t want = MAX_MAPQ * count;
@@ -719,7 +721,7 @@ static void kmer_correct(Ctg* g, const IList* region)
             }
             /* contig.c:811-821 */
             for (int32_t c = g->colbase[start], q = 0; c <= g->colbase[end]; c++, q++) g->col[c].base = best->region[q];
-        }
+        } else if (nodepth) { il_push(nodepth, start); il_push(nodepth, end); }
         for (int k = 0; k < rl.n; k++) free(rl.d[k].region);
         rl.n = 0;
         free(ks.region);
@@ -760,21 +762,78 @@ static int64_t run_kmer_count(Ctg* g, uint8_t* out, int64_t cap)
     if (kmerregion.n > 0) {
         IList win = {0, 0, 0};
         split_region(g, &kmerregion, 0x1, g->cfg->max_len_kmer, &win);
-        kmer_correct(g, &win);
+        kmer_correct(g, &win, NULL, 0);
         free(win.d);
     }
     free(nodepth.d); free(kmerregion.d);
     return get_contig(g, FLAG_ZERO, out, cap);
 }
 
+/* snpvalid.c:37-66: cut points of a window that found no string: the middle of every unflagged stretch that a flagged
+ * column follows (twice, or once for the stretch the window starts with), then the window's end.  The list is read as
+ * (start, end) pairs by ss_kmer_correct: a window that starts on a flagged column, or has no flagged column at all,
+ * yields an odd number of points — the reference then reads one int past the list (undefined behaviour); callers of this
+ * restatement only pin inputs on which every list is even. */
+static void fts_split_region(Ctg* g, int32_t start, int32_t end, uint8_t flag, IList* result)
+{
+    int32_t qstart = -1, qend = -1;
+    for (int32_t c = g->colbase[start]; c <= g->colbase[end]; c++) {
+        const int32_t i = g->colpos[c];
+        if ((g->col[c].flag & flag) == 0) { if (qstart == -1) qstart = i; qend = i; }
+        else if (qstart != -1) {
+            int count = 2;
+            if (qstart == start) { qend = start; count--; }
+            int32_t mid = (qstart + qend) / 2;
+            for (int k = 0; k < count; k++) { il_push(result, mid); if (qstart != qend) mid++; }
+            qstart = qend = -1;
+        }
+    }
+    il_push(result, end);
+}
+
+/* snpvalid.c:3-35.  Returns -2 when a second-pass window list is odd (the reference's behaviour is undefined there). */
+static int64_t run_snp_valid(Ctg* g, uint8_t* out, int64_t cap)
+{
+    g->filter_kind = 0;
+    if (g->L == 0) return 0;
+    ctg_layout(g);
+    IList kmerregion = {0, 0, 0};
+    int odd = 0;
+    get_region(g, 0, g->L - 1, g->cfg->min_len_inter_kmer, 0, FLAG_ZERO, 1, &kmerregion);
+    if (kmerregion.n > 0) {
+        merge_region(&kmerregion);
+        for (int i = 0; i < kmerregion.n; i += 2) create_insert(g, kmerregion.d[i], kmerregion.d[i + 1]);
+    }
+    ctg_layout(g);
+    if (kmerregion.n > 0) {
+        IList win = {0, 0, 0}, failed = {0, 0, 0};
+        split_region(g, &kmerregion, FLAG_ZERO, g->cfg->max_len_kmer, &win);
+        kmer_correct(g, &win, &failed, 1);
+        win.n = 0;
+        if (failed.n > 0) {
+            for (int i = 0; i < failed.n; i += 2) fts_split_region(g, failed.d[i], failed.d[i + 1], FLAG_ZERO, &win);
+            if (win.n & 1) odd = 1;
+            else {
+                for (int i = 0; i < win.n; i += 2) if (win.d[i] > win.d[i + 1]) odd = 1;
+                if (!odd) kmer_correct(g, &win, NULL, 0);
+            }
+        }
+        free(win.d); free(failed.d);
+    }
+    free(kmerregion.d);
+    if (odd) return -2;
+    return get_contig(g, 0, out, cap);
+}
+
 int np_oracle_run_contig(const np_shard_view* v, int contig, int task, const Configure* cfg,
                          uint8_t* out_seq, int64_t out_cap, int64_t* out_len)
 {
-    if (!v || contig < 0 || contig >= v->n_contigs || (task != 1 && task != 2)) return -1;
-    if (task == 2 && !v->qual) return -1;
+    if (!v || contig < 0 || contig >= v->n_contigs || (task != 1 && task != 2 && task != 4)) return -1;
+    if (task != 1 && !v->qual) return -1;
     Ctg g;
     ctg_init(&g, v, contig, cfg);
-    int64_t n = task == 1 ? run_score_chain(&g, out_seq, out_cap) : run_kmer_count(&g, out_seq, out_cap);
+    int64_t n = task == 1 ? run_score_chain(&g, out_seq, out_cap) : task == 2 ? run_kmer_count(&g, out_seq, out_cap) : run_snp_valid(&g, out_seq, out_cap);
+    if (n == -2) { ctg_free(&g); return -2; }
     ctg_free(&g);
     if (n < 0) return -1;
     *out_len = n;

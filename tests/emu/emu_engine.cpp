@@ -160,7 +160,7 @@ static int emu_run(const np_shard_view* v, int task, const Configure* cfg, uint8
     npe::RunStats st;
     npe::V2Stats vs; memset(&vs, 0, sizeof(vs));
     int err = task == 1 ? (variant == 2 ? npe::run_score_chain_v2(be, d, v->ctg_off, &st, &vs) : npe::run_score_chain(be, d, &st))
-                        : npe::run_kmer_count(be, d, &st);
+                        : npe::run_kmer_count(be, d, &st, task);
     if (err) return err > 0 ? -err : err;
     if (st.out_bytes > out_cap) return -1000;
     memcpy(out_seq, d.out, (size_t)st.out_bytes);

@@ -302,3 +302,75 @@ def test_gpu_edge_shapes(E, oracle, eng, kw):
     cfg = E.default_config(b"")
     for task in tasks(E):
         assert eng.polish(sh, task, cfg) == run_checker(oracle.np_oracle_run, sh, task, cfg), task
+
+
+# ---- task 4: snp_valid (snpvalid.c:3-35) -----------------------------------------------------------------------------
+def oracle_contigs(oracle, sh, task, cfg):
+    """Per-contig oracle run -> {name: bytes, or None where the reference's behaviour is undefined (odd cut-point list)}."""
+    import numpy as np
+    oracle.np_oracle_run_contig.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    out = {}
+    for c, n in enumerate(sh.names):
+        cap = int(sh.view.ctg_off[c + 1] - sh.view.ctg_off[c]) * 2 + 4096
+        buf, ln = np.zeros(cap, np.uint8), C.c_int64(0)
+        rc = oracle.np_oracle_run_contig(C.addressof(sh.view), c, task, C.cast(cfg, C.c_void_p), buf.ctypes.data, cap, C.byref(ln))
+        assert rc in (0, -2), rc
+        out[n] = buf[:ln.value].tobytes() if rc == 0 else None
+    return out
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_gpu_snp_valid_matches_oracle_and_reference_md5(E, oracle, eng, synth_files, case):
+    want_md5 = json.load(open(os.path.join(GOLDEN, "synth_md5.json")))[case]["4"]
+    fa, bam = synth_files(case)
+    sh = E.Shard.load(fa, bam, with_qual=True)
+    cfg = E.default_config(fa, bam)
+    got = eng.polish(sh, 4, cfg)
+    assert {"%s_4" % n: md5(s) for n, s in got.items()} == want_md5
+    want = oracle_contigs(oracle, sh, 4, cfg)
+    assert all(v is not None for v in want.values())
+    assert got == want
+
+
+@pytest.mark.parametrize("seed", [41, 42, 43, 44, 45, 46])
+def test_gpu_snp_valid_mutated_thresholds(E, oracle, eng, seed):
+    import random
+    rng = random.Random(seed)
+    kw = dict(seed=rng.randrange(1 << 30), n_contigs=rng.choice([2, 5]), contig_len=rng.choice([8000, 20000]),
+              depth=rng.choice([5, 12, 30, 60]), draft_indel=rng.choice([0.003, 0.02]), read_indel=rng.choice([0.0001, 0.003]),
+              lowercase_frac=rng.choice([0.01, 0.05, 0.15]))
+    sh = E.Shard.synthetic(E.synth_params(**kw), 0, kw["n_contigs"], with_qual=True)
+    cfg = E.default_config(b"")
+    c = cfg.contents
+    c.read_tlen = 2000
+    c.trim_len_edge, c.ext_len_edge = rng.choice([0, 1, 2, 4]), rng.choice([0, 1, 2, 3])
+    c.min_len_inter_kmer = rng.choice([0, 2, 5, 9])
+    c.max_len_kmer, c.max_count_kmer, c.min_map_quality = rng.choice([10, 50, 120]), rng.choice([3, 50]), rng.choice([0, 30])
+    want = oracle_contigs(oracle, sh, 4, cfg)
+    got = eng.polish(sh, 4, cfg)
+    checked = 0
+    for n, s in want.items():
+        if s is not None:                      # contigs with an odd cut-point list: undefined in the reference, not compared
+            assert got[n] == s, n
+            checked += 1
+    assert checked > 0
+
+
+def test_gpu_snp_valid_golden_testdata_engine_abi_and_cli(E, eng):
+    fa, bam = os.path.join(GOLDEN, "td30.step1.fa"), os.path.join(GOLDEN, "td30.step1.bam")
+    exp_path = os.path.join(GOLDEN, "td30.step1.snpvalid.expected.fa")
+    exp = read_fasta(exp_path)
+    sh = E.Shard.load(fa, bam, with_qual=True)
+    got = eng.polish(sh, 4, E.default_config(fa, bam))
+    assert {"%s_4" % n: s for n, s in got.items()} == exp
+    L = E.lib()                                   # the drop-in entry point: snp_valid(tigname, cfg) -> PolishResult*
+    cfg = L.config_init(fa.encode(), bam.encode(), None)
+    for name in [n[:-2] for n in exp]:
+        res = L.snp_valid(name.encode(), cfg)
+        seq = C.string_at(res.contents.contig)
+        assert res.contents.length == len(seq) and seq == exp["%s_4" % name]
+        L.polishresult_destory(res)
+    L.config_destory(cfg)
+    cli = os.path.join(os.path.dirname(E.binding.LIB_PATH), "nextpolish1")
+    ours = subprocess.run([cli, "snpvalid", fa, bam], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    assert ours == open(exp_path, "rb").read()
