@@ -296,6 +296,25 @@ int64_t   np_files_submit(np_files* p, int32_t task, const char* fasta, const ch
 int32_t   np_files_wait(np_files* p, int64_t ticket, np_files_result* out);
 
 
+/* ---- one input on several GPUs of one box: the contig list of ONE draft is cut into one contiguous block
+ * per GPU by cumulative length (the reference's driver cuts its worker jobs the same way: blc_genome,
+ * source/nextPolish:93-117, consumed by nextpolish1.py -b/-i:148-161); every GPU loads and polishes its block, and the
+ * polished bytes are gathered on the first GPU with the path's only collective (grouped ncclSend / ncclRecv, exact
+ * sizes), then downloaded once.  Single process, one host thread per GPU, ncclCommInitAll; NCCL is bound at run time.
+ * A draft larger than the shard budget (NEXTPOLISH_B200_SHARD_MBP million bases per GPU and round, default 256) is cut
+ * into n_devices x rounds blocks and polished round by round (one gather per round), so genome size is bounded by host
+ * memory for the result, not by one shard's 2^31 limits or by HBM.  In the result, load_ms = wall clock of all rounds
+ * and polish_ms = number of rounds.
+ * devices == NULL: GPUs 0 .. n_devices-1.  The result arrays (FASTA order) stay valid until the next np_multi_run. */
+typedef struct np_multi np_multi;
+np_multi* np_multi_create(const int32_t* devices, int32_t n_devices);
+int32_t   np_multi_run(np_multi* m, int32_t task, const char* fasta, const char* bam, const Configure* cfg, np_files_result* out);
+void      np_multi_destroy(np_multi* m);
+/* part[i] = block (0 .. n_parts-1) of contig i: contiguous blocks with balanced cumulative length */
+void      np_partition_contiguous(const int64_t* lengths, int32_t n_contigs, int32_t n_parts, int32_t* part);
+int32_t   np_engine_result_offsets(np_engine* e, int64_t* out_off);
+
+
 /* ---- seeded synthetic inputs (draft FASTA + coordinate-sorted BAM), for bench and tests -- */
 typedef struct {
     uint64_t seed;

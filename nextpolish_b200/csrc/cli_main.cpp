@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <unistd.h>
+#include <string>
 #include <vector>
 #include "../../include/nextpolish_b200.h"
 
@@ -44,6 +46,38 @@ int main(int argc, char* argv[]) {
     time_t t0 = time(nullptr);
     Configure* cfg = config_init(argv[2], argv[3], nullptr);
     const int dev = getenv("NEXTPOLISH_B200_DEVICE") ? atoi(getenv("NEXTPOLISH_B200_DEVICE")) : 0;
+    int gpus = getenv("NEXTPOLISH_B200_GPUS") ? atoi(getenv("NEXTPOLISH_B200_GPUS")) : 1;
+    if (gpus < 1) gpus = 1;
+    const char* hl0 = getenv("NEXTPOLISH_B200_HOST_LOAD");
+    std::string bai = std::string(argv[3]) + ".bai";
+    FILE* fb = fopen(bai.c_str(), "rb");
+    if (fb) fclose(fb);
+    if (fb && !(hl0 && hl0[0] == '1')) {
+        // the indexed-BAM path: contiguous contig blocks, as many rounds as keep a block under the shard budget (genomes
+        // larger than one shard are polished block by block, like the reference polishes contig by contig), one block per
+        // GPU and round, one NCCL gather per round when several GPUs are used (multi_gpu.cu)
+        const int32_t one[1] = {dev};
+        // stdout is the FASTA stream: whatever a library prints there while the GPUs work (NCCL's version banner) goes to stderr
+        fflush(stdout);
+        const int saved = dup(1);
+        dup2(2, 1);
+        np_multi* m = np_multi_create(gpus == 1 ? one : nullptr, gpus);
+        np_files_result r;
+        const bool ok = m && np_multi_run(m, step, argv[2], argv[3], cfg, &r) == NP_OK;
+        fflush(stdout);
+        dup2(saved, 1);
+        close(saved);
+        if (!ok) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
+        for (int i = 0; i < r.n_contigs; i++) {
+            printf(">%s_%d\n", r.names[i], step);
+            fwrite(r.seq + r.start[i], 1, (size_t)r.len[i], stdout);
+            fputc('\n', stdout);
+        }
+        np_multi_destroy(m);
+        config_destory(cfg);
+        fprintf(stderr, "total time:%lds\n", (long)(time(nullptr) - t0));
+        return 0;
+    }
     // the shard is built on the GPU (inflate + record unpack + packing, devload.cu) when the BAM has a .bai index;
     // otherwise (or with NEXTPOLISH_B200_HOST_LOAD=1) the host packer builds it and it is uploaded
     np_dev_shard* ds = nullptr;

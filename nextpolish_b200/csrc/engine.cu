@@ -696,6 +696,16 @@ int32_t np_engine_download(np_engine* e, uint8_t* out_seq, int64_t out_cap, int6
     return NP_OK;
 }
 
+// per-contig offsets of the last run's result (n_contigs + 1 entries), without the bytes
+int32_t np_engine_result_offsets(np_engine* e, int64_t* out_off) {
+    if (!e || !e->ran || !out_off) { np::set_error("np_engine_result_offsets: nothing to read"); return NP_ERR_ARG; }
+    cudaSetDevice(e->device);
+    cudaMemcpyAsync(out_off, e->d.out_off, ((size_t)e->d.n_ctg + 1) * 8, cudaMemcpyDeviceToHost, e->be.stream);
+    cudaError_t er = cudaStreamSynchronize(e->be.stream);
+    if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
+    return NP_OK;
+}
+
 // PolishPoint trace of the last run (only when cfg->trace_polish_open was set): count, and a download of the points
 // (contig-relative positions, contig order) with their per-contig offsets.
 int64_t np_engine_point_count(np_engine* e) { return e && e->ran ? e->d.n_pts : -1; }

@@ -224,6 +224,41 @@ class Stream:
             pass
 
 
+class MultiGpu:
+    """np_multi: ONE input (draft FASTA + BAM) polished on several GPUs of this box — contiguous contig blocks per GPU,
+    one NCCL gather of the polished bytes to the first GPU (csrc/multi_gpu.cu)."""
+
+    def __init__(self, n_gpus, devices=None):
+        arr = (C.c_int32 * n_gpus)(*devices) if devices else None
+        self.h = lib().np_multi_create(arr, n_gpus)
+        if not self.h:
+            raise NativeError(last_error())
+
+    def polish(self, task, fasta, bam, cfg):
+        """-> ({name: polished bytes} in FASTA order, stats dict)"""
+        from .binding import FilesResult
+        r = FilesResult()
+        rc = lib().np_multi_run(self.h, task, fasta.encode(), bam.encode(), cfg, C.byref(r))
+        if rc != 0:
+            raise NativeError("rc=%d: %s" % (rc, last_error()))
+        seqs = {r.names[i].decode(): C.string_at(r.seq + r.start[i], r.len[i]) for i in range(r.n_contigs)}
+        return seqs, {"h2d_bytes": r.h2d_bytes, "d2h_bytes": r.d2h_bytes, "wall_ms": r.load_ms, "rounds": int(r.polish_ms)}
+
+    def close(self):
+        if self.h:
+            lib().np_multi_destroy(self.h)
+            self.h = None
+
+
+def partition_contiguous(lengths, n_parts):
+    """np_partition_contiguous: block index of every contig (contiguous blocks, balanced cumulative length)."""
+    import numpy as np
+    a = np.asarray(lengths, np.int64)
+    out = np.zeros(len(a), np.int32)
+    lib().np_partition_contiguous(a.ctypes.data, len(a), n_parts, out.ctypes.data)
+    return out.tolist()
+
+
 class FilePipeline:
     """np_files: FASTA + BAM (+ .bai) files -> polished sequences on the host, `depth` jobs in flight (each slot = engine +
     host worker thread; load, upload, inflate and unpack of one job overlap the kernels of the other)."""

@@ -45,25 +45,18 @@ class FixedGather:
     (little-endian int64) and whose payload follows; rank `dst` slices afterwards.  `slots` rotating receive
     sets let a gather stay in flight while the next step is being computed.
 
-    On GPUs the collective is issued as ncclAllGather into one contiguous tensor (all_gather_into_tensor): a
-    single symmetric NCCL kernel whose host-side cost does not grow with the number of ranks on the root, unlike
-    gather's grouped send/recv list; the polished bytes are ~1 B per draft base, so the extra copies the other
-    ranks receive cost nothing next to NVLink bandwidth.  The CPU (gloo) test path uses dist.gather."""
+    A true gather (dist.gather: grouped ncclSend / ncclRecv on GPUs, gloo in the CPU tests): only rank `dst` receives —
+    N x (cap + HEADER) bytes per call — every other rank sends its own buffer once.  (Round 1 issued an all-gather, which
+    delivered all N buffers to every rank.)"""
     HEADER = 16
 
     def __init__(self, cap, device, dst=0, group=None, slots=1):
         self.cap, self.dst, self.group = cap, dst, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.allgather = torch.device(device).type == "cuda"
         root = self.rank == dst
         n = cap + self.HEADER
-        if self.allgather:
-            self.flat = [torch.empty(self.world * n, dtype=torch.uint8, device=device) for _ in range(slots)]
-            self.bufs = [[f[r * n:(r + 1) * n] for r in range(self.world)] for f in self.flat]
-        else:
-            self.flat = None
-            self.bufs = [[torch.empty(n, dtype=torch.uint8, device=device) for _ in range(self.world)]
-                         for _ in range(slots)] if root else None
+        self.bufs = [[torch.empty(n, dtype=torch.uint8, device=device) for _ in range(self.world)]
+                     for _ in range(slots)] if root else None
         self.last = 0
 
     def send_buffer(self, device):
@@ -78,8 +71,6 @@ class FixedGather:
     def __call__(self, buf, slot=0, async_op=False):
         """buf: uint8 tensor of cap + HEADER elements (header already filled)."""
         self.last = slot
-        if self.allgather:
-            return dist.all_gather_into_tensor(self.flat[slot], buf, group=self.group, async_op=async_op)
         return dist.gather(buf, self.bufs[slot] if self.bufs else None, dst=self.dst, group=self.group, async_op=async_op)
 
     def result(self, slot=None):

@@ -87,3 +87,18 @@ def test_worker_mirror_bookkeeping(tmp_path):
     fa = tmp_path / "g.fa"
     fa.write_text(">a desc\nAC\n>b\nGT\n")
     assert n1.read_block(str(fa), "all", set()) == ["a", "b"]
+
+
+def test_partition_contiguous_blocks_are_contiguous_and_balanced():
+    """np_partition_contiguous (csrc/multi_gpu.cu): what source/nextPolish:93-117 (blc_genome) does for the worker jobs."""
+    import random
+    from nextpolish_b200 import engine as E
+    rng = random.Random(5)
+    for n_parts in (1, 2, 4, 8):
+        for n in (1, 3, 8, 200, 1000):
+            lens = [int(20000 * (50 ** rng.random())) for _ in range(n)]
+            part = E.partition_contiguous(lens, n_parts)
+            assert part == sorted(part) and part[0] == 0 and max(part) < n_parts
+            if n >= 100:
+                loads = [sum(l for l, p in zip(lens, part) if p == b) for b in range(n_parts)]
+                assert max(loads) - min(loads) <= 2 * max(lens)

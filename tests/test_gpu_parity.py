@@ -374,3 +374,48 @@ def test_gpu_snp_valid_golden_testdata_engine_abi_and_cli(E, eng):
     cli = os.path.join(os.path.dirname(E.binding.LIB_PATH), "nextpolish1")
     ours = subprocess.run([cli, "snpvalid", fa, bam], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
     assert ours == open(exp_path, "rb").read()
+
+
+# ---- the reference's process model: config_init in the parent, Pool forked afterwards ----------------
+def _fork_worker(args):
+    """Child of a forked Pool: calls the drop-in entry point through ctypes like nextpolish1.py:181-189 does."""
+    fn, name = args
+    from nextpolish_b200 import engine as E
+    L = E.lib()
+    res = getattr(L, fn)(name.encode(), _FORK_CFG)
+    seq = C.string_at(res.contents.contig)
+    L.polishresult_destory(res)
+    return name, seq
+
+
+_FORK_CFG = None
+
+
+@pytest.mark.parametrize("step,fn", [(1, "score_chain"), (2, "kmer_count")])
+def test_forked_pool_after_config_init(E, step, fn):
+    """Exactly the reference's worker: config_init() in the parent, multiprocessing.Pool(2) forked AFTERWARDS,
+    score_chain / kmer_count called in the children, imap_unordered(chunksize=1) (nextpolish1.py:219-224).
+    The parent must not have touched CUDA before the fork (it has not: config_init is host code) and every child
+    creates its own engine lazily."""
+    import multiprocessing as mp
+    global _FORK_CFG
+    fa = os.path.join(GOLDEN, "td30.step%d.fa" % step)
+    bam = os.path.join(GOLDEN, "td30.step%d.bam" % step)
+    exp = read_fasta(os.path.join(GOLDEN, "td30.step%d.expected.fa" % step))
+    # a fresh interpreter: this test process already holds a CUDA context (other tests), which must not cross fork()
+    code = r"""
+import ctypes as C, multiprocessing as mp, sys, json, hashlib
+sys.path.insert(0, %r)
+import tests.test_gpu_parity as T
+from nextpolish_b200 import engine as E
+L = E.lib()
+T._FORK_CFG = L.config_init(%r.encode(), %r.encode(), None)
+names = %r
+with mp.get_context("fork").Pool(2) as pool:
+    out = dict(pool.imap_unordered(T._fork_worker, [(%r, n) for n in names], chunksize=1))
+print(json.dumps({k: hashlib.md5(v).hexdigest() for k, v in out.items()}))
+""" % (os.path.dirname(os.path.dirname(os.path.realpath(__file__))), fa, bam, [n[:-2] for n in exp], fn)
+    r = subprocess.run([os.sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    got = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    assert got == {n[:-2]: md5(s) for n, s in exp.items()}
