@@ -261,6 +261,9 @@ int32_t np_bgzf_inflate(int32_t device, const uint8_t* comp, int64_t comp_bytes,
 typedef struct np_dev_shard np_dev_shard;
 np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* bam, const char* const* names,
                                 int32_t n_names, int32_t with_qual);
+/* the same load for callers that already hold the draft in host memory: names[i] has the bases seq[i][0 .. len[i]) */
+np_dev_shard* np_shard_load_gpu_seqs(int32_t device, const char* bam, const char* const* names, const uint8_t* const* seq,
+                                     const int64_t* len, int32_t n_names, int32_t with_qual);
 void        np_dev_shard_view(const np_dev_shard* shard, np_shard_view* out);
 const char* np_dev_shard_contig_name(const np_dev_shard* shard, int32_t i);
 int32_t     np_dev_shard_contig_rank(const np_dev_shard* shard, int32_t i);

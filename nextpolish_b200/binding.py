@@ -74,7 +74,7 @@ EXPORTS = [  # every symbol include/nextpolish_b200.h declares
     "np_engine_result_device", "np_engine_copy_result", "np_engine_pack_result", "np_engine_kernel_times", "np_engine_set_timing", "np_engine_launch_count", "np_engine_window_stats", "np_engine_stream",
     "np_polish_host", "np_synth_write", "np_synth_shard",
     "np_engine_point_count", "np_engine_points",
-    "np_bgzf_inflate", "np_shard_load_gpu", "np_dev_shard_view", "np_dev_shard_contig_name", "np_dev_shard_contig_rank",
+    "np_bgzf_inflate", "np_shard_load_gpu", "np_shard_load_gpu_seqs", "np_dev_shard_view", "np_dev_shard_contig_name", "np_dev_shard_contig_rank",
     "np_dev_shard_stats", "np_dev_shard_download", "np_dev_shard_free",
     "np_stream_create", "np_stream_destroy", "np_stream_submit", "np_stream_wait", "np_stream_launch_count",
     "np_files_create", "np_files_destroy", "np_files_submit", "np_files_wait",

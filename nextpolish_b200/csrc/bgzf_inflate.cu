@@ -128,7 +128,7 @@ cudaMemPool_t thread_pool(int device) {
 // inflate_launch enqueues the copies and the kernel and returns; inflate_finish synchronises the stream and
 // checks every block's status.  Used by callers that keep the bytes in HBM (devload.cu) and overlap host work.
 int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_bytes, const std::vector<npz::Block>& blocks,
-                       uint8_t* d_out, cudaStream_t stream, std::string& err) {
+                       uint8_t* d_out, cudaStream_t stream, std::string& err, bool src_pinned) {
     j.nb = blocks.size(); j.stream = stream;
     if (j.nb == 0) return NP_OK;
     const size_t nb = j.nb;
@@ -142,7 +142,7 @@ int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_byte
     // and go up as one asynchronous DMA; the buffer is reused by the next job only after inflate_finish synchronised.
     static thread_local void* pinned = nullptr; static thread_local size_t pinned_bytes = 0;   // per host thread: loads may run concurrently
     const uint8_t* src = comp_host;
-    if (comp_bytes >= (4u << 20)) {
+    if (!src_pinned && comp_bytes >= (4u << 20)) {
         if (pinned_bytes < comp_bytes) {
             if (pinned) { cudaFreeHost(pinned); pinned = nullptr; pinned_bytes = 0; }
             size_t want = comp_bytes + comp_bytes / 4;

@@ -23,8 +23,10 @@ struct InflateJob {
 };
 // Enqueues the upload of the compressed bytes (block payload offsets are relative to comp_host) and the inflate
 // kernel on `stream`, output into d_out (device); returns without waiting.
+// src_pinned: comp_host lies in page-locked memory (e.g. a BAM mapping registered with cudaHostRegister): it is
+// uploaded by one asynchronous DMA as it is; otherwise larger ranges are first copied into a pinned staging buffer.
 int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_bytes, const std::vector<npz::Block>& blocks,
-                       uint8_t* d_out, cudaStream_t stream, std::string& err);
+                       uint8_t* d_out, cudaStream_t stream, std::string& err, bool src_pinned = false);
 // Synchronises the stream, releases the job's buffers and checks every block's status.
 int32_t inflate_finish(InflateJob& j, float* kernel_ms, std::string& err);
 

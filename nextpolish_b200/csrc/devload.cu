@@ -286,8 +286,25 @@ void np_dev_shard_free(np_dev_shard* s) {
     delete s;
 }
 
+static np_dev_shard* load_gpu_impl(int32_t device, const char* fasta, const char* bam, const char* const* names_in,
+                                   int32_t n_names, int32_t with_qual, const uint8_t* const* pre_seq, const int64_t* pre_len);
+
 np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* bam, const char* const* names_in,
                                 int32_t n_names, int32_t with_qual) {
+    return load_gpu_impl(device, fasta, bam, names_in, n_names, with_qual, nullptr, nullptr);
+}
+// The same load for callers that already hold the draft in host memory (np_multi parses the FASTA once for all GPUs):
+// names[i] has the bases seq[i][0 .. len[i]).
+np_dev_shard* np_shard_load_gpu_seqs(int32_t device, const char* bam, const char* const* names, const uint8_t* const* seq,
+                                     const int64_t* len, int32_t n_names, int32_t with_qual) {
+    if (!names || !seq || !len || n_names <= 0) { np::set_error("np_shard_load_gpu_seqs: bad arguments"); return nullptr; }
+    return load_gpu_impl(device, "", bam, names, n_names, with_qual, seq, len);
+}
+
+}  // extern "C"
+
+static np_dev_shard* load_gpu_impl(int32_t device, const char* fasta, const char* bam, const char* const* names_in,
+                                   int32_t n_names, int32_t with_qual, const uint8_t* const* pre_seq, const int64_t* pre_len) {
     using namespace np;
     if (!fasta || !bam) { set_error("np_shard_load_gpu: fasta / bam is NULL"); return nullptr; }
     int ndev = 0;
@@ -432,7 +449,7 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     // Whole-file loads parse straight into a grow-only pinned buffer of the calling thread (one copy, asynchronous upload);
     // named subsets go through fasta_load (seeks with the .fai).
     struct PinBuf { uint8_t* p = nullptr; size_t cap = 0; };
-    static thread_local PinBuf fa_pin;
+    static thread_local PinBuf fa_pin, fa_perm;      // parsed whole file; bases gathered in shard order
     std::vector<std::string> fa_names; std::vector<int64_t> fa_off;
     std::vector<FastaRecord> recs;
     const uint8_t* flat = nullptr;
@@ -449,6 +466,9 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
         // the previous upload out of this buffer has completed: every load ends with a stream synchronisation
         if (!fasta_load_flat(fasta, fa_names, fa_off, grow, &fa_pin, err)) return fail(err);
         flat = fa_pin.p;
+    } else if (pre_seq) {
+        fa_off.push_back(0);
+        for (int32_t i = 0; i < n_names; i++) { fa_names.push_back(names[(size_t)i]); fa_off.push_back(fa_off.back() + pre_len[i]); }
     } else {
         if (!fasta_load(fasta, names, recs, err)) return fail(err);
         fa_off.push_back(0);
@@ -465,7 +485,17 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     std::stable_sort(slots.begin(), slots.end(), [](const Slot& a, const Slot& b) { return a.tid < b.tid; });
     bool identity = flat != nullptr;
     for (size_t k = 0; k < slots.size() && identity; k++) identity = slots[k].rec_idx == k;
-    std::vector<uint8_t> ctg_perm;                        // only when the order changes or the records came from fasta_load
+    // (when the order changes, or the bases came from fasta_load / the caller: gathered into the thread's pinned buffer)
+    uint8_t* ctg_perm = nullptr; size_t perm_at = 0;
+    if (!identity) {
+        const size_t need = (size_t)fa_off.back() + 16;
+        if (fa_perm.cap < need) {
+            if (fa_perm.p) { cudaFreeHost(fa_perm.p); fa_perm.p = nullptr; fa_perm.cap = 0; }
+            if (cudaMallocHost((void**)&fa_perm.p, need + need / 4 + 4096) != cudaSuccess) { cudaGetLastError(); return fail("cudaMallocHost failed"); }
+            fa_perm.cap = need + need / 4 + 4096;
+        }
+        ctg_perm = fa_perm.p;
+    }
     std::vector<int32_t> slot_of_tid((size_t)std::max(1, n_ref), -1);
     S->ctg_off.push_back(0);
     for (size_t k = 0; k < slots.size(); k++) {
@@ -474,13 +504,14 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
         S->names.push_back(fa_names[ri]);
         S->fasta_rank.push_back((int32_t)ri);
         if (!identity) {
-            const uint8_t* src = flat ? flat + fa_off[ri] : (const uint8_t*)recs[ri].seq.data();
-            ctg_perm.insert(ctg_perm.end(), src, src + len);
+            const uint8_t* src = pre_seq ? pre_seq[ri] : flat ? flat + fa_off[ri] : (const uint8_t*)recs[ri].seq.data();
+            memcpy(ctg_perm + perm_at, src, len);
+            perm_at += len;
         }
         S->ctg_off.push_back(S->ctg_off.back() + (int64_t)len);
         if (slots[k].tid != 0x7fffffff && slot_of_tid[(size_t)slots[k].tid] < 0) slot_of_tid[(size_t)slots[k].tid] = (int32_t)k;
     }
-    const uint8_t* ctg_ptr = identity ? flat : ctg_perm.data();
+    const uint8_t* ctg_ptr = identity ? flat : ctg_perm;
     const size_t ctg_bytes = (size_t)S->ctg_off.back();
     const int32_t n_slots = (int32_t)slots.size();
     if (ctg_bytes >= 0x7fffff00ull) return fail("shard exceeds 2^31 positions: load it in several contig groups");
@@ -582,6 +613,8 @@ np_dev_shard* np_shard_load_gpu(int32_t device, const char* fasta, const char* b
     for (int32_t k = 0; k < n_slots; k++) S->ctg_read_off[(size_t)k + 1] = S->ctg_read_off[(size_t)k] + counts[(size_t)k];
     return S;
 }
+
+extern "C" {
 
 void np_dev_shard_view(const np_dev_shard* s, np_shard_view* v) {
     memset(v, 0, sizeof(*v));

@@ -111,8 +111,9 @@ void np_partition_contiguous(const int64_t* lengths, int32_t n_contigs, int32_t 
 
 // One round: GPU g loads and polishes block names_of[g] (empty: idle); the polished bytes of all GPUs are gathered on the
 // first GPU and downloaded to m->h_out + h_base.  Fills names / start / len (FASTA ranks) of the round's contigs.
-static int32_t multi_round(np_multi* m, int32_t task, const char* fasta, const char* bam, const Configure* cfg,
+static int32_t multi_round(np_multi* m, int32_t task, const char* bam, const Configure* cfg,
                            const std::vector<std::vector<const char*>>& names_of, const std::vector<std::vector<int32_t>>& rank_of,
+                           const uint8_t* flat, const std::vector<int64_t>& fa_off,
                            int64_t h_base, int64_t* h_used, int64_t* h2d_total) {
     const int n = (int)m->dev.size();
     const int wq = task == NP_TASK_KMER_COUNT ? 2 : task == NP_TASK_SNP_VALID ? 1 : 0;
@@ -123,7 +124,9 @@ static int32_t multi_round(np_multi* m, int32_t task, const char* fasta, const c
     auto work = [&](int g) {
         cudaSetDevice(m->dev[(size_t)g]);
         if (names_of[(size_t)g].empty()) return;
-        ds[(size_t)g] = np_shard_load_gpu(m->dev[(size_t)g], fasta, bam, names_of[(size_t)g].data(), (int32_t)names_of[(size_t)g].size(), wq);
+        std::vector<const uint8_t*> seqs; std::vector<int64_t> lens;      // the block's contigs inside the draft parsed once by np_multi_run
+        for (int32_t fr : rank_of[(size_t)g]) { seqs.push_back(flat + fa_off[(size_t)fr]); lens.push_back(fa_off[(size_t)fr + 1] - fa_off[(size_t)fr]); }
+        ds[(size_t)g] = np_shard_load_gpu_seqs(m->dev[(size_t)g], bam, names_of[(size_t)g].data(), seqs.data(), lens.data(), (int32_t)seqs.size(), wq);
         if (!ds[(size_t)g]) { rc[(size_t)g] = NP_ERR_IO; msg[(size_t)g] = np_last_error(); return; }
         np_shard_view v;
         np_dev_shard_view(ds[(size_t)g], &v);
@@ -218,8 +221,12 @@ int32_t np_multi_run(np_multi* m, int32_t task, const char* fasta, const char* b
     const int n = (int)m->dev.size();
     std::string err;
     // contigs in BAM reference order (those the BAM does not know last), as the loaders order them
-    std::vector<std::string> fa_names; std::vector<int64_t> fa_len;
-    if (!np::fasta_names(fasta, fa_names, fa_len, err)) { np::set_error("np_multi_run: " + err); return NP_ERR_IO; }
+    // the draft is read and parsed ONCE (one pass over an mmap of the file) and shared by every GPU's loader
+    std::vector<std::string> fa_names; std::vector<int64_t> fa_off, fa_len;
+    std::vector<uint8_t> draft;
+    auto grow = [](void* ctx, size_t bytes) -> uint8_t* { auto& v = *(std::vector<uint8_t>*)ctx; v.resize(bytes); return v.data(); };
+    if (!np::fasta_load_flat(fasta, fa_names, fa_off, grow, &draft, err)) { np::set_error("np_multi_run: " + err); return NP_ERR_IO; }
+    for (size_t i = 0; i + 1 < fa_off.size(); i++) fa_len.push_back(fa_off[i + 1] - fa_off[i]);
     np::BamFile bf;
     if (!bf.open(bam, err)) { np::set_error("np_multi_run: " + err); return NP_ERR_IO; }
     std::unordered_map<std::string, int> tid_of;
@@ -253,7 +260,7 @@ int32_t np_multi_run(np_multi* m, int32_t task, const char* fasta, const char* b
             rank_of[(size_t)(b % n)].push_back(order[(size_t)k]);
         }
         int64_t used = 0;
-        const int32_t rc = multi_round(m, task, fasta, bam, cfg, names_of, rank_of, h_base, &used, &h2d);
+        const int32_t rc = multi_round(m, task, bam, cfg, names_of, rank_of, draft.data(), fa_off, h_base, &used, &h2d);
         if (rc != NP_OK) return rc;
         h_base += used;
     }
