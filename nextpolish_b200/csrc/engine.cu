@@ -244,19 +244,33 @@ __global__ void __launch_bounds__(npc::TT) k_tile_agg(npe::Dev d, npc::ColGlobal
         g.tile_cov[w] = sa; g.tile_tbl[w] = sb; g.tile_str[w] = sc;
     }
 }
-// exclusive prefix of the tile aggregates, in place; [n_tiles] = totals (one CTA; warp w scans array w)
-__global__ void __launch_bounds__(96) k_tile_scan(npc::ColGlobals g) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int32_t* a = wid == 0 ? g.tile_cov : wid == 1 ? g.tile_tbl : g.tile_str;
-    int32_t carry = 0;
-    for (int32_t base = 0; base <= g.n_tiles; base += 32) {
-        const int32_t i = base + lane;
-        const int32_t v = i < g.n_tiles ? a[i] : 0;
-        int32_t inc = v;
+// exclusive prefix of the three tile aggregates, in place; [n_tiles] = totals.  One CTA: every thread owns a contiguous
+// segment of tiles (serial sum), the 1024 segment sums are scanned with warp shuffles, then every thread rewrites its segment.
+__global__ void __launch_bounds__(1024) k_tile_scan(npc::ColGlobals g) {
+    __shared__ int32_t s_w[3][32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int32_t n = g.n_tiles + 1, per = (n + 1023) / 1024;
+    const int32_t lo = tid * per < n ? tid * per : n, hi = lo + per < n ? lo + per : n;
+    int32_t* arr[3] = {g.tile_cov, g.tile_tbl, g.tile_str};
+    int32_t sum[3] = {0, 0, 0};
+    for (int32_t i = lo; i < hi; i++) if (i < g.n_tiles) { sum[0] += arr[0][i]; sum[1] += arr[1][i]; sum[2] += arr[2][i]; }
+    int32_t inc[3] = {sum[0], sum[1], sum[2]};
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
         #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (i <= g.n_tiles) a[i] = carry + inc - v;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
+        for (int k = 0; k < 3; k++) { const int32_t t = __shfl_up_sync(0xffffffffu, inc[k], o); if (lane >= o) inc[k] += t; }
+    if (lane == 31) { s_w[0][wid] = inc[0]; s_w[1][wid] = inc[1]; s_w[2][wid] = inc[2]; }
+    __syncthreads();
+    int32_t run[3];
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int32_t wpre = 0;
+        for (int i = 0; i < 32; i++) if (i < wid) wpre += s_w[k][i];
+        run[k] = wpre + inc[k] - sum[k];
+    }
+    for (int32_t i = lo; i < hi; i++) {
+        #pragma unroll
+        for (int k = 0; k < 3; k++) { const int32_t v = i < g.n_tiles ? arr[k][i] : 0; arr[k][i] = run[k]; run[k] += v; }
     }
 }
 __global__ void __launch_bounds__(npc::TT) k_col_pass(npe::Dev d, npc::ColGlobals g) {
@@ -444,7 +458,7 @@ struct CudaBackend {
         if (!ok || g.n_tiles <= 0) return;
         begin_timed("tile_agg");
         k_tile_agg<<<(unsigned)g.n_tiles, npc::TT, 0, stream>>>(d, g);
-        k_tile_scan<<<1, 96, 0, stream>>>(g);
+        k_tile_scan<<<1, 1024, 0, stream>>>(g);
         CUDA_TRY(cudaGetLastError());
         launches += 2;
         end_timed();
