@@ -14,6 +14,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -49,8 +52,42 @@ struct Nccl {
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace
 
+// One persistent host thread per GPU: the loader keeps per-thread state (stream, private memory pool, pinned staging
+// buffers), which must survive from one run to the next.
+struct GpuWorker {
+    std::thread th;
+    std::mutex mu; std::condition_variable cv;
+    std::function<void()> job; bool has_job = false, done = true, quit = false;
+    void loop() {
+        for (;;) {
+            std::function<void()> j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || has_job; });
+                if (quit) return;
+                j = std::move(job); has_job = false;
+            }
+            j();
+            { std::lock_guard<std::mutex> lk(mu); done = true; }
+            cv.notify_all();
+        }
+    }
+    void start() { th = std::thread([this] { loop(); }); }
+    void submit(std::function<void()> j) {
+        { std::lock_guard<std::mutex> lk(mu); job = std::move(j); has_job = true; done = false; }
+        cv.notify_all();
+    }
+    void wait() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done; }); }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+};
+
 struct np_multi {
     std::vector<int> dev;
+    std::vector<GpuWorker*> workers;
     std::vector<np_engine*> eng;
     std::vector<ncclComm_t> comm;
     Nccl nccl;
@@ -64,8 +101,16 @@ struct np_multi {
 
 extern "C" {
 
+// runs f(g) for every GPU on its own persistent thread and waits for all of them
+static void on_all_gpus(np_multi* m, const std::function<void(int)>& f) {
+    const int n = (int)m->workers.size();
+    for (int g = 0; g < n; g++) m->workers[(size_t)g]->submit([&f, g] { f(g); });
+    for (int g = 0; g < n; g++) m->workers[(size_t)g]->wait();
+}
+
 void np_multi_destroy(np_multi* m) {
     if (!m) return;
+    for (GpuWorker* w : m->workers) { w->stop(); delete w; }
     for (size_t i = 0; i < m->comm.size(); i++) if (m->comm[i]) m->nccl.CommDestroy(m->comm[i]);
     for (size_t i = 0; i < m->eng.size(); i++) if (m->eng[i]) np_engine_destroy(m->eng[i]);
     if (!m->dev.empty()) cudaSetDevice(m->dev[0]);
@@ -93,6 +138,7 @@ np_multi* np_multi_create(const int32_t* devices, int32_t n_devices) {
         if (!e) { np_multi_destroy(m); return nullptr; }
         m->eng.push_back(e);
     }
+    for (int i = 0; i < n_devices; i++) { GpuWorker* w = new GpuWorker(); m->workers.push_back(w); w->start(); }
     return m;
 }
 
@@ -142,12 +188,7 @@ static int32_t multi_round(np_multi* m, int32_t task, const char* bam, const Con
         }
         if (r != NP_OK) { rc[(size_t)g] = r; msg[(size_t)g] = np_last_error(); }
     };
-    {
-        std::vector<std::thread> th;
-        for (int g = 1; g < n; g++) th.emplace_back(work, g);
-        work(0);
-        for (auto& t : th) t.join();
-    }
+    on_all_gpus(m, work);
     auto cleanup = [&]() { for (int g = 0; g < n; g++) if (ds[(size_t)g]) { cudaSetDevice(m->dev[(size_t)g]); np_dev_shard_free(ds[(size_t)g]); } };
     for (int g = 0; g < n; g++) if (rc[(size_t)g] != NP_OK) { np::set_error("np_multi_run (GPU " + std::to_string(m->dev[(size_t)g]) + "): " + msg[(size_t)g]); cleanup(); return rc[(size_t)g]; }
 
@@ -189,12 +230,7 @@ static int32_t multi_round(np_multi* m, int32_t task, const char* bam, const Con
         }
         if (cudaStreamSynchronize(s) != cudaSuccess) nrc[(size_t)g] = ncclUnhandledCudaError;
     };
-    {
-        std::vector<std::thread> th;
-        for (int g = 1; g < n; g++) th.emplace_back(gather, g);
-        gather(0);
-        for (auto& t : th) t.join();
-    }
+    on_all_gpus(m, gather);
     for (int g = 0; g < n; g++) if (nrc[(size_t)g] != ncclSuccess) { np::set_error(std::string("np_multi_run: gather failed: ") + (n > 1 ? m->nccl.GetErrorString(nrc[(size_t)g]) : "CUDA error")); cleanup(); return NP_ERR_CUDA; }
     for (int g = 0; g < n; g++) {
         if (!ds[(size_t)g]) continue;
