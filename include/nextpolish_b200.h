@@ -299,15 +299,15 @@ int64_t   np_files_submit(np_files* p, int32_t task, const char* fasta, const ch
 int32_t   np_files_wait(np_files* p, int64_t ticket, np_files_result* out);
 
 
-/* ---- one input on several GPUs of one box: the contig list of ONE draft is cut into one contiguous block
- * per GPU by cumulative length (the reference's driver cuts its worker jobs the same way: blc_genome,
- * source/nextPolish:93-117, consumed by nextpolish1.py -b/-i:148-161); every GPU loads and polishes its block, and the
- * polished bytes are gathered on the first GPU with the path's only collective (grouped ncclSend / ncclRecv, exact
- * sizes), then downloaded once.  Single process, one host thread per GPU, ncclCommInitAll; NCCL is bound at run time.
- * A draft larger than the shard budget (NEXTPOLISH_B200_SHARD_MBP million bases per GPU and round, default 256) is cut
- * into n_devices x rounds blocks and polished round by round (one gather per round), so genome size is bounded by host
- * memory for the result, not by one shard's 2^31 limits or by HBM.  In the result, load_ms = wall clock of all rounds
- * and polish_ms = number of rounds.
+/* ---- one input on several GPUs of one box: the contig list of ONE draft is cut into contiguous blocks of
+ * balanced cumulative length (the reference's driver cuts its worker jobs the same way: blc_genome,
+ * source/nextPolish:93-117, consumed by nextpolish1.py -b/-i:148-161); every GPU owns a contiguous range of blocks and
+ * works through it with a few pipelined slots (NEXTPOLISH_B200_SLOTS, default 3: load / inflate of one block overlap the
+ * kernels of the others), appending the polished bytes to its result buffer in HBM; at the end the path's only collective
+ * gathers the result buffers on the first GPU (grouped ncclSend / ncclRecv, exact sizes) and they are downloaded once.
+ * A block never exceeds NEXTPOLISH_B200_BLOCK_MBP million draft bases (default 8), so genome size is bounded by the
+ * result buffers (1 B per base), not by one shard's 2^31 limits or by HBM.  Single process, ncclCommInitAll; NCCL is bound
+ * at run time.  In the result, load_ms = wall clock of parse + all blocks, polish_ms = gather + download.
  * devices == NULL: GPUs 0 .. n_devices-1.  The result arrays (FASTA order) stay valid until the next np_multi_run. */
 typedef struct np_multi np_multi;
 np_multi* np_multi_create(const int32_t* devices, int32_t n_devices);

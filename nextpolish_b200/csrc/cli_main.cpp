@@ -53,9 +53,9 @@ int main(int argc, char* argv[]) {
     FILE* fb = fopen(bai.c_str(), "rb");
     if (fb) fclose(fb);
     if (fb && !(hl0 && hl0[0] == '1')) {
-        // the indexed-BAM path: contiguous contig blocks, as many rounds as keep a block under the shard budget (genomes
-        // larger than one shard are polished block by block, like the reference polishes contig by contig), one block per
-        // GPU and round, one NCCL gather per round when several GPUs are used (multi_gpu.cu)
+        // the indexed-BAM path: contiguous contig blocks under the block budget (genomes larger than one shard are polished
+        // block by block, like the reference polishes contig by contig), pipelined slots per GPU, one NCCL gather at the
+        // end when several GPUs are used (multi_gpu.cu)
         const int32_t one[1] = {dev};
         // stdout is the FASTA stream: whatever a library prints there while the GPUs work (NCCL's version banner) goes to stderr
         fflush(stdout);

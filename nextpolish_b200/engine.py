@@ -225,8 +225,8 @@ class Stream:
 
 
 class MultiGpu:
-    """np_multi: ONE input (draft FASTA + BAM) polished on several GPUs of this box — contiguous contig blocks per GPU,
-    one NCCL gather of the polished bytes to the first GPU (csrc/multi_gpu.cu)."""
+    """np_multi: ONE input (draft FASTA + BAM) polished on several GPUs of this box — contiguous contig blocks, a few
+    pipelined slots per GPU, one NCCL gather of the polished bytes to the first GPU at the end (csrc/multi_gpu.cu)."""
 
     def __init__(self, n_gpus, devices=None):
         arr = (C.c_int32 * n_gpus)(*devices) if devices else None
@@ -242,7 +242,7 @@ class MultiGpu:
         if rc != 0:
             raise NativeError("rc=%d: %s" % (rc, last_error()))
         seqs = {r.names[i].decode(): C.string_at(r.seq + r.start[i], r.len[i]) for i in range(r.n_contigs)}
-        return seqs, {"h2d_bytes": r.h2d_bytes, "d2h_bytes": r.d2h_bytes, "wall_ms": r.load_ms, "rounds": int(r.polish_ms)}
+        return seqs, {"h2d_bytes": r.h2d_bytes, "d2h_bytes": r.d2h_bytes, "blocks_ms": r.load_ms, "gather_download_ms": r.polish_ms}
 
     def close(self):
         if self.h:

@@ -57,37 +57,41 @@ def main():
     ngpu = torch.cuda.device_count()
     md5_by_n = {}
     res["runs"] = []
-    for n in [g for g in (1, 2, 4, 8) if g <= ngpu]:
-        m = E.MultiGpu(n)
-        for t in tasks:
-            m.polish(t, files[t][0], files[t][1], cfg)                  # warm-up (memory pools, pinned buffers)
-        for t in tasks:
-            best, out, st = 1e9, None, None
-            for _ in range(2):
-                t1 = time.time()
-                out, st = m.polish(t, files[t][0], files[t][1], cfg)
-                best = min(best, time.time() - t1)
-            lens = lens_of[t]
-            md5 = hashlib.md5(b"".join(out[k] for k in sorted(out))).hexdigest()
-            md5_by_n.setdefault(t, {})[n] = md5
-            res["runs"].append({"n_gpus": n, "task": t, "wall_ms": best * 1e3, "Mbp_per_s": bp / best / 1e6, "rounds": st["rounds"],
-                                "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"], "md5": md5})
-            if n == 1:
-                keep = out
-                # size-independent properties + a bit-exact sample against the oracle (the five shortest contigs)
-                assert set(out) == set(lens) and all(abs(len(out[k]) - lens[k]) <= 0.02 * lens[k] + 50 for k in lens)
-                O = C.CDLL(os.path.join(ROOT, "oracle", "libnp_oracle.so"))
-                O.np_oracle_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
-                names = sorted(lens, key=lambda k: lens[k])[:5]
-                sh = E.Shard.load(files[t][0], files[t][1], names=names, with_qual=True)
-                cap = int(sh.total_bases * 2) + 4096
-                buf = np.zeros(cap, np.uint8); off = np.zeros(sh.n_contigs + 1, np.int64)
-                assert O.np_oracle_run(C.addressof(sh.view), t, C.cast(cfg, C.c_void_p), buf.ctypes.data, cap, off.ctypes.data) == 0
-                raw = buf.tobytes()
-                for i, nm in enumerate(sh.names):
-                    assert keep[nm] == raw[off[i]:off[i + 1]], (t, nm)
-                res.setdefault("oracle_sample_ok", {})[str(t)] = len(names)
-        m.close()
+    block_sizes = [x for x in os.environ.get("C3_BLOCK_MBP", "").split(",") if x]      # tuning: block budgets to try
+    for blk in (block_sizes or [None]):
+        if blk:
+            os.environ["NEXTPOLISH_B200_BLOCK_MBP"] = blk
+        for n in [g for g in (1, 2, 4, 8) if g <= ngpu]:
+          m = E.MultiGpu(n)
+          for t in tasks:
+              m.polish(t, files[t][0], files[t][1], cfg)                  # warm-up (memory pools, pinned buffers)
+          for t in tasks:
+              best, out, st = 1e9, None, None
+              for _ in range(2):
+                  t1 = time.time()
+                  out, st = m.polish(t, files[t][0], files[t][1], cfg)
+                  best = min(best, time.time() - t1)
+              lens = lens_of[t]
+              md5 = hashlib.md5(b"".join(out[k] for k in sorted(out))).hexdigest()
+              md5_by_n.setdefault(t, {})[n] = md5
+              res["runs"].append({"block_mbp": blk, "n_gpus": n, "task": t, "wall_ms": best * 1e3, "Mbp_per_s": bp / best / 1e6, "blocks_ms": st["blocks_ms"], "gather_download_ms": st["gather_download_ms"],
+                                  "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"], "md5": md5})
+              if n == 1:
+                  keep = out
+                  # size-independent properties + a bit-exact sample against the oracle (the five shortest contigs)
+                  assert set(out) == set(lens) and all(abs(len(out[k]) - lens[k]) <= 0.02 * lens[k] + 50 for k in lens)
+                  O = C.CDLL(os.path.join(ROOT, "oracle", "libnp_oracle.so"))
+                  O.np_oracle_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+                  names = sorted(lens, key=lambda k: lens[k])[:5]
+                  sh = E.Shard.load(files[t][0], files[t][1], names=names, with_qual=True)
+                  cap = int(sh.total_bases * 2) + 4096
+                  buf = np.zeros(cap, np.uint8); off = np.zeros(sh.n_contigs + 1, np.int64)
+                  assert O.np_oracle_run(C.addressof(sh.view), t, C.cast(cfg, C.c_void_p), buf.ctypes.data, cap, off.ctypes.data) == 0
+                  raw = buf.tobytes()
+                  for i, nm in enumerate(sh.names):
+                      assert keep[nm] == raw[off[i]:off[i + 1]], (t, nm)
+                  res.setdefault("oracle_sample_ok", {})[str(t)] = len(names)
+          m.close()
     res["same_bytes_on_every_gpu_count"] = all(len(set(v.values())) == 1 for v in md5_by_n.values())
     free, tot = torch.cuda.mem_get_info(0)
     res["hbm_used_gb_dev0_after"] = (tot - free) / 1e9
