@@ -440,7 +440,7 @@ struct CudaBackend {
     const int32_t* upload_i32(const char* name, const int32_t* h, size_t n) {
         int32_t* p = buf<int32_t>(name, n + 1);
         if (ok && n) {
-            // staged through a pinned bounce buffer so the async copy is legal for pageable vectors
+            // pageable source: the copy is followed by a synchronisation so that the caller's vector may go out of scope
             CUDA_TRY(cudaMemcpyAsync(p, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
         }
@@ -952,6 +952,16 @@ static PolishResult* run_one_contig(const char* tigname, Configure* cfg, int tas
     }
     PolishResult* res = polishresult_init();
     if (rc == NP_OK) rc = np_engine_run(e, task, cfg);
+    if (rc == NP_ERR_LIMIT && wq == 2 && strstr(np_last_error(), "0x40")) {
+        // a window candidate without qualities: the sparse quality stream (only reads that overlap a lowercase draft base)
+        // was not enough for this contig — load every read's qualities and run again
+        if (ds) { np_dev_shard_free(ds); ds = nullptr; }
+        std::vector<std::string> nm{std::string(tigname)};
+        if (!np::shard_load(cfg->fastafn, cfg->bamfn ? cfg->bamfn : "", nm, 1, 4, sh, err)) { fprintf(stderr, "nextpolish_b200: %s\n", err.c_str()); exit(1); }
+        sh.view(&v);
+        rc = np_engine_upload(e, &v);
+        if (rc == NP_OK) rc = np_engine_run(e, task, cfg);
+    }
     if (rc != NP_OK) { fprintf(stderr, "nextpolish_b200: %s\n", np_last_error()); exit(1); }
     int64_t cap = np_engine_result_bytes(e) + 1;
     res->contig = (char*)calloc(1, (size_t)cap + 1);

@@ -154,6 +154,7 @@ bool fasta_load(const std::string& path, const std::vector<std::string>& names,
         for (size_t i = 0; i < fai.size(); i++) idx.emplace(fai[i].name, i);
         FILE* f = fopen(path.c_str(), "rb");
         if (!f) { err = "cannot open " + path; return false; }
+        bool stale = false;
         for (auto& nm : names) {
             auto it = idx.find(nm);
             if (it == idx.end()) { fclose(f); err = "contig " + nm + " not in " + path + ".fai"; return false; }
@@ -170,10 +171,14 @@ bool fasta_load(const std::string& path, const std::vector<std::string>& names,
                 if (raw[k] == '>') break;
                 if (isgraph((unsigned char)raw[k])) r.seq.push_back(raw[k]);
             }
+            // a stale or foreign .fai (or a short read) yields a truncated / shifted record: htslib fails the fetch; here the
+            // index is distrusted and the whole file is parsed instead
+            if ((int64_t)r.seq.size() != e.len) { stale = true; break; }
             out.push_back(std::move(r));
         }
         fclose(f);
-        return true;
+        if (!stale) return true;
+        out.clear();
     }
     std::string text;
     if (!read_file(path, text, err)) return false;
