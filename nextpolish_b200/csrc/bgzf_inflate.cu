@@ -39,7 +39,9 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kDecoders = 1;       // blocks decoded in lockstep by one warp (lanes 0 .. kDecoders-1).  Measured on B200 (52 MB BAM,
                                    // 4225 blocks): 1 decoder x 8 warps 4.3 ms, 2 x 4 warps 5.3 ms, 4 x 2 warps 7.8 ms — with only
                                    // ~29 blocks per SM the kernel runs at the latency of one block, and the batches of a warp's
-                                   // blocks are resolved one after the other
+                                   // blocks are resolved one after the other.  One decoder per LANE (32 blocks per warp in lockstep,
+                                   // each lane resolving its own batch, 2.4 KB of tables per lane) was correct but ran at 27.5 ms:
+                                   // per-lane byte copies through L2 put every block's round at ~90 us
 
 // Persistent warps; every decoder lane pulls BGZF blocks from an atomic ticket.  One round of a warp: decoders that need
 // one parse their deflate block header, all decoders decode a batch of symbols in lockstep, then the warp resolves the
