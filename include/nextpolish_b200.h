@@ -213,6 +213,7 @@ int32_t np_engine_kernel_times(np_engine* e, const char** names, float* ms, int3
 void    np_engine_set_timing(np_engine* e, int32_t on);
 /* Number of kernel launches issued by the last np_engine_run. */
 int32_t np_engine_launch_count(np_engine* e);
+int64_t np_engine_launch_total(np_engine* e);      /* kernel launches of every successful run of this engine */
 /* Fused pileup-scan kernel statistics of the last task-1 run:
  * {window size W, windows, shared-memory bytes per CTA, windows with unresolved stretches,
  *  columns handled by the general (global-memory) kernels}. */
@@ -238,6 +239,20 @@ int64_t    np_stream_submit(np_stream* s, int32_t task, const np_shard_view* hos
                             uint8_t* out_seq, int64_t out_cap, int64_t* out_off);
 int32_t    np_stream_wait(np_stream* s, int64_t ticket);
 int64_t    np_stream_launch_count(np_stream* s);   /* kernel launches of every finished job */
+
+/* Shards that already sit in HBM, polished by `slots` engines at once (resident_slots.cu): contigs are the reference's
+ * parallel unit (one worker process per contig, nextpolish1.py:219-224), so shards are independent and a slot — engine,
+ * stream, scratch, host thread — per job in flight fills the GPU that one chain of short kernels leaves idle.
+ * np_resident_submit gives the job to slot `ticket % slots` (which must be free: wait for ticket - slots first) and
+ * returns; the result lands in dst_device in the gather form of np_engine_pack_result (16-byte header holding the byte
+ * count, then the polished bytes).  dev_shard's arrays must stay valid until np_resident_wait(ticket) returned. */
+typedef struct np_resident np_resident;
+np_resident* np_resident_create(int32_t device, int32_t slots);
+void         np_resident_destroy(np_resident* p);
+int64_t      np_resident_submit(np_resident* p, int32_t task, const np_shard_view* dev_shard, const Configure* cfg,
+                                void* dst_device, int64_t dst_cap);
+int32_t      np_resident_wait(np_resident* p, int64_t ticket, int64_t* out_bytes);
+int64_t      np_resident_launch_count(np_resident* p);   /* kernel launches of every job so far */
 
 
 /* ---- GPU inflate of BGZF (replaces htslib bgzf.c -> zlib inflate on the host, the step

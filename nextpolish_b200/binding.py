@@ -78,6 +78,7 @@ EXPORTS = [  # every symbol include/nextpolish_b200.h declares
     "np_dev_shard_stats", "np_dev_shard_download", "np_dev_shard_free",
     "np_stream_create", "np_stream_destroy", "np_stream_submit", "np_stream_wait", "np_stream_launch_count",
     "np_files_create", "np_files_destroy", "np_files_submit", "np_files_wait",
+    "np_resident_create", "np_resident_destroy", "np_resident_submit", "np_resident_wait", "np_resident_launch_count", "np_engine_launch_total",
     "np_multi_create", "np_multi_run", "np_multi_destroy", "np_partition_contiguous", "np_engine_result_offsets",
 ]
 
@@ -161,6 +162,17 @@ def load(path=None):
     L.np_files_submit.argtypes = [vp, i32, C.c_char_p, C.c_char_p, C.POINTER(Configure)]
     L.np_files_submit.restype = i64
     L.np_files_wait.argtypes = [vp, i64, C.POINTER(FilesResult)]
+    L.np_resident_create.argtypes = [i32, i32]
+    L.np_resident_create.restype = vp
+    L.np_resident_destroy.argtypes = [vp]
+    L.np_resident_destroy.restype = None
+    L.np_resident_submit.restype = i64
+    L.np_resident_submit.argtypes = [vp, i32, C.POINTER(ShardView), C.POINTER(Configure), vp, i64]
+    L.np_resident_wait.argtypes = [vp, i64, C.POINTER(i64)]
+    L.np_resident_launch_count.argtypes = [vp]
+    L.np_resident_launch_count.restype = i64
+    L.np_engine_launch_total.argtypes = [vp]
+    L.np_engine_launch_total.restype = i64
     L.np_multi_create.argtypes = [vp, i32]
     L.np_multi_create.restype = vp
     L.np_multi_run.argtypes = [vp, i32, C.c_char_p, C.c_char_p, C.POINTER(Configure), C.POINTER(FilesResult)]

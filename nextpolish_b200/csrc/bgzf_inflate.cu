@@ -35,8 +35,7 @@ struct WarpBackend {
     __device__ __forceinline__ int32_t shfl(int32_t v, int32_t src) const { return __shfl_sync(0xffffffffu, v, src); }
 };
 
-constexpr int kWarpsPerCta = 8;
-constexpr int kDecoders = 1;       // blocks decoded in lockstep by one warp (lanes 0 .. kDecoders-1).  Measured on B200 (52 MB BAM,
+// kDecoders: blocks decoded in lockstep by one warp (lanes 0 .. kDecoders-1).  Measured on B200 (52 MB BAM,
                                    // 4225 blocks): 1 decoder x 8 warps 4.3 ms, 2 x 4 warps 5.3 ms, 4 x 2 warps 7.8 ms — with only
                                    // ~29 blocks per SM the kernel runs at the latency of one block, and the batches of a warp's
                                    // blocks are resolved one after the other.  One decoder per LANE (32 blocks per warp in lockstep,
@@ -46,14 +45,14 @@ constexpr int kDecoders = 1;       // blocks decoded in lockstep by one warp (la
 // Persistent warps; every decoder lane pulls BGZF blocks from an atomic ticket.  One round of a warp: decoders that need
 // one parse their deflate block header, all decoders decode a batch of symbols in lockstep, then the warp resolves the
 // batches one block after the other.
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_bgzf_inflate(const uint8_t* comp, const npz::Block* blocks, int32_t n_blocks,
-                                                                  uint8_t* out, int32_t* status, int32_t* ticket) {
+template <int kDecoders, int kWarpsPerCta, int kMinCtas>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtas) k_bgzf_inflate(const uint8_t* comp, const npz::Block* blocks, int32_t n_blocks,
+                                                                         uint8_t* out, int32_t* status, int32_t* ticket) {
     __shared__ npz::Tables tabs[kWarpsPerCta][kDecoders];
     const int wid = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
     WarpBackend w;
     const bool dec = lane < kDecoders;
     npz::Tables& mine = tabs[wid][dec ? lane : 0];
-    for (int k = 0; k < kDecoders; k++) npz::init_tables(tabs[wid][k], w);
     npz::Decoder d;
     d.phase = npz::PH_IDLE; d.err = npz::OK; d.pos = 0; d.out = nullptr; d.out_len = 0;
     int32_t blk = -1;
@@ -88,6 +87,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_bgzf_inflate(const uin
             if (lane == k) { if (np < 0) { d.err = -np; d.phase = npz::PH_DONE; } else d.pos = np; }
         }
     }
+}
+
+// decoders per warp: NEXTPOLISH_B200_INFLATE_DECODERS = 1 (default), 2 or 4
+static int inflate_decoders() {
+    static int k = [] { const char* e = getenv("NEXTPOLISH_B200_INFLATE_DECODERS"); const int v = e ? atoi(e) : 1; return v == 2 || v == 4 ? v : 1; }();
+    return k;
+}
+static void launch_inflate(const uint8_t* comp, const npz::Block* blocks, int32_t nb, uint8_t* out, int32_t* status, int32_t* ticket,
+                           int sms, cudaStream_t stream) {
+    const int k = inflate_decoders();
+    const int per_cta = k == 1 ? 8 : k == 2 ? 8 : 8;                 // blocks in flight per CTA: decoders x warps
+    int ctas = (nb + per_cta - 1) / per_cta;
+    if (ctas > sms * 4) ctas = sms * 4;                               // persistent warps pull blocks from the ticket
+    if (k == 1) k_bgzf_inflate<1, 8, 4><<<ctas, 8 * 32, 0, stream>>>(comp, blocks, nb, out, status, ticket);
+    else if (k == 2) k_bgzf_inflate<2, 4, 4><<<ctas, 4 * 32, 0, stream>>>(comp, blocks, nb, out, status, ticket);
+    else k_bgzf_inflate<4, 2, 4><<<ctas, 2 * 32, 0, stream>>>(comp, blocks, nb, out, status, ticket);
 }
 
 struct InflateCtx {     // buffers kept across calls (per process)
@@ -172,12 +187,9 @@ int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_byte
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int ctas = (int)((nb + kWarpsPerCta * kDecoders - 1) / (kWarpsPerCta * kDecoders));
-    if (ctas > sms * 4) ctas = sms * 4;
     cudaEventCreate(&j.e0); cudaEventCreate(&j.e1);
     cudaEventRecord(j.e0, stream);
-    k_bgzf_inflate<<<ctas, kWarpsPerCta * 32, 0, stream>>>((const uint8_t*)j.d_comp, (const npz::Block*)j.d_blocks, (int32_t)nb, d_out,
-                                                          (int32_t*)j.d_status, (int32_t*)j.d_status + nb);
+    launch_inflate((const uint8_t*)j.d_comp, (const npz::Block*)j.d_blocks, (int32_t)nb, d_out, (int32_t*)j.d_status, (int32_t*)j.d_status + nb, sms, stream);
     cudaEventRecord(j.e1, stream);
     return NP_OK;
 }
@@ -237,11 +249,8 @@ int32_t np_bgzf_inflate(int32_t device, const uint8_t* comp, int64_t comp_bytes,
     cudaMemsetAsync((int32_t*)c.d_status + nb, 0, 4, c.stream);          // ticket counter
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    int ctas = (int)((nb + kWarpsPerCta * kDecoders - 1) / (kWarpsPerCta * kDecoders));
-    if (ctas > sms * 4) ctas = sms * 4;                                   // persistent warps pull blocks from the ticket
     cudaEventRecord(c.e0, c.stream);
-    k_bgzf_inflate<<<ctas, kWarpsPerCta * 32, 0, c.stream>>>((const uint8_t*)c.d_comp, (const npz::Block*)c.d_blocks, (int32_t)nb,
-                                                            (uint8_t*)c.d_out, (int32_t*)c.d_status, (int32_t*)c.d_status + nb);
+    launch_inflate((const uint8_t*)c.d_comp, (const npz::Block*)c.d_blocks, (int32_t)nb, (uint8_t*)c.d_out, (int32_t*)c.d_status, (int32_t*)c.d_status + nb, sms, c.stream);
     cudaEventRecord(c.e1, c.stream);
     std::vector<int32_t> st(nb);
     cudaMemcpyAsync(st.data(), c.d_status, nb * 4, cudaMemcpyDeviceToHost, c.stream);

@@ -15,8 +15,9 @@
 // symbol is decoded — put one L2 round trip per symbol on the critical path.
 // Code tables live in shared memory, one small region per warp:
 //   literal/length and distance symbols ordered by code (canonical Huffman, RFC 1951 3.2.2), code-length
-//   histograms, and a 10-bit lookup table for literal/length codes (one shared-memory load decodes the
-//   common symbols; longer codes fall back to the canonical walk).
+//   histograms, and lookup tables indexed by the next 10 (literal/length) / 8 (distance) stream bits whose 32-bit
+//   entries carry code length, extra-bit count and base value (one shared-memory load per code; longer codes
+//   fall back to the canonical walk).
 //
 // The decoder is NP_HD code over a warp backend (lane id, broadcast, barrier) so that tests/emu can run
 // it on the CPU with a 1-lane backend and compare with zlib; the product compiles it into
@@ -39,16 +40,25 @@ struct Block {             // one BGZF block: where its raw deflate payload live
 
 enum { MAXBITS = 15, MAXL = 288, MAXD = 30, FASTBITS = 10, DFASTBITS = 8, BATCH = 32 };
 
-struct Tables {            // per-warp shared memory (4.3 KB)
+// Lookup-table entries (literal/length and distance alike), one 32-bit word:
+//   bits 0-3   code length in bits (0: the code is longer than the table's index — canonical walk)
+//   bits 4-7   number of extra bits that follow the code (RFC 1951 3.2.5)
+//   bits 8-9   kind: literal / length (for the distance table: distance) / end of block / invalid symbol
+//   bits 16-31 literal byte, base length or base distance
+// so that one shared-memory load yields everything a symbol needs and code + extra bits leave the bit buffer together.
+enum { K_LIT = 0, K_BASE = 1, K_END = 2, K_BAD = 3 };
+
+struct Tables {            // per-warp shared memory (5.9 KB)
     uint32_t batch[BATCH];                 // decoded symbols: literal = 0x8000 | byte; match = length | distance << 16
-    uint32_t lenx[32], distx[32];          // RFC 1951 3.2.5: base | extra bits << 16 of length symbol 257+i / distance symbol i
-    int32_t lfirst, lindex, dfirst, dindex; // state of the canonical walk after FASTBITS / DFASTBITS steps (decode_slow resumes there)
+    int32_t lfirst, lindex, dfirst, dindex; // state of the canonical walk after FASTBITS / DFASTBITS steps (the slow path resumes there)
     uint16_t lcount[MAXBITS + 1], lsym[MAXL];
     uint16_t dcount[MAXBITS + 1], dsym[MAXD + 2];
-    uint16_t fast[1 << FASTBITS];          // literal/length: symbol << 4 | code length (0: not in the table)
-    uint16_t dfast[1 << DFASTBITS];        // distance: likewise
-    uint16_t lens[MAXL + MAXD + 2];        // scratch: code lengths while a dynamic header is read
+    uint32_t fast[1 << FASTBITS];          // literal/length entries by the next FASTBITS stream bits
+    uint32_t dfast[1 << DFASTBITS];        // distance entries by the next DFASTBITS stream bits
+    // scratch while a block header is read (code lengths of both alphabets): the lookup table is built afterwards
+    NP_HD uint16_t* lens() { return (uint16_t*)fast; }
 };
+static_assert((MAXL + MAXD + 2) * 2 <= (1 << FASTBITS) * 4, "the code-length scratch borrows the lookup table");
 
 struct Bits {              // LSB-first bit reader over the compressed bytes (lane 0 only)
     const uint8_t* p; const uint8_t* end;
@@ -97,14 +107,33 @@ NP_HD uint32_t rev_bits(uint32_t v, int n) {     // reverse the low n bits
     return r;
 #endif
 }
+// RFC 1951 3.2.5 in closed form: lengths 3,4,..,10, 11,13,15,17, 19,23,27,31, ... 227, 258; distances 1,2,3,4, 5,7, 9,13, ... 24577
+NP_HD int32_t len_base(int s) {     // s = symbol - 257
+    if (s < 8) return 3 + s;
+    if (s == 28) return 258;
+    return ((4 + (s & 3)) << ((s >> 2) - 1)) + 3;
+}
+NP_HD int32_t len_extra(int s) { return s < 8 || s == 28 ? 0 : (s - 4) >> 2; }
+NP_HD int32_t dist_base(int s) { return s < 4 ? s + 1 : ((2 + (s & 1)) << ((s >> 1) - 1)) + 1; }
+NP_HD int32_t dist_extra(int s) { return s < 4 ? 0 : (s >> 1) - 1; }
+NP_HD uint32_t lit_entry(int sym, int l) {      // literal/length symbol with an l-bit code
+    if (sym < 256) return (uint32_t)sym << 16 | (uint32_t)K_LIT << 8 | (uint32_t)l;
+    if (sym == 256) return (uint32_t)K_END << 8 | (uint32_t)l;
+    if (sym >= 286) return (uint32_t)K_BAD << 8 | (uint32_t)l;
+    return (uint32_t)len_base(sym - 257) << 16 | (uint32_t)K_BASE << 8 | (uint32_t)len_extra(sym - 257) << 4 | (uint32_t)l;
+}
+NP_HD uint32_t dist_entry(int sym, int l) {
+    if (sym >= MAXD) return (uint32_t)K_BAD << 8 | (uint32_t)l;
+    return (uint32_t)dist_base(sym) << 16 | (uint32_t)K_BASE << 8 | (uint32_t)dist_extra(sym) << 4 | (uint32_t)l;
+}
 // lookup table of the codes of up to `bits` bits: index = next `bits` stream bits (LSB first)
-NP_HD void build_fast(uint16_t* fast, int bits, const uint16_t* count, const uint16_t* sym) {
+NP_HD void build_fast(uint32_t* fast, int bits, const uint16_t* count, const uint16_t* sym, bool dist) {
     for (int i = 0; i < (1 << bits); i++) fast[i] = 0;
     uint32_t code = 0; int idx = 0;
     for (int l = 1; l <= bits; l++) {
         for (int k = 0; k < count[l]; k++, idx++, code++) {
             uint32_t r = rev_bits(code, l);
-            uint16_t e = (uint16_t)((uint32_t)sym[idx] << 4 | (uint32_t)l);
+            const uint32_t e = dist ? dist_entry(sym[idx], l) : lit_entry(sym[idx], l);
             for (uint32_t j = r; j < (1u << bits); j += 1u << l) fast[j] = e;
         }
         code <<= 1;
@@ -115,8 +144,8 @@ NP_HD void walk_state(const uint16_t* count, int steps, int32_t& first, int32_t&
     for (int l = 1; l <= steps; l++) { const int c = count[l]; index += c; first += c; first <<= 1; }
 }
 NP_HD void build_fast(Tables& t) {
-    build_fast(t.fast, FASTBITS, t.lcount, t.lsym);
-    build_fast(t.dfast, DFASTBITS, t.dcount, t.dsym);
+    build_fast(t.fast, FASTBITS, t.lcount, t.lsym, false);
+    build_fast(t.dfast, DFASTBITS, t.dcount, t.dsym, true);
     walk_state(t.lcount, FASTBITS, t.lfirst, t.lindex);
     walk_state(t.dcount, DFASTBITS, t.dfirst, t.dindex);
 }
@@ -136,21 +165,6 @@ NP_HD int decode_slow(Bits& b, const uint16_t* count, const uint16_t* sym, int f
     }
     return -1;
 }
-NP_HD int decode_dist(Bits& b, const Tables& t) {
-    if (b.cnt < MAXBITS) b.refill();
-    uint32_t e = t.dfast[b.peek(DFASTBITS)];
-    if (e & 15u) { b.drop((int)(e & 15u)); return (int)(e >> 4); }
-    return decode_slow(b, t.dcount, t.dsym);
-}
-NP_HD int decode_lit(Bits& b, const Tables& t) {
-    if (b.cnt < MAXBITS) b.refill();
-    uint32_t e = t.fast[b.peek(FASTBITS)];
-    if (e & 15u) { b.drop((int)(e & 15u)); return (int)(e >> 4); }
-    return decode_slow(b, t.lcount, t.lsym);
-}
-
-// RFC 1951 3.2.5 tables in closed form (a local array would be rebuilt on the stack at every call):
-// lengths 3,4,..,10, 11,13,15,17, 19,23,27,31, ... 227, 258; distances 1,2,3,4, 5,7, 9,13, 17,25, ... 24577
 NP_HD int32_t first_bit(uint32_t v) {     // index of the lowest set bit (v != 0)
 #ifdef __CUDA_ARCH__
     return __ffs((int)v) - 1;
@@ -158,65 +172,64 @@ NP_HD int32_t first_bit(uint32_t v) {     // index of the lowest set bit (v != 0
     return __builtin_ctz(v);
 #endif
 }
-NP_HD int32_t len_base(int s) {     // s = symbol - 257
-    if (s < 8) return 3 + s;
-    if (s == 28) return 258;
-    return ((4 + (s & 3)) << ((s >> 2) - 1)) + 3;
-}
-NP_HD int32_t len_extra(int s) { return s < 8 || s == 28 ? 0 : (s - 4) >> 2; }
-NP_HD int32_t dist_base(int s) { return s < 4 ? s + 1 : ((2 + (s & 1)) << ((s >> 1) - 1)) + 1; }
-NP_HD int32_t dist_extra(int s) { return s < 4 ? 0 : (s >> 1) - 1; }
-// the same as per-warp lookup tables (filled once per warp by init_tables: one load instead of ~8 dependent ALU steps)
-template <class W>
-NP_HD void init_tables(Tables& t, W& w) {
-    for (int i = w.lane(); i < 32; i += w.width()) {
-        t.lenx[i] = i < 29 ? (uint32_t)len_base(i) | (uint32_t)len_extra(i) << 16 : 0xffffffffu;
-        t.distx[i] = i < MAXD ? (uint32_t)dist_base(i) | (uint32_t)dist_extra(i) << 16 : 0xffffffffu;
+// The same walk for a code that missed the lookup table, without consuming it: symbol and code length (0: no such code).
+// `bits` = the next MAXBITS stream bits.
+NP_HD int walk_long(uint32_t bits, const uint16_t* count, const uint16_t* sym, int from, int first, int index, int* len) {
+    int code = (int)(rev_bits(bits, from) << 1);
+    bits >>= from;
+    for (int l = from + 1; l <= MAXBITS; l++) {
+        code |= (int)(bits & 1u); bits >>= 1;
+        const int c = count[l];
+        if (code - c < first) { *len = l; return sym[index + (code - first)]; }
+        index += c; first += c; first <<= 1; code <<= 1;
     }
-    w.sync();
+    *len = 0;
+    return -1;
 }
 
 // reads a dynamic block header into t (lane 0)
 NP_HD int read_dynamic(Bits& b, Tables& t) {
+    uint16_t* lens = t.lens();
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     int nlen = (int)b.get(5) + 257, ndist = (int)b.get(5) + 1, ncode = (int)b.get(4) + 4;
     if (nlen > 286 || ndist > MAXD) return ERR_LENGTHS;
-    for (int i = 0; i < 19; i++) t.lens[i] = 0;
-    for (int i = 0; i < ncode; i++) t.lens[order[i]] = (uint16_t)b.get(3);
+    for (int i = 0; i < 19; i++) lens[i] = 0;
+    for (int i = 0; i < ncode; i++) lens[order[i]] = (uint16_t)b.get(3);
     // the code-length code borrows the distance table's storage while the header is being read
     uint16_t ccount[MAXBITS + 1], csym[19];
-    if (build(ccount, csym, t.lens, 19) != 0) return ERR_LENGTHS;
+    if (build(ccount, csym, lens, 19) != 0) return ERR_LENGTHS;
     int idx = 0;
     while (idx < nlen + ndist) {
         int s = decode_slow(b, ccount, csym);
         if (s < 0) return ERR_CODE;
-        if (s < 16) t.lens[idx++] = (uint16_t)s;
+        if (s < 16) lens[idx++] = (uint16_t)s;
         else {
             int prev = 0, rep;
-            if (s == 16) { if (idx == 0) return ERR_LENGTHS; prev = t.lens[idx - 1]; rep = 3 + (int)b.get(2); }
+            if (s == 16) { if (idx == 0) return ERR_LENGTHS; prev = lens[idx - 1]; rep = 3 + (int)b.get(2); }
             else if (s == 17) rep = 3 + (int)b.get(3);
             else rep = 11 + (int)b.get(7);
             if (idx + rep > nlen + ndist) return ERR_LENGTHS;
-            while (rep--) t.lens[idx++] = (uint16_t)prev;
+            while (rep--) lens[idx++] = (uint16_t)prev;
         }
     }
-    if (t.lens[256] == 0) return ERR_LENGTHS;
-    int e = build(t.lcount, t.lsym, t.lens, nlen);
+    if (lens[256] == 0) return ERR_LENGTHS;
+    int e = build(t.lcount, t.lsym, lens, nlen);
     if (e < 0 || (e > 0 && nlen - t.lcount[0] != 1)) return ERR_LENGTHS;
-    e = build(t.dcount, t.dsym, t.lens + nlen, ndist);
+    e = build(t.dcount, t.dsym, lens + nlen, ndist);
     if (e < 0 || (e > 0 && ndist - t.dcount[0] != 1)) return ERR_LENGTHS;
     build_fast(t);
     return OK;
 }
 NP_HD void set_fixed(Tables& t) {
+    uint16_t* lens = t.lens();
     int s = 0;
-    for (; s < 144; s++) t.lens[s] = 8;
-    for (; s < 256; s++) t.lens[s] = 9;
-    for (; s < 280; s++) t.lens[s] = 7;
-    for (; s < 288; s++) t.lens[s] = 8;
-    build(t.lcount, t.lsym, t.lens, 288);
-    for (s = 0; s < MAXD; s++) t.lens[s] = 5;
-    build(t.dcount, t.dsym, t.lens, MAXD);
+    for (; s < 144; s++) lens[s] = 8;
+    for (; s < 256; s++) lens[s] = 9;
+    for (; s < 280; s++) lens[s] = 7;
+    for (; s < 288; s++) lens[s] = 8;
+    build(t.lcount, t.lsym, lens, 288);
+    for (s = 0; s < MAXD; s++) lens[s] = 5;
+    build(t.dcount, t.dsym, lens, MAXD);
     build_fast(t);
 }
 
@@ -259,7 +272,7 @@ NP_HD int32_t resolve_batch(uint8_t* out, uint32_t out_len, int32_t pos, int32_t
                     }
                 } else if (dst <= upto) {
                     // the match overlaps its own output: only the `dist` bytes before dst are read
-                    for (int32_t j = 0; j < len; j++) out[dst + j] = out[src + j % dist];
+                    for (int32_t j = 0, k = 0; j < len; j++) { out[dst + j] = out[src + k]; k = k + 1 == dist ? 0 : k + 1; }
                     done = true;
                 }
             }
@@ -316,46 +329,39 @@ NP_HD void dec_header(Decoder& d, Tables& t) {
     d.phase = PH_SYMBOLS;
 }
 // Decodes up to BATCH symbols into t.batch; returns their number.  Nothing is written to the output.
-// Tight loop: at most two refill checks, two table loads and two base/extra loads per match.  The bit buffer holds
-// >= 32 valid bits at each check: a literal/length code + extra needs <= 20, a distance code + extra <= 28.
+// Per symbol: one refill check (the bit buffer then holds >= 32 valid bits: a literal/length code + extra bits needs <= 20,
+// a distance code + extra bits <= 28), one table load, one drop of code and extra bits together; a match repeats that for
+// its distance.  Codes longer than the table index (rare) take the canonical walk behind the table.
 NP_HD int32_t dec_batch(Decoder& d, Tables& t) {
     Bits& b = d.b;
     int32_t nsym = 0;
-    bool run = true, end = false;
-    // A fixed trip count and structured ifs (no continue / break): the decoder lanes of a warp reconverge after every
-    // symbol and execute the loop body together, whatever kind of symbol each of them meets.
-    for (int it = 0; it < BATCH; it++) {
-        if (run) {
-            if (b.cnt < 32) b.refill();
-            uint32_t e = t.fast[(uint32_t)b.buf & ((1u << FASTBITS) - 1u)];
-            int s;
-            if (e & 15u) { b.drop((int)(e & 15u)); s = (int)(e >> 4); }
-            else s = decode_slow(b, t.lcount, t.lsym, FASTBITS, t.lfirst, t.lindex);
-            if (s < 256) {
-                if (s < 0) { d.err = ERR_CODE; run = false; }
-                else t.batch[nsym++] = 0x8000u | (uint32_t)s;
-            } else if (s == 256) { end = true; run = false; }
-            else if (s >= 286) { d.err = ERR_CODE; run = false; }
-            else {
-                const uint32_t lx = t.lenx[s - 257];
-                const uint32_t lxb = lx >> 16;
-                const uint32_t len = (lx & 0xffffu) + ((uint32_t)b.buf & ((1u << lxb) - 1u));
-                b.drop((int)lxb);
-                if (b.cnt < 32) b.refill();
-                e = t.dfast[(uint32_t)b.buf & ((1u << DFASTBITS) - 1u)];
-                int ds;
-                if (e & 15u) { b.drop((int)(e & 15u)); ds = (int)(e >> 4); }
-                else ds = decode_slow(b, t.dcount, t.dsym, DFASTBITS, t.dfirst, t.dindex);
-                if (ds < 0 || ds >= MAXD) { d.err = ERR_CODE; run = false; }
-                else {
-                    const uint32_t dx = t.distx[ds];
-                    const uint32_t dxb = dx >> 16;
-                    const uint32_t dist = (dx & 0xffffu) + ((uint32_t)b.buf & ((1u << dxb) - 1u));
-                    b.drop((int)dxb);
-                    t.batch[nsym++] = len | dist << 16;
-                }
-            }
+    bool end = false;
+    while (nsym < BATCH) {
+        if (b.cnt < 32) b.refill();
+        uint32_t lo = (uint32_t)b.buf;
+        uint32_t e = t.fast[lo & ((1u << FASTBITS) - 1u)];
+        if (!(e & 15u)) {
+            int l; const int sym = walk_long(lo & 0x7fffu, t.lcount, t.lsym, FASTBITS, t.lfirst, t.lindex, &l);
+            e = l ? lit_entry(sym, l) : (uint32_t)K_BAD << 8;
         }
+        const uint32_t l = e & 15u, kind = (e >> 8) & 3u;
+        if (kind == K_LIT) { b.drop((int)l); t.batch[nsym++] = 0x8000u | e >> 16; continue; }
+        if (kind != K_BASE) { if (kind == K_END) { b.drop((int)l); end = true; } else d.err = ERR_CODE; break; }
+        const uint32_t x = (e >> 4) & 15u;
+        const uint32_t len = (e >> 16) + ((lo >> l) & ((1u << x) - 1u));
+        b.drop((int)(l + x));
+        if (b.cnt < 32) b.refill();
+        lo = (uint32_t)b.buf;
+        e = t.dfast[lo & ((1u << DFASTBITS) - 1u)];
+        if (!(e & 15u)) {
+            int dl; const int sym = walk_long(lo & 0x7fffu, t.dcount, t.dsym, DFASTBITS, t.dfirst, t.dindex, &dl);
+            e = dl ? dist_entry(sym, dl) : (uint32_t)K_BAD << 8;
+        }
+        if (((e >> 8) & 3u) != K_BASE) { d.err = ERR_CODE; break; }
+        const uint32_t dl = e & 15u, dx = (e >> 4) & 15u;
+        const uint32_t dist = (e >> 16) + ((lo >> dl) & ((1u << dx) - 1u));
+        b.drop((int)(dl + dx));
+        t.batch[nsym++] = len | dist << 16;
     }
     if (!d.err && b.past_end()) d.err = ERR_INPUT;
     if (d.err) { d.phase = PH_DONE; return 0; }              // an inconsistent batch is not resolved

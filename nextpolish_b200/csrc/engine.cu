@@ -141,6 +141,26 @@ __global__ void __launch_bounds__(256) k_items_full(int64_t n, F f) {
     CudaOps ops; f(i, ops);
 }
 
+// Exclusive prefix sums of short arrays (region / window / contig counts: a few thousand entries): one CTA per array, one
+// launch for up to two arrays, instead of the two launches and the tile-state traffic of a device-wide scan each.
+struct SmallScan2 { const int32_t* in[2]; int32_t* out[2]; };
+__global__ void __launch_bounds__(1024) k_small_scan(SmallScan2 a, int32_t n) {
+    __shared__ int32_t scratch[32];
+    __shared__ int32_t carry_s;
+    const int32_t* in = a.in[blockIdx.x]; int32_t* out = a.out[blockIdx.x];
+    CudaOps ops;
+    int32_t carry = 0;
+    for (int32_t base = 0; base < n; base += 1024) {
+        const int32_t i = base + (int32_t)threadIdx.x;
+        const int32_t v = i < n ? in[i] : 0;
+        const int32_t ex = ops.block_exscan(v, scratch);
+        if (i < n) out[i] = carry + ex;
+        if (threadIdx.x == 1023) carry_s = carry + ex + v;
+        __syncthreads();
+        carry = carry_s;
+    }
+}
+
 // ---- tile kernels of the column pass (column_pass.h): one CTA per tile of TW draft positions ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -383,8 +403,29 @@ struct CudaBackend {
             cub_bytes = bytes + 1024;
         }
     }
+    enum { kSmallScan = 1 << 16 };
+    // two exclusive sums over arrays of the same length
+    void exscan2_i32(const int32_t* in_a, int32_t* out_a, const int32_t* in_b, int32_t* out_b, int64_t n) {
+        if (!ok || n <= 0) return;
+        if (n > kSmallScan) { exscan_i32(in_a, out_a, n); exscan_i32(in_b, out_b, n); return; }
+        begin_timed("scan_small");
+        SmallScan2 a{{in_a, in_b}, {out_a, out_b}};
+        k_small_scan<<<2, 1024, 0, stream>>>(a, (int32_t)n);
+        CUDA_TRY(cudaGetLastError());
+        launches++;
+        end_timed();
+    }
     void exscan_i32(const int32_t* in, int32_t* out, int64_t n) {
         if (!ok || n <= 0) return;
+        if (n <= kSmallScan) {
+            begin_timed("scan_small");
+            SmallScan2 a{{in, in}, {out, out}};
+            k_small_scan<<<1, 1024, 0, stream>>>(a, (int32_t)n);
+            CUDA_TRY(cudaGetLastError());
+            launches++;
+            end_timed();
+            return;
+        }
         size_t need = 0;
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n, stream));
         cub_reserve(need);
@@ -697,6 +738,7 @@ int64_t np_engine_result_bytes(np_engine* e) { return e && e->ran ? e->st.out_by
 const uint8_t* np_engine_result_device(np_engine* e) { return e && e->ran ? e->d.out : nullptr; }
 void* np_engine_stream(np_engine* e) { return e ? (void*)e->be.stream : nullptr; }
 int32_t np_engine_launch_count(np_engine* e) { return e ? e->be.launches : 0; }
+int64_t np_engine_launch_total(np_engine* e) { return e ? e->launches_total : 0; }
 
 int32_t np_engine_download(np_engine* e, uint8_t* out_seq, int64_t out_cap, int64_t* out_off) {
     if (!e || !e->ran) { np::set_error("np_engine_download: nothing to download"); return NP_ERR_ARG; }

@@ -19,6 +19,10 @@
 #pragma once
 #include "engine_impl.h"
 
+#ifndef NP_FORCE_REGION_WALK
+#define NP_FORCE_REGION_WALK 0      // test builds set 1: always take the literal per-contig merge (the fallback of the flat merge)
+#endif
+
 namespace npe {
 
 struct Dev2 {
@@ -31,7 +35,13 @@ struct Dev2 {
     // region lists per contig (slices [ctg_run_off[k], ctg_run_off[k+1]) * 2 ints)
     int32_t *gnd, *gkm;          // [2*n_runs+2] regions of every run group, written at the group head's slot
     int32_t *gcnt_nd, *gcnt_km;  // [n_runs] regions emitted by the group headed at this run (0: not a head)
-    int32_t *nd_reg, *km_reg;    // [2*n_runs+2] (start,end) pairs, global positions
+    // flat merge of the region lists (RegionDense / RegionHeads / RegionWrite): arrays indexed by list * (n_runs+1) + slot
+    int32_t *gvalid, *gpos;      // [2*(n_runs+1)] slot holds a region; exclusive scan (dense index)
+    int32_t *dreg, *dctg;        // dense regions per list: (start, end) pairs at dreg + list * 2 * (n_runs+1); contig of each
+    uint8_t* dhead;              // dense: region starts a merged region
+    int32_t *ghead, *gout;       // per slot: valid && head; exclusive scan (index of the merged region)
+    int32_t* reg_bad;            // [1] a contig's list is not in the shape the flat merge handles (see RegionHeads)
+    int32_t *nd_reg, *km_reg;    // [2*n_runs+2] (start,end) pairs, global positions (fallback path)
     int32_t *nd_cnt, *km_cnt;    // per contig: number of regions (pairs)
     int32_t *nd_off, *km_off;    // exclusive scans of the counts
     int32_t *ndl, *kml;          // compacted lists [2*NR]
@@ -202,10 +212,73 @@ struct RegionGroups {    // one thread per lowercase run and variant (0: no-dept
         int32_t gap = variant ? d.P.min_len_inter_kmer : 0, con = variant ? 0 : d.P.min_len_ldr;
         bool with_ext = variant != 0; int32_t ext = d.P.ext_len_edge;
         cnt[r] = 0;
+        if (r == 0) { w.gvalid[variant * ((size_t)w.n_runs + 1) + w.n_runs] = 0; *w.reg_bad = 0; }   // the scans' total entry
         if (r > r0 && !hard_boundary(d, w.run_s, w.run_e, r - 1, gs, ge, gap, with_ext, ext)) return;   // not a group head
         int32_t rend = r + 1;
         while (rend < r1 && !hard_boundary(d, w.run_s, w.run_e, rend - 1, gs, ge, gap, with_ext, ext)) rend++;
-        cnt[r] = regions_from_runs(d, w.run_s, w.run_e, r, rend, gs, ge, gap, con, with_ext, ext, out);
+        const int32_t n = regions_from_runs(d, w.run_s, w.run_e, r, rend, gs, ge, gap, con, with_ext, ext, out);
+        cnt[r] = n;
+        // the group's regions sit in the slots of its first n runs: the head marks every slot of its group
+        for (int32_t q = r; q < rend; q++) w.gvalid[variant * ((size_t)w.n_runs + 1) + q] = q - r < n;
+    }
+};
+// ---- flat merge of the region lists ------------------------------------------------------------
+// contig_merge_region (contig.c:595-620) walks one contig's list; in the shape every list has unless a region's left
+// extension runs across a whole earlier region (starts and ends non-decreasing inside a contig, first region not empty)
+// it reduces to: region i opens a merged region iff it is the contig's first or start_i >= end_(i-1); a merged region ends
+// with the end of its last member.  That form is data-parallel over ALL regions of ALL contigs (slot order = position
+// order = contig order), so the lists are merged and compacted by three flat kernels and two scans instead of one thread
+// per contig.  Any other shape raises reg_bad and the per-contig kernels below (the literal walk) redo the lists.
+struct RegionDense {     // one thread per slot and list: copy the slot's region to its dense index
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t it, B&) const {
+        const Dev& d = w.d;
+        const int64_t s = it >> 1; const int variant = (int)(it & 1);
+        const size_t N1 = (size_t)w.n_runs + 1, ix = variant * N1 + (size_t)s;
+        if (!w.gvalid[ix]) return;
+        const int32_t i = w.gpos[ix];
+        const int32_t* src = (variant ? w.gkm : w.gnd) + 2 * (size_t)s;
+        int32_t* dst = w.dreg + variant * 2 * N1;
+        dst[2 * (size_t)i] = src[0]; dst[2 * (size_t)i + 1] = src[1];
+        w.dctg[variant * N1 + i] = find_contig_i32(d.ctg_goff, d.n_ctg, src[0]);
+    }
+};
+struct RegionHeads {     // one thread per slot (+ the scans' total entry) and list
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t it, B&) const {
+        const int64_t s = it >> 1; const int variant = (int)(it & 1);
+        const size_t N1 = (size_t)w.n_runs + 1, ix = variant * N1 + (size_t)s;
+        w.ghead[ix] = 0;
+        if (s >= w.n_runs || !w.gvalid[ix]) return;
+        const size_t i = (size_t)w.gpos[ix];
+        const int32_t* reg = w.dreg + variant * 2 * N1;
+        const int32_t* ctg = w.dctg + variant * N1;
+        const bool first = i == 0 || ctg[i - 1] != ctg[i];
+        bool head = true;
+        if (first) { if (reg[2 * i] >= reg[2 * i + 1]) *w.reg_bad = 1; }       // the literal walk compares pair 0 with itself
+        else {
+            if (reg[2 * i] < reg[2 * i - 2] || reg[2 * i + 1] < reg[2 * i - 1]) *w.reg_bad = 1;
+            head = reg[2 * i] >= reg[2 * i - 1];
+        }
+        w.ghead[ix] = head;
+        w.dhead[variant * N1 + i] = head;
+    }
+};
+struct RegionWrite {     // one thread per slot and list: merged regions straight into the compact lists
+    Dev2 w;
+    template <class B> NP_HD void operator()(int64_t it, B&) const {
+        const int64_t s = it >> 1; const int variant = (int)(it & 1);
+        const size_t N1 = (size_t)w.n_runs + 1, ix = variant * N1 + (size_t)s;
+        if (!w.gvalid[ix]) return;
+        const size_t i = (size_t)w.gpos[ix];
+        const size_t n = (size_t)w.gpos[variant * N1 + (size_t)w.n_runs];     // dense regions of this list
+        const int32_t* reg = w.dreg + variant * 2 * N1;
+        const int32_t* ctg = w.dctg + variant * N1;
+        const uint8_t* hd = w.dhead + variant * N1;
+        int32_t* out = variant ? w.kml : w.ndl;
+        const size_t j = (size_t)(w.gout[ix] + w.ghead[ix] - 1);
+        if (w.ghead[ix]) out[2 * j] = reg[2 * i];
+        if (i + 1 >= n || ctg[i + 1] != ctg[i] || hd[i + 1]) out[2 * j + 1] = reg[2 * i + 1];
     }
 };
 struct ContigRegions {   // one thread per contig and list (0: no-depth, 1: k-mer): concatenate its groups' regions, contig_merge_region
@@ -842,8 +915,7 @@ void run_window_votes(BE& be, Dev2& w) {
     w.wp_cnt = be.template buf<int32_t>("wp_cnt", (size_t)w.NW + 1);
     w.wp_off = be.template buf<int32_t>("wp_off", (size_t)w.NW + 1);
     be.launch("window_count", (int64_t)w.NW + 1, WindowCount{w});
-    be.exscan_i32(w.wcand, w.wsoff, (int64_t)w.NW + 1);
-    be.exscan_i32(w.wp_cnt, w.wp_off, (int64_t)w.NW + 1);
+    be.exscan2_i32(w.wcand, w.wsoff, w.wp_cnt, w.wp_off, (int64_t)w.NW + 1);
     int32_t WS = 0;
     { const int32_t* ptrs[2] = {w.wsoff + w.NW, w.wp_off + w.NW}; int32_t v[2]; be.read_many(ptrs, 2, v); WS = v[0]; w.NP_w = v[1]; }
     w.wscratch = be.template buf<int32_t>("wscratch", (size_t)WS + 4);
@@ -903,14 +975,36 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st, int mode = 2) {
     w.gkm = be.template buf<int32_t>("gkm", regcap);
     w.gcnt_nd = be.template buf<int32_t>("gcnt_nd", (size_t)w.n_runs + 1);
     w.gcnt_km = be.template buf<int32_t>("gcnt_km", (size_t)w.n_runs + 1);
-    if (w.n_runs > 0) be.launch("region_groups", 2 * (int64_t)w.n_runs, RegionGroups{w});
-    be.launch("contig_regions", 2 * (int64_t)d.n_ctg, ContigRegions{w});
-    be.exscan_i32(w.nd_cnt, w.nd_off, (int64_t)d.n_ctg + 1);
-    be.exscan_i32(w.km_cnt, w.km_off, (int64_t)d.n_ctg + 1);
-    { const int32_t* ptrs[2] = {w.nd_off + d.n_ctg, w.km_off + d.n_ctg}; int32_t v[2]; be.read_many(ptrs, 2, v); w.NR_nd = v[0]; w.NR_km = v[1]; }
-    w.ndl = be.template buf<int32_t>("ndl", 2 * (size_t)w.NR_nd + 2);
-    w.kml = be.template buf<int32_t>("kml", 2 * (size_t)w.NR_km + 2);
-    be.launch("compact_regions", (int64_t)d.n_ctg * CompactRegions::COMPACT_LANES, CompactRegions{w});
+    const size_t N1 = (size_t)w.n_runs + 1, nslot = 2 * N1;         // slots (+ the scans' total entry) of both lists
+    w.gvalid = be.template buf<int32_t>("gvalid", nslot);
+    w.gpos = be.template buf<int32_t>("gpos", nslot);
+    w.ghead = be.template buf<int32_t>("ghead", nslot);
+    w.gout = be.template buf<int32_t>("gout", nslot);
+    w.dreg = be.template buf<int32_t>("dreg", 2 * nslot);
+    w.dctg = be.template buf<int32_t>("dctg", nslot);
+    w.dhead = be.template buf<uint8_t>("dhead", nslot);
+    w.reg_bad = be.template buf<int32_t>("reg_bad", 1);
+    // the region lists never outgrow the run list: one region per run at most
+    w.ndl = be.template buf<int32_t>("ndl", 2 * (size_t)w.n_runs + 2 * (size_t)d.n_ctg + 4);
+    w.kml = be.template buf<int32_t>("kml", 2 * (size_t)w.n_runs + 2 * (size_t)d.n_ctg + 4);
+    int32_t bad = NP_FORCE_REGION_WALK;
+    w.NR_nd = 0; w.NR_km = 0;
+    if (w.n_runs > 0) {
+        be.launch("region_groups", 2 * (int64_t)w.n_runs, RegionGroups{w});
+        be.exscan2_i32(w.gvalid, w.gpos, w.gvalid + N1, w.gpos + N1, (int64_t)N1);
+        be.launch("region_dense", 2 * (int64_t)w.n_runs, RegionDense{w});
+        be.launch("region_heads", 2 * (int64_t)N1, RegionHeads{w});
+        be.exscan2_i32(w.ghead, w.gout, w.ghead + N1, w.gout + N1, (int64_t)N1);
+        be.launch("region_write", 2 * (int64_t)w.n_runs, RegionWrite{w});
+        const int32_t* ptrs[3] = {w.gout + w.n_runs, w.gout + N1 + w.n_runs, w.reg_bad}; int32_t v[3];
+        be.read_many(ptrs, 3, v); w.NR_nd = v[0]; w.NR_km = v[1]; bad |= v[2];
+    }
+    if (bad && w.n_runs > 0) {                                      // the literal per-contig walk
+        be.launch("contig_regions", 2 * (int64_t)d.n_ctg, ContigRegions{w});
+        be.exscan2_i32(w.nd_cnt, w.nd_off, w.km_cnt, w.km_off, (int64_t)d.n_ctg + 1);
+        { const int32_t* ptrs[2] = {w.nd_off + d.n_ctg, w.km_off + d.n_ctg}; int32_t v[2]; be.read_many(ptrs, 2, v); w.NR_nd = v[0]; w.NR_km = v[1]; }
+        be.launch("compact_regions", (int64_t)d.n_ctg * CompactRegions::COMPACT_LANES, CompactRegions{w});
+    }
     // insertion columns inside regions only
     w.inreg = be.template buf<uint8_t>("inreg", (size_t)G + 2);
     be.zero(w.inreg, (size_t)G + 2);
@@ -943,8 +1037,7 @@ int run_kmer_count(BE& be, Dev& d0, RunStats* st, int mode = 2) {
         w.nd_sb = be.template buf<int32_t>("nd_sb", (size_t)w.NR_nd + 1);
         w.nd_soff = be.template buf<int32_t>("nd_soff", (size_t)w.NR_nd + 1);
         be.launch("nodepth_pairs", (int64_t)w.NR_nd + 1, NdPairCount{w});
-        be.exscan_i32(w.nd_pcnt, w.nd_poff, (int64_t)w.NR_nd + 1);
-        be.exscan_i32(w.nd_sb, w.nd_soff, (int64_t)w.NR_nd + 1);
+        be.exscan2_i32(w.nd_pcnt, w.nd_poff, w.nd_sb, w.nd_soff, (int64_t)w.NR_nd + 1);
         int32_t SB = 0;
         { const int32_t* ptrs[2] = {w.nd_poff + w.NR_nd, w.nd_soff + w.NR_nd}; int32_t v[2]; be.read_many(ptrs, 2, v); w.NP_nd = v[0]; SB = v[1]; }
         w.ndp_read = be.template buf<int32_t>("ndp_read", (size_t)w.NP_nd + 1);

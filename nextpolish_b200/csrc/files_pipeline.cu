@@ -114,7 +114,7 @@ extern "C" {
 
 np_files* np_files_create(int32_t device, int32_t depth) {
     if (depth < 1) depth = 1;
-    if (depth > 4) depth = 4;
+    if (depth > 8) depth = 8;
     np_files* P = new np_files();
     P->device = device;
     for (int i = 0; i < depth; i++) {

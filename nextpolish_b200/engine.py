@@ -189,6 +189,45 @@ class DeviceShard:
             pass
 
 
+class ResidentSlots:
+    """np_resident: `slots` engines (stream + scratch + host thread each) polishing shards that already sit in HBM,
+    concurrently.  submit() hands the job to slot ticket % slots (wait for ticket - slots first); the result lands in
+    the caller's device buffer as a 16-byte header (byte count) followed by the polished bytes."""
+
+    def __init__(self, device=0, slots=4):
+        self.slots = slots
+        self.h = lib().np_resident_create(device, slots)
+        if not self.h:
+            raise NativeError(last_error())
+
+    def submit(self, task, dev_view, cfg, dst_ptr, dst_cap):
+        t = lib().np_resident_submit(self.h, task, C.byref(dev_view), cfg, dst_ptr, dst_cap)
+        if t < 0:
+            raise NativeError("rc=%d: %s" % (t, last_error()))
+        return t
+
+    def wait(self, ticket):
+        n = C.c_int64(0)
+        rc = lib().np_resident_wait(self.h, ticket, C.byref(n))
+        if rc != 0:
+            raise NativeError("rc=%d: %s" % (rc, last_error()))
+        return n.value
+
+    def launch_count(self):
+        return lib().np_resident_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().np_resident_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Stream:
     """np_stream: jobs (task, host shard) submitted in order; a job's upload overlaps the kernels of the jobs
     before it (double buffering).  Buffers handed to submit() must stay alive until wait(ticket) returned."""

@@ -90,8 +90,9 @@ def emu():
 @pytest.fixture(scope="session")
 def emu_general_slices():
     """The same test build with the column pass's 64-bit fast path limited to 9 columns per thread slice, so that
-    ordinary inputs reach the general (many insertion sub-columns) loops of column_pass.h."""
-    return _emu_build("libnp_emu_slow.so", ("-DNP_SLICE_FAST_MAX=9",))
+    ordinary inputs reach the general (many insertion sub-columns) loops of column_pass.h; and with task 2's region lists
+    always merged by the literal per-contig walk (the fallback of the flat merge, engine_task2.h)."""
+    return _emu_build("libnp_emu_slow.so", ("-DNP_SLICE_FAST_MAX=9", "-DNP_FORCE_REGION_WALK=1"))
 
 
 def run_checker(fn, shard, task, cfg, extra=()):

@@ -35,7 +35,6 @@ extern "C" int np_emu_bgzf_inflate(const uint8_t* comp, int64_t comp_bytes, uint
         const npz::Block& b = blocks[i];
         if (!b.out_len) continue;
         memset(&t, 0xA5, sizeof t);                       // poison: the decoder must initialise what it reads
-        npz::init_tables(t, w);
         int rc = npz::inflate_block(comp + b.in_off, b.in_len, out + b.out_off, b.out_len, t, w);
         if (rc != npz::OK) return rc;
     }

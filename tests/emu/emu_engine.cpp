@@ -46,6 +46,9 @@ struct EmuBackend {
         int64_t s = 0;
         for (int64_t i = 0; i < n; i++) { int32_t v = in[i]; out[i] = (int32_t)s; s += v; }
     }
+    void exscan2_i32(const int32_t* in_a, int32_t* out_a, const int32_t* in_b, int32_t* out_b, int64_t n) {
+        exscan_i32(in_a, out_a, n); exscan_i32(in_b, out_b, n);
+    }
     void exscan_ncol(const int32_t* ins, int32_t* out, int64_t G) {
         int64_t s = 0;
         for (int64_t i = 0; i <= G; i++) { out[i] = (int32_t)s; s += 1 + ins[i]; }

@@ -183,3 +183,17 @@ def test_emulated_column_pass_general_slices(E, oracle, emu_general_slices, case
     cfg = E.default_config(b"")
     want = run_checker(oracle.np_oracle_run, sh, 1, cfg)
     assert run_checker(L.np_emu_run_impl, sh, 1, cfg, (None, 2)) == want
+
+
+@pytest.mark.parametrize("case", ["c30", "lower", "ragged", "lower_shallow"])
+@pytest.mark.parametrize("task", [2, 4])
+def test_emulated_region_lists_literal_walk(E, oracle, emu_general_slices, case, task):
+    """Task 2 / 4 merge their region lists with flat kernels when every list has the usual shape and with the literal
+    per-contig walk of contig_merge_region otherwise; this build always takes the walk."""
+    if case not in CASES:
+        pytest.skip("no such synthetic case")
+    sh = E.Shard.synthetic(E.synth_params(**CASES[case]), 0, CASES[case]["n_contigs"], with_qual=1)
+    cfg = E.default_config(b"")
+    cfg.contents.read_tlen = 1750
+    want = run_checker(oracle.np_oracle_run, sh, task, cfg)
+    assert run_checker(emu_general_slices.np_emu_run, sh, task, cfg, (None,)) == want
