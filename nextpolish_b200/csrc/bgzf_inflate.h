@@ -26,6 +26,15 @@
 #include <stdint.h>
 #include "device_logic.h"
 
+#ifndef NP_UNLIKELY
+#define NP_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#endif
+#if defined(__CUDACC__)
+#define NP_NO_UNROLL _Pragma("unroll 1")
+#else
+#define NP_NO_UNROLL
+#endif
+
 namespace npz {
 
 enum { OK = 0, ERR_BTYPE = 1, ERR_STORED = 2, ERR_LENGTHS = 3, ERR_CODE = 4, ERR_DIST = 5, ERR_OUTPUT = 6,
@@ -41,12 +50,34 @@ struct Block {             // one BGZF block: where its raw deflate payload live
 enum { MAXBITS = 15, MAXL = 288, MAXD = 30, FASTBITS = 10, DFASTBITS = 8, BATCH = 32 };
 
 // Lookup-table entries (literal/length and distance alike), one 32-bit word:
-//   bits 0-3   code length in bits (0: the code is longer than the table's index — canonical walk)
-//   bits 4-7   number of extra bits that follow the code (RFC 1951 3.2.5)
-//   bits 8-9   kind: literal / length (for the distance table: distance) / end of block / invalid symbol
+//   bits 0-3   code length in bits
+//   bit 4      literal
+//   bit 5      not a symbol with a value (E_SPECIAL): end of block (E_END), a code longer than the table's index — the
+//              canonical walk finds it (E_LONG; takes nothing out of the bit buffer) — or an invalid symbol (neither)
+//   bits 8-15  code length + extra bits (RFC 1951 3.2.5): what the symbol takes out of the bit buffer
 //   bits 16-31 literal byte, base length or base distance
-// so that one shared-memory load yields everything a symbol needs and code + extra bits leave the bit buffer together.
-enum { K_LIT = 0, K_BASE = 1, K_END = 2, K_BAD = 3 };
+// so that one shared-memory load yields everything a symbol needs, code + extra bits leave the bit buffer together, and
+// every rare case hides behind ONE flag test.
+enum { E_LIT = 0x10, E_SPECIAL = 0x20, E_END = 0x40, E_LONG = 0x80 };
+NP_HD uint32_t entry_bits(int l, int x) { return (uint32_t)l | (uint32_t)(l + x) << 8; }
+NP_HD uint32_t entry_take(uint32_t e) {                     // bits 8-15
+#ifdef __CUDA_ARCH__
+    return __byte_perm(e, 0u, 0x4441u);
+#else
+    return (e >> 8) & 0xffu;
+#endif
+}
+NP_HD uint32_t low_mask(uint32_t n) {                       // n ones (n < 32)
+#ifdef __CUDA_ARCH__
+    uint32_t m; asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(m) : "r"(n)); return m;
+#else
+    return ~(0xffffffffu << n);
+#endif
+}
+NP_HD uint32_t entry_value(uint32_t e, uint32_t lo) {       // base + the extra bits that follow the code
+    const uint32_t l = e & 15u;
+    return (e >> 16) + ((lo >> l) & low_mask(entry_take(e) - l));
+}
 
 struct Tables {            // per-warp shared memory (5.9 KB)
     uint32_t batch[BATCH];                 // decoded symbols: literal = 0x8000 | byte; match = length | distance << 16
@@ -60,29 +91,40 @@ struct Tables {            // per-warp shared memory (5.9 KB)
 };
 static_assert((MAXL + MAXD + 2) * 2 <= (1 << FASTBITS) * 4, "the code-length scratch borrows the lookup table");
 
-struct Bits {              // LSB-first bit reader over the compressed bytes (lane 0 only)
-    const uint8_t* p; const uint8_t* end;
-    uint64_t buf; int32_t cnt; int32_t overrun;
-    NP_HD static uint32_t load32(const uint8_t* q) {     // 4 bytes at any alignment, little endian
+struct Bits {              // LSB-first bit reader over the compressed bytes (the decoding lane only)
+    // The payload is consumed as ALIGNED 32-bit words (one load per refill, no end test on the way): the word holding the
+    // first payload byte is shifted into place at the start, and reading runs at most 7 bytes past the payload — inside the
+    // next block's header, or the slack every compressed buffer of this engine carries.  Bits that were never there are
+    // noticed afterwards by comparing the consumed count with the payload size (past_end).
+    const uint8_t* in; uint32_t in_len;
+    uint32_t wi;           // next word to load, in words from the aligned start
+    uint32_t skew;         // bits of the first word that precede the payload
+    uint64_t buf; int32_t cnt;
+    const uint32_t* wbase; // the aligned word that holds the first payload byte
+    NP_HD uint32_t word(uint32_t i) const {
 #ifdef __CUDA_ARCH__
-        const uint32_t* a = (const uint32_t*)((uintptr_t)q & ~(uintptr_t)3);   // two aligned words + funnel shift; the
-        return __funnelshift_r(a[0], a[1], 8u * (uint32_t)((uintptr_t)q & 3u)); // second word may lie past q+4 (buffer slack)
+        return wbase[i];
 #else
-        return (uint32_t)q[0] | (uint32_t)q[1] << 8 | (uint32_t)q[2] << 16 | (uint32_t)q[3] << 24;
+        uint32_t v = 0;                                   // test build: byte loads, nothing outside [in, in + in_len)
+        for (int j = 0; j < 4; j++) {
+            const int64_t o = (int64_t)i * 4 + j - (int64_t)(skew >> 3);
+            if (o >= 0 && o < (int64_t)in_len) v |= (uint32_t)in[o] << (8 * j);
+        }
+        return v;
 #endif
     }
-    NP_HD void refill() {
-        if (cnt <= 32 && p + 4 <= end) { buf |= (uint64_t)load32(p) << cnt; p += 4; cnt += 32; return; }
-        while (cnt <= 56) {
-            if (p < end) buf |= (uint64_t)(*p++) << cnt;
-            else overrun += 8;                   // zeros past the end: an error only if they get consumed
-            cnt += 8;
-        }
+    NP_HD void seek(const uint8_t* base, uint32_t len, uint32_t byte_off) {     // continue at payload byte byte_off
+        const uint32_t mis = (uint32_t)((uintptr_t)(base + byte_off) & 3u);
+        in = base + byte_off; in_len = len - byte_off; skew = 8u * mis;
+        wbase = (const uint32_t*)(in - mis);
+        buf = (uint64_t)(word(0) >> skew); cnt = 32 - (int32_t)skew; wi = 1;
     }
+    NP_HD void refill() { if (cnt <= 32) { buf |= (uint64_t)word(wi++) << cnt; cnt += 32; } }    // afterwards cnt > 32
     NP_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1ull)); }
     NP_HD void drop(int n) { buf >>= n; cnt -= n; }
-    NP_HD uint32_t get(int n) { if (cnt < n) refill(); uint32_t v = peek(n); drop(n); return v; }
-    NP_HD bool past_end() const { return overrun > cnt; }      // consumed bits that were never there
+    NP_HD uint32_t get(int n) { refill(); uint32_t v = peek(n); drop(n); return v; }
+    NP_HD uint32_t consumed_bits() const { return wi * 32u - skew - (uint32_t)cnt; }
+    NP_HD bool past_end() const { return consumed_bits() > in_len * 8u; }      // consumed bits that were never there
 };
 
 // canonical code construction (RFC 1951 3.2.2): count[len], symbols ordered by (len, symbol)
@@ -117,18 +159,18 @@ NP_HD int32_t len_extra(int s) { return s < 8 || s == 28 ? 0 : (s - 4) >> 2; }
 NP_HD int32_t dist_base(int s) { return s < 4 ? s + 1 : ((2 + (s & 1)) << ((s >> 1) - 1)) + 1; }
 NP_HD int32_t dist_extra(int s) { return s < 4 ? 0 : (s >> 1) - 1; }
 NP_HD uint32_t lit_entry(int sym, int l) {      // literal/length symbol with an l-bit code
-    if (sym < 256) return (uint32_t)sym << 16 | (uint32_t)K_LIT << 8 | (uint32_t)l;
-    if (sym == 256) return (uint32_t)K_END << 8 | (uint32_t)l;
-    if (sym >= 286) return (uint32_t)K_BAD << 8 | (uint32_t)l;
-    return (uint32_t)len_base(sym - 257) << 16 | (uint32_t)K_BASE << 8 | (uint32_t)len_extra(sym - 257) << 4 | (uint32_t)l;
+    if (sym < 256) return (uint32_t)sym << 16 | (uint32_t)E_LIT | entry_bits(l, 0);
+    if (sym == 256) return (uint32_t)(E_SPECIAL | E_END) | entry_bits(l, 0);
+    if (sym >= 286) return (uint32_t)E_SPECIAL | entry_bits(l, 0);
+    return (uint32_t)len_base(sym - 257) << 16 | entry_bits(l, len_extra(sym - 257));
 }
 NP_HD uint32_t dist_entry(int sym, int l) {
-    if (sym >= MAXD) return (uint32_t)K_BAD << 8 | (uint32_t)l;
-    return (uint32_t)dist_base(sym) << 16 | (uint32_t)K_BASE << 8 | (uint32_t)dist_extra(sym) << 4 | (uint32_t)l;
+    if (sym >= MAXD) return (uint32_t)E_SPECIAL | entry_bits(l, 0);
+    return (uint32_t)dist_base(sym) << 16 | entry_bits(l, dist_extra(sym));
 }
 // lookup table of the codes of up to `bits` bits: index = next `bits` stream bits (LSB first)
 NP_HD void build_fast(uint32_t* fast, int bits, const uint16_t* count, const uint16_t* sym, bool dist) {
-    for (int i = 0; i < (1 << bits); i++) fast[i] = 0;
+    for (int i = 0; i < (1 << bits); i++) fast[i] = (uint32_t)(E_SPECIAL | E_LONG);
     uint32_t code = 0; int idx = 0;
     for (int l = 1; l <= bits; l++) {
         for (int k = 0; k < count[l]; k++, idx++, code++) {
@@ -153,7 +195,7 @@ NP_HD void build_fast(Tables& t) {
 // The walk's `first` / `index` after l steps depend only on the code-length histogram, and its `code` is the bit-reversed
 // l-bit prefix of the stream: a code known to be longer than `from` bits (it missed the lookup table) resumes there.
 NP_HD int decode_slow(Bits& b, const uint16_t* count, const uint16_t* sym, int from = 0, int first0 = 0, int index0 = 0) {
-    if (b.cnt < MAXBITS) b.refill();
+    b.refill();
     int code = 0, first = first0, index = index0;
     uint32_t bits = b.peek(MAXBITS);
     if (from > 0) { code = (int)(rev_bits(bits, from) << 1); bits >>= from; }
@@ -298,7 +340,7 @@ struct Decoder {
 };
 enum { PH_IDLE = 0, PH_HEADER = 1, PH_SYMBOLS = 2, PH_DONE = 3 };
 NP_HD void dec_start(Decoder& d, const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) {
-    d.b = Bits{in, in + in_len, 0ull, 0, 0};
+    d.b.seek(in, in_len, 0);
     d.in = in; d.out = out; d.in_len = in_len; d.out_len = out_len;
     d.pos = 0; d.last = 0; d.err = OK; d.phase = PH_HEADER;
 }
@@ -311,14 +353,13 @@ NP_HD void dec_header(Decoder& d, Tables& t) {
         b.drop(b.cnt & 7);                                   // to the next byte boundary
         const uint32_t l = b.get(16), nl = b.get(16);
         if ((l ^ 0xffffu) != nl) { d.err = ERR_STORED; d.phase = PH_DONE; return; }
-        // bytes still sitting in the bit buffer belong to the stored data: give them back
-        int32_t back = (b.cnt - b.overrun) / 8; if (back < 0) back = 0;
-        const int32_t src = (int32_t)(b.p - d.in) - back, len = (int32_t)l;
+        // the stored bytes start at the reader's byte position (whole bytes left in the bit buffer belong to them)
+        const int32_t src = (int32_t)(b.in - d.in) + (int32_t)(b.consumed_bits() >> 3), len = (int32_t)l;
         if (src + len > (int32_t)d.in_len) { d.err = ERR_INPUT; d.phase = PH_DONE; return; }
         if (d.pos + len > (int32_t)d.out_len) { d.err = ERR_OUTPUT; d.phase = PH_DONE; return; }
         for (int32_t i = 0; i < len; i++) d.out[d.pos + i] = d.in[src + i];
         d.pos += len;
-        b.p = d.in + src + len; b.buf = 0; b.cnt = 0; b.overrun = 0;
+        b.seek(d.in, d.in_len, (uint32_t)(src + len));
         d.phase = d.last ? PH_DONE : PH_HEADER;
         return;
     }
@@ -328,41 +369,50 @@ NP_HD void dec_header(Decoder& d, Tables& t) {
     if (e) { d.err = e; d.phase = PH_DONE; return; }
     d.phase = PH_SYMBOLS;
 }
+// entries of codes longer than the lookup index: the canonical walk behind the table
+NP_HD uint32_t long_lit_entry(uint32_t lo, const Tables& t) {
+    int l; const int sym = walk_long(lo & 0x7fffu, t.lcount, t.lsym, FASTBITS, t.lfirst, t.lindex, &l);
+    return l ? lit_entry(sym, l) : (uint32_t)E_SPECIAL;
+}
+NP_HD uint32_t long_dist_entry(uint32_t lo, const Tables& t) {
+    int l; const int sym = walk_long(lo & 0x7fffu, t.dcount, t.dsym, DFASTBITS, t.dfirst, t.dindex, &l);
+    return l ? dist_entry(sym, l) : (uint32_t)E_SPECIAL;
+}
 // Decodes up to BATCH symbols into t.batch; returns their number.  Nothing is written to the output.
-// Per symbol: one refill check (the bit buffer then holds >= 32 valid bits: a literal/length code + extra bits needs <= 20,
-// a distance code + extra bits <= 28), one table load, one drop of code and extra bits together; a match repeats that for
-// its distance.  Codes longer than the table index (rare) take the canonical walk behind the table.
+// Per symbol: one refill test (the bit buffer then holds > 32 valid bits: a literal/length code + extra bits needs <= 20),
+// one table load, one drop of code and extra bits together, one flag test for everything rare (long codes, the end of the
+// block, invalid symbols); a match repeats that for its distance (<= 28 bits).  The kernel is bound by instruction issue
+// on this one lane, so the common path is kept a short straight line.
 NP_HD int32_t dec_batch(Decoder& d, Tables& t) {
-    Bits& b = d.b;
+    Bits b = d.b;                                               // the reader's state in registers for the loop
     int32_t nsym = 0;
-    bool end = false;
-    while (nsym < BATCH) {
-        if (b.cnt < 32) b.refill();
+    uint32_t special = 0;
+    do {
+        NP_NO_UNROLL
+        while (b.cnt <= 32) b.refill();                         // (loops, not ifs: the compiler keeps them as branches)
         uint32_t lo = (uint32_t)b.buf;
         uint32_t e = t.fast[lo & ((1u << FASTBITS) - 1u)];
-        if (!(e & 15u)) {
-            int l; const int sym = walk_long(lo & 0x7fffu, t.lcount, t.lsym, FASTBITS, t.lfirst, t.lindex, &l);
-            e = l ? lit_entry(sym, l) : (uint32_t)K_BAD << 8;
+        b.drop((int)entry_take(e));
+        if (NP_UNLIKELY(e & E_SPECIAL)) {
+            if (e & E_LONG) { e = long_lit_entry(lo, t); b.drop((int)entry_take(e)); }
+            if (e & E_SPECIAL) { special = e; break; }
         }
-        const uint32_t l = e & 15u, kind = (e >> 8) & 3u;
-        if (kind == K_LIT) { b.drop((int)l); t.batch[nsym++] = 0x8000u | e >> 16; continue; }
-        if (kind != K_BASE) { if (kind == K_END) { b.drop((int)l); end = true; } else d.err = ERR_CODE; break; }
-        const uint32_t x = (e >> 4) & 15u;
-        const uint32_t len = (e >> 16) + ((lo >> l) & ((1u << x) - 1u));
-        b.drop((int)(l + x));
-        if (b.cnt < 32) b.refill();
+        if (e & E_LIT) { t.batch[nsym++] = 0x8000u | e >> 16; continue; }
+        const uint32_t len = entry_value(e, lo);
+        NP_NO_UNROLL
+        while (NP_UNLIKELY(b.cnt < 28)) b.refill();             // a distance code and its extra bits: 28 bits at most
         lo = (uint32_t)b.buf;
         e = t.dfast[lo & ((1u << DFASTBITS) - 1u)];
-        if (!(e & 15u)) {
-            int dl; const int sym = walk_long(lo & 0x7fffu, t.dcount, t.dsym, DFASTBITS, t.dfirst, t.dindex, &dl);
-            e = dl ? dist_entry(sym, dl) : (uint32_t)K_BAD << 8;
+        if (NP_UNLIKELY(e & E_SPECIAL)) {
+            if (e & E_LONG) e = long_dist_entry(lo, t);
+            if (e & E_SPECIAL) { special = E_SPECIAL; break; }
         }
-        if (((e >> 8) & 3u) != K_BASE) { d.err = ERR_CODE; break; }
-        const uint32_t dl = e & 15u, dx = (e >> 4) & 15u;
-        const uint32_t dist = (e >> 16) + ((lo >> dl) & ((1u << dx) - 1u));
-        b.drop((int)(dl + dx));
-        t.batch[nsym++] = len | dist << 16;
-    }
+        b.drop((int)entry_take(e));
+        t.batch[nsym++] = len | entry_value(e, lo) << 16;
+    } while (nsym < BATCH);
+    d.b = b;
+    bool end = false;
+    if (special) { if (special & E_END) end = true; else d.err = ERR_CODE; }
     if (!d.err && b.past_end()) d.err = ERR_INPUT;
     if (d.err) { d.phase = PH_DONE; return 0; }              // an inconsistent batch is not resolved
     if (end) d.phase = d.last ? PH_DONE : PH_HEADER;
