@@ -292,10 +292,11 @@ void        np_dev_shard_free(np_dev_shard* shard);
 
 /* ---- from-files front end (pipelined): the batch form of the reference ABI's per-contig calls (score_chain / kmer_count,
  * scorechain.c:3-15, kmercount.c:93-126) and of main.c:12-26 — draft FASTA + coordinate-sorted BGZF BAM (+ .bai) in,
- * polished sequences in FASTA order out.  A pipeline owns `depth` slots (engine + host worker thread); a submitted job's
- * file reads, upload, inflate and unpack overlap the kernels of the job before it.  np_files_submit returns a ticket >= 0
- * or a negative NP_ERR_*; at most `depth` tickets may be outstanding (submitted and not yet waited for).  The arrays of a
- * result stay valid until the next np_files_submit that reuses the slot (ticket + depth) or np_files_destroy. */
+ * polished sequences in FASTA order out.  A pipeline owns `depth` workers (engine + host thread) that pull jobs from a
+ * queue: a job's file reads, upload, inflate and unpack overlap the kernels of the others.  np_files_submit returns a
+ * ticket >= 0 or a negative NP_ERR_*; at most 2 x `depth` tickets may be outstanding (submitted and not yet waited for).
+ * The arrays of a result stay valid until the np_files_submit that reuses its record (ticket + 2 x depth) or
+ * np_files_destroy. */
 typedef struct np_files np_files;
 typedef struct {
     int32_t            task;

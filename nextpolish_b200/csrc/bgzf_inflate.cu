@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <string>
 #include <vector>
@@ -12,6 +13,7 @@
 #include "bgzf_inflate.h"
 #include "bgzf_inflate_dev.h"
 #include "errors.h"
+#include "stream_wait.h"
 #include "hostio.h"
 #include "../../include/nextpolish_b200.h"
 
@@ -166,6 +168,11 @@ int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_byte
             if (cudaMallocHost(&pinned, want) == cudaSuccess) pinned_bytes = want; else { pinned = nullptr; cudaGetLastError(); }
         }
         if (pinned) {
+            // one range at a time: with several loads in flight (the pipelined front ends run one host thread per slot)
+            // simultaneous copies would put slots x helper threads on the host's cores at once; measured, the pipeline
+            // then falls into a mode twice as slow in which the slots march in lock step
+            static std::mutex stage_mu;
+            std::lock_guard<std::mutex> stage_lock(stage_mu);
             unsigned hw = std::thread::hardware_concurrency();
             const size_t nt = hw >= 16 ? 8 : hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
             std::vector<std::thread> th;
@@ -197,7 +204,7 @@ int32_t inflate_finish(InflateJob& j, float* kernel_ms, std::string& err) {
     if (j.nb == 0) return NP_OK;
     std::vector<int32_t> st(j.nb);
     cudaMemcpyAsync(st.data(), j.d_status, j.nb * 4, cudaMemcpyDeviceToHost, j.stream);
-    cudaError_t er = cudaStreamSynchronize(j.stream);
+    cudaError_t er = np_wait::stream_wait(j.stream);
     if (kernel_ms && er == cudaSuccess) cudaEventElapsedTime(kernel_ms, j.e0, j.e1);
     cudaEventDestroy(j.e0); cudaEventDestroy(j.e1);
     cudaFreeAsync(j.d_comp, j.stream); cudaFreeAsync(j.d_blocks, j.stream); cudaFreeAsync(j.d_status, j.stream);
@@ -255,7 +262,7 @@ int32_t np_bgzf_inflate(int32_t device, const uint8_t* comp, int64_t comp_bytes,
     std::vector<int32_t> st(nb);
     cudaMemcpyAsync(st.data(), c.d_status, nb * 4, cudaMemcpyDeviceToHost, c.stream);
     cudaMemcpyAsync(out, c.d_out, (size_t)total, cudaMemcpyDeviceToHost, c.stream);
-    cudaError_t er = cudaStreamSynchronize(c.stream);
+    cudaError_t er = np_wait::stream_wait(c.stream);
     if (er != cudaSuccess) { np::set_error(std::string("np_bgzf_inflate: ") + cudaGetErrorString(er)); return NP_ERR_CUDA; }
     if (kernel_ms) cudaEventElapsedTime(kernel_ms, c.e0, c.e1);
     for (size_t i = 0; i < nb; i++)

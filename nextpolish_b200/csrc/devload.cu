@@ -38,6 +38,7 @@
 #include "bgzf_inflate.h"
 #include "bgzf_inflate_dev.h"
 #include "errors.h"
+#include "stream_wait.h"
 #include "hostio.h"
 #include "../../include/nextpolish_b200.h"
 
@@ -282,7 +283,7 @@ extern "C" {
 void np_dev_shard_free(np_dev_shard* s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->stream) np_wait::stream_wait(s->stream);
     delete s;
 }
 
@@ -386,7 +387,7 @@ static np_dev_shard* load_gpu_impl(int32_t device, const char* fasta, const char
         std::string ignored;
         if (job.nb) npz_dev::inflate_finish(job, nullptr, ignored);        // an inflate in flight: wait and release its buffers
         set_error("np_shard_load_gpu: " + m);
-        cudaStreamSynchronize(st);
+        np_wait::stream_wait(st);
         np_dev_shard_free(S);
         return (np_dev_shard*)nullptr;
     };
@@ -524,7 +525,7 @@ static np_dev_shard* load_gpu_impl(int32_t device, const char* fasta, const char
         if (!S->rec_off.alloc(16, st) || !S->rec.alloc(16, st) || (with_qual && (!S->qual_off.alloc(16, st) || !S->qual.alloc(16, st)))) return false;
         cudaMemsetAsync(S->rec_off.p, 0, 16, st);
         if (with_qual) cudaMemsetAsync(S->qual_off.p, 0, 16, st);
-        return cudaStreamSynchronize(st) == cudaSuccess;
+        return np_wait::stream_wait(st) == cudaSuccess;
     };
     if (!any_reads) { if (!finish_empty()) return fail("cudaMalloc failed"); return S; }
     const int32_t n_int = (int32_t)anchors.size() - 1;
@@ -580,7 +581,7 @@ static np_dev_shard* load_gpu_impl(int32_t device, const char* fasta, const char
     cudaMemcpyAsync(&tot[1], d_uoff.as<int32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&tot[2], d_quoff.as<int32_t>() + n_rec, 4, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&h_err, d_err.p, 4, cudaMemcpyDeviceToHost, st);
-    cudaStreamSynchronize(st);
+    np_wait::stream_wait(st);
     lap("index walk + meta + scans (sync)");
     if (h_err) {
         return fail(h_err & DL_ERR_LONG ? "read longer than 65535 bases / CIGAR ops: not a short-read record"
@@ -599,7 +600,7 @@ static np_dev_shard* load_gpu_impl(int32_t device, const char* fasta, const char
     std::vector<int32_t> counts((size_t)n_slots + 1, 0);
     cudaMemcpyAsync(counts.data(), d_scount.p, ((size_t)n_slots + 1) * 4, cudaMemcpyDeviceToHost, st);
     cudaEventRecord(e1, st);
-    cudaError_t er = cudaStreamSynchronize(st);
+    cudaError_t er = np_wait::stream_wait(st);
     if (er != cudaSuccess) return fail(cudaGetErrorString(er));
     lap("pack (sync)");
     if (trace) {

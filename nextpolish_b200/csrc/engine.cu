@@ -19,6 +19,7 @@
 #include "engine_task2.h"
 #include "engine_v2.h"
 #include "errors.h"
+#include "stream_wait.h"
 #include "hostio.h"
 #include "../../include/nextpolish_b200.h"
 
@@ -354,7 +355,7 @@ struct CudaBackend {
         Buf& b = pool[name];
         size_t bytes = count * sizeof(T) + 256;
         if (b.bytes < bytes) {
-            if (b.p) { CUDA_TRY(cudaStreamSynchronize(stream)); CUDA_TRY(cudaFree(b.p)); b.p = nullptr; }
+            if (b.p) { CUDA_TRY(np_wait::stream_wait(stream)); CUDA_TRY(cudaFree(b.p)); b.p = nullptr; }
             size_t want = bytes + bytes / 8;
             CUDA_TRY(cudaMalloc(&b.p, want));
             b.bytes = b.p ? want : 0;
@@ -398,7 +399,7 @@ struct CudaBackend {
     }
     void cub_reserve(size_t bytes) {
         if (bytes > cub_bytes) {
-            if (cub_tmp) { CUDA_TRY(cudaStreamSynchronize(stream)); CUDA_TRY(cudaFree(cub_tmp)); }
+            if (cub_tmp) { CUDA_TRY(np_wait::stream_wait(stream)); CUDA_TRY(cudaFree(cub_tmp)); }
             CUDA_TRY(cudaMalloc(&cub_tmp, bytes + 1024));
             cub_bytes = bytes + 1024;
         }
@@ -483,7 +484,7 @@ struct CudaBackend {
         if (ok && n) {
             // pageable source: the copy is followed by a synchronisation so that the caller's vector may go out of scope
             CUDA_TRY(cudaMemcpyAsync(p, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-            CUDA_TRY(cudaStreamSynchronize(stream));
+            CUDA_TRY(np_wait::stream_wait(stream));
         }
         return p;
     }
@@ -517,13 +518,13 @@ struct CudaBackend {
         for (int i = 0; i < n; i++) out[i] = 0;
         if (!ok) return;
         for (int i = 0; i < n; i++) CUDA_TRY(cudaMemcpyAsync(h_scalar + i, ptrs[i], sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(np_wait::stream_wait(stream));
         if (ok) for (int i = 0; i < n; i++) out[i] = h_scalar[i];
     }
     int32_t read_i32(const int32_t* p) {
         if (!ok) return 0;
         CUDA_TRY(cudaMemcpyAsync(h_scalar, p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(np_wait::stream_wait(stream));
         return ok ? *h_scalar : 0;
     }
     void release() {
@@ -575,7 +576,7 @@ struct np_engine {
 
 static bool dev_reserve(np_engine* e, void** p, size_t* cap, size_t bytes) {
     if (*cap >= bytes && *p) return true;
-    if (*p) { cudaStreamSynchronize(e->be.stream); cudaFree(*p); *p = nullptr; *cap = 0; }
+    if (*p) { np_wait::stream_wait(e->be.stream); cudaFree(*p); *p = nullptr; *cap = 0; }
     size_t want = bytes + bytes / 16 + 256;
     cudaError_t er = cudaMalloc(p, want);
     if (er != cudaSuccess) { np::set_error(std::string("cudaMalloc: ") + cudaGetErrorString(er)); return false; }
@@ -613,7 +614,7 @@ void np_engine_destroy(np_engine* e) {
     if (e->sibling) { np_engine_destroy(e->sibling); e->sibling = nullptr; }
     if (e->copy_done) cudaEventDestroy(e->copy_done);
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->be.stream);
+    np_wait::stream_wait(e->be.stream);
     void* ps[] = {e->s_seq, e->s_goff, e->s_roff, e->s_recoff, e->s_rec, e->s_qoff, e->s_qual};
     for (void* p : ps) if (p) cudaFree(p);
     e->be.release();
@@ -648,14 +649,14 @@ static int32_t set_shard_slice(np_engine* e, const np_shard_view* v, int32_t k0,
     // small metadata goes through the pinned bounce buffer of the engine (the vectors above are pageable)
     cudaMemcpyAsync(e->s_goff, goff.data(), goff.size() * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(e->s_roff, e->h_read_off.data(), e->h_read_off.size() * 8, cudaMemcpyHostToDevice, s);
-    cudaStreamSynchronize(s);      // goff is a local: it must not go out of scope before the copy ran
+    np_wait::stream_wait(s);      // goff is a local: it must not go out of scope before the copy ran
     // record / quality byte ranges of the slice
     uint32_t rec_lo = 0, rec_hi = 0, q_lo = 0, q_hi = 0;
     if (device_resident) {
         cudaMemcpyAsync(&rec_lo, v->rec_off + r0, 4, cudaMemcpyDeviceToHost, s);
         cudaMemcpyAsync(&rec_hi, v->rec_off + r0 + R, 4, cudaMemcpyDeviceToHost, s);
         if (v->qual_off) { cudaMemcpyAsync(&q_lo, v->qual_off + r0, 4, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(&q_hi, v->qual_off + r0 + R, 4, cudaMemcpyDeviceToHost, s); }
-        cudaStreamSynchronize(s);
+        np_wait::stream_wait(s);
     } else {
         rec_lo = v->rec_off[r0]; rec_hi = v->rec_off[r0 + R];
         if (v->qual_off) { q_lo = v->qual_off[r0]; q_hi = v->qual_off[r0 + R]; }
@@ -730,7 +731,7 @@ int32_t np_engine_run(np_engine* e, int32_t task, const Configure* cfg) {
 
 int32_t np_engine_sync(np_engine* e) {
     cudaSetDevice(e->device);
-    cudaError_t er = cudaStreamSynchronize(e->be.stream);
+    cudaError_t er = np_wait::stream_wait(e->be.stream);
     if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
     return NP_OK;
 }
@@ -747,7 +748,7 @@ int32_t np_engine_download(np_engine* e, uint8_t* out_seq, int64_t out_cap, int6
     cudaStream_t s = e->be.stream;
     cudaMemcpyAsync(out_seq, e->d.out, (size_t)e->st.out_bytes, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(out_off, e->d.out_off, ((size_t)e->d.n_ctg + 1) * 8, cudaMemcpyDeviceToHost, s);
-    cudaError_t er = cudaStreamSynchronize(s);
+    cudaError_t er = np_wait::stream_wait(s);
     if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
     return NP_OK;
 }
@@ -757,7 +758,7 @@ int32_t np_engine_result_offsets(np_engine* e, int64_t* out_off) {
     if (!e || !e->ran || !out_off) { np::set_error("np_engine_result_offsets: nothing to read"); return NP_ERR_ARG; }
     cudaSetDevice(e->device);
     cudaMemcpyAsync(out_off, e->d.out_off, ((size_t)e->d.n_ctg + 1) * 8, cudaMemcpyDeviceToHost, e->be.stream);
-    cudaError_t er = cudaStreamSynchronize(e->be.stream);
+    cudaError_t er = np_wait::stream_wait(e->be.stream);
     if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
     return NP_OK;
 }
@@ -773,7 +774,7 @@ int32_t np_engine_points(np_engine* e, PolishPoint* out, int64_t cap, int64_t* o
     cudaStream_t s = e->be.stream;
     if (e->d.n_pts > 0) cudaMemcpyAsync(out, e->d.pts, (size_t)e->d.n_pts * sizeof(PolishPoint), cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(off, e->d.pts_off, ((size_t)e->d.n_ctg + 1) * 8, cudaMemcpyDeviceToHost, s);
-    cudaError_t er = cudaStreamSynchronize(s);
+    cudaError_t er = np_wait::stream_wait(s);
     if (er != cudaSuccess) { np::set_error(cudaGetErrorString(er)); return NP_ERR_CUDA; }
     return NP_OK;
 }
@@ -811,7 +812,7 @@ int32_t np_engine_pack_result(np_engine* e, void* dst_device, int64_t dst_cap) {
 int32_t np_engine_kernel_times(np_engine* e, const char** names, float* ms, int32_t cap) {
     if (!e) return 0;
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->be.stream);
+    np_wait::stream_wait(e->be.stream);
     int32_t n = 0;
     for (size_t i = 0; i < e->be.n_timed && n < cap; i++, n++) {
         names[n] = e->be.timed[i].name;

@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "errors.h"
+#include "stream_wait.h"
 #include "hostio.h"
 #include "../../include/nextpolish_b200.h"
 
@@ -64,6 +65,7 @@ struct GpuWorker {
     std::mutex mu; std::condition_variable cv;
     std::function<void()> job; bool has_job = false, done = true, quit = false;
     void loop() {
+        np_wait::use_blocking_waits(true);
         for (;;) {
             std::function<void()> j;
             {
@@ -307,7 +309,7 @@ int32_t np_multi_run(np_multi* m, int32_t task, const char* fasta, const char* b
             ncclResult_t r = m->nccl.Send(m->d_res[(size_t)g], (size_t)used[(size_t)g], ncclUint8, 0, m->comm[(size_t)g], s);
             if (r != ncclSuccess) nrc[(size_t)g] = r;
         }
-        if (cudaStreamSynchronize(s) != cudaSuccess) nrc[(size_t)g] = ncclUnhandledCudaError;
+        if (np_wait::stream_wait(s) != cudaSuccess) nrc[(size_t)g] = ncclUnhandledCudaError;
     };
     for (int g = 0; g < n; g++) m->workers[(size_t)g * (size_t)K]->submit([&gather, g] { gather(g); });
     for (int g = 0; g < n; g++) m->workers[(size_t)g * (size_t)K]->wait();

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "errors.h"
+#include "stream_wait.h"
 #include "../../include/nextpolish_b200.h"
 
 namespace {
@@ -40,6 +41,7 @@ struct np_resident {
 static void rworker(np_resident* P, RSlot* sp) {
     RSlot& s = *sp;
     cudaSetDevice(P->device);
+    np_wait::use_blocking_waits(true);
     for (;;) {
         {
             std::unique_lock<std::mutex> lk(s.mu);

@@ -299,10 +299,12 @@ def partition_contiguous(lengths, n_parts):
 
 
 class FilePipeline:
-    """np_files: FASTA + BAM (+ .bai) files -> polished sequences on the host, `depth` jobs in flight (each slot = engine +
-    host worker thread; load, upload, inflate and unpack of one job overlap the kernels of the other)."""
+    """np_files: FASTA + BAM (+ .bai) files -> polished sequences on the host; `depth` workers (engine + host thread each)
+    pull jobs from a queue of up to `capacity` = 2 x depth submitted, uncollected jobs (load, upload, inflate and unpack of
+    one job overlap the kernels of the others)."""
 
     def __init__(self, device=0, depth=2):
+        self.capacity = 2 * max(1, min(8, depth))
         self.h = lib().np_files_create(device, depth)
         if not self.h:
             raise NativeError(last_error())

@@ -59,3 +59,46 @@ def test_resident_slots_equal_one_engine(E, slots):
     with pytest.raises(E.NativeError):
         rp.wait(10 ** 6)
     rp.close()
+
+
+def test_files_pipeline_queue_matches_reference_md5(E, synth_files):
+    """np_files: workers pull jobs from a queue; 2 x depth jobs may be outstanding, results come back per ticket and equal
+    the committed md5s of the reference binary's output on the same files (needs <bam>.bai: the GPU loader)."""
+    import json
+    import os
+    import subprocess
+    from tests.conftest import GOLDEN, REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("no samtools to index the BAMs")
+    cases = ["c30", "lower", "ragged"]
+    want = json.load(open(os.path.join(GOLDEN, "synth_md5.json")))
+    files = {}
+    for c in cases:
+        fa, bam = synth_files(c)
+        if not os.path.exists(bam + ".bai"):
+            subprocess.check_call([REF_SAMTOOLS, "index", bam])
+        files[c] = (fa, bam)
+    fp = E.FilePipeline(0, depth=2)
+    assert fp.capacity == 4
+    jobs = [(c, t) for c in cases for t in (1, 2)] * 2
+    done = 0
+
+    def collect():
+        nonlocal done
+        c, t = jobs[done]
+        r = fp.wait_oldest(want_md5=True)
+        assert r["task"] == t
+        assert {"%s_%d" % (n, t): h for n, h in r["md5"].items()} == want[c][str(t)], (c, t)
+        done += 1
+
+    for c, t in jobs:
+        while fp.in_flight() > fp.capacity - 1:
+            collect()
+        fp.submit(t, files[c][0], files[c][1], E.default_config(files[c][0], files[c][1]))
+    with pytest.raises(E.NativeError):              # every record holds an uncollected job
+        while True:
+            fp.submit(1, files["c30"][0], files["c30"][1], E.default_config(files["c30"][0], files["c30"][1]))
+            jobs.append(("c30", 1))
+    while fp.in_flight():
+        collect()
+    fp.close()

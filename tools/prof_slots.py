@@ -34,7 +34,8 @@ for t in (1, 2):
         cap = max(cap, int(sh.total_bases * 1.25) + 4096)
 bp = 2 * bench.WORKLOAD["n_contigs"] * bench.WORKLOAD["contig_len"]
 only = os.environ.get("NP_PROF_ONLY", "")
-for slots in (() if only == "files" else (1, 4, 8, 12, 16)):
+for slots, spin in (() if only == "files" else ((1, "0"), (8, "0"), (8, "1"), (12, "0"), (16, "0"))):
+    os.environ["NEXTPOLISH_B200_SPIN"] = spin
     rp = E.ResidentSlots(0, slots)
     bufs = [torch.zeros(cap + 16, dtype=torch.uint8, device=dev) for _ in range(slots)]
     pend, n = [], 0
@@ -55,14 +56,15 @@ for slots in (() if only == "files" else (1, 4, 8, 12, 16)):
     run(steps)
     torch.cuda.synchronize()
     dt = time.time() - t0
-    print("resident slots %d: %.3f ms per 2-task step = %.0f Mbp/s" % (slots, dt / steps * 1e3, bp * steps / dt / 1e6), flush=True)
+    print("resident slots %d spin %s: %.3f ms per 2-task step = %.0f Mbp/s" % (slots, spin, dt / steps * 1e3, bp * steps / dt / 1e6), flush=True)
     rp.close()
 del keep
 tmp = tempfile.mkdtemp(prefix="npfiles")
 files = bench.write_inputs(tmp, 0, [1, 2])
-for dep in (() if only == "resident" else (4, 6, 8)):
+for dep, spin in (() if only == "resident" else ((3, "0"), (6, "0"), (3, "1"), (6, "1"), (4, "0"), (8, "0"))):
+    os.environ["NEXTPOLISH_B200_SPIN"] = spin
     pipe = E.FilePipeline(0, depth=dep)
-    for n in (6, 24):
+    for n in (8, 80):
         t0 = time.time()
         for i in range(n):
             for t in (1, 2):
@@ -72,6 +74,6 @@ for dep in (() if only == "resident" else (4, 6, 8)):
         while pipe.in_flight():
             pipe.wait_oldest(want_md5=False)
         dt = time.time() - t0
-    print("files depth %d: %.2f ms per 2-task step = %.0f Mbp/s" % (dep, dt / n * 1e3, bp * n / dt / 1e6), flush=True)
+    print("files depth %d spin %s: %.2f ms per 2-task step = %.0f Mbp/s" % (dep, spin, dt / n * 1e3, bp * n / dt / 1e6), flush=True)
     pipe.close()
 print("host cpus", os.cpu_count())
