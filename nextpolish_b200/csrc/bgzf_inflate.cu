@@ -1,10 +1,12 @@
 // bgzf_inflate.cu — GPU inflate of BGZF blocks (one warp per block) and its C ABI.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (nextpolish_b200/csrc/Makefile).
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -126,6 +128,73 @@ static bool reserve(void** p, size_t* cap, size_t bytes) {
 
 }  // namespace
 
+namespace {
+// Copies a byte range into pinned memory with a few helper threads.  The helpers are created once and live for the
+// process (spawning and joining seven threads per load meant stack mappings made and torn down under the process-wide
+// memory-map lock, next to six other loading threads); one copy runs at a time: with several loads in flight
+// simultaneous copies would put slots x helpers on the host's cores at once.
+class StagePool {
+public:
+    void copy(uint8_t* dst, const uint8_t* src, size_t n) {
+        std::lock_guard<std::mutex> one(job_mu_);
+        start_threads();
+        const size_t parts = th_.size() + 1, step = (n + parts - 1) / parts;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = dst; src_ = src; n_ = n; step_ = step; pending_ = (int)th_.size(); gen_++;
+        }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(step, n));                          // the caller takes the first part
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+private:
+    void start_threads() {
+        if (started_) return;
+        started_ = true;
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int nt = hw >= 16 ? 7 : hw >= 8 ? 3 : (hw >= 4 ? 1 : 0);
+        for (int t = 0; t < nt; t++) th_.emplace_back([this, t] { run(t + 1); });
+        for (auto& x : th_) x.detach();                               // process lifetime: they sleep on the condition variable
+    }
+    void run(int part) {
+        uint64_t seen = 0;
+        for (;;) {
+            uint8_t* d; const uint8_t* s; size_t n, step;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_; d = dst_; s = src_; n = n_; step = step_;
+            }
+            const size_t a = (size_t)part * step, b = std::min(n, a + step);
+            if (a < b) memcpy(d + a, s + a, b - a);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                pending_--;
+            }
+            done_.notify_all();
+        }
+    }
+    std::mutex job_mu_, mu_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> th_;
+    bool started_ = false;
+    uint8_t* dst_ = nullptr; const uint8_t* src_ = nullptr; size_t n_ = 0, step_ = 0;
+    int pending_ = 0; uint64_t gen_ = 0;
+};
+void stage_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+    // never destroyed (its threads outlive static destructors); rebuilt in a forked child, whose copy has no threads
+    static std::mutex mu; static StagePool* pool = nullptr; static pid_t owner = 0;
+    StagePool* p;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!pool || owner != getpid()) { pool = new StagePool(); owner = getpid(); }
+        p = pool;
+    }
+    p->copy(dst, src, n);
+}
+}  // namespace
+
 namespace npz_dev {
 cudaMemPool_t thread_pool(int device) {
     static thread_local std::vector<std::pair<int, cudaMemPool_t>> pools;
@@ -168,22 +237,8 @@ int32_t inflate_launch(InflateJob& j, const uint8_t* comp_host, size_t comp_byte
             if (cudaMallocHost(&pinned, want) == cudaSuccess) pinned_bytes = want; else { pinned = nullptr; cudaGetLastError(); }
         }
         if (pinned) {
-            // one range at a time: with several loads in flight (the pipelined front ends run one host thread per slot)
-            // simultaneous copies would put slots x helper threads on the host's cores at once; measured, the pipeline
-            // then falls into a mode twice as slow in which the slots march in lock step
-            static std::mutex stage_mu;
-            std::lock_guard<std::mutex> stage_lock(stage_mu);
-            unsigned hw = std::thread::hardware_concurrency();
-            const size_t nt = hw >= 16 ? 8 : hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
-            std::vector<std::thread> th;
-            const size_t step = (comp_bytes + nt - 1) / nt;
-            uint8_t* const pin = (uint8_t*)pinned;      // a thread_local is not captured: the helper threads need the value
-            for (size_t t = 1; t < nt; t++) {
-                const size_t a = t * step, b = std::min(comp_bytes, a + step);
-                if (a < b) th.emplace_back([=] { memcpy(pin + a, comp_host + a, b - a); });
-            }
-            memcpy(pinned, comp_host, std::min(step, comp_bytes));
-            for (auto& x : th) x.join();
+            // one range at a time, copied by a few persistent helper threads (StagePool above)
+            stage_copy((uint8_t*)pinned, comp_host, comp_bytes);
             src = (const uint8_t*)pinned;
         }
     }

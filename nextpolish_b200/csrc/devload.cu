@@ -14,7 +14,7 @@
 //   k_rec_meta       one thread per record: fields, contig slot, 2-bit / 4-bit decision, packed size, whether the
 //                    qualities are shipped (sparse mode: the span contains a lowercase draft base)
 //   scans            record / quality offsets (CUB)
-//   k_rec_pack       one thread per kept record: header, CIGAR, bases, qualities
+//   k_rec_pack       one warp per kept record: header, CIGAR, bases, qualities (coalesced byte traffic)
 //
 // The result is byte-identical to the host packer's shard (tests/test_devload.py) and is adopted by the engine in
 // place (np_engine_adopt_device).
@@ -166,50 +166,70 @@ struct PackArgs {
     uint32_t* rec_off; uint8_t* rec; uint32_t* qual_off; uint8_t* qual;
     int32_t* slot_count; int32_t n_keep, total_units, total_qunits;
 };
-__global__ void k_rec_pack(PackArgs a) {
-    int32_t r = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (r == 0) {     // closing entries of the offset arrays
+// One WARP per record (round 2; one thread per record with byte loops ran at 1.1 ms per 5 Mb shard because neighbouring
+// threads walked different 280-byte records): the lanes read and write consecutive bytes, so every access of the warp is
+// one or two sectors; a warp handles records r, r + warps, ... of the grid.
+constexpr int kPackWarps = 8;
+__global__ void __launch_bounds__(kPackWarps * 32) k_rec_pack(PackArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int32_t w0 = (int32_t)(blockIdx.x * kPackWarps + (threadIdx.x >> 5)), nw = (int32_t)(gridDim.x * kPackWarps);
+    if (w0 == 0 && lane == 0) {     // closing entries of the offset arrays
         a.rec_off[a.n_keep] = (uint32_t)a.total_units;
         if (a.qual_off) a.qual_off[a.n_keep] = (uint32_t)a.total_qunits;
     }
-    if (r >= a.n_rec || !a.keep[r]) return;
-    const int32_t k = a.kidx[r];
-    const uint8_t* p = a.U + a.rec_start[r] + 4;
-    const uint32_t l_name = p[8], n_cigar = ld16(p + 12);
-    const int32_t l_seq = (int32_t)ld32(p + 16);
-    uint8_t* d = a.rec + (size_t)a.uoff[r] * 16;
-    a.rec_off[k] = (uint32_t)a.uoff[r];
-    // header: pos, flag, mapq, enc, isize, l_qseq, n_cigar (include/nextpolish_b200.h)
-    for (int i = 0; i < 4; i++) d[i] = p[4 + i];
-    d[4] = p[14]; d[5] = p[15]; d[6] = p[9]; d[7] = a.enc[r];
-    for (int i = 0; i < 4; i++) d[8 + i] = p[28 + i];
-    d[12] = (uint8_t)(l_seq & 0xff); d[13] = (uint8_t)(l_seq >> 8); d[14] = p[12]; d[15] = p[13];
-    const uint8_t* cig = p + 32 + l_name;
-    for (uint32_t i = 0; i < 4 * n_cigar; i++) d[16 + i] = cig[i];
-    const uint8_t* seq = cig + 4 * n_cigar;
-    uint8_t* ds = d + 16 + 4 * n_cigar;
-    if (!a.enc[r]) { for (int32_t i = 0; i < (l_seq + 1) / 2; i++) ds[i] = seq[i]; }
-    else {
-        for (int32_t b = 0; b < (l_seq + 3) / 4; b++) {
-            uint32_t o = 0;
-            for (int32_t j = 0; j < 4; j++) {
-                const int32_t i = 4 * b + j;
-                if (i >= l_seq) break;
-                const uint32_t c = (seq[i >> 1] >> ((~i & 1) << 2)) & 0xfu;
-                o |= (c == 1 ? 0u : c == 2 ? 1u : c == 4 ? 2u : 3u) << (6 - 2 * j);
+    for (int32_t r = w0; r < a.n_rec; r += nw) {
+        if (!a.keep[r]) continue;
+        const int32_t k = a.kidx[r];
+        const uint8_t* p = a.U + a.rec_start[r] + 4;
+        // the fixed 32-byte part of the record: one byte per lane, fields through shuffles
+        const uint32_t hb = p[lane];
+        const uint32_t l_name = __shfl_sync(0xffffffffu, hb, 8);
+        const uint32_t n_cigar = __shfl_sync(0xffffffffu, hb, 12) | __shfl_sync(0xffffffffu, hb, 13) << 8;
+        const int32_t l_seq = (int32_t)(__shfl_sync(0xffffffffu, hb, 16) | __shfl_sync(0xffffffffu, hb, 17) << 8 |
+                                        __shfl_sync(0xffffffffu, hb, 18) << 16 | __shfl_sync(0xffffffffu, hb, 19) << 24);
+        const uint32_t enc = a.enc[r];
+        uint8_t* d = a.rec + (size_t)a.uoff[r] * 16;
+        // header: pos, flag, mapq, enc, isize, l_qseq, n_cigar (include/nextpolish_b200.h): byte i of the packed header
+        // comes from byte src[i] of the BAM record (0xff: not a copy)
+        {
+            const uint64_t src_lo = 0xff090f0e07060504ull, src_hi = 0x0d0cffff1f1e1d1cull;     // d[0..7], d[8..15]
+            const uint32_t sidx = lane < 16 ? (uint32_t)(((lane < 8 ? src_lo : src_hi) >> (8 * (lane & 7))) & 0xffu) : 0u;
+            uint32_t v = __shfl_sync(0xffffffffu, hb, (int)(sidx & 31u));
+            if (lane == 7) v = enc;
+            if (lane == 12) v = (uint32_t)l_seq & 0xffu;
+            if (lane == 13) v = ((uint32_t)l_seq >> 8) & 0xffu;
+            if (lane < 16) d[lane] = (uint8_t)v;
+            if (lane == 0) a.rec_off[k] = (uint32_t)a.uoff[r];
+        }
+        const uint8_t* cig = p + 32 + l_name;
+        for (uint32_t i = (uint32_t)lane; i < 4 * n_cigar; i += 32) d[16 + i] = cig[i];
+        const uint8_t* seq = cig + 4 * n_cigar;
+        uint8_t* ds = d + 16 + 4 * n_cigar;
+        if (!enc) { for (int32_t i = lane; i < (l_seq + 1) / 2; i += 32) ds[i] = seq[i]; }
+        else {
+            // four bases (two 4-bit bytes) -> one 2-bit byte; bases past l_seq contribute zero bits
+            for (int32_t bq = lane; bq < (l_seq + 3) / 4; bq += 32) {
+                const uint32_t b0 = seq[2 * bq], b1 = 4 * bq + 2 < l_seq ? seq[2 * bq + 1] : 0u;
+                uint32_t o = 0;
+                #pragma unroll
+                for (int32_t j = 0; j < 4; j++) {
+                    const uint32_t c = ((j < 2 ? b0 : b1) >> ((~j & 1) << 2)) & 0xfu;
+                    const uint32_t two = c == 1 ? 0u : c == 2 ? 1u : c == 4 ? 2u : 3u;
+                    if (4 * bq + j < l_seq) o |= two << (6 - 2 * j);
+                }
+                ds[bq] = (uint8_t)o;
             }
-            ds[b] = (uint8_t)o;
         }
-    }
-    if (a.qual_off) {
-        a.qual_off[k] = (uint32_t)a.quoff[r];
-        if (a.qunits[r]) {
-            const uint8_t* q = seq + (l_seq + 1) / 2;
-            uint8_t* dq = a.qual + (size_t)a.quoff[r] * 16;
-            for (int32_t i = 0; i < l_seq; i++) dq[i] = q[i];
+        if (a.qual_off) {
+            if (lane == 0) a.qual_off[k] = (uint32_t)a.quoff[r];
+            if (a.qunits[r]) {
+                const uint8_t* q = seq + (l_seq + 1) / 2;
+                uint8_t* dq = a.qual + (size_t)a.quoff[r] * 16;
+                for (int32_t i = lane; i < l_seq; i += 32) dq[i] = q[i];
+            }
         }
+        if (lane == 0) atomicAdd(&a.slot_count[a.slot[r]], 1);
     }
-    atomicAdd(&a.slot_count[a.slot[r]], 1);
 }
 __global__ void k_lower_flags(const uint8_t* seq, int64_t n, int32_t* f) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -596,7 +616,12 @@ static np_dev_shard* load_gpu_impl(int32_t device, const char* fasta, const char
     PackArgs pa{U.as<uint8_t>(), d_start.as<int64_t>(), n_rec, d_keep.as<int32_t>(), d_kidx.as<int32_t>(), d_uoff.as<int32_t>(), d_quoff.as<int32_t>(),
                 d_qunits.as<int32_t>(), d_slot.as<int32_t>(), d_enc.as<uint8_t>(), S->rec_off.as<uint32_t>(), S->rec.as<uint8_t>(),
                 with_qual ? S->qual_off.as<uint32_t>() : nullptr, with_qual ? S->qual.as<uint8_t>() : nullptr, d_scount.as<int32_t>(), n_keep, tot[1], tot[2]};
-    k_rec_pack<<<(n_rec + 127) / 128, 128, 0, st>>>(pa);
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const int want = (n_rec + kPackWarps - 1) / kPackWarps, cap = sms * 16;          // resident CTAs: 8 per SM, two rounds
+        k_rec_pack<<<std::max(1, std::min(want, cap)), kPackWarps * 32, 0, st>>>(pa);
+    }
     std::vector<int32_t> counts((size_t)n_slots + 1, 0);
     cudaMemcpyAsync(counts.data(), d_scount.p, ((size_t)n_slots + 1) * 4, cudaMemcpyDeviceToHost, st);
     cudaEventRecord(e1, st);

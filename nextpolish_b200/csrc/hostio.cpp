@@ -114,12 +114,19 @@ bool fasta_load_flat(const std::string& path, std::vector<std::string>& names, s
     const size_t n = (size_t)st.st_size;
     names.clear(); off.assign(1, 0);
     if (n == 0) { close(fd); return true; }
-    void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    // read() into a buffer the calling thread keeps (grow-only): a mapping made and torn down per call costs page-table
+    // work and TLB shootdowns across all of the process's threads — the pipelined front ends call this once per job
+    static thread_local std::vector<char> tbuf;
+    if (tbuf.size() < n) tbuf.resize(n + n / 8);
+    for (size_t got = 0; got < n;) {
+        const ssize_t k = pread(fd, tbuf.data() + got, n - got, (off_t)got);
+        if (k <= 0) { close(fd); err = "cannot read " + path; return false; }
+        got += (size_t)k;
+    }
     close(fd);
-    if (m == MAP_FAILED) { err = "cannot map " + path; return false; }
-    const char* text = (const char*)m;
+    const char* text = tbuf.data();
     uint8_t* dst = grow(ctx, n + 16);                 // the sequences are never longer than the file
-    if (!dst) { munmap(m, n); err = "out of memory"; return false; }
+    if (!dst) { err = "out of memory"; return false; }
     size_t i = 0, w = 0;
     bool in_rec = false;
     while (i < n) {
@@ -142,7 +149,6 @@ bool fasta_load_flat(const std::string& path, std::vector<std::string>& names, s
         i = le + 1;
     }
     if (in_rec) off.push_back((int64_t)w);
-    munmap(m, n);
     return true;
 }
 
