@@ -52,12 +52,18 @@ enum { DL_ERR_CHAIN = 1, DL_ERR_RECORD = 2, DL_ERR_LONG = 4, DL_ERR_ORDER = 8 };
 // One walk per anchor interval: counts the records and writes their offsets into the interval's scratch range
 // (capacity = interval bytes / 36, a record being at least 4 + 32 bytes; range starts computed on the host).
 // A record only says how long it is, so the walk is a chain of dependent loads; one WARP per interval streams the
-// interval through shared memory in 4 KiB windows (coalesced 16-byte loads) and lane 0 follows the chain there: one
-// global round trip per ~12 records instead of one per record.
+// interval through shared memory in 4 KiB windows (16-byte cp.async copies, double-buffered: the window that follows is
+// in flight while lane 0 follows the chain through the current one): no global round trip on the chain at all, where the
+// first version paid one per record and the second one per window.
 constexpr int kWalkWin = 4096, kWalkWarps = 4;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __global__ void __launch_bounds__(kWalkWarps * 32) k_rec_walk(const uint8_t* U, int64_t total, const int64_t* anchors, const int64_t* cap_base, int32_t n_int,
                                                              int32_t* cnt, int64_t* scratch, int32_t* err) {
-    __shared__ __align__(16) uint8_t win[kWalkWarps][kWalkWin + 16];
+    __shared__ __align__(16) uint8_t win[kWalkWarps][2][kWalkWin + 16];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int32_t i = (int32_t)(blockIdx.x * kWalkWarps + wid);
     if (i >= n_int) return;
@@ -66,19 +72,28 @@ __global__ void __launch_bounds__(kWalkWarps * 32) k_rec_walk(const uint8_t* U, 
     int32_t n = 0;
     int64_t* out = scratch + cap_base[i];
     const int64_t cap = cap_base[i + 1] - cap_base[i];
-    uint8_t* w = win[wid];
     bool bad = false;
-    while (off < end && !bad) {
-        const int64_t base = off & ~(int64_t)15;                        // U comes from cudaMalloc: 16-byte aligned windows
-        for (int k = lane; k < kWalkWin / 16; k += 32) {
-            const int64_t a = base + 16 * k;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (a + 16 <= total + 16) v = *(const uint4*)(U + a);       // the inflate buffer has 16 bytes of slack
-            *(uint4*)(w + 16 * k) = v;
+    // a window holds the kWalkWin + 16 bytes from `b` on (U comes from the allocator: 16-byte aligned windows; the inflate
+    // buffer has 16 bytes of slack; chunks past it read as zeros)
+    auto fetch = [&](int buf, int64_t b) {
+        uint8_t* w = win[wid][buf];
+        for (int k = lane; k < (kWalkWin + 16) / 16; k += 32) {
+            const int64_t a = b + 16 * k;
+            if (a + 16 <= total + 16) cp_async16(w + 16 * k, U + a);
+            else *(uint4*)(w + 16 * k) = make_uint4(0u, 0u, 0u, 0u);
         }
+        cp_async_commit();
+    };
+    int64_t base = off & ~(int64_t)15;
+    int cur = 0;
+    if (off < end) fetch(0, base);
+    while (off < end && !bad) {
+        fetch(cur ^ 1, base + kWalkWin);                                // the window that follows, in flight during the walk
+        cp_async_wait<1>();                                             // the current window has landed
         __syncwarp();
         if (lane == 0) {
-            while (off < end && off + 4 <= base + kWalkWin) {
+            const uint8_t* w = win[wid][cur];
+            while (off < end && off + 4 <= base + kWalkWin + 16) {
                 if (off + 4 > total) { bad = true; break; }
                 const uint8_t* p = w + (off - base);
                 const uint32_t bs = (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
@@ -89,8 +104,16 @@ __global__ void __launch_bounds__(kWalkWarps * 32) k_rec_walk(const uint8_t* U, 
         }
         off = __shfl_sync(0xffffffffu, off, 0);
         bad = __shfl_sync(0xffffffffu, (int)bad, 0) != 0;
-        __syncwarp();
+        const int64_t nb = base + kWalkWin;
+        if (off + 4 <= nb + kWalkWin + 16) { base = nb; cur ^= 1; }     // the chain continues inside the prefetched window
+        else {                                                          // a record longer than a window: start over at its end
+            cp_async_wait<0>();
+            __syncwarp();
+            base = off & ~(int64_t)15;
+            if (off < end && !bad) fetch(cur, base);
+        }
     }
+    cp_async_wait<0>();
     if (lane == 0) {
         if (bad || off != end) atomicOr(err, DL_ERR_CHAIN);
         cnt[i] = n;
@@ -165,70 +188,118 @@ struct PackArgs {
     const int32_t *keep, *kidx, *uoff, *quoff, *qunits, *slot; const uint8_t* enc;
     uint32_t* rec_off; uint8_t* rec; uint32_t* qual_off; uint8_t* qual;
     int32_t* slot_count; int32_t n_keep, total_units, total_qunits;
+    int64_t u_bytes;            // inflated bytes in U (the buffer has 16 more)
 };
-// One WARP per record (round 2; one thread per record with byte loops ran at 1.1 ms per 5 Mb shard because neighbouring
-// threads walked different 280-byte records): the lanes read and write consecutive bytes, so every access of the warp is
-// one or two sectors; a warp handles records r, r + warps, ... of the grid.
-constexpr int kPackWarps = 8;
+// One WARP per record, 32 records per warp and round (round 2; one thread per record with byte loops ran at 1.1 ms per
+// 5 Mb shard because neighbouring threads walked different 280-byte records).  ncu on the first warp-per-record builds
+// showed the kernel waiting on chains of small dependent loads (long-scoreboard stalls 23 per issue, 390 GB/s): eight
+// per-record scalars, then the header byte, CIGAR, bases, qualities, each its own 32-byte request.  So
+//   * the per-record scalars of 32 consecutive records are loaded at once, one record per lane (coalesced), and handed
+//     round by shuffles; the offset tables and the per-contig counts are written from that form, too;
+//   * a record is staged in shared memory with ONE request of 16 bytes per lane (512 bytes; longer records take a second
+//     round or, beyond the staging size, are read in place), and the request for the NEXT record is issued before the
+//     current one is processed;
+//   * from the staged copy the lanes write consecutive output bytes.
+constexpr int kPackWarps = 8, kPackStage = 1024;
+struct PackRec { int64_t start; int32_t uoff, quoff, qunits; uint32_t enc; };
+__device__ __forceinline__ void pack_one(const PackArgs& a, const PackRec& m, const uint8_t* p, int lane) {
+    // the fixed 32-byte part of the record: one byte per lane, fields through shuffles
+    const uint32_t hb = p[lane];
+    const uint32_t l_name = __shfl_sync(0xffffffffu, hb, 8);
+    const uint32_t n_cigar = __shfl_sync(0xffffffffu, hb, 12) | __shfl_sync(0xffffffffu, hb, 13) << 8;
+    const int32_t l_seq = (int32_t)(__shfl_sync(0xffffffffu, hb, 16) | __shfl_sync(0xffffffffu, hb, 17) << 8 |
+                                    __shfl_sync(0xffffffffu, hb, 18) << 16 | __shfl_sync(0xffffffffu, hb, 19) << 24);
+    uint8_t* __restrict__ d = a.rec + (size_t)m.uoff * 16;
+    // header: pos, flag, mapq, enc, isize, l_qseq, n_cigar (include/nextpolish_b200.h): byte i of the packed header
+    // comes from byte src[i] of the BAM record (0xff: not a copy)
+    {
+        const uint64_t src_lo = 0xff090f0e07060504ull, src_hi = 0x0d0cffff1f1e1d1cull;     // d[0..7], d[8..15]
+        const uint32_t sidx = lane < 16 ? (uint32_t)(((lane < 8 ? src_lo : src_hi) >> (8 * (lane & 7))) & 0xffu) : 0u;
+        uint32_t v = __shfl_sync(0xffffffffu, hb, (int)(sidx & 31u));
+        if (lane == 7) v = m.enc;
+        if (lane == 12) v = (uint32_t)l_seq & 0xffu;
+        if (lane == 13) v = ((uint32_t)l_seq >> 8) & 0xffu;
+        if (lane < 16) d[lane] = (uint8_t)v;
+    }
+    const uint8_t* cig = p + 32 + l_name;
+    for (uint32_t i = (uint32_t)lane; i < 4 * n_cigar; i += 32) d[16 + i] = cig[i];
+    const uint8_t* seq = cig + 4 * n_cigar;
+    uint8_t* __restrict__ ds = d + 16 + 4 * n_cigar;
+    if (!m.enc) { for (int32_t i = lane; i < (l_seq + 1) / 2; i += 32) ds[i] = seq[i]; }
+    else {
+        // four bases (two 4-bit bytes) -> one 2-bit byte; bases past l_seq contribute zero bits
+        for (int32_t bq = lane; bq < (l_seq + 3) / 4; bq += 32) {
+            const uint32_t b0 = seq[2 * bq], b1 = 4 * bq + 2 < l_seq ? seq[2 * bq + 1] : 0u;
+            uint32_t o = 0;
+            #pragma unroll
+            for (int32_t j = 0; j < 4; j++) {
+                const uint32_t c = ((j < 2 ? b0 : b1) >> ((~j & 1) << 2)) & 0xfu;
+                const uint32_t two = c == 1 ? 0u : c == 2 ? 1u : c == 4 ? 2u : 3u;
+                if (4 * bq + j < l_seq) o |= two << (6 - 2 * j);
+            }
+            ds[bq] = (uint8_t)o;
+        }
+    }
+    if (a.qual_off && m.qunits) {
+        const uint8_t* q = seq + (l_seq + 1) / 2;
+        uint8_t* __restrict__ dq = a.qual + (size_t)m.quoff * 16;
+        for (int32_t i = lane; i < l_seq; i += 32) dq[i] = q[i];
+    }
+}
 __global__ void __launch_bounds__(kPackWarps * 32) k_rec_pack(PackArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int32_t w0 = (int32_t)(blockIdx.x * kPackWarps + (threadIdx.x >> 5)), nw = (int32_t)(gridDim.x * kPackWarps);
+    __shared__ __align__(16) uint8_t stage[kPackWarps][kPackStage];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int32_t w0 = (int32_t)(blockIdx.x * kPackWarps + wid), nw = (int32_t)(gridDim.x * kPackWarps);
     if (w0 == 0 && lane == 0) {     // closing entries of the offset arrays
         a.rec_off[a.n_keep] = (uint32_t)a.total_units;
         if (a.qual_off) a.qual_off[a.n_keep] = (uint32_t)a.total_qunits;
     }
-    for (int32_t r = w0; r < a.n_rec; r += nw) {
-        if (!a.keep[r]) continue;
-        const int32_t k = a.kidx[r];
-        const uint8_t* p = a.U + a.rec_start[r] + 4;
-        // the fixed 32-byte part of the record: one byte per lane, fields through shuffles
-        const uint32_t hb = p[lane];
-        const uint32_t l_name = __shfl_sync(0xffffffffu, hb, 8);
-        const uint32_t n_cigar = __shfl_sync(0xffffffffu, hb, 12) | __shfl_sync(0xffffffffu, hb, 13) << 8;
-        const int32_t l_seq = (int32_t)(__shfl_sync(0xffffffffu, hb, 16) | __shfl_sync(0xffffffffu, hb, 17) << 8 |
-                                        __shfl_sync(0xffffffffu, hb, 18) << 16 | __shfl_sync(0xffffffffu, hb, 19) << 24);
-        const uint32_t enc = a.enc[r];
-        uint8_t* d = a.rec + (size_t)a.uoff[r] * 16;
-        // header: pos, flag, mapq, enc, isize, l_qseq, n_cigar (include/nextpolish_b200.h): byte i of the packed header
-        // comes from byte src[i] of the BAM record (0xff: not a copy)
-        {
-            const uint64_t src_lo = 0xff090f0e07060504ull, src_hi = 0x0d0cffff1f1e1d1cull;     // d[0..7], d[8..15]
-            const uint32_t sidx = lane < 16 ? (uint32_t)(((lane < 8 ? src_lo : src_hi) >> (8 * (lane & 7))) & 0xffu) : 0u;
-            uint32_t v = __shfl_sync(0xffffffffu, hb, (int)(sidx & 31u));
-            if (lane == 7) v = enc;
-            if (lane == 12) v = (uint32_t)l_seq & 0xffu;
-            if (lane == 13) v = ((uint32_t)l_seq >> 8) & 0xffu;
-            if (lane < 16) d[lane] = (uint8_t)v;
-            if (lane == 0) a.rec_off[k] = (uint32_t)a.uoff[r];
+    uint8_t* st = stage[wid];
+    // the first 512 bytes from the 16-byte boundary at or before a record (the inflate buffer has 16 bytes of slack)
+    auto head = [&](int64_t start) {
+        const int64_t at = (start & ~(int64_t)15) + 16 * lane;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (at + 16 <= a.u_bytes + 16) v = *(const uint4*)(a.U + at);
+        return v;
+    };
+    for (int32_t c = w0; (int64_t)c * 32 < a.n_rec; c += nw) {
+        // this lane's record of the round: its scalars, its entries of the offset tables, its contig's count
+        const int32_t r = c * 32 + lane;
+        const bool mine = r < a.n_rec && a.keep[r];
+        PackRec m{0, 0, 0, 0, 0u};
+        if (mine) {
+            m.start = a.rec_start[r]; m.uoff = a.uoff[r]; m.enc = a.enc[r];
+            const int32_t k = a.kidx[r];
+            a.rec_off[k] = (uint32_t)m.uoff;
+            if (a.qual_off) { m.quoff = a.quoff[r]; m.qunits = a.qunits[r]; a.qual_off[k] = (uint32_t)m.quoff; }
+            atomicAdd(&a.slot_count[a.slot[r]], 1);
         }
-        const uint8_t* cig = p + 32 + l_name;
-        for (uint32_t i = (uint32_t)lane; i < 4 * n_cigar; i += 32) d[16 + i] = cig[i];
-        const uint8_t* seq = cig + 4 * n_cigar;
-        uint8_t* ds = d + 16 + 4 * n_cigar;
-        if (!enc) { for (int32_t i = lane; i < (l_seq + 1) / 2; i += 32) ds[i] = seq[i]; }
-        else {
-            // four bases (two 4-bit bytes) -> one 2-bit byte; bases past l_seq contribute zero bits
-            for (int32_t bq = lane; bq < (l_seq + 3) / 4; bq += 32) {
-                const uint32_t b0 = seq[2 * bq], b1 = 4 * bq + 2 < l_seq ? seq[2 * bq + 1] : 0u;
-                uint32_t o = 0;
-                #pragma unroll
-                for (int32_t j = 0; j < 4; j++) {
-                    const uint32_t c = ((j < 2 ? b0 : b1) >> ((~j & 1) << 2)) & 0xfu;
-                    const uint32_t two = c == 1 ? 0u : c == 2 ? 1u : c == 4 ? 2u : 3u;
-                    if (4 * bq + j < l_seq) o |= two << (6 - 2 * j);
+        uint32_t todo = __ballot_sync(0xffffffffu, mine);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (todo) v = head(__shfl_sync(0xffffffffu, m.start, __ffs((int)todo) - 1));
+        while (todo) {
+            const int j = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            PackRec x;
+            x.start = __shfl_sync(0xffffffffu, m.start, j); x.uoff = __shfl_sync(0xffffffffu, m.uoff, j);
+            x.quoff = __shfl_sync(0xffffffffu, m.quoff, j); x.qunits = __shfl_sync(0xffffffffu, m.qunits, j);
+            x.enc = __shfl_sync(0xffffffffu, m.enc, j);
+            *(uint4*)(st + 16 * lane) = v;
+            __syncwarp();
+            if (todo) v = head(__shfl_sync(0xffffffffu, m.start, __ffs((int)todo) - 1));       // the next record's bytes: in flight from here
+            const int64_t base = x.start & ~(int64_t)15;
+            const uint8_t* q = st + (int32_t)(x.start - base);
+            const int32_t need = (int32_t)(x.start - base) + 4 + (int32_t)((uint32_t)q[0] | (uint32_t)q[1] << 8 | (uint32_t)q[2] << 16 | (uint32_t)q[3] << 24);
+            if (need <= kPackStage) {
+                // a record's bytes never end later than the buffer's: chunks that start at or past `need` are not loaded
+                if (need > 512) {
+                    if (512 + 16 * lane < need) *(uint4*)(st + 512 + 16 * lane) = *(const uint4*)(a.U + base + 512 + 16 * lane);
+                    __syncwarp();
                 }
-                ds[bq] = (uint8_t)o;
-            }
+                pack_one(a, x, q + 4, lane);
+            } else pack_one(a, x, a.U + x.start + 4, lane);        // a long record: read in place
+            __syncwarp();                                            // the staging buffer is reused by the next record
         }
-        if (a.qual_off) {
-            if (lane == 0) a.qual_off[k] = (uint32_t)a.quoff[r];
-            if (a.qunits[r]) {
-                const uint8_t* q = seq + (l_seq + 1) / 2;
-                uint8_t* dq = a.qual + (size_t)a.quoff[r] * 16;
-                for (int32_t i = lane; i < l_seq; i += 32) dq[i] = q[i];
-            }
-        }
-        if (lane == 0) atomicAdd(&a.slot_count[a.slot[r]], 1);
     }
 }
 __global__ void k_lower_flags(const uint8_t* seq, int64_t n, int32_t* f) {
@@ -615,11 +686,11 @@ static np_dev_shard* load_gpu_impl(int32_t device, const char* fasta, const char
     if (with_qual) cudaMemsetAsync(S->qual.p, 0, (size_t)S->qual_bytes + 16, st);
     PackArgs pa{U.as<uint8_t>(), d_start.as<int64_t>(), n_rec, d_keep.as<int32_t>(), d_kidx.as<int32_t>(), d_uoff.as<int32_t>(), d_quoff.as<int32_t>(),
                 d_qunits.as<int32_t>(), d_slot.as<int32_t>(), d_enc.as<uint8_t>(), S->rec_off.as<uint32_t>(), S->rec.as<uint8_t>(),
-                with_qual ? S->qual_off.as<uint32_t>() : nullptr, with_qual ? S->qual.as<uint8_t>() : nullptr, d_scount.as<int32_t>(), n_keep, tot[1], tot[2]};
+                with_qual ? S->qual_off.as<uint32_t>() : nullptr, with_qual ? S->qual.as<uint8_t>() : nullptr, d_scount.as<int32_t>(), n_keep, tot[1], tot[2], total};
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        const int want = (n_rec + kPackWarps - 1) / kPackWarps, cap = sms * 16;          // resident CTAs: 8 per SM, two rounds
+        const int want = (n_rec + 32 * kPackWarps - 1) / (32 * kPackWarps), cap = sms * 16;   // 32 records per warp and round
         k_rec_pack<<<std::max(1, std::min(want, cap)), kPackWarps * 32, 0, st>>>(pa);
     }
     std::vector<int32_t> counts((size_t)n_slots + 1, 0);
