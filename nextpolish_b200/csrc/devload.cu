@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32) k_rec_walk(const uint8_t* U, 
         }
         off = __shfl_sync(0xffffffffu, off, 0);
         bad = __shfl_sync(0xffffffffu, (int)bad, 0) != 0;
+        __syncwarp();                                                   // lane 0's reads of this window come before the next fetch into it
         const int64_t nb = base + kWalkWin;
         if (off + 4 <= nb + kWalkWin + 16) { base = nb; cur ^= 1; }     // the chain continues inside the prefetched window
         else {                                                          // a record longer than a window: start over at its end
