@@ -197,3 +197,27 @@ def test_emulated_region_lists_literal_walk(E, oracle, emu_general_slices, case,
     cfg.contents.read_tlen = 1750
     want = run_checker(oracle.np_oracle_run, sh, task, cfg)
     assert run_checker(emu_general_slices.np_emu_run, sh, task, cfg, (None,)) == want
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_emulated_region_merge_mutated_thresholds(E, oracle, emu, seed):
+    """Task 2 / 4 with the thresholds that shape the region lists mutated (ext_len_edge = 0 makes one-base regions whose
+    first pair the literal contig_merge_region compares with itself: the flat merge must detect the shape and hand over
+    to the per-contig walk) and lowercase densities from sparse to 40 %: emulated kernels vs the oracle."""
+    import random
+    rng = random.Random(1000 + seed)
+    p = dict(seed=900 + seed, n_contigs=rng.choice([1, 2, 5]), contig_len=rng.choice([3000, 20000]), depth=rng.choice([8.0, 30.0]),
+             lowercase_frac=rng.choice([0.002, 0.02, 0.1, 0.4]), draft_indel=rng.choice([0, 0.01]))
+    sh = E.Shard.synthetic(E.synth_params(**p), 0, p["n_contigs"], with_qual=1)
+    cfg = E.default_config(b"")
+    cfg.contents.read_tlen = 1750
+    cfg.contents.ext_len_edge = rng.choice([0, 0, 1, 2, 5])
+    cfg.contents.min_len_inter_kmer = rng.choice([0, 1, 5, 20])
+    cfg.contents.min_len_ldr = rng.choice([0, 1, 3, 10])
+    for task in (2, 4):
+        try:
+            want = run_checker(oracle.np_oracle_run, sh, task, cfg)
+        except Exception:
+            assert task == 4          # snp_valid on cut-point lists the reference itself leaves undefined (oracle returns -2)
+            continue
+        assert run_checker(emu.np_emu_run, sh, task, cfg, (None,)) == want, (task, p)
