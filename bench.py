@@ -6,12 +6,15 @@ reads per GPU; a "step" = one pass of every implemented task step (score_chain, 
 shard.  Weak scaling: every rank polishes its own shard of that shape (contigs are independent units,
 SURVEY.md 8e); after each task step the polished FASTA bytes are gathered to rank 0 with one NCCL collective.
 
-value        device-resident: packed shard already in HBM when the timed region starts
+value        device-resident: packed shards already in HBM when the timed region starts, polished through
+             np_resident_submit / np_resident_wait — several engines (stream + scratch + host thread each) work on
+             different shards at once; `resident.one_engine` is the same K steps on ONE engine and stream
 e2e          FROM THE FILES the reference reads: draft FASTA + BGZF BAM (+ .bai) in host memory (page cache) ->
              np_files_submit / np_files_wait (the pipelined form of what the drop-in score_chain()/kmer_count()
              and the native CLI do): compressed bytes host -> device, BGZF inflate + record unpack + packing on
              the GPU, polishing kernels, polished bytes device -> host.  This is what the reference arm does on
-             the CPU with the same files, so e2e / reference is an apples-to-apples ratio.
+             the CPU with the same files, so e2e / reference is an apples-to-apples ratio.  The pipeline is warmed
+             with 4 x workers untimed steps, then exactly K steps are timed (`wall_ms_at_quarters`: drift inside).
 e2e_packed   informational: the same step from pre-packed shards in pinned host memory (np_stream_*)
 roofline     the pileup-scan kernel = the kernel that streams the sorted read blocks against the draft (k_diff,
              "pileup_diff"): algorithmic bytes / its CUDA-event time on the engine stream, against
