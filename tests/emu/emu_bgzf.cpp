@@ -54,3 +54,24 @@ extern "C" int64_t np_emu_bai_record_starts(const char* bam, int32_t tid, uint64
     for (size_t i = 0; i < v.size() && (int64_t)i < cap; i++) out[i] = v[i];
     return (int64_t)v.size();
 }
+
+// fasta_load_flat (hostio.cpp; the draft reader of np_shard_load_gpu / np_multi) for the CPU test that compares it with an
+// independent parse: sequences concatenated into `seq`, their offsets in `off`, names joined by '\n' in `names`.
+extern "C" int64_t np_emu_fasta_flat(const char* path, uint8_t* seq, int64_t cap, int64_t* off, int32_t max_ctg, char* names,
+                                     int64_t names_cap, int32_t* n_ctg) {
+    struct Ctx { std::vector<uint8_t> buf; } ctx;
+    std::vector<std::string> nm;
+    std::vector<int64_t> o;
+    std::string err;
+    auto grow = [](void* c, size_t bytes) -> uint8_t* { auto* x = (Ctx*)c; if (x->buf.size() < bytes) x->buf.resize(bytes); return x->buf.data(); };
+    if (!np::fasta_load_flat(path, nm, o, grow, &ctx, err)) return -1;
+    *n_ctg = (int32_t)nm.size();
+    if ((int32_t)nm.size() > max_ctg || (nm.empty() ? 0 : o.back()) > cap) return -2;
+    for (size_t i = 0; i < o.size(); i++) off[i] = o[i];
+    if (!nm.empty() && o.back() > 0) memcpy(seq, ctx.buf.data(), (size_t)o.back());
+    std::string joined;
+    for (auto& s : nm) { joined += s; joined += '\n'; }
+    if ((int64_t)joined.size() + 1 > names_cap) return -3;
+    memcpy(names, joined.c_str(), joined.size() + 1);
+    return nm.empty() ? 0 : o.back();
+}
