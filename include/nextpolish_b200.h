@@ -328,10 +328,38 @@ int32_t   np_files_wait(np_files* p, int64_t ticket, np_files_result* out);
 typedef struct np_multi np_multi;
 np_multi* np_multi_create(const int32_t* devices, int32_t n_devices);
 int32_t   np_multi_run(np_multi* m, int32_t task, const char* fasta, const char* bam, const Configure* cfg, np_files_result* out);
+/* the same run restricted to the contigs `names` (a worker's block, nextpolish1.py -b/-i :148-161); n_names < 0 = all.
+ * A name the draft does not hold is NP_ERR_ARG.  The result lists the selected contigs in FASTA order. */
+int32_t   np_multi_run_names(np_multi* m, int32_t task, const char* fasta, const char* bam, const Configure* cfg,
+                             const char* const* names, int32_t n_names, np_files_result* out);
 void      np_multi_destroy(np_multi* m);
 /* part[i] = block (0 .. n_parts-1) of contig i: contiguous blocks with balanced cumulative length */
 void      np_partition_contiguous(const int64_t* lengths, int32_t n_contigs, int32_t n_parts, int32_t* part);
 int32_t   np_engine_result_offsets(np_engine* e, int64_t* out_off);
+
+
+/* ---- the worker's file conventions either side of the path (host only, no GPU needed) --------------
+ * Which contigs one worker job polishes and where its output part resumes — nextpolish1.py:148-179,203-210:
+ *   block == NULL / "" or index == NULL / "all": every header of `genome`; otherwise the lines "name<TAB>index" of the
+ *   block file (written by the driver, source/nextPolish:93-117) whose index field equals `index`;
+ *   an existing out_path (not NULL / "stdout") is scanned: contigs of finished records are dropped from the plan, the
+ *   last record (possibly partial) is polished again and resume_offset is the byte offset at which it starts. */
+typedef struct np_part_plan np_part_plan;
+np_part_plan* np_part_plan_create(const char* genome, const char* block, const char* index, const char* out_path);
+void          np_part_plan_destroy(np_part_plan* p);
+int32_t       np_part_plan_count(const np_part_plan* p);            /* contigs still to polish                  */
+const char*   np_part_plan_name(const np_part_plan* p, int32_t i);  /* block-file (or FASTA) order              */
+int32_t       np_part_plan_finished(const np_part_plan* p);         /* finished contigs found in out_path       */
+int64_t       np_part_plan_resume_offset(const np_part_plan* p);
+/* record name of nextpolish1.py:227: name + "_np<task>", or name + "<task>" when its last '_' field starts with "np".
+ * Returns the length written, -1 when cap is too small. */
+int32_t       np_part_record_name(const char* name, int32_t task, char* out, int32_t cap);
+/* the output part: NULL / "stdout" = stdout; an existing file is cut at resume_offset and appended to; else created.
+ * np_part_write prints one record as nextpolish1.py:228 does: ">name_np<task> <len>\nSEQ\n" (uppercase != 0: -u). */
+typedef struct np_part_file np_part_file;
+np_part_file* np_part_open(const char* out_path, int64_t resume_offset);
+int32_t       np_part_write(np_part_file* f, const char* name, int32_t task, const uint8_t* seq, int64_t len, int32_t uppercase);
+int32_t       np_part_close(np_part_file* f);
 
 
 /* ---- seeded synthetic inputs (draft FASTA + coordinate-sorted BAM), for bench and tests -- */

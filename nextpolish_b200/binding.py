@@ -79,7 +79,9 @@ EXPORTS = [  # every symbol include/nextpolish_b200.h declares
     "np_stream_create", "np_stream_destroy", "np_stream_submit", "np_stream_wait", "np_stream_launch_count",
     "np_files_create", "np_files_destroy", "np_files_submit", "np_files_wait",
     "np_resident_create", "np_resident_destroy", "np_resident_submit", "np_resident_wait", "np_resident_launch_count", "np_engine_launch_total",
-    "np_multi_create", "np_multi_run", "np_multi_destroy", "np_partition_contiguous", "np_engine_result_offsets",
+    "np_multi_create", "np_multi_run", "np_multi_run_names", "np_multi_destroy", "np_partition_contiguous", "np_engine_result_offsets",
+    "np_part_plan_create", "np_part_plan_destroy", "np_part_plan_count", "np_part_plan_name", "np_part_plan_finished",
+    "np_part_plan_resume_offset", "np_part_record_name", "np_part_open", "np_part_write", "np_part_close",
 ]
 
 
@@ -176,11 +178,27 @@ def load(path=None):
     L.np_multi_create.argtypes = [vp, i32]
     L.np_multi_create.restype = vp
     L.np_multi_run.argtypes = [vp, i32, C.c_char_p, C.c_char_p, C.POINTER(Configure), C.POINTER(FilesResult)]
+    L.np_multi_run_names.argtypes = [vp, i32, C.c_char_p, C.c_char_p, C.POINTER(Configure), vp, i32, C.POINTER(FilesResult)]
     L.np_multi_destroy.argtypes = [vp]
     L.np_multi_destroy.restype = None
     L.np_partition_contiguous.argtypes = [vp, i32, i32, vp]
     L.np_partition_contiguous.restype = None
     L.np_engine_result_offsets.argtypes = [vp, vp]
+    L.np_part_plan_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
+    L.np_part_plan_create.restype = vp
+    L.np_part_plan_destroy.argtypes = [vp]
+    L.np_part_plan_destroy.restype = None
+    L.np_part_plan_count.argtypes = [vp]
+    L.np_part_plan_name.argtypes = [vp, i32]
+    L.np_part_plan_name.restype = C.c_char_p
+    L.np_part_plan_finished.argtypes = [vp]
+    L.np_part_plan_resume_offset.argtypes = [vp]
+    L.np_part_plan_resume_offset.restype = i64
+    L.np_part_record_name.argtypes = [C.c_char_p, i32, C.c_char_p, i32]
+    L.np_part_open.argtypes = [C.c_char_p, i64]
+    L.np_part_open.restype = vp
+    L.np_part_write.argtypes = [vp, C.c_char_p, i32, C.c_char_p, i64, i32]
+    L.np_part_close.argtypes = [vp]
     L.np_synth_write.argtypes = [C.POINTER(SynthParams), C.c_char_p, C.c_char_p]
     L.np_synth_shard.argtypes = [C.POINTER(SynthParams), i32, i32, i32, i32]
     L.np_synth_shard.restype = vp

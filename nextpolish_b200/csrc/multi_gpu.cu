@@ -160,7 +160,15 @@ void np_partition_contiguous(const int64_t* lengths, int32_t n_contigs, int32_t 
 }
 
 int32_t np_multi_run(np_multi* m, int32_t task, const char* fasta, const char* bam, const Configure* cfg, np_files_result* out) {
-    if (!m || !fasta || !bam || !cfg || !out) { np::set_error("np_multi_run: bad arguments"); return NP_ERR_ARG; }
+    return np_multi_run_names(m, task, fasta, bam, cfg, nullptr, -1, out);
+}
+
+// The same run restricted to the contigs `names` (a worker's block: nextpolish1.py -b/-i, :148-161); n_names < 0: every
+// contig of the draft.  Names the draft does not hold are an error (the reference dereferences NULL there).  The result
+// lists the selected contigs in FASTA order.
+int32_t np_multi_run_names(np_multi* m, int32_t task, const char* fasta, const char* bam, const Configure* cfg,
+                           const char* const* names, int32_t n_names, np_files_result* out) {
+    if (!m || !fasta || !bam || !cfg || !out || (n_names > 0 && !names)) { np::set_error("np_multi_run: bad arguments"); return NP_ERR_ARG; }
     const int n = (int)m->dev.size(), K = m->slots;
     std::string err;
     const double t0 = now_ms();
@@ -175,9 +183,23 @@ int32_t np_multi_run(np_multi* m, int32_t task, const char* fasta, const char* b
     if (!bf.open(bam, err)) { np::set_error("np_multi_run: " + err); return NP_ERR_IO; }
     std::unordered_map<std::string, int> tid_of;
     for (size_t i = 0; i < bf.header().names.size(); i++) tid_of.emplace(bf.header().names[i], (int)i);
-    const int32_t nc = (int32_t)fa_names.size();
-    std::vector<int32_t> order((size_t)nc);
-    for (int32_t i = 0; i < nc; i++) order[(size_t)i] = i;
+    // sel: FASTA indices of the contigs to polish, in FASTA order; sel_pos: their position in the result
+    std::vector<int32_t> sel, sel_pos(fa_names.size(), -1);
+    if (n_names < 0) { for (size_t i = 0; i < fa_names.size(); i++) sel.push_back((int32_t)i); }
+    else {
+        std::unordered_map<std::string, int32_t> fa_idx;
+        for (size_t i = 0; i < fa_names.size(); i++) fa_idx.emplace(fa_names[i], (int32_t)i);
+        std::vector<uint8_t> want(fa_names.size(), 0);
+        for (int32_t k = 0; k < n_names; k++) {
+            auto it = fa_idx.find(names[k] ? names[k] : "");
+            if (it == fa_idx.end()) { np::set_error(std::string("np_multi_run: contig not in the draft: ") + (names[k] ? names[k] : "(null)")); return NP_ERR_ARG; }
+            want[(size_t)it->second] = 1;
+        }
+        for (size_t i = 0; i < fa_names.size(); i++) if (want[i]) sel.push_back((int32_t)i);
+    }
+    for (size_t k = 0; k < sel.size(); k++) sel_pos[(size_t)sel[k]] = (int32_t)k;
+    const int32_t nc = (int32_t)sel.size();
+    std::vector<int32_t> order(sel);
     auto tid = [&](int32_t i) { auto it = tid_of.find(fa_names[(size_t)i]); return it == tid_of.end() ? 0x7fffffff : it->second; };
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return tid(a) < tid(b); });
     std::vector<int64_t> lens((size_t)nc);
@@ -321,7 +343,7 @@ int32_t np_multi_run(np_multi* m, int32_t task, const char* fasta, const char* b
     for (const Block& B : blocks)
         for (size_t i = 0; i < B.slot_rank.size(); i++) {
             // the loader reports, for every slot of the shard, its rank inside the name list it was given
-            const int32_t fr = B.rank[(size_t)B.slot_rank[i]];
+            const int32_t fr = sel_pos[(size_t)B.rank[(size_t)B.slot_rank[i]]];
             m->names[(size_t)fr] = B.slot_name[i];
             m->start[(size_t)fr] = goff[(size_t)B.gpu] + B.off + B.ctg_off[i];
             m->len[(size_t)fr] = B.ctg_off[i + 1] - B.ctg_off[i];

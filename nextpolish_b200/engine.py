@@ -273,11 +273,15 @@ class MultiGpu:
         if not self.h:
             raise NativeError(last_error())
 
-    def polish(self, task, fasta, bam, cfg):
-        """-> ({name: polished bytes} in FASTA order, stats dict)"""
+    def polish(self, task, fasta, bam, cfg, names=None):
+        """-> ({name: polished bytes} in FASTA order, stats dict); names: only these contigs (a worker's block)"""
         from .binding import FilesResult
         r = FilesResult()
-        rc = lib().np_multi_run(self.h, task, fasta.encode(), bam.encode(), cfg, C.byref(r))
+        if names is None:
+            rc = lib().np_multi_run(self.h, task, fasta.encode(), bam.encode(), cfg, C.byref(r))
+        else:
+            arr = (C.c_char_p * max(1, len(names)))(*[n.encode() for n in names])
+            rc = lib().np_multi_run_names(self.h, task, fasta.encode(), bam.encode(), cfg, arr, len(names), C.byref(r))
         if rc != 0:
             raise NativeError("rc=%d: %s" % (rc, last_error()))
         seqs = {r.names[i].decode(): C.string_at(r.seq + r.start[i], r.len[i]) for i in range(r.n_contigs)}
