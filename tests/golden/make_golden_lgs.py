@@ -1,0 +1,155 @@
+#!/usr/bin/env python
+"""Mint the long-read (nextpolish2) fixtures from the reference itself.  Run in the build container, after
+`make -C oracle ref ref2` (oracle/_ref/minimap2, samtools, nextpolish2.so, libnp2_refshim.so).
+
+  lgs_td_windows.npz   two windows of the reference's own source/test_data: lreads.fasta.gz mapped onto raw.genome.fasta
+                       with the vendored minimap2 (-ax map-ont, what the reference's driver runs for lgs reads,
+                       source/nextPolish:199-211), alignments written out as gapped strings clipped to the window
+  lgs_golden.json      (a) whole-path record: md5 / length of ctg_cns_core's output (nextpolish2.so, read type ont) for
+                       both test_data contigs on that BAM — the target of the rows still to build;
+                       (b) first pass (np2_ref_first_pass = get_cns_from_align_tags(fast) of the unmodified ctg_cns.c):
+                       md5 of the position list and of the base string for every seeded case of tests/lgs_cases.py under
+                       all four read types, and for the two test_data windows.
+"""
+import ctypes as C
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.realpath(__file__))))
+REF = os.path.join(ROOT, "oracle", "_ref")
+TD = "/root/reference/source/test_data"
+OUT = os.path.dirname(os.path.realpath(__file__))
+sys.path.insert(0, ROOT)
+from tests import lgs_cases as L  # noqa: E402
+
+WINDOWS = [("tig0000001", 10000, 16000), ("tig0000002", 30000, 35000)]
+
+
+def read_fa(path):
+    d, name = {}, None
+    for line in open(path):
+        if line.startswith(">"):
+            name = line[1:].split()[0]
+            d[name] = []
+        elif name:
+            d[name].append(line.strip())
+    return {k: "".join(v) for k, v in d.items()}
+
+
+def window_alignments(bam, draft, ctg, ws, we):
+    """[(aln_t_s, t_str, q_str)] clipped to [ws, we), BAM order, the window against itself first."""
+    alns = [(0, draft[ws:we], draft[ws:we])]
+    txt = subprocess.run([os.path.join(REF, "samtools"), "view", "-F", "0x904", bam, "%s:%d-%d" % (ctg, ws + 1, we)],
+                         stdout=subprocess.PIPE, check=True).stdout.decode()
+    for line in txt.split("\n"):
+        if not line:
+            continue
+        f = line.split("\t")
+        pos, cigar, seq = int(f[3]) - 1, f[5], f[9]
+        t, q, cols = [], [], []          # cols: target position of every column (insert columns carry the position before)
+        rp, qp = pos, 0
+        for n, op in re.findall(r"(\d+)([MIDNSHP=X])", cigar):
+            n = int(n)
+            if op in "M=X":
+                for k in range(n):
+                    t.append(draft[rp + k]), q.append(seq[qp + k]), cols.append(rp + k)
+                rp += n
+                qp += n
+            elif op == "I":
+                for k in range(n):
+                    t.append("-"), q.append(seq[qp + k]), cols.append(rp - 1)
+                qp += n
+            elif op == "D":
+                for k in range(n):
+                    t.append(draft[rp + k]), q.append("-"), cols.append(rp + k)
+                rp += n
+            elif op == "S":
+                qp += n
+        # clip to the window; first and last column must be match columns (the reference anchors alignments on exact
+        # 8-mers, get_align_shift ctg_cns.c:139)
+        idx = [i for i in range(len(t)) if ws <= cols[i] < we]
+        while idx and not (t[idx[0]] != "-" and q[idx[0]] != "-"):
+            idx.pop(0)
+        while idx and not (t[idx[-1]] != "-" and q[idx[-1]] != "-"):
+            idx.pop()
+        if len(idx) < 50:
+            continue
+        a, b = idx[0], idx[-1] + 1
+        alns.append((cols[a] - ws, "".join(t[a:b]), "".join(q[a:b])))
+    return alns
+
+
+def md5s(res):
+    pos, base = res
+    return {"n": len(base), "pos_md5": hashlib.md5(pos.astype("<u4").tobytes()).hexdigest(), "base_md5": hashlib.md5(base).hexdigest()}
+
+
+def main():
+    tmp = tempfile.mkdtemp(prefix="npgold_lgs")
+    bam = os.path.join(tmp, "lgs.sort.bam")
+    subprocess.check_call(f"{REF}/minimap2 -ax map-ont -t 1 {TD}/raw.genome.fasta {TD}/lreads.fasta.gz 2>/dev/null | "
+                          f"{REF}/samtools view -b -F 0x4 - | {REF}/samtools sort -o {bam} - 2>/dev/null && {REF}/samtools index {bam}",
+                          shell=True, executable="/bin/bash")
+    draft = read_fa(os.path.join(TD, "raw.genome.fasta"))
+    gold = {"whole_path": {}, "first_pass": {}}
+    # (a) the whole path through the reference's own boundary (nextpolish2.py:54-65)
+    class CT(C.Structure):
+        _fields_ = [("len", C.c_uint), ("identity", C.c_float), ("seq", C.c_char_p)]
+
+    class CTD(C.Structure):
+        _fields_ = [("data", C.POINTER(CT)), ("i_m", C.c_int)]
+
+    class REFT(C.Structure):
+        _fields_ = [("n", C.c_char_p), ("s", C.POINTER(C.c_uint32)), ("qv", C.c_void_p), ("qv_l", C.c_uint32), ("length", C.c_uint32)]
+
+    class REFS(C.Structure):
+        _fields_ = [("ref", C.POINTER(REFT)), ("i", C.c_uint32), ("i_m", C.c_uint32)]
+    P = C.CDLL(os.path.join(REF, "nextpolish2.so"))
+    P.read_ref.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int]
+    P.read_ref.restype = C.POINTER(REFS)
+    P.ctg_cns_init.argtypes = [C.c_int] * 3 + [C.c_float] * 3
+    P.ctg_cns_init.restype = C.c_void_p
+    P.ctg_cns_core.argtypes = [C.c_void_p, C.POINTER(REFT), C.c_char_p]
+    P.ctg_cns_core.restype = C.POINTER(CTD)
+    names = [n.encode() for n in draft]
+    lst = os.path.join(tmp, "lgs.list")
+    open(lst, "w").write(bam + "\n")
+    refs = P.read_ref(os.path.join(TD, "raw.genome.fasta").encode(), (C.c_char_p * len(names))(*names), len(names))
+    cfg = P.ctg_cns_init(5000000, 1, 1, 0.8, 0.8, 0.8)
+    for i in range(refs.contents.i):
+        r = P.ctg_cns_core(cfg, refs.contents.ref[i], lst.encode())
+        gold["whole_path"][refs.contents.ref[i].n.decode()] = [
+            {"len": r.contents.data[k].len, "md5": hashlib.md5(r.contents.data[k].seq).hexdigest()} for k in range(r.contents.i_m)]
+    # (b) the first pass
+    S = L.ref_shim()
+    packed = {}
+    for ctg, ws, we in WINDOWS:
+        alns = window_alignments(bam, draft[ctg], ctg, ws, we)
+        case = L.pack_case(alns, we - ws, 1)
+        key = "td_%s_%d_%d" % (ctg, ws, we)
+        for k in ("aln_t_s", "aln_len", "str_off"):
+            packed[key + "." + k] = case[k]
+        packed[key + ".t_str"] = np.frombuffer(case["t_str"], np.uint8)
+        packed[key + ".q_str"] = np.frombuffer(case["q_str"], np.uint8)
+        packed[key + ".len"] = np.array([we - ws], np.int64)
+        for rt in (1, 2, 3, 4):
+            case["read_type"] = rt
+            gold["first_pass"]["%s/rt%d" % (key, rt)] = md5s(L.first_pass_via(S.np2_ref_first_pass, case))
+    np.savez_compressed(os.path.join(OUT, "lgs_td_windows.npz"), **packed)
+    for name, kw in L.CASES.items():
+        for rt in (1, 2, 3, 4):
+            case = L.synthetic_case(**dict(kw, read_type=rt))
+            gold["first_pass"]["%s/rt%d" % (name, rt)] = md5s(L.first_pass_via(S.np2_ref_first_pass, case))
+    json.dump(gold, open(os.path.join(OUT, "lgs_golden.json"), "w"), indent=1, sort_keys=True)
+    print("wrote", len(gold["first_pass"]), "first-pass goldens;", gold["whole_path"])
+
+
+if __name__ == "__main__":
+    main()

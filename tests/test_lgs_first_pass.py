@@ -1,0 +1,105 @@
+"""First pass of the long-read consensus window (nextpolish2.so): the C restatement oracle/np2_oracle.c
+against the goldens minted from the reference (tests/golden/lgs_golden.json, make_golden_lgs.py) and, when oracle/_ref holds
+the stage door into the unmodified ctg_cns.c (libnp2_refshim.so), against the reference live on seeded fuzz inputs."""
+import ctypes as C
+import hashlib
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import lgs_cases as L
+from tests.conftest import GOLDEN, ROOT
+
+
+@pytest.fixture(scope="module")
+def O2():
+    path = os.path.join(ROOT, "oracle", "libnp2_oracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+    return C.CDLL(path)
+
+
+def td_windows():
+    z = np.load(os.path.join(GOLDEN, "lgs_td_windows.npz"))
+    keys = sorted({k.rsplit(".", 1)[0] for k in z.files})
+    out = {}
+    for k in keys:
+        out[k] = dict(len=int(z[k + ".len"][0]), read_type=1, min_cov=4, aln_t_s=z[k + ".aln_t_s"], aln_len=z[k + ".aln_len"],
+                      str_off=z[k + ".str_off"], t_str=z[k + ".t_str"].tobytes(), q_str=z[k + ".q_str"].tobytes())
+    return out
+
+
+def digest(res):
+    pos, base = res
+    return {"n": len(base), "pos_md5": hashlib.md5(pos.astype("<u4").tobytes()).hexdigest(), "base_md5": hashlib.md5(base).hexdigest()}
+
+
+def all_golden_cases():
+    for name, kw in L.CASES.items():
+        for rt in (1, 2, 3, 4):
+            yield "%s/rt%d" % (name, rt), (lambda kw=kw, rt=rt: L.synthetic_case(**dict(kw, read_type=rt)))
+    for key, case in td_windows().items():
+        for rt in (1, 2, 3, 4):
+            yield "%s/rt%d" % (key, rt), (lambda case=case, rt=rt: dict(case, read_type=rt))
+
+
+def test_oracle_matches_reference_goldens(O2):
+    gold = json.load(open(os.path.join(GOLDEN, "lgs_golden.json")))["first_pass"]
+    seen = 0
+    for key, make in all_golden_cases():
+        got = L.first_pass_via(O2.np2_oracle_first_pass, make())
+        assert not isinstance(got, int), (key, got)
+        assert digest(got) == gold[key], key
+        seen += 1
+    assert seen == len(gold) == 52
+
+
+def test_real_windows_look_like_consensus(O2):
+    """Sanity of the real-data fixture itself: ~6 kb windows at test_data depth, consensus within a few percent of the
+    window length, positions non-decreasing and covering the window."""
+    for key, case in td_windows().items():
+        pos, base = L.first_pass_via(O2.np2_oracle_first_pass, case)
+        assert len(case["aln_t_s"]) > 20
+        assert abs(len(base) - case["len"]) < 0.05 * case["len"]
+        assert (np.diff(pos.astype(np.int64)) >= 0).all() and pos[0] == 0 and pos[-1] == case["len"] - 1
+        assert set(base.upper()) <= set(b"ACGTN")
+
+
+@pytest.mark.skipif(L.ref_shim() is None, reason="oracle/_ref/libnp2_refshim.so not built (needs /root/reference)")
+def test_oracle_matches_live_reference_fuzz(O2):
+    S = L.ref_shim()
+    rng = random.Random(2024)
+    for it in range(120):
+        kw = dict(seed=rng.randrange(1 << 30), length=rng.choice([20, 60, 300, 1200]), depth=rng.choice([2, 5, 15, 40]),
+                  read_len=rng.choice([30, 100, 400]), sub=rng.choice([0.0, 0.02, 0.08]), ins=rng.choice([0.0, 0.03, 0.1]),
+                  dele=rng.choice([0.0, 0.03, 0.1]), read_type=rng.choice([1, 2, 3, 4]), min_cov=rng.choice([0, 4, 10]),
+                  long_ins=rng.choice([0, 0.003]), masked=rng.choice([0, 0, 0.02]), homopolymer=rng.random() < 0.3,
+                  odd_chars=rng.random() < 0.2)
+        case = L.synthetic_case(**kw)
+        want = L.first_pass_via(S.np2_ref_first_pass, case)
+        got = L.first_pass_via(O2.np2_oracle_first_pass, case)
+        assert not isinstance(want, int) and not isinstance(got, int), kw
+        assert (want[0] == got[0]).all() and want[1] == got[1], kw
+
+
+def test_oracle_error_codes_and_qv(O2):
+    case = L.synthetic_case(**L.CASES["ont30"])
+    cap = 8000
+    pos, base, qv = np.zeros(cap, np.uint32), np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+    f = O2.np2_oracle_first_pass_qv
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    args = lambda c, cap_: (c["read_type"], len(c["aln_t_s"]), c["aln_t_s"].ctypes.data, c["aln_len"].ctypes.data, c["str_off"].ctypes.data,
+                            c["t_str"], c["q_str"], c["len"], c["min_cov"], pos.ctypes.data, base.ctypes.data, qv.ctypes.data, cap_)
+    n = f(*args(case, cap))
+    assert n == 3000 and qv[:n].max() <= 100 and np.median(qv[:n]) > 60      # 100 * links / coverage of the chosen entry
+    assert f(*args(case, 10)) == -1                                           # output too small
+    short = dict(case, len=case["len"] + 50)                                  # nothing covers the last column
+    assert f(*args(short, cap)) == -2
+    cut = dict(case, len=case["len"] - 50)                                    # alignments leave the window
+    assert f(*args(cut, cap)) == -3
