@@ -1,0 +1,64 @@
+/* nextpolish2_b200.h — C ABI of the long-read consensus path (reference: nextpolish2.so, built from
+ * source/lib/ctg_cns.c, bound by source/lib/nextpolish2.py:54-65).
+ *
+ * STATUS: first slice.  What runs on the GPU is the FIRST PASS of a consensus window — tags, link tally, score chain and
+ * backtrack, i.e. what get_cns_from_align_tags (ctg_cns.c:1876) does up to and including the backtrack of
+ * generate_cns_from_best_score{,_fast} (:1475-1509, :1839-1857): np2_first_pass below, bit-identical to the reference
+ * (tests/test_lgs_first_pass.py, tests/test_zz_lgs_gpu.py).  The reference's own six entry points (read_ref, ctg_cns_init,
+ * ctg_cns_core, free_consensus_trimed_data, ctg_cns_destroy, refs_destroy — ctg_cns.c:2269,3355,3399,2151,3384,2195) are
+ * NOT exported yet: ctg_cns_core also needs the BAM merge / alignment-string stage in front (bsort.c, ctg_cns.c:2403) and
+ * the low-quality-region / POA stage behind (ctg_cns.c:822-1474, dag.c, align.c).  INTEGRATION.md shows where this call
+ * sits inside ctg_cns_core.
+ *
+ * Library: nextpolish_b200/lib/nextpolish2.so (sm_100a only, no CPU path: np2_engine_create fails without a GPU). */
+#ifndef NEXTPOLISH2_B200_H
+#define NEXTPOLISH2_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct np2_engine np2_engine;
+np2_engine* np2_engine_create(int32_t device);
+void        np2_engine_destroy(np2_engine* e);
+const char* np2_last_error(void);
+
+/* A batch of consensus windows (HOST pointers).  Window w is win_len[w] target positions long and owns the alignments
+ * [win_aln0[w], win_aln0[w + 1]), in the order of the reference's tags_list (BAM order; ctg_cns_core puts the window
+ * against itself first, ctg_cns.c:3456-3468).  Alignment i is the pair of gapped strings t_str / q_str
+ * [str_off[i], str_off[i] + aln_len[i]) — the alignment.t_aln_str / q_aln_str of ctg_cns.h:150-162 from aln->shift on:
+ * '-' = gap, 'M' = masked column — whose first column sits on window position aln_t_s[i] and is not a gap. */
+typedef struct {
+    int32_t         n_windows;
+    const int32_t*  win_len;       /* [n_windows]                                            */
+    const int32_t*  win_aln0;      /* [n_windows + 1]                                        */
+    int32_t         read_type;     /* 1 ont, 2 clr, 3 hifi, 4 rs (ctg_cns.c:23-26, -r of nextpolish2.py) */
+    int32_t         min_cov;       /* lower-case threshold; ctg_cns_core passes 4 (:3587)     */
+    const uint32_t* aln_t_s;       /* [n_alignments]                                         */
+    const uint32_t* aln_len;       /* [n_alignments] columns                                 */
+    const uint64_t* str_off;       /* [n_alignments]                                         */
+    const char*     t_str;         /* target (window) side of the alignments                 */
+    const char*     q_str;         /* read side                                              */
+    int64_t         str_bytes;
+} np2_window_batch;
+
+/* First pass of every window of the batch.  Outputs (host, capacity cap entries each): consensus bases in window order and,
+ * inside a window, in forward order: out_pos = window position of the base (sub-column bases repeat the position),
+ * out_base = the base, lower case where coverage <= min_cov (the rule of generate_cns_from_best_score_fast, :1492),
+ * out_qv (may be NULL) = 100 * links / coverage of the chosen link (:1840); out_off[n_windows + 1] = window offsets.
+ * Returns the total number of bases or: -1 cap too small, -2 a window whose last position has no node, -3 an alignment
+ * that is empty, starts on a gap column or leaves its window, -4 the backtrack ran into a node without links (the
+ * reference reads unallocated memory there), -5 a size limit (2^31 columns or alignment columns per batch, a 65535-long
+ * insertion), -6 CUDA failure (np2_last_error). */
+int64_t np2_first_pass(np2_engine* e, const np2_window_batch* batch, uint32_t* out_pos, char* out_base, uint8_t* out_qv,
+                       int64_t cap, int64_t* out_off);
+
+/* kernels launched by this engine so far / figures of the last call: [0] chain segments, [1] segments run again with their
+ * true cut score, [2] stitch iterations, [3] link records */
+int64_t np2_engine_launch_count(np2_engine* e);
+void    np2_engine_last_stats(np2_engine* e, int64_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEXTPOLISH2_B200_H */

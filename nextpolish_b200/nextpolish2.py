@@ -1,0 +1,111 @@
+"""Host-side handle of the long-read consensus path's first slice (include/nextpolish2_b200.h, csrc/lgs_consensus.cu;
+reference boundary: source/lib/nextpolish2.py:54-65 over nextpolish2.so).  Plumbing only: all compute is in
+nextpolish_b200/lib/nextpolish2.so, which has no CPU path.
+
+    eng = LgsEngine(device=0)
+    res = eng.first_pass(windows, read_type=1, min_cov=4)      # [(pos uint32[], base bytes, qv uint8[])] per window
+
+A window is a dict  len, aln_t_s uint32[n], aln_len uint32[n], str_off uint64[n], t_str bytes, q_str bytes  — the gapped
+alignment strings of the reads against the window, window against itself first (ctg_cns.c:3456-3468)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+LIB2_PATH = os.path.join(os.path.dirname(os.path.realpath(__file__)), "lib", "nextpolish2.so")
+EXPORTS2 = ["np2_engine_create", "np2_engine_destroy", "np2_last_error", "np2_first_pass", "np2_engine_launch_count",
+            "np2_engine_last_stats"]                     # every symbol include/nextpolish2_b200.h declares
+ERRORS = {-1: "output capacity too small", -2: "a window's last position has no node",
+          -3: "an alignment is empty, starts on a gap column or leaves its window",
+          -4: "backtrack through a node without links", -5: "size limit", -6: "CUDA failure"}
+
+
+class WindowBatch(C.Structure):  # np2_window_batch
+    _fields_ = [("n_windows", C.c_int32), ("win_len", C.c_void_p), ("win_aln0", C.c_void_p), ("read_type", C.c_int32),
+                ("min_cov", C.c_int32), ("aln_t_s", C.c_void_p), ("aln_len", C.c_void_p), ("str_off", C.c_void_p),
+                ("t_str", C.c_char_p), ("q_str", C.c_char_p), ("str_bytes", C.c_int64)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_LIB2 = None
+
+
+def lib2():
+    global _LIB2
+    if _LIB2 is None:
+        if not os.path.exists(LIB2_PATH):
+            raise OSError("%s is not built: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB2_PATH)
+        L = C.CDLL(LIB2_PATH)
+        L.np2_engine_create.argtypes = [C.c_int32]
+        L.np2_engine_create.restype = C.c_void_p
+        L.np2_engine_destroy.argtypes = [C.c_void_p]
+        L.np2_engine_destroy.restype = None
+        L.np2_last_error.restype = C.c_char_p
+        L.np2_first_pass.argtypes = [C.c_void_p, C.POINTER(WindowBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.np2_first_pass.restype = C.c_int64
+        L.np2_engine_launch_count.argtypes = [C.c_void_p]
+        L.np2_engine_launch_count.restype = C.c_int64
+        L.np2_engine_last_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.np2_engine_last_stats.restype = None
+        _LIB2 = L
+    return _LIB2
+
+
+def make_batch(windows, read_type, min_cov=4):
+    """Several windows as one np2_window_batch; returns (struct, keep-alive list of the arrays it points into)."""
+    win_len = np.array([w["len"] for w in windows], np.int32)
+    win_aln0 = np.zeros(len(windows) + 1, np.int32)
+    t_s, a_len, s_off, t_all, q_all, pos = [], [], [], [], [], 0
+    for i, w in enumerate(windows):
+        win_aln0[i + 1] = win_aln0[i] + len(w["aln_t_s"])
+        t_s.append(np.asarray(w["aln_t_s"], np.uint32)), a_len.append(np.asarray(w["aln_len"], np.uint32))
+        s_off.append(np.asarray(w["str_off"], np.uint64) + np.uint64(pos))
+        t_all.append(w["t_str"]), q_all.append(w["q_str"])
+        pos += len(w["t_str"])
+    cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs).astype(dt)) if xs else np.zeros(0, dt)
+    t_s, a_len, s_off = cat(t_s, np.uint32), cat(a_len, np.uint32), cat(s_off, np.uint64)
+    t_str, q_str = b"".join(t_all), b"".join(q_all)
+    b = WindowBatch(len(windows), win_len.ctypes.data, win_aln0.ctypes.data, read_type, min_cov, t_s.ctypes.data, a_len.ctypes.data,
+                    s_off.ctypes.data, t_str, q_str, len(t_str))
+    return b, [win_len, win_aln0, t_s, a_len, s_off, t_str, q_str]
+
+
+def split_result(n, pos, base, qv, off, n_windows):
+    return [(pos[off[i]:off[i + 1]].copy(), base[off[i]:off[i + 1]].tobytes(), qv[off[i]:off[i + 1]].copy()) for i in range(n_windows)]
+
+
+class LgsEngine:
+    def __init__(self, device=0):
+        self.h = lib2().np2_engine_create(device)
+        if not self.h:
+            raise NativeError(lib2().np2_last_error().decode(errors="replace"))
+
+    def first_pass(self, windows, read_type, min_cov=4):
+        b, keep = make_batch(windows, read_type, min_cov)
+        cap = sum(int(w["len"]) * 2 + int(np.asarray(w["aln_len"]).sum()) for w in windows) + 16
+        pos, base, qv = np.zeros(cap, np.uint32), np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+        off = np.zeros(len(windows) + 1, np.int64)
+        n = lib2().np2_first_pass(self.h, C.byref(b), pos.ctypes.data, base.ctypes.data, qv.ctypes.data, cap, off.ctypes.data)
+        del keep
+        if n < 0:
+            raise NativeError("np2_first_pass: %d (%s): %s" % (n, ERRORS.get(n, "?"), lib2().np2_last_error().decode(errors="replace")))
+        return split_result(n, pos, base, qv, off, len(windows))
+
+    def stats(self):
+        out = (C.c_int64 * 4)()
+        lib2().np2_engine_last_stats(self.h, out)
+        return dict(segments=out[0], reruns=out[1], stitch_iterations=out[2], link_records=out[3], launches=lib2().np2_engine_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            lib2().np2_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -25,12 +25,20 @@ CASES = {
     "hifi_masked": dict(seed=8, length=2000, depth=15, read_len=900, sub=0.003, ins=0.003, dele=0.003, read_type=3, masked=0.01),
     "clr_hp": dict(seed=9, length=2500, depth=35, read_len=800, sub=0.02, ins=0.05, dele=0.05, read_type=2, homopolymer=True),
     "ont_tiny": dict(seed=10, length=40, depth=6, read_len=30, sub=0.05, ins=0.05, dele=0.05, read_type=1),
+    "ont_zones": dict(seed=12, length=1500, depth=12, read_len=400, sub=0.5, ins=0.3, dele=0.3, read_type=1, zones=(5, 40)),
+    "clr_zones": dict(seed=13, length=1500, depth=8, read_len=300, sub=0.6, ins=0.3, dele=0.3, read_type=2, zones=(4, 30)),
+    "hifi_zones": dict(seed=14, length=1200, depth=6, read_len=300, sub=0.6, ins=0.2, dele=0.4, read_type=3, zones=(6, 50)),
+    "rs_zones": dict(seed=15, length=1200, depth=10, read_len=300, sub=0.5, ins=0.4, dele=0.3, read_type=4, zones=(5, 25)),
     "ont_lower_n": dict(seed=11, length=1500, depth=20, read_len=500, sub=0.03, ins=0.03, dele=0.03, read_type=1, odd_chars=True),
 }
 
 
 def synthetic_case(seed=1, length=3000, depth=30, read_len=900, sub=0.03, ins=0.02, dele=0.03, read_type=1, min_cov=4,
-                   long_ins=0.0, masked=0.0, homopolymer=False, odd_chars=False):
+                   long_ins=0.0, masked=0.0, homopolymer=False, odd_chars=False, zones=0):
+    """zones = (clean, dirty): the error rates (given very high) apply only to the last `dirty` of every clean + dirty
+    window positions, the others are error free: clean zones give the score chain its cut
+    columns, the dirty ones drive scores to the reference's clamp at 0 right behind a cut (the case in which a chain
+    segment cannot be computed relative to its cut and has to be run again with the true score)."""
     rng = random.Random(seed)
     if homopolymer:
         draft = []
@@ -47,7 +55,7 @@ def synthetic_case(seed=1, length=3000, depth=30, read_len=900, sub=0.03, ins=0.
         draft = "".join(d)
     alns = [(0, draft, draft)]
     n_reads = max(1, int(depth * length / read_len))
-    starts = sorted(rng.randrange(-read_len // 2, length - 8) for _ in range(n_reads))      # BAM order
+    starts = sorted(rng.randrange(-read_len // 2, max(length - 8, -read_len // 2 + 1)) for _ in range(n_reads))      # BAM order
     for s0 in starts:
         s = max(0, s0)
         e = min(length, s0 + int(read_len * rng.uniform(0.6, 1.4)))
@@ -56,7 +64,7 @@ def synthetic_case(seed=1, length=3000, depth=30, read_len=900, sub=0.03, ins=0.
         t, q = [], []
         p = s
         while p < e:
-            first_or_last = p == s or p == e - 1
+            first_or_last = p == s or p == e - 1 or (zones and p % (zones[0] + zones[1]) < zones[0])
             r = rng.random()
             if not first_or_last and masked and r < masked:
                 run = min(rng.randrange(1, 12), e - 1 - p)
@@ -115,3 +123,37 @@ def first_pass_via(fn, case):
 
 def ref_shim():
     return C.CDLL(REF_SHIM) if os.path.exists(REF_SHIM) else None
+
+
+def make_batch(cases):
+    from nextpolish_b200.nextpolish2 import make_batch as mk
+    return mk(cases, cases[0]["read_type"] if cases else 1, cases[0]["min_cov"] if cases else 4)
+
+
+def first_pass_batch(call, cases):
+    """call(batch_ptr, out_pos, out_base, out_qv, cap, out_off) -> total; returns per-window [(pos, base, qv)] or the code."""
+    b, keep = make_batch(cases)
+    cap = sum(int(c["len"]) * 3 + int(c["aln_len"].sum()) for c in cases) + 16
+    pos, base, qv = np.zeros(cap, np.uint32), np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+    off = np.zeros(len(cases) + 1, np.int64)
+    n = call(C.byref(b), pos.ctypes.data, base.ctypes.data, qv.ctypes.data, cap, off.ctypes.data)
+    del keep
+    if n < 0:
+        return n
+    assert off[-1] == n
+    return [(pos[off[i]:off[i + 1]].copy(), base[off[i]:off[i + 1]].tobytes(), qv[off[i]:off[i + 1]].copy()) for i in range(len(cases))]
+
+
+def oracle_window(O2, case):
+    """(pos, base, qv) of the C restatement, or its negative code."""
+    cap = int(case["len"]) * 3 + int(case["aln_len"].sum()) + 16
+    pos, base, qv = np.zeros(cap, np.uint32), np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+    f = O2.np2_oracle_first_pass_qv
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    n = f(case["read_type"], len(case["aln_t_s"]), case["aln_t_s"].ctypes.data, case["aln_len"].ctypes.data, case["str_off"].ctypes.data,
+          case["t_str"], case["q_str"], case["len"], case["min_cov"], pos.ctypes.data, base.ctypes.data, qv.ctypes.data, cap)
+    if n < 0:
+        return n
+    return pos[:n].copy(), base[:n].tobytes(), qv[:n].copy()

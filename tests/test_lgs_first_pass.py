@@ -1,6 +1,12 @@
-"""First pass of the long-read consensus window (nextpolish2.so): the C restatement oracle/np2_oracle.c
-against the goldens minted from the reference (tests/golden/lgs_golden.json, make_golden_lgs.py) and, when oracle/_ref holds
-the stage door into the unmodified ctg_cns.c (libnp2_refshim.so), against the reference live on seeded fuzz inputs."""
+"""First pass of the long-read consensus window (nextpolish2.so).
+  * the C restatement oracle/np2_oracle.c against the goldens minted from the reference (tests/golden/lgs_golden.json,
+    make_golden_lgs.py) and, when oracle/_ref holds the stage door into the unmodified ctg_cns.c (libnp2_refshim.so),
+    against the reference live on seeded fuzz inputs;
+  * the kernel bodies of the GPU path (csrc/lgs_first_pass.h) compiled for the host (tests/emu/emu_lgs.cpp, test build
+    only) against that oracle: every seeded case x read type, threads run in order and shuffled, the normal build and one
+    with 8-column stretches / 4-column cut blocks (every seam and the speculative-segment re-runs are reached), batches of
+    several windows, rejected inputs;
+  * nextpolish2.so exports what include/nextpolish2_b200.h declares and fails loudly without a GPU."""
 import ctypes as C
 import hashlib
 import json
@@ -55,7 +61,7 @@ def test_oracle_matches_reference_goldens(O2):
         assert not isinstance(got, int), (key, got)
         assert digest(got) == gold[key], key
         seen += 1
-    assert seen == len(gold) == 52
+    assert seen == len(gold) == 68
 
 
 def test_real_windows_look_like_consensus(O2):
@@ -103,3 +109,110 @@ def test_oracle_error_codes_and_qv(O2):
     assert f(*args(short, cap)) == -2
     cut = dict(case, len=case["len"] - 50)                                    # alignments leave the window
     assert f(*args(cut, cap)) == -3
+
+
+# ---- the GPU path's kernel bodies on the host ----------------------------------------------------------------------------
+def _emu2_build(name, defines=()):
+    d = os.path.join(ROOT, "tests", "_emu")
+    os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, name)
+    srcs = [os.path.join(ROOT, "tests", "emu", "emu_lgs.cpp"), os.path.join(ROOT, "nextpolish_b200", "csrc", "lgs_first_pass.h"),
+            os.path.join(ROOT, "include", "nextpolish2_b200.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall"] + list(defines) + ["-o", so, srcs[0]])
+    E = C.CDLL(so)
+    E.np2_emu_first_pass_batch.restype = C.c_int64
+    E.np2_emu_first_pass_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64, C.c_void_p]
+    return E
+
+
+@pytest.fixture(scope="module", params=["product_sizes", "tiny_seams"])
+def emu2(request):
+    if request.param == "product_sizes":
+        return _emu2_build("libnp2_emu.so")
+    return _emu2_build("libnp2_emu_small.so", ("-DNP2_STRETCH=8", "-DNP2_CUT_BLOCK=4"))
+
+
+def emu_call(E, seed, stats=None):
+    st = stats if stats is not None else np.zeros(4, np.int64)
+    return lambda b, p, ba, q, cap, off: E.np2_emu_first_pass_batch(b, p, ba, q, cap, off, seed, st.ctypes.data)
+
+
+def same(got, want):
+    return len(got[1]) == len(want[1]) and (got[0] == want[0]).all() and got[1] == want[1] and (got[2] == want[2]).all()
+
+
+def test_emulated_kernels_match_oracle(O2, emu2):
+    reruns = 0
+    for name, kw in L.CASES.items():
+        for rt in (1, 2, 3, 4):
+            case = L.synthetic_case(**dict(kw, read_type=rt))
+            want = L.oracle_window(O2, case)
+            assert not isinstance(want, int)
+            for seed in (0, 11):                             # threads in order / shuffled
+                st = np.zeros(4, np.int64)
+                got = L.first_pass_batch(emu_call(emu2, seed, st), [case])
+                assert not isinstance(got, int), (name, rt, seed, got)
+                assert same(got[0], want), (name, rt, seed)
+                reruns += int(st[1])
+    assert reruns > 50                                       # the "zones" cases force segments to run again with their true score
+
+
+def test_emulated_kernels_real_windows_and_batches(O2, emu2):
+    wins = list(td_windows().values())
+    for rt in (1, 3):
+        cases = [dict(w, read_type=rt) for w in wins]
+        cases += [L.synthetic_case(**dict(L.CASES[n], read_type=rt)) for n in ("ont_tiny", "ont_shallow", "hifi_zones", "ont_masked")]
+        want = [L.oracle_window(O2, c) for c in cases]
+        st = np.zeros(4, np.int64)
+        got = L.first_pass_batch(emu_call(emu2, 5, st), cases)       # one batch, several windows
+        assert not isinstance(got, int)
+        for g, w in zip(got, want):
+            assert same(g, w), rt
+        assert st[0] >= len(cases)                            # at least one chain segment per window
+        for c, w in zip(cases, want):                         # and each window alone
+            assert same(L.first_pass_batch(emu_call(emu2, 0), [c])[0], w)
+
+
+def test_emulated_kernels_fuzz(O2, emu2):
+    rng = random.Random(77)
+    for it in range(60):
+        kw = dict(seed=rng.randrange(1 << 30), length=rng.choice([20, 60, 300, 900]), depth=rng.choice([1, 2, 5, 15, 40]),
+                  read_len=rng.choice([30, 100, 400]), sub=rng.choice([0.0, 0.02, 0.08, 0.4]), ins=rng.choice([0.0, 0.03, 0.1, 0.3]),
+                  dele=rng.choice([0.0, 0.03, 0.1, 0.3]), read_type=rng.choice([1, 2, 3, 4]), min_cov=rng.choice([0, 4, 10]),
+                  long_ins=rng.choice([0, 0.003]), masked=rng.choice([0, 0, 0.02]), homopolymer=rng.random() < 0.3,
+                  odd_chars=rng.random() < 0.2, zones=rng.choice([0, 0, (4, 20), (6, 60)]))
+        case = L.synthetic_case(**kw)
+        want = L.oracle_window(O2, case)
+        got = L.first_pass_batch(emu_call(emu2, rng.randrange(1, 1 << 20)), [case])
+        if isinstance(want, int):
+            assert got == want, kw
+        else:
+            assert not isinstance(got, int) and same(got[0], want), kw
+
+
+def test_emulated_kernels_reject_what_the_oracle_rejects(O2, emu2):
+    case = L.synthetic_case(**L.CASES["ont30"])
+    for bad in (dict(case, len=case["len"] + 50), dict(case, len=case["len"] - 50)):        # -2: bare last column; -3: out of window
+        want = L.oracle_window(O2, bad)
+        assert isinstance(want, int) and want in (-2, -3)
+        assert L.first_pass_batch(emu_call(emu2, 0), [bad]) == want
+    gap_first = L.pack_case([(0, "ACGTACGTAC", "ACGTACGTAC"), (2, "-GTACG", "TGTACG")], 10, 1)
+    assert L.oracle_window(O2, gap_first) == -3 and L.first_pass_batch(emu_call(emu2, 0), [gap_first]) == -3
+    assert L.first_pass_batch(emu_call(emu2, 0), []) == []                                    # empty batch
+
+
+def test_nextpolish2_library_exports_and_fails_loudly_without_gpu():
+    import re
+    from nextpolish_b200 import nextpolish2 as NP2
+    hdr = open(os.path.join(ROOT, "include", "nextpolish2_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(np2_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(NP2.EXPORTS2), declared ^ set(NP2.EXPORTS2)
+    lib = C.CDLL(NP2.LIB2_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(NP2.NativeError, match="no CPU path"):
+            NP2.LgsEngine(0)
