@@ -57,6 +57,11 @@ int64_t np2_first_pass(np2_engine* e, const np2_window_batch* batch, uint32_t* o
  * true cut score, [2] stitch iterations, [3] link records */
 int64_t np2_engine_launch_count(np2_engine* e);
 void    np2_engine_last_stats(np2_engine* e, int64_t out[4]);
+/* device time (ms, CUDA events on the engine's stream) of every launch of the last np2_first_pass, in launch order; only
+ * recorded when the environment has NEXTPOLISH_B200_LGS_TIMING=1.  names[i] stay valid until the next call.  Returns the
+ * number of entries written.  (NEXTPOLISH_B200_LGS_CHAIN=thread selects the one-thread-per-segment chain kernel instead
+ * of the warp-per-segment one: an A/B switch for measurements.) */
+int32_t np2_engine_kernel_times(np2_engine* e, const char** names, float* ms, int32_t cap);
 
 #ifdef __cplusplus
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -28,8 +29,26 @@ __global__ void __launch_bounds__(256) k_np2(int64_t n, F f) {
     if (i < n) { CudaOps ops; f(i, ops); }
 }
 
+struct WarpCtx {                     // ChainWarp's view of its warp (lgs_first_pass.h)
+    np2::Gath* g;
+    __device__ __forceinline__ int32_t lane() const { return (int32_t)(threadIdx.x & 31); }
+    __device__ __forceinline__ int32_t lanes() const { return 32; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ np2::Gath* scratch() const { return g; }
+};
+template <class F>
+__global__ void __launch_bounds__(256) k_np2_warp(int64_t n_warps, F f) {
+    __shared__ np2::Gath scratch[8][np2::GMAX];
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp < n_warps) { WarpCtx w{scratch[threadIdx.x >> 5]}; f(warp, w); }      // uniform per warp
+}
+
 struct Backend {
     int device = 0;
+    int chain_mode = 1;                  // 1: warp per segment (ChainWarp), 0: thread per segment (Chain); NEXTPOLISH_B200_LGS_CHAIN=thread|warp
+    bool timing = false;                 // NEXTPOLISH_B200_LGS_TIMING=1: CUDA events around every launch
+    struct Timed { std::string name; cudaEvent_t a, b; };
+    std::vector<Timed> timed;
     cudaStream_t stream = nullptr;
     struct Buf { void* p = nullptr; size_t bytes = 0; };
     std::map<std::string, Buf> pool;
@@ -60,10 +79,29 @@ struct Backend {
     }
     void zero(void* p, size_t bytes) { if (ok && p && bytes) NP2_TRY(cudaMemsetAsync(p, 0, bytes, stream)); }
     void fill_ff(void* p, size_t bytes) { if (ok && p && bytes) NP2_TRY(cudaMemsetAsync(p, 0xff, bytes, stream)); }
-    template <class F> void launch(const char*, int64_t n, const F& f) {
+    bool warp_chain() const { return chain_mode == 1; }
+    void t_begin(const char* name) {
+        if (!timing) return;
+        Timed t; t.name = name;
+        NP2_TRY(cudaEventCreate(&t.a)); NP2_TRY(cudaEventCreate(&t.b));
+        NP2_TRY(cudaEventRecord(t.a, stream));
+        timed.push_back(t);
+    }
+    void t_end() { if (timing && !timed.empty()) NP2_TRY(cudaEventRecord(timed.back().b, stream)); }
+    template <class F> void launch(const char* name, int64_t n, const F& f) {
         if (!ok || n <= 0) return;
+        t_begin(name);
         k_np2<F><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, f);
         NP2_TRY(cudaGetLastError());
+        t_end();
+        launches++;
+    }
+    template <class F> void launch_warps(const char* name, int64_t n_warps, const F& f) {
+        if (!ok || n_warps <= 0) return;
+        t_begin(name);
+        k_np2_warp<F><<<(unsigned)((n_warps + 7) / 8), 256, 0, stream>>>(n_warps, f);
+        NP2_TRY(cudaGetLastError());
+        t_end();
         launches++;
     }
     void exscan_i32(const int32_t* in, int32_t* out, int64_t n) {
@@ -75,7 +113,9 @@ struct Backend {
             NP2_TRY(cudaMalloc(&cub_tmp, need + 1024));
             cub_bytes = cub_tmp ? need + 1024 : 0;
         }
+        t_begin("lgs_scan");
         if (ok) NP2_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, need, in, out, (int)n, stream));
+        t_end();
         launches += 2;
     }
     void download(void* dst, const void* src, size_t bytes) {
@@ -84,7 +124,9 @@ struct Backend {
         NP2_TRY(cudaStreamSynchronize(stream));
     }
     int32_t read_i32(const int32_t* p) { int32_t v = 0; download(&v, p, 4); return v; }
+    void clear_timed() { for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); } timed.clear(); }
     void release() {
+        clear_timed();
         for (auto& kv : pool) if (kv.second.p) cudaFree(kv.second.p);
         pool.clear();
         if (cub_tmp) cudaFree(cub_tmp);
@@ -125,6 +167,11 @@ int64_t np2_first_pass(np2_engine* e, const np2_window_batch* b, uint32_t* out_p
     if (!out_pos || !out_base || !b->win_len || !b->win_aln0 || !b->aln_t_s || !b->aln_len || !b->str_off || !b->t_str || !b->q_str) { g_err = "np2_first_pass: bad arguments"; return -6; }
     if (cudaSetDevice(e->be.device) != cudaSuccess) { g_err = "np2_first_pass: cudaSetDevice failed"; return -6; }
     e->be.ok = true; e->be.msg.clear();
+    e->be.clear_timed();
+    const char* cm = getenv("NEXTPOLISH_B200_LGS_CHAIN");
+    e->be.chain_mode = (cm && strcmp(cm, "thread") == 0) ? 0 : 1;
+    const char* tm = getenv("NEXTPOLISH_B200_LGS_TIMING");
+    e->be.timing = tm && tm[0] == '1';
     np2::Batch hb;
     hb.n_win = b->n_windows; hb.win_len = b->win_len; hb.win_aln0 = b->win_aln0; hb.read_type = b->read_type; hb.min_cov = b->min_cov;
     hb.aln_t_s = b->aln_t_s; hb.aln_len = b->aln_len; hb.str_off = b->str_off; hb.t_str = b->t_str; hb.q_str = b->q_str; hb.str_bytes = b->str_bytes;
@@ -135,6 +182,20 @@ int64_t np2_first_pass(np2_engine* e, const np2_window_batch* b, uint32_t* out_p
 }
 
 int64_t np2_engine_launch_count(np2_engine* e) { return e ? e->be.launches : 0; }
+
+int32_t np2_engine_kernel_times(np2_engine* e, const char** names, float* ms, int32_t cap) {
+    if (!e) return 0;
+    cudaSetDevice(e->be.device);
+    cudaStreamSynchronize(e->be.stream);
+    int32_t n = 0;
+    for (auto& t : e->be.timed) {
+        if (n >= cap) break;
+        float v = 0;
+        if (cudaEventElapsedTime(&v, t.a, t.b) != cudaSuccess) v = -1;
+        names[n] = t.name.c_str(); ms[n] = v; n++;
+    }
+    return n;
+}
 void np2_engine_last_stats(np2_engine* e, int64_t out[4]) {
     if (!e || !out) return;
     out[0] = e->last.n_seg; out[1] = e->last.reruns; out[2] = e->last.iterations; out[3] = e->last.n_rec;

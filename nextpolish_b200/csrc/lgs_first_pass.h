@@ -315,6 +315,125 @@ struct Chain {                      // the score chain of one segment (get_cns_f
     }
 };
 
+// ---- the same chain with a warp per segment --------------------------------------------------------------------------------
+// What is slow in the chain is not arithmetic but the look-ups: for every entry, find the node of its predecessor tag and
+// the entries of that node that continue the same pre-predecessor (dependent loads from L2).  The look-ups of all entries
+// that share a sub-column are independent of each other, so the lanes of a warp do them at once (gather: the matching
+// predecessor scores, in order, into the warp's shared scratch); lane 0 then replays the reference's sequential rules over
+// the gathered values, which costs no memory latency.  Groups that do not fit the scratch (more than GMAX entries, or an
+// entry with more than MAXM matches) are done by lane 0 the literal way.
+#ifndef NP2_GMAX
+#define NP2_GMAX 64
+#endif
+#ifndef NP2_MAXM
+#define NP2_MAXM 6
+#endif
+enum { GMAX = NP2_GMAX, MAXM = NP2_MAXM };
+struct Gath { int32_t cnt; int32_t pad; int64_t v[MAXM]; };          // cnt < 0: more matches than MAXM
+
+NP2_HD void gather_entry(const Dev& d, const SegRange& sr, int64_t base, const Ent& em, Gath& g) {
+    g.cnt = 0;
+    if (em.pp_t == -1) return;
+    int32_t plen;
+    const int32_t pn = find_node(d, em.pp_t, em.pp_d, em.pp_b, &plen);
+    const bool at_cut = !sr.start && em.pp_t == sr.c;
+    for (int32_t n = 0; n < plen; n++) {
+        const Ent& en = d.ent[pn + n];
+        if (!(en.pp_t == em.ppp_t && en.pp_d == em.ppp_d && en.pp_b == em.ppp_b)) continue;
+        if (g.cnt == MAXM) { g.cnt = -1; return; }
+        g.v[g.cnt++] = at_cut ? base : en.score;
+    }
+}
+
+struct NodeState { int32_t best, tmp, b, rt; int64_t p_pp, p_pp_, pen, cov; };
+// one matching predecessor score ns_ for entry m of node N (the body of the reference's inner loop)
+NP2_HD void chain_step(Cmp& cmp, NodeState& st, Ent* N, int32_t m, int64_t ns_) {
+    Ent& em = N[m];
+    const int64_t s = ns_ + 10 * (int64_t)em.link - st.pen * st.cov;
+    if (cmp.gt(s, em.score)) { em.score = s; st.p_pp_ = ns_; }
+    if (st.rt == READS_CLR || st.rt == READS_HIFI) {
+        if (cmp.gt(ns_, st.p_pp) || (cmp.eq(ns_, st.p_pp) && em.pp_b != 4)) { st.best = m; st.p_pp = ns_; }
+    } else if (st.rt != READS_RS) {
+        if (((em.ppp_d > 1 || em.pp_d > 0) && ((double)em.link > (double)st.cov * 0.2 || (int32_t)em.link > st.tmp / 2)) ||
+            ((int32_t)em.link > (int32_t)N[st.best].link / 2 && cmp.gt(ns_, st.p_pp) &&
+             (em.pp_b == 4 || em.pp_b == st.b || em.ppp_b == st.b || em.pp_b == em.ppp_b))) { st.best = m; st.p_pp = ns_; }
+    }
+}
+
+// W: lane(), lanes(), sync(), scratch() -> Gath[GMAX] private to the warp (one lane and a local array in the test build)
+struct ChainWarp {
+    Dev d; int32_t rerun_only;
+    template <class W> NP2_HD void operator()(int64_t kk, W& w) const {
+        const int32_t ns = d.blk_idx[d.n_blk], k = (int32_t)kk;
+        if (k >= ns) return;
+        const int32_t mode = d.seg_mode[k];
+        if (rerun_only && mode != MODE_RERUN) return;
+        const SegRange sr = seg_range(d, k, ns);
+        const bool exact = sr.start || mode == MODE_RERUN;
+        const int64_t base = sr.start ? 0 : (mode == MODE_RERUN ? d.seg_S[k] : BIG);
+        Cmp cmp; cmp.T = NEG_INF; cmp.spec = !exact;
+        NodeState st;
+        st.pen = d.read_type == READS_HIFI ? 4 : 3; st.rt = d.read_type;
+        int64_t gbs = NEG_INF; int32_t gb_c = -1, gb_d = 0, gb_b = 0;
+        Gath* G = w.scratch();
+        for (int32_t col = sr.start ? sr.c : sr.c + 1; col <= sr.hi; col++) {
+            const int32_t o = d.rec_off[col], ne = d.n_ent[col];
+            st.cov = (int64_t)(uint16_t)d.cov[col];
+            int32_t g0 = 0;
+            while (g0 < ne) {                                                        // group: the entries of one sub-column
+                int32_t glen = 1;
+                while (g0 + glen < ne && d.ent[o + g0 + glen].d == d.ent[o + g0].d) glen++;
+                const bool fits = glen <= GMAX;
+                if (fits) for (int32_t e = w.lane(); e < glen; e += w.lanes()) gather_entry(d, sr, base, d.ent[o + g0 + e], G[e]);
+                w.sync();
+                if (w.lane() == 0) {
+                    int32_t i = g0;
+                    while (i < g0 + glen) {
+                        Ent* N = d.ent + o + i;
+                        int32_t len = 1;
+                        while (i + len < g0 + glen && N[len].b == N[0].b) len++;
+                        st.b = N[0].b; st.best = 0; st.tmp = 0; st.p_pp = NEG_INF; st.p_pp_ = NEG_INF;
+                        for (int32_t m = 0; m < len; m++) if (N[m].link > st.tmp) st.tmp = N[m].link;
+                        for (int32_t m = 0; m < len; m++) {
+                            Ent& em = N[m];
+                            em.score = 0;
+                            if (em.pp_t == -1) em.score = 10 * (int64_t)em.link - st.pen * st.cov;
+                            else if (fits && G[i - g0 + m].cnt >= 0) {
+                                const Gath& g = G[i - g0 + m];
+                                for (int32_t j = 0; j < g.cnt; j++) chain_step(cmp, st, N, m, g.v[j]);
+                            } else {                                                 // the literal look-up
+                                int32_t plen;
+                                const int32_t pn = find_node(d, em.pp_t, em.pp_d, em.pp_b, &plen);
+                                const bool at_cut = !sr.start && em.pp_t == sr.c;
+                                for (int32_t n = 0; n < plen; n++) {
+                                    const Ent& en = d.ent[pn + n];
+                                    if (!(en.pp_t == em.ppp_t && en.pp_d == em.ppp_d && en.pp_b == em.ppp_b)) continue;
+                                    chain_step(cmp, st, N, m, at_cut ? base : en.score);
+                                }
+                            }
+                            if (st.rt == READS_RS) { if (!cmp.gt(N[st.best].score, em.score)) { st.best = m; st.p_pp = st.p_pp_; } }
+                            else if (cmp.gt(em.score, N[st.best].score) || (cmp.eq(em.score, N[st.best].score) && em.pp_b != 4)) { st.best = m; st.p_pp = st.p_pp_; }
+                        }
+                        N[0].aux = st.best;
+                        if (col == sr.cend && !cmp.gt(gbs, N[st.best].score)) {
+                            gb_c = col; gb_d = N[0].d; gb_b = st.b;
+                            if (cmp.gt(N[st.best].score, gbs)) gbs = N[st.best].score;
+                        }
+                        i += len;
+                    }
+                }
+                w.sync();
+                g0 += glen;
+            }
+        }
+        if (w.lane() == 0) {
+            d.seg_T[k] = exact ? NEG_INF : cmp.T;
+            d.seg_mode[k] = exact ? MODE_EXACT : MODE_SPEC;
+            if (sr.hi == sr.cend) { d.win_gb[sr.w * 3] = gb_c; d.win_gb[sr.w * 3 + 1] = gb_d; d.win_gb[sr.w * 3 + 2] = gb_b; }
+        }
+    }
+};
+
 struct Stitch {                     // true cut scores of one window, in order; marks the segments to run again
     Dev d;
     template <class Ops> NP2_HD void operator()(int64_t w, Ops& ops) const {
@@ -467,7 +586,8 @@ int64_t run_first_pass(BE& be, const Batch& hb, uint32_t* out_pos, uint8_t* out_
     be.launch("lgs_cut_blocks", nblk, CutBlocks{d});
     be.exscan_i32(d.blk_has, d.blk_idx, (int64_t)B1);
     be.launch("lgs_seg_scatter", nblk, SegScatter{d});
-    be.launch("lgs_chain", nblk, Chain{d, 0});
+    const bool warp_chain = be.warp_chain();
+    if (warp_chain) be.launch_warps("lgs_chain", nblk, ChainWarp{d, 0}); else be.launch("lgs_chain", nblk, Chain{d, 0});
     int32_t iterations = 0, reruns = 0;
     for (;;) {
         be.zero(d.n_invalid, 4);
@@ -477,7 +597,7 @@ int64_t run_first_pass(BE& be, const Batch& hb, uint32_t* out_pos, uint8_t* out_
         if (bad <= 0) break;
         reruns += bad;
         if (++iterations > d.n_blk + 2) return -6;                                  // cannot happen: every pass fixes at least one segment
-        be.launch("lgs_chain_rerun", nblk, Chain{d, 1});
+        if (warp_chain) be.launch_warps("lgs_chain_rerun", nblk, ChainWarp{d, 1}); else be.launch("lgs_chain_rerun", nblk, Chain{d, 1});
     }
     be.launch("lgs_backtrack_count", nblk, Backtrack{d, 0});
     be.launch("lgs_prune", hb.n_win, Prune{d});

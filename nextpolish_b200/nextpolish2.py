@@ -14,7 +14,7 @@ import numpy as np
 
 LIB2_PATH = os.path.join(os.path.dirname(os.path.realpath(__file__)), "lib", "nextpolish2.so")
 EXPORTS2 = ["np2_engine_create", "np2_engine_destroy", "np2_last_error", "np2_first_pass", "np2_engine_launch_count",
-            "np2_engine_last_stats"]                     # every symbol include/nextpolish2_b200.h declares
+            "np2_engine_last_stats", "np2_engine_kernel_times"]                     # every symbol include/nextpolish2_b200.h declares
 ERRORS = {-1: "output capacity too small", -2: "a window's last position has no node",
           -3: "an alignment is empty, starts on a gap column or leaves its window",
           -4: "backtrack through a node without links", -5: "size limit", -6: "CUDA failure"}
@@ -50,6 +50,7 @@ def lib2():
         L.np2_engine_launch_count.restype = C.c_int64
         L.np2_engine_last_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.np2_engine_last_stats.restype = None
+        L.np2_engine_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         _LIB2 = L
     return _LIB2
 
@@ -98,6 +99,13 @@ class LgsEngine:
         out = (C.c_int64 * 4)()
         lib2().np2_engine_last_stats(self.h, out)
         return dict(segments=out[0], reruns=out[1], stitch_iterations=out[2], link_records=out[3], launches=lib2().np2_engine_launch_count(self.h))
+
+    def kernel_times(self):
+        """[(launch name, ms)] of the last first_pass (needs NEXTPOLISH_B200_LGS_TIMING=1 in the environment)."""
+        names = (C.c_char_p * 4096)()
+        ms = (C.c_float * 4096)()
+        n = lib2().np2_engine_kernel_times(self.h, names, ms, 4096)
+        return [(names[i].decode(), ms[i]) for i in range(n)]
 
     def close(self):
         if self.h:

@@ -50,6 +50,23 @@ struct EmuBackend {
         std::shuffle(order.begin(), order.end(), rng);
         for (int64_t i : order) f(i, ops);
     }
+    // ChainWarp with one lane and a local scratch (the parallel gather of the product build becomes a loop)
+    struct OneLane {
+        np2::Gath g[np2::GMAX];
+        int32_t lane() const { return 0; }
+        int32_t lanes() const { return 1; }
+        void sync() const {}
+        np2::Gath* scratch() { return g; }
+    };
+    int chain_mode = 1;
+    bool warp_chain() const { return chain_mode == 1; }
+    template <class F> void launch_warps(const char*, int64_t n, const F& f) {
+        launches++;
+        std::vector<int64_t> order((size_t)n);
+        for (int64_t i = 0; i < n; i++) order[(size_t)i] = i;
+        if (shuffle_seed) { std::mt19937_64 rng(shuffle_seed + (uint64_t)launches); std::shuffle(order.begin(), order.end(), rng); }
+        for (int64_t i : order) { OneLane w; memset(w.g, 0xCD, sizeof w.g); f(i, w); }
+    }
     void exscan_i32(const int32_t* in, int32_t* out, int64_t n) {
         int64_t s = 0;
         for (int64_t i = 0; i < n; i++) { const int32_t v = in[i]; out[i] = (int32_t)s; s += v; }
@@ -63,7 +80,8 @@ struct EmuBackend {
 extern "C" int64_t np2_emu_first_pass_batch(const np2_window_batch* b, uint32_t* out_pos, char* out_base, uint8_t* out_qv, int64_t cap,
                                             int64_t* out_off, uint64_t shuffle_seed, int64_t* stats) {
     EmuBackend be;
-    be.shuffle_seed = shuffle_seed;
+    be.shuffle_seed = shuffle_seed & 0xffffffffu;
+    be.chain_mode = (shuffle_seed >> 32) & 1 ? 0 : 1;          // bit 32 of the seed: the thread-per-segment chain
     np2::Batch hb;
     hb.n_win = b->n_windows; hb.win_len = b->win_len; hb.win_aln0 = b->win_aln0; hb.read_type = b->read_type; hb.min_cov = b->min_cov;
     hb.aln_t_s = b->aln_t_s; hb.aln_len = b->aln_len; hb.str_off = b->str_off; hb.t_str = b->t_str; hb.q_str = b->q_str; hb.str_bytes = b->str_bytes;

@@ -4,7 +4,8 @@
     against the reference live on seeded fuzz inputs;
   * the kernel bodies of the GPU path (csrc/lgs_first_pass.h) compiled for the host (tests/emu/emu_lgs.cpp, test build
     only) against that oracle: every seeded case x read type, threads run in order and shuffled, the normal build and one
-    with 8-column stretches / 4-column cut blocks (every seam and the speculative-segment re-runs are reached), batches of
+    with 8-column stretches, 4-column cut blocks and a 3-entry / 1-match gather scratch (every seam, the speculative-segment
+    re-runs and the literal fall-back of the warp chain are reached), both chain kernels, batches of
     several windows, rejected inputs;
   * nextpolish2.so exports what include/nextpolish2_b200.h declares and fails loudly without a GPU."""
 import ctypes as C
@@ -130,7 +131,10 @@ def _emu2_build(name, defines=()):
 def emu2(request):
     if request.param == "product_sizes":
         return _emu2_build("libnp2_emu.so")
-    return _emu2_build("libnp2_emu_small.so", ("-DNP2_STRETCH=8", "-DNP2_CUT_BLOCK=4"))
+    return _emu2_build("libnp2_emu_small.so", ("-DNP2_STRETCH=8", "-DNP2_CUT_BLOCK=4", "-DNP2_GMAX=3", "-DNP2_MAXM=1"))
+
+
+THREAD_CHAIN = 1 << 32          # bit 32 of the emulator's seed argument: Chain instead of ChainWarp (tests/emu/emu_lgs.cpp)
 
 
 def emu_call(E, seed, stats=None):
@@ -149,7 +153,7 @@ def test_emulated_kernels_match_oracle(O2, emu2):
             case = L.synthetic_case(**dict(kw, read_type=rt))
             want = L.oracle_window(O2, case)
             assert not isinstance(want, int)
-            for seed in (0, 11):                             # threads in order / shuffled
+            for seed in (0, 11, 11 | THREAD_CHAIN):          # threads in order / shuffled / the thread-per-segment chain kernel
                 st = np.zeros(4, np.int64)
                 got = L.first_pass_batch(emu_call(emu2, seed, st), [case])
                 assert not isinstance(got, int), (name, rt, seed, got)
@@ -184,7 +188,7 @@ def test_emulated_kernels_fuzz(O2, emu2):
                   odd_chars=rng.random() < 0.2, zones=rng.choice([0, 0, (4, 20), (6, 60)]))
         case = L.synthetic_case(**kw)
         want = L.oracle_window(O2, case)
-        got = L.first_pass_batch(emu_call(emu2, rng.randrange(1, 1 << 20)), [case])
+        got = L.first_pass_batch(emu_call(emu2, rng.randrange(1, 1 << 20) | (THREAD_CHAIN if it % 3 == 0 else 0)), [case])
         if isinstance(want, int):
             assert got == want, kw
         else:
