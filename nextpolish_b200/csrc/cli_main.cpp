@@ -10,6 +10,7 @@
 // Worker grammar (argv[1] starts with '-'): the command line of the reference's per-step worker, lib/nextpolish1.py
 // (:252-334), so that the driver's job lines (source/nextPolish:87-90) can call this binary directly:
 //   nextpolish1 -g genome.fa -t 1 -s sgs.sort.bam [-b input.genome.fasta.blc -i 0] [-o part000.fasta] [-u] [-debug] [flags]
+// (--plan, ours: print what the job would polish and where its output part resumes, then exit without touching a device)
 // with the block file / resume / ">name_np<task> <len>" conventions of nextpolish1.py:148-179,226-229 (part_writer.cpp).
 #include <cstdio>
 #include <cstdlib>
@@ -42,7 +43,7 @@ static long long parse_count(const char* v) {          // parse_num_unit of the 
 
 static int worker_main(int argc, char* argv[]) {
     const char *genome = nullptr, *sgs = nullptr, *lgs = nullptr, *block = nullptr, *index = "all", *outp = "stdout";
-    int task = 0, upper = 0, debug = 0;
+    int task = 0, upper = 0, debug = 0, plan_only = 0;
     struct Opt { const char* name; double val; bool set; };
     Opt opts[] = {{"count_read_ins_sgs", 0, false}, {"min_map_quality", 0, false}, {"max_ins_len_sgs", 0, false}, {"max_ins_fold_sgs", 0, false},
                   {"max_clip_ratio_sgs", 0, false}, {"max_clip_ratio_lgs", 0, false}, {"trim_len_edge", 0, false}, {"ext_len_edge", 0, false},
@@ -63,6 +64,7 @@ static int worker_main(int argc, char* argv[]) {
         else if (a == "-p" || a == "--process") (void)val();        // host processes of the reference's Pool: one GPU batch here
         else if (a == "-u" || a == "--uppercase") upper = 1;
         else if (a == "-debug") debug = 1;
+        else if (a == "--plan") plan_only = 1;                       // not in the reference: print the job's plan, touch no device
         else {
             bool known = false;
             for (Opt& o : opts)
@@ -79,6 +81,12 @@ static int worker_main(int argc, char* argv[]) {
     np_part_plan* plan = np_part_plan_create(genome, block, index, outp);
     if (!plan) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
     if (np_part_plan_finished(plan)) fprintf(stderr, "skip %d polished seqs found in %s\n", np_part_plan_finished(plan), outp);
+    if (plan_only) {
+        printf("task\t%d\nfinished\t%d\nresume_offset\t%lld\n", task, np_part_plan_finished(plan), (long long)np_part_plan_resume_offset(plan));
+        for (int i = 0; i < np_part_plan_count(plan); i++) printf("polish\t%s\n", np_part_plan_name(plan, i));
+        np_part_plan_destroy(plan);
+        return 0;
+    }
     np_part_file* out = np_part_open(outp, np_part_plan_resume_offset(plan));
     if (!out) { fprintf(stderr, "%s\n", np_last_error()); return 1; }
     const int n_names = np_part_plan_count(plan);

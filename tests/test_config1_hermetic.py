@@ -17,10 +17,18 @@ NEED = ["seq_split", "seq_count", "bwa", "samtools", "minimap2", "nextpolish1.so
 have = os.path.exists("/root/reference/source/nextPolish") and all(os.path.exists(os.path.join(ROOT, "oracle", "_ref", n)) for n in NEED)
 
 
-@pytest.mark.skipif(not have, reason="needs /root/reference and make -C oracle ref ref2 refcfg")
-def test_reference_driver_runs_run_cfg_on_the_paralleltask_standin():
+@pytest.fixture(scope="module")
+def config1_run():
+    import shutil
     import run_config1
-    out, log = run_config1.run("reference")
+    out, log = run_config1.run("reference", keep=True)
+    yield out, log
+    shutil.rmtree(out["dir"], ignore_errors=True)
+
+
+@pytest.mark.skipif(not have, reason="needs /root/reference and make -C oracle ref ref2 refcfg")
+def test_reference_driver_runs_run_cfg_on_the_paralleltask_standin(config1_run):
+    out, log = config1_run
     assert out["rc"] == 0, log[-3000:]
     # default task string = 5, 1, 2 (6 dropped: no hifi_fofn; config_parser.py:86-87,104-108): names carry the sgs steps
     assert sorted(out["contigs"]) == ["tig0000001_np12", "tig0000002_np12"]
@@ -28,3 +36,44 @@ def test_reference_driver_runs_run_cfg_on_the_paralleltask_standin():
     assert abs(out["contigs"]["tig0000001_np12"]["len"] - 51009) < 500
     assert abs(out["contigs"]["tig0000002_np12"]["len"] - 60401) < 600
     assert "nextPolish has finished" in log or "N50" in log
+
+
+@pytest.mark.skipif(not have, reason="needs /root/reference and make -C oracle ref ref2 refcfg")
+def test_native_cli_accepts_the_drivers_job_lines(config1_run, tmp_path):
+    """The job lines the driver wrote for its polish steps (source/nextPolish:87-90), handed to OUR native CLI with the
+    interpreter + worker script replaced by the binary: every option parses, and the plan (--plan: no device touched) is
+    the block-file selection / resume behaviour of the reference's worker (nextpolish1.py:148-179)."""
+    import glob
+    import shlex
+    import subprocess
+    from tests.test_part_writer import ref_block_names, ref_scan_output
+    out, _ = config1_run
+    cli = os.path.join(ROOT, "nextpolish_b200", "lib", "nextpolish1")
+    scripts = sorted(glob.glob(os.path.join(out["dir"], "test_data", "01_rundir", "0[12].*", "0*.polish.ref.sh")))
+    assert len(scripts) == 2                                     # score_chain and kmer_count steps
+    seen = 0
+    for sc in scripts:
+        for line in open(sc):
+            argv = shlex.split(line)
+            if not argv:
+                continue
+            assert argv[1].endswith("lib/nextpolish1.py")
+            args = argv[2:]
+            opt = dict(zip(args[::2], args[1::2]))
+            r = subprocess.run([cli] + args + ["--plan"], cwd=tmp_path, capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            plan = [l.split("\t") for l in r.stdout.strip().split("\n")]
+            assert plan[0] == ["task", opt["-t"]] and plan[1] == ["finished", "0"] and plan[2] == ["resume_offset", "0"]
+            want = ref_block_names(opt["-b"], opt["-i"], set())
+            assert [p[1] for p in plan[3:]] == want
+            seen += len(want)
+            if want:                                             # resume: a part with one finished and one partial record
+                part = tmp_path / opt["-o"]
+                part.write_text(">%s_np%s 4\nACGT\n>%s_np%s 9\nAC" % (want[0], opt["-t"], want[-1], opt["-t"]))
+                r = subprocess.run([cli] + args + ["--plan"], cwd=tmp_path, capture_output=True, text=True)
+                done, off = ref_scan_output(str(part))
+                lines = r.stdout.strip().split("\n")
+                assert lines[1] == "finished\t%d" % len(done) and lines[2] == "resume_offset\t%d" % off
+                assert [l.split("\t")[1] for l in lines[3:]] == ref_block_names(opt["-b"], opt["-i"], done)
+                part.unlink()
+    assert seen == 4                                             # 2 contigs x 2 steps
