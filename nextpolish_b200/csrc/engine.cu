@@ -5,6 +5,7 @@
 // double (contig.c:448); the file is compiled with -fmad=false so no FMA contraction can
 // change a rounding relative to the reference's x86-64 SSE2 code.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
@@ -364,7 +365,10 @@ struct CudaBackend {
     }
     void zero(void* p, size_t bytes) { if (ok && p) CUDA_TRY(cudaMemsetAsync(p, 0, bytes, stream)); }
     void fill_ff(void* p, size_t bytes) { if (ok && p) CUDA_TRY(cudaMemsetAsync(p, 0xff, bytes, stream)); }
+    // NEXTPOLISH_B200_NVTX=1: one NVTX range per launch (named like the kernels_ms keys), for timeline profilers
+    bool nvtx = getenv("NEXTPOLISH_B200_NVTX") && getenv("NEXTPOLISH_B200_NVTX")[0] == '1';
     void begin_timed(const char* name) {
+        if (nvtx) nvtxRangePushA(name);
         if (!timing) return;
         if (n_timed == timed.size()) {
             Timed t; t.name = name;
@@ -375,6 +379,7 @@ struct CudaBackend {
         CUDA_TRY(cudaEventRecord(timed[n_timed].a, stream));
     }
     void end_timed() {
+        if (nvtx) nvtxRangePop();
         if (!timing) return;
         CUDA_TRY(cudaEventRecord(timed[n_timed].b, stream));
         n_timed++;
