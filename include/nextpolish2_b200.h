@@ -63,6 +63,22 @@ void    np2_engine_last_stats(np2_engine* e, int64_t out[4]);
  * of the warp-per-segment one: an A/B switch for measurements.) */
 int32_t np2_engine_kernel_times(np2_engine* e, const char** names, float* ms, int32_t cap);
 
+/* ---- the stage in front of the first pass, on the host: the BAM records of one contig -> the alignment strings of its
+ * consensus windows.  Restates the record loop of ctg_cns_core (ctg_cns.c:3444-3566: window geometry with `window` /
+ * `overlap` positions — the reference uses >= 5 Mb / 1 Mb —, record filters, bam2aln, clip_aln, get_align_shift, the
+ * coverage caps, and the draft as read_ref's 2-bit packing leaves it) for everything that does not need the large-indel
+ * machinery; a contig longer than 100 kb with a split-read gap on a supplementary record is refused (NULL,
+ * np2_last_error: code -10).  Needs <bam>.bai.  np2_windows_batch fills a batch that points into the handle (valid until
+ * np2_windows_free) and can go straight into np2_first_pass. */
+typedef struct np2_windows np2_windows;
+np2_windows* np2_windows_from_bam(const char* fasta, const char* bam, const char* contig, int32_t read_type, int32_t window, int32_t overlap);
+int32_t      np2_windows_count(const np2_windows* w);
+/* window i: [start, end) on the contig, its number of alignments (the window itself included) and an FNV-1a hash over
+ * (start, length, target string, read string) of every alignment in order (diagnostics / tests) */
+void         np2_windows_info(const np2_windows* w, int32_t i, int32_t* start, int32_t* end, int32_t* n_alignments, uint64_t* hash);
+void         np2_windows_batch(const np2_windows* w, np2_window_batch* out);
+void         np2_windows_free(np2_windows* w);
+
 #ifdef __cplusplus
 }
 #endif

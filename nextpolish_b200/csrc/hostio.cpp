@@ -462,6 +462,8 @@ bool BamFile::scan(uint64_t voff, int threads, const std::function<bool(const Ba
         r.seq = q + 4 * (size_t)r.n_cigar;
         r.qual = r.seq + ((size_t)r.l_qseq + 1) / 2;
         if ((size_t)(r.qual + r.l_qseq - p) > (size_t)bs) { err = "corrupt BAM record layout"; return false; }
+        r.aux = r.qual + r.l_qseq;
+        r.l_aux = (int32_t)((size_t)bs - (size_t)(r.aux - p));
         s.pos += (size_t)bs + 4;
         if (!visit(r)) return true;
     }

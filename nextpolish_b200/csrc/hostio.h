@@ -51,6 +51,8 @@ struct BamRec {
     const uint32_t* cigar;   // may be unaligned: use memcpy
     const uint8_t*  seq;
     const uint8_t*  qual;
+    const uint8_t*  aux;     // optional fields (tag, type, value ...), l_aux bytes
+    int32_t  l_aux;
 };
 
 class BamFile {

@@ -12,8 +12,9 @@
 #include "lgs_first_pass.h"
 #include "../../include/nextpolish2_b200.h"
 
+namespace { thread_local std::string g_err; }
+namespace np2x { void set_error(const std::string& m) { g_err = m; } }      // shared with lgs_hostio.cpp
 namespace {
-thread_local std::string g_err;
 
 struct CudaOps {
     __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }

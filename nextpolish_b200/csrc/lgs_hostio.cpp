@@ -1,0 +1,340 @@
+// lgs_hostio.cpp — the stage in front of the long-read first pass, on the host: BAM records of one contig -> the clipped,
+// anchored alignment strings of its consensus windows (np2_window_batch, include/nextpolish2_b200.h).  Restates the record
+// loop of ctg_cns_core (source/lib/ctg_cns.c:3444-3566) for the part that does not need the large-indel machinery:
+//   window geometry   cal_win_len :2800, loop :3455-3457,3594      record filters   :3478-3515 (flags 0xD04, aligned fraction)
+//   split-read gap    set_satags :2158, check_indel :2463         strings          bam2aln :2403
+//   clipping          clip_aln :2809                               anchoring        get_align_shift :139 (exact 8-mers)
+//   coverage caps     :3544-3545 (needs the running coverage of get_align_tags :1232-1234)
+//   the draft as the reference sees it: read_ref's 2-bit packing and unpacking (bseq.c:87-123, nt_table :7-16) — a base that
+//   is not A/C/G/T/U becomes 'A' and sets the low bit of the base before it inside the same 16-base word.
+// A contig longer than INS_MIN_CHECK_LEN (100 kb) on which a supplementary / secondary record carries a split-read gap would
+// switch the reference's large-indel path on (:3503-3504,3567-3583): not built — the loader reports it (code -10).
+// Pinned against the reference's own functions run by oracle/ref2_shim.c (np2_ref_contig_windows): window ranges, alignment
+// counts and a hash over every alignment string (tests/test_lgs_from_bam.py).  Host plumbing: no compute of the path here.
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hostio.h"
+#include "../../include/nextpolish2_b200.h"
+
+namespace np2x { void set_error(const std::string& m); }
+
+namespace {
+enum { INS_MIN_CHECK_LEN = 100000, INS_RADOM_LEN = 15000000, MAX_GAP_LEN = 30000 };
+const char NT16[] = "=ACMGRSVTWYHKDBN";
+
+struct Aln {                        // alignment (ctg_cns.h:150-162), the fields this stage touches
+    int64_t shift = 0, aln_len = 0, t_s = 0, t_e = 0, q_s = 0, q_e = 0;
+    std::string t, q;
+};
+struct Pos { uint32_t s, e; };
+struct Gap { Pos gap; uint32_t fs, ds, score; };
+
+uint64_t fnv(uint64_t h, const void* p, size_t n) {
+    const unsigned char* c = (const unsigned char*)p;
+    for (size_t i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
+// read_ref + bit2seq1: what ctg_cns_core's rfseq holds
+std::string two_bit_roundtrip(const std::string& seq) {
+    static const uint8_t nt[128] = {
+        4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4, 4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4, 4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4, 4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,
+        4,0,4,1,4,4,4,2,4,4,4,4,4,4,4,4, 4,4,4,4,3,3,4,4,4,4,4,4,4,4,4,4, 4,0,4,1,4,4,4,2,4,4,4,4,4,4,4,4, 4,4,4,4,3,3,4,4,4,4,4,4,4,4,4,4};
+    std::string out(seq.size(), 'A');
+    for (size_t w0 = 0; w0 < seq.size(); w0 += 16) {
+        uint32_t buffer = 0;
+        const size_t n = std::min<size_t>(16, seq.size() - w0);
+        for (size_t i = 0; i < n; i++) buffer = buffer << 2 | nt[(uint8_t)seq[w0 + i] & 127];
+        for (size_t i = 0; i < n; i++) out[w0 + i] = "ACGT"[(buffer >> (2 * (n - 1 - i))) & 3];
+    }
+    return out;
+}
+
+int32_t cal_win_len(int w, int s, uint64_t l) {                                      // :2800-2807
+    int b = (int)l;
+    if (l > (uint64_t)w) {
+        const int n = (int)((float)(l - s) / (w - s) + 0.999);
+        b = (int)((float)(l + (uint64_t)(n - 1) * s) / n + 0.999);
+    }
+    return b;
+}
+uint32_t cig(const uint32_t* c, uint32_t i) { uint32_t v; memcpy(&v, c + i, 4); return v; }
+int32_t l_qseq_from_cigar(const uint32_t* c, uint32_t n) {                           // cal_l_qseq_from_cigar :2337-2352: S H M = X I
+    int32_t r = 0;
+    for (uint32_t i = 0; i < n; i++) { const uint32_t op = cig(c, i) & 15, len = cig(c, i) >> 4; if (op == 4 || op == 5 || op == 0 || op == 7 || op == 8 || op == 1) r += (int32_t)len; }
+    return r;
+}
+int32_t cal_l_qseq(const np::BamRec& r) {                                            // :2354-2366
+    if (!r.l_qseq) return l_qseq_from_cigar(r.cigar, r.n_cigar);
+    const uint32_t op0 = cig(r.cigar, 0) & 15;
+    if (op0 == 4) return r.l_qseq;
+    int32_t rlen = r.l_qseq;
+    if (op0 == 5) rlen += (int32_t)(cig(r.cigar, 0) >> 4);
+    const uint32_t last = cig(r.cigar, r.n_cigar - 1);
+    if ((last & 15) == 5) rlen += (int32_t)(last >> 4);
+    return rlen;
+}
+uint32_t cigar_clip(const np::BamRec& r, int end) {                                  // cigarint2ul :2314-2320
+    const uint32_t c = cig(r.cigar, end ? r.n_cigar - 1 : 0);
+    return ((c & 15) == 4 || (c & 15) == 5) ? c >> 4 : 0;
+}
+int64_t bam_endpos(const np::BamRec& r) {                                            // htslib: M D N = X consume the reference
+    int64_t l = 0;
+    for (uint32_t i = 0; i < r.n_cigar; i++) { const uint32_t op = cig(r.cigar, i) & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) l += cig(r.cigar, i) >> 4; }
+    return r.pos + (l ? l : 1);
+}
+uint32_t cigarstr2ul(const char* s, int end) {                                       // :2368-2385
+    if (end) {
+        int index = 0;
+        while (*(s + 1) != '\0') { if (*s >= '0' && *s <= '9') index++; else index = 0; s++; }
+        s -= index;
+    }
+    uint32_t result = 0;
+    while (*s >= '0' && *s <= '9') { result = result * 10 + (uint32_t)(*s - '0'); s++; }
+    if (*s != 'H' && *s != 'S') result = 0;
+    return result;
+}
+int32_t cigarstr2rlen(const char* s) {                                               // :2387-2400
+    uint32_t rlen = 0, clen = 0;
+    for (; *s; s++) { if (*s >= '0' && *s <= '9') clen = clen * 10 + (uint32_t)(*s - '0'); else { if (*s == 'M' || *s == 'D') rlen += clen; clen = 0; } }
+    return (int32_t)rlen;
+}
+uint32_t mabs(uint32_t x, uint32_t y) { return x > y ? x - y : y - x; }
+void check_indel(Gap* g, int32_t rlen, const Pos* rfp1, const Pos* rdp1, const Pos* rfp2, const Pos* rdp2) {   // :2463-2492
+    int l = 0;
+    const int32_t mclen = (int32_t)(rlen * 0.1);
+    if (rfp1->s > rfp2->s) { l = 1; std::swap(rfp1, rfp2); std::swap(rdp1, rdp2); }
+    if (rfp2->e > rfp1->e && rdp2->e > rdp1->e && (int64_t)rdp1->s < mclen && (int64_t)rdp2->e > (int64_t)rlen - mclen &&
+        mabs(rfp2->s, rfp1->e) < MAX_GAP_LEN && mabs(rdp2->s, rdp1->e) < MAX_GAP_LEN && rfp1->s != rfp2->s) {
+        const uint32_t score = rdp1->s + (uint32_t)rlen - rdp2->e + mabs(rfp2->s, rfp1->e) + mabs(rdp2->s, rdp1->e);
+        if (score < g->score || !g->score) {
+            g->score = score; g->ds = l ? rdp1->s : rdp2->s; g->fs = l ? rfp1->s : rfp2->s;
+            if (rfp1->e < rfp2->s) { g->gap.s = rfp1->e; g->gap.e = rfp2->s; } else { g->gap.s = rfp2->s; g->gap.e = rfp1->e; }
+        }
+    }
+}
+// the Z value of aux tag SA, or null
+const char* aux_sa(const np::BamRec& r, size_t* len) {
+    const uint8_t* p = r.aux; const uint8_t* end = r.aux + r.l_aux;
+    while (p + 3 <= end) {
+        const char t0 = (char)p[0], t1 = (char)p[1], ty = (char)p[2];
+        p += 3;
+        size_t sz = 0;
+        switch (ty) {
+        case 'A': case 'c': case 'C': sz = 1; break;
+        case 's': case 'S': sz = 2; break;
+        case 'i': case 'I': case 'f': sz = 4; break;
+        case 'd': sz = 8; break;
+        case 'Z': case 'H': { const uint8_t* q = p; while (q < end && *q) q++; if (t0 == 'S' && t1 == 'A' && ty == 'Z') { *len = (size_t)(q - p); return (const char*)p; } p = q + 1; continue; }
+        case 'B': { if (p + 5 > end) return nullptr; const char st = (char)p[0]; uint32_t n; memcpy(&n, p + 1, 4); const size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; p += 5 + es * (size_t)n; continue; }
+        default: return nullptr;
+        }
+        p += sz;
+    }
+    return nullptr;
+}
+// bam2aln :2403-2457: returns the reference position after the alignment, -1 on an operation the reference rejects
+int64_t bam2aln(Aln& a, const std::string& rf, const np::BamRec& r) {
+    uint32_t rdi = 0; int64_t rfi = a.t_s;
+    for (uint32_t i = 0; i < r.n_cigar; i++) {
+        uint32_t n = cig(r.cigar, i) >> 4; const uint32_t c = cig(r.cigar, i) & 15;
+        switch (c) {
+        case 4: case 5: rdi += n; break;
+        case 3: a.t_s += n; rfi += n; break;
+        case 0: while (n--) { a.t.push_back(rfi < (int64_t)rf.size() ? rf[(size_t)rfi] : 'N'); rfi++; a.q.push_back(NT16[(r.seq[rdi >> 1] >> ((~rdi & 1) << 2)) & 15]); rdi++; } break;
+        case 1: while (n--) { a.t.push_back('-'); a.q.push_back(NT16[(r.seq[rdi >> 1] >> ((~rdi & 1) << 2)) & 15]); rdi++; } break;
+        case 2: while (n--) { a.t.push_back(rfi < (int64_t)rf.size() ? rf[(size_t)rfi] : 'N'); rfi++; a.q.push_back('-'); } break;
+        default: return -1;
+        }
+    }
+    a.aln_len = (int64_t)a.t.size();
+    return rfi;
+}
+void clip_aln(Aln& a, int32_t s, int32_t e, int l) {                                 // :2809-2827 (works on columns 0 .. aln_len of t / q)
+    int64_t s_ = 0, e_ = a.aln_len - 1;
+    while (a.t_s < s) { if (a.t[(size_t)s_++] != '-') a.t_s++; if (l && a.q[(size_t)(s_ - 1)] != '-') a.q_s++; }
+    while (a.t[(size_t)s_] == '-') s_++;
+    while (a.t_e > e) { if (a.t[(size_t)e_--] != '-') a.t_e--; if (l && a.q[(size_t)(e_ + 1)] != '-') a.q_e--; }
+    if (e_ > s_ + 500) {
+        a.aln_len = e_ - s_ + 1;
+        a.t.erase(0, (size_t)s_); a.q.erase(0, (size_t)s_);                          // memmove to the front
+    } else a.aln_len = 10;
+}
+void get_align_shift(Aln& a, int k, int l) {                                         // :139-197
+    int64_t i = 0, j = 0;
+    while (i < a.aln_len) {
+        if (a.t[(size_t)i] == a.q[(size_t)i]) j++; else j = 0;
+        if (a.t[(size_t)i] != '-') a.t_s++;
+        if (l && a.q[(size_t)i] != '-') a.q_s++;
+        if (j == k) { a.t_s -= k; a.shift = i - k + 1; a.aln_len = a.aln_len - i + k - 1; if (l) a.q_s -= k; break; }
+        i++;
+    }
+    if (j == k) {
+        i = a.aln_len + i - k; j = 0;
+        int64_t t = 0;
+        while (i >= 0) {
+            if (a.t[(size_t)i] == a.q[(size_t)i]) j++; else j = 0;
+            if (a.t[(size_t)i] != '-') a.t_e--;
+            if (l && a.q[(size_t)i] != '-') a.q_e--;
+            if (j == k) { a.t_e += k; a.aln_len = a.aln_len - t + k - 1; if (l) a.q_e += k; break; }
+            i--; t++;
+        }
+    } else a.aln_len = 0;
+}
+
+struct Window {
+    int32_t s, e; int64_t beg, rege; bool closed = false;
+    std::vector<uint16_t> cov;                                                       // msa[].coverage of get_align_tags
+    std::vector<uint32_t> aln_t_s, aln_len; std::vector<uint64_t> str_off;
+    std::string t, q;
+    uint64_t hash = 14695981039346656037ULL;
+    void add(const Aln& a) {
+        const uint32_t ts = (uint32_t)a.t_s, n = (uint32_t)a.aln_len;
+        aln_t_s.push_back(ts); aln_len.push_back(n); str_off.push_back(t.size());
+        t.append(a.t, (size_t)a.shift, (size_t)n); q.append(a.q, (size_t)a.shift, (size_t)n);
+        hash = fnv(hash, &ts, 4); hash = fnv(hash, &n, 4);
+        hash = fnv(hash, a.t.data() + a.shift, n); hash = fnv(hash, a.q.data() + a.shift, n);
+        int64_t te = (int64_t)a.t_s - 1;                                             // coverage as get_align_tags counts it (:1232-1234)
+        for (uint32_t i = 0; i < n; i++) {
+            const char tc = a.t[(size_t)a.shift + i];
+            bool first = false;
+            if (tc != '-') { te++; first = true; }
+            if (first && a.q[(size_t)a.shift + i] != 'M' && te >= 0 && te < (int64_t)cov.size()) cov[(size_t)te]++;
+        }
+    }
+};
+}  // namespace
+
+struct np2_windows {
+    std::vector<Window> win;
+    int32_t read_type = 1, min_cov = 4;
+    std::vector<int32_t> win_len, win_aln0; std::vector<uint32_t> aln_t_s, aln_len; std::vector<uint64_t> str_off; std::string t, q;
+};
+
+extern "C" {
+
+void np2_windows_free(np2_windows* w) { delete w; }
+int32_t np2_windows_count(const np2_windows* w) { return w ? (int32_t)w->win.size() : 0; }
+void np2_windows_info(const np2_windows* w, int32_t i, int32_t* start, int32_t* end, int32_t* n_alignments, uint64_t* hash) {
+    if (!w || i < 0 || (size_t)i >= w->win.size()) return;
+    const Window& x = w->win[(size_t)i];
+    if (start) *start = x.s;
+    if (end) *end = x.e;
+    if (n_alignments) *n_alignments = (int32_t)x.aln_len.size();
+    if (hash) *hash = x.hash;
+}
+void np2_windows_batch(const np2_windows* w, np2_window_batch* out) {
+    if (!w || !out) return;
+    out->n_windows = (int32_t)w->win.size(); out->win_len = w->win_len.data(); out->win_aln0 = w->win_aln0.data();
+    out->read_type = w->read_type; out->min_cov = w->min_cov;
+    out->aln_t_s = w->aln_t_s.data(); out->aln_len = w->aln_len.data(); out->str_off = w->str_off.data();
+    out->t_str = w->t.data(); out->q_str = w->q.data(); out->str_bytes = (int64_t)w->t.size();
+}
+
+np2_windows* np2_windows_from_bam(const char* fasta, const char* bam, const char* contig, int32_t read_type, int32_t window, int32_t overlap) {
+    std::string err;
+    if (!fasta || !bam || !contig || window <= overlap || overlap < 0) { np2x::set_error("np2_windows_from_bam: bad arguments"); return nullptr; }
+    std::vector<np::FastaRecord> fr;
+    if (!np::fasta_load(fasta, {contig}, fr, err) || fr.size() != 1) { np2x::set_error("np2_windows_from_bam: " + (err.empty() ? std::string("contig not in the FASTA") : err)); return nullptr; }
+    const std::string rf = two_bit_roundtrip(fr[0].seq);
+    const int64_t L = (int64_t)rf.size();
+    np::BamFile bf;
+    if (!bf.open(bam, err)) { np2x::set_error("np2_windows_from_bam: " + err); return nullptr; }
+    int tid = -1;
+    for (size_t i = 0; i < bf.header().names.size(); i++) if (bf.header().names[i] == contig) tid = (int)i;
+    np2_windows* W = new np2_windows();
+    W->read_type = read_type; W->min_cov = 4;                                        // ctg_cns_core passes min_cov 4 (:3587)
+    const double max_clip_ratio = read_type == 3 ? 0.1 : 0.7;                        // :3443
+    // windows (:3448, :3455-3457, :3594); every window starts with itself as the first alignment (:3458-3468)
+    const int32_t b = cal_win_len(window, overlap, (uint64_t)L);
+    for (int32_t s = 0, e = 0; e < L;) {
+        e = s + b > L ? (int32_t)L : s + b;
+        Window x;
+        x.s = s; x.e = e; x.beg = s > 0 ? s - 1 : 0;                                  // the region string "ctg:s-rege" is 1-based (:3473)
+        x.rege = s == 0 ? (e > INS_RADOM_LEN ? e : INS_RADOM_LEN) : e;
+        x.cov.assign((size_t)(e - s) + 1, 0);
+        Aln self; self.t = rf.substr((size_t)s, (size_t)(e - s)); self.q = self.t; self.aln_len = e - s; self.t_s = 0;
+        x.add(self);
+        W->win.push_back(std::move(x));
+        s = e - overlap;
+    }
+    int32_t rc = 0;
+    uint64_t voff = 0; bool has = false;
+    if (tid >= 0 && L > 0) {
+        if (!bf.bai_first_offset(tid, &voff, &has, err)) { np2x::set_error("np2_windows_from_bam: " + err + " (the BAM needs its .bai index)"); delete W; return nullptr; }
+    }
+    if (has) {
+        auto visit = [&](const np::BamRec& r) -> bool {
+            if (r.tid != tid) return r.tid < tid && r.tid >= 0;                      // records before the contig in the first chunk's block: skip; after: stop
+            if (r.n_cigar == 0) return true;
+            const int64_t endpos = bam_endpos(r);
+            const int32_t l_qseq = cal_l_qseq(r);
+            Pos rfp1{(uint32_t)r.pos, (uint32_t)endpos}, rdp1{cigar_clip(r, 0), (uint32_t)l_qseq - cigar_clip(r, 1)}, rfp2, rdp2;
+            Gap g; memset(&g, 0, sizeof g);
+            size_t salen = 0;
+            if (const char* sa = aux_sa(r, &salen)) {                                // set_satags :2158-2179 + the loop :3491-3502
+                std::string z(sa, salen);
+                const uint8_t strand = r.flag & 16 ? 1 : 0;
+                size_t p = 0;
+                while (p < z.size()) {
+                    size_t semi = z.find(';', p); if (semi == std::string::npos) semi = z.size();
+                    std::vector<std::string> f; size_t a0 = p;
+                    while (a0 <= semi) { size_t c = z.find(',', a0); if (c == std::string::npos || c > semi) c = semi; f.emplace_back(z, a0, c - a0); a0 = c + 1; }
+                    if (f.size() >= 4 && f[0] == contig && (uint8_t)(f[2][0] == '+' ? 0 : 1) == strand) {
+                        rfp2.s = (uint32_t)(atoll(f[1].c_str()) - 1); rfp2.e = rfp2.s + (uint32_t)cigarstr2rlen(f[3].c_str());
+                        rdp2.s = cigarstr2ul(f[3].c_str(), 0); rdp2.e = (uint32_t)l_qseq - cigarstr2ul(f[3].c_str(), 1);
+                        check_indel(&g, l_qseq, &rfp1, &rdp1, &rfp2, &rdp2);
+                    }
+                    p = semi + 1;
+                }
+            }
+            Aln full; bool have_full = false; int64_t full_end = 0;
+            for (Window& x : W->win) {
+                if (!(r.pos < x.rege && endpos > x.beg)) continue;                    // htslib's region iterator
+                if (x.closed) continue;
+                if (r.pos >= x.e) { x.closed = true; }                                // `if (p >= e) rege = 0` (:3478): nothing after it is aligned
+                if (!x.closed && (r.flag & 0xD04) && L > INS_MIN_CHECK_LEN && g.score) { rc = -10; return false; }   // sup_aln (:3503-3504)
+                if (r.flag & 0xD04) continue;
+                if (!g.score && (double)(rdp1.e - rdp1.s) / (double)l_qseq <= max_clip_ratio) continue;   // :3510
+                if (x.closed) continue;
+                if (!have_full) {
+                    full.t_s = r.pos; full.t_e = endpos; full.q_s = rdp1.s; full.q_e = rdp1.e;
+                    full_end = bam2aln(full, rf, r);
+                    have_full = true;
+                }
+                if (full_end != endpos) { rc = -12; return false; }                   // "bamaln error" (:3527-3530): an operation bam2aln rejects
+                Aln a = full;
+                if (a.t_s < x.s || a.t_e > x.e) clip_aln(a, x.s, x.e, (int)g.score);
+                get_align_shift(a, 8, (int)g.score);
+                if (a.t_s > a.t_e - 500) continue;
+                a.t_s -= x.s; a.t_e -= x.s;
+                const uint16_t c0 = x.cov[(size_t)a.t_s], c1 = x.cov[(size_t)a.t_e];
+                if ((c0 > 3000 && c1 > 3000) || (c0 > 500 && c1 > 500 && (double)(rdp1.e - rdp1.s) < l_qseq * 0.9)) continue;   // :3544-3545
+                if (a.aln_len <= 0) continue;                                         // (an empty tag list changes nothing in the reference)
+                x.add(a);
+            }
+            return true;
+        };
+        if (!bf.scan(voff, 4, visit, err) && rc == 0) { np2x::set_error("np2_windows_from_bam: " + err); delete W; return nullptr; }
+    }
+    if (rc == -10) { np2x::set_error("np2_windows_from_bam: a split-read gap on a contig longer than 100 kb needs the reference's large-indel path, which is not built (code -10)"); delete W; return nullptr; }
+    if (rc == -12) { np2x::set_error("np2_windows_from_bam: CIGAR operation outside M/I/D/N/S/H (the reference stops with \"bamaln error\") (code -12)"); delete W; return nullptr; }
+    // flatten
+    W->win_aln0.push_back(0);
+    for (const Window& x : W->win) {
+        W->win_len.push_back(x.e - x.s);
+        const uint64_t base = W->t.size();
+        for (size_t i = 0; i < x.aln_len.size(); i++) { W->aln_t_s.push_back(x.aln_t_s[i]); W->aln_len.push_back(x.aln_len[i]); W->str_off.push_back(base + x.str_off[i]); }
+        W->t += x.t; W->q += x.q;
+        W->win_aln0.push_back((int32_t)W->aln_len.size());
+    }
+    for (Window& x : W->win) { std::string().swap(x.t); std::string().swap(x.q); std::vector<uint16_t>().swap(x.cov); }
+    return W;
+}
+
+}  // extern "C"

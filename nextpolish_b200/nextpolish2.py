@@ -14,7 +14,8 @@ import numpy as np
 
 LIB2_PATH = os.path.join(os.path.dirname(os.path.realpath(__file__)), "lib", "nextpolish2.so")
 EXPORTS2 = ["np2_engine_create", "np2_engine_destroy", "np2_last_error", "np2_first_pass", "np2_engine_launch_count",
-            "np2_engine_last_stats", "np2_engine_kernel_times"]                     # every symbol include/nextpolish2_b200.h declares
+            "np2_engine_last_stats", "np2_engine_kernel_times",
+            "np2_windows_from_bam", "np2_windows_count", "np2_windows_info", "np2_windows_batch", "np2_windows_free"]                     # every symbol include/nextpolish2_b200.h declares
 ERRORS = {-1: "output capacity too small", -2: "a window's last position has no node",
           -3: "an alignment is empty, starts on a gap column or leaves its window",
           -4: "backtrack through a node without links", -5: "size limit", -6: "CUDA failure"}
@@ -51,6 +52,15 @@ def lib2():
         L.np2_engine_last_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.np2_engine_last_stats.restype = None
         L.np2_engine_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.np2_windows_from_bam.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]
+        L.np2_windows_from_bam.restype = C.c_void_p
+        L.np2_windows_count.argtypes = [C.c_void_p]
+        L.np2_windows_info.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.np2_windows_info.restype = None
+        L.np2_windows_batch.argtypes = [C.c_void_p, C.POINTER(WindowBatch)]
+        L.np2_windows_batch.restype = None
+        L.np2_windows_free.argtypes = [C.c_void_p]
+        L.np2_windows_free.restype = None
         _LIB2 = L
     return _LIB2
 
@@ -78,11 +88,74 @@ def split_result(n, pos, base, qv, off, n_windows):
     return [(pos[off[i]:off[i + 1]].copy(), base[off[i]:off[i + 1]].tobytes(), qv[off[i]:off[i + 1]].copy()) for i in range(n_windows)]
 
 
+class ContigWindows:
+    """np2_windows_from_bam: the consensus windows of one contig with their alignment strings, built on the host from the
+    draft FASTA and an indexed long-read BAM (the record loop of ctg_cns_core, ctg_cns.c:3444-3566)."""
+
+    def __init__(self, fasta, bam, contig, read_type, window=5000000, overlap=1000000):
+        self.h = lib2().np2_windows_from_bam(fasta.encode(), bam.encode(), contig.encode(), read_type, window, overlap)
+        if not self.h:
+            raise NativeError(lib2().np2_last_error().decode(errors="replace"))
+        self.read_type = read_type
+        self.batch = WindowBatch()
+        lib2().np2_windows_batch(self.h, C.byref(self.batch))
+
+    def info(self):
+        """[(start, end, n_alignments, hash)] per window"""
+        out = []
+        for i in range(lib2().np2_windows_count(self.h)):
+            s, e, n, h = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint64()
+            lib2().np2_windows_info(self.h, i, C.byref(s), C.byref(e), C.byref(n), C.byref(h))
+            out.append((s.value, e.value, n.value, h.value))
+        return out
+
+    def windows(self):
+        """The windows as dicts (the form LgsEngine.first_pass and the oracle helpers take); copies."""
+        b, out = self.batch, []
+        n_aln = (C.c_int32 * (b.n_windows + 1)).from_address(b.win_aln0)
+        wl = (C.c_int32 * b.n_windows).from_address(b.win_len)
+        tot = n_aln[b.n_windows]
+        t_s = np.frombuffer((C.c_uint32 * tot).from_address(b.aln_t_s), np.uint32) if tot else np.zeros(0, np.uint32)
+        a_l = np.frombuffer((C.c_uint32 * tot).from_address(b.aln_len), np.uint32) if tot else np.zeros(0, np.uint32)
+        s_o = np.frombuffer((C.c_uint64 * tot).from_address(b.str_off), np.uint64) if tot else np.zeros(0, np.uint64)
+        t_all = C.string_at(b.t_str, b.str_bytes)
+        q_all = C.string_at(b.q_str, b.str_bytes)
+        for i in range(b.n_windows):
+            lo, hi = n_aln[i], n_aln[i + 1]
+            b0 = int(s_o[lo]) if hi > lo else 0
+            b1 = int(s_o[hi - 1] + a_l[hi - 1]) if hi > lo else 0
+            out.append(dict(len=int(wl[i]), read_type=self.read_type, min_cov=b.min_cov, aln_t_s=t_s[lo:hi].copy(), aln_len=a_l[lo:hi].copy(),
+                            str_off=(s_o[lo:hi] - np.uint64(b0)).astype(np.uint64), t_str=t_all[b0:b1], q_str=q_all[b0:b1]))
+        return out
+
+    def close(self):
+        if self.h:
+            lib2().np2_windows_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class LgsEngine:
     def __init__(self, device=0):
         self.h = lib2().np2_engine_create(device)
         if not self.h:
             raise NativeError(lib2().np2_last_error().decode(errors="replace"))
+
+    def first_pass_contig(self, cw):
+        """First pass of every window of a ContigWindows handle (no copies of the strings)."""
+        b = cw.batch
+        cap = int(b.str_bytes) + 16
+        pos, base, qv = np.zeros(cap, np.uint32), np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+        off = np.zeros(b.n_windows + 1, np.int64)
+        n = lib2().np2_first_pass(self.h, C.byref(b), pos.ctypes.data, base.ctypes.data, qv.ctypes.data, cap, off.ctypes.data)
+        if n < 0:
+            raise NativeError("np2_first_pass: %d (%s): %s" % (n, ERRORS.get(n, "?"), lib2().np2_last_error().decode(errors="replace")))
+        return split_result(n, pos, base, qv, off, b.n_windows)
 
     def first_pass(self, windows, read_type, min_cov=4):
         b, keep = make_batch(windows, read_type, min_cov)

@@ -52,3 +52,142 @@ int np2_ref_first_pass(int read_type, int n_reads, const uint32_t *aln_t_s, cons
 	free(c);
 	return n;
 }
+
+/* ---- the stage in front of the first pass: BAM records -> clipped, anchored alignment strings ---------------------------
+ * The record loop of ctg_cns_core (ctg_cns.c:3455-3566) for ONE indexed BAM, written out here with the reference's own
+ * functions (cal_l_qseq, cigarint2ul, set_satags, check_indel, bam2aln, clip_aln, get_align_shift, get_align_tags,
+ * cal_win_len) and its own window geometry (w = window size, ovl = overlap; ctg_cns.c:3368-3372 fixes 1 Mb overlap and
+ * >= 5 Mb windows, the tests also use small ones), restricted to what does not need the large-indel machinery: it
+ * returns -10 as soon as a supplementary / secondary record with a split-read gap is seen on a contig longer than
+ * INS_MIN_CHECK_LEN (the only way `brk_g` survives the loop, :3567).  Per window it reports the number of alignments, an
+ * FNV-1a hash over (start, length, target string, read string) of every alignment in tags_list order, and the first-pass
+ * consensus (fast variant, as np2_ref_first_pass).  Returns the number of windows, -1 (caps), -10, -11 (I/O). */
+static uint64_t fnv(uint64_t h, const void *p, size_t n){
+	const unsigned char *c = p;
+	for (size_t i = 0; i < n; i++){ h ^= c[i]; h *= 1099511628211ULL; }
+	return h;
+}
+
+int np2_ref_contig_windows(const char *bam_path, const char *ctg, const char *rfseq, int ref_len, int read_type, int w, int ovl,
+		int min_cov, int max_windows, int32_t *win_s, int32_t *win_e, int32_t *win_nalns, uint64_t *win_hash,
+		int64_t *win_out_off, uint32_t *out_pos, char *out_base, int64_t cap){
+	READS_TYPE = read_type;
+	if (READS_TYPE != READS_ONT){ GAP_MIN_LEN = 5; GAP_MIN_RATIO1 = 0.3; }
+	else { GAP_MIN_LEN = 3; GAP_MIN_RATIO1 = 0.01; }
+	MAX_CLIP_RATIO = READS_TYPE == READS_HIFI ? 0.1 : 0.7;
+	samFile *fp = sam_open(bam_path, "r");
+	if (!fp) return -11;
+	bam_hdr_t *hdr = sam_hdr_read(fp);
+	hts_idx_t *idx = sam_index_load(fp, bam_path);
+	if (!hdr || !idx) return -11;
+	bam1_t *brecord = bam_init1();
+	alignment aln_, aln;
+	memset(&aln, 0, sizeof(aln));
+	aln.max_aln_len = 100000;
+	aln.t_aln_str = malloc(aln.max_aln_len);
+	aln.q_aln_str = malloc(aln.max_aln_len);
+	satags sas; memset(&sas, 0, sizeof(sas));
+	int32_t j, l, p, s, e, l_qseq, rege, nw = 0, rc = 0;
+	pos rfp1, rdp1, rfp2, rdp2;
+	gap g;
+	int64_t total = 0;
+	int32_t b = cal_win_len(w, ovl, ref_len);
+	s = e = 0;
+	while (e < ref_len && !rc){
+		e = s + b > ref_len ? ref_len : s + b;
+		l = e - s;
+		if (nw >= max_windows) { rc = -1; break; }
+		memset(&aln_, 0, sizeof(aln_));
+		aln_.q_aln_str = aln_.t_aln_str = (char *) rfseq + s;
+		aln_.aln_q_len = aln_.aln_t_len = l;
+		aln_.aln_t_e = aln_.aln_len = l;
+		uint32_t seq_count = 0, seq_count_m = max(l / 1000, 2);
+		msa_p *msa = calloc(l + 1, sizeof(msa_p));
+		align_tags_t *tags_list = malloc(seq_count_m * sizeof(align_tags_t));
+		uint64_t h = 14695981039346656037ULL;
+		get_align_tags(&aln_, &tags_list[seq_count++], msa);
+		h = fnv(h, &aln_.aln_t_s, 4); h = fnv(h, &aln_.aln_len, 4); h = fnv(h, aln_.t_aln_str, l); h = fnv(h, aln_.q_aln_str, l);
+		rege = s == 0 ? (e > INS_RADOM_LEN ? e : INS_RADOM_LEN) : e;
+		char reg[1024];
+		sprintf(reg, "%s:%d-%d", ctg, s, rege);
+		hts_itr_t *it = sam_itr_querys(idx, hdr, reg);
+		p = 0;
+		while (it && sam_itr_next(fp, it, brecord) >= 0){
+			p = brecord->core.pos;
+			if (p >= e) rege = 0;
+			uint32_t *cigar = bam_get_cigar(brecord);
+			l_qseq = cal_l_qseq(brecord);
+			rfp1.s = brecord->core.pos;
+			rfp1.e = bam_endpos(brecord);
+			rdp1.s = cigarint2ul(cigar, brecord->core.n_cigar, 0);
+			rdp1.e = l_qseq - cigarint2ul(cigar, brecord->core.n_cigar, 1);
+			uint8_t *satag_ = bam_aux_get(brecord, "SA");
+			g.score = 0;
+			if (satag_){
+				set_satags(satag_, &sas);
+				uint8_t strand = brecord->core.flag & 16 ? 1 : 0;
+				for (j = 0; j < sas.i; j++){
+					satag *sa = &sas.sa[j];
+					if (strcmp(sa->rname, ctg) == 0 && sa->strand == strand){
+						rfp2.s = sa->pos;
+						rfp2.e = sa->pos + cigarstr2rlen(sa->cigar);
+						rdp2.s = cigarstr2ul(sa->cigar, 0);
+						rdp2.e = l_qseq - cigarstr2ul(sa->cigar, 1);
+						check_indel(&g, l_qseq, &rfp1, &rdp1, &rfp2, &rdp2);
+					}
+				}
+			}
+			if (rege && brecord->core.flag & 0xD04 && ref_len > INS_MIN_CHECK_LEN && g.score) { rc = -10; break; }
+			if (brecord->core.flag & 0xD04) continue;
+			if ((!g.score) && (rdp1.e - rdp1.s) / (double) l_qseq <= MAX_CLIP_RATIO) continue;
+			if (!rege) continue;
+			aln.aln_t_s = rfp1.s;
+			aln.aln_t_e = rfp1.e;
+			aln.aln_q_s = rdp1.s;
+			aln.aln_q_e = rdp1.e;
+			aln.aln_len = aln.shift = 0;
+			l = bam2aln(&aln, rfseq, bam_get_seq(brecord), cigar, brecord->core.n_cigar);
+			if (l != aln.aln_t_e) { rc = -11; break; }
+			if (aln.aln_t_s < s || aln.aln_t_e > e) clip_aln(&aln, s, e, g.score);
+			get_align_shift(&aln, 8, g.score);
+			if (aln.aln_t_s > aln.aln_t_e - 500) continue;
+			aln.aln_t_s -= s;
+			aln.aln_t_e -= s;
+			if ((msa[aln.aln_t_s].coverage > 3000 && msa[aln.aln_t_e].coverage > 3000) ||
+				(msa[aln.aln_t_s].coverage > 500 && msa[aln.aln_t_e].coverage > 500 && rdp1.e - rdp1.s < l_qseq * 0.9)) continue;
+			get_align_tags(&aln, &tags_list[seq_count++], msa);
+			h = fnv(h, &aln.aln_t_s, 4); h = fnv(h, &aln.aln_len, 4);
+			h = fnv(h, aln.t_aln_str + aln.shift, aln.aln_len); h = fnv(h, aln.q_aln_str + aln.shift, aln.aln_len);
+			if (seq_count >= seq_count_m){
+				seq_count_m += 1000;
+				tags_list = realloc(tags_list, seq_count_m * sizeof(align_tags_t));
+			}
+		}
+		if (it) hts_itr_destroy(it);
+		if (rc) { for (uint32_t i = 0; i < seq_count; i++) free(tags_list[i].align_tags); free(tags_list); free(msa); break; }
+		win_s[nw] = s; win_e[nw] = e; win_nalns[nw] = seq_count; win_hash[nw] = h; win_out_off[nw] = total;
+		consensus_data *c = get_cns_from_align_tags(tags_list, msa, seq_count, e - s, min_cov, 0, 1, NULL);
+		if (total + c->len > cap) rc = -1;
+		for (unsigned i = 0; !rc && i < c->len; i++){
+			out_pos[total + i] = c->cns_bases[c->len - 1 - i].pos;
+			out_base[total + i] = c->cns_bases[c->len - 1 - i].base;
+		}
+		if (!rc) total += c->len;
+		free(c->cns_bases); free(c);
+		nw++;
+		s = e - ovl;
+	}
+	if (!rc) win_out_off[nw] = total;
+	free(aln.t_aln_str); free(aln.q_aln_str);
+	if (sas.i_m) free(sas.sa);
+	bam_destroy1(brecord); hts_idx_destroy(idx); bam_hdr_destroy(hdr); sam_close(fp);
+	return rc ? rc : nw;
+}
+
+/* the draft as ctg_cns_core sees it: read_ref's 2-bit packing (seq2bit1) and bit2seq1 (ctg_cns.c:2283,3446) */
+void np2_ref_roundtrip(const char *seq, int len, char *out){
+	uint32_t *s = malloc(sizeof(uint32_t) * (len / 16 + 1));
+	seq2bit1(s, len, (char *) seq);
+	bit2seq1(s, len, out);
+	free(s);
+}

@@ -91,6 +91,40 @@ def md5s(res):
     return {"n": len(base), "pos_md5": hashlib.md5(pos.astype("<u4").tobytes()).hexdigest(), "base_md5": hashlib.md5(base).hexdigest()}
 
 
+GEOMETRIES = [(5000000, 1000000), (20000, 4000), (9000, 1000)]
+
+
+def ref_contig_windows(S, bam, ctg, seq, rt, w, ovl):
+    """np2_ref_contig_windows on the reference's view of the draft -> [(start, end, n_alns, hash, pos, base)]"""
+    rf = C.create_string_buffer(len(seq) + 1)
+    S.np2_ref_roundtrip.argtypes = [C.c_char_p, C.c_int, C.c_char_p]
+    S.np2_ref_roundtrip(seq.encode(), len(seq), rf)
+    MW, cap = 256, len(seq) * 8
+    ws, we, wn = np.zeros(MW, np.int32), np.zeros(MW, np.int32), np.zeros(MW, np.int32)
+    wh, woff = np.zeros(MW, np.uint64), np.zeros(MW + 1, np.int64)
+    pos, base = np.zeros(cap, np.uint32), np.zeros(cap, np.uint8)
+    f = S.np2_ref_contig_windows
+    f.restype = C.c_int
+    f.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int64]
+    n = f(bam.encode(), ctg.encode(), rf.value, len(seq), rt, w, ovl, 4, MW, ws.ctypes.data, we.ctypes.data, wn.ctypes.data,
+          wh.ctypes.data, woff.ctypes.data, pos.ctypes.data, base.ctypes.data, cap)
+    assert n > 0, n
+    return [(int(ws[i]), int(we[i]), int(wn[i]), int(wh[i]), pos[woff[i]:woff[i + 1]].copy(), base[woff[i]:woff[i + 1]].tobytes()) for i in range(n)]
+
+
+def front_goldens(S, fa_path, bam):
+    out = {}
+    for ctg, seq in read_fa(fa_path).items():
+        for w, ovl in GEOMETRIES:
+            for rt in (1, 3):
+                wins = ref_contig_windows(S, bam, ctg, seq, rt, w, ovl)
+                out["%s/w%d_o%d/rt%d" % (ctg, w, ovl, rt)] = [
+                    {"start": a, "end": b, "n_alns": n, "hash": "%016x" % h, "n": len(base),
+                     "pos_md5": hashlib.md5(pos.astype("<u4").tobytes()).hexdigest(), "base_md5": hashlib.md5(base).hexdigest()}
+                    for a, b, n, h, pos, base in wins]
+    return out
+
+
 def main():
     tmp = tempfile.mkdtemp(prefix="npgold_lgs")
     bam = os.path.join(tmp, "lgs.sort.bam")
@@ -147,6 +181,25 @@ def main():
         for rt in (1, 2, 3, 4):
             case = L.synthetic_case(**dict(kw, read_type=rt))
             gold["first_pass"]["%s/rt%d" % (name, rt)] = md5s(L.first_pass_via(S.np2_ref_first_pass, case))
+    # (c) the stage in front: BAM records -> alignment strings (np2_ref_contig_windows: the reference's own functions in
+    # the record loop of ctg_cns_core).  Fixture: a 30 % subsample of the BAM above (lgs_td.bam + .bai, ~1 MB) and the
+    # draft with a few N / lower-case bases written into it (what read_ref's 2-bit packing does to them is part of the pin).
+    import random
+    import shutil
+    sub = os.path.join(OUT, "lgs_td.bam")
+    subprocess.check_call(f"{REF}/samtools view -b -s 7.3 -o {sub} {bam} && {REF}/samtools index {sub}", shell=True)
+    rng = random.Random(5)
+    fa_path = os.path.join(OUT, "lgs_td.fa")
+    with open(fa_path, "w") as f:
+        for name, seq in draft.items():
+            d = list(seq)
+            for _ in range(40):
+                i = rng.randrange(len(d))
+                d[i] = rng.choice(["N", "n", d[i].lower(), "R"])
+            f.write(">%s\n" % name)
+            for i in range(0, len(d), 70):
+                f.write("".join(d[i:i + 70]) + "\n")
+    gold["from_bam"] = front_goldens(S, fa_path, sub)
     json.dump(gold, open(os.path.join(OUT, "lgs_golden.json"), "w"), indent=1, sort_keys=True)
     print("wrote", len(gold["first_pass"]), "first-pass goldens;", gold["whole_path"])
 

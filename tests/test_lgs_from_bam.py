@@ -1,0 +1,121 @@
+"""The stage in front of the long-read first pass: BAM records of a contig -> the alignment strings of its
+consensus windows, np2_windows_from_bam (csrc/lgs_hostio.cpp, host code in nextpolish2.so) against the reference's own
+functions run in the record loop of ctg_cns_core (oracle/ref2_shim.c: np2_ref_contig_windows) — goldens in
+tests/golden/lgs_golden.json["from_bam"] (window ranges, alignment counts, a hash over every alignment string, and the
+reference's first-pass consensus from that BAM), minted by make_golden_lgs.py on a 30 % subsample of the reference's
+test_data long reads mapped with the vendored minimap2 (tests/golden/lgs_td.bam) and a draft with N / lower-case / IUPAC
+bases written into it (read_ref's 2-bit packing is part of the pin).  The loader's batch then goes through the kernel
+bodies of the GPU path in the host test build: BAM -> first-pass consensus equals the reference's."""
+import ctypes as C
+import hashlib
+import json
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from tests import lgs_cases as L
+from tests.conftest import GOLDEN
+from tests.test_lgs_first_pass import _emu2_build
+
+FA = os.path.join(GOLDEN, "lgs_td.fa")
+BAM = os.path.join(GOLDEN, "lgs_td.bam")
+
+
+@pytest.fixture(scope="module")
+def NP2(E):                                                   # E: makes sure the libraries are built
+    from nextpolish_b200 import nextpolish2
+    nextpolish2.lib2()
+    return nextpolish2
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return json.load(open(os.path.join(GOLDEN, "lgs_golden.json")))["from_bam"]
+
+
+def keys(gold):
+    for key in sorted(gold):
+        ctg, geo, rt = key.split("/")
+        w, o = geo[1:].split("_o")
+        yield key, ctg, int(w), int(o), int(rt[2:])
+
+
+def test_windows_and_alignment_strings_match_the_reference(NP2, gold):
+    seen = 0
+    for key, ctg, w, o, rt in keys(gold):
+        cw = NP2.ContigWindows(FA, BAM, ctg, rt, w, o)
+        got = [(s, e, n, "%016x" % h) for s, e, n, h in cw.info()]
+        want = [(x["start"], x["end"], x["n_alns"], x["hash"]) for x in gold[key]]
+        assert got == want, key
+        seen += len(want)
+        cw.close()
+    assert seen > 30                                           # 2 contigs x (1 + 3-4 + 6-7 windows) x 2 read types
+
+
+def test_bam_to_first_pass_consensus_matches_the_reference(NP2, gold):
+    E2 = _emu2_build("libnp2_emu.so")
+    for key, ctg, w, o, rt in keys(gold):
+        cw = NP2.ContigWindows(FA, BAM, ctg, rt, w, o)
+        b = cw.batch
+        cap = int(b.str_bytes) + 16
+        pos, base, qv = np.zeros(cap, np.uint32), np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+        off = np.zeros(b.n_windows + 1, np.int64)
+        n = E2.np2_emu_first_pass_batch(C.byref(b), pos.ctypes.data, base.ctypes.data, qv.ctypes.data, cap, off.ctypes.data, 9, None)
+        assert n > 0, (key, n)
+        for i, x in enumerate(gold[key]):
+            p, s = pos[off[i]:off[i + 1]], base[off[i]:off[i + 1]].tobytes()
+            got = {"n": len(s), "pos_md5": hashlib.md5(p.astype("<u4").tobytes()).hexdigest(), "base_md5": hashlib.md5(s).hexdigest()}
+            assert got == {k: x[k] for k in got}, (key, i)
+        cw.close()
+
+
+def test_windows_as_dicts_round_trip_through_the_oracle(NP2):
+    """ContigWindows.windows(): the same windows as stand-alone inputs (what LgsEngine.first_pass takes)."""
+    import subprocess
+    from tests.conftest import ROOT
+    path = os.path.join(ROOT, "oracle", "libnp2_oracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+    O2 = C.CDLL(path)
+    cw = NP2.ContigWindows(FA, BAM, "tig0000002", 1, 20000, 4000)
+    wins = cw.windows()
+    assert [w["len"] for w in wins] == [e - s for s, e, _, _ in cw.info()]
+    E2 = _emu2_build("libnp2_emu.so")
+    whole = L.first_pass_batch(lambda b, p, ba, q, cap, off: E2.np2_emu_first_pass_batch(b, p, ba, q, cap, off, 0, None), wins)
+    for w, got in zip(wins, whole):
+        want = L.oracle_window(O2, w)
+        assert (got[0] == want[0]).all() and got[1] == want[1] and (got[2] == want[2]).all()
+    cw.close()
+
+
+@pytest.mark.skipif(L.ref_shim() is None, reason="oracle/_ref/libnp2_refshim.so not built (needs /root/reference)")
+def test_live_reference_other_read_types_and_geometry(NP2):
+    from tests.golden.make_golden_lgs import read_fa, ref_contig_windows
+    S = L.ref_shim()
+    draft = read_fa(FA)
+    for ctg in draft:
+        for rt, w, o in ((2, 30000, 5000), (4, 12345, 678)):
+            want = [(a, b, n, h) for a, b, n, h, _, _ in ref_contig_windows(S, BAM, ctg, draft[ctg], rt, w, o)]
+            cw = NP2.ContigWindows(FA, BAM, ctg, rt, w, o)
+            assert cw.info() == want, (ctg, rt, w, o)
+            cw.close()
+
+
+def test_loader_edges(NP2, tmp_path):
+    with pytest.raises(NP2.NativeError, match="not in the FASTA|contig"):
+        NP2.ContigWindows(FA, BAM, "no_such_contig", 1)
+    # a contig the BAM does not know: one window, only the window itself
+    fa2 = str(tmp_path / "two.fa")
+    open(fa2, "w").write(open(FA).read() + ">lonely\n" + "ACGTTGCA" * 50 + "\n")
+    cw = NP2.ContigWindows(fa2, BAM, "lonely", 1)
+    assert [(s, e, n) for s, e, n, _ in cw.info()] == [(0, 400, 1)]
+    cw.close()
+    # without the index the loader says so
+    bam2 = str(tmp_path / "noindex.bam")
+    shutil.copy(BAM, bam2)
+    with pytest.raises(NP2.NativeError, match="bai"):
+        NP2.ContigWindows(FA, bam2, "tig0000001", 1)
+    with pytest.raises(NP2.NativeError, match="bad arguments"):
+        NP2.ContigWindows(FA, BAM, "tig0000001", 1, window=1000, overlap=1000)

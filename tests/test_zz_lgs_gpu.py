@@ -96,3 +96,21 @@ def test_gpu_first_pass_larger_window_deep(lgs, O2):
     got = lgs.first_pass([case], 1, 4)[0]
     assert same(got, want)
     assert abs(len(got[1]) - 60000) < 600
+
+
+def test_gpu_bam_to_first_pass_consensus_matches_the_reference(lgs):
+    """Draft FASTA + indexed long-read BAM -> np2_windows_from_bam (host) -> np2_first_pass (GPU): the reference's own
+    first-pass consensus of every window (goldens minted through oracle/ref2_shim.c), several window geometries."""
+    from nextpolish_b200 import nextpolish2 as NP2
+    gold = json.load(open(os.path.join(GOLDEN, "lgs_golden.json")))["from_bam"]
+    fa, bam = os.path.join(GOLDEN, "lgs_td.fa"), os.path.join(GOLDEN, "lgs_td.bam")
+    for key in sorted(gold):
+        ctg, geo, rt = key.split("/")
+        w, o = geo[1:].split("_o")
+        cw = NP2.ContigWindows(fa, bam, ctg, int(rt[2:]), int(w), int(o))
+        res = lgs.first_pass_contig(cw)
+        assert len(res) == len(gold[key])
+        for (pos, base, _), x in zip(res, gold[key]):
+            got = {"n": len(base), "pos_md5": hashlib.md5(pos.astype("<u4").tobytes()).hexdigest(), "base_md5": hashlib.md5(base).hexdigest()}
+            assert got == {k: x[k] for k in got}, key
+        cw.close()
