@@ -6,9 +6,10 @@
  * generate_cns_from_best_score{,_fast} (:1475-1509, :1839-1857): np2_first_pass below, bit-identical to the reference
  * (tests/test_lgs_first_pass.py, tests/test_zz_lgs_gpu.py).  The reference's own six entry points (read_ref, ctg_cns_init,
  * ctg_cns_core, free_consensus_trimed_data, ctg_cns_destroy, refs_destroy — ctg_cns.c:2269,3355,3399,2151,3384,2195) are
- * NOT exported yet: ctg_cns_core also needs the BAM merge / alignment-string stage in front (bsort.c, ctg_cns.c:2403) and
- * the low-quality-region / POA stage behind (ctg_cns.c:822-1474, dag.c, align.c).  INTEGRATION.md shows where this call
- * sits inside ctg_cns_core.
+ * NOT exported yet: ctg_cns_core also needs the low-quality-region / POA stage behind the first pass (ctg_cns.c:822-1474,
+ * dag.c, align.c), the large-indel path and the window linking (:3053-3330).  The stage in front — BAM records to alignment
+ * strings — exists on the host for one indexed BAM (np2_windows_from_bam below; the reference merges several BAMs,
+ * bsort.c).  INTEGRATION.md shows where these calls sit inside ctg_cns_core.
  *
  * Library: nextpolish_b200/lib/nextpolish2.so (sm_100a only, no CPU path: np2_engine_create fails without a GPU). */
 #ifndef NEXTPOLISH2_B200_H
