@@ -74,7 +74,8 @@ int32_t np2_engine_kernel_times(np2_engine* e, const char** names, float* ms, in
 typedef struct np2_windows np2_windows;
 np2_windows* np2_windows_from_bam(const char* fasta, const char* bam, const char* contig, int32_t read_type, int32_t window, int32_t overlap);
 int32_t      np2_windows_count(const np2_windows* w);
-/* window i: [start, end) on the contig, its number of alignments (the window itself included) and an FNV-1a hash over
+/* window i: [start, end) on the contig, its number of alignments as the reference counts them (the window itself and the
+ * rare alignments left empty by the anchoring included; the empty ones are not in the batch) and an FNV-1a hash over
  * (start, length, target string, read string) of every alignment in order (diagnostics / tests) */
 void         np2_windows_info(const np2_windows* w, int32_t i, int32_t* start, int32_t* end, int32_t* n_alignments, uint64_t* hash);
 void         np2_windows_batch(const np2_windows* w, np2_window_batch* out);

@@ -188,7 +188,7 @@ void get_align_shift(Aln& a, int k, int l) {                                    
 }
 
 struct Window {
-    int32_t s, e; int64_t beg, rege; bool closed = false;
+    int32_t s, e; int64_t beg, rege; bool closed = false; int32_t n_empty = 0;
     std::vector<uint16_t> cov;                                                       // msa[].coverage of get_align_tags
     std::vector<uint32_t> aln_t_s, aln_len; std::vector<uint64_t> str_off;
     std::string t, q;
@@ -225,7 +225,7 @@ void np2_windows_info(const np2_windows* w, int32_t i, int32_t* start, int32_t* 
     const Window& x = w->win[(size_t)i];
     if (start) *start = x.s;
     if (end) *end = x.e;
-    if (n_alignments) *n_alignments = (int32_t)x.aln_len.size();
+    if (n_alignments) *n_alignments = (int32_t)x.aln_len.size() + x.n_empty;
     if (hash) *hash = x.hash;
 }
 void np2_windows_batch(const np2_windows* w, np2_window_batch* out) {
@@ -311,11 +311,15 @@ np2_windows* np2_windows_from_bam(const char* fasta, const char* bam, const char
                 Aln a = full;
                 if (a.t_s < x.s || a.t_e > x.e) clip_aln(a, x.s, x.e, (int)g.score);
                 get_align_shift(a, 8, (int)g.score);
-                if (a.t_s > a.t_e - 500) continue;
+                if ((uint32_t)a.t_s > (uint32_t)a.t_e - 500u) continue;               // unsigned in the reference (:3540): an alignment that ends before position 500 of the contig always passes
                 a.t_s -= x.s; a.t_e -= x.s;
                 const uint16_t c0 = x.cov[(size_t)a.t_s], c1 = x.cov[(size_t)a.t_e];
                 if ((c0 > 3000 && c1 > 3000) || (c0 > 500 && c1 > 500 && (double)(rdp1.e - rdp1.s) < l_qseq * 0.9)) continue;   // :3544-3545
-                if (a.aln_len <= 0) continue;                                         // (an empty tag list changes nothing in the reference)
+                if (a.aln_len <= 0) {                                                 // no exact 8-mer: the reference appends an EMPTY tag list (it changes
+                    const uint32_t ts = (uint32_t)a.t_s, n0 = 0;                      // nothing downstream); counted and hashed like the reference does,
+                    x.hash = fnv(fnv(x.hash, &ts, 4), &n0, 4); x.n_empty++;           // not handed to the first pass
+                    continue;
+                }
                 x.add(a);
             }
             return true;

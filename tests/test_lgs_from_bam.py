@@ -96,7 +96,7 @@ def test_live_reference_other_read_types_and_geometry(NP2):
     S = L.ref_shim()
     draft = read_fa(FA)
     for ctg in draft:
-        for rt, w, o in ((2, 30000, 5000), (4, 12345, 678)):
+        for rt, w, o in ((2, 30000, 5000), (4, 12345, 678), (1, 1200, 100), (3, 501, 0)):      # tiny windows: clip_aln's short branch, the unsigned length test
             want = [(a, b, n, h) for a, b, n, h, _, _ in ref_contig_windows(S, BAM, ctg, draft[ctg], rt, w, o)]
             cw = NP2.ContigWindows(FA, BAM, ctg, rt, w, o)
             assert cw.info() == want, (ctg, rt, w, o)
