@@ -80,6 +80,16 @@ int32_t      np2_windows_count(const np2_windows* w);
 void         np2_windows_info(const np2_windows* w, int32_t i, int32_t* start, int32_t* end, int32_t* n_alignments, uint64_t* hash);
 void         np2_windows_batch(const np2_windows* w, np2_window_batch* out);
 void         np2_windows_free(np2_windows* w);
+/* contig start of window i (what ctg_cns_core keeps as uncorrected_len) for all windows: out[n_windows] */
+void         np2_windows_starts(const np2_windows* w, int32_t* out);
+
+/* ---- behind the first pass: the windows' consensus joined into one sequence the way the reference's FAST mode does
+ * (link_consensus_fast, ctg_cns.c:3053-3119; ctg_cns_core returns this when its local `fast` is set, :3620 — the shipped
+ * reference never sets it: its production mode re-polishes low-quality regions first, which is not built).  Host code.
+ * win_start[i] = contig start of window i, win_off / pos / base = np2_first_pass's outputs, overlap as given to
+ * np2_windows_from_bam.  Returns the length written to out_seq, -1 cap too small, -7 windows that cannot be linked. */
+int64_t      np2_link_windows_fast(int32_t n_windows, const int32_t* win_start, const int64_t* win_off, const uint32_t* pos,
+                                   const char* base, int32_t overlap, char* out_seq, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -228,6 +228,10 @@ void np2_windows_info(const np2_windows* w, int32_t i, int32_t* start, int32_t* 
     if (n_alignments) *n_alignments = (int32_t)x.aln_len.size() + x.n_empty;
     if (hash) *hash = x.hash;
 }
+void np2_windows_starts(const np2_windows* w, int32_t* out) {
+    if (!w || !out) return;
+    for (size_t i = 0; i < w->win.size(); i++) out[i] = w->win[i].s;
+}
 void np2_windows_batch(const np2_windows* w, np2_window_batch* out) {
     if (!w || !out) return;
     out->n_windows = (int32_t)w->win.size(); out->win_len = w->win_len.data(); out->win_aln0 = w->win_aln0.data();
@@ -339,6 +343,62 @@ np2_windows* np2_windows_from_bam(const char* fasta, const char* bam, const char
     }
     for (Window& x : W->win) { std::string().swap(x.t); std::string().swap(x.q); std::vector<uint16_t>().swap(x.cov); }
     return W;
+}
+
+// link_consensus_fast (ctg_cns.c:3053-3119): the windows' first-pass consensus joined into one sequence.  Neighbouring windows
+// overlap by `overlap` positions; around the middle of the overlap the two consensus lists are walked against each other
+// until k = 50 consecutive bases agree in contig position and letter, and the windows are cut there.  The reference walks
+// its lists in backtrack order (index 0 = the window's last base): B(i, j) below is that view of the forward arrays.
+// Returns the length written, -1 when cap is too small, -7 when two windows cannot be linked (the reference would run
+// off its arrays or stop on its assert).
+int64_t np2_link_windows_fast(int32_t n_windows, const int32_t* win_start, const int64_t* win_off, const uint32_t* pos, const char* base,
+                              int32_t overlap, char* out_seq, int64_t cap) {
+    if (n_windows < 0 || (n_windows > 0 && (!win_start || !win_off || !pos || !base || !out_seq))) { np2x::set_error("np2_link_windows_fast: bad arguments"); return -6; }
+    const int k = 50;
+    const int64_t s = overlap / 2;
+    std::vector<int64_t> len((size_t)n_windows), lstrip((size_t)n_windows, 0), rstrip((size_t)n_windows, 0);
+    for (int32_t i = 0; i < n_windows; i++) len[(size_t)i] = win_off[i + 1] - win_off[i];
+    auto P = [&](int32_t i, int64_t j) -> int64_t { return (int64_t)pos[win_off[i] + (len[(size_t)i] - 1 - j)]; };
+    auto Bc = [&](int32_t i, int64_t j) -> char { return base[win_off[i] + (len[(size_t)i] - 1 - j)]; };
+    auto in = [&](int32_t i, int64_t j) { return j >= 0 && j < len[(size_t)i]; };
+    bool bad = false;
+    int l = 0; int32_t last_c = -1, last_n = -1;
+    for (int32_t i = n_windows - 1; i > 0 && !bad; i--) {
+        const int32_t c = i, nx = i - 1;                                             // consensus, consensusnext
+        int64_t& rs = rstrip[(size_t)c]; int64_t& ls = lstrip[(size_t)nx];
+        rs = ls = s;
+        if (len[(size_t)c] <= s || len[(size_t)nx] <= s) { bad = true; break; }
+        #define NP2_CK(ix, jx) if (!in(ix, jx)) { bad = true; break; }
+        while (true) { NP2_CK(c, len[(size_t)c] - rs) if (!(P(c, len[(size_t)c] - rs) < P(c, len[(size_t)c] - 1) + s)) break; rs++; }
+        if (bad) break;
+        while (true) { NP2_CK(c, len[(size_t)c] - rs) if (!(P(c, len[(size_t)c] - rs) > P(c, len[(size_t)c] - 1) + s)) break; rs--; }
+        if (bad) break;
+        while (true) { NP2_CK(nx, ls) if (!(P(nx, ls) < P(nx, 0) - s)) break; ls--; }
+        if (bad) break;
+        while (true) { NP2_CK(nx, ls) if (!(P(nx, ls) > P(nx, 0) - s)) break; ls++; }
+        if (bad) break;
+        l = 0;
+        const int64_t p = (int64_t)win_start[c] - (int64_t)win_start[nx];            // uncorrected_len difference
+        int64_t guard = 0;
+        while (l < k) {
+            NP2_CK(nx, ls) NP2_CK(c, len[(size_t)c] - rs)
+            if (++guard > 4 * (len[(size_t)c] + len[(size_t)nx]) + 1000) { bad = true; break; }
+            const int64_t j = P(nx, ls) - P(c, len[(size_t)c] - rs);
+            if (j == p && Bc(c, len[(size_t)c] - rs) == Bc(nx, ls)) { l++; ls--; rs++; }
+            else { l = 0; if (j >= p) ls++; else ls--; }
+        }
+        #undef NP2_CK
+        last_c = c; last_n = nx;
+    }
+    if (bad) { np2x::set_error("np2_link_windows_fast: neighbouring windows do not link (no 50 agreeing bases around the middle of their overlap) (code -7)"); return -7; }
+    if (n_windows > 1) { rstrip[(size_t)last_c] -= k; lstrip[(size_t)last_n] += k; }    // only the pair handled last, as in the reference (:3094-3098)
+    int64_t n = 0;
+    for (int32_t i = 0; i < n_windows; i++)
+        for (int64_t j = len[(size_t)i] - rstrip[(size_t)i] - 1; j >= lstrip[(size_t)i]; j--) {
+            if (n >= cap) { np2x::set_error("np2_link_windows_fast: output capacity too small"); return -1; }
+            out_seq[n++] = Bc(i, j);
+        }
+    return n;
 }
 
 }  // extern "C"

@@ -15,7 +15,8 @@ import numpy as np
 LIB2_PATH = os.path.join(os.path.dirname(os.path.realpath(__file__)), "lib", "nextpolish2.so")
 EXPORTS2 = ["np2_engine_create", "np2_engine_destroy", "np2_last_error", "np2_first_pass", "np2_engine_launch_count",
             "np2_engine_last_stats", "np2_engine_kernel_times",
-            "np2_windows_from_bam", "np2_windows_count", "np2_windows_info", "np2_windows_batch", "np2_windows_free"]                     # every symbol include/nextpolish2_b200.h declares
+            "np2_windows_from_bam", "np2_windows_count", "np2_windows_info", "np2_windows_batch", "np2_windows_free",
+            "np2_windows_starts", "np2_link_windows_fast"]                     # every symbol include/nextpolish2_b200.h declares
 ERRORS = {-1: "output capacity too small", -2: "a window's last position has no node",
           -3: "an alignment is empty, starts on a gap column or leaves its window",
           -4: "backtrack through a node without links", -5: "size limit", -6: "CUDA failure"}
@@ -61,6 +62,10 @@ def lib2():
         L.np2_windows_batch.restype = None
         L.np2_windows_free.argtypes = [C.c_void_p]
         L.np2_windows_free.restype = None
+        L.np2_windows_starts.argtypes = [C.c_void_p, C.c_void_p]
+        L.np2_windows_starts.restype = None
+        L.np2_link_windows_fast.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+        L.np2_link_windows_fast.restype = C.c_int64
         _LIB2 = L
     return _LIB2
 
@@ -140,6 +145,22 @@ class ContigWindows:
             pass
 
 
+def link_windows_fast(starts, results, overlap):
+    """np2_link_windows_fast over per-window first-pass results [(pos, base, qv)] -> the linked sequence (bytes)."""
+    n = len(results)
+    ws = np.asarray(starts, np.int32)
+    off = np.zeros(n + 1, np.int64)
+    for i, r in enumerate(results):
+        off[i + 1] = off[i] + len(r[1])
+    pos = np.concatenate([r[0] for r in results]).astype(np.uint32) if n else np.zeros(0, np.uint32)
+    base = np.frombuffer(b"".join(r[1] for r in results), np.uint8).copy() if n else np.zeros(0, np.uint8)
+    out = np.zeros(int(off[n]) + 16, np.uint8)
+    m = lib2().np2_link_windows_fast(n, ws.ctypes.data, off.ctypes.data, pos.ctypes.data, base.ctypes.data, overlap, out.ctypes.data, len(out))
+    if m < 0:
+        raise NativeError("np2_link_windows_fast: %d: %s" % (m, lib2().np2_last_error().decode(errors="replace")))
+    return out[:m].tobytes()
+
+
 class LgsEngine:
     def __init__(self, device=0):
         self.h = lib2().np2_engine_create(device)
@@ -156,6 +177,16 @@ class LgsEngine:
         if n < 0:
             raise NativeError("np2_first_pass: %d (%s): %s" % (n, ERRORS.get(n, "?"), lib2().np2_last_error().decode(errors="replace")))
         return split_result(n, pos, base, qv, off, b.n_windows)
+
+    def polish_contig_fast(self, fasta, bam, contig, read_type, window=5000000, overlap=1000000):
+        """FASTA + indexed long-read BAM -> the contig's consensus in the reference's fast mode: windows from the BAM
+        (host), first pass (GPU), link_consensus_fast (host)."""
+        cw = ContigWindows(fasta, bam, contig, read_type, window, overlap)
+        try:
+            res = self.first_pass_contig(cw)
+            return link_windows_fast([s for s, _, _, _ in cw.info()], res, overlap)
+        finally:
+            cw.close()
 
     def first_pass(self, windows, read_type, min_cov=4):
         b, keep = make_batch(windows, read_type, min_cov)

@@ -68,9 +68,9 @@ static uint64_t fnv(uint64_t h, const void *p, size_t n){
 	return h;
 }
 
-int np2_ref_contig_windows(const char *bam_path, const char *ctg, const char *rfseq, int ref_len, int read_type, int w, int ovl,
+static int contig_windows_impl(const char *bam_path, const char *ctg, const char *rfseq, int ref_len, int read_type, int w, int ovl,
 		int min_cov, int max_windows, int32_t *win_s, int32_t *win_e, int32_t *win_nalns, uint64_t *win_hash,
-		int64_t *win_out_off, uint32_t *out_pos, char *out_base, int64_t cap){
+		int64_t *win_out_off, uint32_t *out_pos, char *out_base, int64_t cap, consensuss_data *keep){
 	READS_TYPE = read_type;
 	if (READS_TYPE != READS_ONT){ GAP_MIN_LEN = 5; GAP_MIN_RATIO1 = 0.3; }
 	else { GAP_MIN_LEN = 3; GAP_MIN_RATIO1 = 0.01; }
@@ -173,7 +173,11 @@ int np2_ref_contig_windows(const char *bam_path, const char *ctg, const char *rf
 			out_base[total + i] = c->cns_bases[c->len - 1 - i].base;
 		}
 		if (!rc) total += c->len;
-		free(c->cns_bases); free(c);
+		if (keep && !rc){                               /* as ctg_cns_core stores it (:3587-3593) */
+			c->uncorrected_len = s;
+			keep->consensus[keep->i] = c;
+			if (++keep->i >= keep->i_m){ keep->i_m += 5; keep->consensus = realloc(keep->consensus, keep->i_m * sizeof(consensus_data *)); }
+		}else { free(c->cns_bases); free(c); }
 		nw++;
 		s = e - ovl;
 	}
@@ -190,4 +194,39 @@ void np2_ref_roundtrip(const char *seq, int len, char *out){
 	seq2bit1(s, len, (char *) seq);
 	bit2seq1(s, len, out);
 	free(s);
+}
+
+int np2_ref_contig_windows(const char *bam_path, const char *ctg, const char *rfseq, int ref_len, int read_type, int w, int ovl,
+		int min_cov, int max_windows, int32_t *win_s, int32_t *win_e, int32_t *win_nalns, uint64_t *win_hash,
+		int64_t *win_out_off, uint32_t *out_pos, char *out_base, int64_t cap){
+	return contig_windows_impl(bam_path, ctg, rfseq, ref_len, read_type, w, ovl, min_cov, max_windows, win_s, win_e, win_nalns,
+		win_hash, win_out_off, out_pos, out_base, cap, NULL);
+}
+
+/* The reference's FAST mode for one contig, end to end: the windows' first-pass consensus linked by link_consensus_fast
+ * (ctg_cns.c:3053-3119; what ctg_cns_core returns when its local `fast` is set, :3620 — the shipped code never sets it).
+ * Returns the length of the linked sequence written to out_seq, or a negative code of np2_ref_contig_windows. */
+int64_t np2_ref_contig_fast(const char *bam_path, const char *ctg, const char *rfseq, int ref_len, int read_type, int w, int ovl,
+		char *out_seq, int64_t cap){
+	enum { MW = 4096 };
+	int32_t *ws = malloc(MW * 4), *we = malloc(MW * 4), *wn = malloc(MW * 4);
+	uint64_t *wh = malloc(MW * 8);
+	int64_t *woff = malloc((MW + 1) * 8);
+	int64_t ocap = (int64_t) ref_len * 4 + 1024;
+	uint32_t *pos = malloc(ocap * 4);
+	char *base = malloc(ocap);
+	consensuss_data ct;
+	memset(&ct, 0, sizeof(ct));
+	ct.i_m = 5; ct.s = ovl; ct.w = w;
+	ct.consensus = malloc(ct.i_m * sizeof(consensus_data *));
+	int nw = contig_windows_impl(bam_path, ctg, rfseq, ref_len, read_type, w, ovl, 4, MW, ws, we, wn, wh, woff, pos, base, ocap, &ct);
+	int64_t n = nw;
+	if (nw > 0){
+		consensus_trimed_data *d = link_consensus_fast(&ct, ref_len, 50);
+		n = d->data[0].len;
+		if (n > cap) n = -1; else memcpy(out_seq, d->data[0].seq, n);
+		free_consensus_trimed_data(d);
+	}
+	free(ct.consensus); free(ws); free(we); free(wn); free(wh); free(woff); free(pos); free(base);
+	return n;
 }

@@ -112,6 +112,22 @@ def ref_contig_windows(S, bam, ctg, seq, rt, w, ovl):
     return [(int(ws[i]), int(we[i]), int(wn[i]), int(wh[i]), pos[woff[i]:woff[i + 1]].copy(), base[woff[i]:woff[i + 1]].tobytes()) for i in range(n)]
 
 
+def ref_contig_fast(S, bam, ctg, seq, rt, w, ovl):
+    """np2_ref_contig_fast -> (length, linked sequence).  Window sizes must stay well above the overlap and the overlap
+    above ~100 positions: link_consensus_fast has no bounds on its walks (tiny windows make the reference spin)."""
+    rf = C.create_string_buffer(len(seq) + 1)
+    S.np2_ref_roundtrip.argtypes = [C.c_char_p, C.c_int, C.c_char_p]
+    S.np2_ref_roundtrip(seq.encode(), len(seq), rf)
+    cap = len(seq) * 2 + 1000
+    out = C.create_string_buffer(cap)
+    f = S.np2_ref_contig_fast
+    f.restype = C.c_int64
+    f.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int64]
+    n = f(bam.encode(), ctg.encode(), rf.value, len(seq), rt, w, ovl, out, cap)
+    assert n > 0, n
+    return n, out.raw[:n]
+
+
 def front_goldens(S, fa_path, bam):
     out = {}
     for ctg, seq in read_fa(fa_path).items():
@@ -200,6 +216,13 @@ def main():
             for i in range(0, len(d), 70):
                 f.write("".join(d[i:i + 70]) + "\n")
     gold["from_bam"] = front_goldens(S, fa_path, sub)
+    # (d) the reference's fast mode end to end (np2_ref_contig_fast: first pass of every window + link_consensus_fast)
+    gold["fast_mode"] = {}
+    for ctg, seq in read_fa(fa_path).items():
+        for w, ovl in GEOMETRIES:
+            for rt in (1, 3):
+                n, linked = ref_contig_fast(S, sub, ctg, seq, rt, w, ovl)
+                gold["fast_mode"]["%s/w%d_o%d/rt%d" % (ctg, w, ovl, rt)] = {"len": n, "md5": hashlib.md5(linked).hexdigest()}
     json.dump(gold, open(os.path.join(OUT, "lgs_golden.json"), "w"), indent=1, sort_keys=True)
     print("wrote", len(gold["first_pass"]), "first-pass goldens;", gold["whole_path"])
 

@@ -119,3 +119,32 @@ def test_loader_edges(NP2, tmp_path):
         NP2.ContigWindows(FA, bam2, "tig0000001", 1)
     with pytest.raises(NP2.NativeError, match="bad arguments"):
         NP2.ContigWindows(FA, BAM, "tig0000001", 1, window=1000, overlap=1000)
+
+
+def test_fast_mode_end_to_end_matches_the_reference(NP2):
+    """FASTA + BAM -> windows (host) -> first pass (kernel bodies, host test build) -> np2_link_windows_fast (host) against the
+    reference's fast mode (first pass of every window + link_consensus_fast, ctg_cns.c:3053-3119): the linked contig,
+    byte for byte, for one window and for 3-8 linked windows; the result does not depend on the window geometry."""
+    gold = json.load(open(os.path.join(GOLDEN, "lgs_golden.json")))["fast_mode"]
+    E2 = _emu2_build("libnp2_emu.so")
+    per_contig = {}
+    for key in sorted(gold):
+        ctg, geo, rt = key.split("/")
+        w, o = (int(x) for x in geo[1:].split("_o"))
+        cw = NP2.ContigWindows(FA, BAM, ctg, int(rt[2:]), w, o)
+        b = cw.batch
+        cap = int(b.str_bytes) + 16
+        pos, base, qv = np.zeros(cap, np.uint32), np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+        off = np.zeros(b.n_windows + 1, np.int64)
+        n = E2.np2_emu_first_pass_batch(C.byref(b), pos.ctypes.data, base.ctypes.data, qv.ctypes.data, cap, off.ctypes.data, 0, None)
+        assert n > 0
+        linked = NP2.link_windows_fast([s for s, _, _, _ in cw.info()], NP2.split_result(n, pos, base, qv, off, b.n_windows), o)
+        assert {"len": len(linked), "md5": hashlib.md5(linked).hexdigest()} == gold[key], key
+        per_contig.setdefault((ctg, rt), set()).add(linked)
+        cw.close()
+    assert all(len(v) == 1 for v in per_contig.values())
+    # windows that cannot be linked are reported, not walked off (the reference has no bounds there)
+    pos = np.arange(100, dtype=np.uint32)
+    res = [(pos, b"A" * 100, None), (pos, b"C" * 100, None)]
+    with pytest.raises(NP2.NativeError, match="-7"):
+        NP2.link_windows_fast([0, 60], res, 40)

@@ -114,3 +114,14 @@ def test_gpu_bam_to_first_pass_consensus_matches_the_reference(lgs):
             got = {"n": len(base), "pos_md5": hashlib.md5(pos.astype("<u4").tobytes()).hexdigest(), "base_md5": hashlib.md5(base).hexdigest()}
             assert got == {k: x[k] for k in got}, key
         cw.close()
+
+
+def test_gpu_fast_mode_end_to_end_matches_the_reference(lgs):
+    """LgsEngine.polish_contig_fast: FASTA + BAM -> linked contig consensus, the reference's fast mode byte for byte."""
+    gold = json.load(open(os.path.join(GOLDEN, "lgs_golden.json")))["fast_mode"]
+    fa, bam = os.path.join(GOLDEN, "lgs_td.fa"), os.path.join(GOLDEN, "lgs_td.bam")
+    for key in sorted(gold):
+        ctg, geo, rt = key.split("/")
+        w, o = (int(x) for x in geo[1:].split("_o"))
+        seq = lgs.polish_contig_fast(fa, bam, ctg, int(rt[2:]), w, o)
+        assert {"len": len(seq), "md5": hashlib.md5(seq).hexdigest()} == gold[key], key
