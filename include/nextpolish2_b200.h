@@ -1,7 +1,8 @@
 /* nextpolish2_b200.h — C ABI of the long-read consensus path (reference: nextpolish2.so, built from
  * source/lib/ctg_cns.c, bound by source/lib/nextpolish2.py:54-65).
  *
- * STATUS: first slice.  What runs on the GPU is the FIRST PASS of a consensus window — tags, link tally, score chain and
+ * STATUS: first slice — a contig can be polished end to end in the reference's FAST mode (np2_windows_from_bam ->
+ * np2_first_pass -> np2_link_windows_fast), not yet in its production mode.  What runs on the GPU is the FIRST PASS of a consensus window — tags, link tally, score chain and
  * backtrack, i.e. what get_cns_from_align_tags (ctg_cns.c:1876) does up to and including the backtrack of
  * generate_cns_from_best_score{,_fast} (:1475-1509, :1839-1857): np2_first_pass below, bit-identical to the reference
  * (tests/test_lgs_first_pass.py, tests/test_zz_lgs_gpu.py).  The reference's own six entry points (read_ref, ctg_cns_init,
