@@ -221,3 +221,113 @@ class LgsEngine:
             self.close()
         except Exception:
             pass
+
+
+# ---- host-side mirror of the reference's long-read worker (source/lib/nextpolish2.py) -------------------------------------
+def _read_corrected(path, corrected):
+    """read_corrected_seqs (nextpolish2.py:116-137): finished contigs of an existing output and the offset at which its
+    last record (possibly partial; `_s<k>` pieces of a split contig belong together) starts."""
+    last, cur, pos = "", 0, 0
+    with open(path) as f:
+        for line in f:
+            if line.startswith(">"):
+                parts = line.split()[0].split("_s")
+                last = parts[0][1:]
+                if len(parts) == 1 or parts[1] == "0":
+                    pos += cur
+                    cur = len(line)
+                else:
+                    cur += len(line)
+                corrected.add(last)
+            else:
+                cur += len(line)
+    if last:
+        corrected.discard(last)
+    return pos
+
+
+def _read_uncorrected(path, index, corrected):
+    """read_uncorrected_seqs (nextpolish2.py:98-114), in file order."""
+    names = []
+    with open(path) as f:
+        for line in f:
+            if index != "all":
+                p = line.strip().split()
+                if p and p[0] not in corrected and len(p) > 1 and p[1] == index and p[0] not in names:
+                    names.append(p[0])
+            elif line.startswith(">"):
+                n = line.strip().split()[0][1:]
+                if n not in corrected and n not in names:
+                    names.append(n)
+    return names
+
+
+def main(argv=None):
+    """python -m nextpolish_b200.nextpolish2 -g genome.fa -l lgs.sort.bam.list -r ont --fast [-b blc -i 0] [-o out] [-u] [-w 5M]
+
+    The command line of the reference's lib/nextpolish2.py (block file, resume, `>name len` records, -u, -w) over this
+    engine.  Only the reference's FAST mode exists here (first pass + link_consensus_fast), so the
+    mirror insists on --fast: without it it refuses instead of printing something the reference's default run would not."""
+    import argparse
+    import sys
+    ap = argparse.ArgumentParser(description="Long-read polish on the GPU, the reference's fast mode (mirror of lib/nextpolish2.py).")
+    ap.add_argument("-g", "--genome", required=True)
+    ap.add_argument("-l", "--bam_list", required=True, help="file with the sorted, indexed long-read BAM (one line; the reference merges several)")
+    ap.add_argument("-r", "--read_type", required=True, type=str.lower, choices=["clr", "hifi", "ont"])
+    ap.add_argument("-b", "--block")
+    ap.add_argument("-i", "--block_index", default="all")
+    ap.add_argument("-o", "--out", default="stdout")
+    ap.add_argument("-p", "--process", type=int, default=10)
+    ap.add_argument("-u", "--uppercase", action="store_true")
+    ap.add_argument("-w", "--window", default="5M")
+    ap.add_argument("-a", "--auto", action="store_false", default=True)
+    ap.add_argument("-sp", "--split", action="store_false", default=True)
+    ap.add_argument("-id", "--alignment_identity_ratio", type=float, default=0.8)
+    ap.add_argument("-as", "--alignment_score_ratio", type=float, default=0.8)
+    ap.add_argument("--fast", action="store_true", help="the reference's fast mode (ctg_cns.c:3433,3620): the only one built")
+    args, _unknown = ap.parse_known_args(argv)
+    if not args.fast:
+        sys.stderr.write("only the reference's fast mode is built (pass --fast); its default mode re-polishes low-quality regions "
+                         "(ctg_cns.c:822-1474), which this engine does not do yet: use the reference's nextpolish2.py for it\n")
+        return 1
+    unit = {"k": 1e3, "m": 1e6, "g": 1e9}.get(args.window[-1].lower())
+    window = int(float(args.window[:-1]) * unit) if unit else int(args.window)
+    window = max(window, 5000000)                      # set_window_process never goes below 5 M (nextpolish2.py:75-76)
+    bams = [l.strip() for l in open(args.bam_list) if l.strip()]
+    if len(bams) != 1:
+        sys.stderr.write("exactly one BAM in the list is supported (merging several, bsort.c, is not built)\n")
+        return 1
+    rt = {"ont": 1, "clr": 2, "hifi": 3}[args.read_type]
+    out, corrected = sys.stdout, set()
+    if args.out != "stdout":
+        if os.path.exists(args.out):
+            at = _read_corrected(args.out, corrected)
+            out = open(args.out, "r+")
+            out.seek(at)
+            out.truncate()
+        else:
+            out = open(args.out, "w")
+    block = args.genome if (args.block_index == "all" or not args.block) else args.block
+    names = _read_uncorrected(block, "all" if block == args.genome else args.block_index, corrected)
+    rc = 0
+    if names:
+        eng = LgsEngine(int(os.environ.get("NEXTPOLISH_B200_DEVICE", "0")))
+        for name in names:
+            seq = eng.polish_contig_fast(args.genome, bams[0], name, rt, window, 1000000).decode()
+            if args.uppercase:
+                seq = seq.upper()
+            if len(seq) > 10:                          # nextpolish2.py:199-203
+                out.write(">%s %d\n%s\n" % (name, len(seq), seq))
+            else:
+                sys.stderr.write("Failed to correct sequence: %s\n" % name)
+                rc = 1
+                break
+        eng.close()
+    if out is not sys.stdout:
+        out.close()
+    return rc
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

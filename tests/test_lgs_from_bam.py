@@ -148,3 +148,30 @@ def test_fast_mode_end_to_end_matches_the_reference(NP2):
     res = [(pos, b"A" * 100, None), (pos, b"C" * 100, None)]
     with pytest.raises(NP2.NativeError, match="-7"):
         NP2.link_windows_fast([0, 60], res, 40)
+
+
+def test_worker_mirror_command_line_without_gpu_work(NP2, tmp_path, capsys):
+    """python -m nextpolish_b200.nextpolish2: refuses the production mode, one BAM per list, resume / block rules of
+    nextpolish2.py:98-137 (a finished part leaves nothing to polish: no device is touched)."""
+    lst = tmp_path / "lgs.list"
+    lst.write_text(BAM + "\n")
+    assert NP2.main(["-g", FA, "-l", str(lst), "-r", "ont"]) == 1
+    assert "fast mode" in capsys.readouterr().err
+    two = tmp_path / "two.list"
+    two.write_text(BAM + "\n" + BAM + "\n")
+    assert NP2.main(["-g", FA, "-l", str(two), "-r", "ont", "--fast"]) == 1
+    # resume scan: tig0000001 finished, tig0000002 split into two pieces of which the second is partial -> redone
+    out = tmp_path / "part.fasta"
+    out.write_text(">tig0000001 4\nACGT\n>tig0000002_s0 8\nACGTACGT\n>tig0000002_s1 9\nAC")
+    done = set()
+    at = NP2._read_corrected(str(out), done)
+    assert done == {"tig0000001"} and at == len(">tig0000001 4\nACGT\n")
+    assert NP2._read_uncorrected(FA, "all", done) == ["tig0000002"]
+    blc = tmp_path / "g.blc"
+    blc.write_text("tig0000001\t0\ntig0000002\t1\n\n")
+    assert NP2._read_uncorrected(str(blc), "0", set()) == ["tig0000001"]
+    assert NP2._read_uncorrected(str(blc), "1", {"tig0000002"}) == []
+    # a block whose contigs are all finished: exit 0, the partial tail is cut, nothing else happens
+    out.write_text(">tig0000001 4\nACGT\n>tig0000002 8\nACGTACGT\n>tig0000002 3\nAC")
+    assert NP2.main(["-g", FA, "-l", str(lst), "-r", "hifi", "--fast", "-b", str(blc), "-i", "0", "-o", str(out), "-w", "5M"]) == 0
+    assert out.read_text() == ">tig0000001 4\nACGT\n>tig0000002 8\nACGTACGT\n"

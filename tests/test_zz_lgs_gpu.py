@@ -125,3 +125,27 @@ def test_gpu_fast_mode_end_to_end_matches_the_reference(lgs):
         w, o = (int(x) for x in geo[1:].split("_o"))
         seq = lgs.polish_contig_fast(fa, bam, ctg, int(rt[2:]), w, o)
         assert {"len": len(seq), "md5": hashlib.md5(seq).hexdigest()} == gold[key], key
+
+
+def test_gpu_worker_mirror_writes_the_fast_mode_contigs(tmp_path):
+    """python -m nextpolish_b200.nextpolish2 -g -l -r --fast -o: `>name len` records of both contigs (nextpolish2.py:196-200),
+    resume of a cut output, -u."""
+    from nextpolish_b200 import nextpolish2 as NP2
+    from tests.conftest import read_fasta
+    gold = json.load(open(os.path.join(GOLDEN, "lgs_golden.json")))["fast_mode"]
+    fa, bam = os.path.join(GOLDEN, "lgs_td.fa"), os.path.join(GOLDEN, "lgs_td.bam")
+    lst = tmp_path / "lgs.list"
+    lst.write_text(bam + "\n")
+    out = str(tmp_path / "lgs.part000.fasta")
+    assert NP2.main(["-g", fa, "-l", str(lst), "-r", "ont", "--fast", "-o", out]) == 0
+    got = read_fasta(out)
+    for ctg in ("tig0000001", "tig0000002"):
+        want = gold["%s/w5000000_o1000000/rt1" % ctg]
+        assert {"len": len(got[ctg]), "md5": hashlib.md5(got[ctg]).hexdigest()} == want
+    headers = [l.split() for l in open(out) if l.startswith(">")]
+    assert all(int(h[1]) == len(got[h[0][1:]]) for h in headers)
+    full = open(out).read()
+    cut = full[:len(full) - 2000]                                    # the last record loses its tail: redone on resume
+    open(out, "w").write(cut)
+    assert NP2.main(["-g", fa, "-l", str(lst), "-r", "ont", "--fast", "-o", out]) == 0
+    assert open(out).read() == full
