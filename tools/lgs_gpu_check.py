@@ -70,11 +70,11 @@ def main():
                               "oracle_cpu_ms_1core": round(cpu_ms, 1), "alignment_columns": int(case["aln_len"].sum()), "window": kw["length"],
                               "stats": eng.stats(), "kernels_ms": dict(sorted(agg.items(), key=lambda kv: -kv[1]))}), flush=True)
     os.environ["NEXTPOLISH_B200_LGS_TIMING"] = "0"
-    # the GPU tests of the CLI's worker grammar and of np_multi_run_names, called without pytest (tests/test_zz_cli_worker.py)
+    # the GPU tests of the CLI's worker grammar and of np_multi_run_names, called without pytest (tests/test_zzz_cli_worker.py)
     import pathlib
     import tempfile
     from nextpolish_b200 import engine as E
-    from tests import test_zz_cli_worker as TW
+    from tests import test_zzz_cli_worker as TW
     from tests.synth_cases import CASES as SC
     tmp = pathlib.Path(tempfile.mkdtemp(prefix="lgs_check"))
 
