@@ -175,3 +175,89 @@ def test_worker_mirror_command_line_without_gpu_work(NP2, tmp_path, capsys):
     out.write_text(">tig0000001 4\nACGT\n>tig0000002 8\nACGTACGT\n>tig0000002 3\nAC")
     assert NP2.main(["-g", FA, "-l", str(lst), "-r", "hifi", "--fast", "-b", str(blc), "-i", "0", "-o", str(out), "-w", "5M"]) == 0
     assert out.read_text() == ">tig0000001 4\nACGT\n>tig0000002 8\nACGTACGT\n"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "samtools")), reason="needs oracle/_ref/samtools")
+def test_loader_refuses_what_is_not_built(NP2, tmp_path):
+    """(-12) a CIGAR operation the reference's bam2aln rejects ("bamaln error", ctg_cns.c:3527-3530); (-10) a split-read gap
+    on a supplementary record of a contig longer than 100 kb, which would switch the reference's large-indel path on."""
+    import subprocess
+    from tests.conftest import REF_SAMTOOLS
+    sam = subprocess.run([REF_SAMTOOLS, "view", "-h", BAM], stdout=subprocess.PIPE, check=True).stdout.decode().split("\n")
+
+    def write_bam(lines, path):
+        p = subprocess.run([REF_SAMTOOLS, "view", "-b", "-o", path, "-"], input="\n".join(lines).encode(), check=True)
+        subprocess.check_call([REF_SAMTOOLS, "index", path])
+
+    # -12: the first primary record's leading M run becomes '=' (valid BAM, but not an operation bam2aln handles)
+    lines, done = [], False
+    for l in sam:
+        f = l.split("\t")
+        if not done and not l.startswith("@") and len(f) > 5 and not int(f[1]) & 0x904 and f[5][0].isdigit():
+            import re
+            f[5] = re.sub(r"^(\d+S)?(\d+)M", lambda m: (m.group(1) or "") + m.group(2) + "=", f[5], count=1)
+            l, done = "\t".join(f), True
+        lines.append(l)
+    bam12 = str(tmp_path / "eq.bam")
+    write_bam(lines, bam12)
+    with pytest.raises(NP2.NativeError, match="-12"):
+        NP2.ContigWindows(FA, bam12, "tig0000001", 1)
+    # -10: the same alignments on a contig declared (and padded to) 150 kb: short contigs take split reads in their stride,
+    # long ones hand them to the large-indel path
+    has_split = any("\tSA:Z:" in l and not l.startswith("@") and int(l.split("\t")[1]) & 0x800 for l in sam)
+    assert has_split
+    fa150 = str(tmp_path / "long.fa")
+    from tests.golden.make_golden_lgs import read_fa
+    d = read_fa(FA)
+    with open(fa150, "w") as f:
+        for n, s in d.items():
+            f.write(">%s\n%s\n" % (n, s + "ACGT" * ((150000 - len(s)) // 4 + 1)))
+    lines = [l.replace("LN:%d" % len(d["tig0000001"]), "LN:%d" % (len(d["tig0000001"]) + 4 * ((150000 - len(d["tig0000001"])) // 4 + 1)))
+             .replace("LN:%d" % len(d["tig0000002"]), "LN:%d" % (len(d["tig0000002"]) + 4 * ((150000 - len(d["tig0000002"])) // 4 + 1))) if l.startswith("@SQ") else l for l in sam]
+    # a split read on tig0000001: primary 5000M5000S at 1001, supplementary 5000S5000M at 6201 (a 200-base gap on the contig),
+    # each naming the other in SA — check_indel (ctg_cns.c:2463) gives it a gap score, and the record is supplementary
+    seq = d["tig0000001"].upper().replace("N", "A").replace("R", "A")
+    rd = seq[1000:6000] + seq[6200:11200]
+    lines = [l for l in lines if l]
+    lines.append("\t".join(["split1", "0", "tig0000001", "1001", "60", "5000M5000S", "*", "0", "0", rd, "*", "SA:Z:tig0000001,6201,+,5000S5000M,60,0;"]))
+    lines.append("\t".join(["split1", "2048", "tig0000001", "6201", "60", "5000S5000M", "*", "0", "0", rd, "*", "SA:Z:tig0000001,1001,+,5000M5000S,60,0;"]))
+    unsorted = str(tmp_path / "long.unsorted.bam")
+    subprocess.run([REF_SAMTOOLS, "view", "-b", "-o", unsorted, "-"], input="\n".join(lines).encode(), check=True)
+    bam10 = str(tmp_path / "long.bam")
+    subprocess.check_call([REF_SAMTOOLS, "sort", "-o", bam10, unsorted], stderr=subprocess.DEVNULL)
+    subprocess.check_call([REF_SAMTOOLS, "index", bam10])
+    outcomes = []
+    for ctg in d:
+        try:
+            NP2.ContigWindows(fa150, bam10, ctg, 1).close()
+            outcomes.append("ok")
+        except NP2.NativeError as ex:
+            assert "-10" in str(ex)
+            outcomes.append("refused")
+    assert outcomes == ["refused", "ok"]
+    # the same split read on the 51 kb contig is taken in its stride (no large-indel path below 100 kb, ctg_cns.c:3450)
+    short_lines = [l for l in sam if l] + lines[-2:]
+    short_unsorted, short_bam = str(tmp_path / "short.unsorted.bam"), str(tmp_path / "short.bam")
+    subprocess.run([REF_SAMTOOLS, "view", "-b", "-o", short_unsorted, "-"], input="\n".join(short_lines).encode(), check=True)
+    subprocess.check_call([REF_SAMTOOLS, "sort", "-o", short_bam, short_unsorted], stderr=subprocess.DEVNULL)
+    subprocess.check_call([REF_SAMTOOLS, "index", short_bam])
+    cw = NP2.ContigWindows(FA, short_bam, "tig0000001", 1)
+    base_cw = NP2.ContigWindows(FA, BAM, "tig0000001", 1)
+    assert cw.info()[0][2] == base_cw.info()[0][2] + 1           # one more alignment: the primary half (the supplementary one is filtered)
+    if L.ref_shim() is not None:
+        from tests.golden.make_golden_lgs import ref_contig_windows as rcw
+        want = [(a, b, n, h) for a, b, n, h, _, _ in rcw(L.ref_shim(), short_bam, "tig0000001", d["tig0000001"], 1, 5000000, 1000000)]
+        assert cw.info() == want
+    cw.close(), base_cw.close()
+    # whether a contig is refused depends on its reads (a supplementary record whose SA partner passes check_indel); the
+    # reference's own loop (shim) must agree contig by contig when it is available
+    if L.ref_shim() is not None:
+        from tests.golden.make_golden_lgs import ref_contig_windows
+        d150 = read_fa(fa150)
+        for ctg, got in zip(d, outcomes):
+            try:
+                ref_contig_windows(L.ref_shim(), bam10, ctg, d150[ctg], 1, 5000000, 1000000)
+                want = "ok"
+            except AssertionError as ex:
+                want = "refused" if "-10" in str(ex) else "error"
+            assert got == want, ctg
