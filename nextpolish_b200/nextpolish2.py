@@ -4,6 +4,10 @@ nextpolish_b200/lib/nextpolish2.so, which has no CPU path.
 
     eng = LgsEngine(device=0)
     res = eng.first_pass(windows, read_type=1, min_cov=4)      # [(pos uint32[], base bytes, qv uint8[])] per window
+    cw  = ContigWindows(fasta, bam, "ctg1", read_type=1)       # windows + alignment strings of a contig from an indexed BAM (host)
+    res = eng.first_pass_contig(cw)
+    seq = eng.polish_contig_fast(fasta, bam, "ctg1", 1)        # files -> windows -> first pass -> linked contig (the reference's fast mode)
+    python -m nextpolish_b200.nextpolish2 -g genome.fa -l lgs.sort.bam.list -r ont --fast -o out.fa      # lib/nextpolish2.py's command line
 
 A window is a dict  len, aln_t_s uint32[n], aln_len uint32[n], str_off uint64[n], t_str bytes, q_str bytes  — the gapped
 alignment strings of the reads against the window, window against itself first (ctg_cns.c:3456-3468)."""
