@@ -9,8 +9,8 @@
  * ctg_cns_core, free_consensus_trimed_data, ctg_cns_destroy, refs_destroy — ctg_cns.c:2269,3355,3399,2151,3384,2195) are
  * NOT exported yet: ctg_cns_core also needs the low-quality-region / POA stage behind the first pass (ctg_cns.c:822-1474,
  * dag.c, align.c), the large-indel path and the window linking (:3053-3330).  The stage in front — BAM records to alignment
- * strings — exists on the host for one indexed BAM (np2_windows_from_bam below; the reference merges several BAMs,
- * bsort.c).  INTEGRATION.md shows where these calls sit inside ctg_cns_core.
+ * strings — exists on the host (np2_windows_from_bam / np2_windows_from_bams below; several BAMs are merged in the order
+ * of the reference's bam_merge_iter, bsort.c).  INTEGRATION.md shows where these calls sit inside ctg_cns_core.
  *
  * Library: nextpolish_b200/lib/nextpolish2.so (sm_100a only, no CPU path: np2_engine_create fails without a GPU). */
 #ifndef NEXTPOLISH2_B200_H
@@ -74,6 +74,10 @@ int32_t np2_engine_kernel_times(np2_engine* e, const char** names, float* ms, in
  * np2_windows_free) and can go straight into np2_first_pass. */
 typedef struct np2_windows np2_windows;
 np2_windows* np2_windows_from_bam(const char* fasta, const char* bam, const char* contig, int32_t read_type, int32_t window, int32_t overlap);
+/* the same for a list of sorted, indexed BAMs (nextpolish2.py -l: the driver lists the part BAMs of the mapping step): records
+ * in the order of the reference's merge iterator (bsort.c:174-199: position, forward strand first, then list order) */
+np2_windows* np2_windows_from_bams(const char* fasta, const char* const* bams, int32_t n_bams, const char* contig, int32_t read_type,
+                                   int32_t window, int32_t overlap);
 int32_t      np2_windows_count(const np2_windows* w);
 /* window i: [start, end) on the contig, its number of alignments as the reference counts them (the window itself and the
  * rare alignments left empty by the anchoring included; the empty ones are not in the batch) and an FNV-1a hash over

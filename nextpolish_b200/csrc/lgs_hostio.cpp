@@ -241,8 +241,20 @@ void np2_windows_batch(const np2_windows* w, np2_window_batch* out) {
 }
 
 np2_windows* np2_windows_from_bam(const char* fasta, const char* bam, const char* contig, int32_t read_type, int32_t window, int32_t overlap) {
+    const char* one[1] = {bam};
+    return np2_windows_from_bams(fasta, bam ? one : nullptr, 1, contig, read_type, window, overlap);
+}
+
+// Several sorted, indexed BAMs (the driver maps the long reads in parts and lists the part BAMs, source/nextPolish:209-211,
+// nextpolish2.py -l): records are taken in the order of the reference's merge iterator (bam_merge_iter, bsort.c:174-199,
+// 1428-1461): by position, forward strand before reverse, then by the file's place in the list; records of one file keep
+// their order.  One BAM is streamed; with several, the contig's records are held in memory for the merge.
+np2_windows* np2_windows_from_bams(const char* fasta, const char* const* bams, int32_t n_bams, const char* contig, int32_t read_type,
+                                   int32_t window, int32_t overlap) {
     std::string err;
-    if (!fasta || !bam || !contig || window <= overlap || overlap < 0) { np2x::set_error("np2_windows_from_bam: bad arguments"); return nullptr; }
+    if (!fasta || !bams || n_bams < 1 || !contig || window <= overlap || overlap < 0) { np2x::set_error("np2_windows_from_bam: bad arguments"); return nullptr; }
+    for (int32_t i = 0; i < n_bams; i++) if (!bams[i]) { np2x::set_error("np2_windows_from_bam: bad arguments"); return nullptr; }
+    const char* bam = bams[0];
     std::vector<np::FastaRecord> fr;
     if (!np::fasta_load(fasta, {contig}, fr, err) || fr.size() != 1) { np2x::set_error("np2_windows_from_bam: " + (err.empty() ? std::string("contig not in the FASTA") : err)); return nullptr; }
     const std::string rf = two_bit_roundtrip(fr[0].seq);
@@ -269,12 +281,11 @@ np2_windows* np2_windows_from_bam(const char* fasta, const char* bam, const char
     }
     int32_t rc = 0;
     uint64_t voff = 0; bool has = false;
-    if (tid >= 0 && L > 0) {
+    if (n_bams == 1 && tid >= 0 && L > 0) {
         if (!bf.bai_first_offset(tid, &voff, &has, err)) { np2x::set_error("np2_windows_from_bam: " + err + " (the BAM needs its .bai index)"); delete W; return nullptr; }
     }
-    if (has) {
-        auto visit = [&](const np::BamRec& r) -> bool {
-            if (r.tid != tid) return r.tid < tid && r.tid >= 0;                      // records before the contig in the first chunk's block: skip; after: stop
+    {
+        auto process = [&](const np::BamRec& r) -> bool {
             if (r.n_cigar == 0) return true;
             const int64_t endpos = bam_endpos(r);
             const int32_t l_qseq = cal_l_qseq(r);
@@ -328,7 +339,57 @@ np2_windows* np2_windows_from_bam(const char* fasta, const char* bam, const char
             }
             return true;
         };
-        if (!bf.scan(voff, 4, visit, err) && rc == 0) { np2x::set_error("np2_windows_from_bam: " + err); delete W; return nullptr; }
+        if (n_bams == 1) {
+            auto visit = [&](const np::BamRec& r) -> bool {
+                if (r.tid != tid) return r.tid < tid && r.tid >= 0;                  // records before the contig in the first chunk's block: skip; after: stop
+                return process(r);
+            };
+            if (has && !bf.scan(voff, 4, visit, err) && rc == 0) { np2x::set_error("np2_windows_from_bam: " + err); delete W; return nullptr; }
+        } else {
+            struct Owned { int32_t pos; uint16_t flag; uint32_t n_cigar; int32_t l_qseq, l_aux; size_t off; };
+            std::vector<std::vector<Owned>> recs((size_t)n_bams);
+            std::vector<std::vector<uint8_t>> bytes((size_t)n_bams);
+            for (int32_t k = 0; k < n_bams; k++) {
+                np::BamFile f;
+                if (!f.open(bams[k], err)) { np2x::set_error("np2_windows_from_bam: " + err); delete W; return nullptr; }
+                int t = -1;
+                for (size_t i = 0; i < f.header().names.size(); i++) if (f.header().names[i] == contig) t = (int)i;
+                uint64_t vo = 0; bool hs = false;
+                if (t < 0 || L == 0) continue;
+                if (!f.bai_first_offset(t, &vo, &hs, err)) { np2x::set_error("np2_windows_from_bam: " + err + " (every BAM needs its .bai index)"); delete W; return nullptr; }
+                if (!hs) continue;
+                auto collect = [&](const np::BamRec& r) -> bool {
+                    if (r.tid != t) return r.tid < t && r.tid >= 0;
+                    Owned o{r.pos, r.flag, r.n_cigar, r.l_qseq, r.l_aux, bytes[(size_t)k].size()};
+                    const size_t nc = 4 * (size_t)r.n_cigar, ns = ((size_t)r.l_qseq + 1) / 2;
+                    bytes[(size_t)k].insert(bytes[(size_t)k].end(), (const uint8_t*)r.cigar, (const uint8_t*)r.cigar + nc);
+                    bytes[(size_t)k].insert(bytes[(size_t)k].end(), r.seq, r.seq + ns);
+                    bytes[(size_t)k].insert(bytes[(size_t)k].end(), r.aux, r.aux + r.l_aux);
+                    recs[(size_t)k].push_back(o);
+                    return true;
+                };
+                if (!f.scan(vo, 4, collect, err)) { np2x::set_error("np2_windows_from_bam: " + err); delete W; return nullptr; }
+            }
+            std::vector<size_t> head((size_t)n_bams, 0);
+            for (;;) {
+                int best = -1;
+                for (int32_t k = 0; k < n_bams; k++) {
+                    if (head[(size_t)k] >= recs[(size_t)k].size()) continue;
+                    if (best < 0) { best = k; continue; }
+                    const Owned& a = recs[(size_t)k][head[(size_t)k]]; const Owned& b = recs[(size_t)best][head[(size_t)best]];
+                    const int ra = a.flag & 16 ? 1 : 0, rb = b.flag & 16 ? 1 : 0;
+                    if (a.pos < b.pos || (a.pos == b.pos && ra < rb)) best = k;      // equal position and strand: the earlier file wins
+                }
+                if (best < 0) break;
+                const Owned& o = recs[(size_t)best][head[(size_t)best]++];
+                const uint8_t* p = bytes[(size_t)best].data() + o.off;
+                np::BamRec r;
+                r.tid = tid; r.pos = o.pos; r.mapq = 0; r.flag = o.flag; r.n_cigar = o.n_cigar; r.l_qseq = o.l_qseq; r.isize = 0;
+                r.cigar = (const uint32_t*)p; r.seq = p + 4 * (size_t)o.n_cigar; r.qual = nullptr;
+                r.aux = r.seq + ((size_t)o.l_qseq + 1) / 2; r.l_aux = o.l_aux;
+                if (!process(r)) break;
+            }
+        }
     }
     if (rc == -10) { np2x::set_error("np2_windows_from_bam: a split-read gap on a contig longer than 100 kb needs the reference's large-indel path, which is not built (code -10)"); delete W; return nullptr; }
     if (rc == -12) { np2x::set_error("np2_windows_from_bam: CIGAR operation outside M/I/D/N/S/H (the reference stops with \"bamaln error\") (code -12)"); delete W; return nullptr; }

@@ -19,7 +19,7 @@ import numpy as np
 LIB2_PATH = os.path.join(os.path.dirname(os.path.realpath(__file__)), "lib", "nextpolish2.so")
 EXPORTS2 = ["np2_engine_create", "np2_engine_destroy", "np2_last_error", "np2_first_pass", "np2_engine_launch_count",
             "np2_engine_last_stats", "np2_engine_kernel_times",
-            "np2_windows_from_bam", "np2_windows_count", "np2_windows_info", "np2_windows_batch", "np2_windows_free",
+            "np2_windows_from_bam", "np2_windows_from_bams", "np2_windows_count", "np2_windows_info", "np2_windows_batch", "np2_windows_free",
             "np2_windows_starts", "np2_link_windows_fast"]                     # every symbol include/nextpolish2_b200.h declares
 ERRORS = {-1: "output capacity too small", -2: "a window's last position has no node",
           -3: "an alignment is empty, starts on a gap column or leaves its window",
@@ -59,6 +59,8 @@ def lib2():
         L.np2_engine_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.np2_windows_from_bam.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]
         L.np2_windows_from_bam.restype = C.c_void_p
+        L.np2_windows_from_bams.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]
+        L.np2_windows_from_bams.restype = C.c_void_p
         L.np2_windows_count.argtypes = [C.c_void_p]
         L.np2_windows_info.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.np2_windows_info.restype = None
@@ -102,7 +104,10 @@ class ContigWindows:
     draft FASTA and an indexed long-read BAM (the record loop of ctg_cns_core, ctg_cns.c:3444-3566)."""
 
     def __init__(self, fasta, bam, contig, read_type, window=5000000, overlap=1000000):
-        self.h = lib2().np2_windows_from_bam(fasta.encode(), bam.encode(), contig.encode(), read_type, window, overlap)
+        """bam: one path, or a list of paths (merged in the reference's order, bsort.c:174-199)"""
+        bams = [bam] if isinstance(bam, str) else list(bam)
+        arr = (C.c_char_p * len(bams))(*[b.encode() for b in bams])
+        self.h = lib2().np2_windows_from_bams(fasta.encode(), arr, len(bams), contig.encode(), read_type, window, overlap)
         if not self.h:
             raise NativeError(lib2().np2_last_error().decode(errors="replace"))
         self.read_type = read_type
@@ -276,7 +281,7 @@ def main(argv=None):
     import sys
     ap = argparse.ArgumentParser(description="Long-read polish on the GPU, the reference's fast mode (mirror of lib/nextpolish2.py).")
     ap.add_argument("-g", "--genome", required=True)
-    ap.add_argument("-l", "--bam_list", required=True, help="file with the sorted, indexed long-read BAM (one line; the reference merges several)")
+    ap.add_argument("-l", "--bam_list", required=True, help="file listing the sorted, indexed long-read BAMs, one per line")
     ap.add_argument("-r", "--read_type", required=True, type=str.lower, choices=["clr", "hifi", "ont"])
     ap.add_argument("-b", "--block")
     ap.add_argument("-i", "--block_index", default="all")
@@ -298,8 +303,8 @@ def main(argv=None):
     window = int(float(args.window[:-1]) * unit) if unit else int(args.window)
     window = max(window, 5000000)                      # set_window_process never goes below 5 M (nextpolish2.py:75-76)
     bams = [l.strip() for l in open(args.bam_list) if l.strip()]
-    if len(bams) != 1:
-        sys.stderr.write("exactly one BAM in the list is supported (merging several, bsort.c, is not built)\n")
+    if not bams:
+        sys.stderr.write("the BAM list is empty\n")
         return 1
     rt = {"ont": 1, "clr": 2, "hifi": 3}[args.read_type]
     out, corrected = sys.stdout, set()
@@ -317,7 +322,7 @@ def main(argv=None):
     if names:
         eng = LgsEngine(int(os.environ.get("NEXTPOLISH_B200_DEVICE", "0")))
         for name in names:
-            seq = eng.polish_contig_fast(args.genome, bams[0], name, rt, window, 1000000).decode()
+            seq = eng.polish_contig_fast(args.genome, bams, name, rt, window, 1000000).decode()
             if args.uppercase:
                 seq = seq.upper()
             if len(seq) > 10:                          # nextpolish2.py:199-203

@@ -75,12 +75,21 @@ static int contig_windows_impl(const char *bam_path, const char *ctg, const char
 	if (READS_TYPE != READS_ONT){ GAP_MIN_LEN = 5; GAP_MIN_RATIO1 = 0.3; }
 	else { GAP_MIN_LEN = 3; GAP_MIN_RATIO1 = 0.01; }
 	MAX_CLIP_RATIO = READS_TYPE == READS_HIFI ? 0.1 : 0.7;
-	samFile *fp = sam_open(bam_path, "r");
-	if (!fp) return -11;
-	bam_hdr_t *hdr = sam_hdr_read(fp);
-	hts_idx_t *idx = sam_index_load(fp, bam_path);
-	if (!hdr || !idx) return -11;
-	bam1_t *brecord = bam_init1();
+	/* a path ending in ".list" is a BAM list and goes through the reference's own merge iterator (bam_merge_iter, bsort.c:1202,
+	 * 1428: what ctg_cns_core uses, :3475); anything else is one BAM read with htslib's region iterator */
+	const size_t plen = strlen(bam_path);
+	const int use_merge = plen > 5 && strcmp(bam_path + plen - 5, ".list") == 0;
+	samFile *fp = NULL; bam_hdr_t *hdr = NULL; hts_idx_t *idx = NULL;
+	bam1_t *brecord = NULL, *own = NULL;
+	bam_merge_iter bam_iter;
+	if (!use_merge){
+		fp = sam_open(bam_path, "r");
+		if (!fp) return -11;
+		hdr = sam_hdr_read(fp);
+		idx = sam_index_load(fp, bam_path);
+		if (!hdr || !idx) return -11;
+		brecord = own = bam_init1();
+	}
 	alignment aln_, aln;
 	memset(&aln, 0, sizeof(aln));
 	aln.max_aln_len = 100000;
@@ -110,9 +119,12 @@ static int contig_windows_impl(const char *bam_path, const char *ctg, const char
 		rege = s == 0 ? (e > INS_RADOM_LEN ? e : INS_RADOM_LEN) : e;
 		char reg[1024];
 		sprintf(reg, "%s:%d-%d", ctg, s, rege);
-		hts_itr_t *it = sam_itr_querys(idx, hdr, reg);
+		hts_itr_t *it = NULL;
+		if (use_merge) bam_merge_iter_init(0, NULL, bam_path, reg, &bam_iter);
+		else it = sam_itr_querys(idx, hdr, reg);
 		p = 0;
-		while (it && sam_itr_next(fp, it, brecord) >= 0){
+		while (use_merge ? bam_merge_iter_core(&bam_iter) > 0 : (it && sam_itr_next(fp, it, brecord) >= 0)){
+			if (use_merge) brecord = bam_iter.heap->entry.bam_record;
 			p = brecord->core.pos;
 			if (p >= e) rege = 0;
 			uint32_t *cigar = bam_get_cigar(brecord);
@@ -164,6 +176,7 @@ static int contig_windows_impl(const char *bam_path, const char *ctg, const char
 			}
 		}
 		if (it) hts_itr_destroy(it);
+		if (use_merge) bam_merge_iter_destroy(&bam_iter);
 		if (rc) { for (uint32_t i = 0; i < seq_count; i++) free(tags_list[i].align_tags); free(tags_list); free(msa); break; }
 		win_s[nw] = s; win_e[nw] = e; win_nalns[nw] = seq_count; win_hash[nw] = h; win_out_off[nw] = total;
 		consensus_data *c = get_cns_from_align_tags(tags_list, msa, seq_count, e - s, min_cov, 0, 1, NULL);
@@ -184,7 +197,7 @@ static int contig_windows_impl(const char *bam_path, const char *ctg, const char
 	if (!rc) win_out_off[nw] = total;
 	free(aln.t_aln_str); free(aln.q_aln_str);
 	if (sas.i_m) free(sas.sa);
-	bam_destroy1(brecord); hts_idx_destroy(idx); bam_hdr_destroy(hdr); sam_close(fp);
+	if (!use_merge){ bam_destroy1(own); hts_idx_destroy(idx); bam_hdr_destroy(hdr); sam_close(fp); }
 	return rc ? rc : nw;
 }
 

@@ -157,9 +157,9 @@ def test_worker_mirror_command_line_without_gpu_work(NP2, tmp_path, capsys):
     lst.write_text(BAM + "\n")
     assert NP2.main(["-g", FA, "-l", str(lst), "-r", "ont"]) == 1
     assert "fast mode" in capsys.readouterr().err
-    two = tmp_path / "two.list"
-    two.write_text(BAM + "\n" + BAM + "\n")
-    assert NP2.main(["-g", FA, "-l", str(two), "-r", "ont", "--fast"]) == 1
+    empty = tmp_path / "empty.list"
+    empty.write_text("\n")
+    assert NP2.main(["-g", FA, "-l", str(empty), "-r", "ont", "--fast"]) == 1
     # resume scan: tig0000001 finished, tig0000002 split into two pieces of which the second is partial -> redone
     out = tmp_path / "part.fasta"
     out.write_text(">tig0000001 4\nACGT\n>tig0000002_s0 8\nACGTACGT\n>tig0000002_s1 9\nAC")
@@ -261,3 +261,39 @@ def test_loader_refuses_what_is_not_built(NP2, tmp_path):
             except AssertionError as ex:
                 want = "refused" if "-10" in str(ex) else "error"
             assert got == want, ctg
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "samtools")), reason="needs oracle/_ref/samtools")
+def test_several_bams_are_merged_in_the_reference_order(NP2, tmp_path):
+    """The driver maps long reads in parts and lists the part BAMs (nextpolish2.py -l): the loader takes the records in the
+    order of the reference's merge iterator (bsort.c:174-199,1428-1461: position, forward strand first, list order).  The
+    fixture BAM split in two by read name; against the reference's own bam_merge_iter (shim) when it is available."""
+    import subprocess
+    from tests.conftest import REF_SAMTOOLS
+    a, b = str(tmp_path / "part_a.bam"), str(tmp_path / "part_b.bam")
+    subprocess.check_call([REF_SAMTOOLS, "view", "-b", "-s", "3.5", "-o", a, "-U", b, BAM])
+    subprocess.check_call([REF_SAMTOOLS, "index", a])
+    subprocess.check_call([REF_SAMTOOLS, "index", b])
+    lst = tmp_path / "parts.list"
+    lst.write_text(a + "\n" + b + "\n")
+    single = {}
+    for ctg in ("tig0000001", "tig0000002"):
+        for order in ([a, b], [b, a]):
+            cw = NP2.ContigWindows(FA, order, ctg, 1, 20000, 4000)
+            one = NP2.ContigWindows(FA, BAM, ctg, 1, 20000, 4000)
+            assert [x[:3] for x in cw.info()] == [x[:3] for x in one.info()]          # same windows and alignment counts as the unsplit BAM
+            single[(ctg, tuple(order))] = cw.info()
+            cw.close(), one.close()
+    # a list whose second BAM has nothing for the contig is the first BAM alone
+    lonely = NP2.ContigWindows(FA, [a, a], "tig0000001", 1, 20000, 4000)
+    assert lonely.info()[0][2] > NP2.ContigWindows(FA, a, "tig0000001", 1, 20000, 4000).info()[0][2]   # (the same reads twice: more alignments)
+    lonely.close()
+    if L.ref_shim() is not None:
+        from tests.golden.make_golden_lgs import read_fa, ref_contig_windows
+        draft = read_fa(FA)
+        for ctg in draft:
+            for rt, w, o in ((1, 20000, 4000), (3, 5000000, 1000000), (2, 7000, 900)):
+                want = [(x[0], x[1], x[2], x[3]) for x in ref_contig_windows(L.ref_shim(), str(lst), ctg, draft[ctg], rt, w, o)]
+                cw = NP2.ContigWindows(FA, [a, b], ctg, rt, w, o)
+                assert cw.info() == want, (ctg, rt, w, o)
+                cw.close()
