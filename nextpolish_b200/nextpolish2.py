@@ -294,6 +294,7 @@ def main(argv=None):
     ap.add_argument("-id", "--alignment_identity_ratio", type=float, default=0.8)
     ap.add_argument("-as", "--alignment_score_ratio", type=float, default=0.8)
     ap.add_argument("--fast", action="store_true", help="the reference's fast mode (ctg_cns.c:3433,3620): the only one built")
+    ap.add_argument("--plan", action="store_true", help="print the contigs this job would polish and the BAMs it would read, touch no device")
     args, _unknown = ap.parse_known_args(argv)
     if not args.fast:
         sys.stderr.write("only the reference's fast mode is built (pass --fast); its default mode re-polishes low-quality regions "
@@ -319,6 +320,9 @@ def main(argv=None):
     block = args.genome if (args.block_index == "all" or not args.block) else args.block
     names = _read_uncorrected(block, "all" if block == args.genome else args.block_index, corrected)
     rc = 0
+    if args.plan:
+        sys.stdout.write("".join("bam\t%s\n" % b for b in bams) + "".join("polish\t%s\n" % n for n in names))
+        names = []
     if names:
         eng = LgsEngine(int(os.environ.get("NEXTPOLISH_B200_DEVICE", "0")))
         for name in names:

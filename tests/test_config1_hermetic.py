@@ -77,3 +77,32 @@ def test_native_cli_accepts_the_drivers_job_lines(config1_run, tmp_path):
                 assert [l.split("\t")[1] for l in lines[3:]] == ref_block_names(opt["-b"], opt["-i"], done)
                 part.unlink()
     assert seen == 4                                             # 2 contigs x 2 steps
+
+
+@pytest.mark.skipif(not have, reason="needs /root/reference and make -C oracle ref ref2 refcfg")
+def test_long_read_worker_mirror_accepts_the_drivers_job_lines(config1_run, capsys):
+    """The long-read step's job lines (python lib/nextpolish2.py -sp -p N -g G -b blc -i i -l lgs.sort.bam.list -r ont -o part,
+    source/nextPolish:70-84) parse in our mirror of that worker; --fast --plan prints what it would do without a device."""
+    import glob
+    import shlex
+    from nextpolish_b200 import nextpolish2 as NP2
+    from tests.test_part_writer import ref_block_names
+    out, _ = config1_run
+    scripts = sorted(glob.glob(os.path.join(out["dir"], "test_data", "01_rundir", "00.lgs_polish", "0*.polish.ref.sh")))
+    assert len(scripts) == 1
+    seen = []
+    for line in open(scripts[0]):
+        argv = shlex.split(line)
+        if not argv:
+            continue
+        assert argv[1].endswith("lib/nextpolish2.py")
+        args = argv[2:]
+        opt = {a: args[i + 1] for i, a in enumerate(args[:-1]) if a in ("-g", "-b", "-i", "-l", "-r", "-o", "-p")}
+        capsys.readouterr()
+        assert NP2.main(args + ["--fast", "--plan", "-o", "stdout"]) == 0
+        printed = [l.split("\t") for l in capsys.readouterr().out.strip().split("\n") if l]
+        assert [p[1] for p in printed if p[0] == "bam"] == [l.strip() for l in open(opt["-l"]) if l.strip()]
+        assert [p[1] for p in printed if p[0] == "polish"] == ref_block_names(opt["-b"], opt["-i"], set())
+        seen += [p[1] for p in printed if p[0] == "polish"]
+        assert NP2.main(args) == 1                                  # without --fast: refused (the default mode is not built)
+    assert sorted(seen) == ["tig0000001", "tig0000002"]
