@@ -241,7 +241,11 @@ static bool inflate_block(const uint8_t* d, const BlockDesc& b, uint8_t* out, z_
     zs.next_out = out;
     zs.avail_out = (uInt)b.isize;
     int rc = inflate(&zs, Z_FINISH);
-    return rc == Z_STREAM_END && zs.avail_out == 0;
+    if (!(rc == Z_STREAM_END && zs.avail_out == 0)) return false;
+    // the block trailer's CRC32 of the inflated bytes, as htslib checks it (bgzf.c: bgzf_uncompress / inflate_block)
+    const uint8_t* t = p + b.csize - 8;
+    const uint32_t want = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+    return (uint32_t)crc32(crc32(0L, Z_NULL, 0), out, (uInt)b.isize) == want;
 }
 
 struct Stream {

@@ -1,5 +1,6 @@
 """Host-side readers of the loader (csrc/hostio.cpp) against independent parses — CPU only (test build tests/emu)."""
 import ctypes as C
+import os
 import random
 
 import numpy as np
@@ -75,3 +76,24 @@ def test_fasta_load_flat_random(emu, tmp_path, seed):
     q.write_bytes(b">s\nAC\n")
     assert _load(emu, q) == (["s"], [b"AC"])
     assert _load(emu, p) == want
+
+
+def test_host_reader_checks_the_bgzf_crc(E, tmp_path):
+    """A flipped bit in a block's CRC32 trailer (the payload still inflates to the right length) is an error, as in htslib."""
+    import shutil
+    from tests.conftest import GOLDEN
+    src = os.path.join(GOLDEN, "td30.step1.bam")
+    fa = os.path.join(GOLDEN, "td30.step1.fa")
+    bad = str(tmp_path / "crc.bam")
+    raw = bytearray(open(src, "rb").read())
+    # second BGZF block: header 18 bytes (BC subfield holds the block size - 1), trailer = CRC32, ISIZE
+    bsize0 = raw[16] | (raw[17] << 8)
+    o = bsize0 + 1
+    assert raw[o:o + 4] == b"\x1f\x8b\x08\x04"
+    bsize1 = raw[o + 16] | (raw[o + 17] << 8)
+    raw[o + bsize1 + 1 - 8] ^= 0x01
+    open(bad, "wb").write(raw)
+    shutil.copy(src + ".bai", bad + ".bai")
+    with pytest.raises(E.NativeError):
+        E.Shard.load(fa, bad, with_qual=False)
+    E.Shard.load(fa, src, with_qual=False).close()
