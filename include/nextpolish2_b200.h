@@ -48,6 +48,8 @@ typedef struct {
  * inside a window, in forward order: out_pos = window position of the base (sub-column bases repeat the position),
  * out_base = the base, lower case where coverage <= min_cov (the rule of generate_cns_from_best_score_fast, :1492),
  * out_qv (may be NULL) = 100 * links / coverage of the chosen link (:1840); out_off[n_windows + 1] = window offsets.
+ * Device memory: about 60 bytes per alignment column of the batch (the two strings, one 24-byte link record and one 32-byte
+ * entry slot per column) plus 30 bytes per window position: a 5 Mb window at 30x is ~10 GB, so size batches accordingly.
  * Returns the total number of bases or: -1 cap too small, -2 a window whose last position has no node, -3 an alignment
  * that is empty, starts on a gap column or leaves its window, -4 the backtrack ran into a node without links (the
  * reference reads unallocated memory there), -5 a size limit (2^31 columns or alignment columns per batch, a 65535-long
