@@ -324,9 +324,21 @@ def main(argv=None):
         sys.stdout.write("".join("bam\t%s\n" % b for b in bams) + "".join("polish\t%s\n" % n for n in names))
         names = []
     if names:
+        # the windows of the next contig are built on a host thread (np2_windows_from_bams: file reads, inflate, alignment
+        # strings; the ctypes call drops the GIL) while the GPU works on the current one
+        from concurrent.futures import ThreadPoolExecutor
         eng = LgsEngine(int(os.environ.get("NEXTPOLISH_B200_DEVICE", "0")))
-        for name in names:
-            seq = eng.polish_contig_fast(args.genome, bams, name, rt, window, 1000000).decode()
+        pool = ThreadPoolExecutor(1)
+        load = lambda n: ContigWindows(args.genome, bams, n, rt, window, 1000000)
+        pending = pool.submit(load, names[0])
+        for k, name in enumerate(names):
+            cw = pending.result()
+            if k + 1 < len(names):
+                pending = pool.submit(load, names[k + 1])
+            try:
+                seq = link_windows_fast([s for s, _, _, _ in cw.info()], eng.first_pass_contig(cw), 1000000).decode()
+            finally:
+                cw.close()
             if args.uppercase:
                 seq = seq.upper()
             if len(seq) > 10:                          # nextpolish2.py:199-203
@@ -335,6 +347,7 @@ def main(argv=None):
                 sys.stderr.write("Failed to correct sequence: %s\n" % name)
                 rc = 1
                 break
+        pool.shutdown(wait=True)
         eng.close()
     if out is not sys.stdout:
         out.close()
