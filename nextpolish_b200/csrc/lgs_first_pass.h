@@ -526,6 +526,8 @@ struct Stats { int32_t n_seg, reruns, iterations; int64_t n_rec; };
 template <class BE>
 int64_t run_first_pass(BE& be, const Batch& hb, uint32_t* out_pos, uint8_t* out_base, uint8_t* out_qv, int64_t cap, int64_t* out_off, Stats* st) {
     if (hb.n_win < 1) { if (out_off) out_off[0] = 0; return 0; }
+    if (hb.win_aln0[0] != 0) return -3;
+    for (int32_t w = 0; w < hb.n_win; w++) if (hb.win_aln0[w + 1] < hb.win_aln0[w]) return -3;
     const int32_t n_aln = hb.win_aln0[hb.n_win];
     // host-side tables: column / block offsets of the windows, stretch offsets of the alignments
     int64_t ctot = 0, nblk = 0, nst = 0, total_cols = 0;
