@@ -9,6 +9,10 @@
 //   is not A/C/G/T/U becomes 'A' and sets the low bit of the base before it inside the same 16-base word.
 // A contig longer than INS_MIN_CHECK_LEN (100 kb) on which a supplementary / secondary record carries a split-read gap would
 // switch the reference's large-indel path on (:3503-3504,3567-3583): not built — the loader reports it (code -10).
+// The clipping and anchoring steps keep the reference's exact index arithmetic on purpose (its "too short" branch, the order in
+// which start / end / length are adjusted, unsigned comparisons): every quirk changes which reads enter a window, so
+// those two functions follow the reference statement by statement; everything around them (record reading, SA parsing, window
+// bookkeeping, coverage, merge of several BAMs) is this engine's own.
 // Pinned against the reference's own functions run by oracle/ref2_shim.c (np2_ref_contig_windows): window ranges, alignment
 // counts and a hash over every alignment string (tests/test_lgs_from_bam.py).  Host plumbing: no compute of the path here.
 #include <algorithm>
