@@ -154,6 +154,15 @@ class ContigWindows:
             pass
 
 
+def production_case(base, qv):
+    """The letter case of the reference's production first pass (generate_cns_from_best_score, ctg_cns.c:1839-1846): upper case
+    only where coverage > min_cov (already in `base`, the fast variant's rule) AND the link quality qv > LQBASE_MIN_QV = 20."""
+    b = np.frombuffer(base, np.uint8).copy()
+    low = (np.asarray(qv) <= 20) & (b >= 65) & (b <= 90)
+    b[low] |= 32
+    return b.tobytes()
+
+
 def link_windows_fast(starts, results, overlap):
     """np2_link_windows_fast over per-window first-pass results [(pos, base, qv)] -> the linked sequence (bytes)."""
     n = len(results)

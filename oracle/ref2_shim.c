@@ -243,3 +243,38 @@ int64_t np2_ref_contig_fast(const char *bam_path, const char *ctg, const char *r
 	free(ct.consensus); free(ws); free(we); free(wn); free(wh); free(woff); free(pos); free(base);
 	return n;
 }
+
+/* The PRODUCTION variant of the window consensus on alignment strings: get_cns_from_align_tags(..., fast = 0, ...) with no
+ * gap clusters — first pass, low-quality regions, candidate ranking, POA, second round (ctg_cns.c:1859-1873 and everything
+ * it calls).  Output as np2_ref_first_pass plus the per-base qv; list order as the reference leaves it (forward). */
+int np2_ref_window_prod(int read_type, int n_reads, const uint32_t *aln_t_s, const uint32_t *aln_len, const uint64_t *str_off,
+		const char *t_str, const char *q_str, int len, int min_cov, uint32_t *out_pos, char *out_base, uint8_t *out_qv, int cap){
+	READS_TYPE = read_type;
+	if (READS_TYPE != READS_ONT){ GAP_MIN_LEN = 5; GAP_MIN_RATIO1 = 0.3; }
+	else { GAP_MIN_LEN = 3; GAP_MIN_RATIO1 = 0.01; }
+	msa_p *msa = calloc(len + 1, sizeof(msa_p));
+	align_tags_t *tags_list = malloc((n_reads > 0 ? n_reads : 1) * sizeof(align_tags_t));
+	for (int i = 0; i < n_reads; i++){
+		alignment aln;
+		memset(&aln, 0, sizeof(aln));
+		aln.aln_len = aln_len[i];
+		aln.aln_t_s = aln_t_s[i];
+		aln.t_aln_str = (char *) t_str + str_off[i];
+		aln.q_aln_str = (char *) q_str + str_off[i];
+		get_align_tags(&aln, &tags_list[i], msa);
+	}
+	if (len < 1 || msa[len - 1].max_size == 0) return -2;
+	gap_clusters clusters;
+	memset(&clusters, 0, sizeof(clusters));
+	consensus_data *c = get_cns_from_align_tags(tags_list, msa, n_reads, len, min_cov, 0, 0, &clusters);
+	int n = (int) c->len;
+	if (n > cap) n = -1;
+	for (int i = 0; i < n; i++){
+		out_pos[i] = c->cns_bases[i].pos;
+		out_base[i] = c->cns_bases[i].base;
+		out_qv[i] = (uint8_t) c->cns_bases[i].qv;
+	}
+	free(c->cns_bases);
+	free(c);
+	return n;
+}

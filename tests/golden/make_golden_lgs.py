@@ -128,6 +128,33 @@ def ref_contig_fast(S, bam, ctg, seq, rt, w, ovl):
     return n, out.raw[:n]
 
 
+PROD_CLEAN = {
+    "hifi20": dict(L.CASES["hifi20"]),
+    "hifi_exact": dict(seed=31, length=3000, depth=20, read_len=1500, sub=0.0, ins=0.0, dele=0.0, read_type=3),
+    "hifi_deep": dict(seed=32, length=5000, depth=40, read_len=2000, sub=0.001, ins=0.001, dele=0.001, read_type=3),
+    "clr_exact": dict(seed=33, length=2500, depth=25, read_len=900, sub=0.0, ins=0.0, dele=0.0, read_type=2),
+    "ont_exact_shallow": dict(seed=34, length=2000, depth=3, read_len=700, sub=0.0, ins=0.0, dele=0.0, read_type=1),
+    # noisy reads under their own read type's rules: the production stages find nothing they change here either
+    "ont30/ont": dict(L.CASES["ont30"], read_type=1), "ont30/clr": dict(L.CASES["ont30"], read_type=2),
+    "clr30/clr": dict(L.CASES["clr30"], read_type=2), "clr_hp/clr": dict(L.CASES["clr_hp"], read_type=2),
+    "hifi20/ont": dict(L.CASES["hifi20"], read_type=1), "hifi20/clr": dict(L.CASES["hifi20"], read_type=2),
+}
+# ... and windows the missing stages DO change (recorded so that the gap stays visible in the tests)
+PROD_CHANGED = {"clr30/ont": dict(L.CASES["clr30"], read_type=1), "ont30/hifi": dict(L.CASES["ont30"], read_type=3)}
+
+
+def ref_window_prod(S, case):
+    cap = case["len"] * 3 + int(case["aln_len"].sum())
+    pos, base, qv = np.zeros(cap, np.uint32), np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+    f = S.np2_ref_window_prod
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    n = f(case["read_type"], len(case["aln_t_s"]), case["aln_t_s"].ctypes.data, case["aln_len"].ctypes.data, case["str_off"].ctypes.data,
+          case["t_str"], case["q_str"], case["len"], case["min_cov"], pos.ctypes.data, base.ctypes.data, qv.ctypes.data, cap)
+    assert n > 0, n
+    return n, pos[:n].copy(), base[:n].tobytes(), qv[:n].copy()
+
+
 def front_goldens(S, fa_path, bam):
     out = {}
     for ctg, seq in read_fa(fa_path).items():
@@ -223,6 +250,18 @@ def main():
             for rt in (1, 3):
                 n, linked = ref_contig_fast(S, sub, ctg, seq, rt, w, ovl)
                 gold["fast_mode"]["%s/w%d_o%d/rt%d" % (ctg, w, ovl, rt)] = {"len": n, "md5": hashlib.md5(linked).hexdigest()}
+    # (e) the PRODUCTION window consensus (np2_ref_window_prod: get_cns_from_align_tags with fast = 0 — first pass, low-quality
+    # regions, POA, second round) on accurate reads: where it finds nothing to re-polish it must equal the first pass with
+    # the production letter-case rule (qv > 20), which pins that rule and the qv values
+    gold["production_clean"] = {}
+    for name, kw in PROD_CLEAN.items():
+        case = L.synthetic_case(**kw)
+        n, pos, base, qv = ref_window_prod(S, case)
+        gold["production_clean"][name] = {"n": n, "base_md5": hashlib.md5(base).hexdigest()}
+    gold["production_changed"] = {}
+    for name, kw in PROD_CHANGED.items():
+        n, pos, base, qv = ref_window_prod(S, L.synthetic_case(**kw))
+        gold["production_changed"][name] = {"n": n, "base_md5": hashlib.md5(base).hexdigest()}
     json.dump(gold, open(os.path.join(OUT, "lgs_golden.json"), "w"), indent=1, sort_keys=True)
     print("wrote", len(gold["first_pass"]), "first-pass goldens;", gold["whole_path"])
 

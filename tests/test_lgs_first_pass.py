@@ -220,3 +220,26 @@ def test_nextpolish2_library_exports_and_fails_loudly_without_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(NP2.NativeError, match="no CPU path"):
             NP2.LgsEngine(0)
+
+
+def test_production_window_consensus_on_accurate_reads(O2, emu2):
+    """The reference's PRODUCTION window consensus (get_cns_from_align_tags with fast = 0: first pass, low-quality regions, POA,
+    second round; goldens through np2_ref_window_prod) on windows where it finds nothing to re-polish (accurate reads; noisy reads under their own read type's rules): it equals the
+    first pass with the production letter-case rule applied to the link qualities (nextpolish2.production_case) — which
+    pins that rule, and the qv values on the side of the threshold they fall, against the reference.  (With noisy reads the two differ: that stage is not built.)"""
+    from nextpolish_b200 import nextpolish2 as NP2
+    from tests.golden.make_golden_lgs import PROD_CLEAN
+    gold = json.load(open(os.path.join(GOLDEN, "lgs_golden.json")))["production_clean"]
+    for name, kw in PROD_CLEAN.items():
+        case = L.synthetic_case(**kw)
+        for res in (L.oracle_window(O2, case), L.first_pass_batch(emu_call(emu2, 4), [case])[0]):
+            pos, base, qv = res
+            cased = NP2.production_case(base, qv)
+            got = {"n": len(cased), "base_md5": hashlib.md5(cased).hexdigest()}
+            assert got == {k: gold[name][k] for k in got}, name          # (the qv array itself is rewritten by the later stages: compared through the case only)
+    from tests.golden.make_golden_lgs import PROD_CHANGED
+    changed = json.load(open(os.path.join(GOLDEN, "lgs_golden.json")))["production_changed"]
+    for name, kw in PROD_CHANGED.items():                    # windows the stage that is not built does change
+        fp = L.oracle_window(O2, L.synthetic_case(**kw))
+        cased = NP2.production_case(fp[1], fp[2])
+        assert {"n": len(cased), "base_md5": hashlib.md5(cased).hexdigest()} != changed[name], name
